@@ -1,0 +1,419 @@
+// RPN proposal path pieces for B200 (sm_100a): segmented radix-select top-k and the fused
+// anchor-generation + delta2bbox3D decode.
+//
+// Replaces (reference, /root/reference):
+//   scores.topk(nms_pre) / scores.topk(max_num)      mmdet/models/anchor_heads/rpn_head_3d.py:108-112, :147
+//   sigmoid over every anchor                         rpn_head_3d.py:87-90
+//   AnchorGenerator3D.grid_anchors (numpy + H2D)      mmdet/core/anchor/anchor_generator_3d.py:56-71
+//   delta2bbox3D (~25 elementwise launches)           mmdet/core/bbox/transforms.py:105-160
+//
+// Top-k.  Keys are 64-bit: (order-preserving score bits) << 32 | ~logical_index, so keys are unique and
+// "descending key" is exactly "descending score, ties -> lower index" (the build's tie rule; torch's own
+// tie order is unspecified).  The logical index of an RPN score is its position after
+// permute(2,3,1,0).reshape(-1) of the [A,D,H,W] map -- the order the reference's anchors are generated
+// in -- while memory is read in its native, coalesced order.  Six MSB-first histogram passes
+// (11/11/10 bits over the score word, 11/11/10 over the index word) find the k-th largest key exactly;
+// one collect pass appends the k keys >= it; a rank-by-counting pass sorts them.  Every (volume, level)
+// segment shares each launch; nothing syncs the host.
+#include "common.cuh"
+
+namespace roi3d {
+
+constexpr int kMaxSeg = 64;
+constexpr int kBins = 2048;
+constexpr int kItemsPerThread = 16;
+constexpr int kTopkThreads = 256;
+constexpr int kItemsPerCta = kItemsPerThread * kTopkThreads;
+
+struct SegDesc {
+  long long off;
+  unsigned len;
+  int A, D, H, W;  // A == 0: logical index == memory index
+};
+
+struct SegTable {
+  SegDesc s[kMaxSeg];
+};
+
+struct SegState {           // device, per segment
+  unsigned long long prefix;  // key bits decided so far (left-aligned value of the decided digits)
+  int k_rem;                // how many keys still to take inside the current prefix
+  int k_take;               // min(k, len)
+  int cand_count;
+  int pad;
+};
+
+__device__ __forceinline__ unsigned okey(float s) {
+  s = s + 0.0f;
+  unsigned u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float okey_inv(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+
+// torch's fp32 sigmoid: 1 / (1 + exp(-x))   (rpn_head_3d.py:90)
+__device__ __forceinline__ float sigmoid_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__device__ __forceinline__ unsigned logical_index(const SegDesc &d, unsigned m) {
+  if (d.A == 0) return m;
+  // memory m = ((a*D + z)*H + y)*W + x  ->  logical ((y*W + x)*D + z)*A + a
+  const unsigned x = m % d.W;
+  unsigned t = m / d.W;
+  const unsigned y = t % d.H;
+  t /= d.H;
+  const unsigned z = t % d.D;
+  const unsigned a = t / d.D;
+  return ((y * d.W + x) * d.D + z) * d.A + a;
+}
+
+// pass p: digit position and width.  Score word: bits 63..53, 52..42, 41..32; index word: 31..21, 20..10, 9..0
+__device__ __forceinline__ void pass_geometry(int pass, int &shift, int &bits) {
+  const int sh[6] = {53, 42, 32, 21, 10, 0};
+  const int bw[6] = {11, 11, 10, 11, 11, 10};
+  shift = sh[pass], bits = bw[pass];
+}
+
+template <bool SIGMOID>
+__global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__restrict__ scores, const SegTable tab,
+                                                                 const SegState *__restrict__ state, int pass,
+                                                                 unsigned *__restrict__ hist /*[nseg][kBins]*/) {
+  const int seg = blockIdx.y;
+  const SegDesc d = tab.s[seg];
+  const long long base = (long long)blockIdx.x * kItemsPerCta;
+  if (base >= (long long)d.len) return;
+  const SegState st = state[seg];
+  if (st.k_take <= 0) return;
+  __shared__ unsigned h[kBins];
+  for (int i = threadIdx.x; i < kBins; i += kTopkThreads) h[i] = 0;
+  __syncthreads();
+  int shift, bits;
+  pass_geometry(pass, shift, bits);
+  const unsigned dmask = (1u << bits) - 1u;
+  const bool low_word = pass >= 3;
+  const unsigned pre_hi = (unsigned)(st.prefix >> 32);
+  const float *src = scores + d.off;
+#pragma unroll 4
+  for (int it = 0; it < kItemsPerThread; ++it) {
+    const long long m = base + (long long)it * kTopkThreads + threadIdx.x;
+    if (m < (long long)d.len) {
+      float v = __ldg(src + m);
+      if (SIGMOID) v = sigmoid_ref(v);
+      const unsigned kh = okey(v);
+      if (!low_word) {
+        // participates iff the already-decided high digits match
+        const int decided = 32 - (shift - 32) - bits;  // number of decided bits of the score word
+        const bool match = decided == 0 || (kh >> (32 - decided)) == (pre_hi >> (32 - decided));
+        if (match) atomicAdd(&h[(kh >> (shift - 32)) & dmask], 1u);
+      } else if (kh == pre_hi) {
+        const unsigned kl = ~logical_index(d, (unsigned)m);
+        const unsigned pre_lo = (unsigned)st.prefix;
+        const int decided = 32 - shift - bits;
+        const bool match = decided == 0 || (kl >> (32 - decided)) == (pre_lo >> (32 - decided));
+        if (match) atomicAdd(&h[(kl >> shift) & dmask], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  unsigned *g = hist + (long long)seg * kBins;
+  for (int i = threadIdx.x; i < kBins; i += kTopkThreads) {
+    const unsigned c = h[i];
+    if (c) atomicAdd(&g[i], c);
+  }
+}
+
+// One CTA per segment: pick the digit where the descending cumulative count crosses k_rem.
+__global__ void __launch_bounds__(256) topk_scan_kernel(unsigned *__restrict__ hist, SegState *__restrict__ state,
+                                                        int pass) {
+  const int seg = blockIdx.x;
+  SegState st = state[seg];
+  if (st.k_take <= 0) return;
+  unsigned *g = hist + (long long)seg * kBins;
+  __shared__ unsigned part[256];
+  __shared__ int s_digit, s_krem;
+  // thread t owns bins [8t, 8t+8) ; descending order means high bins first
+  unsigned loc[8], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    loc[i] = g[threadIdx.x * 8 + i];
+    sum += loc[i];
+    g[threadIdx.x * 8 + i] = 0;  // leave the histogram clean for the next pass
+  }
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  // suffix sum over threads above me (256 entries; simple serial-in-smem log scan)
+  for (int o = 1; o < 256; o <<= 1) {
+    unsigned v = (threadIdx.x + o < 256) ? part[threadIdx.x + o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const unsigned above = part[threadIdx.x] - sum;  // keys in bins strictly above my 8 bins
+  const unsigned k = (unsigned)st.k_rem;
+  if (above < k && above + sum >= k) {
+    unsigned cum = above;
+    for (int i = 7; i >= 0; --i) {
+      if (cum + loc[i] >= k) {
+        s_digit = threadIdx.x * 8 + i;
+        s_krem = (int)(k - cum);
+        break;
+      }
+      cum += loc[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int shift, bits;
+    pass_geometry(pass, shift, bits);
+    st.prefix |= (unsigned long long)(unsigned)s_digit << shift;
+    st.k_rem = s_krem;
+    state[seg] = st;
+  }
+}
+
+template <bool SIGMOID>
+__global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const float *__restrict__ scores,
+                                                                    const SegTable tab, SegState *__restrict__ state,
+                                                                    int k, unsigned long long *__restrict__ cand) {
+  const int seg = blockIdx.y;
+  const SegDesc d = tab.s[seg];
+  const long long base = (long long)blockIdx.x * kItemsPerCta;
+  if (base >= (long long)d.len) return;
+  const SegState st = state[seg];
+  if (st.k_take <= 0) return;
+  const unsigned thr_hi = (unsigned)(st.prefix >> 32);
+  const float *src = scores + d.off;
+#pragma unroll 4
+  for (int it = 0; it < kItemsPerThread; ++it) {
+    const long long m = base + (long long)it * kTopkThreads + threadIdx.x;
+    if (m < (long long)d.len) {
+      float v = __ldg(src + m);
+      if (SIGMOID) v = sigmoid_ref(v);
+      const unsigned kh = okey(v);
+      if (kh >= thr_hi) {
+        const unsigned long long key = ((unsigned long long)kh << 32) | (unsigned)~logical_index(d, (unsigned)m);
+        if (key >= st.prefix) {
+          const int pos = atomicAdd(&state[seg].cand_count, 1);
+          if (pos < k) cand[(long long)seg * k + pos] = key;
+        }
+      }
+    }
+  }
+}
+
+// rank-by-counting sort of the (unique) candidate keys, descending.  grid (ceil(k/256), nseg).
+__global__ void __launch_bounds__(256) topk_sort_kernel(const unsigned long long *__restrict__ cand,
+                                                        const SegState *__restrict__ state, int k,
+                                                        int64_t *__restrict__ out_idx, float *__restrict__ out_val) {
+  const int seg = blockIdx.y;
+  const int n = state[seg].k_take;
+  if ((int)(blockIdx.x * 256) >= n) return;
+  const unsigned long long *c = cand + (long long)seg * k;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const unsigned long long ki = i < n ? c[i] : 0ULL;
+  __shared__ unsigned long long keys[256];
+  int rank = 0;
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    __syncthreads();
+    keys[threadIdx.x] = (j0 + threadIdx.x) < n ? c[j0 + threadIdx.x] : 0ULL;
+    __syncthreads();
+    const int lim = min(256, n - j0);
+    if (i < n) {
+#pragma unroll 8
+      for (int t = 0; t < lim; ++t) rank += keys[t] > ki;
+    }
+  }
+  if (i < n) {
+    out_idx[(long long)seg * k + rank] = (int64_t)(unsigned)~(unsigned)ki;
+    out_val[(long long)seg * k + rank] = okey_inv((unsigned)(ki >> 32));
+  }
+}
+
+__global__ void topk_init_kernel(SegState *state, const SegTable tab, int nseg, int k) {
+  const int s = threadIdx.x;
+  if (s >= nseg) return;
+  SegState st;
+  st.prefix = 0ULL;
+  st.k_take = (int)min((unsigned)k, tab.s[s].len);
+  st.k_rem = st.k_take;
+  st.cand_count = 0;
+  st.pad = 0;
+  state[s] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused anchors + delta2bbox3D + score append for selected anchors of one level.
+// ------------------------------------------------------------------------------------------------
+struct DecodeParams {
+  const float *bbox_pred;  // [6A, D, H, W]
+  int A, D, H, W;
+  float stride, dstride;
+  float base[16][6];
+  float means[6], stds[6];
+  float img_h, img_w, img_d;
+  float max_ratio;
+  const int64_t *idx;
+  const float *scores;
+  int n;
+  float *out;
+};
+
+__global__ void __launch_bounds__(256) decode_proposals_kernel(const DecodeParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  float *o = p.out + (long long)i * 7;
+  const long long li = p.idx[i];
+  if (li < 0) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) o[j] = 0.0f;
+    return;
+  }
+  // logical index ((y*W + x)*D + z)*A + a   (anchor_generator_3d.py:59-70, np.meshgrid 'xy' order)
+  long long t = li;
+  const int a = (int)(t % p.A);
+  t /= p.A;
+  const int z = (int)(t % p.D);
+  t /= p.D;
+  const int x = (int)(t % p.W);
+  const int y = (int)(t / p.W);
+  const float sx = (float)x * p.stride, sy = (float)y * p.stride, sz = (float)z * p.dstride;
+  const float ax1 = __fadd_rn(p.base[a][0], sx), ay1 = __fadd_rn(p.base[a][1], sy);
+  const float ax2 = __fadd_rn(p.base[a][2], sx), ay2 = __fadd_rn(p.base[a][3], sy);
+  const float az1 = __fadd_rn(p.base[a][4], sz), az2 = __fadd_rn(p.base[a][5], sz);
+  const long long plane = (long long)p.D * p.H * p.W;
+  const long long sp = ((long long)z * p.H + y) * p.W + x;
+  float d[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float raw = __ldg(p.bbox_pred + (long long)(a * 6 + j) * plane + sp);
+    d[j] = __fadd_rn(__fmul_rn(raw, p.stds[j]), p.means[j]);  // deltas * stds + means (transforms.py:114)
+  }
+  const float mr = p.max_ratio;
+  const float dx = d[0], dy = d[1];
+  const float dw = fminf(fmaxf(d[2], -mr), mr), dh = fminf(fmaxf(d[3], -mr), mr);
+  const float dz = fminf(fmaxf(d[4], -mr), mr), dd = fminf(fmaxf(d[5], -mr), mr);
+  const float px = __fmul_rn(__fadd_rn(ax1, ax2), 0.5f), py = __fmul_rn(__fadd_rn(ay1, ay2), 0.5f);
+  const float pz = __fmul_rn(__fadd_rn(az1, az2), 0.5f);
+  const float pw = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f), ph = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
+  const float pdz = __fadd_rn(__fsub_rn(az2, az1), 1.0f);
+  const float gw = __fmul_rn(pw, expf(dw)), gh = __fmul_rn(ph, expf(dh)), gd = __fmul_rn(pdz, expf(dd));
+  const float gx = __fadd_rn(px, __fmul_rn(pw, dx)), gy = __fadd_rn(py, __fmul_rn(ph, dy));
+  const float gz = __fadd_rn(pz, __fmul_rn(pdz, dz));
+  float x1 = __fadd_rn(__fsub_rn(gx, __fmul_rn(gw, 0.5f)), 0.5f), y1 = __fadd_rn(__fsub_rn(gy, __fmul_rn(gh, 0.5f)), 0.5f);
+  float x2 = __fsub_rn(__fadd_rn(gx, __fmul_rn(gw, 0.5f)), 0.5f), y2 = __fsub_rn(__fadd_rn(gy, __fmul_rn(gh, 0.5f)), 0.5f);
+  float z1 = __fadd_rn(__fsub_rn(gz, __fmul_rn(gd, 0.5f)), 0.5f), z2 = __fsub_rn(__fadd_rn(gz, __fmul_rn(gd, 0.5f)), 0.5f);
+  if (p.img_w > 0.0f) {
+    x1 = fminf(fmaxf(x1, 0.0f), p.img_w - 1.0f), x2 = fminf(fmaxf(x2, 0.0f), p.img_w - 1.0f);
+    y1 = fminf(fmaxf(y1, 0.0f), p.img_h - 1.0f), y2 = fminf(fmaxf(y2, 0.0f), p.img_h - 1.0f);
+    z1 = fminf(fmaxf(z1, 0.0f), p.img_d - 1.0f), z2 = fminf(fmaxf(z2, 0.0f), p.img_d - 1.0f);
+  }
+  o[0] = x1, o[1] = y1, o[2] = x2, o[3] = y2, o[4] = z1, o[5] = z2;
+  o[6] = p.scores ? p.scores[i] : 0.0f;
+}
+
+}  // namespace roi3d
+
+using namespace roi3d;
+
+extern "C" {
+
+static const size_t kStateBytes = 2048;                                     // kMaxSeg * sizeof(SegState) rounded up
+static const size_t kHistBytes = (size_t)kMaxSeg * kBins * sizeof(unsigned);  // 512 KiB
+
+size_t roi3d_topk_workspace_bytes(int nseg, int k) {
+  if (nseg <= 0 || k <= 0) return 256;
+  const size_t ns = (size_t)(nseg < kMaxSeg ? nseg : kMaxSeg);
+  return kStateBytes + kHistBytes + ns * (size_t)k * sizeof(unsigned long long);
+}
+
+int roi3d_topk_segmented(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
+                         const int32_t *seg_adhw, int nseg, int k, int apply_sigmoid, int64_t *out_idx_dev,
+                         float *out_val_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
+  ROI3D_CHECK_ARG(nseg >= 0 && k >= 0, "bad sizes");
+  if (nseg == 0 || k == 0) return ROI3D_OK;
+  ROI3D_CHECK_ARG(scores_dev && seg_off && seg_len && out_idx_dev && out_val_dev && workspace_dev, "NULL pointer");
+  ROI3D_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace_dev) & 255) == 0, "workspace must be 256-byte aligned");
+  if (workspace_bytes < roi3d_topk_workspace_bytes(nseg, k)) {
+    set_error("topk workspace too small: %zu < %zu", workspace_bytes, roi3d_topk_workspace_bytes(nseg, k));
+    return ROI3D_ENOMEM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ROI3D_CUDA(cudaMemsetAsync(out_idx_dev, 0xFF, sizeof(int64_t) * (size_t)nseg * k, st));
+  ROI3D_CUDA(cudaMemsetAsync(out_val_dev, 0, sizeof(float) * (size_t)nseg * k, st));
+  for (int s0 = 0; s0 < nseg; s0 += kMaxSeg) {
+    const int ns = nseg - s0 < kMaxSeg ? nseg - s0 : kMaxSeg;
+    SegTable tab;
+    long long maxlen = 0;
+    for (int s = 0; s < ns; ++s) {
+      ROI3D_CHECK_ARG(seg_len[s0 + s] >= 0 && seg_len[s0 + s] < 4294967295LL, "segment %d too long", s0 + s);
+      tab.s[s].off = seg_off[s0 + s];
+      tab.s[s].len = (unsigned)seg_len[s0 + s];
+      if (seg_adhw) {
+        tab.s[s].A = seg_adhw[(s0 + s) * 4 + 0], tab.s[s].D = seg_adhw[(s0 + s) * 4 + 1];
+        tab.s[s].H = seg_adhw[(s0 + s) * 4 + 2], tab.s[s].W = seg_adhw[(s0 + s) * 4 + 3];
+        ROI3D_CHECK_ARG(tab.s[s].A == 0 || (long long)tab.s[s].A * tab.s[s].D * tab.s[s].H * tab.s[s].W == seg_len[s0 + s],
+                        "segment %d: A*D*H*W != len", s0 + s);
+      } else {
+        tab.s[s].A = tab.s[s].D = tab.s[s].H = tab.s[s].W = 0;
+      }
+      if (seg_len[s0 + s] > maxlen) maxlen = seg_len[s0 + s];
+    }
+    static_assert(sizeof(SegState) * kMaxSeg <= 2048, "state block");
+    char *b = static_cast<char *>(workspace_dev);
+    SegState *state = reinterpret_cast<SegState *>(b);
+    unsigned *hist = reinterpret_cast<unsigned *>(b + kStateBytes);
+    unsigned long long *cand = reinterpret_cast<unsigned long long *>(b + kStateBytes + kHistBytes);
+    topk_init_kernel<<<1, kMaxSeg, 0, st>>>(state, tab, ns, k);
+    ROI3D_LAUNCH_CHECK();
+    if (maxlen == 0) continue;
+    ROI3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)ns * kBins * sizeof(unsigned), st));
+    const dim3 grid((unsigned)ceil_div_ll(maxlen, kItemsPerCta), ns);
+    for (int pass = 0; pass < 6; ++pass) {
+      if (apply_sigmoid)
+        topk_hist_kernel<true><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist);
+      else
+        topk_hist_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist);
+      ROI3D_LAUNCH_CHECK();
+      topk_scan_kernel<<<ns, 256, 0, st>>>(hist, state, pass);
+      ROI3D_LAUNCH_CHECK();
+    }
+    if (apply_sigmoid)
+      topk_collect_kernel<true><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand);
+    else
+      topk_collect_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand);
+    ROI3D_LAUNCH_CHECK();
+    topk_sort_kernel<<<dim3(ceil_div(k, 256), ns), 256, 0, st>>>(cand, state, k, out_idx_dev + (size_t)s0 * k,
+                                                                out_val_dev + (size_t)s0 * k);
+    ROI3D_LAUNCH_CHECK();
+  }
+  return ROI3D_OK;
+}
+
+int roi3d_decode_proposals(const float *bbox_pred_dev, int A, int D, int H, int W, float stride, float depth_stride,
+                           const float *base_anchors_host, const int64_t *idx_dev, const float *scores_dev, int n,
+                           const float *means6_host, const float *stds6_host, float img_h, float img_w, float img_d,
+                           float *out_dev, void *stream) {
+  ROI3D_CHECK_ARG(n >= 0, "bad n");
+  if (n == 0) return ROI3D_OK;
+  ROI3D_CHECK_ARG(bbox_pred_dev && base_anchors_host && idx_dev && out_dev, "NULL pointer");
+  ROI3D_CHECK_ARG(A >= 1 && A <= 16, "A=%d out of [1,16]", A);
+  ROI3D_CHECK_ARG(D > 0 && H > 0 && W > 0, "bad dims");
+  DecodeParams p;
+  p.bbox_pred = bbox_pred_dev, p.A = A, p.D = D, p.H = H, p.W = W, p.stride = stride, p.dstride = depth_stride;
+  for (int a = 0; a < A; ++a)
+    for (int j = 0; j < 6; ++j) p.base[a][j] = base_anchors_host[a * 6 + j];
+  for (int j = 0; j < 6; ++j) {
+    p.means[j] = means6_host ? means6_host[j] : 0.0f;
+    p.stds[j] = stds6_host ? stds6_host[j] : 1.0f;
+  }
+  p.img_h = img_h, p.img_w = img_w, p.img_d = img_d;
+  // max_ratio = np.abs(np.log(16/1000)) evaluated in float64 then used as a python float by clamp
+  p.max_ratio = (float)4.135166556742356;
+  p.idx = idx_dev, p.scores = scores_dev, p.n = n, p.out = out_dev;
+  decode_proposals_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+}  // extern "C"

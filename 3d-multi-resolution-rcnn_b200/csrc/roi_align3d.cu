@@ -1,0 +1,892 @@
+// RoIAlign3D forward / backward and the fused multi-level RoI extractor for B200 (sm_100a).
+//
+// Replaces (reference, /root/reference):
+//   ROIAlignForward3D / bilinear_interpolate_3d          mmdet/ops/roi_align/src/roi_align_kernel.cu:214-291, :64-149
+//   ROIAlignBackward3D / bilinear_interpolate_gradient_3d roi_align_kernel.cu:519-636, :383-442
+//   SingleRoIExtractor.forward / map_roi_levels           mmdet/models/roi_extractors/single_level.py:58-104
+//
+// Design.  The reference evaluates every output bin independently: S^3
+// trilinear samples x 8 scattered 4-byte loads (64 loads / 64 atomics per output element at S=2).
+// Trilinear sampling, bin averaging, the out-of-range rule and the border clamp are all separable
+// per axis, so here each RoI axis is reduced once to a small dense weight table
+//     A_axis[p][v] = sum over the S samples i of bin p of ( h(p,i)*[v==low] + l(p,i)*[v==high] ),
+// and the output is the tensor contraction  out[pd,ph,pw] = 1/count * sum_z A_d[pd][z] sum_y A_h[ph][y]
+// sum_x A_w[pw][x] F[z,y,x].  One warp owns (RoI, 32*CV channels, pd, a group of ROWS ph-rows): lanes
+// run over CHANNELS of the channels-last feature map, so every feature access is one coalesced
+// 128*CV-byte line, all table lookups are warp-uniform shared-memory broadcasts, and there is no
+// divergence.  Each feature row is contracted along x once (PW partial sums in registers), then
+// folded into the ROWS x PW register accumulators with the combined z*y weight.  Results are
+// transposed through a padded per-warp shared-memory tile so the [K,C,PD,PH,PW] output is written
+// in contiguous runs with streaming stores.  The sample coordinates use exactly the rounding
+// sequence of the compiled reference (common.cuh), so the tables -- and therefore which voxels are
+// touched and with what weights -- are bit-identical; only the summation order differs (fp32, a few
+// ulp; tolerance 1e-5 forward / 1e-4 backward per BASELINE.json).
+//
+// RoIs whose footprint exceeds the table capacity, and output widths other than 7/14, take the
+// "generic" path: the same warp-per-(RoI, channel-vector) mapping evaluating the reference's sample
+// loops literally (bit-exact against the oracle with contract=1).
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace roi3d {
+
+struct LevelDev {
+  const float *feats;
+  float *grad;
+  int D, H, W;
+  float scale, scale_d;
+};
+
+struct RoiParams {
+  LevelDev lv[ROI3D_MAX_LEVELS];
+  int num_levels;
+  float inv_finest;
+  int B, C;
+  const float *rois;
+  int K;
+  int PD, PH, PW;
+  int sample_num;
+  float *out;             // forward
+  const float *grad_out;  // backward
+  int64_t *lvls_out;
+  int nchunk, nphg;
+  long long total_items;
+  int bug_compat;
+};
+
+constexpr int kWarps = 4;
+constexpr int RXMAX = 40, RYMAX = 40, RZMAX = 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int CV>
+__device__ __forceinline__ void ldv(const float *p, float (&v)[CV]) {
+  if constexpr (CV == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  } else if constexpr (CV == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    v[0] = t.x, v[1] = t.y;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+
+template <int CV>
+__device__ __forceinline__ void redv(float *p, const float (&v)[CV]) {
+  if constexpr (CV == 4) {
+    atomicAdd(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+  } else if constexpr (CV == 2) {
+    atomicAdd(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
+  } else {
+    atomicAdd(p, v[0]);
+  }
+}
+
+// Per-warp decode of one work item + RoI geometry.
+struct Item {
+  int k, chunk, pd, ph0, rows, lvl, b;
+  bool ok;
+  Axis axw, axh, axd;
+  LevelDev L;
+};
+
+__device__ __forceinline__ Item decode_item(const RoiParams &p, long long item, int ROWS) {
+  Item it;
+  int phg = (int)(item % p.nphg);
+  item /= p.nphg;
+  it.pd = (int)(item % p.PD);
+  item /= p.PD;
+  it.chunk = (int)(item % p.nchunk);
+  it.k = (int)(item / p.nchunk);
+  it.ph0 = phg * ROWS;
+  it.rows = min(ROWS, p.PH - it.ph0);
+  const float *roi = p.rois + (long long)it.k * 7;
+  float r[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r[i] = __ldg(roi + i);
+  it.lvl = p.num_levels > 1 ? roi_level(r, p.num_levels, p.inv_finest) : 0;
+  it.L = p.lv[it.lvl];
+  it.b = (int)r[0];
+  it.ok = it.b >= 0 && it.b < p.B;
+  it.axw = axis_setup(r[1], r[3], it.L.scale, p.PW, p.sample_num);
+  it.axh = axis_setup(r[2], r[4], it.L.scale, p.PH, p.sample_num);
+  it.axd = axis_setup(r[5], r[6], it.L.scale_d, p.PD, p.sample_num);
+  return it;
+}
+
+// Per-warp weight tables in shared memory.
+//   Dx[(x - xmin) * PWP + pw], Dy[(y - ymin) * 8 + r], Dz[z - zmin]; xlo/xhi[pw] relative to xmin.
+template <int PW>
+struct Tables {
+  static constexpr int PWP = (PW + 3) / 4 * 4;
+  static constexpr int FLOATS = RXMAX * PWP + RYMAX * 8 + RZMAX + 32 + RXMAX;
+  float *Dx, *Dy, *Dz;
+  int *xlo, *xhi;
+  int *xany;
+  int xmin, xmax, ymin, ymax, zmin, zmax;
+  bool empty, fits;
+  __device__ __forceinline__ void bind(float *sm) {
+    Dx = sm;
+    Dy = Dx + RXMAX * PWP;
+    Dz = Dy + RYMAX * 8;
+    xlo = reinterpret_cast<int *>(Dz + RZMAX);
+    xhi = xlo + 16;
+    xany = xhi + 16;
+  }
+};
+
+template <int PW>
+__device__ __forceinline__ void build_tables(Tables<PW> &T, const Item &it, int lane) {
+  constexpr int PWP = Tables<PW>::PWP;
+  // lanes [0,PW): x axis; lanes [16,16+rows): y axis; lane 31: z axis.
+  int role = -1, pidx = 0, size = 1;
+  Axis ax = it.axw;
+  if (lane < PW) {
+    role = 0, pidx = lane, size = it.L.W, ax = it.axw;
+  } else if (lane >= 16 && lane < 16 + it.rows) {
+    role = 1, pidx = it.ph0 + lane - 16, size = it.L.H, ax = it.axh;
+  } else if (lane == 31) {
+    role = 2, pidx = it.pd, size = it.L.D, ax = it.axd;
+  }
+  int lo = INT_MAX, hi = -1;
+  if (role >= 0) {
+    for (int i = 0; i < ax.S; ++i) {
+      Tap t = axis_tap(axis_coord(ax, pidx, i), size);
+      if (t.valid) lo = min(lo, t.low), hi = max(hi, t.high);
+    }
+  }
+  T.xmin = __reduce_min_sync(FULL, role == 0 ? lo : INT_MAX);
+  T.xmax = __reduce_max_sync(FULL, role == 0 ? hi : -1);
+  T.ymin = __reduce_min_sync(FULL, role == 1 ? lo : INT_MAX);
+  T.ymax = __reduce_max_sync(FULL, role == 1 ? hi : -1);
+  T.zmin = __reduce_min_sync(FULL, role == 2 ? lo : INT_MAX);
+  T.zmax = __reduce_max_sync(FULL, role == 2 ? hi : -1);
+  T.empty = T.xmax < T.xmin || T.ymax < T.ymin || T.zmax < T.zmin;
+  T.fits = T.empty || ((T.xmax - T.xmin < RXMAX) && (T.ymax - T.ymin < RYMAX) && (T.zmax - T.zmin < RZMAX));
+  if (T.empty || !T.fits) return;
+  const int RX = T.xmax - T.xmin + 1, RY = T.ymax - T.ymin + 1, RZ = T.zmax - T.zmin + 1;
+  for (int i = lane; i < RX * PWP; i += 32) T.Dx[i] = 0.0f;
+  for (int i = lane; i < RY * 8; i += 32) T.Dy[i] = 0.0f;
+  for (int i = lane; i < RZ; i += 32) T.Dz[i] = 0.0f;
+  for (int i = lane; i < RX; i += 32) T.xany[i] = 0;
+  __syncwarp();
+  if (role >= 0) {
+    float *tab = role == 0 ? T.Dx : role == 1 ? T.Dy : T.Dz;
+    const int stride = role == 0 ? PWP : role == 1 ? 8 : 1;
+    const int col = role == 0 ? lane : role == 1 ? lane - 16 : 0;
+    const int mn = role == 0 ? T.xmin : role == 1 ? T.ymin : T.zmin;
+    for (int i = 0; i < ax.S; ++i) {
+      Tap t = axis_tap(axis_coord(ax, pidx, i), size);
+      if (t.valid) {
+        tab[(t.low - mn) * stride + col] += t.h;
+        tab[(t.high - mn) * stride + col] += t.l;
+        if (role == 0) T.xany[t.low - mn] = 1, T.xany[t.high - mn] = 1;
+      }
+    }
+    if (role == 0) {
+      T.xlo[lane] = hi >= lo ? lo - T.xmin : 0;
+      T.xhi[lane] = hi >= lo ? hi - T.xmin : -1;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic (literal) evaluation of one output bin for CV channels per lane: the reference's sample
+// loops and its exact corner-weight / FFMA-chain arithmetic (roi_align_kernel.cu:134-146 + SASS).
+// ---------------------------------------------------------------------------------------------
+template <int CV>
+__device__ __forceinline__ void literal_bin_fwd(const Item &it, const float *fb, int C, int pd, int ph, int pw,
+                                                float (&out)[CV]) {
+  const int D = it.L.D, H = it.L.H, W = it.L.W;
+  float acc[CV];
+#pragma unroll
+  for (int c = 0; c < CV; ++c) acc[c] = 0.0f;
+  for (int iz = 0; iz < it.axd.S; ++iz) {
+    Tap tz = axis_tap(axis_coord(it.axd, pd, iz), D);
+    for (int iy = 0; iy < it.axh.S; ++iy) {
+      Tap ty = axis_tap(axis_coord(it.axh, ph, iy), H);
+      for (int ix = 0; ix < it.axw.S; ++ix) {
+        Tap tx = axis_tap(axis_coord(it.axw, pw, ix), W);
+        if (!(tz.valid && ty.valid && tx.valid)) continue;  // contributes 0, still counted
+        const float hxhy = __fmul_rn(tx.h, ty.h), lxhy = __fmul_rn(tx.l, ty.h);
+        const float hxly = __fmul_rn(tx.h, ty.l), lxly = __fmul_rn(tx.l, ty.l);
+        const float w1 = __fmul_rn(hxhy, tz.h), w2 = __fmul_rn(lxhy, tz.h), w3 = __fmul_rn(hxly, tz.h),
+                    w4 = __fmul_rn(lxly, tz.h), w5 = __fmul_rn(hxhy, tz.l), w6 = __fmul_rn(lxhy, tz.l),
+                    w7 = __fmul_rn(hxly, tz.l), w8 = __fmul_rn(lxly, tz.l);
+        const long long zl = (long long)tz.low * H, zh = (long long)tz.high * H;
+        float f1[CV], f2[CV], f3[CV], f4[CV], f5[CV], f6[CV], f7[CV], f8[CV];
+        ldv<CV>(fb + ((zl + ty.low) * W + tx.low) * C, f1);
+        ldv<CV>(fb + ((zl + ty.low) * W + tx.high) * C, f2);
+        ldv<CV>(fb + ((zl + ty.high) * W + tx.low) * C, f3);
+        ldv<CV>(fb + ((zl + ty.high) * W + tx.high) * C, f4);
+        ldv<CV>(fb + ((zh + ty.low) * W + tx.low) * C, f5);
+        ldv<CV>(fb + ((zh + ty.low) * W + tx.high) * C, f6);
+        ldv<CV>(fb + ((zh + ty.high) * W + tx.low) * C, f7);
+        ldv<CV>(fb + ((zh + ty.high) * W + tx.high) * C, f8);
+#pragma unroll
+        for (int c = 0; c < CV; ++c) {
+          float t = __fmul_rn(w2, f2[c]);
+          t = __fmaf_rn(w1, f1[c], t);
+          t = __fmaf_rn(w3, f3[c], t);
+          t = __fmaf_rn(w4, f4[c], t);
+          t = __fmaf_rn(w5, f5[c], t);
+          t = __fmaf_rn(w6, f6[c], t);
+          t = __fmaf_rn(w7, f7[c], t);
+          t = __fmaf_rn(w8, f8[c], t);
+          acc[c] = __fadd_rn(acc[c], t);
+        }
+      }
+    }
+  }
+  const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
+#pragma unroll
+  for (int c = 0; c < CV; ++c) out[c] = __fdiv_rn(acc[c], count);
+}
+
+template <int CV>
+__device__ __forceinline__ void literal_bin_bwd(const Item &it, float *gb, int C, int pd, int ph, int pw,
+                                                const float (&top)[CV]) {
+  const int D = it.L.D, H = it.L.H, W = it.L.W;
+  const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
+  for (int iz = 0; iz < it.axd.S; ++iz) {
+    Tap tz = axis_tap(axis_coord(it.axd, pd, iz), D);
+    for (int iy = 0; iy < it.axh.S; ++iy) {
+      Tap ty = axis_tap(axis_coord(it.axh, ph, iy), H);
+      for (int ix = 0; ix < it.axw.S; ++ix) {
+        Tap tx = axis_tap(axis_coord(it.axw, pw, ix), W);
+        if (!(tz.valid && ty.valid && tx.valid)) continue;
+        const float hxhy = __fmul_rn(tx.h, ty.h), lxhy = __fmul_rn(tx.l, ty.h);
+        const float hxly = __fmul_rn(tx.h, ty.l), lxly = __fmul_rn(tx.l, ty.l);
+        const float w[8] = {__fmul_rn(hxhy, tz.h), __fmul_rn(lxhy, tz.h), __fmul_rn(hxly, tz.h),
+                            __fmul_rn(lxly, tz.h), __fmul_rn(hxhy, tz.l), __fmul_rn(lxhy, tz.l),
+                            __fmul_rn(hxly, tz.l), __fmul_rn(lxly, tz.l)};
+        const long long zl = (long long)tz.low * H, zh = (long long)tz.high * H;
+        const long long off[8] = {((zl + ty.low) * W + tx.low) * C,  ((zl + ty.low) * W + tx.high) * C,
+                                  ((zl + ty.high) * W + tx.low) * C, ((zl + ty.high) * W + tx.high) * C,
+                                  ((zh + ty.low) * W + tx.low) * C,  ((zh + ty.low) * W + tx.high) * C,
+                                  ((zh + ty.high) * W + tx.low) * C, ((zh + ty.high) * W + tx.high) * C};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float g[CV];
+#pragma unroll
+          for (int c = 0; c < CV; ++c) g[c] = __fdiv_rn(__fmul_rn(top[c], w[q]), count);
+          redv<CV>(gb + off[q], g);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward, channels-last, separable.  One warp per (k, chunk, pd, ph-group).
+// ---------------------------------------------------------------------------------------------
+template <int PW, int ROWS, int CV, int NXU>
+__global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_cl_kernel(const RoiParams p) {
+  using TB = Tables<PW>;
+  constexpr int PWP = TB::PWP;
+  constexpr int STAGE = ROWS * PW * 33;
+  constexpr int WARP_FLOATS = STAGE > TB::FLOATS ? STAGE : TB::FLOATS;
+  extern __shared__ float smem_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *sm = smem_all + warp * WARP_FLOATS;
+  const long long item = (long long)blockIdx.x * kWarps + warp;
+  if (item >= p.total_items) return;  // warp-uniform; no block-level barrier is used below
+
+  const Item it = decode_item(p, item, ROWS);
+  const int C = p.C;
+  if (p.lvls_out != nullptr && it.chunk == 0 && it.pd == 0 && it.ph0 == 0 && lane == 0) p.lvls_out[it.k] = it.lvl;
+
+  int c_base = (it.chunk * 32 + lane) * CV;
+  const bool active = c_base < C;
+  if (!active) c_base = 0;
+  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+  const float *fb = it.L.feats + (long long)(it.ok ? it.b : 0) * vox * C + c_base;
+
+  float acc[ROWS][PW][CV];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int w = 0; w < PW; ++w)
+#pragma unroll
+      for (int c = 0; c < CV; ++c) acc[r][w][c] = 0.0f;
+
+  TB T;
+  T.bind(sm);
+  T.empty = true, T.fits = true;
+  if (it.ok) build_tables<PW>(T, it, lane);
+  const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
+
+  if (it.ok && !T.fits) {
+    // footprint larger than the tables: literal evaluation, uncoalesced stores (rare path)
+    for (int r = 0; r < it.rows; ++r)
+      for (int pw = 0; pw < PW; ++pw) {
+        float v[CV];
+        literal_bin_fwd<CV>(it, fb, C, it.pd, it.ph0 + r, pw, v);
+        if (active) {
+#pragma unroll
+          for (int c = 0; c < CV; ++c) {
+            const long long o =
+                ((((long long)it.k * C + c_base + c) * p.PD + it.pd) * p.PH + it.ph0 + r) * PW + pw;
+            p.out[o] = v[c];
+          }
+        }
+      }
+    return;
+  }
+
+  if (!T.empty) {
+    const int RY = T.ymax - T.ymin + 1;
+    for (int z = T.zmin; z <= T.zmax; ++z) {
+      const float wz = T.Dz[z - T.zmin];
+      if (wz == 0.0f) continue;
+      for (int yy = 0; yy < RY; ++yy) {
+        float wr[ROWS];
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          wr[r] = wz * T.Dy[yy * 8 + r];
+          any |= wr[r] != 0.0f;
+        }
+        if (!any) continue;
+        const float *rowp = fb + (((long long)z * it.L.H + (T.ymin + yy)) * it.L.W + T.xmin) * C;
+        float t1[PW][CV];
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) {
+          const int lo = T.xlo[pw];
+          const int n = T.xhi[pw] - lo + 1;
+          const float *q = rowp + (long long)lo * C;
+          const float *wq = T.Dx + lo * PWP + pw;
+          float t[CV];
+#pragma unroll
+          for (int c = 0; c < CV; ++c) t[c] = 0.0f;
+#pragma unroll
+          for (int j = 0; j < NXU; ++j) {
+            if (j < n) {
+              float f[CV];
+              ldv<CV>(q + (long long)j * C, f);
+              const float w = wq[j * PWP];
+#pragma unroll
+              for (int c = 0; c < CV; ++c) t[c] = fmaf(w, f[c], t[c]);
+            }
+          }
+          for (int j = NXU; j < n; ++j) {
+            float f[CV];
+            ldv<CV>(q + (long long)j * C, f);
+            const float w = wq[j * PWP];
+#pragma unroll
+            for (int c = 0; c < CV; ++c) t[c] = fmaf(w, f[c], t[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < CV; ++c) t1[pw][c] = t[c];
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          if (wr[r] != 0.0f) {
+#pragma unroll
+            for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+              for (int c = 0; c < CV; ++c) acc[r][pw][c] = fmaf(wr[r], t1[pw][c], acc[r][pw][c]);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: divide by the sample count, transpose through smem, stream out ----
+  const int NB = it.rows * PW;
+  float *stage = sm;  // aliases the tables: all table reads are done
+  const long long out_base = (((long long)it.k * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
+  const long long ch_stride = (long long)p.PD * p.PH * PW;
+#pragma unroll
+  for (int c = 0; c < CV; ++c) {
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw) stage[(r * PW + pw) * 33 + lane] = __fdiv_rn(acc[r][pw][c], count);
+    __syncwarp();
+    int cl = 0, bin = lane;
+    while (bin >= NB) bin -= NB, ++cl;
+    while (cl < 32) {
+      const int ch = (it.chunk * 32 + cl) * CV + c;
+      if (ch < C) __stcs(p.out + out_base + (long long)ch * ch_stride + bin, stage[bin * 33 + cl]);
+      bin += 32;
+      while (bin >= NB) bin -= NB, ++cl;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward, channels-last, separable (transposed contraction).  Same work split as the forward.
+// One vector red per (row voxel, lane) instead of 64 scalar atomics per output element.
+// ---------------------------------------------------------------------------------------------
+template <int PW, int ROWS, int CV>
+__global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const RoiParams p) {
+  using TB = Tables<PW>;
+  constexpr int PWP = TB::PWP;
+  constexpr int STAGE = ROWS * PW * 33;
+  constexpr int WARP_FLOATS = STAGE > TB::FLOATS ? STAGE : TB::FLOATS;
+  extern __shared__ float smem_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *sm = smem_all + warp * WARP_FLOATS;
+  const long long item = (long long)blockIdx.x * kWarps + warp;
+  if (item >= p.total_items) return;
+
+  const Item it = decode_item(p, item, ROWS);
+  if (!it.ok) return;
+  const int C = p.C;
+  int c_base = (it.chunk * 32 + lane) * CV;
+  const bool active = c_base < C;
+  if (!active) c_base = 0;
+  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+  float *gb = it.L.grad + (long long)it.b * vox * C + c_base;
+  const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
+
+  // ---- stage-in of this warp's grad_out tile: coalesced reads, transposed through smem ----
+  const int NB = it.rows * PW;
+  const long long ch_stride = (long long)p.PD * p.PH * PW;
+  // reference index (roi_align_kernel.cu:554-555): pd*PD*PW + ph*PW + pw when bug_compat
+  const long long row_base = p.bug_compat ? ((long long)it.pd * p.PD + it.ph0) * PW
+                                          : ((long long)it.pd * p.PH + it.ph0) * PW;
+  const long long top_base = ((long long)it.k * C) * ch_stride + row_base;
+  const long long top_total = (long long)p.K * C * ch_stride;
+  float g[ROWS][PW][CV];
+  float *stage = sm;
+#pragma unroll
+  for (int c = 0; c < CV; ++c) {
+    __syncwarp();
+    int cl = 0, bin = lane;
+    while (bin >= NB) bin -= NB, ++cl;
+    while (cl < 32) {
+      const int ch = (it.chunk * 32 + cl) * CV + c;
+      const long long o = top_base + (long long)ch * ch_stride + bin;
+      stage[bin * 33 + cl] = (ch < C && o < top_total) ? __ldcs(p.grad_out + o) : 0.0f;
+      bin += 32;
+      while (bin >= NB) bin -= NB, ++cl;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw)
+        g[r][pw][c] = r < it.rows ? stage[(r * PW + pw) * 33 + lane] : 0.0f;
+  }
+  __syncwarp();
+
+  TB T;
+  T.bind(sm);
+  build_tables<PW>(T, it, lane);
+  if (T.empty) return;
+
+  if (!T.fits) {
+    for (int r = 0; r < it.rows; ++r)
+      for (int pw = 0; pw < PW; ++pw) {
+        float top[CV];
+#pragma unroll
+        for (int c = 0; c < CV; ++c) top[c] = 0.0f;
+        // dynamic (r,pw) register indexing is not possible: select with a static sweep
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+          for (int ww = 0; ww < PW; ++ww)
+            if (rr == r && ww == pw) {
+#pragma unroll
+              for (int c = 0; c < CV; ++c) top[c] = g[rr][ww][c];
+            }
+        if (active) literal_bin_bwd<CV>(it, gb, C, it.pd, it.ph0 + r, pw, top);
+      }
+    return;
+  }
+
+  // scale once by 1/count (reference: top*w/count per corner, roi_align_kernel.cu:600-608)
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+      for (int c = 0; c < CV; ++c) g[r][pw][c] = __fdiv_rn(g[r][pw][c], count);
+
+  const int RY = T.ymax - T.ymin + 1, RX = T.xmax - T.xmin + 1;
+  for (int z = T.zmin; z <= T.zmax; ++z) {
+    const float wz = T.Dz[z - T.zmin];
+    if (wz == 0.0f) continue;
+    for (int yy = 0; yy < RY; ++yy) {
+      float wr[ROWS];
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        wr[r] = wz * T.Dy[yy * 8 + r];
+        any |= wr[r] != 0.0f;
+      }
+      if (!any) continue;
+      float u[PW][CV];
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+        for (int c = 0; c < CV; ++c) u[pw][c] = 0.0f;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if (wr[r] != 0.0f) {
+#pragma unroll
+          for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+            for (int c = 0; c < CV; ++c) u[pw][c] = fmaf(wr[r], g[r][pw][c], u[pw][c]);
+        }
+      }
+      float *rowp = gb + (((long long)z * it.L.H + (T.ymin + yy)) * it.L.W + T.xmin) * C;
+      for (int xx = 0; xx < RX; ++xx) {
+        if (!T.xany[xx]) continue;
+        float wx[PWP];
+#pragma unroll
+        for (int q = 0; q < PWP / 4; ++q) {
+          const float4 t = *reinterpret_cast<const float4 *>(T.Dx + xx * PWP + q * 4);
+          wx[q * 4 + 0] = t.x, wx[q * 4 + 1] = t.y, wx[q * 4 + 2] = t.z, wx[q * 4 + 3] = t.w;
+        }
+        float v[CV];
+#pragma unroll
+        for (int c = 0; c < CV; ++c) v[c] = 0.0f;
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+          for (int c = 0; c < CV; ++c) v[c] = fmaf(wx[pw], u[pw][c], v[c]);
+        if (active) redv<CV>(rowp + (long long)xx * C, v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic kernels (any PD/PH/PW): one warp per (k, chunk, pd, ph), literal evaluation.
+// ---------------------------------------------------------------------------------------------
+template <int CV>
+__global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_generic_kernel(const RoiParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * kWarps + warp;
+  if (item >= p.total_items) return;
+  const Item it = decode_item(p, item, 1);
+  const int C = p.C;
+  if (p.lvls_out != nullptr && it.chunk == 0 && it.pd == 0 && it.ph0 == 0 && lane == 0) p.lvls_out[it.k] = it.lvl;
+  int c_base = (it.chunk * 32 + lane) * CV;
+  const bool active = c_base < C;
+  if (!active) c_base = 0;
+  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+  const float *fb = it.L.feats + (long long)(it.ok ? it.b : 0) * vox * C + c_base;
+  for (int pw = 0; pw < p.PW; ++pw) {
+    float v[CV];
+    if (it.ok) {
+      literal_bin_fwd<CV>(it, fb, C, it.pd, it.ph0, pw, v);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CV; ++c) v[c] = 0.0f;
+    }
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < CV; ++c)
+        p.out[((((long long)it.k * C + c_base + c) * p.PD + it.pd) * p.PH + it.ph0) * p.PW + pw] = v[c];
+    }
+  }
+}
+
+template <int CV>
+__global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_generic_kernel(const RoiParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * kWarps + warp;
+  if (item >= p.total_items) return;
+  const Item it = decode_item(p, item, 1);
+  if (!it.ok) return;
+  const int C = p.C;
+  int c_base = (it.chunk * 32 + lane) * CV;
+  if (c_base >= C) return;
+  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+  float *gb = it.L.grad + (long long)it.b * vox * C + c_base;
+  const long long bins = (long long)p.PD * p.PH * p.PW;
+  const long long total = (long long)p.K * C * bins;
+  for (int pw = 0; pw < p.PW; ++pw) {
+    float top[CV];
+#pragma unroll
+    for (int c = 0; c < CV; ++c) {
+      const long long off = p.bug_compat ? ((long long)it.pd * p.PD * p.PW + (long long)it.ph0 * p.PW + pw)
+                                         : (((long long)it.pd * p.PH + it.ph0) * p.PW + pw);
+      const long long o = ((long long)it.k * C + c_base + c) * bins + off;
+      top[c] = o < total ? __ldg(p.grad_out + o) : 0.0f;
+    }
+    literal_bin_bwd<CV>(it, gb, C, it.pd, it.ph0, pw, top);
+  }
+}
+
+__global__ void map_roi_levels_kernel(const float *rois, int K, int num_levels, float inv_finest, int64_t *lvls) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float r[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r[i] = rois[(long long)k * 7 + i];
+  lvls[k] = roi_level(r, num_levels, inv_finest);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layout conversion: per batch a [C][S] <-> [S][C] transpose (S = D*H*W), 32x32 tiles, padded smem.
+// ---------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols,
+                                 int tiles_c) {
+  // src [rows][cols] -> dst [cols][rows]; blockIdx.y = batch; blockIdx.x = linear tile index
+  __shared__ float tile[32][33];
+  const long long boff = (long long)blockIdx.y * rows * cols;
+  const int c0 = (blockIdx.x % tiles_c) * 32, r0 = (blockIdx.x / tiles_c) * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + i][tx] = __ldcs(src + boff + (long long)r * cols + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, r = r0 + tx;
+    if (r < rows && c < cols) dst[boff + (long long)c * rows + r] = tile[tx][ty + i];
+  }
+}
+
+static int transpose_launch(const float *src, float *dst, int B, int rows, int cols, cudaStream_t st) {
+  dim3 block(32, 8);
+  const long long tc = ceil_div_ll(cols, 32), tr = ceil_div_ll(rows, 32);
+  ROI3D_CHECK_ARG(tc * tr < 2147483647LL && B <= 65535, "transpose: tensor too large for one launch");
+  dim3 grid((unsigned)(tc * tr), (unsigned)B);
+  transpose_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols, (int)tc);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dispatch
+// ---------------------------------------------------------------------------------------------
+static int g_fwd_variant = 0;  // 0 = auto; see roi3d_set_tuning
+static int g_bwd_variant = 0;
+
+template <int PW, int ROWS, int CV, int NXU>
+static int launch_fwd(RoiParams &p, cudaStream_t st) {
+  using TB = Tables<PW>;
+  constexpr int STAGE = ROWS * PW * 33;
+  constexpr int WARP_FLOATS = STAGE > TB::FLOATS ? STAGE : TB::FLOATS;
+  const size_t smem = (size_t)kWarps * WARP_FLOATS * sizeof(float);
+  p.nchunk = ceil_div(p.C, 32 * CV);
+  p.nphg = ceil_div(p.PH, ROWS);
+  p.total_items = (long long)p.K * p.nchunk * p.PD * p.nphg;
+  auto kern = roi_align3d_fwd_cl_kernel<PW, ROWS, CV, NXU>;
+  ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long blocks = ceil_div_ll(p.total_items, kWarps);
+  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
+  kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+template <int PW, int ROWS, int CV>
+static int launch_bwd(RoiParams &p, cudaStream_t st) {
+  using TB = Tables<PW>;
+  constexpr int STAGE = ROWS * PW * 33;
+  constexpr int WARP_FLOATS = STAGE > TB::FLOATS ? STAGE : TB::FLOATS;
+  const size_t smem = (size_t)kWarps * WARP_FLOATS * sizeof(float);
+  p.nchunk = ceil_div(p.C, 32 * CV);
+  p.nphg = ceil_div(p.PH, ROWS);
+  p.total_items = (long long)p.K * p.nchunk * p.PD * p.nphg;
+  auto kern = roi_align3d_bwd_cl_kernel<PW, ROWS, CV>;
+  ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long blocks = ceil_div_ll(p.total_items, kWarps);
+  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d backward: too many work items");
+  kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+template <int CV>
+static int launch_generic(RoiParams &p, bool fwd, cudaStream_t st) {
+  p.nchunk = ceil_div(p.C, 32 * CV);
+  p.nphg = p.PH;
+  p.total_items = (long long)p.K * p.nchunk * p.PD * p.nphg;
+  const long long blocks = ceil_div_ll(p.total_items, kWarps);
+  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d: too many work items");
+  if (fwd)
+    roi_align3d_fwd_generic_kernel<CV><<<(unsigned)blocks, kWarps * 32, 0, st>>>(p);
+  else
+    roi_align3d_bwd_generic_kernel<CV><<<(unsigned)blocks, kWarps * 32, 0, st>>>(p);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+static bool aligned(const void *ptr, size_t a) { return (reinterpret_cast<uintptr_t>(ptr) % a) == 0; }
+
+static int pick_cv(const RoiParams &p, bool bwd) {
+  int cv = 4;
+  for (int l = 0; l < p.num_levels; ++l) {
+    const void *ptr = bwd ? (const void *)p.lv[l].grad : (const void *)p.lv[l].feats;
+    while (cv > 1 && (p.C % cv != 0 || !aligned(ptr, cv * sizeof(float)))) cv >>= 1;
+  }
+  return cv;
+}
+
+static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
+  if (p.K == 0) return ROI3D_OK;
+  const int cvmax = pick_cv(p, false);
+  const int v = g_fwd_variant;
+  if (v == 99) {  // force the literal path (tests)
+    if (cvmax >= 2) return launch_generic<2>(p, true, st);
+    return launch_generic<1>(p, true, st);
+  }
+  if (p.PW == 7) {
+    if (v == 1 || cvmax == 1) return launch_fwd<7, 7, 1, 3>(p, st);
+    if (v == 2 && cvmax >= 4) return launch_fwd<7, 4, 4, 3>(p, st);
+    return launch_fwd<7, 7, 2, 3>(p, st);
+  }
+  if (p.PW == 14) {
+    if (v == 1 || cvmax == 1) return launch_fwd<14, 7, 1, 3>(p, st);
+    if (v == 2 && cvmax >= 4) return launch_fwd<14, 2, 4, 3>(p, st);
+    return launch_fwd<14, 4, 2, 3>(p, st);
+  }
+  if (cvmax >= 2) return launch_generic<2>(p, true, st);
+  return launch_generic<1>(p, true, st);
+}
+
+static int dispatch_bwd(RoiParams &p, cudaStream_t st) {
+  if (p.K == 0) return ROI3D_OK;
+  const int cvmax = pick_cv(p, true);
+  const int v = g_bwd_variant;
+  if (v == 99) {
+    if (cvmax >= 2) return launch_generic<2>(p, false, st);
+    return launch_generic<1>(p, false, st);
+  }
+  if (p.PW == 7) {
+    if (v == 1 || cvmax == 1) return launch_bwd<7, 7, 1>(p, st);
+    if (v == 2 && cvmax >= 4) return launch_bwd<7, 4, 4>(p, st);
+    return launch_bwd<7, 7, 2>(p, st);
+  }
+  if (p.PW == 14) {
+    if (v == 1 || cvmax == 1) return launch_bwd<14, 7, 1>(p, st);
+    if (v == 2 && cvmax >= 4) return launch_bwd<14, 2, 4>(p, st);
+    return launch_bwd<14, 4, 2>(p, st);
+  }
+  if (cvmax >= 2) return launch_generic<2>(p, false, st);
+  return launch_generic<1>(p, false, st);
+}
+
+static int fill_params(RoiParams &p, const roi3d_level_t *levels, int num_levels, int B, int C, const float *rois,
+                       int K, int PD, int PH, int PW, int sample_num, float finest_scale, bool bwd) {
+  ROI3D_CHECK_ARG(num_levels >= 1 && num_levels <= ROI3D_MAX_LEVELS, "num_levels=%d out of [1,%d]", num_levels,
+                  ROI3D_MAX_LEVELS);
+  ROI3D_CHECK_ARG(B > 0 && C > 0 && K >= 0, "bad sizes B=%d C=%d K=%d", B, C, K);
+  ROI3D_CHECK_ARG(PD > 0 && PH > 0 && PW > 0, "bad output size %dx%dx%d", PD, PH, PW);
+  ROI3D_CHECK_ARG(K == 0 || rois != nullptr, "rois is NULL");
+  ROI3D_CHECK_ARG(finest_scale > 0.0f || num_levels == 1, "finest_scale must be > 0");
+  for (int l = 0; l < num_levels; ++l) {
+    ROI3D_CHECK_ARG(levels[l].layout == ROI3D_NDHWC,
+                    "level %d: the kernels read channels-last (ROI3D_NDHWC) memory; convert with "
+                    "roi3d_ncdhw_to_ndhwc first",
+                    l);
+    ROI3D_CHECK_ARG(levels[l].D > 0 && levels[l].H > 0 && levels[l].W > 0, "level %d: bad dims", l);
+    ROI3D_CHECK_ARG(bwd ? levels[l].grad_dev != nullptr : levels[l].feats_dev != nullptr, "level %d: NULL pointer", l);
+    ROI3D_CHECK_ARG((long long)levels[l].D * levels[l].H * levels[l].W < (1LL << 31), "level %d too large", l);
+    p.lv[l].feats = levels[l].feats_dev;
+    p.lv[l].grad = levels[l].grad_dev;
+    p.lv[l].D = levels[l].D, p.lv[l].H = levels[l].H, p.lv[l].W = levels[l].W;
+    p.lv[l].scale = levels[l].spatial_scale, p.lv[l].scale_d = levels[l].spatial_scale_depth;
+  }
+  p.num_levels = num_levels;
+  p.inv_finest = num_levels > 1 ? 1.0f / finest_scale : 0.0f;
+  p.B = B, p.C = C, p.rois = rois, p.K = K, p.PD = PD, p.PH = PH, p.PW = PW, p.sample_num = sample_num;
+  p.out = nullptr, p.grad_out = nullptr, p.lvls_out = nullptr, p.bug_compat = 0;
+  return ROI3D_OK;
+}
+
+}  // namespace roi3d
+
+using namespace roi3d;
+
+extern "C" {
+
+int roi3d_set_tuning(int key, int value) {
+  if (key == 0) g_fwd_variant = value;
+  else if (key == 1) g_bwd_variant = value;
+  else return ROI3D_EINVAL;
+  return ROI3D_OK;
+}
+
+int roi3d_extract_forward(const roi3d_level_t *levels, int num_levels, int B, int C, const float *rois_dev, int K,
+                          int PD, int PH, int PW, int sample_num, float finest_scale, float *out_dev,
+                          int64_t *lvls_out_dev, void *stream) {
+  RoiParams p;
+  int rc = fill_params(p, levels, num_levels, B, C, rois_dev, K, PD, PH, PW, sample_num, finest_scale, false);
+  if (rc) return rc;
+  ROI3D_CHECK_ARG(K == 0 || out_dev != nullptr, "out is NULL");
+  p.out = out_dev;
+  p.lvls_out = lvls_out_dev;
+  return dispatch_fwd(p, (cudaStream_t)stream);
+}
+
+int roi3d_extract_backward(const roi3d_level_t *levels, int num_levels, int B, int C, const float *rois_dev, int K,
+                           int PD, int PH, int PW, int sample_num, float finest_scale, const float *grad_out_dev,
+                           int zero_fill, int bug_compat, void *stream) {
+  RoiParams p;
+  int rc = fill_params(p, levels, num_levels, B, C, rois_dev, K, PD, PH, PW, sample_num, finest_scale, true);
+  if (rc) return rc;
+  ROI3D_CHECK_ARG(K == 0 || grad_out_dev != nullptr, "grad_out is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zero_fill) {
+    for (int l = 0; l < num_levels; ++l) {
+      const size_t bytes = (size_t)B * C * levels[l].D * levels[l].H * levels[l].W * sizeof(float);
+      ROI3D_CUDA(cudaMemsetAsync(levels[l].grad_dev, 0, bytes, st));
+    }
+  }
+  p.grad_out = grad_out_dev;
+  p.bug_compat = bug_compat;
+  return dispatch_bwd(p, st);
+}
+
+int roi3d_roi_align3d_forward(const float *feats_dev, int layout, int B, int C, int D, int H, int W,
+                              const float *rois_dev, int K, int PD, int PH, int PW, float spatial_scale,
+                              float spatial_scale_depth, int sample_num, float *out_dev, void *stream) {
+  roi3d_level_t lv;
+  lv.feats_dev = feats_dev, lv.grad_dev = nullptr, lv.layout = layout, lv.D = D, lv.H = H, lv.W = W;
+  lv.spatial_scale = spatial_scale, lv.spatial_scale_depth = spatial_scale_depth;
+  return roi3d_extract_forward(&lv, 1, B, C, rois_dev, K, PD, PH, PW, sample_num, 56.0f, out_dev, nullptr, stream);
+}
+
+int roi3d_roi_align3d_backward(const float *grad_out_dev, const float *rois_dev, int K, int PD, int PH, int PW,
+                               float spatial_scale, float spatial_scale_depth, int sample_num, float *grad_in_dev,
+                               int layout, int B, int C, int D, int H, int W, int zero_fill, int bug_compat,
+                               void *stream) {
+  roi3d_level_t lv;
+  lv.feats_dev = nullptr, lv.grad_dev = grad_in_dev, lv.layout = layout, lv.D = D, lv.H = H, lv.W = W;
+  lv.spatial_scale = spatial_scale, lv.spatial_scale_depth = spatial_scale_depth;
+  return roi3d_extract_backward(&lv, 1, B, C, rois_dev, K, PD, PH, PW, sample_num, 56.0f, grad_out_dev, zero_fill,
+                                bug_compat, stream);
+}
+
+int roi3d_map_roi_levels(const float *rois_dev, int K, int num_levels, float finest_scale, int64_t *lvls_dev,
+                         void *stream) {
+  ROI3D_CHECK_ARG(K >= 0 && num_levels >= 1 && finest_scale > 0.0f, "bad arguments");
+  if (K == 0) return ROI3D_OK;
+  ROI3D_CHECK_ARG(rois_dev && lvls_dev, "NULL pointer");
+  map_roi_levels_kernel<<<ceil_div(K, 256), 256, 0, (cudaStream_t)stream>>>(rois_dev, K, num_levels,
+                                                                           1.0f / finest_scale, lvls_dev);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+int roi3d_ncdhw_to_ndhwc(const float *src_dev, float *dst_dev, int B, int C, int D, int H, int W, void *stream) {
+  ROI3D_CHECK_ARG(src_dev && dst_dev && B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "bad arguments");
+  // [C][S] -> [S][C]: rows = C, cols = S
+  const long long S = (long long)D * H * W;
+  ROI3D_CHECK_ARG(S < (1LL << 31), "level too large");
+  return transpose_launch(src_dev, dst_dev, B, C, (int)S, (cudaStream_t)stream);
+}
+
+int roi3d_ndhwc_to_ncdhw(const float *src_dev, float *dst_dev, int B, int C, int D, int H, int W, void *stream) {
+  ROI3D_CHECK_ARG(src_dev && dst_dev && B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "bad arguments");
+  const long long S = (long long)D * H * W;
+  ROI3D_CHECK_ARG(S < (1LL << 31), "level too large");
+  // [S][C] -> [C][S]: rows = S, cols = C
+  return transpose_launch(src_dev, dst_dev, B, (int)S, C, (cudaStream_t)stream);
+}
+
+}  // extern "C"

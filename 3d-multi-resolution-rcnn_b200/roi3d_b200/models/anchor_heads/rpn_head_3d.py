@@ -1,0 +1,186 @@
+"""RPN proposal path on the B200 kernels: `get_bboxes` / `get_bboxes_single` of the reference's RPNHead3D
+(mmdet/models/anchor_heads/rpn_head_3d.py:72-149, anchor_head_3d.py:232-268).
+
+`RPNProposal3D` holds what the reference head holds for this path (anchor generators per level, strides, target
+means/stds, use_sigmoid_cls) and exposes `get_bboxes(cls_scores, bbox_preds, img_metas, cfg)` with the same
+arguments and the same return value: a list (one entry per image) of [<=max_num, 7] proposals
+(x1,y1,x2,y2,z1,z2,score), and the list of anchors the reference also returns.
+
+Per level the reference runs: permute + sigmoid over every anchor, topk(nms_pre), ~25 elementwise launches of
+delta2bbox3D, cat, a host-synchronising NMS, slice; then cat + topk(max_num) (rpn_head_3d.py:82-148) -- for
+every image separately, with anchors rebuilt in numpy and copied H2D on every call.  Here, for ALL images and
+levels together: one segmented radix-select top-k (sigmoid fused, logical permuted indices), one fused
+anchor+decode kernel per level, one batched NMS over every (image, level) segment, a handful of torch index ops,
+one segmented top-k for the final cut, and a single host read of the result lengths at the end.
+
+Not reproduced: the `pos_indices` inside-flag filter (rpn_head_3d.py:97-106), which only triggers when a cached
+training-loss mask has exactly the same length as the level's scores, and the `min_bbox_size > 0` branch, which
+stops in a debugger in the reference (:125-132); `min_bbox_size > 0` raises here.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ... import _lib
+from ..._util import check_cuda_f32, scratch, stream_ptr
+from ...core.anchor import AnchorGenerator3D
+from ...ops.nms.nms_wrapper import nms3d_batched
+
+
+def _cfg_get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False):
+    """Segmented top-k over a list of CUDA fp32 tensors (one segment each).
+
+    permute_adhw=True: each tensor is an [A, D, H, W] score map and indices refer to
+    permute(2,3,1,0).reshape(-1) positions (rpn_head_3d.py:87-89).  Returns (idx [nseg,k] int64, val [nseg,k]);
+    rows past a segment's length hold -1 / 0.  Descending, ties -> lower index.  No host sync.
+    """
+    nseg = len(scores_list)
+    dev = scores_list[0].device
+    segs = []
+    for s in scores_list:
+        check_cuda_f32(s, "scores")
+        segs.append(s if s.is_contiguous() else s.contiguous())
+    base = min(s.data_ptr() for s in segs)
+    off = np.array([(s.data_ptr() - base) // 4 for s in segs], dtype=np.int64)
+    ln = np.array([s.numel() for s in segs], dtype=np.int64)
+    if permute_adhw:
+        adhw = np.array([list(s.shape[-4:]) for s in segs], dtype=np.int32)
+        adhw_p = adhw.ctypes.data
+    else:
+        adhw, adhw_p = None, None
+    idx = torch.empty((nseg, k), dtype=torch.int64, device=dev)
+    val = torch.empty((nseg, k), dtype=torch.float32, device=dev)
+    nbytes = _lib.lib.roi3d_topk_workspace_bytes(nseg, k)
+    _buf, ws = scratch(dev, nbytes, "topk")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.roi3d_topk_segmented(base, off.ctypes.data, ln.ctypes.data, adhw_p, nseg, int(k),
+                                                 int(bool(apply_sigmoid)), idx.data_ptr(), val.data_ptr(), ws,
+                                                 nbytes, stream_ptr()))
+    del segs, adhw
+    return idx, val
+
+
+def decode_proposals(bbox_pred, base_anchors, stride, depth_stride, idx, scores, means, stds, img_shape):
+    """Fused grid-anchor + delta2bbox3D + score append for the selected anchors of one level.
+    bbox_pred [6A, D, H, W]; idx int64 [n] logical indices (-1 -> zero row); returns [n, 7]."""
+    check_cuda_f32(bbox_pred, "bbox_pred", ndim=4)
+    bbox_pred = bbox_pred.contiguous()
+    A = base_anchors.shape[0]
+    D, H, W = bbox_pred.shape[1:]
+    n = idx.numel()
+    out = torch.empty((n, 7), dtype=torch.float32, device=bbox_pred.device)
+    base = np.ascontiguousarray(base_anchors.detach().cpu().numpy(), dtype=np.float32)
+    m = np.asarray(means, dtype=np.float32)
+    s = np.asarray(stds, dtype=np.float32)
+    if img_shape is None:
+        ih = iw = idp = 0.0
+    else:
+        ih, iw, idp = float(img_shape[0]), float(img_shape[1]), float(img_shape[3])  # (H, W, 3, D)
+    with torch.cuda.device(bbox_pred.device):
+        _lib.check(_lib.lib.roi3d_decode_proposals(bbox_pred.data_ptr(), A, D, H, W, float(stride),
+                                                   float(depth_stride), base.ctypes.data, idx.data_ptr(),
+                                                   None if scores is None else scores.data_ptr(), n,
+                                                   m.ctypes.data, s.ctypes.data, ih, iw, idp, out.data_ptr(),
+                                                   stream_ptr()))
+    return out
+
+
+class RPNProposal3D(object):
+    """The proposal half of RPNHead3D/AnchorHead3D (anchor_head_3d.py:27-70 constructor keys)."""
+
+    def __init__(self, anchor_scales=(8,), anchor_depth_scales=(2,), anchor_ratios=(1.0,),
+                 anchor_strides=(4, 8, 16, 32, 64), anchor_strides_depth=(2, 4, 8, 16, 32),
+                 anchor_base_sizes=None, anchor_base_depths=None, target_means=(.0, .0, .0, .0, .0, .0),
+                 target_stds=(1.0, 1.0, 1.0, 1.0, 1.0, 1.0), use_sigmoid_cls=True):
+        self.anchor_strides = list(anchor_strides)
+        self.anchor_strides_depth = list(anchor_strides_depth)
+        self.anchor_base_sizes = list(anchor_strides) if anchor_base_sizes is None else list(anchor_base_sizes)
+        self.anchor_base_depths = (list(anchor_strides_depth) if anchor_base_depths is None
+                                   else list(anchor_base_depths))
+        self.target_means = tuple(target_means)
+        self.target_stds = tuple(target_stds)
+        self.use_sigmoid_cls = use_sigmoid_cls
+        if not use_sigmoid_cls:
+            raise NotImplementedError("softmax RPN scores are not used by configs/3d-multi-resolution-rcnn.py")
+        self.anchor_generators = [
+            AnchorGenerator3D(b, list(anchor_scales), list(anchor_depth_scales), list(anchor_ratios), d)
+            for b, d in zip(self.anchor_base_sizes, self.anchor_base_depths)
+        ]
+        self.num_anchors = len(anchor_ratios) * len(anchor_scales)
+
+    def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg, rescale=False, return_anchors=False):
+        """cls_scores[l]: [B, A, D, H, W]; bbox_preds[l]: [B, 6A, D, H, W]; img_metas[b]['img_shape'] = (H, W, 3, D).
+        Returns the list of per-image proposals (and per-image selected anchors when return_anchors)."""
+        assert len(cls_scores) == len(bbox_preds)
+        nms_pre = int(_cfg_get(cfg, 'nms_pre'))
+        nms_post = int(_cfg_get(cfg, 'nms_post'))
+        max_num = int(_cfg_get(cfg, 'max_num'))
+        nms_thr = float(_cfg_get(cfg, 'nms_thr'))
+        if _cfg_get(cfg, 'min_bbox_size', 0) > 0:
+            raise NotImplementedError("min_bbox_size > 0 is broken in the reference (rpn_head_3d.py:125-132)")
+        if _cfg_get(cfg, 'nms_across_levels', False):
+            raise NotImplementedError("nms_across_levels=True is not used by the 3D config")
+        L, B = len(cls_scores), len(img_metas)
+        dev = cls_scores[0].device
+        A = self.num_anchors
+
+        # 1. top-k of sigmoid(score) per (image, level) segment, all in one pass set
+        segs, seg_meta = [], []
+        for b in range(B):
+            for l in range(L):
+                s = cls_scores[l][b].detach()
+                assert s.shape[0] == A, "cls_score channels must equal num_anchors"
+                segs.append(s)
+                seg_meta.append((b, l))
+        k = nms_pre if nms_pre > 0 else max(s.numel() for s in segs)
+        k = min(k, max(s.numel() for s in segs))
+        idx, val = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True)
+
+        # 2. decode the selected anchors, per segment (the kernel is tiny; one launch per segment)
+        dets = torch.empty((B * L, k, 7), dtype=torch.float32, device=dev)
+        counts = []
+        for sid, (b, l) in enumerate(seg_meta):
+            img_shape = img_metas[b]['img_shape']
+            dets[sid] = decode_proposals(bbox_preds[l][b].detach(), self.anchor_generators[l].base_anchors,
+                                         self.anchor_strides[l], self.anchor_strides_depth[l], idx[sid], val[sid],
+                                         self.target_means, self.target_stds, img_shape)
+            counts.append(min(k, segs[sid].numel()))
+        seg_counts = torch.tensor(counts, dtype=torch.int32, device=dev)
+
+        # 3. one batched NMS; kept rows in descending-score order
+        _keep, keep_s, num_keep = nms3d_batched(dets, seg_counts, nms_thr, want_score_order=True)
+
+        # 4. proposals[:nms_post] per segment (rpn_head_3d.py:135), then per image cat + topk(max_num) (:139-148)
+        P = min(nms_post, k)
+        take = keep_s[:, :P].clamp_(min=0, max=k - 1)
+        valid = torch.arange(P, device=dev)[None, :] < num_keep[:, None].clamp(max=P)
+        props = torch.gather(dets, 1, take[:, :, None].expand(-1, -1, 7))          # [B*L, P, 7]
+        cat_scores = torch.where(valid, props[:, :, 6], props.new_full((), float('-inf')))
+        props = props.view(B, L * P, 7)
+        cat_scores = cat_scores.view(B, L * P)
+        n_valid = valid.view(B, L * P).sum(dim=1)
+        # compact valid rows to the front of each image (stable) so indices match the reference's cat order
+        order = torch.sort((~valid.view(B, L * P)).to(torch.uint8), dim=1, stable=True)[1]
+        props = torch.gather(props, 1, order[:, :, None].expand(-1, -1, 7))
+        cat_scores = torch.gather(cat_scores, 1, order)
+        kk = min(max_num, L * P)
+        fidx, _ = topk_segmented([cat_scores[b] for b in range(B)], kk, apply_sigmoid=False)
+        final = torch.gather(props, 1, fidx.clamp(min=0)[:, :, None].expand(-1, -1, 7))  # [B, kk, 7]
+        n_out = n_valid.clamp(max=kk).tolist()  # the single host read of the whole path
+        result = [final[b, :n_out[b]] for b in range(B)]
+        if return_anchors:
+            return result, None
+        return result
+
+    def get_bboxes_single(self, cls_scores, bbox_preds, img_shape, cfg):
+        """One image: cls_scores[l] [A, D, H, W], bbox_preds[l] [6A, D, H, W] (rpn_head_3d.py:72-79)."""
+        out = self.get_bboxes([c[None] for c in cls_scores], [r[None] for r in bbox_preds],
+                              [dict(img_shape=img_shape, scale_factor=1.0)], cfg)
+        return out[0]

@@ -1,0 +1,188 @@
+/*
+ * roi3d_b200.h -- C ABI of libroi3d_b200.so: the B200-native (sm_100a) 3D R-CNN RoI hot path.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one native entry point (or the torch-op
+ * composition) of the reference arthur801031/3d-multi-resolution-rcnn; the reference interface is cited
+ * per function as file:line under /root/reference.  The reference binds its natives with pybind11 over
+ * at::Tensor; here the boundary is plain pointers + sizes + a CUDA stream, so any host (the Python
+ * mirror in 3d-multi-resolution-rcnn_b200/roi3d_b200, ctypes, cffi, C++) can bind it.  INTEGRATION.md
+ * shows the stub a reference maintainer adds to mmdet/ops.
+ *
+ * Conventions
+ *   - Every `const float*`/`float*` named *_dev is a DEVICE pointer on the current CUDA device; entry
+ *     points ending in `_host` take HOST pointers and do their own H2D/D2H.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All device entry
+ *     points are asynchronous on that stream and never synchronise the host.
+ *   - Return value: 0 on success, a negative ROI3D_E* code on failure; roi3d_last_error() returns a
+ *     thread-local message.  Nothing prints, nothing calls exit() (the reference does both:
+ *     roi_align_cuda.cpp:80-83, roi_align_kernel.cu:679-682).
+ *   - Boxes are (x1,y1,x2,y2,z1,z2) in input-image pixels with the +1 size convention
+ *     (nms_kernel.cu:23-33); RoIs are (batch_idx, x1,y1,x2,y2,z1,z2) fp32 (roi_align_kernel.cu:231-238).
+ *   - Feature layout: ROI3D_NCDHW is the reference's contiguous [B,C,D,H,W]; ROI3D_NDHWC is the same
+ *     logical tensor stored channels-last ([B,D,H,W,C] in memory, torch.channels_last_3d), which is
+ *     what the kernels read natively with channel-contiguous vector loads.
+ */
+#ifndef ROI3D_B200_H_
+#define ROI3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROI3D_ABI_VERSION 1
+
+#define ROI3D_NCDHW 0
+#define ROI3D_NDHWC 1
+
+#define ROI3D_OK 0
+#define ROI3D_EINVAL (-1)  /* bad argument (shape, alignment, unsupported size) */
+#define ROI3D_ECUDA (-2)   /* CUDA runtime / launch error */
+#define ROI3D_ENOMEM (-3)  /* workspace too small / allocation failed */
+
+#define ROI3D_MAX_LEVELS 8
+
+int roi3d_abi_version(void);
+const char *roi3d_last_error(void);
+/* SM count / name of the current device (for grid sizing in the host mirror and for bench.py). */
+int roi3d_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * One FPN level as the RoI extractor sees it.
+ * Replaces: the (features, spatial_scale, spatial_scale_depth) triple held by each RoIAlign3D module,
+ * mmdet/ops/roi_align/modules/roi_align_3d.py:7-18, built per stride pair in
+ * mmdet/models/roi_extractors/single_level.py:45-56.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct roi3d_level {
+  const float *feats_dev; /* forward input; may be NULL for backward-only calls */
+  float *grad_dev;        /* backward output (same shape/layout as feats), accumulated into */
+  int32_t layout;         /* ROI3D_NCDHW or ROI3D_NDHWC */
+  int32_t D, H, W;
+  float spatial_scale;       /* 1/stride      (x,y) */
+  float spatial_scale_depth; /* 1/depth_stride (z)  */
+} roi3d_level_t;
+
+/* ------------------------------------------------------------------------------------------------
+ * RoIAlign3D forward.
+ * Replaces: roi_align_cuda.forward3d -> roi_align_forward_cuda_3d -> ROIAlignForwardLaucher3D,
+ *   mmdet/ops/roi_align/src/roi_align_cuda.cpp:68-94, roi_align_kernel.cu:316-337 (kernel :214-291).
+ * out_dev: [K, C, PD, PH, PW] contiguous, fully overwritten (no pre-zeroing needed, unlike
+ *   functions/roi_align_3d.py:32).  feats: [B,C,D,H,W] in `layout`.
+ * ---------------------------------------------------------------------------------------------- */
+int roi3d_roi_align3d_forward(const float *feats_dev, int layout, int B, int C, int D, int H, int W,
+                              const float *rois_dev, int K, int PD, int PH, int PW, float spatial_scale,
+                              float spatial_scale_depth, int sample_num, float *out_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RoIAlign3D backward.
+ * Replaces: roi_align_cuda.backward3d -> ROIAlignBackwardLaucher3D,
+ *   roi_align_cuda.cpp:123-150, roi_align_kernel.cu:666-692 (kernel :519-636).
+ * grad_in_dev [B,C,D,H,W] in `layout` is ACCUMULATED into (caller zero-fills, as
+ *   functions/roi_align_3d.py:84 does); pass zero_fill=1 to have the library clear it first.
+ * bug_compat=1 reproduces the reference's top_diff index for non-cubic outputs
+ *   (roi_align_kernel.cu:554-555); default 0 = the mathematically correct gradient.
+ * ---------------------------------------------------------------------------------------------- */
+int roi3d_roi_align3d_backward(const float *grad_out_dev, const float *rois_dev, int K, int PD, int PH, int PW,
+                               float spatial_scale, float spatial_scale_depth, int sample_num,
+                               float *grad_in_dev, int layout, int B, int C, int D, int H, int W,
+                               int zero_fill, int bug_compat, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FPN level mapping.
+ * Replaces: SingleRoIExtractor.map_roi_levels, mmdet/models/roi_extractors/single_level.py:58-82
+ *   (about 8 torch elementwise launches).  lvls_dev: int64[K].
+ * ---------------------------------------------------------------------------------------------- */
+int roi3d_map_roi_levels(const float *rois_dev, int K, int num_levels, float finest_scale, int64_t *lvls_dev,
+                         void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-level RoI extractor, forward and backward: level mapping + per-level RoIAlign3D +
+ * scatter into one [K,C,PD,PH,PW] tensor in ONE launch, no host sync.
+ * Replaces: SingleRoIExtractor.forward, single_level.py:84-104 (per-level mask, .any() sync,
+ *   boolean-index gather, RoIAlign3D launch, index-add), and its autograd backward.
+ * All levels share B and C.  lvls_out_dev may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int roi3d_extract_forward(const roi3d_level_t *levels, int num_levels, int B, int C, const float *rois_dev,
+                          int K, int PD, int PH, int PW, int sample_num, float finest_scale, float *out_dev,
+                          int64_t *lvls_out_dev, void *stream);
+int roi3d_extract_backward(const roi3d_level_t *levels, int num_levels, int B, int C, const float *rois_dev,
+                           int K, int PD, int PH, int PW, int sample_num, float finest_scale,
+                           const float *grad_out_dev, int zero_fill, int bug_compat, void *stream);
+
+/* Layout conversion of one level, [B,C,D,H,W] <-> channels-last; used by the host mirror when a caller
+ * hands the reference's NCDHW-contiguous tensors to the channels-last kernels. */
+int roi3d_ncdhw_to_ndhwc(const float *src_dev, float *dst_dev, int B, int C, int D, int H, int W, void *stream);
+int roi3d_ndhwc_to_ncdhw(const float *src_dev, float *dst_dev, int B, int C, int D, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3D IoU NMS, batched over independent segments (one segment = one (volume, level) or one class).
+ * Replaces: nms_cuda.nms_3d -> nms_cuda_3d, mmdet/ops/nms/src/nms_cuda.cpp:16-21,
+ *   nms_kernel.cu:196-257 (kernel :81-129): device sort, 64x64 IoU bitmask, blocking D2H copy of
+ *   the mask and a host sweep.  Here the order, the mask (upper triangle only) and the sweep all run
+ *   on the device.
+ * dets_dev: [nseg, n_max, 7] fp32 (x1,y1,x2,y2,z1,z2,score); segment s uses its first
+ *   seg_counts_dev[s] rows (seg_counts_dev == NULL: every segment has n_max rows).
+ * keep_dev: int64 [nseg, n_max]: kept ORIGINAL row indices, ascending (nms_kernel.cu:253-256).
+ * keep_by_score_dev (optional, may be NULL): the same indices in descending-score order
+ *   (what `dets[inds][:nms_post]` needs when the input was already score-sorted).
+ * num_keep_dev: int32 [nseg].
+ * Order rule for equal scores: lower original index first.
+ * ---------------------------------------------------------------------------------------------- */
+size_t roi3d_nms3d_workspace_bytes(int nseg, int n_max);
+int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max,
+                        float iou_thr, int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev,
+                        void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Host-buffer form of one NMS call: what mmdet.ops.nms(dets_numpy, thr, device_id) does
+ * (mmdet/ops/nms/nms_wrapper.py:29-32,42-52).  keep_host capacity n; returns count in *num_keep_host. */
+int roi3d_nms3d_host(const float *dets_host, int n, float iou_thr, int64_t *keep_host, int32_t *num_keep_host);
+
+/* Experiment knob (not part of the reference surface): key 0 = forward kernel variant, 1 = backward
+ * kernel variant; value 0 = auto, 1/2 = alternative register tilings, 99 = literal (reference-order) path. */
+int roi3d_set_tuning(int key, int value);
+
+/* Host-buffer form of RoIAlign3D forward (H2D feats+rois, kernel, D2H out): the e2e path bench.py times. */
+int roi3d_roi_align3d_forward_host(const float *feats_host, int layout, int B, int C, int D, int H, int W,
+                                   const float *rois_host, int K, int PD, int PH, int PW, float spatial_scale,
+                                   float spatial_scale_depth, int sample_num, float *out_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * RPN proposal path pieces (RPNHead3D.get_bboxes_single,
+ * mmdet/models/anchor_heads/rpn_head_3d.py:72-149).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Segmented top-k by radix select: for each segment s (n_s = seg_len[s] scores starting at
+ * scores_dev + seg_off[s]) the k_s = min(k, n_s) largest, DESCENDING, ties -> lower index.
+ * Replaces: scores.topk(cfg.nms_pre), rpn_head_3d.py:108-112, and the final topk :147.
+ * apply_sigmoid=1 ranks sigmoid(x) = 1/(1+exp(-x)) (rpn_head_3d.py:90) and returns those values.
+ * seg_off/seg_len are HOST arrays (int64) of length nseg.
+ * seg_adhw (HOST int32 [nseg,4] = A,D,H,W, or NULL): when given (A>0), segment s is an [A,D,H,W] score map
+ *   and indices are LOGICAL positions after permute(2,3,1,0).reshape(-1) (rpn_head_3d.py:87-89), i.e.
+ *   ((y*W + x)*D + z)*A + a -- the order grid_anchors enumerates anchors in -- both for the returned index
+ *   and for the tie rule; memory is still read in its native order.
+ * out_idx_dev: int64 [nseg, k] (index within the segment); out_val_dev: fp32 [nseg, k];
+ * rows beyond k_s are filled with -1 / 0. */
+size_t roi3d_topk_workspace_bytes(int nseg, int k);
+int roi3d_topk_segmented(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
+                         const int32_t *seg_adhw, int nseg, int k, int apply_sigmoid, int64_t *out_idx_dev,
+                         float *out_val_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Anchor base + decode of selected anchors for one level, fused:
+ *   anchors as AnchorGenerator3D.grid_anchors would generate them
+ *   (mmdet/core/anchor/anchor_generator_3d.py:56-71: flat index = ((y*W + x)*D + z)*A + a),
+ *   deltas gathered from bbox_pred [6A, D, H, W] as permute(2,3,1,0).reshape(-1,6) would
+ *   (rpn_head_3d.py:94), then delta2bbox3D (mmdet/core/bbox/transforms.py:105-160) with the
+ *   img_shape clamp, and the score appended (rpn_head_3d.py:133).
+ * idx_dev: int64[n] flat anchor indices (e.g. from roi3d_topk_segmented); -1 entries produce a zero row.
+ * base_anchors_host: [A,6] fp32 HOST.  out_dev: [n,7]. */
+int roi3d_decode_proposals(const float *bbox_pred_dev, int A, int D, int H, int W, float stride,
+                           float depth_stride, const float *base_anchors_host, const int64_t *idx_dev,
+                           const float *scores_dev, int n, const float *means6_host, const float *stds6_host,
+                           float img_h, float img_w, float img_d, float *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROI3D_B200_H_ */

@@ -1,0 +1,414 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libroi3d_b200.so via the Python host mirror) and is compared with the CPU oracle on the same seeded inputs;
+where oracle/_ref is present the reference's OWN kernels are run beside it, which pins the oracle.
+
+Tolerances (BASELINE.json north_star): NMS keep lists bit-exact; RoIAlign forward 1e-5, backward 1e-4,
+measured as max|a-b| / max(1, max|ref|)  (norm-relative: pure elementwise relative error is ill-conditioned on
+zero-mean data)."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-5
+BWD_TOL = 1e-4
+
+
+def rel_err(a, ref):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(a - ref).max() / max(1.0, np.abs(ref).max())) if a.size else 0.0
+
+
+def cl(x):
+    return x.contiguous(memory_format=torch.channels_last_3d)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------ NMS
+@pytest.mark.parametrize("n,thr", [(1, 0.5), (2, 0.5), (63, 0.7), (64, 0.7), (65, 0.3), (300, 0.5), (2000, 0.7),
+                                   (2000, 0.1), (4097, 0.7)])
+def test_nms_keep_bit_exact(oracle, dev, n, thr):
+    from roi3d_b200.ops import nms
+    dets = synth.c1_boxes(n, seed=n)
+    want = oracle.nms3d(dets, thr)
+    t = torch.from_numpy(dets).to(dev)
+    kept, inds = nms(t, thr)
+    assert inds.dtype == torch.int64 and inds.device == t.device
+    assert np.array_equal(inds.cpu().numpy(), want)
+    assert torch.equal(kept, t[inds])
+    # numpy + device_id form (host-buffer C ABI entry)
+    kept_np, inds_np = nms(dets, thr, device_id=0)
+    assert isinstance(inds_np, np.ndarray) and np.array_equal(inds_np, want)
+    assert np.array_equal(kept_np, dets[want])
+
+
+def test_nms_ties_and_duplicates(oracle, dev):
+    from roi3d_b200.ops import nms
+    dets = synth.c1_boxes(500, seed=11)
+    dets[:, 6] = np.round(dets[:, 6] * 8) / 8          # many equal scores
+    dets[100:200, :6] = dets[0:100, :6]                # exact duplicate boxes
+    want = oracle.nms3d(dets, 0.5)
+    _, inds = nms(torch.from_numpy(dets).to(dev), 0.5)
+    assert np.array_equal(inds.cpu().numpy(), want)
+
+
+def test_nms_batched_segments(oracle, dev):
+    from roi3d_b200.ops import nms3d_batched
+    sizes = [0, 1, 64, 130, 700, 2000]
+    n_max = 2000
+    dets = np.zeros((len(sizes), n_max, 7), np.float32)
+    for s, n in enumerate(sizes):
+        dets[s, :n] = synth.c1_boxes(n, seed=100 + s) if n else 0
+    cnt = torch.tensor(sizes, dtype=torch.int32, device=dev)
+    keep, keep_s, num = nms3d_batched(torch.from_numpy(dets).to(dev), cnt, 0.7)
+    num = num.cpu().numpy()
+    for s, n in enumerate(sizes):
+        want, want_s = oracle.nms3d(dets[s, :n], 0.7, return_score_order=True)
+        assert num[s] == len(want)
+        assert np.array_equal(keep[s, :num[s]].cpu().numpy(), want)
+        assert np.array_equal(keep_s[s, :num[s]].cpu().numpy(), want_s)
+
+
+def test_nms_against_reference_kernel(oracle, ref_ops, dev):
+    """Pins the oracle: the reference's own nms_cuda_3d (oracle/_ref) on the same boxes."""
+    if "nms_cuda" not in ref_ops:
+        pytest.skip("oracle/_ref not built: %s" % ref_ops.get("error"))
+    from roi3d_b200.ops import nms
+    for n, thr, seed in [(2000, 0.7, 0), (2000, 0.3, 1), (777, 0.5, 2)]:
+        dets = synth.c1_boxes(n, seed=seed)
+        t = torch.from_numpy(dets).to(dev)
+        ref = ref_ops["nms_cuda"].nms_3d(t, thr).cpu().numpy()
+        assert np.array_equal(ref, oracle.nms3d(dets, thr)), "oracle disagrees with the reference kernel"
+        assert np.array_equal(nms(t, thr)[1].cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------------- RoIAlign
+def _feats(shape, seed):
+    return np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+
+
+CASES = [
+    # (B, C, D, H, W), out_size, out_size_depth, scale, scale_d, sample_num, n_rois
+    ((1, 64, 10, 32, 32), 7, 7, 0.25, 0.5, 2, 24),
+    ((2, 32, 9, 14, 15), 7, 3, 0.25, 0.5, 2, 16),       # real-config bbox shape 7x7x3
+    ((1, 40, 12, 20, 20), 14, 14, 0.25, 0.5, 2, 12),    # C not a multiple of 32*CV
+    ((2, 64, 8, 16, 16), 14, 10, 0.125, 0.25, 2, 10),   # real-config mask shape 14x14x10
+    ((1, 6, 10, 16, 16), 7, 7, 0.25, 0.5, 0, 10),       # adaptive sampling, odd channel count
+    ((1, 16, 6, 12, 12), 5, 4, 0.25, 0.5, 2, 8),        # generic output size
+    ((1, 8, 20, 60, 60), 7, 7, 1.0, 1.0, 2, 6),         # footprint larger than the tables -> literal path
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("layout", ["channels_last", "contiguous"])
+def test_roi_align_forward(oracle, dev, case, layout):
+    from roi3d_b200.ops import RoIAlign3D
+    shape, ps, pdp, sc, scd, sn, k = case
+    B, C, D, H, W = shape
+    f = _feats(shape, 1)
+    img = (int(W / sc), int(H / sc), int(D / scd))
+    rois = np.concatenate([synth.c2_rois(k, seed=2, img=img, batch=B),
+                           synth.adversarial_rois((D, H, W), sc, scd, batch=B)], 0)
+    if sn == 0:  # adaptive sampling of a zero-size RoI is 0/0 in the reference; checked separately
+        ok = (rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2]) & (rois[:, 6] >= rois[:, 5])
+        rois = rois[ok]
+    want = oracle.roi_align3d_forward(f, rois, ps, pdp, sc, scd, sn)
+    ft = torch.from_numpy(f).to(dev)
+    if layout == "channels_last":
+        ft = cl(ft)
+    out = RoIAlign3D(ps, pdp, sc, scd, sn)(ft, torch.from_numpy(rois).to(dev))
+    assert out.shape == want.shape and out.is_contiguous()
+    assert rel_err(out.cpu().numpy(), want) <= FWD_TOL
+
+
+def test_roi_align_forward_literal_path_is_bit_exact(oracle, dev):
+    """Variant 99 evaluates the reference's sample loops literally: identical bits to oracle(contract=1)."""
+    import roi3d_b200
+    from roi3d_b200.ops import RoIAlign3D
+    f = _feats((1, 32, 10, 24, 24), 3)
+    rois = synth.c2_rois(20, seed=4, img=(96, 96, 20))
+    want = oracle.roi_align3d_forward(f, rois, 7, 7, 0.25, 0.5, 2)
+    roi3d_b200._lib.set_tuning(0, 99)
+    try:
+        out = RoIAlign3D(7, 7, 0.25, 0.5, 2)(cl(torch.from_numpy(f).to(dev)), torch.from_numpy(rois).to(dev))
+    finally:
+        roi3d_b200._lib.set_tuning(0, 0)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_roi_align_adaptive_zero_size_is_nan_like_reference(oracle, dev):
+    from roi3d_b200.ops import RoIAlign3D
+    f = _feats((1, 32, 6, 8, 8), 5)
+    rois = np.array([[0, 10, 10, 9, 9, 4, 3]], np.float32)
+    want = oracle.roi_align3d_forward(f, rois, 7, 7, 0.25, 0.5, 0)
+    out = RoIAlign3D(7, 7, 0.25, 0.5, 0)(cl(torch.from_numpy(f).to(dev)), torch.from_numpy(rois).to(dev))
+    assert np.isnan(want).all() and torch.isnan(out).all()
+
+
+def test_roi_align_empty_rois(dev):
+    from roi3d_b200.ops import RoIAlign3D
+    f = torch.zeros(1, 32, 4, 8, 8, device=dev)
+    out = RoIAlign3D(7, 3, 0.25, 0.5, 2)(f, torch.zeros(0, 7, device=dev))
+    assert out.shape == (0, 32, 3, 7, 7)
+
+
+@pytest.mark.parametrize("case", CASES[:6])
+@pytest.mark.parametrize("layout", ["channels_last", "contiguous"])
+def test_roi_align_backward(oracle, dev, case, layout):
+    from roi3d_b200.ops import RoIAlign3D
+    shape, ps, pdp, sc, scd, sn, k = case
+    B, C, D, H, W = shape
+    img = (int(W / sc), int(H / sc), int(D / scd))
+    rois = np.concatenate([synth.c2_rois(k, seed=2, img=img, batch=B),
+                           synth.adversarial_rois((D, H, W), sc, scd, batch=B)], 0)
+    ok = (rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2]) & (rois[:, 6] >= rois[:, 5])
+    rois = rois[ok] if sn == 0 else rois
+    g = _feats((rois.shape[0], C, pdp, ps, ps), 6)
+    want = oracle.roi_align3d_backward(g, rois, shape, sc, scd, sn)
+    ft = torch.from_numpy(_feats(shape, 1)).to(dev)
+    if layout == "channels_last":
+        ft = cl(ft)
+    ft.requires_grad_(True)
+    out = RoIAlign3D(ps, pdp, sc, scd, sn)(ft, torch.from_numpy(rois).to(dev))
+    out.backward(torch.from_numpy(g).to(dev))
+    assert ft.grad.shape == tuple(shape)
+    assert rel_err(ft.grad.cpu().numpy(), want) <= BWD_TOL
+
+
+def test_roi_align_backward_bug_compat(oracle, dev):
+    from roi3d_b200.ops import RoIAlign3D, set_bug_compat
+    shape = (1, 32, 9, 15, 15)
+    rois = synth.c2_rois(6, seed=5, img=(60, 60, 18))
+    g = _feats((6, 32, 3, 7, 7), 7)
+    want = oracle.roi_align3d_backward(g, rois, shape, 0.25, 0.5, 2, bug_compat=True)
+    ft = cl(torch.zeros(shape, device=dev)).requires_grad_(True)
+    set_bug_compat(True)
+    try:
+        RoIAlign3D(7, 3, 0.25, 0.5, 2)(ft, torch.from_numpy(rois).to(dev)).backward(torch.from_numpy(g).to(dev))
+    finally:
+        set_bug_compat(False)
+    assert rel_err(ft.grad.cpu().numpy(), want) <= BWD_TOL
+
+
+def test_roi_align_against_reference_kernels(oracle, ref_ops, dev):
+    """Pins the oracle: the reference's own forward3d / backward3d (oracle/_ref) on the same inputs."""
+    if "roi_align_cuda" not in ref_ops:
+        pytest.skip("oracle/_ref not built: %s" % ref_ops.get("error"))
+    from roi3d_b200.ops import RoIAlign3D
+    ra = ref_ops["roi_align_cuda"]
+    shape = (2, 64, 10, 32, 32)
+    f = _feats(shape, 8)
+    rois = np.concatenate([synth.c2_rois(40, seed=9, img=(128, 128, 20), batch=2),
+                           synth.adversarial_rois((10, 32, 32), 0.25, 0.5, batch=2)], 0)
+    ft, rt = torch.from_numpy(f).to(dev), torch.from_numpy(rois).to(dev)
+    for (ps, pdp) in [(7, 7), (14, 14)]:
+        ref_out = torch.zeros(rois.shape[0], 64, pdp, ps, ps, device=dev)
+        ra.forward3d(ft, rt, pdp, ps, ps, 0.25, 0.5, 2, ref_out)
+        torch.cuda.synchronize()
+        want = oracle.roi_align3d_forward(f, rois, ps, pdp, 0.25, 0.5, 2)
+        assert np.array_equal(ref_out.cpu().numpy(), want), "oracle(contract=1) is not bit-identical to the reference"
+        x = cl(ft.clone()).requires_grad_(True)
+        out = RoIAlign3D(ps, pdp, 0.25, 0.5, 2)(x, rt)
+        assert rel_err(out.detach().cpu().numpy(), ref_out.cpu().numpy()) <= FWD_TOL
+        g = torch.from_numpy(_feats(tuple(out.shape), 10)).to(dev)
+        ref_grad = torch.zeros(shape, device=dev)
+        ra.backward3d(g, rt, pdp, ps, ps, 0.25, 0.5, 2, ref_grad)
+        torch.cuda.synchronize()
+        out.backward(g)
+        assert rel_err(x.grad.cpu().numpy(), ref_grad.cpu().numpy()) <= BWD_TOL
+        assert rel_err(oracle.roi_align3d_backward(g.cpu().numpy(), rois, shape, 0.25, 0.5, 2),
+                       ref_grad.cpu().numpy()) <= BWD_TOL
+
+
+# ------------------------------------------------------------------------------- extractor / levels
+def test_map_roi_levels_matches_oracle_and_torch(oracle, dev):
+    from roi3d_b200 import SingleRoIExtractor
+    ex = SingleRoIExtractor(dict(type='RoIAlign3D', out_size=7, out_size_depth=7, sample_num=2), 32,
+                            [4, 8, 16, 32], [2, 4, 8, 16])
+    rois = synth.c3_rois(2000, vols=1, seed=4)
+    # boundary sweep: volumes whose sqrt lands on / next to 56 * 2^k
+    edge = []
+    for k in range(0, 4):
+        s = 56.0 * 2 ** k
+        for dlt in (-2e-3, -1e-4, 0.0, 1e-4, 2e-3):
+            w = np.float32(s * (1 + dlt))
+            edge.append([0, 0, 0, w - 1, w - 1, 0, 0])
+    rois = np.concatenate([rois, np.asarray(edge, np.float32)], 0)
+    rt = torch.from_numpy(rois).to(dev)
+    got = ex.map_roi_levels(rt, 4)
+    assert got.dtype == torch.int64
+    assert np.array_equal(got.cpu().numpy(), oracle.map_roi_levels(rois, 4))
+    # the reference expression evaluated by torch's CUDA elementwise kernels (single_level.py:73-81)
+    scale = torch.sqrt((rt[:, 3] - rt[:, 1] + 1) * (rt[:, 4] - rt[:, 2] + 1) * (rt[:, 6] - rt[:, 5] + 1))
+    ref = torch.floor(torch.log2(scale / 56 + 1e-6)).clamp(min=0, max=3).long()
+    assert torch.equal(got, ref)
+    hist = np.bincount(got.cpu().numpy(), minlength=4)
+    assert (hist > 0).all()
+
+
+def _pyramid(B, C, seed, base=(10, 32, 32), levels=4):
+    feats = []
+    for l in range(levels):
+        shape = (B, C) + tuple(max(1, s >> l) for s in base)
+        feats.append(_feats(shape, seed + l))
+    return feats
+
+
+@pytest.mark.parametrize("ps,pdp", [(7, 7), (14, 10)])
+def test_extractor_forward_backward_multilevel(oracle, dev, ps, pdp):
+    from roi3d_b200 import SingleRoIExtractor
+    B, C = 2, 64
+    strides, dstrides = [4, 8, 16, 32], [2, 4, 8, 16]
+    feats = _pyramid(B, C, 20)
+    rois = synth.c3_rois(60, vols=B, seed=4, img=(128, 128, 20))
+    lv = oracle.map_roi_levels(rois, 4)
+    assert len(np.unique(lv)) >= 3
+    want = np.zeros((rois.shape[0], C, pdp, ps, ps), np.float32)
+    g = _feats(want.shape, 30)
+    want_grads = []
+    for l in range(4):
+        sel = lv == l
+        want[sel] = oracle.roi_align3d_forward(feats[l], rois[sel], ps, pdp, 1 / strides[l], 1 / dstrides[l], 2)
+        want_grads.append(oracle.roi_align3d_backward(g[sel], rois[sel], feats[l].shape, 1 / strides[l],
+                                                      1 / dstrides[l], 2))
+    ex = SingleRoIExtractor(dict(type='RoIAlign3D', out_size=ps, out_size_depth=pdp, sample_num=2), C, strides,
+                            dstrides)
+    ft = [cl(torch.from_numpy(f).to(dev)).requires_grad_(True) for f in feats]
+    out = ex(ft, torch.from_numpy(rois).to(dev))
+    assert rel_err(out.detach().cpu().numpy(), want) <= FWD_TOL
+    out.backward(torch.from_numpy(g).to(dev))
+    for l in range(4):
+        assert rel_err(ft[l].grad.cpu().numpy(), want_grads[l]) <= BWD_TOL
+    # NCDHW-contiguous inputs (the reference's layout) give the same values and contiguous grads
+    ft2 = [torch.from_numpy(f).to(dev).requires_grad_(True) for f in feats]
+    out2 = ex(ft2, torch.from_numpy(rois).to(dev))
+    assert torch.equal(out2, out)
+    out2.backward(torch.from_numpy(g).to(dev))
+    for l in range(4):
+        assert ft2[l].grad.is_contiguous()
+        assert rel_err(ft2[l].grad.cpu().numpy(), want_grads[l]) <= BWD_TOL
+
+
+# -------------------------------------------------------------------------------------- proposal path
+def test_topk_segmented_exact(oracle, dev):
+    from roi3d_b200.models.anchor_heads import topk_segmented
+    rng = np.random.default_rng(40)
+    segs = [rng.standard_normal(n).astype(np.float32) for n in (5, 300, 5000, 70000)]
+    segs.append(np.round(rng.standard_normal(20000) * 4).astype(np.float32) / 4)    # heavy ties
+    segs.append(np.full(3000, 0.25, np.float32))                                     # all equal
+    k = 2000
+    idx, val = topk_segmented([torch.from_numpy(s).to(dev) for s in segs], k)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    for s, seg in enumerate(segs):
+        want = oracle.topk(seg, k)
+        m = len(want)
+        assert np.array_equal(idx[s, :m], want)
+        assert np.array_equal(val[s, :m], seg[want])
+        assert (idx[s, m:] == -1).all()
+
+
+def test_topk_permuted_sigmoid(oracle, dev):
+    from roi3d_b200.models.anchor_heads import topk_segmented
+    rng = np.random.default_rng(41)
+    maps = [2 * rng.standard_normal(s).astype(np.float32) for s in ((1, 8, 16, 16), (3, 4, 6, 5), (1, 2, 3, 3))]
+    maps[1] = np.round(maps[1])   # ties: the tie rule must use LOGICAL (permuted) indices
+    k = 200
+    idx, val = topk_segmented([torch.from_numpy(m).to(dev) for m in maps], k, apply_sigmoid=True,
+                              permute_adhw=True)
+    for s, m in enumerate(maps):
+        t = torch.from_numpy(m).to(dev)
+        flat = t.permute(2, 3, 1, 0).reshape(-1).sigmoid().cpu().numpy()   # rpn_head_3d.py:87-90, on CUDA
+        want = oracle.topk(flat, k)
+        n = len(want)
+        assert np.array_equal(idx[s, :n].cpu().numpy(), want)
+        assert np.array_equal(val[s, :n].cpu().numpy(), flat[want])
+
+
+def test_decode_matches_oracle(oracle, dev):
+    from roi3d_b200 import AnchorGenerator3D
+    from roi3d_b200.models.anchor_heads import decode_proposals
+    rng = np.random.default_rng(42)
+    A, D, H, W = 3, 5, 6, 7
+    gen = AnchorGenerator3D(8, [2, 4, 8], [2, 3, 4], [1.0], 4)
+    assert gen.num_base_anchors == 3
+    reg = (0.5 * rng.standard_normal((6 * A, D, H, W))).astype(np.float32)
+    reg[:, 0, 0, 0] = 50.0          # exercises the ratio clamp
+    n_all = A * D * H * W
+    idx = rng.permutation(n_all)[:150].astype(np.int64)
+    idx[7] = -1
+    sc = rng.uniform(0, 1, 150).astype(np.float32)
+    img_shape = (48, 56, 3, 20)
+    anchors = oracle.grid_anchors(oracle.gen_base_anchors(8, [2, 4, 8], [2, 3, 4], [1.0], 4), (D, H, W), 8, 4)
+    assert np.array_equal(gen.grid_anchors((D, H, W), 8, 4, device=dev).cpu().numpy(), anchors)
+    deltas = np.transpose(reg, (2, 3, 1, 0)).reshape(-1, 6)
+    means, stds = (0.0, 0.1, 0, 0, 0, 0), (1.0, 0.5, 1, 1, 2, 1)
+    sel = np.where(idx >= 0, idx, 0)
+    want = oracle.delta2bbox3d(anchors[sel], deltas[sel], means, stds, img_shape)
+    got = decode_proposals(torch.from_numpy(reg).to(dev), gen.base_anchors, 8, 4, torch.from_numpy(idx).to(dev),
+                           torch.from_numpy(sc).to(dev), means, stds, img_shape).cpu().numpy()
+    ok = idx >= 0
+    assert np.abs(got[ok, :6] - want[ok]).max() <= 1e-3      # expf last-bit differences only (glibc vs CUDA)
+    assert np.array_equal(got[ok, 6], sc[ok]) and np.all(got[~ok] == 0)
+    # against the torch-op form of the reference expression on the same device
+    from roi3d_b200 import delta2bbox3D
+    tw = delta2bbox3D(torch.from_numpy(anchors[sel]).to(dev), torch.from_numpy(deltas[sel]).to(dev), means, stds,
+                      img_shape).cpu().numpy()
+    assert np.abs(got[ok, :6] - tw[ok]).max() <= 1e-4
+
+
+def _rpn_inputs(B, dims, seed):
+    rng = np.random.default_rng(seed)
+    cls = [(2 * rng.standard_normal((B, 1) + d)).astype(np.float32) for d in dims]
+    reg = [(0.1 * rng.standard_normal((B, 6) + d)).astype(np.float32) for d in dims]
+    return cls, reg
+
+
+def test_rpn_get_bboxes_matches_oracle(oracle, dev):
+    from roi3d_b200 import RPNProposal3D
+    B = 2
+    dims = [(8, 16, 16), (4, 8, 8), (2, 4, 4)]
+    strides, dstrides = [4, 8, 16], [2, 4, 8]
+    cls, reg = _rpn_inputs(B, dims, 50)
+    cfg = dict(nms_pre=300, nms_post=100, max_num=150, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
+    head = RPNProposal3D(anchor_scales=[2], anchor_depth_scales=[2], anchor_ratios=[1.0], anchor_strides=strides,
+                         anchor_strides_depth=dstrides)
+    metas = [dict(img_shape=(64, 64, 3, 16), scale_factor=1.0)] * B
+    got = head.get_bboxes([torch.from_numpy(c).to(dev) for c in cls], [torch.from_numpy(r).to(dev) for r in reg],
+                          metas, cfg)
+    assert len(got) == B
+    for b in range(B):
+        anchors = [oracle.grid_anchors(oracle.gen_base_anchors(s, [2], [2], [1.0], ds), d, s, ds)
+                   for d, s, ds in zip(dims, strides, dstrides)]
+        want = oracle.get_bboxes_single([c[b] for c in cls], [r[b] for r in reg], anchors, (64, 64, 3, 16),
+                                        300, 100, 150, 0.7)
+        g = got[b].cpu().numpy()
+        assert g.shape == want.shape
+        assert np.abs(g - want).max() <= 1e-3
+
+
+def test_multiclass_nms_matches_oracle(oracle, dev):
+    from roi3d_b200 import multiclass_nms_3d
+    rng = np.random.default_rng(60)
+    n = 400
+    d = synth.c1_boxes(n, seed=61)
+    s1 = d[:, 6]
+    s2 = rng.permutation(s1)
+    scores = np.stack([1 - s1, s1, s2], 1).astype(np.float32)
+    boxes = np.concatenate([d[:, :6] * 0, d[:, :6], d[:, :6] + 1.5], 1).astype(np.float32)
+    for max_num in (2000, 37):
+        want_b, want_l = oracle.multiclass_nms_3d(boxes, scores, 0.2, 0.5, max_num)
+        got_b, got_l = multiclass_nms_3d(torch.from_numpy(boxes).to(dev), torch.from_numpy(scores).to(dev), 0.2,
+                                         dict(type='nms', iou_thr=0.5), max_num)
+        assert np.array_equal(got_b.cpu().numpy(), want_b)
+        assert np.array_equal(got_l.cpu().numpy(), want_l)
+    got_b, got_l = multiclass_nms_3d(torch.from_numpy(boxes).to(dev), torch.from_numpy(scores).to(dev), 5.0,
+                                     dict(type='nms', iou_thr=0.5), 10)
+    assert got_b.shape == (0, 7) and got_l.shape == (0,)
