@@ -279,6 +279,62 @@ __device__ __forceinline__ void literal_bin_bwd(const Item &it, float *gb, int C
   }
 }
 
+// Literal evaluation of a warp's whole (pd, ph-group) tile, kept out of line so that its register
+// footprint does not inflate the fast kernels that only call it for oversized footprints.
+template <int CV>
+__device__ __noinline__ void literal_tile_fwd(const Item &it, const float *fb, int C, int PD, int PH, int PW,
+                                              int c_base, bool active, float *out) {
+  for (int r = 0; r < it.rows; ++r)
+    for (int pw = 0; pw < PW; ++pw) {
+      float v[CV];
+      literal_bin_fwd<CV>(it, fb, C, it.pd, it.ph0 + r, pw, v);
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < CV; ++c)
+          out[((((long long)it.k * C + c_base + c) * PD + it.pd) * PH + it.ph0 + r) * PW + pw] = v[c];
+      }
+    }
+}
+
+// Epilogue shared by the forward kernels: acc / count -> padded smem tile [bin][33] (lane = channel, no bank
+// conflicts) -> global [channel][bin] in contiguous runs.  The flattened (channel, bin) walk advances by
+// 32 elements per step with incremental offsets only (no division, no inner loop when NB >= 32).
+template <int ROWS, int PW, int CV>
+__device__ __forceinline__ void copy_out_tile(const float (&acc)[ROWS][PW][CV], float count, float *stage, int lane,
+                                              int NB, int chunk, int C, float *out_tile, long long ch_stride) {
+  // The reference divides by the sample count (roi_align_kernel.cu:288).  1/count is exact for the
+  // power-of-two counts of fixed sample_num (2^3 = 8) and within one ulp otherwise; count == 0
+  // (adaptive sampling of an empty RoI) still yields NaN (0 * inf) like the reference's 0/0.
+  const float inv = __frcp_rn(count);
+  const int col_stride = CV * (int)ch_stride;  // global distance between consecutive smem columns (< 2^31: checked)
+#pragma unroll
+  for (int c = 0; c < CV; ++c) {
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw) stage[(r * PW + pw) * 33 + lane] = acc[r][pw][c] * inv;
+    __syncwarp();
+    const int cols = min(32, (C - chunk * 32 * CV - c + CV - 1) / CV);  // columns whose channel is < C
+    const int total = cols * NB;
+    float *dst = out_tile + ((long long)chunk * 32 * CV + c) * ch_stride;
+    if (NB >= 32) {
+      // +32 per step crosses at most one column boundary: predicated fix-up, no inner loop
+      int bin = lane, sidx = lane * 33, goff = lane;
+      for (int idx = lane; idx < total; idx += 32) {
+        __stcs(dst + goff, stage[sidx]);
+        bin += 32, sidx += 32 * 33, goff += 32;
+        if (bin >= NB) bin -= NB, sidx += 1 - NB * 33, goff += col_stride - NB;
+      }
+    } else {
+      for (int idx = lane; idx < total; idx += 32) {
+        const int cl = idx / NB, bin = idx - cl * NB;
+        __stcs(dst + (long long)cl * col_stride + bin, stage[bin * 33 + cl]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward, channels-last, separable.  One warp per (k, chunk, pd, ph-group).
 // ---------------------------------------------------------------------------------------------
@@ -287,8 +343,8 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_cl_kernel(const R
   using TB = Tables<PW>;
   constexpr int PWP = TB::PWP;
   constexpr int STAGE = ROWS * PW * 33;
-  constexpr int WARP_FLOATS = STAGE > TB::FLOATS ? STAGE : TB::FLOATS;
-  extern __shared__ float smem_all[];
+  constexpr int WARP_FLOATS = ((STAGE > TB::FLOATS ? STAGE : TB::FLOATS) + 3) / 4 * 4;  // 16-byte aligned per warp
+  extern __shared__ __align__(16) float smem_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *sm = smem_all + warp * WARP_FLOATS;
   const long long item = (long long)blockIdx.x * kWarps + warp;
@@ -320,24 +376,31 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_cl_kernel(const R
 
   if (it.ok && !T.fits) {
     // footprint larger than the tables: literal evaluation, uncoalesced stores (rare path)
-    for (int r = 0; r < it.rows; ++r)
-      for (int pw = 0; pw < PW; ++pw) {
-        float v[CV];
-        literal_bin_fwd<CV>(it, fb, C, it.pd, it.ph0 + r, pw, v);
-        if (active) {
-#pragma unroll
-          for (int c = 0; c < CV; ++c) {
-            const long long o =
-                ((((long long)it.k * C + c_base + c) * p.PD + it.pd) * p.PH + it.ph0 + r) * PW + pw;
-            p.out[o] = v[c];
-          }
-        }
-      }
+    literal_tile_fwd<CV>(it, fb, C, p.PD, p.PH, PW, c_base, active, p.out);
     return;
   }
 
   if (!T.empty) {
     const int RY = T.ymax - T.ymin + 1;
+    // Per-warp constants of the x-contraction: for every bin pw its first NXU taps as (element
+    // offset from the row start, weight); the index is clamped into the bin's support and the weight
+    // forced to 0 past it, so the row loop below is branch-free.
+    bool long_bins = false;
+    int toff[PW][NXU];
+    float tw[PW][NXU];
+#pragma unroll
+    for (int pw = 0; pw < PW; ++pw) {
+      const int lo = T.xlo[pw];
+      const int n = T.xhi[pw] - lo + 1;
+      const int last = n > 0 ? n - 1 : 0;
+      long_bins |= n > NXU;
+#pragma unroll
+      for (int j = 0; j < NXU; ++j) {
+        const int jj = j < last ? j : last;
+        toff[pw][j] = (lo + jj) * C;
+        tw[pw][j] = j < n ? T.Dx[(lo + jj) * PWP + pw] : 0.0f;
+      }
+    }
     for (int z = T.zmin; z <= T.zmax; ++z) {
       const float wz = T.Dz[z - T.zmin];
       if (wz == 0.0f) continue;
@@ -351,35 +414,40 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_cl_kernel(const R
         }
         if (!any) continue;
         const float *rowp = fb + (((long long)z * it.L.H + (T.ymin + yy)) * it.L.W + T.xmin) * C;
+        // x-contraction of this feature row.  Phase 1: all PW*NXU loads are issued before any is
+        // consumed (independent, branch-free, in flight together); phase 2 (bins wider than NXU
+        // taps; one warp-uniform test) finishes the long bins.
+        float fr[PW][NXU][CV];
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+          for (int j = 0; j < NXU; ++j) ldv<CV>(rowp + toff[pw][j], fr[pw][j]);
         float t1[PW][CV];
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw) {
-          const int lo = T.xlo[pw];
-          const int n = T.xhi[pw] - lo + 1;
-          const float *q = rowp + (long long)lo * C;
-          const float *wq = T.Dx + lo * PWP + pw;
-          float t[CV];
 #pragma unroll
-          for (int c = 0; c < CV; ++c) t[c] = 0.0f;
+          for (int c = 0; c < CV; ++c) t1[pw][c] = tw[pw][0] * fr[pw][0][c];
 #pragma unroll
-          for (int j = 0; j < NXU; ++j) {
-            if (j < n) {
+          for (int j = 1; j < NXU; ++j)
+#pragma unroll
+            for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(tw[pw][j], fr[pw][j][c], t1[pw][c]);
+        }
+        if (long_bins) {
+#pragma unroll
+          for (int pw = 0; pw < PW; ++pw) {
+            const int lo = T.xlo[pw];
+            const int n = T.xhi[pw] - lo + 1;
+            const float *q = rowp + (long long)lo * C;
+            const float *wq = T.Dx + lo * PWP + pw;
+#pragma unroll 1
+            for (int j = NXU; j < n; ++j) {
               float f[CV];
               ldv<CV>(q + (long long)j * C, f);
               const float w = wq[j * PWP];
 #pragma unroll
-              for (int c = 0; c < CV; ++c) t[c] = fmaf(w, f[c], t[c]);
+              for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(w, f[c], t1[pw][c]);
             }
           }
-          for (int j = NXU; j < n; ++j) {
-            float f[CV];
-            ldv<CV>(q + (long long)j * C, f);
-            const float w = wq[j * PWP];
-#pragma unroll
-            for (int c = 0; c < CV; ++c) t[c] = fmaf(w, f[c], t[c]);
-          }
-#pragma unroll
-          for (int c = 0; c < CV; ++c) t1[pw][c] = t[c];
         }
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
@@ -399,23 +467,225 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_cl_kernel(const R
   float *stage = sm;  // aliases the tables: all table reads are done
   const long long out_base = (((long long)it.k * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
   const long long ch_stride = (long long)p.PD * p.PH * PW;
-#pragma unroll
-  for (int c = 0; c < CV; ++c) {
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-      for (int pw = 0; pw < PW; ++pw) stage[(r * PW + pw) * 33 + lane] = __fdiv_rn(acc[r][pw][c], count);
-    __syncwarp();
-    int cl = 0, bin = lane;
-    while (bin >= NB) bin -= NB, ++cl;
-    while (cl < 32) {
-      const int ch = (it.chunk * 32 + cl) * CV + c;
-      if (ch < C) __stcs(p.out + out_base + (long long)ch * ch_stride + bin, stage[bin * 33 + cl]);
-      bin += 32;
-      while (bin >= NB) bin -= NB, ++cl;
-    }
+  copy_out_tile<ROWS, PW, CV>(acc, count, stage, lane, NB, it.chunk, C, p.out + out_base, ch_stride);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward, channels-last, separable, rows staged through a per-warp cp.async ring.
+//
+// Same work split and arithmetic as roi_align3d_fwd_cl_kernel, but the feature rows a warp needs
+// ([xmin..xmax] x 32*CV channels of one (z,y) row) are copied global->shared with 16-byte cp.async
+// (LDGSTS, no register staging) NS-1 rows ahead of the row being contracted.  The loads of the next
+// rows are in flight while the current row is reduced, each voxel of the row is fetched once instead
+// of once per tap, and the register file no longer holds the taps, which raises occupancy.
+// Ring capacity per warp is RXR voxels per row; wider footprints take the literal path.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR>
+__global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_ring_kernel(const RoiParams p) {
+  using TB = Tables<PW>;
+  constexpr int PWP = TB::PWP;
+  constexpr int VOX = 32 * CV;                 // floats per voxel-chunk
+  constexpr int LPV = VOX / 4;                 // lanes (16 B each) per voxel-chunk
+  constexpr int VPI = 32 / LPV;                // voxel-chunks copied per warp instruction
+  constexpr int RING = NS * RXR * VOX;         // floats
+  constexpr int STAGE = ROWS * PW * 33;
+  constexpr int LISTS = 80;                    // ylist[<=40] + zlist[<=32] as bytes, rounded up (floats: 20)
+  constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
+  constexpr int WARP_FLOATS = (TB::FLOATS + LISTS / 4 + RING_OR_STAGE + 3) / 4 * 4;
+  static_assert(LPV <= 32 && VPI >= 1, "voxel chunk wider than a warp copy");
+  extern __shared__ __align__(16) float smem_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *sm = smem_all + warp * WARP_FLOATS;
+  const long long item = (long long)blockIdx.x * kWarps + warp;
+  if (item >= p.total_items) return;  // warp-uniform; no block-level barrier is used below
+
+  const Item it = decode_item(p, item, ROWS);
+  const int C = p.C;
+  if (p.lvls_out != nullptr && it.chunk == 0 && it.pd == 0 && it.ph0 == 0 && lane == 0) p.lvls_out[it.k] = it.lvl;
+
+  int c_base = (it.chunk * 32 + lane) * CV;
+  const bool active = c_base < C;
+  if (!active) c_base = 0;
+  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+  const float *fb_roi = it.L.feats + (long long)(it.ok ? it.b : 0) * vox * C;
+  const float *fb = fb_roi + c_base;
+
+  TB T;
+  T.bind(sm);
+  unsigned char *ylist = reinterpret_cast<unsigned char *>(sm + ((TB::FLOATS + 3) / 4 * 4));
+  unsigned char *zlist = ylist + 40;
+  float *ring = sm + ((TB::FLOATS + 3) / 4 * 4) + LISTS / 4;
+  T.empty = true, T.fits = true;
+  if (it.ok) build_tables<PW>(T, it, lane);
+  const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
+  const int RX = T.xmax - T.xmin + 1;
+  // the 16-byte copies need the chunk to lie inside C and be 16-byte aligned: C % 4 == 0 is checked by
+  // the dispatcher; a partial last chunk (C not a multiple of 32*CV) copies only the lanes inside C.
+
+  if (it.ok && !T.empty && (!T.fits || RX > RXR)) {
+    // footprint larger than the tables / the ring: literal evaluation, uncoalesced stores (rare path)
+    literal_tile_fwd<CV>(it, fb, C, p.PD, p.PH, PW, c_base, active, p.out);
+    return;
   }
+
+  float acc[ROWS][PW][CV];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int w = 0; w < PW; ++w)
+#pragma unroll
+      for (int c = 0; c < CV; ++c) acc[r][w][c] = 0.0f;
+
+  if (!T.empty) {
+    // ---- compact lists of the z slices / y rows that carry weight for this (pd, ph-group) ----
+    const int RY = T.ymax - T.ymin + 1, RZ = T.zmax - T.zmin + 1;
+    int ny = 0, nz = 0;
+    for (int y0 = 0; y0 < RY; y0 += 32) {
+      const int yy = y0 + lane;
+      bool a = false;
+      if (yy < RY) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) a |= T.Dy[yy * 8 + r] != 0.0f;
+      }
+      const unsigned bal = __ballot_sync(FULL, a);
+      if (a) ylist[ny + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)yy;
+      ny += __popc(bal);
+    }
+    {
+      const bool a = lane < RZ && T.Dz[lane] != 0.0f;
+      const unsigned bal = __ballot_sync(FULL, a);
+      if (a) zlist[__popc(bal & ((1u << lane) - 1u))] = (unsigned char)lane;
+      nz = __popc(bal);
+    }
+    __syncwarp();
+    const int nrows = ny * nz;
+
+    // per-warp constants of the x-contraction (see roi_align3d_fwd_cl_kernel)
+    bool long_bins = false;
+    int soff[PW];
+    float tw[PW][NXU];
+    int tj[PW][NXU];
+#pragma unroll
+    for (int pw = 0; pw < PW; ++pw) {
+      const int lo = T.xlo[pw];
+      const int n = T.xhi[pw] - lo + 1;
+      const int last = n > 0 ? n - 1 : 0;
+      long_bins |= n > NXU;
+      soff[pw] = lo * VOX + lane * CV;
+#pragma unroll
+      for (int j = 0; j < NXU; ++j) {
+        const int jj = j < last ? j : last;
+        tj[pw][j] = jj * VOX;
+        tw[pw][j] = j < n ? T.Dx[(lo + jj) * PWP + pw] : 0.0f;
+      }
+    }
+
+    // copy geometry: lane -> (voxel within the instruction, 16-byte piece of the voxel chunk)
+    const int cv_v = lane / LPV, cv_p = lane % LPV;
+    const int ch_piece = it.chunk * VOX + cv_p * 4;          // first channel of this lane's 16 bytes
+    const bool piece_ok = ch_piece + 4 <= C;
+    const int cp_dst = cv_p * 4;
+    // producer cursor (row to prefetch next) walks (zi, yi) incrementally: no division in the loop
+    const long long row_elems = (long long)it.L.W * C;
+    const float *src0 = fb_roi + ((long long)T.ymin * it.L.W + T.xmin) * C + ch_piece;
+    int pz = 0, py = 0, pstage = 0;
+    auto issue = [&]() {
+      const int z = T.zmin + zlist[pz];
+      const int yy = ylist[py];
+      const float *src = src0 + ((long long)z * it.L.H + yy) * row_elems;
+      float *dst = ring + pstage * (RXR * VOX) + cp_dst;
+      if (piece_ok) {
+#pragma unroll 2
+        for (int v = cv_v; v < RX; v += VPI) cp_async16(dst + v * VOX, src + (long long)v * C);
+      }
+      cp_async_commit();
+      if (++py == ny) py = 0, ++pz;
+      if (++pstage == NS) pstage = 0;
+    };
+#pragma unroll
+    for (int r = 0; r < NS - 1; ++r) {
+      if (r < nrows) issue();
+      else cp_async_commit();
+    }
+    int cz = 0, cy = 0, cstage = 0;
+    for (int r = 0; r < nrows; ++r) {
+      cp_async_wait<NS - 2>();
+      __syncwarp();
+      const int zi = zlist[cz], yy = ylist[cy];
+      const float wz = T.Dz[zi];
+      const float *row = ring + cstage * (RXR * VOX);
+      if (++cy == ny) cy = 0, ++cz;
+      if (++cstage == NS) cstage = 0;
+      float t1[PW][CV];
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw) {
+        const float *q = row + soff[pw];
+#pragma unroll
+        for (int c = 0; c < CV; ++c) t1[pw][c] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NXU; ++j) {
+          float f[CV];
+          if constexpr (CV == 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(q + tj[pw][j]);
+            f[0] = t.x, f[1] = t.y, f[2] = t.z, f[3] = t.w;
+          } else if constexpr (CV == 2) {
+            const float2 t = *reinterpret_cast<const float2 *>(q + tj[pw][j]);
+            f[0] = t.x, f[1] = t.y;
+          } else {
+            f[0] = q[tj[pw][j]];
+          }
+#pragma unroll
+          for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(tw[pw][j], f[c], t1[pw][c]);
+        }
+      }
+      if (long_bins) {
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) {
+          const int lo = T.xlo[pw];
+          const int n = T.xhi[pw] - lo + 1;
+          const float *q = row + soff[pw];
+          const float *wq = T.Dx + lo * PWP + pw;
+#pragma unroll 1
+          for (int j = NXU; j < n; ++j) {
+            const float w = wq[j * PWP];
+#pragma unroll
+            for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(w, q[j * VOX + c], t1[pw][c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr) {
+        const float w = wz * T.Dy[yy * 8 + rr];
+        if (w != 0.0f) {
+#pragma unroll
+          for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+            for (int c = 0; c < CV; ++c) acc[rr][pw][c] = fmaf(w, t1[pw][c], acc[rr][pw][c]);
+        }
+      }
+      __syncwarp();
+      if (r + NS - 1 < nrows) issue();
+      else cp_async_commit();
+    }
+    cp_async_wait<0>();
+  }
+
+  // ---- epilogue: divide by the sample count, transpose through smem, stream out ----
+  const int NB = it.rows * PW;
+  float *stage = ring;  // the ring is drained
+  const long long out_base = (((long long)it.k * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
+  const long long ch_stride = (long long)p.PD * p.PH * PW;
+  copy_out_tile<ROWS, PW, CV>(acc, count, stage, lane, NB, it.chunk, C, p.out + out_base, ch_stride);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -427,8 +697,8 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
   using TB = Tables<PW>;
   constexpr int PWP = TB::PWP;
   constexpr int STAGE = ROWS * PW * 33;
-  constexpr int WARP_FLOATS = STAGE > TB::FLOATS ? STAGE : TB::FLOATS;
-  extern __shared__ float smem_all[];
+  constexpr int WARP_FLOATS = ((STAGE > TB::FLOATS ? STAGE : TB::FLOATS) + 3) / 4 * 4;  // 16-byte aligned per warp
+  extern __shared__ __align__(16) float smem_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *sm = smem_all + warp * WARP_FLOATS;
   const long long item = (long long)blockIdx.x * kWarps + warp;
@@ -668,7 +938,7 @@ template <int PW, int ROWS, int CV, int NXU>
 static int launch_fwd(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
   constexpr int STAGE = ROWS * PW * 33;
-  constexpr int WARP_FLOATS = STAGE > TB::FLOATS ? STAGE : TB::FLOATS;
+  constexpr int WARP_FLOATS = ((STAGE > TB::FLOATS ? STAGE : TB::FLOATS) + 3) / 4 * 4;  // 16-byte aligned per warp
   const size_t smem = (size_t)kWarps * WARP_FLOATS * sizeof(float);
   p.nchunk = ceil_div(p.C, 32 * CV);
   p.nphg = ceil_div(p.PH, ROWS);
@@ -682,11 +952,32 @@ static int launch_fwd(RoiParams &p, cudaStream_t st) {
   return ROI3D_OK;
 }
 
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR>
+static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
+  using TB = Tables<PW>;
+  constexpr int VOX = 32 * CV;
+  constexpr int RING = NS * RXR * VOX;
+  constexpr int STAGE = ROWS * PW * 33;
+  constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
+  constexpr int WARP_FLOATS = (TB::FLOATS + 80 / 4 + RING_OR_STAGE + 3) / 4 * 4;
+  const size_t smem = (size_t)kWarps * WARP_FLOATS * sizeof(float);
+  p.nchunk = ceil_div(p.C, 32 * CV);
+  p.nphg = ceil_div(p.PH, ROWS);
+  p.total_items = (long long)p.K * p.nchunk * p.PD * p.nphg;
+  auto kern = roi_align3d_fwd_ring_kernel<PW, ROWS, CV, NXU, NS, RXR>;
+  ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long blocks = ceil_div_ll(p.total_items, kWarps);
+  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
+  kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
 template <int PW, int ROWS, int CV>
 static int launch_bwd(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
   constexpr int STAGE = ROWS * PW * 33;
-  constexpr int WARP_FLOATS = STAGE > TB::FLOATS ? STAGE : TB::FLOATS;
+  constexpr int WARP_FLOATS = ((STAGE > TB::FLOATS ? STAGE : TB::FLOATS) + 3) / 4 * 4;  // 16-byte aligned per warp
   const size_t smem = (size_t)kWarps * WARP_FLOATS * sizeof(float);
   p.nchunk = ceil_div(p.C, 32 * CV);
   p.nphg = ceil_div(p.PH, ROWS);
@@ -734,12 +1025,26 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
     if (cvmax >= 2) return launch_generic<2>(p, true, st);
     return launch_generic<1>(p, true, st);
   }
+  bool ring_ok = p.C % 4 == 0;
+  for (int l = 0; l < p.num_levels; ++l) ring_ok = ring_ok && aligned(p.lv[l].feats, 16);
   if (p.PW == 7) {
+    if (ring_ok && cvmax >= 2) {
+      if (v == 0) return launch_fwd_ring<7, 7, 2, 3, 3, 18>(p, st);
+      if (v == 5) return launch_fwd_ring<7, 7, 2, 3, 4, 18>(p, st);
+      if (v == 6) return launch_fwd_ring<7, 7, 1, 3, 4, 20>(p, st);
+      if (v == 7) return launch_fwd_ring<7, 4, 2, 3, 3, 18>(p, st);
+    }
     if (v == 1 || cvmax == 1) return launch_fwd<7, 7, 1, 3>(p, st);
     if (v == 2 && cvmax >= 4) return launch_fwd<7, 4, 4, 3>(p, st);
     return launch_fwd<7, 7, 2, 3>(p, st);
   }
   if (p.PW == 14) {
+    if (ring_ok && cvmax >= 2) {
+      if (v == 0) return launch_fwd_ring<14, 4, 2, 3, 3, 18>(p, st);
+      if (v == 5) return launch_fwd_ring<14, 4, 2, 3, 4, 18>(p, st);
+      if (v == 6) return launch_fwd_ring<14, 7, 1, 3, 4, 20>(p, st);
+      if (v == 7) return launch_fwd_ring<14, 2, 2, 3, 3, 18>(p, st);
+    }
     if (v == 1 || cvmax == 1) return launch_fwd<14, 7, 1, 3>(p, st);
     if (v == 2 && cvmax >= 4) return launch_fwd<14, 2, 4, 3>(p, st);
     return launch_fwd<14, 4, 2, 3>(p, st);

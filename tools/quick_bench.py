@@ -39,7 +39,13 @@ def timeit(fn, iters=20, warm=3, flush=True):
     return ts[len(ts) // 2], ts[0]
 
 
-res = {}
+class _Res(dict):
+    def __setitem__(self, k, v):
+        print(k, v, flush=True)
+        dict.__setitem__(self, k, v)
+
+
+res = _Res()
 which = sys.argv[1:] or ["c2", "nms", "c3", "ref"]
 
 if "c2" in which:
@@ -47,7 +53,7 @@ if "c2" in which:
     fcl = f.contiguous(memory_format=torch.channels_last_3d)
     rois = torch.from_numpy(synth.c2_rois(512, seed=2)).to(dev)
     layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
-    for v in (0, 1, 2):
+    for v in (0, 5, 6, 7, 3):
         _lib.set_tuning(0, v)
         med, mn = timeit(lambda: layer(fcl, rois))
         res["c2_fwd_cl_v%d_us" % v] = (med, mn)
@@ -144,5 +150,3 @@ if "c3" in which:
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "quick_bench.json"), "w") as fh:
     json.dump(res, fh, indent=1)
-for k, v in res.items():
-    print(k, v)
