@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_ring_kernel(const
   constexpr int VOX = 32 * CV;                 // floats per voxel-chunk
   constexpr int LPV = VOX / 4;                 // lanes (16 B each) per voxel-chunk
   constexpr int VPI = 32 / LPV;                // voxel-chunks copied per warp instruction
-  constexpr int RING = NS * RXR * VOX;         // floats
+  constexpr int STRIDE = (RXR + 2) * VOX;      // floats per ring stage (two zero pad voxels)
+  constexpr int RING = NS * STRIDE;            // floats
   constexpr int STAGE = ROWS * PW * 33;
   constexpr int LISTS = 80;                    // ylist[<=40] + zlist[<=32] as bytes, rounded up (floats: 20)
   constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
@@ -570,46 +571,52 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_ring_kernel(const
     __syncwarp();
     const int nrows = ny * nz;
 
-    // per-warp constants of the x-contraction (see roi_align3d_fwd_cl_kernel)
+    // per-warp constants of the x-contraction: for every bin pw its first NXU taps (weight forced to 0
+    // past the bin's support).  Ring rows carry two zero-filled pad voxels after the RX real ones, so a
+    // zero-weight tap always reads initialised shared memory and tap offsets are compile-time constants.
     bool long_bins = false;
     int soff[PW];
     float tw[PW][NXU];
-    int tj[PW][NXU];
 #pragma unroll
     for (int pw = 0; pw < PW; ++pw) {
       const int lo = T.xlo[pw];
       const int n = T.xhi[pw] - lo + 1;
-      const int last = n > 0 ? n - 1 : 0;
       long_bins |= n > NXU;
       soff[pw] = lo * VOX + lane * CV;
 #pragma unroll
-      for (int j = 0; j < NXU; ++j) {
-        const int jj = j < last ? j : last;
-        tj[pw][j] = jj * VOX;
-        tw[pw][j] = j < n ? T.Dx[(lo + jj) * PWP + pw] : 0.0f;
-      }
+      for (int j = 0; j < NXU; ++j) tw[pw][j] = j < n ? T.Dx[(lo + j) * PWP + pw] : 0.0f;
     }
+    static_assert(NXU <= 3, "pad voxels cover taps lo+1, lo+2 only");
+    for (int sidx = 0; sidx < NS; ++sidx) {
+      float *padp = ring + sidx * STRIDE + RX * VOX;
+      for (int i = lane; i < 2 * VOX; i += 32) padp[i] = 0.0f;
+    }
+    __syncwarp();
 
     // copy geometry: lane -> (voxel within the instruction, 16-byte piece of the voxel chunk)
     const int cv_v = lane / LPV, cv_p = lane % LPV;
     const int ch_piece = it.chunk * VOX + cv_p * 4;          // first channel of this lane's 16 bytes
     const bool piece_ok = ch_piece + 4 <= C;
-    const int cp_dst = cv_p * 4;
-    // producer cursor (row to prefetch next) walks (zi, yi) incrementally: no division in the loop
+    // producer cursor (row to prefetch next): rows are visited y-major, z-minor, so that all z slices of
+    // one y row are contracted along x back to back and the y-stage runs once per y row.
     const long long row_elems = (long long)it.L.W * C;
-    const float *src0 = fb_roi + ((long long)T.ymin * it.L.W + T.xmin) * C + ch_piece;
+    const long long slice_elems = (long long)it.L.H * row_elems;
+    const float *src0 = fb_roi + ((long long)T.zmin * it.L.H + T.ymin) * row_elems + (long long)T.xmin * C + ch_piece +
+                        (long long)cv_v * C;
+    float *dst0 = ring + cv_p * 4 + cv_v * VOX;
     int pz = 0, py = 0, pstage = 0;
     auto issue = [&]() {
-      const int z = T.zmin + zlist[pz];
-      const int yy = ylist[py];
-      const float *src = src0 + ((long long)z * it.L.H + yy) * row_elems;
-      float *dst = ring + pstage * (RXR * VOX) + cp_dst;
+      const float *src = src0 + (long long)zlist[pz] * slice_elems + (long long)ylist[py] * row_elems;
+      float *dst = dst0 + pstage * STRIDE;
       if (piece_ok) {
 #pragma unroll 2
-        for (int v = cv_v; v < RX; v += VPI) cp_async16(dst + v * VOX, src + (long long)v * C);
+        for (int v = cv_v; v < RX; v += VPI) {
+          cp_async16(dst, src);
+          dst += VPI * VOX, src += (long long)VPI * C;
+        }
       }
       cp_async_commit();
-      if (++py == ny) py = 0, ++pz;
+      if (++pz == nz) pz = 0, ++py;
       if (++pstage == NS) pstage = 0;
     };
 #pragma unroll
@@ -617,65 +624,73 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_ring_kernel(const
       if (r < nrows) issue();
       else cp_async_commit();
     }
-    int cz = 0, cy = 0, cstage = 0;
-    for (int r = 0; r < nrows; ++r) {
-      cp_async_wait<NS - 2>();
-      __syncwarp();
-      const int zi = zlist[cz], yy = ylist[cy];
-      const float wz = T.Dz[zi];
-      const float *row = ring + cstage * (RXR * VOX);
-      if (++cy == ny) cy = 0, ++cz;
-      if (++cstage == NS) cstage = 0;
+    int cstage = 0, r = 0;
+    for (int yi = 0; yi < ny; ++yi) {
       float t1[PW][CV];
 #pragma unroll
-      for (int pw = 0; pw < PW; ++pw) {
-        const float *q = row + soff[pw];
+      for (int pw = 0; pw < PW; ++pw)
 #pragma unroll
         for (int c = 0; c < CV; ++c) t1[pw][c] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NXU; ++j) {
-          float f[CV];
-          if constexpr (CV == 4) {
-            const float4 t = *reinterpret_cast<const float4 *>(q + tj[pw][j]);
-            f[0] = t.x, f[1] = t.y, f[2] = t.z, f[3] = t.w;
-          } else if constexpr (CV == 2) {
-            const float2 t = *reinterpret_cast<const float2 *>(q + tj[pw][j]);
-            f[0] = t.x, f[1] = t.y;
-          } else {
-            f[0] = q[tj[pw][j]];
-          }
-#pragma unroll
-          for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(tw[pw][j], f[c], t1[pw][c]);
-        }
-      }
-      if (long_bins) {
+      for (int zi = 0; zi < nz; ++zi, ++r) {
+        cp_async_wait<NS - 2>();
+        __syncwarp();
+        const float wz = T.Dz[zlist[zi]];
+        const float *row = ring + cstage * STRIDE;
+        if (++cstage == NS) cstage = 0;
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw) {
-          const int lo = T.xlo[pw];
-          const int n = T.xhi[pw] - lo + 1;
           const float *q = row + soff[pw];
-          const float *wq = T.Dx + lo * PWP + pw;
-#pragma unroll 1
-          for (int j = NXU; j < n; ++j) {
-            const float w = wq[j * PWP];
+          float tz[CV];
 #pragma unroll
-            for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(w, q[j * VOX + c], t1[pw][c]);
+          for (int j = 0; j < NXU; ++j) {
+            float f[CV];
+            if constexpr (CV == 4) {
+              const float4 t = *reinterpret_cast<const float4 *>(q + j * VOX);
+              f[0] = t.x, f[1] = t.y, f[2] = t.z, f[3] = t.w;
+            } else if constexpr (CV == 2) {
+              const float2 t = *reinterpret_cast<const float2 *>(q + j * VOX);
+              f[0] = t.x, f[1] = t.y;
+            } else {
+              f[0] = q[j * VOX];
+            }
+#pragma unroll
+            for (int c = 0; c < CV; ++c) tz[c] = j == 0 ? tw[pw][0] * f[c] : fmaf(tw[pw][j], f[c], tz[c]);
           }
+          if (long_bins) {
+            const int lo = T.xlo[pw];
+            const int n = T.xhi[pw] - lo + 1;
+            const float *wq = T.Dx + lo * PWP + pw;
+#pragma unroll 1
+            for (int j = NXU; j < n; ++j) {
+              const float w = wq[j * PWP];
+#pragma unroll
+              for (int c = 0; c < CV; ++c) tz[c] = fmaf(w, q[j * VOX + c], tz[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(wz, tz[c], t1[pw][c]);
         }
+        __syncwarp();
+        if (r + NS - 1 < nrows) issue();
+        else cp_async_commit();
+      }
+      // y-stage, once per feature row index y
+      const int yy = ylist[yi];
+      float wy[8];
+      {
+        const float4 a = *reinterpret_cast<const float4 *>(T.Dy + yy * 8);
+        const float4 b4 = *reinterpret_cast<const float4 *>(T.Dy + yy * 8 + 4);
+        wy[0] = a.x, wy[1] = a.y, wy[2] = a.z, wy[3] = a.w, wy[4] = b4.x, wy[5] = b4.y, wy[6] = b4.z, wy[7] = b4.w;
       }
 #pragma unroll
       for (int rr = 0; rr < ROWS; ++rr) {
-        const float w = wz * T.Dy[yy * 8 + rr];
-        if (w != 0.0f) {
+        if (wy[rr] != 0.0f) {
 #pragma unroll
           for (int pw = 0; pw < PW; ++pw)
 #pragma unroll
-            for (int c = 0; c < CV; ++c) acc[rr][pw][c] = fmaf(w, t1[pw][c], acc[rr][pw][c]);
+            for (int c = 0; c < CV; ++c) acc[rr][pw][c] = fmaf(wy[rr], t1[pw][c], acc[rr][pw][c]);
         }
       }
-      __syncwarp();
-      if (r + NS - 1 < nrows) issue();
-      else cp_async_commit();
     }
     cp_async_wait<0>();
   }
@@ -956,7 +971,7 @@ template <int PW, int ROWS, int CV, int NXU, int NS, int RXR>
 static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
   constexpr int VOX = 32 * CV;
-  constexpr int RING = NS * RXR * VOX;
+  constexpr int RING = NS * (RXR + 2) * VOX;
   constexpr int STAGE = ROWS * PW * 33;
   constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
   constexpr int WARP_FLOATS = (TB::FLOATS + 80 / 4 + RING_OR_STAGE + 3) / 4 * 4;

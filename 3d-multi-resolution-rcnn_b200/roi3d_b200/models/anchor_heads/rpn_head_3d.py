@@ -142,6 +142,17 @@ class RPNProposal3D(object):
         k = nms_pre if nms_pre > 0 else max(s.numel() for s in segs)
         k = min(k, max(s.numel() for s in segs))
         idx, val = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True)
+        # The reference only sorts a level when it has MORE than nms_pre anchors (rpn_head_3d.py:96,108-112);
+        # a smaller level reaches NMS in anchor order, and `proposals[:nms_post]` then truncates in that order
+        # (nms returns ascending input indices, nms_kernel.cu:253-256).  Reproduce that: put such segments back
+        # in ascending anchor order and truncate them by original index instead of by score.
+        unsorted = [not (nms_pre > 0 and s.numel() > nms_pre) for s in segs]
+        for sid, flag in enumerate(unsorted):
+            if flag:
+                n = segs[sid].numel()
+                o = torch.argsort(idx[sid, :n])
+                idx[sid, :n] = idx[sid, :n][o]
+                val[sid, :n] = val[sid, :n][o]
 
         # 2. decode the selected anchors, per segment (the kernel is tiny; one launch per segment)
         dets = torch.empty((B * L, k, 7), dtype=torch.float32, device=dev)
@@ -155,7 +166,9 @@ class RPNProposal3D(object):
         seg_counts = torch.tensor(counts, dtype=torch.int32, device=dev)
 
         # 3. one batched NMS; kept rows in descending-score order
-        _keep, keep_s, num_keep = nms3d_batched(dets, seg_counts, nms_thr, want_score_order=True)
+        keep_i, keep_s, num_keep = nms3d_batched(dets, seg_counts, nms_thr, want_score_order=True)
+        if any(unsorted):
+            keep_s = torch.where(torch.tensor(unsorted, device=dev)[:, None], keep_i, keep_s)
 
         # 4. proposals[:nms_post] per segment (rpn_head_3d.py:135), then per image cat + topk(max_num) (:139-148)
         P = min(nms_post, k)

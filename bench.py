@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native 3D RoI hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): RoIs/s of 3D RoIAlign forward on workload C2 = BASELINE.json configs[1]
+("3D RoIAlign fwd on one synthetic FPN P2 level 256ch x 40x128x128, 512 RoIs, 7x7x7 out, sampling_ratio 2").
+One "step" = one RoIAlign3D forward over one batch of 512 RoIs.  Every rank runs the same per-GPU workload on its own
+volume (weak scaling, no data-path collective: volumes are independent); `value` = N * 512 * K / max-over-ranks
+device time.  One JSON line is printed by rank 0 with, besides the contract keys:
+  roofline      dominant kernel (roi_align3d_fwd_ring_kernel): algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle (CPU restatement of the reference; the reference has no CPU RoIAlign) on a bounded sample
+  e2e           the same metric through the C-ABI host-buffer entry (pinned host NCDHW features -> H2D -> layout
+                conversion -> kernel -> D2H of the pooled features), i.e. what a caller holding host tensors pays
+  extra         secondary rows: NCDHW-input path, RoIAlign backward, C3 (mask branch fwd+bwd, 4 levels), C1 3D NMS
+`--impl reference` times the reference's own algorithm on the host cores (oracle port, all threads) on the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "3d-multi-resolution-rcnn_b200")
+for _p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "roialign3d_fwd_rois_per_sec"
+UNIT = "RoIs/s"
+C2 = dict(B=1, C=256, D=40, H=128, W=128, K=512, P=7, PD=7, scale=0.25, scale_d=0.5, sample_num=2)
+WORKLOAD = ("C2: RoIAlign3D fwd, FPN P2 level 256ch x 40x128x128 fp32 (671 MB, > L2 so no flush needed), 512 RoIs, "
+            "7x7x7 bins, sample_num 2; features resident in HBM in torch.channels_last_3d memory format")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary rows (C3, NMS, backward)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# algorithmic bytes: output write + compulsory read of the U distinct voxels touched + rois
+# ---------------------------------------------------------------------------------------------------------------
+def unique_voxels(rois, D, H, W, P, PD, scale, scale_d, sample_num):
+    """U = number of distinct (b,z,y,x) voxels the RoI set samples (host arithmetic in float32, same formulas as
+    the kernel; used only to count bytes)."""
+    f32 = np.float32
+    touched = {}
+
+    def axis(c1, c2, s, Pn, size):
+        start = f32(c1) * f32(s)
+        sz = max(f32(f32(c2) + f32(1)) * f32(s) - start, f32(0))
+        b = f32(sz) / f32(Pn)
+        S = sample_num if sample_num > 0 else int(np.ceil(b))
+        m = np.zeros(size, bool)
+        for p in range(Pn):
+            for i in range(S):
+                c = f32(start + f32(p) * b) + f32(f32(i + 0.5) * b) / f32(S)
+                if c < -1.0 or c > size:
+                    continue
+                c = max(c, f32(0))
+                lo = int(c)
+                if lo >= size - 1:
+                    lo = hi = size - 1
+                else:
+                    hi = lo + 1
+                m[lo] = m[hi] = True
+        return m
+
+    for r in rois:
+        b = int(r[0])
+        vol = touched.setdefault(b, np.zeros((D, H, W), bool))
+        mx, my, mz = axis(r[1], r[3], scale, P, W), axis(r[2], r[4], scale, P, H), axis(r[5], r[6], scale_d, PD, D)
+        zs, ys, xs = np.nonzero(mz)[0], np.nonzero(my)[0], np.nonzero(mx)[0]
+        if len(zs) and len(ys) and len(xs):
+            vol[zs[0]:zs[-1] + 1, ys[0]:ys[-1] + 1, xs[0]:xs[-1] + 1] |= (mz[zs[0]:zs[-1] + 1, None, None] &
+                                                                       my[None, ys[0]:ys[-1] + 1, None] &
+                                                                       mx[None, None, xs[0]:xs[-1] + 1])
+    return int(sum(int(v.sum()) for v in touched.values()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8:
+                self.rows.append((time.time(), parts))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [p for (t, p) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [p for (_t, p) in self.rows]
+        if not rows:
+            return None
+        sm, mx, reasons = [], [], set()
+        for p in rows:
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def c2_inputs(torch, dev, rank):
+    import synth
+    g = torch.Generator(device=dev)
+    g.manual_seed(1 + rank)
+    feats = torch.randn((C2["B"], C2["C"], C2["D"], C2["H"], C2["W"]), device=dev, generator=g)
+    feats_cl = feats.contiguous(memory_format=torch.channels_last_3d)
+    rois_np = synth.c2_rois(C2["K"], seed=2 + rank)
+    return feats, feats_cl, rois_np
+
+
+def time_steps(torch, fn, steps, warmup, dist=None):
+    """W warm-ups, then K steps bracketed by barrier + synchronize; device time by CUDA events on the launching
+    stream; returns (total_ms max over ranks, per-step list of this rank)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
+        fn()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total = evs[0].elapsed_time(evs[-1])
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    if dist is not None:
+        t = torch.tensor([total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+    return total, per
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores.  The reference has no CPU RoIAlign
+    (functions/roi_align_3d.py:36-37 raises NotImplementedError), so this is the oracle port (kind "port") with every
+    host thread, on the same workload; each step is a bounded sample of the 512 RoIs."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    import synth
+    oracle.build()
+    rng = np.random.default_rng(1)
+    feats = rng.standard_normal((C2["B"], C2["C"], C2["D"], C2["H"], C2["W"]), dtype=np.float32)
+    rois = synth.c2_rois(C2["K"], seed=2)
+    cores = oracle.num_threads()
+    # size the per-step sample so a step takes ~1 s
+    t0 = time.perf_counter()
+    oracle.roi_align3d_forward(feats, rois[:8], C2["P"], C2["PD"], C2["scale"], C2["scale_d"], C2["sample_num"])
+    t8 = max(time.perf_counter() - t0, 1e-4)
+    n = int(min(C2["K"], max(8, 8 * round(1.0 / t8))))
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    for _ in range(warmup):
+        oracle.roi_align3d_forward(feats, rois[:n], C2["P"], C2["PD"], C2["scale"], C2["scale_d"], C2["sample_num"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.roi_align3d_forward(feats, rois[:n], C2["P"], C2["PD"], C2["scale"], C2["scale_d"], C2["sample_num"])
+    dt = time.perf_counter() - t0
+    val = n * steps / dt
+    sample = "%d of the 512 C2 RoIs per step, all 256 channels, oracle C port (gcc -O2 -fopenmp)" % n
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU arm: host cores only, no GPU work"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+
+    import torch
+    import roi3d_b200
+    from roi3d_b200 import _lib
+    from roi3d_b200.ops import RoIAlign3D, nms3d_batched
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    feats, feats_cl, rois_np = c2_inputs(torch, dev, rank)
+    rois = torch.from_numpy(rois_np).to(dev)
+    layer = RoIAlign3D(C2["P"], C2["PD"], C2["scale"], C2["scale_d"], C2["sample_num"])
+    out = layer(feats_cl, rois)  # first call: context/library load outside any timed region
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    t_wall0 = time.time()
+
+    # ---- headline: device-resident inputs ----------------------------------------------------------------
+    launches = [0]
+
+    def step():
+        layer(feats_cl, rois)
+        launches[0] += 1
+
+    total_ms, per = time_steps(torch, step, steps, warmup, dist)
+    gpu_launches = steps  # one roi_align3d_fwd_ring_kernel launch per step inside the timed region
+    value = world * C2["K"] * steps / (total_ms * 1e-3)
+    kernel_ms = float(np.median(per))  # one launch per step: the per-step event time is the kernel's duration
+
+    # ---- e2e: host buffers through the C-ABI host entry ---------------------------------------------------
+    e2e_steps = max(1, min(steps, 10))
+    feats_h = torch.empty(feats.shape, dtype=torch.float32).pin_memory()
+    feats_h.copy_(feats)  # NCDHW, the reference's layout
+    rois_h = torch.from_numpy(rois_np).pin_memory()
+    out_h = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        _lib.check(_lib.lib.roi3d_roi_align3d_forward_host(
+            feats_h.data_ptr(), _lib.NCDHW, C2["B"], C2["C"], C2["D"], C2["H"], C2["W"], rois_h.data_ptr(), C2["K"],
+            C2["PD"], C2["P"], C2["P"], C2["scale"], C2["scale_d"], C2["sample_num"], out_h.data_ptr()))
+
+    for _ in range(2):
+        e2e_step()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()  # synchronous: returns after the D2H copy completed
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * C2["K"] * e2e_steps / e2e_s
+    h2d = feats_h.numel() * 4 + rois_h.numel() * 4
+    d2h = out_h.numel() * 4
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- secondary rows -------------------------------------------------------------------------------------
+    extra = {}
+    if not args.no_extra and rank == 0:
+        try:
+            extra = secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, kernel_ms * 1e3)
+        except Exception as e:  # secondary rows never take the headline down
+            extra = {"error": repr(e)}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel -----------------------------------------------------------------
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        U = unique_voxels(rois_np, C2["D"], C2["H"], C2["W"], C2["P"], C2["PD"], C2["scale"], C2["scale_d"],
+                          C2["sample_num"])
+        out_bytes = C2["K"] * C2["C"] * C2["PD"] * C2["P"] * C2["P"] * 4
+        alg_bytes = out_bytes + U * C2["C"] * 4 + C2["K"] * 28
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "r01_c2_fwd_ncu_summary.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_ring_kernel<7,7,2>", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes": alg_bytes, "unique_voxels": U, "kernel_us": kernel_ms * 1e3,
+                    "output_only_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9}
+        cpu = cpu_baseline()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "inputs (671 MB features + 180 MB output) exceed the 126 MB L2",
+                       "per_gpu": "each rank runs C2 on its own volume; no collective on the data path",
+                       "e2e_layout": "host features NCDHW-contiguous (reference layout); conversion to channels-last "
+                                     "runs on the device inside the timed call"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+            "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    """The oracle (CPU port of the reference kernel) on a bounded sample of C2, on this box's host cores."""
+    import oracle
+    import synth
+    oracle.build()
+    rng = np.random.default_rng(1)
+    feats = rng.standard_normal((C2["B"], C2["C"], C2["D"], C2["H"], C2["W"]), dtype=np.float32)
+    rois = synth.c2_rois(C2["K"], seed=2)
+    cores = oracle.num_threads()
+    t0 = time.perf_counter()
+    oracle.roi_align3d_forward(feats, rois[:8], C2["P"], C2["PD"], C2["scale"], C2["scale_d"], C2["sample_num"])
+    t8 = max(time.perf_counter() - t0, 1e-4)
+    n = int(min(C2["K"], max(8, 8 * round(10.0 / t8))))  # about 10 s of CPU work
+    t0 = time.perf_counter()
+    oracle.roi_align3d_forward(feats, rois[:n], C2["P"], C2["PD"], C2["scale"], C2["scale_d"], C2["sample_num"])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of the 512 C2 RoIs (all 256 channels, full P2 level), one pass, %.1f s" % (n, dt)}
+
+
+def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_us):
+    """Other BASELINE.json configs, timed the same way (CUDA events, median of a few iterations)."""
+    import roi3d_b200
+    import synth
+    from roi3d_b200 import SingleRoIExtractor
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def med_us(fn, iters=10, warm=2, do_flush=True):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            if do_flush:
+                flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        return float(np.median(ts))
+
+    ex = {}
+    # C2 with the reference's NCDHW-contiguous input: includes the on-device layout conversion (cache disabled)
+    saved = roi3d_b200._util._CACHE_SIZE
+    roi3d_b200._util._CACHE_SIZE = 0
+    roi3d_b200._util.clear_layout_cache()
+    us = med_us(lambda: layer(feats, rois), iters=5)
+    roi3d_b200._util._CACHE_SIZE = saved
+    ex["c2_fwd_ncdhw_input_us"] = us
+    ex["c2_fwd_ncdhw_input_rois_per_sec"] = C2["K"] / (us * 1e-6)
+    # C2 backward (grad of the pooled features w.r.t. the level), zero-fill of the 671 MB gradient included
+    fcl = feats_cl.detach().requires_grad_(True)
+    out = layer(fcl, rois)
+    g = torch.randn_like(out)
+
+    def bwd():
+        fcl.grad = None
+        out.backward(g, retain_graph=True)
+    us = med_us(bwd, iters=5)
+    ex["c2_bwd_us_incl_zero_fill"] = us
+    ex["c2_fwd_us"] = fwd_us
+    ex["c2_fwd_bwd_rois_per_sec"] = C2["K"] / ((us + fwd_us) * 1e-6)
+    del out, g, fcl
+    torch.cuda.empty_cache()
+    # C1: 3D NMS, 2000 boxes, thr 0.7 (device resident, no host sync) and 40 segments batched
+    dets = torch.from_numpy(synth.c1_boxes(2000, seed=0)).to(dev)
+    d1 = dets[None].contiguous()
+    us = med_us(lambda: nms3d_batched(d1, None, 0.7), iters=30, do_flush=False)
+    ex["c1_nms2000_us"] = us
+    ex["c1_nms2000_boxes_per_sec"] = 2000 / (us * 1e-6)
+    ex["c1_nms2000_iou_pairs_per_sec"] = 1999000 / (us * 1e-6)
+    d40 = dets[None].repeat(40, 1, 1).contiguous()
+    us = med_us(lambda: nms3d_batched(d40, None, 0.7), iters=10, do_flush=False)
+    ex["c1_nms2000_x40_batched_us"] = us
+    ex["c1_nms2000_x40_boxes_per_sec"] = 40 * 2000 / (us * 1e-6)
+    del d40
+    # C3: mask branch, 14^3, 4 levels with level mapping, 2 volumes x 512 RoIs, fwd + bwd
+    dims = [(40, 128, 128), (20, 64, 64), (10, 32, 32), (5, 16, 16)]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)
+    pyr = [torch.randn((2, 256) + d, device=dev, generator=gen).contiguous(memory_format=torch.channels_last_3d)
+           for d in dims]
+    r3 = torch.from_numpy(synth.c3_rois(512, vols=2, seed=4)).to(dev)
+    ext = SingleRoIExtractor(dict(type='RoIAlign3D', out_size=14, out_size_depth=14, sample_num=2), 256,
+                             [4, 8, 16, 32], [2, 4, 8, 16])
+    ex["c3_level_hist"] = torch.bincount(ext.map_roi_levels(r3, 4), minlength=4).tolist()
+    us_f = med_us(lambda: ext(pyr, r3), iters=5)
+    ex["c3_fwd_us"] = us_f
+    for t in pyr:
+        t.requires_grad_(True)
+    o3 = ext(pyr, r3)
+    g3 = torch.randn_like(o3)
+
+    def bwd3():
+        for t in pyr:
+            t.grad = None
+        o3.backward(g3, retain_graph=True)
+    us_b = med_us(bwd3, iters=3, warm=1)
+    ex["c3_bwd_us_incl_zero_fill"] = us_b
+    ex["c3_fwd_bwd_rois_per_sec"] = 1024 / ((us_f + us_b) * 1e-6)
+    ex["c3_fwd_output_gbs"] = o3.numel() * 4 / (us_f * 1e-6) / 1e9
+    return ex
+
+
+if __name__ == "__main__":
+    main()
