@@ -50,34 +50,34 @@ __device__ __forceinline__ bool iou3d_gt(const SortedBox &a, float Sa, const Sor
 }
 
 // ------------------------------------------------------------------------------------------------
-// 1. rank + gather.  grid (ceil(n_max/256), nseg), block 256.
+// 1. rank + gather.  grid (ceil(n_max/32), nseg), block 256 = 32 boxes x 8 slices of the j range
+//    (each warp scans one slice with warp-uniform loads; partial ranks are summed through smem).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nms3d_rank_kernel(const float *__restrict__ dets, const int32_t *seg_counts,
                                                          int n_max, SortedBox *__restrict__ sorted,
                                                          int32_t *__restrict__ order) {
   const int seg = blockIdx.y;
   const int n = seg_counts ? min(max(seg_counts[seg], 0), n_max) : n_max;
-  if ((int)(blockIdx.x * 256) >= n) return;
+  if ((int)(blockIdx.x * 32) >= n) return;
   const float *d = dets + (long long)seg * n_max * 7;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  const unsigned ki = i < n ? score_key(d[(long long)i * 7 + 6]) : 0u;
-  __shared__ unsigned keys[256];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const unsigned ki = i < n ? score_key(__ldg(d + (long long)i * 7 + 6)) : 0u;
+  const int per = (n + 7) >> 3;
+  const int j0 = slice * per, j1 = min(n, j0 + per);
   int rank = 0;
-  for (int j0 = 0; j0 < n; j0 += 256) {
-    const int j = j0 + threadIdx.x;
-    __syncthreads();
-    keys[threadIdx.x] = j < n ? score_key(d[(long long)j * 7 + 6]) : 0u;
-    __syncthreads();
-    const int lim = min(256, n - j0);
-    if (i < n) {
-#pragma unroll 8
-      for (int t = 0; t < lim; ++t) {
-        const unsigned kj = keys[t];
-        rank += (kj > ki) || (kj == ki && (j0 + t) < i);
-      }
-    }
+#pragma unroll 4
+  for (int j = j0; j < j1; ++j) {
+    const unsigned kj = score_key(__ldg(d + (long long)j * 7 + 6));  // warp-uniform address: one broadcast load
+    rank += (kj > ki) || (kj == ki && j < i);
   }
-  if (i < n) {
+  __shared__ int part[8][32];
+  part[slice][lane] = rank;
+  __syncthreads();
+  if (slice == 0 && i < n) {
+    rank = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rank += part[q][lane];
     const float *b = d + (long long)i * 7;
     SortedBox sb;
     sb.x1 = b[0], sb.y1 = b[1], sb.x2 = b[2], sb.y2 = b[3], sb.z1 = b[4], sb.z2 = b[5];
@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(256) nms3d_mask_kernel(const SortedBox *__rest
 // ------------------------------------------------------------------------------------------------
 // 3. greedy sweep + compaction.  One CTA (256 threads) per segment.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxColBlocks = 1024;  // n_max <= 65536
+constexpr int kMaxColBlocks = 512;   // n_max <= 32768 (static shared memory budget)
+constexpr int kPanelW = 32;           // words of each mask row held in shared memory per diagonal tile
 
 __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long long *__restrict__ mask,
                                                           const int32_t *__restrict__ order,
@@ -147,25 +148,56 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
 
   __shared__ unsigned long long remv[kMaxColBlocks];
   __shared__ unsigned long long keptw[kMaxColBlocks];
-  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long panel[2][64][kPanelW];
   __shared__ unsigned long long s_kept;
   __shared__ int s_warp[8];
   __shared__ int s_base;
 
   for (int i = tid; i < cb; i += 256) remv[i] = 0ULL;
   for (int i = tid; i < n; i += 256) fl[i] = 0;
+
+  // Row panels: for diagonal tile `blk` the words [blk, blk+kPanelW) of its 64 mask rows, copied to shared
+  // memory with cp.async one tile ahead of the resolve (the rows do not depend on the sweep state).
+  auto prefetch = [&](int blk, int buf) {
+    if (blk < cb) {
+      const int nwp = min(kPanelW, cb - blk);
+      for (int idx = tid; idx < 64 * kPanelW; idx += 256) {
+        const int row = idx / kPanelW, w = idx - row * kPanelW;
+        const int grow = blk * 64 + row;
+        unsigned long long *dst = &panel[buf][row][w];
+        if (grow < n && w < nwp) {
+          const unsigned sd = (unsigned)__cvta_generic_to_shared(dst);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sd), "l"(m + (long long)grow * cbm + blk + w)
+                       : "memory");
+        } else {
+          *dst = 0ULL;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  prefetch(0, 0);
   __syncthreads();
 
   for (int blk = 0; blk < cb; ++blk) {
-    const int bs = min(64, n - blk * 64);
-    if (tid < 64) diag[tid] = tid < bs ? m[((long long)blk * 64 + tid) * cbm + blk] : 0ULL;
+    const int buf = blk & 1;
+    prefetch(blk + 1, buf ^ 1);
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     __syncthreads();
+    const int bs = min(64, n - blk * 64);
     if (tid == 0) {
+      // serial resolve of the diagonal tile with all 64 diagonal words in registers (fully unrolled:
+      // the bit tests use compile-time positions, the chain is test -> predicated OR)
+      unsigned long long dg[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) dg[i] = panel[buf][i][0];
       unsigned long long r = remv[blk], kept = 0ULL;
-      for (int i = 0; i < bs; ++i) {
+      if (bs < 64) r |= ~0ULL << bs;  // rows past n never count as kept
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
         if (!((r >> i) & 1ULL)) {
           kept |= 1ULL << i;
-          r |= diag[i];
+          r |= dg[i];
         }
       }
       s_kept = kept;
@@ -175,9 +207,23 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
     const unsigned long long kept = s_kept;
     const int nw = cb - blk - 1;
     if (nw > 0) {
-      // thread -> (row i, word w): consecutive threads read consecutive words of one mask row
-      for (int idx = tid; idx < nw * 64; idx += 256) {
-        const int i = idx / nw, w = blk + 1 + idx % nw;
+      // words blk+1 .. blk+kPanelW-1 from the panel: thread -> (word w, 8-row group g)
+      const int nwp = min(kPanelW - 1, nw);
+      {
+        const int w = 1 + (tid & (kPanelW - 1)), g = tid / kPanelW;  // kPanelW == 32, 256 threads -> g in [0,8)
+        if (w <= nwp) {
+          unsigned long long v = 0ULL;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int row = g * 8 + q;
+            if ((kept >> row) & 1ULL) v |= panel[buf][row][w];
+          }
+          if (v) atomicOr(&remv[blk + w], v);
+        }
+      }
+      // words beyond the panel (only when n > 64*kPanelW): straight from global memory
+      for (int idx = tid; idx < (nw - nwp) * 64; idx += 256) {
+        const int i = idx / (nw - nwp), w = blk + 1 + nwp + idx % (nw - nwp);
         if ((kept >> i) & 1ULL) {
           const unsigned long long v = m[((long long)blk * 64 + i) * cbm + w];
           if (v) atomicOr(&remv[w], v);
@@ -186,6 +232,7 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
     }
     __syncthreads();
   }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 
   // ---- kept set -> (a) descending-score list, (b) flags by original index ----
   if (tid == 0) s_base = 0;
@@ -309,7 +356,7 @@ int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, in
     return ROI3D_ENOMEM;
   }
   const int cbm = (n_max + 63) / 64;
-  nms3d_rank_kernel<<<dim3(ceil_div(n_max, 256), nseg), 256, 0, st>>>(dets_dev, seg_counts_dev, n_max, w.sorted,
+  nms3d_rank_kernel<<<dim3(ceil_div(n_max, 32), nseg), 256, 0, st>>>(dets_dev, seg_counts_dev, n_max, w.sorted,
                                                                       w.order);
   ROI3D_LAUNCH_CHECK();
   nms3d_mask_kernel<<<dim3(ceil_div(cbm, 4), cbm, nseg), 256, 0, st>>>(w.sorted, seg_counts_dev, n_max, iou_thr,
