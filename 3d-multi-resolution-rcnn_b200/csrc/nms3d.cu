@@ -188,18 +188,34 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
     if (tid == 0) {
       // serial resolve of the diagonal tile with all 64 diagonal words in registers (fully unrolled:
       // the bit tests use compile-time positions, the chain is test -> predicated OR)
-      unsigned long long dg[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) dg[i] = panel[buf][i][0];
-      unsigned long long r = remv[blk], kept = 0ULL;
-      if (bs < 64) r |= ~0ULL << bs;  // rows past n never count as kept
+      // 32-bit halves: the test of step i is a single LOP3 on a compile-time bit, the update a predicated OR.
+      // Row i only carries bits j > i, so rows >= 32 have an empty low word.
+      unsigned dlo[32], dhi[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        if (!((r >> i) & 1ULL)) {
-          kept |= 1ULL << i;
-          r |= dg[i];
+        const unsigned long long d = panel[buf][i][0];
+        if (i < 32) dlo[i] = (unsigned)d;
+        dhi[i] = (unsigned)(d >> 32);
+      }
+      unsigned long long r0 = remv[blk];
+      if (bs < 64) r0 |= ~0ULL << bs;  // rows past n never count as kept
+      unsigned rlo = (unsigned)r0, rhi = (unsigned)(r0 >> 32), klo = 0u, khi = 0u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (!(rlo & (1u << i))) {
+          klo |= 1u << i;
+          rlo |= dlo[i];
+          rhi |= dhi[i];
         }
       }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (!(rhi & (1u << i))) {
+          khi |= 1u << i;
+          rhi |= dhi[32 + i];
+        }
+      }
+      const unsigned long long kept = ((unsigned long long)khi << 32) | klo;
       s_kept = kept;
       keptw[blk] = kept;
     }

@@ -319,12 +319,15 @@ __device__ __forceinline__ void copy_out_tile(const float (&acc)[ROWS][PW][CV], 
     const int total = cols * NB;
     float *dst = out_tile + ((long long)chunk * 32 * CV + c) * ch_stride;
     if (NB >= 32) {
-      // +32 per step crosses at most one column boundary: predicated fix-up, no inner loop
-      int bin = lane, sidx = lane * 33, goff = lane;
+      // +32 per step crosses at most one column boundary: running pointers with a predicated fix-up
+      int bin = lane;
+      const float *sp = stage + lane * 33;
+      float *gp = dst + lane;
+      const int s_wrap = 1 - NB * 33, g_wrap = col_stride - NB;
       for (int idx = lane; idx < total; idx += 32) {
-        __stcs(dst + goff, stage[sidx]);
-        bin += 32, sidx += 32 * 33, goff += 32;
-        if (bin >= NB) bin -= NB, sidx += 1 - NB * 33, goff += col_stride - NB;
+        __stcs(gp, *sp);
+        bin += 32, sp += 32 * 33, gp += 32;
+        if (bin >= NB) bin -= NB, sp += s_wrap, gp += g_wrap;
       }
     } else {
       for (int idx = lane; idx < total; idx += 32) {
@@ -490,8 +493,8 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-template <int PW, int ROWS, int CV, int NXU, int NS, int RXR>
-__global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_ring_kernel(const RoiParams p) {
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel(const RoiParams p) {
   using TB = Tables<PW>;
   constexpr int PWP = TB::PWP;
   constexpr int VOX = 32 * CV;                 // floats per voxel-chunk
@@ -707,12 +710,29 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_ring_kernel(const
 // Backward, channels-last, separable (transposed contraction).  Same work split as the forward.
 // One vector red per (row voxel, lane) instead of 64 scalar atomics per output element.
 // ---------------------------------------------------------------------------------------------
-template <int PW, int ROWS, int CV>
+// Literal backward of a warp's whole (pd, ph-group) tile, out of line (see literal_tile_fwd).
+template <int CV>
+__device__ __noinline__ void literal_tile_bwd(const Item &it, float *gb, int C, int PW, const float *stage, int lane,
+                                              bool active, float inv_unused) {
+  (void)inv_unused;
+  for (int r = 0; r < it.rows; ++r)
+    for (int pw = 0; pw < PW; ++pw) {
+      float top[CV];
+#pragma unroll
+      for (int c = 0; c < CV; ++c) top[c] = stage[(c * it.rows * PW + r * PW + pw) * 33 + lane];
+      if (active) literal_bin_bwd<CV>(it, gb, C, it.pd, it.ph0 + r, pw, top);
+    }
+}
+
+template <int PW, int ROWS, int CV, int RXR>
 __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const RoiParams p) {
   using TB = Tables<PW>;
   constexpr int PWP = TB::PWP;
-  constexpr int STAGE = ROWS * PW * 33;
-  constexpr int WARP_FLOATS = ((STAGE > TB::FLOATS ? STAGE : TB::FLOATS) + 3) / 4 * 4;  // 16-byte aligned per warp
+  constexpr int VOX = 32 * CV;
+  constexpr int STAGE = CV * ROWS * PW * 33;     // all CV slots of the grad tile at once
+  constexpr int UX = RXR * VOX;                  // x-expanded row, [xx][lane*CV + c]
+  constexpr int LISTS = 80;
+  constexpr int WARP_FLOATS = (TB::FLOATS + LISTS / 4 + (STAGE > UX ? STAGE : UX) + 3) / 4 * 4;
   extern __shared__ __align__(16) float smem_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *sm = smem_all + warp * WARP_FLOATS;
@@ -729,114 +749,144 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
   float *gb = it.L.grad + (long long)it.b * vox * C + c_base;
   const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
 
-  // ---- stage-in of this warp's grad_out tile: coalesced reads, transposed through smem ----
+  TB T;
+  T.bind(sm);
+  unsigned char *ylist = reinterpret_cast<unsigned char *>(sm + ((TB::FLOATS + 3) / 4 * 4));
+  unsigned char *zlist = ylist + 40;
+  float *stage = sm + ((TB::FLOATS + 3) / 4 * 4) + LISTS / 4;
+  float *ux = stage;  // aliases the stage-in tile once the gradients are in registers
+
+  // ---- stage-in of this warp's grad_out tile: 4-byte cp.async copies that transpose on the fly
+  //      (coalesced global reads -> [bin][33] padded smem), all in flight together ----
   const int NB = it.rows * PW;
   const long long ch_stride = (long long)p.PD * p.PH * PW;
   // reference index (roi_align_kernel.cu:554-555): pd*PD*PW + ph*PW + pw when bug_compat
   const long long row_base = p.bug_compat ? ((long long)it.pd * p.PD + it.ph0) * PW
                                           : ((long long)it.pd * p.PH + it.ph0) * PW;
-  const long long top_base = ((long long)it.k * C) * ch_stride + row_base;
   const long long top_total = (long long)p.K * C * ch_stride;
-  float g[ROWS][PW][CV];
-  float *stage = sm;
+  {
+    const int col_stride = CV * (int)ch_stride;
 #pragma unroll
-  for (int c = 0; c < CV; ++c) {
-    __syncwarp();
-    int cl = 0, bin = lane;
-    while (bin >= NB) bin -= NB, ++cl;
-    while (cl < 32) {
-      const int ch = (it.chunk * 32 + cl) * CV + c;
-      const long long o = top_base + (long long)ch * ch_stride + bin;
-      stage[bin * 33 + cl] = (ch < C && o < top_total) ? __ldcs(p.grad_out + o) : 0.0f;
-      bin += 32;
-      while (bin >= NB) bin -= NB, ++cl;
+    for (int c = 0; c < CV; ++c) {
+      const int cols = min(32, (C - it.chunk * 32 * CV - c + CV - 1) / CV);
+      const int total = cols * NB;
+      float *st = stage + c * (NB * 33);
+      const long long g0 = ((long long)it.k * C + (long long)it.chunk * 32 * CV + c) * ch_stride + row_base;
+      for (int idx = lane; idx < 32 * NB; idx += 32) {
+        const int cl = idx / NB, bin = idx - cl * NB;
+        float *dst = st + bin * 33 + cl;
+        const long long o = g0 + (long long)cl * col_stride + bin;
+        if (idx < total && o < top_total) {
+          const unsigned sd = (unsigned)__cvta_generic_to_shared(dst);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sd), "l"(p.grad_out + o) : "memory");
+        } else {
+          *dst = 0.0f;
+        }
+      }
     }
-    __syncwarp();
+    cp_async_commit();
+  }
+  build_tables<PW>(T, it, lane);  // overlaps the copies
+  cp_async_wait<0>();
+  __syncwarp();
+  if (T.empty) return;
+  const int RX = T.xmax - T.xmin + 1;
+  if (!T.fits || RX > RXR) {
+    literal_tile_bwd<CV>(it, gb, C, PW, stage, lane, active, 0.0f);
+    return;
+  }
+  // gradients to registers, scaled once by 1/count (reference: top*w/count per corner, :600-608)
+  const float inv = __frcp_rn(count);
+  float g[ROWS][PW][CV];
+#pragma unroll
+  for (int c = 0; c < CV; ++c)
 #pragma unroll
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int pw = 0; pw < PW; ++pw)
-        g[r][pw][c] = r < it.rows ? stage[(r * PW + pw) * 33 + lane] : 0.0f;
+        g[r][pw][c] = r < it.rows ? stage[(c * NB + r * PW + pw) * 33 + lane] * inv : 0.0f;
+
+  // compact lists of the y rows / z slices that carry weight (as in the forward)
+  const int RY = T.ymax - T.ymin + 1, RZ = T.zmax - T.zmin + 1;
+  int ny = 0, nz = 0;
+  for (int y0 = 0; y0 < RY; y0 += 32) {
+    const int yy = y0 + lane;
+    bool a = false;
+    if (yy < RY) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) a |= T.Dy[yy * 8 + r] != 0.0f;
+    }
+    const unsigned bal = __ballot_sync(FULL, a);
+    if (a) ylist[ny + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)yy;
+    ny += __popc(bal);
+  }
+  {
+    const bool a = lane < RZ && T.Dz[lane] != 0.0f;
+    const unsigned bal = __ballot_sync(FULL, a);
+    if (a) zlist[__popc(bal & ((1u << lane) - 1u))] = (unsigned char)lane;
+    nz = __popc(bal);
   }
   __syncwarp();
 
-  TB T;
-  T.bind(sm);
-  build_tables<PW>(T, it, lane);
-  if (T.empty) return;
-
-  if (!T.fits) {
-    for (int r = 0; r < it.rows; ++r)
-      for (int pw = 0; pw < PW; ++pw) {
-        float top[CV];
-#pragma unroll
-        for (int c = 0; c < CV; ++c) top[c] = 0.0f;
-        // dynamic (r,pw) register indexing is not possible: select with a static sweep
-#pragma unroll
-        for (int rr = 0; rr < ROWS; ++rr)
-#pragma unroll
-          for (int ww = 0; ww < PW; ++ww)
-            if (rr == r && ww == pw) {
-#pragma unroll
-              for (int c = 0; c < CV; ++c) top[c] = g[rr][ww][c];
-            }
-        if (active) literal_bin_bwd<CV>(it, gb, C, it.pd, it.ph0 + r, pw, top);
-      }
-    return;
-  }
-
-  // scale once by 1/count (reference: top*w/count per corner, roi_align_kernel.cu:600-608)
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r)
+  const long long row_elems = (long long)it.L.W * C;
+  const long long slice_elems = (long long)it.L.H * row_elems;
+  float *gbase = gb + ((long long)T.zmin * it.L.H + T.ymin) * row_elems + (long long)T.xmin * C;
+  for (int yi = 0; yi < ny; ++yi) {
+    const int yy = ylist[yi];
+    float wy[8];
+    {
+      const float4 a = *reinterpret_cast<const float4 *>(T.Dy + yy * 8);
+      const float4 b4 = *reinterpret_cast<const float4 *>(T.Dy + yy * 8 + 4);
+      wy[0] = a.x, wy[1] = a.y, wy[2] = a.z, wy[3] = a.w, wy[4] = b4.x, wy[5] = b4.y, wy[6] = b4.z, wy[7] = b4.w;
+    }
+    // u[pw] = sum over the ph rows of this group of wy * g  (once per y)
+    float u[PW][CV];
 #pragma unroll
     for (int pw = 0; pw < PW; ++pw)
 #pragma unroll
-      for (int c = 0; c < CV; ++c) g[r][pw][c] = __fdiv_rn(g[r][pw][c], count);
-
-  const int RY = T.ymax - T.ymin + 1, RX = T.xmax - T.xmin + 1;
-  for (int z = T.zmin; z <= T.zmax; ++z) {
-    const float wz = T.Dz[z - T.zmin];
-    if (wz == 0.0f) continue;
-    for (int yy = 0; yy < RY; ++yy) {
-      float wr[ROWS];
-      bool any = false;
+      for (int c = 0; c < CV; ++c) u[pw][c] = 0.0f;
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
-        wr[r] = wz * T.Dy[yy * 8 + r];
-        any |= wr[r] != 0.0f;
-      }
-      if (!any) continue;
-      float u[PW][CV];
-#pragma unroll
-      for (int pw = 0; pw < PW; ++pw)
-#pragma unroll
-        for (int c = 0; c < CV; ++c) u[pw][c] = 0.0f;
-#pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
-        if (wr[r] != 0.0f) {
-#pragma unroll
-          for (int pw = 0; pw < PW; ++pw)
-#pragma unroll
-            for (int c = 0; c < CV; ++c) u[pw][c] = fmaf(wr[r], g[r][pw][c], u[pw][c]);
-        }
-      }
-      float *rowp = gb + (((long long)z * it.L.H + (T.ymin + yy)) * it.L.W + T.xmin) * C;
-      for (int xx = 0; xx < RX; ++xx) {
-        if (!T.xany[xx]) continue;
-        float wx[PWP];
-#pragma unroll
-        for (int q = 0; q < PWP / 4; ++q) {
-          const float4 t = *reinterpret_cast<const float4 *>(T.Dx + xx * PWP + q * 4);
-          wx[q * 4 + 0] = t.x, wx[q * 4 + 1] = t.y, wx[q * 4 + 2] = t.z, wx[q * 4 + 3] = t.w;
-        }
-        float v[CV];
-#pragma unroll
-        for (int c = 0; c < CV; ++c) v[c] = 0.0f;
+    for (int r = 0; r < ROWS; ++r) {
+      if (wy[r] != 0.0f) {
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw)
 #pragma unroll
-          for (int c = 0; c < CV; ++c) v[c] = fmaf(wx[pw], u[pw][c], v[c]);
-        if (active) redv<CV>(rowp + (long long)xx * C, v);
+          for (int c = 0; c < CV; ++c) u[pw][c] = fmaf(wy[r], g[r][pw][c], u[pw][c]);
+      }
+    }
+    // x-expansion, once per y: ux[xx] = sum_pw Dx[xx][pw] * u[pw]   (kept per lane in shared memory)
+    __syncwarp();
+    for (int xx = 0; xx < RX; ++xx) {
+      float wx[PWP];
+#pragma unroll
+      for (int q = 0; q < PWP / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4 *>(T.Dx + xx * PWP + q * 4);
+        wx[q * 4 + 0] = t.x, wx[q * 4 + 1] = t.y, wx[q * 4 + 2] = t.z, wx[q * 4 + 3] = t.w;
+      }
+      float v[CV];
+#pragma unroll
+      for (int c = 0; c < CV; ++c) v[c] = 0.0f;
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+        for (int c = 0; c < CV; ++c) v[c] = fmaf(wx[pw], u[pw][c], v[c]);
+#pragma unroll
+      for (int c = 0; c < CV; ++c) ux[xx * VOX + lane * CV + c] = v[c];
+    }
+    __syncwarp();
+    // scatter: one vector red per (z, x) voxel of this y row
+    float *rowy = gbase + (long long)yy * row_elems;
+    for (int zi = 0; zi < nz; ++zi) {
+      const int zrel = zlist[zi];
+      const float wz = T.Dz[zrel];
+      float *q = rowy + (long long)zrel * slice_elems;
+#pragma unroll 2
+      for (int xx = 0; xx < RX; ++xx) {
+        if (!T.xany[xx]) continue;
+        float v[CV];
+#pragma unroll
+        for (int c = 0; c < CV; ++c) v[c] = wz * ux[xx * VOX + lane * CV + c];
+        if (active) redv<CV>(q + (long long)xx * C, v);
       }
     }
   }
@@ -967,7 +1017,7 @@ static int launch_fwd(RoiParams &p, cudaStream_t st) {
   return ROI3D_OK;
 }
 
-template <int PW, int ROWS, int CV, int NXU, int NS, int RXR>
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB = 0>
 static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
   constexpr int VOX = 32 * CV;
@@ -979,7 +1029,7 @@ static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   p.nchunk = ceil_div(p.C, 32 * CV);
   p.nphg = ceil_div(p.PH, ROWS);
   p.total_items = (long long)p.K * p.nchunk * p.PD * p.nphg;
-  auto kern = roi_align3d_fwd_ring_kernel<PW, ROWS, CV, NXU, NS, RXR>;
+  auto kern = roi_align3d_fwd_ring_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = ceil_div_ll(p.total_items, kWarps);
   ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
@@ -988,16 +1038,18 @@ static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   return ROI3D_OK;
 }
 
-template <int PW, int ROWS, int CV>
+template <int PW, int ROWS, int CV, int RXR>
 static int launch_bwd(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
-  constexpr int STAGE = ROWS * PW * 33;
-  constexpr int WARP_FLOATS = ((STAGE > TB::FLOATS ? STAGE : TB::FLOATS) + 3) / 4 * 4;  // 16-byte aligned per warp
+  constexpr int VOX = 32 * CV;
+  constexpr int STAGE = CV * ROWS * PW * 33;
+  constexpr int UX = RXR * VOX;
+  constexpr int WARP_FLOATS = (TB::FLOATS + 80 / 4 + (STAGE > UX ? STAGE : UX) + 3) / 4 * 4;
   const size_t smem = (size_t)kWarps * WARP_FLOATS * sizeof(float);
   p.nchunk = ceil_div(p.C, 32 * CV);
   p.nphg = ceil_div(p.PH, ROWS);
   p.total_items = (long long)p.K * p.nchunk * p.PD * p.nphg;
-  auto kern = roi_align3d_bwd_cl_kernel<PW, ROWS, CV>;
+  auto kern = roi_align3d_bwd_cl_kernel<PW, ROWS, CV, RXR>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = ceil_div_ll(p.total_items, kWarps);
   ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d backward: too many work items");
@@ -1048,6 +1100,9 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
       if (v == 5) return launch_fwd_ring<7, 7, 2, 3, 4, 18>(p, st);
       if (v == 6) return launch_fwd_ring<7, 7, 1, 3, 4, 20>(p, st);
       if (v == 7) return launch_fwd_ring<7, 4, 2, 3, 3, 18>(p, st);
+      if (v == 8) return launch_fwd_ring<7, 7, 2, 3, 2, 18, 4>(p, st);
+      if (v == 9) return launch_fwd_ring<7, 7, 2, 3, 2, 18, 3>(p, st);
+      if (v == 10) return launch_fwd_ring<7, 4, 2, 3, 2, 18, 4>(p, st);
     }
     if (v == 1 || cvmax == 1) return launch_fwd<7, 7, 1, 3>(p, st);
     if (v == 2 && cvmax >= 4) return launch_fwd<7, 4, 4, 3>(p, st);
@@ -1077,14 +1132,14 @@ static int dispatch_bwd(RoiParams &p, cudaStream_t st) {
     return launch_generic<1>(p, false, st);
   }
   if (p.PW == 7) {
-    if (v == 1 || cvmax == 1) return launch_bwd<7, 7, 1>(p, st);
-    if (v == 2 && cvmax >= 4) return launch_bwd<7, 4, 4>(p, st);
-    return launch_bwd<7, 7, 2>(p, st);
+    if (v == 1 || cvmax == 1) return launch_bwd<7, 7, 1, 40>(p, st);
+    if (v == 2 && cvmax >= 4) return launch_bwd<7, 4, 4, 16>(p, st);
+    return launch_bwd<7, 7, 2, 26>(p, st);
   }
   if (p.PW == 14) {
-    if (v == 1 || cvmax == 1) return launch_bwd<14, 7, 1>(p, st);
-    if (v == 2 && cvmax >= 4) return launch_bwd<14, 2, 4>(p, st);
-    return launch_bwd<14, 4, 2>(p, st);
+    if (v == 1 || cvmax == 1) return launch_bwd<14, 7, 1, 40>(p, st);
+    if (v == 2 && cvmax >= 4) return launch_bwd<14, 2, 4, 16>(p, st);
+    return launch_bwd<14, 4, 2, 30>(p, st);
   }
   if (cvmax >= 2) return launch_generic<2>(p, false, st);
   return launch_generic<1>(p, false, st);
