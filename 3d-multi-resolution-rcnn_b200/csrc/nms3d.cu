@@ -63,13 +63,27 @@ __global__ void __launch_bounds__(256) nms3d_rank_kernel(const float *__restrict
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   const unsigned ki = i < n ? score_key(__ldg(d + (long long)i * 7 + 6)) : 0u;
-  const int per = (n + 7) >> 3;
-  const int j0 = slice * per, j1 = min(n, j0 + per);
+  // keys are staged through shared memory in tiles: one coalesced-ish gather with every load in flight at once
+  // (the scores sit 28 bytes apart), then warp-uniform broadcast reads; slice s of each tile is scanned by warp s.
+  constexpr int kTile = 2048;
+  __shared__ unsigned keys[kTile];
   int rank = 0;
-#pragma unroll 4
-  for (int j = j0; j < j1; ++j) {
-    const unsigned kj = score_key(__ldg(d + (long long)j * 7 + 6));  // warp-uniform address: one broadcast load
-    rank += (kj > ki) || (kj == ki && j < i);
+  for (int t0 = 0; t0 < n; t0 += kTile) {
+    const int tn = min(kTile, n - t0);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kTile / 256; ++q) {
+      const int j = q * 256 + threadIdx.x;
+      if (j < tn) keys[j] = score_key(__ldg(d + (long long)(t0 + j) * 7 + 6));
+    }
+    __syncthreads();
+    const int per = (tn + 7) >> 3;
+    const int j0 = slice * per, j1 = min(tn, j0 + per);
+#pragma unroll 8
+    for (int j = j0; j < j1; ++j) {
+      const unsigned kj = keys[j];
+      rank += (kj > ki) || (kj == ki && (t0 + j) < i);
+    }
   }
   __shared__ int part[8][32];
   part[slice][lane] = rank;
