@@ -312,6 +312,81 @@ __global__ void __launch_bounds__(256) decode_proposals_kernel(const DecodeParam
   o[6] = p.scores ? p.scores[i] : 0.0f;
 }
 
+// Batched form: one launch decodes the selected anchors of every (image, level) segment.
+struct DecodeSeg {
+  const float *bbox_pred;  // [6A, D, H, W] of this (image, level)
+  int A, D, H, W;
+  int level;               // index into DecodeBatch::base / stride tables
+  float img_h, img_w, img_d;
+};
+
+struct DecodeBatch {
+  DecodeSeg seg[kMaxSeg];
+  float base[ROI3D_MAX_LEVELS][4][6];
+  float stride[ROI3D_MAX_LEVELS], dstride[ROI3D_MAX_LEVELS];
+  float means[6], stds[6];
+  float max_ratio;
+  const int64_t *idx;   // [nseg, k]
+  const float *scores;  // [nseg, k]
+  int k;
+  float *out;           // [nseg, k, 7]
+};
+
+__global__ void __launch_bounds__(256) decode_proposals_batched_kernel(const DecodeBatch b) {
+  const int s = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.k) return;
+  DecodeParams p;
+  const DecodeSeg &sg = b.seg[s];
+  p.bbox_pred = sg.bbox_pred, p.A = sg.A, p.D = sg.D, p.H = sg.H, p.W = sg.W;
+  p.stride = b.stride[sg.level], p.dstride = b.dstride[sg.level];
+  float *o = b.out + ((long long)s * b.k + i) * 7;
+  const long long li = b.idx[(long long)s * b.k + i];
+  if (li < 0) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) o[j] = 0.0f;
+    return;
+  }
+  long long t = li;
+  const int a = (int)(t % p.A);
+  t /= p.A;
+  const int z = (int)(t % p.D);
+  t /= p.D;
+  const int x = (int)(t % p.W);
+  const int y = (int)(t / p.W);
+  const float *bs = b.base[sg.level][a];
+  const float sx = (float)x * p.stride, sy = (float)y * p.stride, sz = (float)z * p.dstride;
+  const float ax1 = __fadd_rn(bs[0], sx), ay1 = __fadd_rn(bs[1], sy);
+  const float ax2 = __fadd_rn(bs[2], sx), ay2 = __fadd_rn(bs[3], sy);
+  const float az1 = __fadd_rn(bs[4], sz), az2 = __fadd_rn(bs[5], sz);
+  const long long plane = (long long)p.D * p.H * p.W;
+  const long long sp = ((long long)z * p.H + y) * p.W + x;
+  float d[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    d[j] = __fadd_rn(__fmul_rn(__ldg(p.bbox_pred + (long long)(a * 6 + j) * plane + sp), b.stds[j]), b.means[j]);
+  const float mr = b.max_ratio;
+  const float dw = fminf(fmaxf(d[2], -mr), mr), dh = fminf(fmaxf(d[3], -mr), mr);
+  const float dz = fminf(fmaxf(d[4], -mr), mr), dd = fminf(fmaxf(d[5], -mr), mr);
+  const float px = __fmul_rn(__fadd_rn(ax1, ax2), 0.5f), py = __fmul_rn(__fadd_rn(ay1, ay2), 0.5f);
+  const float pz = __fmul_rn(__fadd_rn(az1, az2), 0.5f);
+  const float pw = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f), ph = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
+  const float pdz = __fadd_rn(__fsub_rn(az2, az1), 1.0f);
+  const float gw = __fmul_rn(pw, expf(dw)), gh = __fmul_rn(ph, expf(dh)), gd = __fmul_rn(pdz, expf(dd));
+  const float gx = __fadd_rn(px, __fmul_rn(pw, d[0])), gy = __fadd_rn(py, __fmul_rn(ph, d[1]));
+  const float gz = __fadd_rn(pz, __fmul_rn(pdz, dz));
+  float x1 = __fadd_rn(__fsub_rn(gx, __fmul_rn(gw, 0.5f)), 0.5f), y1 = __fadd_rn(__fsub_rn(gy, __fmul_rn(gh, 0.5f)), 0.5f);
+  float x2 = __fsub_rn(__fadd_rn(gx, __fmul_rn(gw, 0.5f)), 0.5f), y2 = __fsub_rn(__fadd_rn(gy, __fmul_rn(gh, 0.5f)), 0.5f);
+  float z1 = __fadd_rn(__fsub_rn(gz, __fmul_rn(gd, 0.5f)), 0.5f), z2 = __fsub_rn(__fadd_rn(gz, __fmul_rn(gd, 0.5f)), 0.5f);
+  if (sg.img_w > 0.0f) {
+    x1 = fminf(fmaxf(x1, 0.0f), sg.img_w - 1.0f), x2 = fminf(fmaxf(x2, 0.0f), sg.img_w - 1.0f);
+    y1 = fminf(fmaxf(y1, 0.0f), sg.img_h - 1.0f), y2 = fminf(fmaxf(y2, 0.0f), sg.img_h - 1.0f);
+    z1 = fminf(fmaxf(z1, 0.0f), sg.img_d - 1.0f), z2 = fminf(fmaxf(z2, 0.0f), sg.img_d - 1.0f);
+  }
+  o[0] = x1, o[1] = y1, o[2] = x2, o[3] = y2, o[4] = z1, o[5] = z2;
+  o[6] = b.scores ? b.scores[(long long)s * b.k + i] : 0.0f;
+}
+
 }  // namespace roi3d
 
 using namespace roi3d;
@@ -413,6 +488,52 @@ int roi3d_decode_proposals(const float *bbox_pred_dev, int A, int D, int H, int 
   p.idx = idx_dev, p.scores = scores_dev, p.n = n, p.out = out_dev;
   decode_proposals_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p);
   ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+int roi3d_decode_proposals_batched(const float *const *bbox_pred_dev_ptrs, const int32_t *seg_adhw,
+                                   const int32_t *seg_level, const float *seg_img_hwd, int nseg, int num_levels,
+                                   int A, const float *base_anchors_host, const float *strides_host,
+                                   const float *depth_strides_host, const int64_t *idx_dev, const float *scores_dev,
+                                   int k, const float *means6_host, const float *stds6_host, float *out_dev,
+                                   void *stream) {
+  ROI3D_CHECK_ARG(nseg >= 0 && k >= 0, "bad sizes");
+  if (nseg == 0 || k == 0) return ROI3D_OK;
+  ROI3D_CHECK_ARG(bbox_pred_dev_ptrs && seg_adhw && seg_level && base_anchors_host && strides_host &&
+                      depth_strides_host && idx_dev && out_dev,
+                  "NULL pointer");
+  ROI3D_CHECK_ARG(A >= 1 && A <= 4, "batched decode supports 1..4 base anchors per level, got %d", A);
+  ROI3D_CHECK_ARG(num_levels >= 1 && num_levels <= ROI3D_MAX_LEVELS, "num_levels out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s0 = 0; s0 < nseg; s0 += kMaxSeg) {
+    const int ns = nseg - s0 < kMaxSeg ? nseg - s0 : kMaxSeg;
+    DecodeBatch b;
+    for (int s = 0; s < ns; ++s) {
+      DecodeSeg &sg = b.seg[s];
+      sg.bbox_pred = bbox_pred_dev_ptrs[s0 + s];
+      sg.A = seg_adhw[(s0 + s) * 4 + 0], sg.D = seg_adhw[(s0 + s) * 4 + 1];
+      sg.H = seg_adhw[(s0 + s) * 4 + 2], sg.W = seg_adhw[(s0 + s) * 4 + 3];
+      sg.level = seg_level[s0 + s];
+      ROI3D_CHECK_ARG(sg.A == A && sg.level >= 0 && sg.level < num_levels && sg.bbox_pred, "segment %d: bad descriptor", s0 + s);
+      sg.img_h = seg_img_hwd ? seg_img_hwd[(s0 + s) * 3 + 0] : 0.0f;
+      sg.img_w = seg_img_hwd ? seg_img_hwd[(s0 + s) * 3 + 1] : 0.0f;
+      sg.img_d = seg_img_hwd ? seg_img_hwd[(s0 + s) * 3 + 2] : 0.0f;
+    }
+    for (int l = 0; l < num_levels; ++l) {
+      for (int a = 0; a < A; ++a)
+        for (int j = 0; j < 6; ++j) b.base[l][a][j] = base_anchors_host[(l * A + a) * 6 + j];
+      b.stride[l] = strides_host[l], b.dstride[l] = depth_strides_host[l];
+    }
+    for (int j = 0; j < 6; ++j) {
+      b.means[j] = means6_host ? means6_host[j] : 0.0f;
+      b.stds[j] = stds6_host ? stds6_host[j] : 1.0f;
+    }
+    b.max_ratio = (float)4.135166556742356;
+    b.idx = idx_dev + (size_t)s0 * k, b.scores = scores_dev ? scores_dev + (size_t)s0 * k : nullptr;
+    b.k = k, b.out = out_dev + (size_t)s0 * k * 7;
+    decode_proposals_batched_kernel<<<dim3(ceil_div(k, 256), ns), 256, 0, st>>>(b);
+    ROI3D_LAUNCH_CHECK();
+  }
   return ROI3D_OK;
 }
 

@@ -59,6 +59,7 @@ def _load():
         "roi3d_topk_segmented": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, c_size_t, P]),
         "roi3d_decode_proposals": (c_int, [P, c_int, c_int, c_int, c_int, c_float, c_float, P, P, P, c_int, P, P,
                                            c_float, c_float, c_float, P, P]),
+        "roi3d_decode_proposals_batched": (c_int, [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly

@@ -154,15 +154,29 @@ class RPNProposal3D(object):
                 idx[sid, :n] = idx[sid, :n][o]
                 val[sid, :n] = val[sid, :n][o]
 
-        # 2. decode the selected anchors, per segment (the kernel is tiny; one launch per segment)
+        # 2. decode the selected anchors of every segment in ONE launch (anchors recomputed in closed form)
         dets = torch.empty((B * L, k, 7), dtype=torch.float32, device=dev)
-        counts = []
-        for sid, (b, l) in enumerate(seg_meta):
-            img_shape = img_metas[b]['img_shape']
-            dets[sid] = decode_proposals(bbox_preds[l][b].detach(), self.anchor_generators[l].base_anchors,
-                                         self.anchor_strides[l], self.anchor_strides_depth[l], idx[sid], val[sid],
-                                         self.target_means, self.target_stds, img_shape)
-            counts.append(min(k, segs[sid].numel()))
+        preds = [bbox_preds[l][b].detach() for (b, l) in seg_meta]
+        preds = [t if t.is_contiguous() else t.contiguous() for t in preds]
+        for t in preds:
+            check_cuda_f32(t, "bbox_pred", ndim=4)
+        ptrs = (ctypes.c_void_p * len(preds))(*[t.data_ptr() for t in preds])
+        adhw = np.array([[A] + list(t.shape[1:]) for t in preds], dtype=np.int32)
+        lvl = np.array([l for (_b, l) in seg_meta], dtype=np.int32)
+        img = np.array([[img_metas[b]['img_shape'][0], img_metas[b]['img_shape'][1], img_metas[b]['img_shape'][3]]
+                        for (b, _l) in seg_meta], dtype=np.float32)
+        base = np.ascontiguousarray(np.stack([g.base_anchors.numpy() for g in self.anchor_generators[:L]]),
+                                    dtype=np.float32)
+        strides = np.asarray(self.anchor_strides[:L], dtype=np.float32)
+        dstrides = np.asarray(self.anchor_strides_depth[:L], dtype=np.float32)
+        means = np.asarray(self.target_means, dtype=np.float32)
+        stds = np.asarray(self.target_stds, dtype=np.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.roi3d_decode_proposals_batched(
+                ptrs, adhw.ctypes.data, lvl.ctypes.data, img.ctypes.data, B * L, L, A, base.ctypes.data,
+                strides.ctypes.data, dstrides.ctypes.data, idx.data_ptr(), val.data_ptr(), k, means.ctypes.data,
+                stds.ctypes.data, dets.data_ptr(), stream_ptr()))
+        counts = [min(k, s.numel()) for s in segs]
         seg_counts = torch.tensor(counts, dtype=torch.int32, device=dev)
 
         # 3. one batched NMS; kept rows in descending-score order

@@ -459,6 +459,31 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ex["c3_bwd_us_incl_zero_fill"] = us_b
     ex["c3_fwd_bwd_rois_per_sec"] = 1024 / ((us_f + us_b) * 1e-6)
     ex["c3_fwd_output_gbs"] = o3.numel() * 4 / (us_f * 1e-6) / 1e9
+    del pyr, o3, g3
+    torch.cuda.empty_cache()
+    # C4: RPN proposal path, 8 volumes of 512x512x160 (5 levels, A=1) on this GPU: top-k 2000 -> decode -> 3D NMS 0.7
+    # -> 1000 per level -> top 1000 per volume.  Wall time of the public call (includes its one host read).
+    from roi3d_b200 import RPNProposal3D
+    Bv = 8
+    dims4 = [(80, 128, 128), (40, 64, 64), (20, 32, 32), (10, 16, 16), (5, 8, 8)]
+    gen.manual_seed(6)
+    cls = [2 * torch.randn((Bv, 1) + d, device=dev, generator=gen) for d in dims4]
+    reg = [0.1 * torch.randn((Bv, 6) + d, device=dev, generator=gen) for d in dims4]
+    head = RPNProposal3D(anchor_scales=[2], anchor_depth_scales=[2], anchor_ratios=[1.0],
+                         anchor_strides=[4, 8, 16, 32, 64], anchor_strides_depth=[2, 4, 8, 16, 32])
+    cfg = dict(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
+    metas = [dict(img_shape=(512, 512, 3, 160), scale_factor=1.0)] * Bv
+    props = head.get_bboxes(cls, reg, metas, cfg)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        head.get_bboxes(cls, reg, metas, cfg)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 5
+    ex["c4_proposal_path_8vol_us"] = dt * 1e6
+    ex["c4_volumes_per_sec"] = Bv / dt
+    ex["c4_anchors_scored_per_sec"] = Bv * sum(int(np.prod(d)) for d in dims4) / dt
+    ex["c4_proposals_out"] = [int(p.shape[0]) for p in props]
     return ex
 
 

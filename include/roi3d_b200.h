@@ -182,6 +182,18 @@ int roi3d_decode_proposals(const float *bbox_pred_dev, int A, int D, int H, int 
                            const float *scores_dev, int n, const float *means6_host, const float *stds6_host,
                            float img_h, float img_w, float img_d, float *out_dev, void *stream);
 
+/* Batched form of roi3d_decode_proposals: every (image, level) segment in one launch.
+ * bbox_pred_dev_ptrs: HOST array [nseg] of device pointers to that segment's [6A,D,H,W] map; seg_adhw HOST int32
+ * [nseg,4]; seg_level HOST int32 [nseg] (index into the per-level tables); seg_img_hwd HOST fp32 [nseg,3] =
+ * (img H, W, D) or NULL for no clamp; base_anchors_host [num_levels, A, 6]; strides per level.
+ * idx_dev/scores_dev: [nseg,k] (e.g. straight from roi3d_topk_segmented); out_dev: [nseg,k,7]. */
+int roi3d_decode_proposals_batched(const float *const *bbox_pred_dev_ptrs, const int32_t *seg_adhw,
+                                   const int32_t *seg_level, const float *seg_img_hwd, int nseg, int num_levels,
+                                   int A, const float *base_anchors_host, const float *strides_host,
+                                   const float *depth_strides_host, const int64_t *idx_dev, const float *scores_dev,
+                                   int k, const float *means6_host, const float *stds6_host, float *out_dev,
+                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -412,3 +412,18 @@ def test_multiclass_nms_matches_oracle(oracle, dev):
     got_b, got_l = multiclass_nms_3d(torch.from_numpy(boxes).to(dev), torch.from_numpy(scores).to(dev), 5.0,
                                      dict(type='nms', iou_thr=0.5), 10)
     assert got_b.shape == (0, 7) and got_l.shape == (0,)
+
+
+def test_roi_align_forward_wide_rois(oracle, dev):
+    """RoIs wider than the 18-voxel row ring / the 40-voxel tables take the literal path: same tolerance."""
+    from roi3d_b200.ops import RoIAlign3D
+    shape = (1, 64, 8, 40, 72)
+    f = _feats(shape, 12)
+    rois = np.array([[0, 2, 3, 250, 120, 1, 12],       # 62 voxels wide: tables too small -> literal path
+                     [0, 10, 8, 140, 150, 2, 14],      # 33 x 36 voxels
+                     [0, 100.5, 20.25, 200, 60, 0, 9],  # 25 voxels wide
+                     [0, 30, 30, 60, 60, 3, 8]], np.float32)
+    for ps, pdp in [(7, 7), (14, 14)]:
+        want = oracle.roi_align3d_forward(f, rois, ps, pdp, 0.25, 0.5, 2)
+        out = RoIAlign3D(ps, pdp, 0.25, 0.5, 2)(cl(torch.from_numpy(f).to(dev)), torch.from_numpy(rois).to(dev))
+        assert rel_err(out.cpu().numpy(), want) <= FWD_TOL
