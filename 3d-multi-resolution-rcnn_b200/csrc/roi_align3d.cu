@@ -91,15 +91,16 @@ struct Item {
   LevelDev L;
 };
 
-__device__ __forceinline__ Item decode_item(const RoiParams &p, long long item, int ROWS) {
+__device__ __forceinline__ Item decode_item(const RoiParams &p, long long item64, int ROWS) {
   Item it;
-  int phg = (int)(item % p.nphg);
-  item /= p.nphg;
-  it.pd = (int)(item % p.PD);
-  item /= p.PD;
-  it.chunk = (int)(item % p.nchunk);
-  it.k = (int)(item / p.nchunk);
-  it.ph0 = phg * ROWS;
+  unsigned item = (unsigned)item64;  // launchers guarantee total_items < 2^31: 32-bit div/mod only
+  const unsigned phg = item % (unsigned)p.nphg;
+  item /= (unsigned)p.nphg;
+  it.pd = (int)(item % (unsigned)p.PD);
+  item /= (unsigned)p.PD;
+  it.chunk = (int)(item % (unsigned)p.nchunk);
+  it.k = (int)(item / (unsigned)p.nchunk);
+  it.ph0 = (int)phg * ROWS;
   it.rows = min(ROWS, p.PH - it.ph0);
   const float *roi = p.rois + (long long)it.k * 7;
   float r[7];
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel
   constexpr int STRIDE = (RXR + 2) * VOX;      // floats per ring stage (two zero pad voxels)
   constexpr int RING = NS * STRIDE;            // floats
   constexpr int STAGE = ROWS * PW * 33;
-  constexpr int LISTS = 80;                    // ylist[<=40] + zlist[<=32] as bytes, rounded up (floats: 20)
+  constexpr int LISTS = 384;                   // ylist[40] + zlist[32] bytes (pad to 80) + yoff[40] + zoff[32] ints
   constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
   constexpr int WARP_FLOATS = (TB::FLOATS + LISTS / 4 + RING_OR_STAGE + 3) / 4 * 4;
   static_assert(LPV <= 32 && VPI >= 1, "voxel chunk wider than a warp copy");
@@ -528,6 +529,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel
   T.bind(sm);
   unsigned char *ylist = reinterpret_cast<unsigned char *>(sm + ((TB::FLOATS + 3) / 4 * 4));
   unsigned char *zlist = ylist + 40;
+  int *yoff = reinterpret_cast<int *>(ylist + 80);
+  int *zoff = yoff + 40;
   float *ring = sm + ((TB::FLOATS + 3) / 4 * 4) + LISTS / 4;
   T.empty = true, T.fits = true;
   if (it.ok) build_tables<PW>(T, it, lane);
@@ -607,9 +610,13 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel
     const float *src0 = fb_roi + ((long long)T.zmin * it.L.H + T.ymin) * row_elems + (long long)T.xmin * C + ch_piece +
                         (long long)cv_v * C;
     float *dst0 = ring + cv_p * 4 + cv_v * VOX;
+    // row offsets in units of 4 floats (16 B; C % 4 == 0), < 2^31 for any level the dispatcher accepts
+    for (int i = lane; i < nz; i += 32) zoff[i] = (int)(((long long)zlist[i] * slice_elems) >> 2);
+    for (int i = lane; i < ny; i += 32) yoff[i] = (int)(((long long)ylist[i] * row_elems) >> 2);
+    __syncwarp();
     int pz = 0, py = 0, pstage = 0;
     auto issue = [&]() {
-      const float *src = src0 + (long long)zlist[pz] * slice_elems + (long long)ylist[py] * row_elems;
+      const float *src = src0 + ((long long)(zoff[pz] + yoff[py]) << 2);
       float *dst = dst0 + pstage * STRIDE;
       if (piece_ok) {
 #pragma unroll 2
@@ -640,10 +647,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel
         const float wz = T.Dz[zlist[zi]];
         const float *row = ring + cstage * STRIDE;
         if (++cstage == NS) cstage = 0;
+        float tz[PW][CV];
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw) {
           const float *q = row + soff[pw];
-          float tz[CV];
 #pragma unroll
           for (int j = 0; j < NXU; ++j) {
             float f[CV];
@@ -657,22 +664,28 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel
               f[0] = q[j * VOX];
             }
 #pragma unroll
-            for (int c = 0; c < CV; ++c) tz[c] = j == 0 ? tw[pw][0] * f[c] : fmaf(tw[pw][j], f[c], tz[c]);
+            for (int c = 0; c < CV; ++c) tz[pw][c] = j == 0 ? tw[pw][0] * f[c] : fmaf(tw[pw][j], f[c], tz[pw][c]);
           }
-          if (long_bins) {
+        }
+        if (long_bins) {  // one warp-uniform test per row; bins wider than NXU taps are rare
+#pragma unroll
+          for (int pw = 0; pw < PW; ++pw) {
             const int lo = T.xlo[pw];
             const int n = T.xhi[pw] - lo + 1;
+            const float *q = row + soff[pw];
             const float *wq = T.Dx + lo * PWP + pw;
 #pragma unroll 1
             for (int j = NXU; j < n; ++j) {
               const float w = wq[j * PWP];
 #pragma unroll
-              for (int c = 0; c < CV; ++c) tz[c] = fmaf(w, q[j * VOX + c], tz[c]);
+              for (int c = 0; c < CV; ++c) tz[pw][c] = fmaf(w, q[j * VOX + c], tz[pw][c]);
             }
           }
-#pragma unroll
-          for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(wz, tz[c], t1[pw][c]);
         }
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+          for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(wz, tz[pw][c], t1[pw][c]);
         __syncwarp();
         if (r + NS - 1 < nrows) issue();
         else cp_async_commit();
@@ -1011,7 +1024,7 @@ static int launch_fwd(RoiParams &p, cudaStream_t st) {
   auto kern = roi_align3d_fwd_cl_kernel<PW, ROWS, CV, NXU>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = ceil_div_ll(p.total_items, kWarps);
-  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
+  ROI3D_CHECK_ARG(p.total_items < 2147483647LL, "roi_align3d forward: too many work items");
   kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
@@ -1024,7 +1037,7 @@ static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   constexpr int RING = NS * (RXR + 2) * VOX;
   constexpr int STAGE = ROWS * PW * 33;
   constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
-  constexpr int WARP_FLOATS = (TB::FLOATS + 80 / 4 + RING_OR_STAGE + 3) / 4 * 4;
+  constexpr int WARP_FLOATS = (TB::FLOATS + 384 / 4 + RING_OR_STAGE + 3) / 4 * 4;
   const size_t smem = (size_t)kWarps * WARP_FLOATS * sizeof(float);
   p.nchunk = ceil_div(p.C, 32 * CV);
   p.nphg = ceil_div(p.PH, ROWS);
@@ -1032,7 +1045,7 @@ static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   auto kern = roi_align3d_fwd_ring_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = ceil_div_ll(p.total_items, kWarps);
-  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
+  ROI3D_CHECK_ARG(p.total_items < 2147483647LL, "roi_align3d forward: too many work items");
   kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
@@ -1052,7 +1065,7 @@ static int launch_bwd(RoiParams &p, cudaStream_t st) {
   auto kern = roi_align3d_bwd_cl_kernel<PW, ROWS, CV, RXR>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = ceil_div_ll(p.total_items, kWarps);
-  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d backward: too many work items");
+  ROI3D_CHECK_ARG(p.total_items < 2147483647LL, "roi_align3d backward: too many work items");
   kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
@@ -1064,7 +1077,7 @@ static int launch_generic(RoiParams &p, bool fwd, cudaStream_t st) {
   p.nphg = p.PH;
   p.total_items = (long long)p.K * p.nchunk * p.PD * p.nphg;
   const long long blocks = ceil_div_ll(p.total_items, kWarps);
-  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d: too many work items");
+  ROI3D_CHECK_ARG(p.total_items < 2147483647LL, "roi_align3d: too many work items");
   if (fwd)
     roi_align3d_fwd_generic_kernel<CV><<<(unsigned)blocks, kWarps * 32, 0, st>>>(p);
   else
@@ -1096,11 +1109,14 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
   for (int l = 0; l < p.num_levels; ++l) ring_ok = ring_ok && aligned(p.lv[l].feats, 16);
   if (p.PW == 7) {
     if (ring_ok && cvmax >= 2) {
-      if (v == 0) return launch_fwd_ring<7, 7, 2, 3, 3, 18>(p, st);
+      if (v == 0) return launch_fwd_ring<7, 7, 2, 3, 4, 18, 2>(p, st);
+      if (v == 13) return launch_fwd_ring<7, 7, 2, 3, 3, 18>(p, st);
       if (v == 5) return launch_fwd_ring<7, 7, 2, 3, 4, 18>(p, st);
       if (v == 6) return launch_fwd_ring<7, 7, 1, 3, 4, 20>(p, st);
       if (v == 7) return launch_fwd_ring<7, 4, 2, 3, 3, 18>(p, st);
       if (v == 8) return launch_fwd_ring<7, 7, 2, 3, 2, 18, 4>(p, st);
+      if (v == 11) return launch_fwd_ring<7, 7, 2, 3, 3, 18, 3>(p, st);
+      if (v == 12) return launch_fwd_ring<7, 7, 2, 3, 4, 18, 2>(p, st);
       if (v == 9) return launch_fwd_ring<7, 7, 2, 3, 2, 18, 3>(p, st);
       if (v == 10) return launch_fwd_ring<7, 4, 2, 3, 2, 18, 4>(p, st);
     }
@@ -1111,6 +1127,8 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
   if (p.PW == 14) {
     if (ring_ok && cvmax >= 2) {
       if (v == 0) return launch_fwd_ring<14, 4, 2, 3, 3, 18>(p, st);
+      if (v == 12) return launch_fwd_ring<14, 4, 2, 3, 4, 18, 2>(p, st);
+      if (v == 11) return launch_fwd_ring<14, 4, 2, 3, 3, 18, 3>(p, st);
       if (v == 5) return launch_fwd_ring<14, 4, 2, 3, 4, 18>(p, st);
       if (v == 6) return launch_fwd_ring<14, 7, 1, 3, 4, 20>(p, st);
       if (v == 7) return launch_fwd_ring<14, 2, 2, 3, 3, 18>(p, st);
@@ -1161,6 +1179,7 @@ static int fill_params(RoiParams &p, const roi3d_level_t *levels, int num_levels
     ROI3D_CHECK_ARG(levels[l].D > 0 && levels[l].H > 0 && levels[l].W > 0, "level %d: bad dims", l);
     ROI3D_CHECK_ARG(bwd ? levels[l].grad_dev != nullptr : levels[l].feats_dev != nullptr, "level %d: NULL pointer", l);
     ROI3D_CHECK_ARG((long long)levels[l].D * levels[l].H * levels[l].W < (1LL << 31), "level %d too large", l);
+    ROI3D_CHECK_ARG((long long)levels[l].D * levels[l].H * levels[l].W * C < (1LL << 33), "level %d too large", l);
     p.lv[l].feats = levels[l].feats_dev;
     p.lv[l].grad = levels[l].grad_dev;
     p.lv[l].D = levels[l].D, p.lv[l].H = levels[l].H, p.lv[l].W = levels[l].W;
