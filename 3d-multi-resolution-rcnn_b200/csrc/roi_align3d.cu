@@ -782,19 +782,28 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
 #pragma unroll
     for (int c = 0; c < CV; ++c) {
       const int cols = min(32, (C - it.chunk * 32 * CV - c + CV - 1) / CV);
-      const int total = cols * NB;
       float *st = stage + c * (NB * 33);
       const long long g0 = ((long long)it.k * C + (long long)it.chunk * 32 * CV + c) * ch_stride + row_base;
-      for (int idx = lane; idx < 32 * NB; idx += 32) {
-        const int cl = idx / NB, bin = idx - cl * NB;
-        float *dst = st + bin * 33 + cl;
-        const long long o = g0 + (long long)cl * col_stride + bin;
-        if (idx < total && o < top_total) {
-          const unsigned sd = (unsigned)__cvta_generic_to_shared(dst);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sd), "l"(p.grad_out + o) : "memory");
-        } else {
-          *dst = 0.0f;
-        }
+      // elements past the end of grad_out can only be addressed with bug_compat's wrong row base
+      long long lim = top_total - g0;
+      int total = cols * NB;
+      if (lim < (long long)(cols - 1) * col_stride + NB) {
+        total = 0;  // rare (last RoI / channel with bug_compat): zero the tile, copy nothing out of range
+      }
+      if (total < 32 * NB) {
+        for (int i = lane; i < NB * 33; i += 32) st[i] = 0.0f;
+        __syncwarp();
+      }
+      // flattened (column, bin) walk, +32 per step with running pointers (cf. copy_out_tile)
+      int cl = 0, bin = lane;
+      while (bin >= NB) bin -= NB, ++cl;
+      unsigned sp = (unsigned)__cvta_generic_to_shared(st + bin * 33 + cl);
+      const float *gp = p.grad_out + g0 + (long long)cl * col_stride + bin;
+      const int s_wrap = (1 - NB * 33) * 4, g_wrap = col_stride - NB;
+      for (int idx = lane; idx < total; idx += 32) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp), "l"(gp) : "memory");
+        bin += 32, sp += 32 * 33 * 4, gp += 32;
+        while (bin >= NB) bin -= NB, sp += s_wrap, gp += g_wrap;
       }
     }
     cp_async_commit();
@@ -844,6 +853,16 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
   const long long row_elems = (long long)it.L.W * C;
   const long long slice_elems = (long long)it.L.H * row_elems;
   float *gbase = gb + ((long long)T.zmin * it.L.H + T.ymin) * row_elems + (long long)T.xmin * C;
+  bool has_gaps = false;
+  for (int x0 = 0; x0 < RX; x0 += 32) has_gaps |= __any_sync(FULL, x0 + lane < RX && !T.xany[x0 + lane]);
+  float zw[4];
+  long long zo[4];
+#pragma unroll
+  for (int zi = 0; zi < 4; ++zi) {
+    const int zrel = zi < nz ? zlist[zi] : 0;
+    zw[zi] = zi < nz ? T.Dz[zrel] : 0.0f;
+    zo[zi] = (long long)zrel * slice_elems;
+  }
   for (int yi = 0; yi < ny; ++yi) {
     const int yy = ylist[yi];
     float wy[8];
@@ -887,19 +906,32 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
       for (int c = 0; c < CV; ++c) ux[xx * VOX + lane * CV + c] = v[c];
     }
     __syncwarp();
-    // scatter: one vector red per (z, x) voxel of this y row
-    float *rowy = gbase + (long long)yy * row_elems;
-    for (int zi = 0; zi < nz; ++zi) {
-      const int zrel = zlist[zi];
-      const float wz = T.Dz[zrel];
-      float *q = rowy + (long long)zrel * slice_elems;
-#pragma unroll 2
-      for (int xx = 0; xx < RX; ++xx) {
-        if (!T.xany[xx]) continue;
+    // scatter: one vector red per (z, x) voxel of this y row.  x is the outer loop so each ux value is read
+    // once; the (typically 2-3) z slices are handled by a predicated unrolled inner loop whose weights and
+    // slice offsets live in registers.
+    float *q = gbase + (long long)yy * row_elems;
+    const float *uxl = ux + lane * CV;
+    for (int xx = 0; xx < RX; ++xx, q += C) {
+      if (has_gaps && !T.xany[xx]) continue;
+      float uv[CV];
+#pragma unroll
+      for (int c = 0; c < CV; ++c) uv[c] = uxl[xx * VOX + c];
+#pragma unroll
+      for (int zi = 0; zi < 4; ++zi) {
+        if (zi < nz) {
+          float v[CV];
+#pragma unroll
+          for (int c = 0; c < CV; ++c) v[c] = zw[zi] * uv[c];
+          if (active) redv<CV>(q + zo[zi], v);
+        }
+      }
+      for (int zi = 4; zi < nz; ++zi) {
+        const int zrel = zlist[zi];
+        const float wz = T.Dz[zrel];
         float v[CV];
 #pragma unroll
-        for (int c = 0; c < CV; ++c) v[c] = wz * ux[xx * VOX + lane * CV + c];
-        if (active) redv<CV>(q + (long long)xx * C, v);
+        for (int c = 0; c < CV; ++c) v[c] = wz * uv[c];
+        if (active) redv<CV>(q + (long long)zrel * slice_elems, v);
       }
     }
   }
