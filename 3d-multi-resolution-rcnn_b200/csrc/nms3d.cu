@@ -11,10 +11,11 @@
 //                         sorted 32-byte records that also carry the per-box volume factors;
 //   2. mask kernel     -- upper-triangular 64x64 tiles only, column boxes staged in shared memory,
 //                         one uint64 word per (row, column-tile);
-//   3. sweep kernel    -- one CTA per segment walks the 64-box diagonal tiles: a single thread resolves
-//                         a tile from its 64 diagonal words held in shared memory, then all threads OR the
-//                         kept rows into the `removed` words of the later tiles; the kept set is then
-//                         compacted twice (ascending original index, and descending score).
+//   3. sweep kernel    -- one CTA per segment walks the 64-box diagonal tiles as a pipeline: warp 0 resolves
+//                         tile b (one lane, the 64 diagonal words in registers) and updates the next tile's
+//                         `removed` word itself, while warps 1..7 apply tile b-1 to the later words and
+//                         prefetch the mask rows of tile b+2 with cp.async; the kept set is then compacted
+//                         position-parallel twice (descending score, and ascending original index).
 // No host synchronisation, no D2H copy; many (volume, level, class) segments share the three launches.
 //
 // Bit-exactness: IoU uses explicit _rn intrinsics in exactly the operation order of the compiled
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256) nms3d_mask_kernel(const SortedBox *__rest
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxColBlocks = 512;   // n_max <= 32768 (static shared memory budget)
 constexpr int kPanelW = 32;           // words of each mask row held in shared memory per diagonal tile
+constexpr int kPanelBufs = 4;         // tile b-1 (apply), b (resolve), b+1 (landed), b+2 (in flight)
 
 __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long long *__restrict__ mask,
                                                           const int32_t *__restrict__ order,
@@ -162,23 +164,32 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
 
   __shared__ unsigned long long remv[kMaxColBlocks];
   __shared__ unsigned long long keptw[kMaxColBlocks];
-  __shared__ unsigned long long panel[2][64][kPanelW];
-  __shared__ unsigned long long s_kept;
+  extern __shared__ __align__(16) unsigned long long panel_dyn[];  // [kPanelBufs][64][kPanelW]
+  auto panel = [&](int buf, int row, int w) -> unsigned long long & {
+    return panel_dyn[((size_t)buf * 64 + row) * kPanelW + w];
+  };
   __shared__ int s_warp[8];
-  __shared__ int s_base;
 
   for (int i = tid; i < cb; i += 256) remv[i] = 0ULL;
-  for (int i = tid; i < n; i += 256) fl[i] = 0;
+  for (int i = tid; i < cb; i += 256) keptw[i] = 0ULL;
 
-  // Row panels: for diagonal tile `blk` the words [blk, blk+kPanelW) of its 64 mask rows, copied to shared
-  // memory with cp.async one tile ahead of the resolve (the rows do not depend on the sweep state).
-  auto prefetch = [&](int blk, int buf) {
+  // Pipeline over the 64-box diagonal tiles, one __syncthreads per tile:
+  //   warp 0 (resolver)   resolves tile b from panel[b%4] (lane 0: the 64 diagonal words in registers, a
+  //                       test -> predicated-OR chain on 32-bit halves), then ORs the kept rows into word b+1
+  //                       itself, so the next tile's state is complete without waiting for anyone;
+  //   warps 1..7 (helpers) meanwhile apply tile b-1's kept rows (panel[(b-1)%4]) to the words >= b+1 and
+  //                       prefetch tile b+2's rows (words [b+2, b+2+kPanelW) of its 64 mask rows) with
+  //                       cp.async into panel[(b+2)%4] (two tiles ahead hides the L2 round trip); the mask
+  //                       rows do not depend on the sweep state.
+  const int warp = tid >> 5, lane = tid & 31;
+  auto prefetch = [&](int blk) {  // helpers only: 224 threads
     if (blk < cb) {
+      const int buf = blk % kPanelBufs;
       const int nwp = min(kPanelW, cb - blk);
-      for (int idx = tid; idx < 64 * kPanelW; idx += 256) {
+      for (int idx = tid - 32; idx < 64 * kPanelW; idx += 224) {
         const int row = idx / kPanelW, w = idx - row * kPanelW;
         const int grow = blk * 64 + row;
-        unsigned long long *dst = &panel[buf][row][w];
+        unsigned long long *dst = &panel(buf, row, w);
         if (grow < n && w < nwp) {
           const unsigned sd = (unsigned)__cvta_generic_to_shared(dst);
           asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sd), "l"(m + (long long)grow * cbm + blk + w)
@@ -190,141 +201,180 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
-  prefetch(0, 0);
+  if (warp > 0) {
+    prefetch(0);
+    prefetch(1);
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // tile 0 landed, tile 1 may still be in flight
+  }
   __syncthreads();
 
   for (int blk = 0; blk < cb; ++blk) {
-    const int buf = blk & 1;
-    prefetch(blk + 1, buf ^ 1);
-    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    __syncthreads();
-    const int bs = min(64, n - blk * 64);
-    if (tid == 0) {
-      // serial resolve of the diagonal tile with all 64 diagonal words in registers (fully unrolled:
-      // the bit tests use compile-time positions, the chain is test -> predicated OR)
-      // 32-bit halves: the test of step i is a single LOP3 on a compile-time bit, the update a predicated OR.
-      // Row i only carries bits j > i, so rows >= 32 have an empty low word.
-      unsigned dlo[32], dhi[64];
+    if (warp == 0) {
+      const int buf = blk % kPanelBufs;
+      const int bs = min(64, n - blk * 64);
+      unsigned long long kept = 0ULL;
+      if (lane == 0) {
+        unsigned dlo[32], dhi[64];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const unsigned long long d = panel[buf][i][0];
-        if (i < 32) dlo[i] = (unsigned)d;
-        dhi[i] = (unsigned)(d >> 32);
-      }
-      unsigned long long r0 = remv[blk];
-      if (bs < 64) r0 |= ~0ULL << bs;  // rows past n never count as kept
-      unsigned rlo = (unsigned)r0, rhi = (unsigned)(r0 >> 32), klo = 0u, khi = 0u;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (!(rlo & (1u << i))) {
-          klo |= 1u << i;
-          rlo |= dlo[i];
-          rhi |= dhi[i];
+        for (int i = 0; i < 64; ++i) {
+          const unsigned long long d = panel(buf, i, 0);
+          if (i < 32) dlo[i] = (unsigned)d;
+          dhi[i] = (unsigned)(d >> 32);
         }
-      }
+        // pin all 96 words in registers before the chain starts (otherwise ptxas sinks the shared-memory
+        // loads into the chain and every step pays their latency)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (!(rhi & (1u << i))) {
-          khi |= 1u << i;
-          rhi |= dhi[32 + i];
+        for (int i = 0; i < 64; ++i) {
+          if (i < 32) asm volatile("" : "+r"(dlo[i]));
+          asm volatile("" : "+r"(dhi[i]));
         }
+        unsigned long long r0 = remv[blk];
+        if (bs < 64) r0 |= ~0ULL << bs;  // rows past n never count as kept
+        unsigned rlo = (unsigned)r0, rhi = (unsigned)(r0 >> 32), klo = 0u, khi = 0u;
+        asm volatile("" : "+r"(rlo), "+r"(rhi));  // ordered after the pins above: the chain starts with all words loaded
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (!(rlo & (1u << i))) {
+            klo |= 1u << i;
+            rlo |= dlo[i];
+            rhi |= dhi[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (!(rhi & (1u << i))) {
+            khi |= 1u << i;
+            rhi |= dhi[32 + i];
+          }
+        }
+        kept = ((unsigned long long)khi << 32) | klo;
+        keptw[blk] = kept;
       }
-      const unsigned long long kept = ((unsigned long long)khi << 32) | klo;
-      s_kept = kept;
-      keptw[blk] = kept;
-    }
-    __syncthreads();
-    const unsigned long long kept = s_kept;
-    const int nw = cb - blk - 1;
-    if (nw > 0) {
-      // words blk+1 .. blk+kPanelW-1 from the panel: thread -> (word w, 8-row group g)
-      const int nwp = min(kPanelW - 1, nw);
-      {
-        const int w = 1 + (tid & (kPanelW - 1)), g = tid / kPanelW;  // kPanelW == 32, 256 threads -> g in [0,8)
+      kept = __shfl_sync(0xffffffffu, kept, 0);
+      if (blk + 1 < cb) {
+        // word blk+1: lanes take rows lane and lane+32, OR-reduce across the warp
+        unsigned long long v = 0ULL;
+        if ((kept >> lane) & 1ULL) v |= panel(buf, lane, 1);
+        if ((kept >> (lane + 32)) & 1ULL) v |= panel(buf, lane + 32, 1);
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+        if (lane == 0) atomicOr(&remv[blk + 1], ((unsigned long long)hi << 32) | lo);
+      }
+    } else {
+      // helpers: finish tile blk-1 (words >= blk+1), then fetch tile blk+1
+      if (blk >= 1) {
+        const int pb = blk - 1, buf = pb % kPanelBufs;
+        const unsigned long long kept = keptw[pb];
+        const int nw = cb - pb - 1;              // words after the diagonal of tile pb
+        const int nwp = min(kPanelW - 1, nw);    // of which the panel holds nwp (w = 1..nwp)
+        // panel words w = 2..nwp  (w = 1 was applied by the resolver): thread -> (word, 8-row group)
+        const int ht = tid - 32;                 // 0..223
+        const int w = 2 + (ht & 31), g = ht >> 5;  // g in 0..6 -> rows are split 7 ways (10 rows each, last 4)
         if (w <= nwp) {
           unsigned long long v = 0ULL;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int row = g * 8 + q;
-            if ((kept >> row) & 1ULL) v |= panel[buf][row][w];
+          const int r0 = g * 10, r1 = min(64, r0 + 10);
+          for (int row = r0; row < r1; ++row)
+            if ((kept >> row) & 1ULL) v |= panel(buf, row, w);
+          if (v) atomicOr(&remv[pb + w], v);
+        }
+        // words beyond the panel (only when n > 64*kPanelW): straight from global memory
+        for (int idx = ht; idx < (nw - nwp) * 64; idx += 224) {
+          const int i = idx / (nw - nwp), ww = pb + 1 + nwp + idx % (nw - nwp);
+          if ((kept >> i) & 1ULL) {
+            const unsigned long long v = m[((long long)pb * 64 + i) * cbm + ww];
+            if (v) atomicOr(&remv[ww], v);
           }
-          if (v) atomicOr(&remv[blk + w], v);
         }
       }
-      // words beyond the panel (only when n > 64*kPanelW): straight from global memory
-      for (int idx = tid; idx < (nw - nwp) * 64; idx += 256) {
-        const int i = idx / (nw - nwp), w = blk + 1 + nwp + idx % (nw - nwp);
-        if ((kept >> i) & 1ULL) {
-          const unsigned long long v = m[((long long)blk * 64 + i) * cbm + w];
-          if (v) atomicOr(&remv[w], v);
-        }
-      }
+      prefetch(blk + 2);                                       // two tiles ahead: hides the L2 round trip
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // tile blk+1 has landed
     }
     __syncthreads();
   }
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  // the last tile's kept rows have no later words to update; nothing left to apply
 
-  // ---- kept set -> (a) descending-score list, (b) flags by original index ----
-  if (tid == 0) s_base = 0;
+  // ---- kept set -> (a) descending-score list, (b) ascending original index ----
+  // Everything below is position-parallel: no per-thread serial chains of dependent global loads.
+  __shared__ int excl[kMaxColBlocks];           // exclusive prefix of popc(keptw)
+  __shared__ unsigned bitmap[kMaxColBlocks * 2];  // kept flags by ORIGINAL index
+  __shared__ int s_total;
+  // (1) block scan of the per-word kept counts (cb <= 512: two words per thread)
+  {
+    const int w0 = tid * 2;
+    const int c0 = w0 < cb ? __popcll(keptw[w0]) : 0;
+    const int c1 = w0 + 1 < cb ? __popcll(keptw[w0 + 1]) : 0;
+    int incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q < warp) woff += s_warp[q];
+      tot += s_warp[q];
+    }
+    const int base = woff + incl - (c0 + c1);
+    if (w0 < cb) excl[w0] = base;
+    if (w0 + 1 < cb) excl[w0 + 1] = base + c0;
+    if (tid == 0) s_total = tot;
+    for (int i = tid; i < ((n + 31) >> 5); i += 256) bitmap[i] = 0u;
+    __syncthreads();
+  }
+  const int total = s_total;
+  // (2) every sorted position in parallel: rank among the kept, original index (coalesced load)
+  for (int pos = tid; pos < n; pos += 256) {
+    const unsigned long long kw = keptw[pos >> 6];
+    const int b = pos & 63;
+    if ((kw >> b) & 1ULL) {
+      const int rank = excl[pos >> 6] + __popcll(kw & ((1ULL << b) - 1ULL));
+      const int orig = ord[pos];
+      if (kps) kps[rank] = orig;
+      atomicOr(&bitmap[orig >> 5], 1u << (orig & 31));
+    }
+  }
   __syncthreads();
-  for (int w0 = 0; w0 < cb; w0 += 256) {
-    const int w = w0 + tid;
-    const unsigned long long kw = w < cb ? keptw[w] : 0ULL;
-    const int cnt = __popcll(kw);
-    // block exclusive scan of cnt
+  // (3) ascending original index: scan the bitmap words (<= 1024: four per thread), then write out
+  {
+    const int nbw = (n + 31) >> 5;
+    unsigned wds[4];
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int w = tid * 4 + q;
+      wds[q] = w < nbw ? bitmap[w] : 0u;
+      cnt += __popc(wds[q]);
+    }
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((tid & 31) >= o) incl += t;
+      if (lane >= o) incl += t;
     }
-    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
     __syncthreads();
-    int woff = 0, tot = 0;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int woff = 0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (q < (tid >> 5)) woff += s_warp[q];
-      tot += s_warp[q];
-    }
-    int pos = s_base + woff + incl - cnt;
-    unsigned long long bits = kw;
-    while (bits) {
-      const int b = __ffsll((long long)bits) - 1;
-      bits &= bits - 1;
-      const int orig = ord[w * 64 + b];
-      if (kps) kps[pos] = orig;
-      fl[orig] = 1;
-      ++pos;
-    }
-    __syncthreads();
-    if (tid == 0) s_base += tot;
-    __syncthreads();
-  }
-  const int total = s_base;
-  __syncthreads();
-
-  // ---- ascending original index: ordered compaction of flags ----
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += 256) {
-    const int i = i0 + tid;
-    const int f = (i < n) ? fl[i] : 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    const int lane = tid & 31;
-    if (lane == 0) s_warp[tid >> 5] = __popc(bal);
-    __syncthreads();
-    int woff = 0, tot = 0;
+    for (int q = 0; q < 8; ++q)
+      if (q < warp) woff += s_warp[q];
+    int outp = woff + incl - cnt;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (q < (tid >> 5)) woff += s_warp[q];
-      tot += s_warp[q];
+    for (int q = 0; q < 4; ++q) {
+      unsigned bits = wds[q];
+      const int base_idx = (tid * 4 + q) * 32;
+      while (bits) {
+        const int bb = __ffs((int)bits) - 1;
+        bits &= bits - 1;
+        kp[outp++] = base_idx + bb;
+      }
     }
-    if (f) kp[s_base + woff + __popc(bal & ((1u << lane) - 1u))] = i;
-    __syncthreads();
-    if (tid == 0) s_base += tot;
-    __syncthreads();
   }
   if (tid == 0) num_keep[seg] = total;
+  (void)fl;
 }
 
 struct NmsWorkspace {
@@ -392,8 +442,12 @@ int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, in
   nms3d_mask_kernel<<<dim3(ceil_div(cbm, 4), cbm, nseg), 256, 0, st>>>(w.sorted, seg_counts_dev, n_max, iou_thr,
                                                                        w.mask);
   ROI3D_LAUNCH_CHECK();
-  nms3d_sweep_kernel<<<nseg, 256, 0, st>>>(w.mask, w.order, seg_counts_dev, n_max, w.flags, keep_dev,
-                                           keep_by_score_dev, num_keep_dev);
+  {
+    const size_t panel_bytes = (size_t)kPanelBufs * 64 * kPanelW * sizeof(unsigned long long);  // 64 KiB
+    ROI3D_CUDA(cudaFuncSetAttribute(nms3d_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_bytes));
+    nms3d_sweep_kernel<<<nseg, 256, panel_bytes, st>>>(w.mask, w.order, seg_counts_dev, n_max, w.flags, keep_dev,
+                                                      keep_by_score_dev, num_keep_dev);
+  }
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
 }

@@ -317,24 +317,18 @@ __device__ __forceinline__ void copy_out_tile(const float (&acc)[ROWS][PW][CV], 
       for (int pw = 0; pw < PW; ++pw) stage[(r * PW + pw) * 33 + lane] = acc[r][pw][c] * inv;
     __syncwarp();
     const int cols = min(32, (C - chunk * 32 * CV - c + CV - 1) / CV);  // columns whose channel is < C
-    const int total = cols * NB;
     float *dst = out_tile + ((long long)chunk * 32 * CV + c) * ch_stride;
-    if (NB >= 32) {
-      // +32 per step crosses at most one column boundary: running pointers with a predicated fix-up
-      int bin = lane;
-      const float *sp = stage + lane * 33;
-      float *gp = dst + lane;
-      const int s_wrap = 1 - NB * 33, g_wrap = col_stride - NB;
-      for (int idx = lane; idx < total; idx += 32) {
-        __stcs(gp, *sp);
-        bin += 32, sp += 32 * 33, gp += 32;
-        if (bin >= NB) bin -= NB, sp += s_wrap, gp += g_wrap;
-      }
-    } else {
-      for (int idx = lane; idx < total; idx += 32) {
-        const int cl = idx / NB, bin = idx - cl * NB;
-        __stcs(dst + (long long)cl * col_stride + bin, stage[bin * 33 + cl]);
-      }
+    // one column (= one channel's contiguous run of NB floats) at a time, lanes along the run:
+    // ceil(NB/32) predicated stores per column, no index arithmetic beyond two pointer bumps
+    const float *sp = stage + lane * 33;
+    float *gp = dst + lane;
+#pragma unroll 4
+    for (int cl = 0; cl < cols; ++cl) {
+      if (lane < NB) __stcs(gp, sp[0]);
+      if (lane + 32 < NB) __stcs(gp + 32, sp[32 * 33]);
+      for (int bin = lane + 64; bin < NB; bin += 32) __stcs(gp + (bin - lane), sp[(bin - lane) * 33]);
+      sp += 1;
+      gp += col_stride;
     }
   }
 }
@@ -794,16 +788,20 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
         for (int i = lane; i < NB * 33; i += 32) st[i] = 0.0f;
         __syncwarp();
       }
-      // flattened (column, bin) walk, +32 per step with running pointers (cf. copy_out_tile)
-      int cl = 0, bin = lane;
-      while (bin >= NB) bin -= NB, ++cl;
-      unsigned sp = (unsigned)__cvta_generic_to_shared(st + bin * 33 + cl);
-      const float *gp = p.grad_out + g0 + (long long)cl * col_stride + bin;
-      const int s_wrap = (1 - NB * 33) * 4, g_wrap = col_stride - NB;
-      for (int idx = lane; idx < total; idx += 32) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp), "l"(gp) : "memory");
-        bin += 32, sp += 32 * 33 * 4, gp += 32;
-        while (bin >= NB) bin -= NB, sp += s_wrap, gp += g_wrap;
+      // one column (channel run of NB floats) at a time, lanes along the run (cf. copy_out_tile)
+      const int ncol = total / NB;
+      unsigned sp = (unsigned)__cvta_generic_to_shared(st + lane * 33);
+      const float *gp = p.grad_out + g0 + lane;
+#pragma unroll 4
+      for (int cl = 0; cl < ncol; ++cl) {
+        if (lane < NB) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp), "l"(gp) : "memory");
+        if (lane + 32 < NB)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp + 32 * 33 * 4), "l"(gp + 32) : "memory");
+        for (int bin = lane + 64; bin < NB; bin += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp + (bin - lane) * 33 * 4), "l"(gp + (bin - lane))
+                       : "memory");
+        sp += 4;
+        gp += col_stride;
       }
     }
     cp_async_commit();
