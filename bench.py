@@ -196,6 +196,7 @@ def run_reference(args):
     import oracle
     import synth
     oracle.build()
+    oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     rng = np.random.default_rng(1)
     feats = rng.standard_normal((C2["B"], C2["C"], C2["D"], C2["H"], C2["W"]), dtype=np.float32)
     rois = synth.c2_rois(C2["K"], seed=2)
@@ -327,17 +328,17 @@ def main():
         alg_bytes = out_bytes + U * C2["C"] * 4 + C2["K"] * 28
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "r01_c2_fwd_ncu_summary.json")
+        prof = os.path.join(ROOT, "profiles", "r01_final_c2_fwd_ncu_summary.json")
         if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_ring_kernel<7,7,2>", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_ring_kernel<7,7,2,3,4,18,2>", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes": alg_bytes, "unique_voxels": U, "kernel_us": kernel_ms * 1e3,
                     "output_only_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9}
-        cpu = cpu_baseline()
+        cpu = cpu_baseline() if world == 1 else None  # reported on rank 0 at N=1 only
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -361,6 +362,7 @@ def cpu_baseline():
     import oracle
     import synth
     oracle.build()
+    oracle.set_num_threads(os.cpu_count() or 1)
     rng = np.random.default_rng(1)
     feats = rng.standard_normal((C2["B"], C2["C"], C2["D"], C2["H"], C2["W"]), dtype=np.float32)
     rois = synth.c2_rois(C2["K"], seed=2)
