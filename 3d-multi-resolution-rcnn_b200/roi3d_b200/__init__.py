@@ -20,8 +20,10 @@ from .core.anchor import AnchorGenerator3D
 from .core.bbox import bbox2roi3D, delta2bbox3D
 from .core.post_processing import multiclass_nms_3d
 from .models.anchor_heads import RPNProposal3D
+from .models.builder import build_roi_extractor, build_rpn_proposal
 from .models.roi_extractors import SingleRoIExtractor
 from .ops import RoIAlign3D, nms, roi_align_3d, soft_nms
 
 __all__ = ['ops', 'nms', 'soft_nms', 'RoIAlign3D', 'roi_align_3d', 'SingleRoIExtractor', 'RPNProposal3D',
-           'AnchorGenerator3D', 'delta2bbox3D', 'bbox2roi3D', 'multiclass_nms_3d']
+           'AnchorGenerator3D', 'delta2bbox3D', 'bbox2roi3D', 'multiclass_nms_3d', 'build_roi_extractor',
+           'build_rpn_proposal']

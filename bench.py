@@ -486,6 +486,35 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ex["c4_volumes_per_sec"] = Bv / dt
     ex["c4_anchors_scored_per_sec"] = Bv * sum(int(np.prod(d)) for d in dims4) / dt
     ex["c4_proposals_out"] = [int(p.shape[0]) for p in props]
+    del cls, reg, props
+    torch.cuda.empty_cache()
+    # C5: RoI stage of configs/3d-multi-resolution-rcnn.py (proposals -> bbox extractor 7x7x3 -> FC head -> decode ->
+    # multiclass NMS -> mask extractor 14x14x10 -> conv mask head), one 512x512x160 volume, 64-ch pyramids, random init.
+    # Heads are plain torch layers (out of scope); wall time of the whole stage and of its hot-path part.
+    import roi_stage
+    stage = roi_stage.RoIStage(max_masks=100).to(dev)
+    feats5, cls5, reg5, metas5 = roi_stage.synthetic_inputs(1, device=dev)
+    stage(feats5, cls5, reg5, metas5)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        out5 = stage(feats5, cls5, reg5, metas5)
+    torch.cuda.synchronize()
+    ex["c5_roi_stage_1vol_us"] = (time.perf_counter() - t0) / 3 * 1e6
+    ex["c5_detections"] = int(out5[0][0].shape[0])
+
+    def hot_only():
+        props5 = stage.rpn.get_bboxes(cls5, reg5, metas5, roi_stage.TEST_CFG_RPN)
+        rois5 = roi3d_b200.bbox2roi3D(props5)
+        stage.bbox_ex(feats5[:4], rois5)
+        stage.mask_ex(feats5[:4], rois5[:100].contiguous())
+    hot_only()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        hot_only()
+    torch.cuda.synchronize()
+    ex["c5_hot_path_only_us"] = (time.perf_counter() - t0) / 3 * 1e6
     return ex
 
 

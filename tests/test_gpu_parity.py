@@ -427,3 +427,31 @@ def test_roi_align_forward_wide_rois(oracle, dev):
         want = oracle.roi_align3d_forward(f, rois, ps, pdp, 0.25, 0.5, 2)
         out = RoIAlign3D(ps, pdp, 0.25, 0.5, 2)(cl(torch.from_numpy(f).to(dev)), torch.from_numpy(rois).to(dev))
         assert rel_err(out.cpu().numpy(), want) <= FWD_TOL
+
+
+def test_reference_config_roi_stage(oracle, dev):
+    """C5 harness at a small volume: the reference's config dicts build the drop-in modules unchanged and the whole
+    RoI stage runs; the hot-path pieces inside it are re-checked against the oracle."""
+    import roi3d_b200
+    import roi_stage
+    stage = roi_stage.RoIStage(max_masks=20).to(dev)
+    assert stage.bbox_ex.roi_layers[0].out_size == 7 and stage.bbox_ex.roi_layers[0].out_size_depth == 3
+    assert stage.mask_ex.roi_layers[3].spatial_scale == 1 / 32
+    feats, cls, reg, metas = roi_stage.synthetic_inputs(1, vol_dhw=(32, 128, 128), device=dev)
+    out = stage(feats, cls, reg, metas)
+    det, lab, masks = out[0]
+    assert det.shape[1] == 7 and lab.dtype == torch.int64 and det.shape[0] == lab.shape[0]
+    assert det.shape[0] > 0, "random heads should leave some detections above score_thr=0.2"
+    assert masks.shape[1:] == (2, 20, 28, 28)          # deconv doubles 10x14x14 (mask_size 28 / depth 20, config :121-122)
+    # the extractor inside the stage vs the oracle, on the stage's own proposals
+    props = stage.rpn.get_bboxes(cls, reg, metas, roi_stage.TEST_CFG_RPN)
+    rois = roi3d_b200.bbox2roi3D(props)[:64].contiguous()
+    got = stage.bbox_ex(feats[:4], rois).cpu().numpy()
+    rn = rois.cpu().numpy()
+    lv = oracle.map_roi_levels(rn, 4)
+    want = np.zeros_like(got)
+    for l, (s, ds) in enumerate(zip([4, 8, 16, 32], [2, 4, 8, 16])):
+        sel = lv == l
+        if sel.any():
+            want[sel] = oracle.roi_align3d_forward(feats[l].cpu().numpy(), rn[sel], 7, 3, 1 / s, 1 / ds, 2)
+    assert rel_err(got, want) <= FWD_TOL
