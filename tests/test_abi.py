@@ -71,3 +71,32 @@ def test_cpu_inputs_fail_loudly():
         nms([[0, 0, 1, 1, 0, 1, .5]], 0.5)
     d, i = nms(torch.zeros(0, 7), 0.5)
     assert d.shape == (0, 7) and i.dtype == torch.long and i.numel() == 0
+
+
+def test_argument_errors_are_codes_with_messages_not_prints_or_exits():
+    """Argument validation happens before any CUDA call, so it can be exercised without a GPU.  The reference prints
+    and returns 0 (roi_align_cuda.cpp:80-83) or calls exit(-1) (roi_align_kernel.cu:679-682) on bad input."""
+    import ctypes
+
+    import roi3d_b200
+    from roi3d_b200 import _lib
+    lib = _lib.lib
+    lv = (_lib.Level * 1)()
+    lv[0].layout = _lib.NCDHW          # the kernels need channels-last: must be refused, not mis-read
+    lv[0].D, lv[0].H, lv[0].W = 4, 4, 4
+    lv[0].feats_dev = 1 << 20
+    rc = lib.roi3d_extract_forward(lv, 1, 1, 32, 1 << 20, 5, 7, 7, 7, 2, 56.0, 1 << 20, None, None)
+    assert rc == -1 and b"channels-last" in lib.roi3d_last_error()
+    rc = lib.roi3d_extract_forward(lv, 0, 1, 32, None, 0, 7, 7, 7, 2, 56.0, None, None, None)
+    assert rc == -1 and b"num_levels" in lib.roi3d_last_error()
+    rc = lib.roi3d_nms3d_batched(None, None, -1, 10, 0.5, None, None, None, None, 0, None)
+    assert rc == -1
+    rc = lib.roi3d_nms3d_batched(1 << 20, None, 1, 1 << 20, 0.5, 1 << 20, None, 1 << 20, 1 << 20, 1 << 30, None)
+    assert rc == -1 and b"n_max" in lib.roi3d_last_error()
+    with __import__("pytest").raises(_lib.Roi3dError):
+        _lib.check(lib.roi3d_topk_segmented(None, None, None, None, 1, 5, 0, None, None, None, 0, None))
+    assert lib.roi3d_set_tuning(77, 0) == -1
+    # empty work is a no-op success, as in the reference wrapper (nms_wrapper.py:39-40)
+    assert lib.roi3d_nms3d_batched(None, None, 0, 0, 0.5, None, None, None, None, 0, None) == 0
+    n = ctypes.c_int32(7)
+    assert lib.roi3d_nms3d_host(None, 0, 0.5, None, ctypes.addressof(n)) == 0 and n.value == 0

@@ -455,3 +455,71 @@ def test_reference_config_roi_stage(oracle, dev):
         if sel.any():
             want[sel] = oracle.roi_align3d_forward(feats[l].cpu().numpy(), rn[sel], 7, 3, 1 / s, 1 / ds, 2)
     assert rel_err(got, want) <= FWD_TOL
+
+
+# --------------------------------------------------------------- full BASELINE sizes, size-independent properties
+def test_c2_full_size_properties(oracle, dev):
+    """BASELINE C2 at full size (256ch x 40x128x128, 512 RoIs): partition of unity, linearity, forward/backward
+    adjointness, and a sampled check against the oracle on a channel subset."""
+    from roi3d_b200.ops import RoIAlign3D
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    shape = (1, 256, 40, 128, 128)
+    x = cl(torch.randn(shape, device=dev, generator=g))
+    y = cl(torch.randn(shape, device=dev, generator=g))
+    rois_np = synth.c2_rois(512, seed=2)
+    rois = torch.from_numpy(rois_np).to(dev)
+    layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
+    fx, fy = layer(x, rois), layer(y, rois)
+    # every C2 RoI lies inside the map, so all 8 samples of every bin are valid: weights sum to one
+    ones = layer(cl(torch.full(shape, 3.25, device=dev)), rois)
+    assert float((ones - 3.25).abs().max()) <= 1e-5
+    lin = layer(cl(2.0 * x - 0.5 * y), rois)
+    assert float((lin - (2.0 * fx - 0.5 * fy)).abs().max()) <= 2e-5
+    # sampled oracle check: 3 channels, all RoIs
+    ch = [0, 101, 255]
+    want = oracle.roi_align3d_forward(x[:, ch].cpu().numpy(), rois_np, 7, 7, 0.25, 0.5, 2)
+    assert rel_err(fx[:, ch].cpu().numpy(), want) <= FWD_TOL
+    # adjointness <f(x), g> == <x, f^T(g)> in float64
+    xg = x.clone().requires_grad_(True)
+    out = layer(xg, rois)
+    gout = torch.randn(out.shape, device=dev, generator=g)
+    out.backward(gout)
+    lhs = float((out.detach().double() * gout.double()).sum())
+    rhs = float((x.double() * xg.grad.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_c1_full_size_properties(oracle, dev):
+    """BASELINE C1 (2000 clustered boxes, thr 0.7): bit-exact keep, ascending order, idempotence, and no kept pair
+    overlaps above the threshold."""
+    from roi3d_b200.ops import nms
+    dets = synth.c1_boxes(2000, seed=0)
+    t = torch.from_numpy(dets).to(dev)
+    kept, inds = nms(t, 0.7)
+    assert np.array_equal(inds.cpu().numpy(), oracle.nms3d(dets, 0.7))
+    assert bool((inds[1:] > inds[:-1]).all())
+    kept2, inds2 = nms(kept, 0.7)
+    assert inds2.numel() == kept.shape[0] and torch.equal(kept2, kept)
+    k = kept.cpu().numpy()
+    order = np.argsort(-k[:, 6], kind="stable")
+    k = k[order]
+    for i in range(0, len(k), 97):
+        for j in range(i + 1, min(i + 40, len(k))):
+            assert not oracle.iou3d(k[i, :6], k[j, :6]) > 0.7
+
+
+def test_topk_full_p2_level_and_large_segment(oracle, dev):
+    """Top-k over a full P2 level (1.31 M scores) and a 4.4 M-score segment (1.5x scale): same values as
+    torch.topk, indices exact against the oracle's tie rule."""
+    from roi3d_b200.models.anchor_heads import topk_segmented
+    g = torch.Generator(device=dev)
+    g.manual_seed(6)
+    for n, k in [(80 * 128 * 128, 2000), (4423680, 2000)]:
+        s = 2 * torch.randn(n, device=dev, generator=g)
+        idx, val = topk_segmented([s], k)
+        tv, ti = torch.topk(s, k)
+        assert torch.equal(val[0], tv)
+        assert torch.equal(s[idx[0]], tv)
+        want = oracle.topk(s.cpu().numpy(), k)
+        assert np.array_equal(idx[0].cpu().numpy(), want)
