@@ -28,7 +28,15 @@ struct Scratch {
   cudaStream_t stream = nullptr;
   std::mutex mu;
 };
-static Scratch g_scratch;
+static Scratch g_scratch_dev[64];  // one grow-only scratch per CUDA device (one process may drive several)
+
+static int current_scratch(Scratch **out) {
+  int dev = 0;
+  ROI3D_CUDA(cudaGetDevice(&dev));
+  ROI3D_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  *out = &g_scratch_dev[dev];
+  return ROI3D_OK;
+}
 
 static int ensure(Scratch &s, size_t dev_bytes, size_t pin_bytes) {
   if (!s.stream) ROI3D_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -78,6 +86,12 @@ int roi3d_nms3d_host(const float *dets_host, int n, float iou_thr, int64_t *keep
     return ROI3D_OK;
   }
   ROI3D_CHECK_ARG(dets_host && keep_host, "NULL pointer");
+  Scratch *sc = nullptr;
+  {
+    int rc0 = current_scratch(&sc);
+    if (rc0) return rc0;
+  }
+  Scratch &g_scratch = *sc;
   std::lock_guard<std::mutex> lock(g_scratch.mu);
   const size_t dets_b = up256(sizeof(float) * 7 * (size_t)n), keep_b = up256(sizeof(int64_t) * (size_t)n);
   const size_t ws_b = roi3d_nms3d_workspace_bytes(1, n);
@@ -106,6 +120,12 @@ int roi3d_roi_align3d_forward_host(const float *feats_host, int layout, int B, i
   if (K == 0) return ROI3D_OK;
   ROI3D_CHECK_ARG(feats_host && rois_host && out_host, "NULL pointer");
   ROI3D_CHECK_ARG(layout == ROI3D_NCDHW || layout == ROI3D_NDHWC, "bad layout");
+  Scratch *sc = nullptr;
+  {
+    int rc0 = current_scratch(&sc);
+    if (rc0) return rc0;
+  }
+  Scratch &g_scratch = *sc;
   std::lock_guard<std::mutex> lock(g_scratch.mu);
   const size_t feat_b = up256(sizeof(float) * (size_t)B * C * D * H * W);
   const size_t rois_b = up256(sizeof(float) * 7 * (size_t)K);
