@@ -52,6 +52,7 @@ struct RoiParams {
   int64_t *lvls_out;
   int nchunk, nphg;
   long long total_items;
+  int items_per_roi, ctas_per_roi;  // ring2 kernels: CTA -> (RoI, group of kWarps sub-items)
   int bug_compat;
 };
 
@@ -714,6 +715,310 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel
 }
 
 // ---------------------------------------------------------------------------------------------
+// Forward ring kernel with CTA-shared per-RoI tables: the four warps of a CTA always work on the same
+// RoI (grid = K x ceil(items per RoI / 4)), so the axis tables are built once per CTA by three warps in
+// parallel (x, y and z bins) instead of once per warp, and sit once in shared memory.  Everything after
+// the table build is the per-warp pipeline of roi_align3d_fwd_ring_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int RZMAX2 = 40;
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kernel(const RoiParams p) {
+  using TB = Tables<PW>;
+  constexpr int PWP = TB::PWP;
+  constexpr int VOX = 32 * CV;                 // floats per voxel-chunk
+  constexpr int LPV = VOX / 4;                 // lanes (16 B each) per voxel-chunk
+  constexpr int VPI = 32 / LPV;                // voxel-chunks copied per warp instruction
+  constexpr int STRIDE = (RXR + 2) * VOX;      // floats per ring stage (two zero pad voxels)
+  constexpr int RING = NS * STRIDE;            // floats
+  constexpr int STAGE = ROWS * PW * 33;
+  constexpr int LISTS = 416;                   // ylist[40] + zlist[40] bytes + yoff[40] + zoff[40] ints, 16-byte multiple
+  constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
+  constexpr int WARP_FLOATS = (LISTS / 4 + RING_OR_STAGE + 3) / 4 * 4;
+  constexpr int PP = 16;                       // padded row length of the shared y / z tables (PH, PD <= 16)
+  constexpr int SH_FLOATS = RXMAX * PWP + RYMAX * PP + RZMAX2 * PP + 32 + 3 * 32 * 2 + 16;
+  static_assert(LPV <= 32 && VPI >= 1, "voxel chunk wider than a warp copy");
+  extern __shared__ __align__(16) float smem_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  // ---- CTA-shared per-RoI tables (all warps of a CTA work on the same RoI) ----
+  float *SDx = smem_all;                       // [x - xmin][PWP]
+  float *SDy = SDx + RXMAX * PWP;              // [y - ymin][PP], all PH rows
+  float *SDz = SDy + RYMAX * PP;               // [z - zmin][PP], all PD slices
+  int *Sxlo = reinterpret_cast<int *>(SDz + RZMAX2 * PP);
+  int *Sxhi = Sxlo + 16;
+  int *Srng = Sxhi + 16;                       // [3 axes][32 roles][lo, hi]
+  int *Sbox = Srng + 3 * 32 * 2;               // xmin, xmax, ymin, ymax, zmin, zmax
+  float *sm = smem_all + ((SH_FLOATS + 3) / 4 * 4) + warp * WARP_FLOATS;
+
+  const int k = blockIdx.x / p.ctas_per_roi;
+  const int sub = (blockIdx.x - k * p.ctas_per_roi) * kWarps + warp;
+  const bool valid = sub < p.items_per_roi;
+  Item it;
+  {
+    unsigned item = (unsigned)(valid ? sub : 0);
+    const unsigned phg = item % (unsigned)p.nphg;
+    item /= (unsigned)p.nphg;
+    it.pd = (int)(item % (unsigned)p.PD);
+    it.chunk = (int)(item / (unsigned)p.PD);
+    it.k = k;
+    it.ph0 = (int)phg * ROWS;
+    it.rows = min(ROWS, p.PH - it.ph0);
+    float r[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
+    it.lvl = p.num_levels > 1 ? roi_level(r, p.num_levels, p.inv_finest) : 0;
+    it.L = p.lv[it.lvl];
+    it.b = (int)r[0];
+    it.ok = it.b >= 0 && it.b < p.B;
+    it.axw = axis_setup(r[1], r[3], it.L.scale, p.PW, p.sample_num);
+    it.axh = axis_setup(r[2], r[4], it.L.scale, p.PH, p.sample_num);
+    it.axd = axis_setup(r[5], r[6], it.L.scale_d, p.PD, p.sample_num);
+  }
+  const int C = p.C;
+  if (p.lvls_out != nullptr && blockIdx.x == k * p.ctas_per_roi && tid == 0) p.lvls_out[k] = it.lvl;
+
+  // role threads: warp 0 lanes [0,PW) -> x bins, warp 1 lanes [0,PH) -> y bins, warp 2 lanes [0,PD) -> z bins
+  const int role = (warp == 0 && lane < PW) ? 0 : (warp == 1 && lane < p.PH) ? 1 : (warp == 2 && lane < p.PD) ? 2 : -1;
+  const Axis ax = role == 1 ? it.axh : role == 2 ? it.axd : it.axw;
+  const int asize = role == 1 ? it.L.H : role == 2 ? it.L.D : it.L.W;
+  int lo = INT_MAX, hi = -1;
+  if (role >= 0 && it.ok) {
+    for (int i = 0; i < ax.S; ++i) {
+      Tap t = axis_tap(axis_coord(ax, lane, i), asize);
+      if (t.valid) lo = min(lo, t.low), hi = max(hi, t.high);
+    }
+  }
+  if (warp < 3) {
+    const int mn = __reduce_min_sync(FULL, role >= 0 ? lo : INT_MAX);
+    const int mx = __reduce_max_sync(FULL, role >= 0 ? hi : -1);
+    if (lane == 0) Sbox[warp * 2] = mn, Sbox[warp * 2 + 1] = mx;
+  }
+  __syncthreads();
+  TB T;
+  T.Dx = SDx, T.xlo = Sxlo, T.xhi = Sxhi;
+  T.xmin = Sbox[0], T.xmax = Sbox[1], T.ymin = Sbox[2], T.ymax = Sbox[3], T.zmin = Sbox[4], T.zmax = Sbox[5];
+  T.empty = !it.ok || T.xmax < T.xmin || T.ymax < T.ymin || T.zmax < T.zmin;
+  T.fits = T.empty || ((T.xmax - T.xmin < RXMAX) && (T.ymax - T.ymin < RYMAX) && (T.zmax - T.zmin < RZMAX2));
+  const int RX = T.xmax - T.xmin + 1;
+  if (!T.empty && T.fits) {
+    const int RY = T.ymax - T.ymin + 1, RZ = T.zmax - T.zmin + 1;
+    for (int i = tid; i < RX * PWP; i += kWarps * 32) SDx[i] = 0.0f;
+    for (int i = tid; i < RY * PP; i += kWarps * 32) SDy[i] = 0.0f;
+    for (int i = tid; i < RZ * PP; i += kWarps * 32) SDz[i] = 0.0f;
+  }
+  __syncthreads();
+  if (!T.empty && T.fits && role >= 0) {
+    float *tab = role == 0 ? SDx : role == 1 ? SDy : SDz;
+    const int stride = role == 0 ? PWP : PP;
+    const int mn = role == 0 ? T.xmin : role == 1 ? T.ymin : T.zmin;
+    for (int i = 0; i < ax.S; ++i) {
+      Tap t = axis_tap(axis_coord(ax, lane, i), asize);
+      if (t.valid) {
+        tab[(t.low - mn) * stride + lane] += t.h;
+        tab[(t.high - mn) * stride + lane] += t.l;
+      }
+    }
+    if (role == 0) {
+      Sxlo[lane] = hi >= lo ? lo - T.xmin : 0;
+      Sxhi[lane] = hi >= lo ? hi - T.xmin : -1;
+    }
+  }
+  __syncthreads();
+  if (!valid) return;  // padding warp of the last CTA of this RoI: no further block-level barriers below
+
+  int c_base = (it.chunk * 32 + lane) * CV;
+  const bool active = c_base < C;
+  if (!active) c_base = 0;
+  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+  const float *fb_roi = it.L.feats + (long long)(it.ok ? it.b : 0) * vox * C;
+  const float *fb = fb_roi + c_base;
+  unsigned char *ylist = reinterpret_cast<unsigned char *>(sm);
+  unsigned char *zlist = ylist + 40;
+  int *yoff = reinterpret_cast<int *>(ylist + 80);
+  int *zoff = yoff + 40;
+  float *ring = sm + LISTS / 4;
+  const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
+  // the 16-byte copies need the chunk to lie inside C and be 16-byte aligned: C % 4 == 0 is checked by
+  // the dispatcher; a partial last chunk (C not a multiple of 32*CV) copies only the lanes inside C.
+
+  if (!T.empty && (!T.fits || RX > RXR)) {
+    // footprint larger than the tables / the ring: literal evaluation, uncoalesced stores (rare path)
+    literal_tile_fwd<CV>(it, fb, C, p.PD, p.PH, PW, c_base, active, p.out);
+    return;
+  }
+
+  float acc[ROWS][PW][CV];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int w = 0; w < PW; ++w)
+#pragma unroll
+      for (int c = 0; c < CV; ++c) acc[r][w][c] = 0.0f;
+
+  if (!T.empty) {
+    // ---- compact lists of the z slices / y rows that carry weight for this (pd, ph-group) ----
+    const int RY = T.ymax - T.ymin + 1, RZ = T.zmax - T.zmin + 1;
+    int ny = 0, nz = 0;
+    for (int y0 = 0; y0 < RY; y0 += 32) {
+      const int yy = y0 + lane;
+      bool a = false;
+      if (yy < RY) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) a |= (r < it.rows) && SDy[yy * PP + it.ph0 + r] != 0.0f;
+      }
+      const unsigned bal = __ballot_sync(FULL, a);
+      if (a) ylist[ny + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)yy;
+      ny += __popc(bal);
+    }
+    for (int z0 = 0; z0 < RZ; z0 += 32) {
+      const int zz = z0 + lane;
+      const bool a = zz < RZ && SDz[zz * PP + it.pd] != 0.0f;
+      const unsigned bal = __ballot_sync(FULL, a);
+      if (a) zlist[nz + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)zz;
+      nz += __popc(bal);
+    }
+    __syncwarp();
+    const int nrows = ny * nz;
+
+    // per-warp constants of the x-contraction: for every bin pw its first NXU taps (weight forced to 0
+    // past the bin's support).  Ring rows carry two zero-filled pad voxels after the RX real ones, so a
+    // zero-weight tap always reads initialised shared memory and tap offsets are compile-time constants.
+    bool long_bins = false;
+    int soff[PW];
+    float tw[PW][NXU];
+#pragma unroll
+    for (int pw = 0; pw < PW; ++pw) {
+      const int lo = T.xlo[pw];
+      const int n = T.xhi[pw] - lo + 1;
+      long_bins |= n > NXU;
+      soff[pw] = lo * VOX + lane * CV;
+#pragma unroll
+      for (int j = 0; j < NXU; ++j) tw[pw][j] = j < n ? T.Dx[(lo + j) * PWP + pw] : 0.0f;
+    }
+    static_assert(NXU <= 3, "pad voxels cover taps lo+1, lo+2 only");
+    for (int sidx = 0; sidx < NS; ++sidx) {
+      float *padp = ring + sidx * STRIDE + RX * VOX;
+      for (int i = lane; i < 2 * VOX; i += 32) padp[i] = 0.0f;
+    }
+    __syncwarp();
+
+    // copy geometry: lane -> (voxel within the instruction, 16-byte piece of the voxel chunk)
+    const int cv_v = lane / LPV, cv_p = lane % LPV;
+    const int ch_piece = it.chunk * VOX + cv_p * 4;          // first channel of this lane's 16 bytes
+    const bool piece_ok = ch_piece + 4 <= C;
+    // producer cursor (row to prefetch next): rows are visited y-major, z-minor, so that all z slices of
+    // one y row are contracted along x back to back and the y-stage runs once per y row.
+    const long long row_elems = (long long)it.L.W * C;
+    const long long slice_elems = (long long)it.L.H * row_elems;
+    const float *src0 = fb_roi + ((long long)T.zmin * it.L.H + T.ymin) * row_elems + (long long)T.xmin * C + ch_piece +
+                        (long long)cv_v * C;
+    float *dst0 = ring + cv_p * 4 + cv_v * VOX;
+    // row offsets in units of 4 floats (16 B; C % 4 == 0), < 2^31 for any level the dispatcher accepts
+    for (int i = lane; i < nz; i += 32) zoff[i] = (int)(((long long)zlist[i] * slice_elems) >> 2);
+    for (int i = lane; i < ny; i += 32) yoff[i] = (int)(((long long)ylist[i] * row_elems) >> 2);
+    __syncwarp();
+    int pz = 0, py = 0, pstage = 0;
+    auto issue = [&]() {
+      const float *src = src0 + ((long long)(zoff[pz] + yoff[py]) << 2);
+      float *dst = dst0 + pstage * STRIDE;
+      if (piece_ok) {
+#pragma unroll 2
+        for (int v = cv_v; v < RX; v += VPI) {
+          cp_async16(dst, src);
+          dst += VPI * VOX, src += (long long)VPI * C;
+        }
+      }
+      cp_async_commit();
+      if (++pz == nz) pz = 0, ++py;
+      if (++pstage == NS) pstage = 0;
+    };
+#pragma unroll
+    for (int r = 0; r < NS - 1; ++r) {
+      if (r < nrows) issue();
+      else cp_async_commit();
+    }
+    int cstage = 0, r = 0;
+    for (int yi = 0; yi < ny; ++yi) {
+      float t1[PW][CV];
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+        for (int c = 0; c < CV; ++c) t1[pw][c] = 0.0f;
+      for (int zi = 0; zi < nz; ++zi, ++r) {
+        cp_async_wait<NS - 2>();
+        __syncwarp();
+        const float wz = SDz[zlist[zi] * PP + it.pd];
+        const float *row = ring + cstage * STRIDE;
+        if (++cstage == NS) cstage = 0;
+        float tz[PW][CV];
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) {
+          const float *q = row + soff[pw];
+#pragma unroll
+          for (int j = 0; j < NXU; ++j) {
+            float f[CV];
+            if constexpr (CV == 4) {
+              const float4 t = *reinterpret_cast<const float4 *>(q + j * VOX);
+              f[0] = t.x, f[1] = t.y, f[2] = t.z, f[3] = t.w;
+            } else if constexpr (CV == 2) {
+              const float2 t = *reinterpret_cast<const float2 *>(q + j * VOX);
+              f[0] = t.x, f[1] = t.y;
+            } else {
+              f[0] = q[j * VOX];
+            }
+#pragma unroll
+            for (int c = 0; c < CV; ++c) tz[pw][c] = j == 0 ? tw[pw][0] * f[c] : fmaf(tw[pw][j], f[c], tz[pw][c]);
+          }
+        }
+        if (long_bins) {  // one warp-uniform test per row; bins wider than NXU taps are rare
+#pragma unroll
+          for (int pw = 0; pw < PW; ++pw) {
+            const int lo = T.xlo[pw];
+            const int n = T.xhi[pw] - lo + 1;
+            const float *q = row + soff[pw];
+            const float *wq = T.Dx + lo * PWP + pw;
+#pragma unroll 1
+            for (int j = NXU; j < n; ++j) {
+              const float w = wq[j * PWP];
+#pragma unroll
+              for (int c = 0; c < CV; ++c) tz[pw][c] = fmaf(w, q[j * VOX + c], tz[pw][c]);
+            }
+          }
+        }
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+          for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(wz, tz[pw][c], t1[pw][c]);
+        __syncwarp();
+        if (r + NS - 1 < nrows) issue();
+        else cp_async_commit();
+      }
+      // y-stage, once per feature row index y
+      const int yy = ylist[yi];
+      float wy[ROWS];
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr) wy[rr] = rr < it.rows ? SDy[yy * PP + it.ph0 + rr] : 0.0f;
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr) {
+        if (wy[rr] != 0.0f) {
+#pragma unroll
+          for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+            for (int c = 0; c < CV; ++c) acc[rr][pw][c] = fmaf(wy[rr], t1[pw][c], acc[rr][pw][c]);
+        }
+      }
+    }
+    cp_async_wait<0>();
+  }
+
+  // ---- epilogue: divide by the sample count, transpose through smem, stream out ----
+  const int NB = it.rows * PW;
+  float *stage = ring;  // the ring is drained
+  const long long out_base = (((long long)it.k * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
+  const long long ch_stride = (long long)p.PD * p.PH * PW;
+  copy_out_tile<ROWS, PW, CV>(acc, count, stage, lane, NB, it.chunk, C, p.out + out_base, ch_stride);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Backward, channels-last, separable (transposed contraction).  Same work split as the forward.
 // One vector red per (row voxel, lane) instead of 64 scalar atomics per output element.
 // ---------------------------------------------------------------------------------------------
@@ -1081,6 +1386,30 @@ static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   return ROI3D_OK;
 }
 
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB = 0>
+static int launch_fwd_ring2(RoiParams &p, cudaStream_t st) {
+  using TB = Tables<PW>;
+  constexpr int VOX = 32 * CV;
+  constexpr int RING = NS * (RXR + 2) * VOX;
+  constexpr int STAGE = ROWS * PW * 33;
+  constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
+  constexpr int WARP_FLOATS = (416 / 4 + RING_OR_STAGE + 3) / 4 * 4;
+  constexpr int SH_FLOATS = RXMAX * TB::PWP + RYMAX * 16 + RZMAX2 * 16 + 32 + 3 * 32 * 2 + 16;
+  const size_t smem = ((size_t)((SH_FLOATS + 3) / 4 * 4) + (size_t)kWarps * WARP_FLOATS) * sizeof(float);
+  p.nchunk = ceil_div(p.C, 32 * CV);
+  p.nphg = ceil_div(p.PH, ROWS);
+  p.items_per_roi = p.nchunk * p.PD * p.nphg;
+  p.ctas_per_roi = ceil_div(p.items_per_roi, kWarps);
+  p.total_items = (long long)p.K * p.items_per_roi;
+  const long long blocks = (long long)p.K * p.ctas_per_roi;
+  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
+  auto kern = roi_align3d_fwd_ring2_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB>;
+  ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
 template <int PW, int ROWS, int CV, int RXR>
 static int launch_bwd(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
@@ -1139,7 +1468,13 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
   for (int l = 0; l < p.num_levels; ++l) ring_ok = ring_ok && aligned(p.lv[l].feats, 16);
   if (p.PW == 7) {
     if (ring_ok && cvmax >= 2) {
-      if (v == 0) return launch_fwd_ring<7, 7, 2, 3, 4, 18, 2>(p, st);
+      if (p.PH <= 16 && p.PD <= 16) {
+        if (v == 0 || v == 22) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2>(p, st);  // default
+        if (v == 20) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2>(p, st);
+        if (v == 21) return launch_fwd_ring2<7, 7, 2, 3, 3, 18, 3>(p, st);
+        if (v == 23) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 0>(p, st);
+      }
+      if (v == 0 || v == 30) return launch_fwd_ring<7, 7, 2, 3, 4, 18, 2>(p, st);  // per-warp tables (PH or PD > 16)
       if (v == 13) return launch_fwd_ring<7, 7, 2, 3, 3, 18>(p, st);
       if (v == 5) return launch_fwd_ring<7, 7, 2, 3, 4, 18>(p, st);
       if (v == 6) return launch_fwd_ring<7, 7, 1, 3, 4, 20>(p, st);
@@ -1156,7 +1491,13 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
   }
   if (p.PW == 14) {
     if (ring_ok && cvmax >= 2) {
-      if (v == 0) return launch_fwd_ring<14, 4, 2, 3, 3, 18>(p, st);
+      if (p.PH <= 16 && p.PD <= 16) {
+        if (v == 0 || v == 20) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0>(p, st);  // default
+        if (v == 21) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 3>(p, st);
+        if (v == 22) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2>(p, st);
+        if (v == 23) return launch_fwd_ring2<14, 7, 1, 3, 4, 20, 0>(p, st);
+      }
+      if (v == 0 || v == 30) return launch_fwd_ring<14, 4, 2, 3, 3, 18>(p, st);  // per-warp tables (PH or PD > 16)
       if (v == 12) return launch_fwd_ring<14, 4, 2, 3, 4, 18, 2>(p, st);
       if (v == 11) return launch_fwd_ring<14, 4, 2, 3, 3, 18, 3>(p, st);
       if (v == 5) return launch_fwd_ring<14, 4, 2, 3, 4, 18>(p, st);

@@ -8,7 +8,7 @@ Metric (BASELINE.json): RoIs/s of 3D RoIAlign forward on workload C2 = BASELINE.
 One "step" = one RoIAlign3D forward over one batch of 512 RoIs.  Every rank runs the same per-GPU workload on its own
 volume (weak scaling, no data-path collective: volumes are independent); `value` = N * 512 * K / max-over-ranks
 device time.  One JSON line is printed by rank 0 with, besides the contract keys:
-  roofline      dominant kernel (roi_align3d_fwd_ring_kernel): algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  roofline      dominant kernel (roi_align3d_fwd_ring2_kernel): algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
   cpu_baseline  the oracle (CPU restatement of the reference; the reference has no CPU RoIAlign) on a bounded sample
   e2e           the same metric through the C-ABI host-buffer entry (pinned host NCDHW features -> H2D -> layout
                 conversion -> kernel -> D2H of the pooled features), i.e. what a caller holding host tensors pays
@@ -273,7 +273,7 @@ def main():
         launches[0] += 1
 
     total_ms, per = time_steps(torch, step, steps, warmup, dist)
-    gpu_launches = steps  # one roi_align3d_fwd_ring_kernel launch per step inside the timed region
+    gpu_launches = steps  # one roi_align3d_fwd_ring2_kernel launch per step inside the timed region
     value = world * C2["K"] * steps / (total_ms * 1e-3)
     kernel_ms = float(np.median(per))  # one launch per step: the per-step event time is the kernel's duration
 
@@ -334,7 +334,7 @@ def main():
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_ring_kernel<7,7,2,3,4,18,2>", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_ring2_kernel<7,7,2,3,5,18,2>", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes": alg_bytes, "unique_voxels": U, "kernel_us": kernel_ms * 1e3,
                     "output_only_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9}
