@@ -714,6 +714,32 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel
   copy_out_tile<ROWS, PW, CV>(acc, count, stage, lane, NB, it.chunk, C, p.out + out_base, ch_stride);
 }
 
+// ---- TMA bulk-copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers for the per-warp row ring ----
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned ok = 0;
+  for (int spin = 0; spin < (1 << 24); ++spin) {  // bounded: a byte-count mismatch traps instead of hanging the GPU
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward ring kernel with CTA-shared per-RoI tables: the four warps of a CTA always work on the same
 // RoI (grid = K x ceil(items per RoI / 4)), so the axis tables are built once per CTA by three warps in
@@ -721,7 +747,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel
 // the table build is the per-warp pipeline of roi_align3d_fwd_ring_kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int RZMAX2 = 40;
-template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB>
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB, bool BULK>
 __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kernel(const RoiParams p) {
   using TB = Tables<PW>;
   constexpr int PWP = TB::PWP;
@@ -731,7 +757,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
   constexpr int STRIDE = (RXR + 2) * VOX;      // floats per ring stage (two zero pad voxels)
   constexpr int RING = NS * STRIDE;            // floats
   constexpr int STAGE = ROWS * PW * 33;
-  constexpr int LISTS = 416;                   // ylist[40] + zlist[40] bytes + yoff[40] + zoff[40] ints, 16-byte multiple
+  constexpr int LISTS = 480;                   // ylist[40] + zlist[40] bytes + yoff[40] + zoff[40] ints + 8 mbarriers
   constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
   constexpr int WARP_FLOATS = (LISTS / 4 + RING_OR_STAGE + 3) / 4 * 4;
   constexpr int PP = 16;                       // padded row length of the shared y / z tables (PH, PD <= 16)
@@ -917,25 +943,50 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
     for (int i = lane; i < ny; i += 32) yoff[i] = (int)(((long long)ylist[i] * row_elems) >> 2);
     __syncwarp();
     int pz = 0, py = 0, pstage = 0;
-    auto issue = [&]() {
-      const float *src = src0 + ((long long)(zoff[pz] + yoff[py]) << 2);
-      float *dst = dst0 + pstage * STRIDE;
-      if (piece_ok) {
-#pragma unroll 2
-        for (int v = cv_v; v < RX; v += VPI) {
-          cp_async16(dst, src);
-          dst += VPI * VOX, src += (long long)VPI * C;
-        }
+    // BULK: the row is fetched by the TMA engine -- lane v issues one cp.async.bulk of this warp's channel chunk
+    // of voxel v (<= 128*CV bytes, contiguous), completion is counted in bytes on the stage's mbarrier.
+    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(ylist + 416);
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const unsigned chunk_bytes = (unsigned)min(VOX, C - it.chunk * VOX) * 4u;
+    const float *srcb = fb_roi + ((long long)T.zmin * it.L.H + T.ymin) * row_elems + (long long)T.xmin * C +
+                        (long long)it.chunk * VOX;
+    if constexpr (BULK) {
+      static_assert(NS <= 8, "eight mbarriers per warp");
+      if (lane == 0) {
+        for (int sidx = 0; sidx < NS; ++sidx) mbar_init(mbar0 + sidx * 8, 1);
+        mbar_fence_init();
       }
-      cp_async_commit();
+      __syncwarp();
+    }
+    auto issue = [&]() {
+      if constexpr (BULK) {
+        const float *src = srcb + ((long long)(zoff[pz] + yoff[py]) << 2);
+        const unsigned mb = mbar0 + pstage * 8;
+        if (lane == 0) mbar_expect_tx(mb, (unsigned)RX * chunk_bytes);
+        __syncwarp();
+        for (int v = lane; v < RX; v += 32)
+          bulk_g2s(ring_s + (unsigned)(pstage * STRIDE + v * VOX) * 4u, src + (long long)v * C, chunk_bytes, mb);
+      } else {
+        const float *src = src0 + ((long long)(zoff[pz] + yoff[py]) << 2);
+        float *dst = dst0 + pstage * STRIDE;
+        if (piece_ok) {
+#pragma unroll 2
+          for (int v = cv_v; v < RX; v += VPI) {
+            cp_async16(dst, src);
+            dst += VPI * VOX, src += (long long)VPI * C;
+          }
+        }
+        cp_async_commit();
+      }
       if (++pz == nz) pz = 0, ++py;
       if (++pstage == NS) pstage = 0;
     };
 #pragma unroll
     for (int r = 0; r < NS - 1; ++r) {
       if (r < nrows) issue();
-      else cp_async_commit();
+      else if constexpr (!BULK) cp_async_commit();
     }
+    unsigned cpar = 0;
     int cstage = 0, r = 0;
     for (int yi = 0; yi < ny; ++yi) {
       float t1[PW][CV];
@@ -944,11 +995,15 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
 #pragma unroll
         for (int c = 0; c < CV; ++c) t1[pw][c] = 0.0f;
       for (int zi = 0; zi < nz; ++zi, ++r) {
-        cp_async_wait<NS - 2>();
-        __syncwarp();
+        if constexpr (BULK) {
+          mbar_wait(mbar0 + cstage * 8, cpar);
+        } else {
+          cp_async_wait<NS - 2>();
+          __syncwarp();
+        }
         const float wz = SDz[zlist[zi] * PP + it.pd];
         const float *row = ring + cstage * STRIDE;
-        if (++cstage == NS) cstage = 0;
+        if (++cstage == NS) cstage = 0, cpar ^= 1u;
         float tz[PW][CV];
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw) {
@@ -990,7 +1045,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
           for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(wz, tz[pw][c], t1[pw][c]);
         __syncwarp();
         if (r + NS - 1 < nrows) issue();
-        else cp_async_commit();
+        else if constexpr (!BULK) cp_async_commit();
       }
       // y-stage, once per feature row index y
       const int yy = ylist[yi];
@@ -1007,7 +1062,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
         }
       }
     }
-    cp_async_wait<0>();
+    if constexpr (!BULK) cp_async_wait<0>();
   }
 
   // ---- epilogue: divide by the sample count, transpose through smem, stream out ----
@@ -1386,14 +1441,14 @@ static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   return ROI3D_OK;
 }
 
-template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB = 0>
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB = 0, bool BULK = false>
 static int launch_fwd_ring2(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
   constexpr int VOX = 32 * CV;
   constexpr int RING = NS * (RXR + 2) * VOX;
   constexpr int STAGE = ROWS * PW * 33;
   constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
-  constexpr int WARP_FLOATS = (416 / 4 + RING_OR_STAGE + 3) / 4 * 4;
+  constexpr int WARP_FLOATS = (480 / 4 + RING_OR_STAGE + 3) / 4 * 4;
   constexpr int SH_FLOATS = RXMAX * TB::PWP + RYMAX * 16 + RZMAX2 * 16 + 32 + 3 * 32 * 2 + 16;
   const size_t smem = ((size_t)((SH_FLOATS + 3) / 4 * 4) + (size_t)kWarps * WARP_FLOATS) * sizeof(float);
   p.nchunk = ceil_div(p.C, 32 * CV);
@@ -1403,7 +1458,7 @@ static int launch_fwd_ring2(RoiParams &p, cudaStream_t st) {
   p.total_items = (long long)p.K * p.items_per_roi;
   const long long blocks = (long long)p.K * p.ctas_per_roi;
   ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
-  auto kern = roi_align3d_fwd_ring2_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB>;
+  auto kern = roi_align3d_fwd_ring2_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB, BULK>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
   ROI3D_LAUNCH_CHECK();
@@ -1471,6 +1526,9 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
       if (p.PH <= 16 && p.PD <= 16) {
         if (v == 0 || v == 22) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2>(p, st);  // default
         if (v == 20) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2>(p, st);
+        if (v == 40) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, true>(p, st);
+        if (v == 41) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, true>(p, st);
+        if (v == 42) return launch_fwd_ring2<7, 7, 2, 3, 6, 18, 2, true>(p, st);
         if (v == 21) return launch_fwd_ring2<7, 7, 2, 3, 3, 18, 3>(p, st);
         if (v == 23) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 0>(p, st);
       }
@@ -1493,6 +1551,7 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
     if (ring_ok && cvmax >= 2) {
       if (p.PH <= 16 && p.PD <= 16) {
         if (v == 0 || v == 20) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0>(p, st);  // default
+        if (v == 40) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 0, true>(p, st);
         if (v == 21) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 3>(p, st);
         if (v == 22) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2>(p, st);
         if (v == 23) return launch_fwd_ring2<14, 7, 1, 3, 4, 20, 0>(p, st);
