@@ -1274,13 +1274,16 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
       float uv[CV];
 #pragma unroll
       for (int c = 0; c < CV; ++c) uv[c] = uxl[xx * VOX + c];
+      // No per-lane `active` test here: lanes past the last channel hold zero gradients (their stage-in columns
+      // were zero-filled) and point at channel 0, so their reds add +0.0 to a valid address.  Keeping the loop
+      // free of lane-dependent branches lets the warp-uniform `zi < nz` tests compile to plain predication.
 #pragma unroll
       for (int zi = 0; zi < 4; ++zi) {
         if (zi < nz) {
           float v[CV];
 #pragma unroll
           for (int c = 0; c < CV; ++c) v[c] = zw[zi] * uv[c];
-          if (active) redv<CV>(q + zo[zi], v);
+          redv<CV>(q + zo[zi], v);
         }
       }
       for (int zi = 4; zi < nz; ++zi) {
@@ -1289,7 +1292,7 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
         float v[CV];
 #pragma unroll
         for (int c = 0; c < CV; ++c) v[c] = wz * uv[c];
-        if (active) redv<CV>(q + (long long)zrel * slice_elems, v);
+        redv<CV>(q + (long long)zrel * slice_elems, v);
       }
     }
   }
