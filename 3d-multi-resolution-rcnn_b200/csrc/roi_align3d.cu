@@ -1367,11 +1367,74 @@ __global__ void map_roi_levels_kernel(const float *rois, int K, int num_levels, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Layout conversion: per batch a [C][S] <-> [S][C] transpose (S = D*H*W), 32x32 tiles, padded smem.
+// Layout conversion: per batch a [C][S] <-> [S][C] transpose (S = D*H*W).
+// Fast path (C % 4 == 0, S % 4 == 0, 16-byte aligned): 32 x 128 tiles, 16-byte global accesses on both
+// sides (float4 along the contiguous dimension of the source when reading, of the destination when
+// writing), padded shared tile so both phases are bank-conflict free.  Generic path: 32 x 32 tiles.
 // ---------------------------------------------------------------------------------------------
+// src [rows][cols] -> dst [cols][rows].  Tile = 32 rows x 128 cols.  256 threads.
+__global__ void __launch_bounds__(256) transpose_r32c128_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                                                 int rows, int cols, int tiles_c) {
+  __shared__ float tile[32][129];
+  const long long boff = (long long)blockIdx.y * rows * cols;
+  const int c0 = (blockIdx.x % tiles_c) * 128, r0 = (blockIdx.x / tiles_c) * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // read: one warp = one source row segment of 128 floats (32 lanes x float4)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + warp + i * 8, c = c0 + lane * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows && c < cols) v = __ldcs(reinterpret_cast<const float4 *>(src + boff + (long long)r * cols + c));
+    tile[warp + i * 8][lane * 4 + 0] = v.x, tile[warp + i * 8][lane * 4 + 1] = v.y;
+    tile[warp + i * 8][lane * 4 + 2] = v.z, tile[warp + i * 8][lane * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  // write: 8 lanes x float4 cover the 32 rows (contiguous in dst) of one column; a warp covers 4 columns
+  const int rq = (lane & 7) * 4, cs = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cl = warp * 16 + i * 4 + cs;  // 8 warps x 16 columns = 128
+    const int c = c0 + cl, r = r0 + rq;
+    if (c < cols && r < rows) {
+      const float4 v = make_float4(tile[rq + 0][cl], tile[rq + 1][cl], tile[rq + 2][cl], tile[rq + 3][cl]);
+      *reinterpret_cast<float4 *>(dst + boff + (long long)c * rows + r) = v;
+    }
+  }
+}
+
+// src [rows][cols] -> dst [cols][rows].  Tile = 128 rows x 32 cols (the mirror image, for [S][C] -> [C][S]).
+__global__ void __launch_bounds__(256) transpose_r128c32_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                                                 int rows, int cols, int tiles_c) {
+  __shared__ float tile[32][129];  // tile[col][row]
+  const long long boff = (long long)blockIdx.y * rows * cols;
+  const int c0 = (blockIdx.x % tiles_c) * 32, r0 = (blockIdx.x / tiles_c) * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // read: 8 lanes x float4 cover the 32 columns (contiguous in src) of one row; a warp covers 4 rows
+  const int cq = (lane & 7) * 4, rs = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = warp * 16 + i * 4 + rs;
+    const int r = r0 + rl, c = c0 + cq;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows && c < cols) v = __ldcs(reinterpret_cast<const float4 *>(src + boff + (long long)r * cols + c));
+    tile[cq + 0][rl] = v.x, tile[cq + 1][rl] = v.y, tile[cq + 2][rl] = v.z, tile[cq + 3][rl] = v.w;
+  }
+  __syncthreads();
+  // write: one warp = one destination row segment of 128 floats
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + warp + i * 8, r = r0 + lane * 4;
+    if (c < cols && r < rows) {
+      const float4 v = make_float4(tile[warp + i * 8][lane * 4 + 0], tile[warp + i * 8][lane * 4 + 1],
+                                   tile[warp + i * 8][lane * 4 + 2], tile[warp + i * 8][lane * 4 + 3]);
+      *reinterpret_cast<float4 *>(dst + boff + (long long)c * rows + r) = v;
+    }
+  }
+}
+
 __global__ void transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols,
                                  int tiles_c) {
-  // src [rows][cols] -> dst [cols][rows]; blockIdx.y = batch; blockIdx.x = linear tile index
+  // generic: src [rows][cols] -> dst [cols][rows]; blockIdx.y = batch; blockIdx.x = linear tile index
   __shared__ float tile[32][33];
   const long long boff = (long long)blockIdx.y * rows * cols;
   const int c0 = (blockIdx.x % tiles_c) * 32, r0 = (blockIdx.x / tiles_c) * 32;
@@ -1389,12 +1452,25 @@ __global__ void transpose_kernel(const float *__restrict__ src, float *__restric
   }
 }
 
+// long_dim: 0 = rows is the short (channel) dimension [C][S] -> [S][C]; 1 = rows is the long dimension.
 static int transpose_launch(const float *src, float *dst, int B, int rows, int cols, cudaStream_t st) {
-  dim3 block(32, 8);
-  const long long tc = ceil_div_ll(cols, 32), tr = ceil_div_ll(rows, 32);
-  ROI3D_CHECK_ARG(tc * tr < 2147483647LL && B <= 65535, "transpose: tensor too large for one launch");
-  dim3 grid((unsigned)(tc * tr), (unsigned)B);
-  transpose_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols, (int)tc);
+  const bool vec_ok = rows % 4 == 0 && cols % 4 == 0 && (reinterpret_cast<uintptr_t>(src) % 16) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dst) % 16) == 0;
+  ROI3D_CHECK_ARG(B <= 65535, "transpose: batch too large");
+  if (vec_ok && cols >= rows) {  // [C][S] -> [S][C]
+    const long long tc = ceil_div_ll(cols, 128), tr = ceil_div_ll(rows, 32);
+    ROI3D_CHECK_ARG(tc * tr < 2147483647LL, "transpose: tensor too large for one launch");
+    transpose_r32c128_kernel<<<dim3((unsigned)(tc * tr), (unsigned)B), 256, 0, st>>>(src, dst, rows, cols, (int)tc);
+  } else if (vec_ok) {           // [S][C] -> [C][S]
+    const long long tc = ceil_div_ll(cols, 32), tr = ceil_div_ll(rows, 128);
+    ROI3D_CHECK_ARG(tc * tr < 2147483647LL, "transpose: tensor too large for one launch");
+    transpose_r128c32_kernel<<<dim3((unsigned)(tc * tr), (unsigned)B), 256, 0, st>>>(src, dst, rows, cols, (int)tc);
+  } else {
+    dim3 block(32, 8);
+    const long long tc = ceil_div_ll(cols, 32), tr = ceil_div_ll(rows, 32);
+    ROI3D_CHECK_ARG(tc * tr < 2147483647LL, "transpose: tensor too large for one launch");
+    transpose_kernel<<<dim3((unsigned)(tc * tr), (unsigned)B), block, 0, st>>>(src, dst, rows, cols, (int)tc);
+  }
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
 }
