@@ -53,7 +53,7 @@ if "c2" in which:
     fcl = f.contiguous(memory_format=torch.channels_last_3d)
     rois = torch.from_numpy(synth.c2_rois(512, seed=2)).to(dev)
     layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
-    for v in (0, 40, 41, 42):
+    for v in (0, 30):
         _lib.set_tuning(0, v)
         med, mn = timeit(lambda: layer(fcl, rois))
         res["c2_fwd_cl_v%d_us" % v] = (med, mn)
