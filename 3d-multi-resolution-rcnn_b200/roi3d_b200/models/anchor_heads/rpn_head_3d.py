@@ -115,9 +115,18 @@ class RPNProposal3D(object):
         ]
         self.num_anchors = len(anchor_ratios) * len(anchor_scales)
 
-    def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg, rescale=False, return_anchors=False):
+    def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg, rescale=False, img_meta_2=None, img_meta_3=None,
+                   return_anchors=False):
         """cls_scores[l]: [B, A, D, H, W]; bbox_preds[l]: [B, 6A, D, H, W]; img_metas[b]['img_shape'] = (H, W, 3, D).
-        Returns the list of per-image proposals (and per-image selected anchors when return_anchors)."""
+        Same positional arguments as AnchorHead3D.get_bboxes (anchor_head_3d.py:232-233): `img_meta_2` / `img_meta_3`,
+        when given, replace `img_metas` (the reference's swap for the 1.5x / third scale, :234-237).
+        Returns the list of per-image proposals; with return_anchors=True the reference's 2-tuple
+        (result_list, anchors_list) is returned, anchors_list holding None (the reference only uses it for debug
+        drawing, anchor_head_3d.py:270-547)."""
+        if img_meta_2 is not None:
+            img_metas = img_meta_2
+        if img_meta_3 is not None:
+            img_metas = img_meta_3
         assert len(cls_scores) == len(bbox_preds)
         nms_pre = int(_cfg_get(cfg, 'nms_pre'))
         nms_post = int(_cfg_get(cfg, 'nms_post'))
@@ -203,7 +212,7 @@ class RPNProposal3D(object):
         n_out = n_valid.clamp(max=kk).tolist()  # the single host read of the whole path
         result = [final[b, :n_out[b]] for b in range(B)]
         if return_anchors:
-            return result, None
+            return result, [None] * len(result)
         return result
 
     def get_bboxes_single(self, cls_scores, bbox_preds, img_shape, cfg):
