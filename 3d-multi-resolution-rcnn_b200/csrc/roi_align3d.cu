@@ -747,8 +747,9 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
 // the table build is the per-warp pipeline of roi_align3d_fwd_ring_kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int RZMAX2 = 40;
-template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB, bool BULK>
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB, bool BULK, bool F2 = false>
 __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kernel(const RoiParams p) {
+  static_assert(!F2 || CV == 2, "packed f32x2 arithmetic pairs the two channels of a lane");
   using TB = Tables<PW>;
   constexpr int PWP = TB::PWP;
   constexpr int VOX = 32 * CV;                 // floats per voxel-chunk
@@ -1008,6 +1009,18 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
 #pragma unroll
         for (int pw = 0; pw < PW; ++pw) {
           const float *q = row + soff[pw];
+          if constexpr (F2) {
+            // sm_100 packed fp32 (FFMA2 / FMUL2): both channels of the lane in one issue slot; each half is
+            // rounded exactly like the scalar fmul / fma, so the pinned arithmetic is unchanged
+            float2 z2;
+#pragma unroll
+            for (int j = 0; j < NXU; ++j) {
+              const float2 t = *reinterpret_cast<const float2 *>(q + j * VOX);
+              const float2 w2 = make_float2(tw[pw][j], tw[pw][j]);
+              z2 = j == 0 ? __fmul2_rn(w2, t) : __ffma2_rn(w2, t, z2);
+            }
+            tz[pw][0] = z2.x, tz[pw][1] = z2.y;
+          } else {
 #pragma unroll
           for (int j = 0; j < NXU; ++j) {
             float f[CV];
@@ -1022,6 +1035,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
             }
 #pragma unroll
             for (int c = 0; c < CV; ++c) tz[pw][c] = j == 0 ? tw[pw][0] * f[c] : fmaf(tw[pw][j], f[c], tz[pw][c]);
+          }
           }
         }
         if (long_bins) {  // one warp-uniform test per row; bins wider than NXU taps are rare
@@ -1040,9 +1054,16 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
           }
         }
 #pragma unroll
-        for (int pw = 0; pw < PW; ++pw)
+        for (int pw = 0; pw < PW; ++pw) {
+          if constexpr (F2) {
+            const float2 o = __ffma2_rn(make_float2(wz, wz), make_float2(tz[pw][0], tz[pw][1]),
+                                        make_float2(t1[pw][0], t1[pw][1]));
+            t1[pw][0] = o.x, t1[pw][1] = o.y;
+          } else {
 #pragma unroll
-          for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(wz, tz[pw][c], t1[pw][c]);
+            for (int c = 0; c < CV; ++c) t1[pw][c] = fmaf(wz, tz[pw][c], t1[pw][c]);
+          }
+        }
         __syncwarp();
         if (r + NS - 1 < nrows) issue();
         else if constexpr (!BULK) cp_async_commit();
@@ -1056,9 +1077,16 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
       for (int rr = 0; rr < ROWS; ++rr) {
         if (wy[rr] != 0.0f) {
 #pragma unroll
-          for (int pw = 0; pw < PW; ++pw)
+          for (int pw = 0; pw < PW; ++pw) {
+            if constexpr (F2) {
+              const float2 o = __ffma2_rn(make_float2(wy[rr], wy[rr]), make_float2(t1[pw][0], t1[pw][1]),
+                                          make_float2(acc[rr][pw][0], acc[rr][pw][1]));
+              acc[rr][pw][0] = o.x, acc[rr][pw][1] = o.y;
+            } else {
 #pragma unroll
-            for (int c = 0; c < CV; ++c) acc[rr][pw][c] = fmaf(wy[rr], t1[pw][c], acc[rr][pw][c]);
+              for (int c = 0; c < CV; ++c) acc[rr][pw][c] = fmaf(wy[rr], t1[pw][c], acc[rr][pw][c]);
+            }
+          }
         }
       }
     }
@@ -1091,8 +1119,9 @@ __device__ __noinline__ void literal_tile_bwd(const Item &it, float *gb, int C, 
     }
 }
 
-template <int PW, int ROWS, int CV, int RXR>
+template <int PW, int ROWS, int CV, int RXR, bool F2 = false>
 __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const RoiParams p) {
+  static_assert(!F2 || CV == 2, "packed f32x2 arithmetic pairs the two channels of a lane");
   using TB = Tables<PW>;
   constexpr int PWP = TB::PWP;
   constexpr int VOX = 32 * CV;
@@ -1239,9 +1268,16 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
     for (int r = 0; r < ROWS; ++r) {
       if (wy[r] != 0.0f) {
 #pragma unroll
-        for (int pw = 0; pw < PW; ++pw)
+        for (int pw = 0; pw < PW; ++pw) {
+          if constexpr (F2) {  // FFMA2: both channels in one issue slot, each half rounded like fmaf
+            const float2 o = __ffma2_rn(make_float2(wy[r], wy[r]), make_float2(g[r][pw][0], g[r][pw][1]),
+                                        make_float2(u[pw][0], u[pw][1]));
+            u[pw][0] = o.x, u[pw][1] = o.y;
+          } else {
 #pragma unroll
-          for (int c = 0; c < CV; ++c) u[pw][c] = fmaf(wy[r], g[r][pw][c], u[pw][c]);
+            for (int c = 0; c < CV; ++c) u[pw][c] = fmaf(wy[r], g[r][pw][c], u[pw][c]);
+          }
+        }
       }
     }
     // x-expansion, once per y: ux[xx] = sum_pw Dx[xx][pw] * u[pw]   (kept per lane in shared memory)
@@ -1257,9 +1293,15 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
 #pragma unroll
       for (int c = 0; c < CV; ++c) v[c] = 0.0f;
 #pragma unroll
-      for (int pw = 0; pw < PW; ++pw)
+      for (int pw = 0; pw < PW; ++pw) {
+        if constexpr (F2) {
+          const float2 o = __ffma2_rn(make_float2(wx[pw], wx[pw]), make_float2(u[pw][0], u[pw][1]), make_float2(v[0], v[1]));
+          v[0] = o.x, v[1] = o.y;
+        } else {
 #pragma unroll
-        for (int c = 0; c < CV; ++c) v[c] = fmaf(wx[pw], u[pw][c], v[c]);
+          for (int c = 0; c < CV; ++c) v[c] = fmaf(wx[pw], u[pw][c], v[c]);
+        }
+      }
 #pragma unroll
       for (int c = 0; c < CV; ++c) ux[xx * VOX + lane * CV + c] = v[c];
     }
@@ -1281,8 +1323,13 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
       for (int zi = 0; zi < 4; ++zi) {
         if (zi < nz) {
           float v[CV];
+          if constexpr (F2) {
+            const float2 o = __fmul2_rn(make_float2(zw[zi], zw[zi]), make_float2(uv[0], uv[1]));
+            v[0] = o.x, v[1] = o.y;
+          } else {
 #pragma unroll
-          for (int c = 0; c < CV; ++c) v[c] = zw[zi] * uv[c];
+            for (int c = 0; c < CV; ++c) v[c] = zw[zi] * uv[c];
+          }
           redv<CV>(q + zo[zi], v);
         }
       }
@@ -1293,6 +1340,283 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_bwd_cl_kernel(const R
 #pragma unroll
         for (int c = 0; c < CV; ++c) v[c] = wz * uv[c];
         redv<CV>(q + (long long)zrel * slice_elems, v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward with CTA-shared per-RoI tables (the backward twin of roi_align3d_fwd_ring2_kernel): the four
+// warps of a CTA work on the same RoI, its axis tables are built once per CTA by three warps in parallel
+// while every warp's grad_out tile is already in flight (cp.async), and the x-expansion is fused with the
+// scatter -- each expanded voxel value goes from registers straight into its (typically 2-3) vector reds,
+// two voxels per iteration for instruction-level parallelism, with no shared-memory round trip.
+// ---------------------------------------------------------------------------------------------
+template <int PW, int ROWS, int CV, bool F2, int MINB, int PP>
+__global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_bwd2_kernel(const RoiParams p) {
+  static_assert(!F2 || CV == 2, "packed f32x2 arithmetic pairs the two channels of a lane");
+  using TB = Tables<PW>;
+  constexpr int PWP = TB::PWP;
+  constexpr int STAGE = CV * ROWS * PW * 33;     // all CV slots of the grad tile at once
+  constexpr int LISTS = 80;
+  constexpr int WARP_FLOATS = (LISTS / 4 + STAGE + 3) / 4 * 4;
+  constexpr int SH_FLOATS = (RXMAX + 1) * PWP + RYMAX * PP + RZMAX2 * PP + RXMAX + 8;
+  extern __shared__ __align__(16) float smem_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  float *SDx = smem_all;                         // [x - xmin][PWP] (+1 row: the paired x loop may read one past RX)
+  float *SDy = SDx + (RXMAX + 1) * PWP;          // [y - ymin][PP]
+  float *SDz = SDy + RYMAX * PP;                 // [z - zmin][PP]
+  int *Sxany = reinterpret_cast<int *>(SDz + RZMAX2 * PP);
+  int *Sbox = Sxany + RXMAX;
+  float *sm = smem_all + ((SH_FLOATS + 3) / 4 * 4) + warp * WARP_FLOATS;
+
+  const int k = blockIdx.x / p.ctas_per_roi;
+  const int sub = (blockIdx.x - k * p.ctas_per_roi) * kWarps + warp;
+  const bool valid = sub < p.items_per_roi;
+  Item it;
+  {
+    unsigned item = (unsigned)(valid ? sub : 0);
+    const unsigned phg = item % (unsigned)p.nphg;
+    item /= (unsigned)p.nphg;
+    it.pd = (int)(item % (unsigned)p.PD);
+    it.chunk = (int)(item / (unsigned)p.PD);
+    it.k = k;
+    it.ph0 = (int)phg * ROWS;
+    it.rows = min(ROWS, p.PH - it.ph0);
+    float r[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
+    it.lvl = p.num_levels > 1 ? roi_level(r, p.num_levels, p.inv_finest) : 0;
+    it.L = p.lv[it.lvl];
+    it.b = (int)r[0];
+    it.ok = it.b >= 0 && it.b < p.B;
+    it.axw = axis_setup(r[1], r[3], it.L.scale, p.PW, p.sample_num);
+    it.axh = axis_setup(r[2], r[4], it.L.scale, p.PH, p.sample_num);
+    it.axd = axis_setup(r[5], r[6], it.L.scale_d, p.PD, p.sample_num);
+  }
+  if (!it.ok) return;  // same RoI for the whole CTA: uniform exit before any barrier
+  const int C = p.C;
+  int c_base = (it.chunk * 32 + lane) * CV;
+  const bool active = c_base < C;
+  if (!active) c_base = 0;
+  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+  float *gb = it.L.grad + (long long)it.b * vox * C + c_base;
+  unsigned char *ylist = reinterpret_cast<unsigned char *>(sm);
+  unsigned char *zlist = ylist + 40;
+  float *stage = sm + LISTS / 4;
+
+  // ---- stage-in of this warp's grad_out tile (see roi_align3d_bwd_cl_kernel), issued before the table build ----
+  const int NB = it.rows * PW;
+  if (valid) {
+    const long long ch_stride = (long long)p.PD * p.PH * PW;
+    // reference index (roi_align_kernel.cu:554-555): pd*PD*PW + ph*PW + pw when bug_compat
+    const long long row_base = p.bug_compat ? ((long long)it.pd * p.PD + it.ph0) * PW
+                                            : ((long long)it.pd * p.PH + it.ph0) * PW;
+    const long long top_total = (long long)p.K * C * ch_stride;
+    const int col_stride = CV * (int)ch_stride;
+#pragma unroll
+    for (int c = 0; c < CV; ++c) {
+      const int cols = min(32, (C - it.chunk * 32 * CV - c + CV - 1) / CV);
+      float *st = stage + c * (NB * 33);
+      const long long g0 = ((long long)it.k * C + (long long)it.chunk * 32 * CV + c) * ch_stride + row_base;
+      long long lim = top_total - g0;  // elements past the end of grad_out: only reachable with bug_compat's row base
+      int total = cols * NB;
+      if (lim < (long long)(cols - 1) * col_stride + NB) total = 0;
+      if (total < 32 * NB) {
+        for (int i = lane; i < NB * 33; i += 32) st[i] = 0.0f;
+        __syncwarp();
+      }
+      const int ncol = total / NB;
+      unsigned sp = (unsigned)__cvta_generic_to_shared(st + lane * 33);
+      const float *gp = p.grad_out + g0 + lane;
+#pragma unroll 4
+      for (int cl = 0; cl < ncol; ++cl) {
+        if (lane < NB) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp), "l"(gp) : "memory");
+        if (lane + 32 < NB)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp + 32 * 33 * 4), "l"(gp + 32) : "memory");
+        for (int bin = lane + 64; bin < NB; bin += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp + (bin - lane) * 33 * 4), "l"(gp + (bin - lane))
+                       : "memory");
+        sp += 4;
+        gp += col_stride;
+      }
+    }
+    cp_async_commit();
+  }
+
+  // ---- CTA-shared tables: warp 0 lanes [0,PW) -> x bins, warp 1 lanes [0,PH) -> y bins, warp 2 lanes [0,PD) -> z bins
+  const int role = (warp == 0 && lane < PW) ? 0 : (warp == 1 && lane < p.PH) ? 1 : (warp == 2 && lane < p.PD) ? 2 : -1;
+  const Axis ax = role == 1 ? it.axh : role == 2 ? it.axd : it.axw;
+  const int asize = role == 1 ? it.L.H : role == 2 ? it.L.D : it.L.W;
+  int lo = INT_MAX, hi = -1;
+  if (role >= 0) {
+    for (int i = 0; i < ax.S; ++i) {
+      Tap t = axis_tap(axis_coord(ax, lane, i), asize);
+      if (t.valid) lo = min(lo, t.low), hi = max(hi, t.high);
+    }
+  }
+  if (warp < 3) {
+    const int mn = __reduce_min_sync(FULL, role >= 0 ? lo : INT_MAX);
+    const int mx = __reduce_max_sync(FULL, role >= 0 ? hi : -1);
+    if (lane == 0) Sbox[warp * 2] = mn, Sbox[warp * 2 + 1] = mx;
+  }
+  __syncthreads();
+  const int xmin = Sbox[0], xmax = Sbox[1], ymin = Sbox[2], ymax = Sbox[3], zmin = Sbox[4], zmax = Sbox[5];
+  const bool empty = xmax < xmin || ymax < ymin || zmax < zmin;
+  const bool fits = empty || ((xmax - xmin < RXMAX) && (ymax - ymin < RYMAX) && (zmax - zmin < RZMAX2));
+  const int RX = xmax - xmin + 1, RY = ymax - ymin + 1, RZ = zmax - zmin + 1;
+  if (!empty && fits) {
+    for (int i = tid; i < (RX + 1) * PWP; i += kWarps * 32) SDx[i] = 0.0f;
+    for (int i = tid; i < RY * PP; i += kWarps * 32) SDy[i] = 0.0f;
+    for (int i = tid; i < RZ * PP; i += kWarps * 32) SDz[i] = 0.0f;
+    for (int i = tid; i < RX; i += kWarps * 32) Sxany[i] = 0;
+  }
+  __syncthreads();
+  if (!empty && fits && role >= 0) {
+    float *tab = role == 0 ? SDx : role == 1 ? SDy : SDz;
+    const int stride = role == 0 ? PWP : PP;
+    const int mn = role == 0 ? xmin : role == 1 ? ymin : zmin;
+    for (int i = 0; i < ax.S; ++i) {
+      Tap t = axis_tap(axis_coord(ax, lane, i), asize);
+      if (t.valid) {
+        tab[(t.low - mn) * stride + lane] += t.h;
+        tab[(t.high - mn) * stride + lane] += t.l;
+        if (role == 0) Sxany[t.low - mn] = 1, Sxany[t.high - mn] = 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (!valid) return;  // padding warp of the last CTA of this RoI: no block-level barriers below
+  cp_async_wait<0>();
+  __syncwarp();
+  if (empty) return;
+  if (!fits) {
+    literal_tile_bwd<CV>(it, gb, C, PW, stage, lane, active, 0.0f);
+    return;
+  }
+  // gradients to registers, scaled once by 1/count (reference: top*w/count per corner, :600-608)
+  const float inv = __frcp_rn((float)(it.axd.S * it.axh.S * it.axw.S));
+  float g[ROWS][PW][CV];
+#pragma unroll
+  for (int c = 0; c < CV; ++c)
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw)
+        g[r][pw][c] = r < it.rows ? stage[(c * NB + r * PW + pw) * 33 + lane] * inv : 0.0f;
+
+  // compact lists of the y rows / z slices that carry weight for this (pd, ph-group)
+  int ny = 0, nz = 0;
+  for (int y0 = 0; y0 < RY; y0 += 32) {
+    const int yy = y0 + lane;
+    bool a = false;
+    if (yy < RY) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) a |= (r < it.rows) && SDy[yy * PP + it.ph0 + r] != 0.0f;
+    }
+    const unsigned bal = __ballot_sync(FULL, a);
+    if (a) ylist[ny + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)yy;
+    ny += __popc(bal);
+  }
+  for (int z0 = 0; z0 < RZ; z0 += 32) {
+    const int zz = z0 + lane;
+    const bool a = zz < RZ && SDz[zz * PP + it.pd] != 0.0f;
+    const unsigned bal = __ballot_sync(FULL, a);
+    if (a) zlist[nz + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)zz;
+    nz += __popc(bal);
+  }
+  __syncwarp();
+
+  const long long row_elems = (long long)it.L.W * C;
+  const long long slice_elems = (long long)it.L.H * row_elems;
+  float *gbase = gb + ((long long)zmin * it.L.H + ymin) * row_elems + (long long)xmin * C;
+  bool has_gaps = false;
+  for (int x0 = 0; x0 < RX; x0 += 32) has_gaps |= __any_sync(FULL, x0 + lane < RX && !Sxany[x0 + lane]);
+  float zw[4];
+  long long zo[4];
+#pragma unroll
+  for (int zi = 0; zi < 4; ++zi) {
+    const int zrel = zi < nz ? zlist[zi] : 0;
+    zw[zi] = zi < nz ? SDz[zrel * PP + it.pd] : 0.0f;
+    zo[zi] = (long long)zrel * slice_elems;
+  }
+  for (int yi = 0; yi < ny; ++yi) {
+    const int yy = ylist[yi];
+    // u[pw] = sum over the ph rows of this group of wy * g  (once per y)
+    float u[PW][CV];
+#pragma unroll
+    for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+      for (int c = 0; c < CV; ++c) u[pw][c] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const float wy = r < it.rows ? SDy[yy * PP + it.ph0 + r] : 0.0f;
+      if (wy != 0.0f) {
+#pragma unroll
+        for (int pw = 0; pw < PW; ++pw) {
+          if constexpr (F2) {
+            const float2 o = __ffma2_rn(make_float2(wy, wy), make_float2(g[r][pw][0], g[r][pw][1]),
+                                        make_float2(u[pw][0], u[pw][1]));
+            u[pw][0] = o.x, u[pw][1] = o.y;
+          } else {
+#pragma unroll
+            for (int c = 0; c < CV; ++c) u[pw][c] = fmaf(wy, g[r][pw][c], u[pw][c]);
+          }
+        }
+      }
+    }
+    // fused x-expansion + scatter, two voxels per iteration: v[x] = sum_pw Dx[x][pw] * u[pw], then one vector
+    // red per (z, x).  Lanes past the last channel hold zero gradients and point at channel 0 (+0.0 adds), so
+    // the loop has no lane-dependent branch.
+    float *q = gbase + (long long)yy * row_elems;
+    for (int xx = 0; xx < RX; xx += 2, q += 2 * (long long)C) {
+      float wx[2][PWP];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int t4 = 0; t4 < PWP / 4; ++t4) {
+          const float4 t = *reinterpret_cast<const float4 *>(SDx + (xx + h) * PWP + t4 * 4);
+          wx[h][t4 * 4 + 0] = t.x, wx[h][t4 * 4 + 1] = t.y, wx[h][t4 * 4 + 2] = t.z, wx[h][t4 * 4 + 3] = t.w;
+        }
+      float v[2][CV];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < CV; ++c) v[h][c] = 0.0f;
+#pragma unroll
+      for (int pw = 0; pw < PW; ++pw)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if constexpr (F2) {
+            const float2 o = __ffma2_rn(make_float2(wx[h][pw], wx[h][pw]), make_float2(u[pw][0], u[pw][1]),
+                                        make_float2(v[h][0], v[h][1]));
+            v[h][0] = o.x, v[h][1] = o.y;
+          } else {
+#pragma unroll
+            for (int c = 0; c < CV; ++c) v[h][c] = fmaf(wx[h][pw], u[pw][c], v[h][c]);
+          }
+        }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (xx + h >= RX || (has_gaps && !Sxany[xx + h])) continue;  // warp-uniform
+        float *qh = q + h * (long long)C;
+#pragma unroll
+        for (int zi = 0; zi < 4; ++zi) {
+          if (zi < nz) {
+            float o[CV];
+#pragma unroll
+            for (int c = 0; c < CV; ++c) o[c] = zw[zi] * v[h][c];
+            redv<CV>(qh + zo[zi], o);
+          }
+        }
+        for (int zi = 4; zi < nz; ++zi) {
+          const int zrel = zlist[zi];
+          const float wz = SDz[zrel * PP + it.pd];
+          float o[CV];
+#pragma unroll
+          for (int c = 0; c < CV; ++c) o[c] = wz * v[h][c];
+          redv<CV>(qh + (long long)zrel * slice_elems, o);
+        }
       }
     }
   }
@@ -1520,7 +1844,7 @@ static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   return ROI3D_OK;
 }
 
-template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB = 0, bool BULK = false>
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB = 0, bool BULK = false, bool F2 = false>
 static int launch_fwd_ring2(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
   constexpr int VOX = 32 * CV;
@@ -1537,14 +1861,14 @@ static int launch_fwd_ring2(RoiParams &p, cudaStream_t st) {
   p.total_items = (long long)p.K * p.items_per_roi;
   const long long blocks = (long long)p.K * p.ctas_per_roi;
   ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
-  auto kern = roi_align3d_fwd_ring2_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB, BULK>;
+  auto kern = roi_align3d_fwd_ring2_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB, BULK, F2>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
 }
 
-template <int PW, int ROWS, int CV, int RXR>
+template <int PW, int ROWS, int CV, int RXR, bool F2 = false>
 static int launch_bwd(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
   constexpr int VOX = 32 * CV;
@@ -1555,10 +1879,32 @@ static int launch_bwd(RoiParams &p, cudaStream_t st) {
   p.nchunk = ceil_div(p.C, 32 * CV);
   p.nphg = ceil_div(p.PH, ROWS);
   p.total_items = (long long)p.K * p.nchunk * p.PD * p.nphg;
-  auto kern = roi_align3d_bwd_cl_kernel<PW, ROWS, CV, RXR>;
+  auto kern = roi_align3d_bwd_cl_kernel<PW, ROWS, CV, RXR, F2>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = ceil_div_ll(p.total_items, kWarps);
   ROI3D_CHECK_ARG(p.total_items < 2147483647LL, "roi_align3d backward: too many work items");
+  kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+template <int PW, int ROWS, int CV, bool F2 = false, int MINB = 0, int PP = 16>
+static int launch_bwd2(RoiParams &p, cudaStream_t st) {
+  ROI3D_CHECK_ARG(p.PH <= PP && p.PD <= PP, "roi_align3d backward: table rows narrower than PH / PD");
+  using TB = Tables<PW>;
+  constexpr int STAGE = CV * ROWS * PW * 33;
+  constexpr int WARP_FLOATS = (80 / 4 + STAGE + 3) / 4 * 4;
+  constexpr int SH_FLOATS = (RXMAX + 1) * TB::PWP + RYMAX * PP + RZMAX2 * PP + RXMAX + 8;
+  const size_t smem = ((size_t)((SH_FLOATS + 3) / 4 * 4) + (size_t)kWarps * WARP_FLOATS) * sizeof(float);
+  p.nchunk = ceil_div(p.C, 32 * CV);
+  p.nphg = ceil_div(p.PH, ROWS);
+  p.items_per_roi = p.nchunk * p.PD * p.nphg;
+  p.ctas_per_roi = ceil_div(p.items_per_roi, kWarps);
+  p.total_items = (long long)p.K * p.items_per_roi;
+  const long long blocks = (long long)p.K * p.ctas_per_roi;
+  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d backward: too many work items");
+  auto kern = roi_align3d_bwd2_kernel<PW, ROWS, CV, F2, MINB, PP>;
+  ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
@@ -1603,8 +1949,11 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
   if (p.PW == 7) {
     if (ring_ok && cvmax >= 2) {
       if (p.PH <= 16 && p.PD <= 16) {
-        if (v == 0 || v == 22) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2>(p, st);  // default
+        if (v == 0 || v == 50) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, false, true>(p, st);  // default
+        if (v == 22) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2>(p, st);  // scalar-FMA twin of the default
         if (v == 20) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2>(p, st);
+        if (v == 51) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, false, true>(p, st);
+        if (v == 52) return launch_fwd_ring2<7, 7, 2, 3, 6, 18, 2, false, true>(p, st);
         if (v == 40) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, true>(p, st);
         if (v == 41) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, true>(p, st);
         if (v == 42) return launch_fwd_ring2<7, 7, 2, 3, 6, 18, 2, true>(p, st);
@@ -1629,8 +1978,11 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
   if (p.PW == 14) {
     if (ring_ok && cvmax >= 2) {
       if (p.PH <= 16 && p.PD <= 16) {
-        if (v == 0 || v == 20) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0>(p, st);  // default
+        if (v == 0 || v == 50) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0, false, true>(p, st);  // default
+        if (v == 20) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0>(p, st);  // scalar-FMA twin of the default
         if (v == 40) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 0, true>(p, st);
+        if (v == 51) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2, false, true>(p, st);
+        if (v == 52) return launch_fwd_ring2<14, 7, 2, 3, 3, 18, 0, false, true>(p, st);
         if (v == 21) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 3>(p, st);
         if (v == 22) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2>(p, st);
         if (v == 23) return launch_fwd_ring2<14, 7, 1, 3, 4, 20, 0>(p, st);
@@ -1661,11 +2013,27 @@ static int dispatch_bwd(RoiParams &p, cudaStream_t st) {
   if (p.PW == 7) {
     if (v == 1 || cvmax == 1) return launch_bwd<7, 7, 1, 40>(p, st);
     if (v == 2 && cvmax >= 4) return launch_bwd<7, 4, 4, 16>(p, st);
+    if (p.PH <= 16 && p.PD <= 16 && cvmax >= 2) {
+      if (v == 60) return launch_bwd2<7, 7, 2, false>(p, st);
+      if (v == 61) return launch_bwd2<7, 7, 2, true>(p, st);
+      if (p.PH <= 8 && p.PD <= 8) {
+        if (v == 62) return launch_bwd2<7, 7, 2, false, 4, 8>(p, st);
+        if (v == 63) return launch_bwd2<7, 7, 2, true, 4, 8>(p, st);
+      }
+    }
+    if (v == 50) return launch_bwd<7, 7, 2, 26, true>(p, st);
     return launch_bwd<7, 7, 2, 26>(p, st);
   }
   if (p.PW == 14) {
     if (v == 1 || cvmax == 1) return launch_bwd<14, 7, 1, 40>(p, st);
     if (v == 2 && cvmax >= 4) return launch_bwd<14, 2, 4, 16>(p, st);
+    if (p.PH <= 16 && p.PD <= 16 && cvmax >= 2) {
+      if (v == 60) return launch_bwd2<14, 4, 2, false>(p, st);
+      if (v == 61) return launch_bwd2<14, 4, 2, true>(p, st);
+      if (v == 62) return launch_bwd2<14, 4, 2, false, 3>(p, st);
+      if (v == 63) return launch_bwd2<14, 4, 2, true, 3>(p, st);
+    }
+    if (v == 50) return launch_bwd<14, 4, 2, 30, true>(p, st);
     return launch_bwd<14, 4, 2, 30>(p, st);
   }
   if (cvmax >= 2) return launch_generic<2>(p, false, st);

@@ -47,13 +47,15 @@ class _Res(dict):
 
 res = _Res()
 which = sys.argv[1:] or ["c2", "nms", "c3", "ref"]
+BWD_VARIANTS = [int(x) for x in os.environ.get("QB_BWD", "0,1,2").split(",")]
+FWD_VARIANTS = [int(x) for x in os.environ.get("QB_FWD", "0,30").split(",")]
 
 if "c2" in which:
     f = torch.randn(1, 256, 40, 128, 128, device=dev)
     fcl = f.contiguous(memory_format=torch.channels_last_3d)
     rois = torch.from_numpy(synth.c2_rois(512, seed=2)).to(dev)
     layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
-    for v in (0, 30):
+    for v in FWD_VARIANTS:
         _lib.set_tuning(0, v)
         med, mn = timeit(lambda: layer(fcl, rois))
         res["c2_fwd_cl_v%d_us" % v] = (med, mn)
@@ -72,7 +74,7 @@ if "c2" in which:
     fcl.requires_grad_(True)
     out = layer(fcl, rois)
     g = torch.randn_like(out)
-    for v in (0, 1, 2):
+    for v in BWD_VARIANTS:
         _lib.set_tuning(1, v)
         def bwd():
             fcl.grad = None
@@ -128,7 +130,7 @@ if "c3" in which:
                             [4, 8, 16, 32], [2, 4, 8, 16])
     lv = ex.map_roi_levels(rois, 4)
     res["c3_level_hist"] = np.bincount(lv.cpu().numpy(), minlength=4).tolist()
-    for v in (0, 40):
+    for v in FWD_VARIANTS:
         _lib.set_tuning(0, v)
         med, mn = timeit(lambda: ex(feats, rois), iters=5)
         res["c3_fwd_v%d_us" % v] = (med, mn)
@@ -137,7 +139,7 @@ if "c3" in which:
         f.requires_grad_(True)
     out = ex(feats, rois)
     g = torch.randn_like(out)
-    for v in (0, 1, 2):
+    for v in BWD_VARIANTS:
         _lib.set_tuning(1, v)
         def bwd3():
             for f in feats:
