@@ -25,6 +25,7 @@
 // RoIs whose footprint exceeds the table capacity, and output widths other than 7/14, take the
 // "generic" path: the same warp-per-(RoI, channel-vector) mapping evaluating the reference's sample
 // loops literally (bit-exact against the oracle with contract=1).
+#include <cuda.h>
 #include <limits.h>
 
 #include "common.cuh"
@@ -52,7 +53,8 @@ struct RoiParams {
   int64_t *lvls_out;
   int nchunk, nphg;
   long long total_items;
-  int items_per_roi, ctas_per_roi;  // ring2 kernels: CTA -> (RoI, group of kWarps sub-items)
+  int items_per_roi, ctas_per_roi;  // ring2 kernels: CTA -> (RoI, group of kWarps * items_per_warp sub-items)
+  int items_per_warp;
   int bug_compat;
 };
 
@@ -740,6 +742,35 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
   __trap();
 }
 
+// One TMA descriptor per pyramid level: the channels-last level seen as a 2-D tensor [voxel][channel], box =
+// (RXR voxels) x (one warp's channel chunk).  A whole feature row of the RoI footprint is then ONE
+// cp.async.bulk.tensor instruction issued by one lane (SASS UTMALDG) instead of RX/2 LDGSTS per warp.
+struct alignas(64) TmapSet {
+  CUtensorMap m[ROI3D_MAX_LEVELS];
+};
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int c0, int c1, unsigned mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(mbar)
+      : "memory");
+}
+
+// Shared-memory layout of the ring2 kernel, shared by the kernel and its launcher.
+template <int PW, int ROWS, int CV, int NS, int RXR, int BULK>
+struct Ring2Layout {
+  static constexpr int VOX = 32 * CV;
+  static constexpr int STRIDE = (RXR + 2) * VOX;
+  static constexpr int RING = NS * STRIDE;
+  static constexpr int STAGE = ROWS * PW * 33;
+  static constexpr int LISTS = BULK == 2 ? 512 : 480;  // bytes; TMA destinations must be 128-byte aligned
+  static constexpr int ALIGN = BULK == 2 ? 32 : 4;     // floats
+  static constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
+  static constexpr int WARP_FLOATS = (LISTS / 4 + RING_OR_STAGE + ALIGN - 1) / ALIGN * ALIGN;
+  static constexpr int SH_FLOATS = RXMAX * Tables<PW>::PWP + RYMAX * 16 + 40 * 16 + 32 + 3 * 32 * 2 + 16;
+  static constexpr int SH_PAD = (SH_FLOATS + ALIGN - 1) / ALIGN * ALIGN;
+  static constexpr size_t BYTES = ((size_t)SH_PAD + (size_t)kWarps * WARP_FLOATS) * sizeof(float);
+};
+
 // ---------------------------------------------------------------------------------------------
 // Forward ring kernel with CTA-shared per-RoI tables: the four warps of a CTA always work on the same
 // RoI (grid = K x ceil(items per RoI / 4)), so the axis tables are built once per CTA by three warps in
@@ -747,24 +778,23 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
 // the table build is the per-warp pipeline of roi_align3d_fwd_ring_kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int RZMAX2 = 40;
-template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB, bool BULK, bool F2 = false>
-__global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kernel(const RoiParams p) {
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB, int BULK, bool F2 = false, bool MULTI = false>
+__global__ void __launch_bounds__(kWarps * 32, MINB)
+    roi_align3d_fwd_ring2_kernel(const RoiParams p, const __grid_constant__ TmapSet tm) {
   static_assert(!F2 || CV == 2, "packed f32x2 arithmetic pairs the two channels of a lane");
   using TB = Tables<PW>;
+  using LY = Ring2Layout<PW, ROWS, CV, NS, RXR, BULK>;
   constexpr int PWP = TB::PWP;
   constexpr int VOX = 32 * CV;                 // floats per voxel-chunk
   constexpr int LPV = VOX / 4;                 // lanes (16 B each) per voxel-chunk
   constexpr int VPI = 32 / LPV;                // voxel-chunks copied per warp instruction
-  constexpr int STRIDE = (RXR + 2) * VOX;      // floats per ring stage (two zero pad voxels)
-  constexpr int RING = NS * STRIDE;            // floats
-  constexpr int STAGE = ROWS * PW * 33;
-  constexpr int LISTS = 480;                   // ylist[40] + zlist[40] bytes + yoff[40] + zoff[40] ints + 8 mbarriers
-  constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
-  constexpr int WARP_FLOATS = (LISTS / 4 + RING_OR_STAGE + 3) / 4 * 4;
+  constexpr int STRIDE = LY::STRIDE;           // floats per ring stage (two zero pad voxels)
+  constexpr int LISTS = LY::LISTS;             // ylist[40] + zlist[40] bytes + yoff[40] + zoff[40] ints + 8 mbarriers
+  constexpr int WARP_FLOATS = LY::WARP_FLOATS;
   constexpr int PP = 16;                       // padded row length of the shared y / z tables (PH, PD <= 16)
-  constexpr int SH_FLOATS = RXMAX * PWP + RYMAX * PP + RZMAX2 * PP + 32 + 3 * 32 * 2 + 16;
   static_assert(LPV <= 32 && VPI >= 1, "voxel chunk wider than a warp copy");
-  extern __shared__ __align__(16) float smem_all[];
+  extern __shared__ __align__(128) float smem_r2[];
+  float *smem_all = smem_r2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   // ---- CTA-shared per-RoI tables (all warps of a CTA work on the same RoI) ----
   float *SDx = smem_all;                       // [x - xmin][PWP]
@@ -774,21 +804,18 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
   int *Sxhi = Sxlo + 16;
   int *Srng = Sxhi + 16;                       // [3 axes][32 roles][lo, hi]
   int *Sbox = Srng + 3 * 32 * 2;               // xmin, xmax, ymin, ymax, zmin, zmax
-  float *sm = smem_all + ((SH_FLOATS + 3) / 4 * 4) + warp * WARP_FLOATS;
+  float *sm = smem_all + LY::SH_PAD + warp * WARP_FLOATS;
 
+  // CTA -> (RoI k, group of kWarps * p.items_per_warp consecutive sub-items); warp w takes sub-items
+  // first + w, first + w + kWarps, ...  Sub-item order: channel chunk fastest, then pd, then ph-group, so with
+  // nchunk == kWarps a warp keeps its channel chunk and walks the pd slices of one RoI.
   const int k = blockIdx.x / p.ctas_per_roi;
-  const int sub = (blockIdx.x - k * p.ctas_per_roi) * kWarps + warp;
-  const bool valid = sub < p.items_per_roi;
+  const int items_per_warp = MULTI ? p.items_per_warp : 1;
+  const int first = (blockIdx.x - k * p.ctas_per_roi) * kWarps * items_per_warp;
   Item it;
   {
-    unsigned item = (unsigned)(valid ? sub : 0);
-    const unsigned phg = item % (unsigned)p.nphg;
-    item /= (unsigned)p.nphg;
-    it.pd = (int)(item % (unsigned)p.PD);
-    it.chunk = (int)(item / (unsigned)p.PD);
     it.k = k;
-    it.ph0 = (int)phg * ROWS;
-    it.rows = min(ROWS, p.PH - it.ph0);
+    it.pd = 0, it.chunk = 0, it.ph0 = 0, it.rows = 0;
     float r[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
@@ -850,27 +877,71 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
     }
   }
   __syncthreads();
-  if (!valid) return;  // padding warp of the last CTA of this RoI: no further block-level barriers below
+  // no block-level barriers below: warps run their sub-items independently
 
-  int c_base = (it.chunk * 32 + lane) * CV;
-  const bool active = c_base < C;
-  if (!active) c_base = 0;
-  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
-  const float *fb_roi = it.L.feats + (long long)(it.ok ? it.b : 0) * vox * C;
-  const float *fb = fb_roi + c_base;
   unsigned char *ylist = reinterpret_cast<unsigned char *>(sm);
   unsigned char *zlist = ylist + 40;
   int *yoff = reinterpret_cast<int *>(ylist + 80);
   int *zoff = yoff + 40;
   float *ring = sm + LISTS / 4;
   const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
+  const bool use_ring = !T.empty && T.fits && RX <= RXR;
+
+  // per-warp constants of the x-contraction (RoI-level, shared by all sub-items of the warp): for every bin pw
+  // its first NXU taps (weight forced to 0 past the bin's support).  Ring rows carry two zero-filled pad voxels
+  // after the RX real ones, so a zero-weight tap always reads initialised shared memory and tap offsets are
+  // compile-time constants.
+  bool long_bins = false;
+  int soff[PW];
+  float tw[PW][NXU];
+  static_assert(NXU <= 3, "pad voxels cover taps lo+1, lo+2 only");
+#pragma unroll
+  for (int pw = 0; pw < PW; ++pw) {
+    const int lo = use_ring ? T.xlo[pw] : 0;
+    const int n = use_ring ? T.xhi[pw] - lo + 1 : 0;
+    long_bins |= n > NXU;
+    soff[pw] = lo * VOX + lane * CV;
+#pragma unroll
+    for (int j = 0; j < NXU; ++j) tw[pw][j] = j < n ? T.Dx[(lo + j) * PWP + pw] : 0.0f;
+  }
+  const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(ylist + 416);
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+  if constexpr (BULK) {
+    static_assert(NS <= 8, "eight mbarriers per warp");
+    if (lane == 0) {
+      for (int sidx = 0; sidx < NS; ++sidx) mbar_init(mbar0 + sidx * 8, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
+  int pstage = 0, cstage = 0;  // ring cursors persist across sub-items (every issued row is consumed)
+  unsigned cpar = 0;
+
+  for (int g = 0; g < items_per_warp; ++g) {
+  const int sub = first + g * kWarps + warp;
+  if (sub >= p.items_per_roi) break;
+  {
+    unsigned item = (unsigned)sub;
+    it.chunk = (int)(item % (unsigned)p.nchunk);
+    item /= (unsigned)p.nchunk;
+    it.pd = (int)(item % (unsigned)p.PD);
+    const unsigned phg = item / (unsigned)p.PD;
+    it.ph0 = (int)phg * ROWS;
+    it.rows = min(ROWS, p.PH - it.ph0);
+  }
+  int c_base = (it.chunk * 32 + lane) * CV;
+  const bool active = c_base < C;
+  if (!active) c_base = 0;
+  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+  const float *fb_roi = it.L.feats + (long long)(it.ok ? it.b : 0) * vox * C;
+  const float *fb = fb_roi + c_base;
   // the 16-byte copies need the chunk to lie inside C and be 16-byte aligned: C % 4 == 0 is checked by
   // the dispatcher; a partial last chunk (C not a multiple of 32*CV) copies only the lanes inside C.
 
   if (!T.empty && (!T.fits || RX > RXR)) {
     // footprint larger than the tables / the ring: literal evaluation, uncoalesced stores (rare path)
     literal_tile_fwd<CV>(it, fb, C, p.PD, p.PH, PW, c_base, active, p.out);
-    return;
+    continue;
   }
 
   float acc[ROWS][PW][CV];
@@ -906,24 +977,9 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
     __syncwarp();
     const int nrows = ny * nz;
 
-    // per-warp constants of the x-contraction: for every bin pw its first NXU taps (weight forced to 0
-    // past the bin's support).  Ring rows carry two zero-filled pad voxels after the RX real ones, so a
-    // zero-weight tap always reads initialised shared memory and tap offsets are compile-time constants.
-    bool long_bins = false;
-    int soff[PW];
-    float tw[PW][NXU];
-#pragma unroll
-    for (int pw = 0; pw < PW; ++pw) {
-      const int lo = T.xlo[pw];
-      const int n = T.xhi[pw] - lo + 1;
-      long_bins |= n > NXU;
-      soff[pw] = lo * VOX + lane * CV;
-#pragma unroll
-      for (int j = 0; j < NXU; ++j) tw[pw][j] = j < n ? T.Dx[(lo + j) * PWP + pw] : 0.0f;
-    }
-    static_assert(NXU <= 3, "pad voxels cover taps lo+1, lo+2 only");
     for (int sidx = 0; sidx < NS; ++sidx) {
-      float *padp = ring + sidx * STRIDE + RX * VOX;
+      // (TMA mode: the box always fills slots [0, RXR); taps past RX then read neighbouring voxels with weight 0)
+      float *padp = ring + sidx * STRIDE + (BULK == 2 ? RXR : RX) * VOX;
       for (int i = lane; i < 2 * VOX; i += 32) padp[i] = 0.0f;
     }
     __syncwarp();
@@ -940,27 +996,30 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
                         (long long)cv_v * C;
     float *dst0 = ring + cv_p * 4 + cv_v * VOX;
     // row offsets in units of 4 floats (16 B; C % 4 == 0), < 2^31 for any level the dispatcher accepts
-    for (int i = lane; i < nz; i += 32) zoff[i] = (int)(((long long)zlist[i] * slice_elems) >> 2);
-    for (int i = lane; i < ny; i += 32) yoff[i] = (int)(((long long)ylist[i] * row_elems) >> 2);
+    if constexpr (BULK == 2) {  // TMA coordinates are voxel indices
+      for (int i = lane; i < nz; i += 32) zoff[i] = (int)zlist[i] * it.L.H * it.L.W;
+      for (int i = lane; i < ny; i += 32) yoff[i] = (int)ylist[i] * it.L.W;
+    } else {
+      for (int i = lane; i < nz; i += 32) zoff[i] = (int)(((long long)zlist[i] * slice_elems) >> 2);
+      for (int i = lane; i < ny; i += 32) yoff[i] = (int)(((long long)ylist[i] * row_elems) >> 2);
+    }
     __syncwarp();
-    int pz = 0, py = 0, pstage = 0;
-    // BULK: the row is fetched by the TMA engine -- lane v issues one cp.async.bulk of this warp's channel chunk
-    // of voxel v (<= 128*CV bytes, contiguous), completion is counted in bytes on the stage's mbarrier.
-    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(ylist + 416);
-    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const int vbase = (((it.ok ? it.b : 0) * it.L.D + T.zmin) * it.L.H + T.ymin) * it.L.W + T.xmin;
+    const void *tmap = &tm.m[it.lvl];
+    int pz = 0, py = 0;
+    // BULK == 1: lane v issues one cp.async.bulk of this warp's channel chunk of voxel v (<= 128*CV bytes,
+    // contiguous); BULK == 2: one tensor copy per row; completion is counted in bytes on the stage's mbarrier.
     const unsigned chunk_bytes = (unsigned)min(VOX, C - it.chunk * VOX) * 4u;
     const float *srcb = fb_roi + ((long long)T.zmin * it.L.H + T.ymin) * row_elems + (long long)T.xmin * C +
                         (long long)it.chunk * VOX;
-    if constexpr (BULK) {
-      static_assert(NS <= 8, "eight mbarriers per warp");
-      if (lane == 0) {
-        for (int sidx = 0; sidx < NS; ++sidx) mbar_init(mbar0 + sidx * 8, 1);
-        mbar_fence_init();
-      }
-      __syncwarp();
-    }
     auto issue = [&]() {
-      if constexpr (BULK) {
+      if constexpr (BULK == 2) {
+        if (lane == 0) {
+          const unsigned mb = mbar0 + pstage * 8;
+          mbar_expect_tx(mb, (unsigned)(RXR * VOX * 4));
+          tma_load_2d(ring_s + (unsigned)(pstage * STRIDE) * 4u, tmap, it.chunk * VOX, vbase + zoff[pz] + yoff[py], mb);
+        }
+      } else if constexpr (BULK == 1) {
         const float *src = srcb + ((long long)(zoff[pz] + yoff[py]) << 2);
         const unsigned mb = mbar0 + pstage * 8;
         if (lane == 0) mbar_expect_tx(mb, (unsigned)RX * chunk_bytes);
@@ -987,8 +1046,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
       if (r < nrows) issue();
       else if constexpr (!BULK) cp_async_commit();
     }
-    unsigned cpar = 0;
-    int cstage = 0, r = 0;
+    int r = 0;
     for (int yi = 0; yi < ny; ++yi) {
       float t1[PW][CV];
 #pragma unroll
@@ -1099,6 +1157,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring2_kerne
   const long long out_base = (((long long)it.k * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
   const long long ch_stride = (long long)p.PD * p.PH * PW;
   copy_out_tile<ROWS, PW, CV>(acc, count, stage, lane, NB, it.chunk, C, p.out + out_base, ch_stride);
+  __syncwarp();  // the staging tile aliases the ring the next sub-item prefetches into
+  }  // sub-item loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1429,8 +1489,34 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_bwd2_kernel(con
       const int ncol = total / NB;
       unsigned sp = (unsigned)__cvta_generic_to_shared(st + lane * 33);
       const float *gp = p.grad_out + g0 + lane;
-#pragma unroll 4
-      for (int cl = 0; cl < ncol; ++cl) {
+      // four columns per iteration through four address registers and immediate shared offsets: a copy still
+      // queued in the memory pipeline does not hold up the address update of the next one
+      int cl = 0;
+      for (; cl + 4 <= ncol; cl += 4) {
+        const float *g0p = gp, *g1p = gp + col_stride, *g2p = gp + 2 * col_stride, *g3p = gp + 3 * col_stride;
+        if (lane < NB) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp), "l"(g0p) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0+4], [%1], 4;\n" ::"r"(sp), "l"(g1p) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0+8], [%1], 4;\n" ::"r"(sp), "l"(g2p) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0+12], [%1], 4;\n" ::"r"(sp), "l"(g3p) : "memory");
+        }
+        if (lane + 32 < NB) {
+          asm volatile("cp.async.ca.shared.global [%0+4224], [%1+128], 4;\n" ::"r"(sp), "l"(g0p) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0+4228], [%1+128], 4;\n" ::"r"(sp), "l"(g1p) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0+4232], [%1+128], 4;\n" ::"r"(sp), "l"(g2p) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0+4236], [%1+128], 4;\n" ::"r"(sp), "l"(g3p) : "memory");
+        }
+        for (int bin = lane + 64; bin < NB; bin += 32) {
+          const unsigned so = sp + (bin - lane) * 33 * 4;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(so), "l"(g0p + (bin - lane)) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0+4], [%1], 4;\n" ::"r"(so), "l"(g1p + (bin - lane)) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0+8], [%1], 4;\n" ::"r"(so), "l"(g2p + (bin - lane)) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0+12], [%1], 4;\n" ::"r"(so), "l"(g3p + (bin - lane)) : "memory");
+        }
+        sp += 16;
+        gp += 4 * col_stride;
+      }
+      for (; cl < ncol; ++cl) {
         if (lane < NB) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp), "l"(gp) : "memory");
         if (lane + 32 < NB)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sp + 32 * 33 * 4), "l"(gp + 32) : "memory");
@@ -1596,26 +1682,36 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_bwd2_kernel(con
             for (int c = 0; c < CV; ++c) v[h][c] = fmaf(wx[h][pw], u[pw][c], v[h][c]);
           }
         }
+      // all products and addresses first, then the reds back to back: distinct registers per red, so a red still
+      // waiting in the memory pipeline does not stall the next one on a register it has yet to read
+      float o[2][4][CV];
+      float *ad[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int zi = 0; zi < 4; ++zi) {
+          ad[h][zi] = q + h * (long long)C + zo[zi];
+          if constexpr (F2) {
+            const float2 t = __fmul2_rn(make_float2(zw[zi], zw[zi]), make_float2(v[h][0], v[h][1]));
+            o[h][zi][0] = t.x, o[h][zi][1] = t.y;
+          } else {
+#pragma unroll
+            for (int c = 0; c < CV; ++c) o[h][zi][c] = zw[zi] * v[h][c];
+          }
+        }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (xx + h >= RX || (has_gaps && !Sxany[xx + h])) continue;  // warp-uniform
-        float *qh = q + h * (long long)C;
 #pragma unroll
-        for (int zi = 0; zi < 4; ++zi) {
-          if (zi < nz) {
-            float o[CV];
-#pragma unroll
-            for (int c = 0; c < CV; ++c) o[c] = zw[zi] * v[h][c];
-            redv<CV>(qh + zo[zi], o);
-          }
-        }
+        for (int zi = 0; zi < 4; ++zi)
+          if (zi < nz) redv<CV>(ad[h][zi], o[h][zi]);
         for (int zi = 4; zi < nz; ++zi) {
           const int zrel = zlist[zi];
           const float wz = SDz[zrel * PP + it.pd];
-          float o[CV];
+          float t[CV];
 #pragma unroll
-          for (int c = 0; c < CV; ++c) o[c] = wz * v[h][c];
-          redv<CV>(qh + (long long)zrel * slice_elems, o);
+          for (int c = 0; c < CV; ++c) t[c] = wz * v[h][c];
+          redv<CV>(q + h * (long long)C + (long long)zrel * slice_elems, t);
         }
       }
     }
@@ -1803,6 +1899,7 @@ static int transpose_launch(const float *src, float *dst, int B, int rows, int c
 // Dispatch
 // ---------------------------------------------------------------------------------------------
 static int g_fwd_variant = 0;  // 0 = auto; see roi3d_set_tuning
+static int g_fwd_items_per_warp = 0;  // 0 = auto
 static int g_bwd_variant = 0;
 
 template <int PW, int ROWS, int CV, int NXU>
@@ -1844,26 +1941,73 @@ static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   return ROI3D_OK;
 }
 
-template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB = 0, bool BULK = false, bool F2 = false>
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// Fills one descriptor per level: tensor [B*D*H*W voxels][C channels] fp32, box = box_vox voxels x box_ch channels.
+static int build_tmaps(const RoiParams &p, int box_vox, int box_ch, TmapSet &tm) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ROI3D_ECUDA;
+  }
+  for (int l = 0; l < p.num_levels; ++l) {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.C, (cuuint64_t)p.B * p.lv[l].D * p.lv[l].H * p.lv[l].W};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.C * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_ch, (cuuint32_t)box_vox};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tm.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p.lv[l].feats), dims, strides,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+      return ROI3D_ECUDA;
+    }
+  }
+  return ROI3D_OK;
+}
+
+// TMA mode needs whole 32*CV-channel chunks, 16-byte aligned levels (checked by the caller) and int voxel indices.
+static bool tma_ok(const RoiParams &p, int vox_chunk) {
+  if (p.C % vox_chunk != 0) return false;
+  for (int l = 0; l < p.num_levels; ++l)
+    if ((long long)p.B * p.lv[l].D * p.lv[l].H * p.lv[l].W >= 2147483647LL - 64) return false;
+  return true;
+}
+
+template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB = 0, int BULK = 0, bool F2 = false, bool MULTI = false, int ITEMS = 1>
 static int launch_fwd_ring2(RoiParams &p, cudaStream_t st) {
-  using TB = Tables<PW>;
-  constexpr int VOX = 32 * CV;
-  constexpr int RING = NS * (RXR + 2) * VOX;
-  constexpr int STAGE = ROWS * PW * 33;
-  constexpr int RING_OR_STAGE = RING > STAGE ? RING : STAGE;
-  constexpr int WARP_FLOATS = (480 / 4 + RING_OR_STAGE + 3) / 4 * 4;
-  constexpr int SH_FLOATS = RXMAX * TB::PWP + RYMAX * 16 + RZMAX2 * 16 + 32 + 3 * 32 * 2 + 16;
-  const size_t smem = ((size_t)((SH_FLOATS + 3) / 4 * 4) + (size_t)kWarps * WARP_FLOATS) * sizeof(float);
+  using LY = Ring2Layout<PW, ROWS, CV, NS, RXR, BULK>;
+  const size_t smem = LY::BYTES;
   p.nchunk = ceil_div(p.C, 32 * CV);
   p.nphg = ceil_div(p.PH, ROWS);
   p.items_per_roi = p.nchunk * p.PD * p.nphg;
-  p.ctas_per_roi = ceil_div(p.items_per_roi, kWarps);
+  p.items_per_warp = !MULTI ? 1 : g_fwd_items_per_warp > 0 ? g_fwd_items_per_warp : ITEMS;
+  p.ctas_per_roi = ceil_div(p.items_per_roi, kWarps * p.items_per_warp);
   p.total_items = (long long)p.K * p.items_per_roi;
   const long long blocks = (long long)p.K * p.ctas_per_roi;
   ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
-  auto kern = roi_align3d_fwd_ring2_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB, BULK, F2>;
+  static TmapSet tm;  // only the TMA instantiations read it
+  if constexpr (BULK == 2) {
+    const int rc = build_tmaps(p, RXR, 32 * CV, tm);
+    if (rc) return rc;
+  }
+  auto kern = roi_align3d_fwd_ring2_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB, BULK, F2, MULTI>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p);
+  kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p, tm);
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
 }
@@ -1949,14 +2093,19 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
   if (p.PW == 7) {
     if (ring_ok && cvmax >= 2) {
       if (p.PH <= 16 && p.PD <= 16) {
-        if (v == 0 || v == 50) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, false, true>(p, st);  // default
+        if (v == 0 || v == 50) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, 0, true>(p, st);  // default
         if (v == 22) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2>(p, st);  // scalar-FMA twin of the default
+        if (v == 56) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, 0, true, true, 2>(p, st);  // walks 2 sub-items per warp
+        if (v >= 70 && v <= 72 && tma_ok(p, 64)) {
+          if (v == 70) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, 2, true>(p, st);
+          if (v == 71) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, 2, true>(p, st);
+        }
         if (v == 20) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2>(p, st);
-        if (v == 51) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, false, true>(p, st);
-        if (v == 52) return launch_fwd_ring2<7, 7, 2, 3, 6, 18, 2, false, true>(p, st);
-        if (v == 40) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, true>(p, st);
-        if (v == 41) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, true>(p, st);
-        if (v == 42) return launch_fwd_ring2<7, 7, 2, 3, 6, 18, 2, true>(p, st);
+        if (v == 51) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, 0, true>(p, st);
+        if (v == 52) return launch_fwd_ring2<7, 7, 2, 3, 6, 18, 2, 0, true>(p, st);
+        if (v == 40) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, 1>(p, st);
+        if (v == 41) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, 1>(p, st);
+        if (v == 42) return launch_fwd_ring2<7, 7, 2, 3, 6, 18, 2, 1>(p, st);
         if (v == 21) return launch_fwd_ring2<7, 7, 2, 3, 3, 18, 3>(p, st);
         if (v == 23) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 0>(p, st);
       }
@@ -1978,11 +2127,17 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
   if (p.PW == 14) {
     if (ring_ok && cvmax >= 2) {
       if (p.PH <= 16 && p.PD <= 16) {
-        if (v == 0 || v == 50) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0, false, true>(p, st);  // default
+        if (v == 0 || v == 56) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0, 0, true, true, 7>(p, st);  // default
+        if (v == 50) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0, 0, true>(p, st);  // one sub-item per warp
         if (v == 20) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0>(p, st);  // scalar-FMA twin of the default
-        if (v == 40) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 0, true>(p, st);
-        if (v == 51) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2, false, true>(p, st);
-        if (v == 52) return launch_fwd_ring2<14, 7, 2, 3, 3, 18, 0, false, true>(p, st);
+        if (v >= 70 && v <= 72 && tma_ok(p, 64)) {
+          if (v == 70) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0, 2, true>(p, st);
+          if (v == 71) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 0, 2, true>(p, st);
+          if (v == 72) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2, 2, true>(p, st);
+        }
+        if (v == 40) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 0, 1>(p, st);
+        if (v == 51) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2, 0, true>(p, st);
+        if (v == 52) return launch_fwd_ring2<14, 7, 2, 3, 3, 18, 0, 0, true>(p, st);
         if (v == 21) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 3>(p, st);
         if (v == 22) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2>(p, st);
         if (v == 23) return launch_fwd_ring2<14, 7, 1, 3, 4, 20, 0>(p, st);
@@ -2014,27 +2169,33 @@ static int dispatch_bwd(RoiParams &p, cudaStream_t st) {
     if (v == 1 || cvmax == 1) return launch_bwd<7, 7, 1, 40>(p, st);
     if (v == 2 && cvmax >= 4) return launch_bwd<7, 4, 4, 16>(p, st);
     if (p.PH <= 16 && p.PD <= 16 && cvmax >= 2) {
+      if (v == 0 || v == 61) return launch_bwd2<7, 7, 2, true>(p, st);  // default
       if (v == 60) return launch_bwd2<7, 7, 2, false>(p, st);
-      if (v == 61) return launch_bwd2<7, 7, 2, true>(p, st);
+      if (v == 64) return launch_bwd2<7, 4, 2, true>(p, st);
       if (p.PH <= 8 && p.PD <= 8) {
         if (v == 62) return launch_bwd2<7, 7, 2, false, 4, 8>(p, st);
         if (v == 63) return launch_bwd2<7, 7, 2, true, 4, 8>(p, st);
+        if (v == 65) return launch_bwd2<7, 4, 2, true, 4, 8>(p, st);
+        if (v == 66) return launch_bwd2<7, 4, 2, true, 5, 8>(p, st);
       }
     }
     if (v == 50) return launch_bwd<7, 7, 2, 26, true>(p, st);
-    return launch_bwd<7, 7, 2, 26>(p, st);
+    return launch_bwd<7, 7, 2, 26>(p, st);  // per-warp tables (v == 3, or PH / PD > 16)
   }
   if (p.PW == 14) {
     if (v == 1 || cvmax == 1) return launch_bwd<14, 7, 1, 40>(p, st);
     if (v == 2 && cvmax >= 4) return launch_bwd<14, 2, 4, 16>(p, st);
     if (p.PH <= 16 && p.PD <= 16 && cvmax >= 2) {
+      if (v == 0 || v == 61) return launch_bwd2<14, 4, 2, true>(p, st);  // default
       if (v == 60) return launch_bwd2<14, 4, 2, false>(p, st);
-      if (v == 61) return launch_bwd2<14, 4, 2, true>(p, st);
       if (v == 62) return launch_bwd2<14, 4, 2, false, 3>(p, st);
       if (v == 63) return launch_bwd2<14, 4, 2, true, 3>(p, st);
+      if (v == 64) return launch_bwd2<14, 2, 2, true>(p, st);
+      if (v == 65) return launch_bwd2<14, 2, 2, true, 4>(p, st);
+      if (v == 66) return launch_bwd2<14, 2, 2, true, 5>(p, st);
     }
     if (v == 50) return launch_bwd<14, 4, 2, 30, true>(p, st);
-    return launch_bwd<14, 4, 2, 30>(p, st);
+    return launch_bwd<14, 4, 2, 30>(p, st);  // per-warp tables (v == 3, or PH / PD > 16)
   }
   if (cvmax >= 2) return launch_generic<2>(p, false, st);
   return launch_generic<1>(p, false, st);
@@ -2078,6 +2239,7 @@ extern "C" {
 int roi3d_set_tuning(int key, int value) {
   if (key == 0) g_fwd_variant = value;
   else if (key == 1) g_bwd_variant = value;
+  else if (key == 2) g_fwd_items_per_warp = value;
   else return ROI3D_EINVAL;
   return ROI3D_OK;
 }

@@ -140,7 +140,8 @@ int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, in
 int roi3d_nms3d_host(const float *dets_host, int n, float iou_thr, int64_t *keep_host, int32_t *num_keep_host);
 
 /* Experiment knob (not part of the reference surface): key 0 = forward kernel variant, 1 = backward
- * kernel variant; value 0 = auto, 1/2 = alternative register tilings, 99 = literal (reference-order) path. */
+ * kernel variant; value 0 = auto, 1/2 = alternative register tilings, 99 = literal (reference-order) path.
+ * key 2 = sub-items one forward warp walks per RoI (0 = auto). */
 int roi3d_set_tuning(int key, int value);
 
 /* Host-buffer form of RoIAlign3D forward (H2D feats+rois, kernel, D2H out): the e2e path bench.py times. */

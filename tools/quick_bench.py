@@ -56,10 +56,12 @@ if "c2" in which:
     rois = torch.from_numpy(synth.c2_rois(512, seed=2)).to(dev)
     layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
     for v in FWD_VARIANTS:
-        _lib.set_tuning(0, v)
+        _lib.set_tuning(0, v % 1000)
+        _lib.set_tuning(2, v // 1000)
         med, mn = timeit(lambda: layer(fcl, rois))
         res["c2_fwd_cl_v%d_us" % v] = (med, mn)
     _lib.set_tuning(0, 0)
+    _lib.set_tuning(2, 0)
     med, mn = timeit(lambda: layer(fcl, rois), flush=False)
     res["c2_fwd_cl_noflush_us"] = (med, mn)
     roi3d_b200._util._CACHE_SIZE = 0
@@ -131,10 +133,12 @@ if "c3" in which:
     lv = ex.map_roi_levels(rois, 4)
     res["c3_level_hist"] = np.bincount(lv.cpu().numpy(), minlength=4).tolist()
     for v in FWD_VARIANTS:
-        _lib.set_tuning(0, v)
+        _lib.set_tuning(0, v % 1000)
+        _lib.set_tuning(2, v // 1000)
         med, mn = timeit(lambda: ex(feats, rois), iters=5)
         res["c3_fwd_v%d_us" % v] = (med, mn)
     _lib.set_tuning(0, 0)
+    _lib.set_tuning(2, 0)
     for f in feats:
         f.requires_grad_(True)
     out = ex(feats, rois)
