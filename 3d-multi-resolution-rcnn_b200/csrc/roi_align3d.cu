@@ -2186,12 +2186,12 @@ static int dispatch_bwd(RoiParams &p, cudaStream_t st) {
     if (v == 1 || cvmax == 1) return launch_bwd<14, 7, 1, 40>(p, st);
     if (v == 2 && cvmax >= 4) return launch_bwd<14, 2, 4, 16>(p, st);
     if (p.PH <= 16 && p.PD <= 16 && cvmax >= 2) {
-      if (v == 0 || v == 61) return launch_bwd2<14, 4, 2, true>(p, st);  // default
+      if (v == 0 || v == 65) return launch_bwd2<14, 2, 2, true, 4>(p, st);  // default: 2 ph rows per warp, 16 warps / SM
+      if (v == 61) return launch_bwd2<14, 4, 2, true>(p, st);
       if (v == 60) return launch_bwd2<14, 4, 2, false>(p, st);
       if (v == 62) return launch_bwd2<14, 4, 2, false, 3>(p, st);
       if (v == 63) return launch_bwd2<14, 4, 2, true, 3>(p, st);
       if (v == 64) return launch_bwd2<14, 2, 2, true>(p, st);
-      if (v == 65) return launch_bwd2<14, 2, 2, true, 4>(p, st);
       if (v == 66) return launch_bwd2<14, 2, 2, true, 5>(p, st);
     }
     if (v == 50) return launch_bwd<14, 4, 2, 30, true>(p, st);
