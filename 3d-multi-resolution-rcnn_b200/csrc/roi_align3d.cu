@@ -51,6 +51,7 @@ struct RoiParams {
   float *out;             // forward
   const float *grad_out;  // backward
   int64_t *lvls_out;
+  const int *out_rows;    // forward: output row of RoI k (nullptr = k)
   int nchunk, nphg;
   long long total_items;
   int items_per_roi, ctas_per_roi;  // ring2 kernels: CTA -> (RoI, group of kWarps * items_per_warp sub-items)
@@ -88,7 +89,7 @@ __device__ __forceinline__ void redv(float *p, const float (&v)[CV]) {
 
 // Per-warp decode of one work item + RoI geometry.
 struct Item {
-  int k, chunk, pd, ph0, rows, lvl, b;
+  int k, krow, chunk, pd, ph0, rows, lvl, b;
   bool ok;
   Axis axw, axh, axd;
   LevelDev L;
@@ -103,6 +104,7 @@ __device__ __forceinline__ Item decode_item(const RoiParams &p, long long item64
   item /= (unsigned)p.PD;
   it.chunk = (int)(item % (unsigned)p.nchunk);
   it.k = (int)(item / (unsigned)p.nchunk);
+  it.krow = p.out_rows != nullptr ? __ldg(p.out_rows + it.k) : it.k;
   it.ph0 = (int)phg * ROWS;
   it.rows = min(ROWS, p.PH - it.ph0);
   const float *roi = p.rois + (long long)it.k * 7;
@@ -295,7 +297,7 @@ __device__ __noinline__ void literal_tile_fwd(const Item &it, const float *fb, i
       if (active) {
 #pragma unroll
         for (int c = 0; c < CV; ++c)
-          out[((((long long)it.k * C + c_base + c) * PD + it.pd) * PH + it.ph0 + r) * PW + pw] = v[c];
+          out[((((long long)it.krow * C + c_base + c) * PD + it.pd) * PH + it.ph0 + r) * PW + pw] = v[c];
       }
     }
 }
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_cl_kernel(const R
   // ---- epilogue: divide by the sample count, transpose through smem, stream out ----
   const int NB = it.rows * PW;
   float *stage = sm;  // aliases the tables: all table reads are done
-  const long long out_base = (((long long)it.k * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
+  const long long out_base = (((long long)it.krow * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
   const long long ch_stride = (long long)p.PD * p.PH * PW;
   copy_out_tile<ROWS, PW, CV>(acc, count, stage, lane, NB, it.chunk, C, p.out + out_base, ch_stride);
 }
@@ -711,7 +713,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) roi_align3d_fwd_ring_kernel
   // ---- epilogue: divide by the sample count, transpose through smem, stream out ----
   const int NB = it.rows * PW;
   float *stage = ring;  // the ring is drained
-  const long long out_base = (((long long)it.k * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
+  const long long out_base = (((long long)it.krow * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
   const long long ch_stride = (long long)p.PD * p.PH * PW;
   copy_out_tile<ROWS, PW, CV>(acc, count, stage, lane, NB, it.chunk, C, p.out + out_base, ch_stride);
 }
@@ -815,6 +817,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB)
   Item it;
   {
     it.k = k;
+    it.krow = p.out_rows != nullptr ? __ldg(p.out_rows + k) : k;
     it.pd = 0, it.chunk = 0, it.ph0 = 0, it.rows = 0;
     float r[7];
 #pragma unroll
@@ -1154,7 +1157,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB)
   // ---- epilogue: divide by the sample count, transpose through smem, stream out ----
   const int NB = it.rows * PW;
   float *stage = ring;  // the ring is drained
-  const long long out_base = (((long long)it.k * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
+  const long long out_base = (((long long)it.krow * C) * p.PD + it.pd) * p.PH * PW + (long long)it.ph0 * PW;
   const long long ch_stride = (long long)p.PD * p.PH * PW;
   copy_out_tile<ROWS, PW, CV>(acc, count, stage, lane, NB, it.chunk, C, p.out + out_base, ch_stride);
   __syncwarp();  // the staging tile aliases the ring the next sub-item prefetches into
@@ -1745,7 +1748,7 @@ __global__ void __launch_bounds__(kWarps * 32) roi_align3d_fwd_generic_kernel(co
     if (active) {
 #pragma unroll
       for (int c = 0; c < CV; ++c)
-        p.out[((((long long)it.k * C + c_base + c) * p.PD + it.pd) * p.PH + it.ph0) * p.PW + pw] = v[c];
+        p.out[((((long long)it.krow * C + c_base + c) * p.PD + it.pd) * p.PH + it.ph0) * p.PW + pw] = v[c];
     }
   }
 }
@@ -1900,6 +1903,7 @@ static int transpose_launch(const float *src, float *dst, int B, int rows, int c
 // ---------------------------------------------------------------------------------------------
 static int g_fwd_variant = 0;  // 0 = auto; see roi3d_set_tuning
 static int g_fwd_items_per_warp = 0;  // 0 = auto
+extern int g_host_pipeline_kb;        // host_api.cu
 static int g_bwd_variant = 0;
 
 template <int PW, int ROWS, int CV, int NXU>
@@ -2226,7 +2230,7 @@ static int fill_params(RoiParams &p, const roi3d_level_t *levels, int num_levels
   p.num_levels = num_levels;
   p.inv_finest = num_levels > 1 ? 1.0f / finest_scale : 0.0f;
   p.B = B, p.C = C, p.rois = rois, p.K = K, p.PD = PD, p.PH = PH, p.PW = PW, p.sample_num = sample_num;
-  p.out = nullptr, p.grad_out = nullptr, p.lvls_out = nullptr, p.bug_compat = 0;
+  p.out = nullptr, p.grad_out = nullptr, p.lvls_out = nullptr, p.out_rows = nullptr, p.bug_compat = 0;
   return ROI3D_OK;
 }
 
@@ -2240,6 +2244,7 @@ int roi3d_set_tuning(int key, int value) {
   if (key == 0) g_fwd_variant = value;
   else if (key == 1) g_bwd_variant = value;
   else if (key == 2) g_fwd_items_per_warp = value;
+  else if (key == 4) g_host_pipeline_kb = value;
   else return ROI3D_EINVAL;
   return ROI3D_OK;
 }
@@ -2282,6 +2287,22 @@ int roi3d_roi_align3d_forward(const float *feats_dev, int layout, int B, int C, 
   lv.feats_dev = feats_dev, lv.grad_dev = nullptr, lv.layout = layout, lv.D = D, lv.H = H, lv.W = W;
   lv.spatial_scale = spatial_scale, lv.spatial_scale_depth = spatial_scale_depth;
   return roi3d_extract_forward(&lv, 1, B, C, rois_dev, K, PD, PH, PW, sample_num, 56.0f, out_dev, nullptr, stream);
+}
+
+int roi3d_roi_align3d_forward_rows(const float *feats_dev, int layout, int B, int C, int D, int H, int W,
+                                   const float *rois_dev, int K, int PD, int PH, int PW, float spatial_scale,
+                                   float spatial_scale_depth, int sample_num, float *out_dev, const int32_t *out_rows_dev,
+                                   void *stream) {
+  roi3d_level_t lv;
+  lv.feats_dev = feats_dev, lv.grad_dev = nullptr, lv.layout = layout, lv.D = D, lv.H = H, lv.W = W;
+  lv.spatial_scale = spatial_scale, lv.spatial_scale_depth = spatial_scale_depth;
+  RoiParams p;
+  int rc = fill_params(p, &lv, 1, B, C, rois_dev, K, PD, PH, PW, sample_num, 56.0f, false);
+  if (rc) return rc;
+  ROI3D_CHECK_ARG(K == 0 || out_dev != nullptr, "out is NULL");
+  p.out = out_dev;
+  p.out_rows = out_rows_dev;
+  return dispatch_fwd(p, (cudaStream_t)stream);
 }
 
 int roi3d_roi_align3d_backward(const float *grad_out_dev, const float *rois_dev, int K, int PD, int PH, int PW,

@@ -41,6 +41,8 @@ def _load():
         "roi3d_set_tuning": (c_int, [c_int, c_int]),
         "roi3d_roi_align3d_forward": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int,
                                               c_int, c_float, c_float, c_int, P, P]),
+        "roi3d_roi_align3d_forward_rows": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int,
+                                                   c_int, c_int, c_float, c_float, c_int, P, P, P]),
         "roi3d_roi_align3d_backward": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P, c_int,
                                                c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
         "roi3d_map_roi_levels": (c_int, [P, c_int, c_int, c_float, P, P]),

@@ -75,6 +75,14 @@ int roi3d_roi_align3d_forward(const float *feats_dev, int layout, int B, int C, 
                               const float *rois_dev, int K, int PD, int PH, int PW, float spatial_scale,
                               float spatial_scale_depth, int sample_num, float *out_dev, void *stream);
 
+/* Forward with an output row map: the tile of RoI k is written to row out_rows_dev[k] of out_dev (NULL = row k).
+ * out_dev may be mapped pinned host memory (the kernel's streaming stores then cross PCIe directly), which is how
+ * roi3d_roi_align3d_forward_host returns results while later z slabs of the volume are still being uploaded. */
+int roi3d_roi_align3d_forward_rows(const float *feats_dev, int layout, int B, int C, int D, int H, int W,
+                                   const float *rois_dev, int K, int PD, int PH, int PW, float spatial_scale,
+                                   float spatial_scale_depth, int sample_num, float *out_dev,
+                                   const int32_t *out_rows_dev, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * RoIAlign3D backward.
  * Replaces: roi_align_cuda.backward3d -> ROIAlignBackwardLaucher3D,
@@ -141,7 +149,8 @@ int roi3d_nms3d_host(const float *dets_host, int n, float iou_thr, int64_t *keep
 
 /* Experiment knob (not part of the reference surface): key 0 = forward kernel variant, 1 = backward
  * kernel variant; value 0 = auto, 1/2 = alternative register tilings, 99 = literal (reference-order) path.
- * key 2 = sub-items one forward warp walks per RoI (0 = auto). */
+ * key 2 = sub-items one forward warp walks per RoI (0 = auto); key 4 = volume size in KB from which
+ * roi3d_roi_align3d_forward_host pipelines its copies (0 = auto, 32 MB; -1 = never). */
 int roi3d_set_tuning(int key, int value);
 
 /* Host-buffer form of RoIAlign3D forward (H2D feats+rois, kernel, D2H out): the e2e path bench.py times. */

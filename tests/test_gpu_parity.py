@@ -523,3 +523,32 @@ def test_topk_full_p2_level_and_large_segment(oracle, dev):
         assert torch.equal(s[idx[0]], tv)
         want = oracle.topk(s.cpu().numpy(), k)
         assert np.array_equal(idx[0].cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["NCDHW", "NDHWC"])
+@pytest.mark.parametrize("pipeline_kb", [-1, 1])
+def test_roi_align_host_entry(oracle, dev, layout, pipeline_kb):
+    """roi3d_roi_align3d_forward_host (numpy in / out): the plain path and the z-slab pipelined path (forced on a
+    small volume through tuning key 4) give the device path's bits and the oracle's values; RoIs that are empty,
+    out of the volume or NaN still land in their own output rows."""
+    import roi3d_b200
+    from roi3d_b200.ops import RoIAlign3D, roi_align_3d_host
+    shape = (1, 64, 24, 20, 28)
+    f = _feats(shape, 21)
+    rois = np.concatenate([synth.c2_rois(96, seed=5, img=(112, 80, 48)),
+                           synth.adversarial_rois(shape[2:], 0.25, 0.5)], 0)
+    rois = rois[np.random.RandomState(0).permutation(len(rois))]
+    want = oracle.roi_align3d_forward(f, rois, 7, 7, 0.25, 0.5, 2)
+    dev_out = RoIAlign3D(7, 7, 0.25, 0.5, 2)(cl(torch.from_numpy(f).to(dev)), torch.from_numpy(rois).to(dev))
+    src = f if layout == "NCDHW" else np.ascontiguousarray(f.transpose(0, 2, 3, 4, 1))
+    pinned = torch.empty(dev_out.shape, dtype=torch.float32).pin_memory()  # mapped: the kernels store into it directly
+    roi3d_b200._lib.set_tuning(4, pipeline_kb)
+    try:
+        got = roi_align_3d_host(src, rois, 7, 7, 0.25, 0.5, 2, layout=layout)
+        again = roi_align_3d_host(src, rois, 7, 7, 0.25, 0.5, 2, layout=layout, out=pinned.numpy())
+    finally:
+        roi3d_b200._lib.set_tuning(4, 0)
+    assert np.array_equal(got, dev_out.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(got, again, equal_nan=True)
+    assert rel_err(got, want) <= FWD_TOL
