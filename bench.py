@@ -328,13 +328,13 @@ def main():
         alg_bytes = out_bytes + U * C2["C"] * 4 + C2["K"] * 28
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "r01_final_c2_fwd_ncu_summary.json")
+        prof = os.path.join(ROOT, "profiles", "r01_end_c2_fwd_ncu_summary.json")
         if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_ring2_kernel<7,7,2,3,5,18,2>", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_ring2_kernel<7,7,2,3,5,18,2,0,1,0>", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes": alg_bytes, "unique_voxels": U, "kernel_us": kernel_ms * 1e3,
                     "output_only_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9}

@@ -552,3 +552,30 @@ def test_roi_align_host_entry(oracle, dev, layout, pipeline_kb):
     assert np.array_equal(got, dev_out.cpu().numpy(), equal_nan=True)
     assert np.array_equal(got, again, equal_nan=True)
     assert rel_err(got, want) <= FWD_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("out_size", [7, 14, 5])
+def test_roi_align_forward_row_map(dev, out_size):
+    """roi3d_roi_align3d_forward_rows: RoI k lands in output row out_rows[k], bit-identical to the plain call
+    (ring kernels for 7 / 14 wide outputs, literal kernels for other widths, wide RoIs included)."""
+    import roi3d_b200
+    from roi3d_b200 import _lib
+    from roi3d_b200.ops import RoIAlign3D
+    from roi3d_b200._util import stream_ptr
+    shape = (1, 64, 12, 40, 72)
+    f = cl(torch.from_numpy(_feats(shape, 31)).to(dev))
+    rois_np = np.concatenate([synth.c2_rois(40, seed=9, img=(288, 160, 24)),
+                              np.array([[0, 2, 3, 250, 120, 1, 12]], np.float32)], 0)
+    rois = torch.from_numpy(rois_np).to(dev)
+    K = rois.shape[0]
+    plain = RoIAlign3D(out_size, out_size, 0.25, 0.5, 2)(f, rois)
+    perm = torch.randperm(K, generator=torch.Generator().manual_seed(1)).to(torch.int32).to(dev)
+    out = torch.full_like(plain, float("nan"))
+    fcl = f.permute(0, 2, 3, 4, 1)
+    assert fcl.is_contiguous()
+    _lib.check(_lib.lib.roi3d_roi_align3d_forward_rows(
+        fcl.data_ptr(), _lib.NDHWC, 1, 64, 12, 40, 72, rois.data_ptr(), K, out_size, out_size, out_size, 0.25, 0.5, 2,
+        out.data_ptr(), perm.data_ptr(), stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out[perm.long()], plain)

@@ -73,7 +73,7 @@ def launches(path, out):
         name = r[4]
         short = name.split("(")[0][-90:]
         ns = float(r[14])
-        a = agg.setdefault(short, [0, 0.0, r[7], r[8]])
+        a = agg.setdefault((short, r[8]), [0, 0.0, r[7], r[8]])
         a[0] += 1
         a[1] += ns
         total += ns
@@ -81,7 +81,7 @@ def launches(path, out):
         fh.write("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n\n")
         fh.write("source: `%s`  (%d launches, %.1f us total)\n\n" % (path, len(rows), total / 1e3))
         fh.write("| kernel | launches | total us | avg us | share | block | grid |\n|---|---|---|---|---|---|---|\n")
-        for k, (n, ns, blk, grd) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        for (k, _g), (n, ns, blk, grd) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             fh.write("| `%s` | %d | %.1f | %.1f | %.1f%% | %s | %s |\n" % (k, n, ns / 1e3, ns / 1e3 / n, 100 * ns / total, blk, grd))
     print("wrote", out)
 
