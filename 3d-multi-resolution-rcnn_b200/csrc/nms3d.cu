@@ -50,6 +50,28 @@ __device__ __forceinline__ bool iou3d_gt(const SortedBox &a, float Sa, const Sor
   return __fdiv_rn(inter, uni) > thr;
 }
 
+// Evaluation-time flavour (N1): the reference's numpy nms_3d_python (mmdet/core/evaluation/coco_utils.py:245-282)
+// works in float64 on the json boxes (fp32 values widened), volume = ((x2-x1+1)*(y2-y1+1))*(z2-z1+1), iou =
+// inter / ((vol_i + vol_j) - inter), and KEEPS iou <= thr -- so a NaN iou suppresses.  Same operation order,
+// no contraction (explicit _rn double intrinsics).
+__device__ __forceinline__ bool iou3d_f64_suppresses(const SortedBox &a, const SortedBox &b, double thr) {
+  const double ax1 = a.x1, ay1 = a.y1, ax2 = a.x2, ay2 = a.y2, az1 = a.z1, az2 = a.z2;
+  const double bx1 = b.x1, by1 = b.y1, bx2 = b.x2, by2 = b.y2, bz1 = b.z1, bz2 = b.z2;
+  const double va = __dmul_rn(__dmul_rn(__dadd_rn(__dsub_rn(ax2, ax1), 1.0), __dadd_rn(__dsub_rn(ay2, ay1), 1.0)),
+                              __dadd_rn(__dsub_rn(az2, az1), 1.0));
+  const double vb = __dmul_rn(__dmul_rn(__dadd_rn(__dsub_rn(bx2, bx1), 1.0), __dadd_rn(__dsub_rn(by2, by1), 1.0)),
+                              __dadd_rn(__dsub_rn(bz2, bz1), 1.0));
+  // np.maximum / np.minimum propagate NaN; fmax / fmin do not -- a NaN coordinate must poison the iou
+  const bool nan_in = !(ax1 == ax1 && ay1 == ay1 && ax2 == ax2 && ay2 == ay2 && az1 == az1 && az2 == az2 && bx1 == bx1 &&
+                        by1 == by1 && bx2 == bx2 && by2 == by2 && bz1 == bz1 && bz2 == bz2);
+  const double w = fmax(0.0, __dadd_rn(__dsub_rn(fmin(ax2, bx2), fmax(ax1, bx1)), 1.0));
+  const double h = fmax(0.0, __dadd_rn(__dsub_rn(fmin(ay2, by2), fmax(ay1, by1)), 1.0));
+  const double d = fmax(0.0, __dadd_rn(__dsub_rn(fmin(az2, bz2), fmax(az1, bz1)), 1.0));
+  const double inter = __dmul_rn(__dmul_rn(w, h), d);
+  const double iou = __ddiv_rn(inter, __dsub_rn(__dadd_rn(va, vb), inter));
+  return nan_in || !(iou <= thr);
+}
+
 // ------------------------------------------------------------------------------------------------
 // 1. rank + gather.  grid (ceil(n_max/32), nseg), block 256 = 32 boxes x 8 slices of the j range
 //    (each warp scans one slice with warp-uniform loads; partial ranks are summed through smem).
@@ -107,8 +129,9 @@ __global__ void __launch_bounds__(256) nms3d_rank_kernel(const float *__restrict
 // 2. suppression bit matrix, upper triangle.  grid (ceil(cb/4), cb, nseg), block 256 =
 //    64 rows x 4 column tiles.  mask[seg][row][cbm] (cbm = ceil(n_max/64)).
 // ------------------------------------------------------------------------------------------------
+template <bool F64>
 __global__ void __launch_bounds__(256) nms3d_mask_kernel(const SortedBox *__restrict__ sorted,
-                                                         const int32_t *seg_counts, int n_max, float thr,
+                                                         const int32_t *seg_counts, int n_max, float thr, double thr64,
                                                          unsigned long long *__restrict__ mask) {
   const int seg = blockIdx.z;
   const int n = seg_counts ? min(max(seg_counts[seg], 0), n_max) : n_max;
@@ -133,7 +156,7 @@ __global__ void __launch_bounds__(256) nms3d_mask_kernel(const SortedBox *__rest
   const int start = (cblk == rb) ? rl + 1 : 0;
   unsigned long long t = 0;
   for (int j = start; j < csize; ++j) {
-    if (iou3d_gt(a, Sa, cols[cq][j], thr)) t |= 1ULL << j;
+    if (F64 ? iou3d_f64_suppresses(a, cols[cq][j], thr64) : iou3d_gt(a, Sa, cols[cq][j], thr)) t |= 1ULL << j;
   }
   mask[((long long)seg * n_max + row) * cbm + cblk] = t;
 }
@@ -415,9 +438,9 @@ size_t roi3d_nms3d_workspace_bytes(int nseg, int n_max) {
   return carve(nullptr, nseg, n_max).bytes;
 }
 
-int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, float iou_thr,
-                        int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev, void *workspace_dev,
-                        size_t workspace_bytes, void *stream) {
+static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, float iou_thr,
+                        double iou_thr64, bool f64, int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev,
+                        void *workspace_dev, size_t workspace_bytes, void *stream) {
   ROI3D_CHECK_ARG(nseg >= 0 && n_max >= 0, "bad sizes nseg=%d n_max=%d", nseg, n_max);
   if (nseg == 0) return ROI3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -439,8 +462,12 @@ int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, in
   nms3d_rank_kernel<<<dim3(ceil_div(n_max, 32), nseg), 256, 0, st>>>(dets_dev, seg_counts_dev, n_max, w.sorted,
                                                                       w.order);
   ROI3D_LAUNCH_CHECK();
-  nms3d_mask_kernel<<<dim3(ceil_div(cbm, 4), cbm, nseg), 256, 0, st>>>(w.sorted, seg_counts_dev, n_max, iou_thr,
-                                                                       w.mask);
+  if (f64)
+    nms3d_mask_kernel<true><<<dim3(ceil_div(cbm, 4), cbm, nseg), 256, 0, st>>>(w.sorted, seg_counts_dev, n_max, iou_thr,
+                                                                               iou_thr64, w.mask);
+  else
+    nms3d_mask_kernel<false><<<dim3(ceil_div(cbm, 4), cbm, nseg), 256, 0, st>>>(w.sorted, seg_counts_dev, n_max, iou_thr,
+                                                                                iou_thr64, w.mask);
   ROI3D_LAUNCH_CHECK();
   {
     const size_t panel_bytes = (size_t)kPanelBufs * 64 * kPanelW * sizeof(unsigned long long);  // 64 KiB
@@ -450,6 +477,20 @@ int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, in
   }
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
+}
+
+int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, float iou_thr,
+                        int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev, void *workspace_dev,
+                        size_t workspace_bytes, void *stream) {
+  return nms3d_launch(dets_dev, seg_counts_dev, nseg, n_max, iou_thr, 0.0, false, keep_dev, keep_by_score_dev,
+                      num_keep_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int roi3d_nms3d_eval_batched(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, double iou_thr,
+                             int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev, void *workspace_dev,
+                             size_t workspace_bytes, void *stream) {
+  return nms3d_launch(dets_dev, seg_counts_dev, nseg, n_max, 0.0f, iou_thr, true, keep_dev, keep_by_score_dev,
+                      num_keep_dev, workspace_dev, workspace_bytes, stream);
 }
 
 }  // extern "C"

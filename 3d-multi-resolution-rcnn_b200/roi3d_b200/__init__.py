@@ -9,6 +9,7 @@ Module paths mirror the reference's (`mmdet.X` -> `roi3d_b200.X`):
     roi3d_b200.core.anchor               AnchorGenerator3D                              (core/anchor/anchor_generator_3d.py)
     roi3d_b200.core.bbox                 delta2bbox3D, bbox2roi3D                       (core/bbox/transforms.py)
     roi3d_b200.core.post_processing      multiclass_nms_3d                              (core/post_processing/bbox_nms.py)
+    roi3d_b200.core.evaluation           apply_nms, nms_3d_python                       (core/evaluation/coco_utils.py)
     roi3d_b200.parallel                  shard_indices, gather_detections               (replaces eval_hooks.py:134-149)
 
 Everything computes in hand-written CUDA (libroi3d_b200.so, C ABI in include/roi3d_b200.h).  Importing this
@@ -19,6 +20,7 @@ from . import ops
 from .core.anchor import AnchorGenerator3D
 from .core.bbox import bbox2roi3D, delta2bbox3D
 from .core.post_processing import multiclass_nms_3d
+from .core.evaluation import apply_nms, nms_3d_eval_batched
 from .models.anchor_heads import RPNProposal3D
 from .models.builder import build_roi_extractor, build_rpn_proposal
 from .models.roi_extractors import SingleRoIExtractor
@@ -26,4 +28,4 @@ from .ops import RoIAlign3D, nms, roi_align_3d, soft_nms
 
 __all__ = ['ops', 'nms', 'soft_nms', 'RoIAlign3D', 'roi_align_3d', 'SingleRoIExtractor', 'RPNProposal3D',
            'AnchorGenerator3D', 'delta2bbox3D', 'bbox2roi3D', 'multiclass_nms_3d', 'build_roi_extractor',
-           'build_rpn_proposal']
+           'build_rpn_proposal', 'apply_nms', 'nms_3d_eval_batched']

@@ -515,6 +515,27 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
         hot_only()
     torch.cuda.synchronize()
     ex["c5_hot_path_only_us"] = (time.perf_counter() - t0) / 3 * 1e6
+    # N1: evaluation-time NMS, coco_utils.apply_nms: 64 volumes x 300 json detections, iou 0.1 -- host
+    # lists in, host lists out (upload, one batched float64-IoU device NMS, read-back), beside the numpy reference
+    import oracle  # CPU baseline leg of this row (the numpy reference restated), never on the measured path
+    from roi3d_b200.core.evaluation import nms_3d_eval_batched
+    vols = []
+    for v in range(64):
+        b = synth.c1_boxes(300, seed=100 + v)
+        vols.append(b)
+    nms_3d_eval_batched(vols, 0.1, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        kept = nms_3d_eval_batched(vols, 0.1, device=dev)
+    dt = (time.perf_counter() - t0) / 5
+    ex["n1_eval_nms_64vol_x300_us"] = dt * 1e6
+    ex["n1_eval_nms_boxes_per_sec"] = 64 * 300 / dt
+    ex["n1_eval_nms_kept"] = int(sum(len(k) for k in kept))
+    t0 = time.perf_counter()
+    ref_kept = [oracle.nms_3d_python(b.astype(np.float64), 0.1) for b in vols]
+    ex["n1_eval_nms_numpy_reference_us"] = (time.perf_counter() - t0) * 1e6
+    ex["n1_eval_nms_identical_to_numpy"] = bool(all(np.array_equal(a, b) for a, b in zip(kept, ref_kept)))
     return ex
 
 

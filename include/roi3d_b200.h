@@ -143,6 +143,15 @@ int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, in
                         float iou_thr, int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev,
                         void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Evaluation-time flavour of the same NMS.
+ * Replaces: nms_3d_python, mmdet/core/evaluation/coco_utils.py:245-282 (numpy float64, per volume, called from
+ *   apply_nms :306-332 with thr 0.1): IoU evaluated in float64 in numpy's operation order on the fp32 boxes,
+ *   a box is dropped unless iou <= iou_thr (so a NaN iou drops it).  keep_by_score_dev is the reference's return
+ *   order (descending score; equal scores: lower index first); keep_dev (ascending index) must be non-NULL too. */
+int roi3d_nms3d_eval_batched(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, double iou_thr,
+                             int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev,
+                             void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* Host-buffer form of one NMS call: what mmdet.ops.nms(dets_numpy, thr, device_id) does
  * (mmdet/ops/nms/nms_wrapper.py:29-32,42-52).  keep_host capacity n; returns count in *num_keep_host. */
 int roi3d_nms3d_host(const float *dets_host, int n, float iou_thr, int64_t *keep_host, int32_t *num_keep_host);

@@ -334,6 +334,23 @@ def nms_3d_python(boxes, iou_thr):
     return np.asarray(keep, dtype=np.int64)
 
 
+def apply_nms(full_filename_to_id, json_results, nms_thresh=0.1, score_thresh=0):
+    """apply_nms, mmdet/core/evaluation/coco_utils.py:306-332 (without the precomputed-proposal filter): per volume,
+    scan all json results for the volume's image id, nms_3d_python on their 'original_bbox' rows (float64), keep the
+    survivors in score order, drop those below score_thresh."""
+    out = []
+    for _filename, img_id in full_filename_to_id.items():
+        cur = [r for r in json_results if r['image_id'] == img_id]
+        if not cur:
+            continue
+        boxes = np.array([r['original_bbox'] for r in cur])
+        for i in nms_3d_python(boxes, nms_thresh):
+            if cur[i]['score'] < score_thresh:
+                continue
+            out.append(cur[i])
+    return out
+
+
 def nms_cpu_2d(dets, thr):
     """nms_cpu_kernel (mmdet/ops/nms/src/nms_cpu.cpp:5-59): 2-D NMS over columns 0-3 ranked by column 4,
     suppressing ovr >= thr -- what the reference's CPU wrapper runs even on 7-column input."""

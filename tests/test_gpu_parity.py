@@ -579,3 +579,69 @@ def test_roi_align_forward_row_map(dev, out_size):
         out.data_ptr(), perm.data_ptr(), stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(out[perm.long()], plain)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# evaluation-time NMS (coco_utils.py:245-332) on the device, float64 IoU in numpy's operation order
+# ---------------------------------------------------------------------------------------------------------------
+def _eval_volumes(nvol, seed):
+    rng = np.random.RandomState(seed)
+    vols = []
+    for v in range(nvol):
+        n = int(rng.randint(0, 400)) if v else 300
+        b = synth.c1_boxes(max(n, 1), seed=seed + v)[:n]
+        if n:
+            b[:, 6] = rng.permutation(np.linspace(0.05, 0.99, n)).astype(np.float32)
+        vols.append(b)
+    return vols
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("thr", [0.1, 0.3, 0.0])
+def test_eval_nms_matches_numpy_reference(oracle, dev, thr):
+    from roi3d_b200.core.evaluation import nms_3d_eval_batched
+    vols = _eval_volumes(9, 40)
+    # boxes whose IoU sits exactly on / next to the threshold in float64: identical boxes shifted by whole voxels
+    edge = np.array([[0, 0, 9, 9, 0, 9, 0.9], [0, 0, 9, 9, 0, 9, 0.8], [9, 0, 18, 9, 0, 9, 0.7],
+                     [0, 0, 9, 9, 8, 17, 0.6], [100, 100, 100, 100, 50, 50, 0.5], [100, 100, 100, 100, 50, 50, 0.5]],
+                    np.float32)
+    vols.append(edge)
+    got = nms_3d_eval_batched(vols, thr, device=dev)
+    assert len(got) == len(vols)
+    for b, g in zip(vols, got):
+        want = oracle.nms_3d_python(b.astype(np.float64), thr)
+        assert np.array_equal(g, want)
+
+
+@pytest.mark.gpu
+def test_eval_nms_nan_box_is_dropped_like_numpy(oracle, dev):
+    from roi3d_b200.core.evaluation import nms_3d_eval_batched
+    b = synth.c1_boxes(64, seed=3)
+    b[:, 6] = np.linspace(0.99, 0.1, 64, dtype=np.float32)
+    b[10, 2] = np.nan
+    with np.errstate(invalid="ignore"):
+        want = oracle.nms_3d_python(b.astype(np.float64), 0.1)
+    got = nms_3d_eval_batched([b], 0.1, device=dev)[0]
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_apply_nms_matches_reference_restatement(oracle, dev):
+    """apply_nms over json-style results of several volumes (interleaved, one volume without detections)."""
+    from roi3d_b200.core.evaluation import apply_nms, nms_3d_python
+    vols = _eval_volumes(5, 60)
+    name_to_id = {"vol%d.npy" % v: 100 + v for v in range(len(vols) + 1)}  # one extra volume with no results
+    results = []
+    for v, b in enumerate(vols):
+        for i, row in enumerate(b):
+            results.append(dict(image_id=100 + v, original_bbox=[float(x) for x in row], score=float(row[6]),
+                                category_id=1, tag=(v, i)))
+    rng = np.random.RandomState(1)
+    results = [results[i] for i in rng.permutation(len(results))]
+    want = oracle.apply_nms(name_to_id, results, 0.1, 0.3)
+    with torch.cuda.device(dev):
+        got = apply_nms(name_to_id, results, 0.1, 0.3)
+        one = nms_3d_python(results[:50], [r['original_bbox'] for r in results[:50]], 0.1)
+    assert [r['tag'] for r in got] == [r['tag'] for r in want] and len(got) > 0
+    keep = oracle.nms_3d_python(np.array([r['original_bbox'] for r in results[:50]]), 0.1)
+    assert [r['tag'] for r in one] == [results[i]['tag'] for i in keep]

@@ -178,3 +178,18 @@ def test_multiclass_nms(oracle):
     assert np.all(bb[:, 6] > 0.2)
     bb, lab = oracle.multiclass_nms_3d(d[:, :6], scores, 2.0, 0.5, max_num=50)
     assert bb.shape == (0, 7) and lab.shape == (0,)
+
+
+def test_apply_nms_restatement_groups_by_volume_and_keeps_score_order(oracle):
+    """oracle.apply_nms (coco_utils.py:306-332): per volume in dict order, survivors in descending score, score
+    threshold applied after NMS; results of other volumes never interact."""
+    box = [0, 0, 9, 9, 0, 9]
+    res = [dict(image_id=2, original_bbox=box + [0.6], score=0.6, tag="b-low"),
+           dict(image_id=1, original_bbox=box + [0.9], score=0.9, tag="a-high"),
+           dict(image_id=2, original_bbox=box + [0.8], score=0.8, tag="b-high"),
+           dict(image_id=1, original_bbox=[50, 50, 59, 59, 20, 29, 0.2], score=0.2, tag="a-far-weak"),
+           dict(image_id=1, original_bbox=[1, 0, 10, 9, 0, 9, 0.7], score=0.7, tag="a-overlap")]
+    out = oracle.apply_nms({"a": 1, "b": 2, "c": 3}, res, 0.1, 0.3)
+    assert [r["tag"] for r in out] == ["a-high", "b-high"]
+    out = oracle.apply_nms({"b": 2, "a": 1}, res, 1.0, 0.0)  # iou <= 1 keeps everything: pure ordering
+    assert [r["tag"] for r in out] == ["b-high", "b-low", "a-high", "a-overlap", "a-far-weak"]
