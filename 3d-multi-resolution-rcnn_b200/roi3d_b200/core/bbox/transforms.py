@@ -1,6 +1,11 @@
 """3D box helpers of the proposal path (reference: mmdet/core/bbox/transforms.py)."""
+import ctypes
+
 import numpy as np
 import torch
+
+from ... import _lib
+from ..._util import check_cuda_f32, stream_ptr
 
 
 def bbox2roi3D(bbox_list):
@@ -45,3 +50,24 @@ def delta2bbox3D(rois, deltas, means=(0, 0, 0, 0, 0, 0), stds=(1, 1, 1, 1, 1, 1)
         y1, y2 = y1.clamp(0, max_shape[0] - 1), y2.clamp(0, max_shape[0] - 1)
         z1, z2 = z1.clamp(0, max_shape[3] - 1), z2.clamp(0, max_shape[3] - 1)
     return torch.stack([x1, y1, x2, y2, z1, z2], dim=-1).view_as(deltas)
+
+
+def bbox2delta3d(proposals, gt, means=(0, 0, 0, 0, 0, 0), stds=(1, 1, 1, 1, 1, 1)):
+    """Regression targets (dx, dy, dw, dh, dz, dd) of `gt` w.r.t. `proposals`, one kernel.
+    Reference: bbox2delta3d, transforms.py:33-63 (about 30 elementwise launches)."""
+    assert proposals.size() == gt.size()
+    p, g = proposals.float().contiguous(), gt.float().contiguous()
+    check_cuda_f32(p, "proposals", ndim=2)
+    check_cuda_f32(g, "gt", ndim=2)
+    if p.shape[1] < 6:
+        raise NotImplementedError("bbox2delta3d: boxes need 6 columns")
+    n = p.shape[0]
+    out = p.new_empty((n, 6))
+    m6 = (ctypes.c_float * 6)(*[float(x) for x in means])
+    s6 = (ctypes.c_float * 6)(*[float(x) for x in stds])
+    if n:
+        with torch.cuda.device(p.device):
+            _lib.check(_lib.lib.roi3d_bbox2delta3d(p.data_ptr(), p.shape[1], g.data_ptr(), g.shape[1], n,
+                                                   ctypes.addressof(m6), ctypes.addressof(s6), out.data_ptr(),
+                                                   stream_ptr()))
+    return out

@@ -536,6 +536,52 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ref_kept = [oracle.nms_3d_python(b.astype(np.float64), 0.1) for b in vols]
     ex["n1_eval_nms_numpy_reference_us"] = (time.perf_counter() - t0) * 1e6
     ex["n1_eval_nms_identical_to_numpy"] = bool(all(np.array_equal(a, b) for a, b in zip(kept, ref_kept)))
+    # N2: MaxIoU assigner as the RPN uses it in training: all anchors of one 512x512x160 volume
+    # (1 497 920, five levels) against 16 gts; pos 0.7 / neg 0.3 / min_pos 0.3.  Device-resident, CUDA events.
+    from roi3d_b200.core.bbox import MaxIoUAssigner, bbox2delta3d
+    from roi3d_b200 import AnchorGenerator3D
+    anchors = []
+    for (d_, h_, w_), st_, sd_ in zip(dims4, [4, 8, 16, 32, 64], [2, 4, 8, 16, 32]):
+        gen_a = AnchorGenerator3D(st_, [2], [2], [1.0], sd_)
+        anchors.append(gen_a.grid_anchors((d_, h_, w_), st_, sd_, device=dev))
+    anchors = torch.cat(anchors, 0).contiguous()
+    gsel = torch.randint(0, anchors.shape[0], (16,), generator=torch.Generator().manual_seed(9)).to(dev)
+    gts = (anchors[gsel] + torch.from_numpy(np.random.default_rng(9).uniform(-2, 2, (16, 6)).astype(np.float32)).to(dev))
+    gts = gts.contiguous()  # gts are jittered anchors so that all four rules fire
+    assigner = MaxIoUAssigner(0.7, 0.3, 0.3, True)
+    res = assigner.assign(anchors, gts)
+    us = med_us(lambda: assigner.assign(anchors, gts), iters=10, do_flush=False)
+    ex["n2_assign_anchors"] = int(anchors.shape[0])
+    ex["n2_assign_1p5M_anchors_x16gt_us"] = us
+    ex["n2_assign_pairs_per_sec"] = anchors.shape[0] * 16 / (us * 1e-6)
+    ex["n2_assign_pos_neg"] = [int((res.gt_inds > 0).sum()), int((res.gt_inds == 0).sum())]
+
+    def torch_way():  # the reference's formulation (dense matrix, two reductions, gt loop) with today's torch ops
+        b1, b2 = gts, anchors
+        xa, ya = torch.max(b1[:, None, 0], b2[:, 0]), torch.max(b1[:, None, 1], b2[:, 1])
+        xb, yb = torch.min(b1[:, None, 2], b2[:, 2]), torch.min(b1[:, None, 3], b2[:, 3])
+        za, zb = torch.max(b1[:, None, 4], b2[:, 4]), torch.min(b1[:, None, 5], b2[:, 5])
+        inter = (xb - xa + 1).clamp(min=0) * (yb - ya + 1).clamp(min=0) * (zb - za + 1).clamp(min=0)
+        a1 = (b1[:, 2] - b1[:, 0] + 1) * (b1[:, 3] - b1[:, 1] + 1) * (b1[:, 5] - b1[:, 4] + 1)
+        a2 = (b2[:, 2] - b2[:, 0] + 1) * (b2[:, 3] - b2[:, 1] + 1) * (b2[:, 5] - b2[:, 4] + 1)
+        ov = inter / (a1[:, None] + a2 - inter)
+        out = ov.new_full((ov.size(1),), -1, dtype=torch.long)
+        mo, am = ov.max(dim=0)
+        gm, _ = ov.max(dim=1)
+        out[(mo >= 0) & (mo < 0.3)] = 0
+        pos = mo >= 0.7
+        out[pos] = am[pos] + 1
+        for i in range(ov.size(0)):
+            if gm[i] >= 0.3:
+                out[ov[i, :] == gm[i]] = i + 1
+        return out
+    ref_out = torch_way()
+    ex["n2_assign_torch_formulation_us"] = med_us(torch_way, iters=3, warm=1, do_flush=False)
+    ex["n2_assign_identical_to_torch_formulation"] = bool(torch.equal(ref_out, res.gt_inds))
+    pos_idx = torch.nonzero(res.gt_inds > 0).squeeze(1)
+    if pos_idx.numel():
+        pa, pg = anchors[pos_idx].contiguous(), gts[res.gt_inds[pos_idx] - 1].contiguous()
+        ex["n2_bbox2delta3d_us"] = med_us(lambda: bbox2delta3d(pa, pg), iters=10, do_flush=False)
     return ex
 
 

@@ -156,6 +156,33 @@ int roi3d_nms3d_eval_batched(const float *dets_dev, const int32_t *seg_counts_de
  * (mmdet/ops/nms/nms_wrapper.py:29-32,42-52).  keep_host capacity n; returns count in *num_keep_host. */
 int roi3d_nms3d_host(const float *dets_host, int n, float iou_thr, int64_t *keep_host, int32_t *num_keep_host);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training-time glue between the proposal path and RoIAlign.
+ *
+ * roi3d_bbox_overlaps3d: dense IoU matrix iou[m, n] of boxes1[m] x boxes2[n] (rows of `stride` floats, the first six
+ *   are x1,y1,x2,y2,z1,z2).  Replaces: bbox_overlaps, 6-column non-aligned branch, mmdet/core/bbox/geometry.py:49-60.
+ * roi3d_assign_max_iou: MaxIoUAssigner.assign -> assign_wrt_overlaps, mmdet/core/bbox/assigners/
+ *   max_iou_assigner.py:100,128-171, fused over the IoU (the [k, n] matrix is never stored).  Rules in order:
+ *   -1 by default; 0 where neg_iou_lo <= max_overlap < neg_iou_hi (a float neg_iou_thr t is the pair (0, t));
+ *   argmax + 1 where max_overlap >= pos_iou_thr; then for every gt i in ascending order with
+ *   gt_max[i] >= min_pos_iou: i + 1 for every box whose IoU equals gt_max[i] (gt_max_assign_all) or for the
+ *   lowest-index such box.  Ties of the per-box argmax go to the lowest gt index.  assigned_labels_dev (optional)
+ *   = gt_labels[assigned - 1] for positives, 0 otherwise.  n == 0 or k == 0 is an error like the reference's
+ *   ValueError.  The ignore-region branch (ignore_iof_thr > 0) is not implemented (unused by the config).
+ * roi3d_bbox2delta3d: bbox2delta3d, mmdet/core/bbox/transforms.py:33-63; deltas [n, 6] = (dx, dy, dw, dh, dz, dd);
+ *   means6 / stds6 are HOST pointers to six floats (NULL = 0 / 1).
+ * ---------------------------------------------------------------------------------------------- */
+int roi3d_bbox_overlaps3d(const float *boxes1_dev, int m, int stride1, const float *boxes2_dev, int n, int stride2,
+                          float *iou_dev, void *stream);
+size_t roi3d_assign_workspace_bytes(int n, int k);
+int roi3d_assign_max_iou(const float *bboxes_dev, int n, int stride, const float *gt_dev, int k,
+                         const int64_t *gt_labels_dev, float pos_iou_thr, float neg_iou_lo, float neg_iou_hi,
+                         float min_pos_iou, int gt_max_assign_all, int64_t *assigned_gt_inds_dev,
+                         float *max_overlaps_dev, int64_t *assigned_labels_dev, void *workspace_dev,
+                         size_t workspace_bytes, void *stream);
+int roi3d_bbox2delta3d(const float *proposals_dev, int stride_p, const float *gt_dev, int stride_g, int n,
+                       const float *means6, const float *stds6, float *deltas_dev, void *stream);
+
 /* Experiment knob (not part of the reference surface): key 0 = forward kernel variant, 1 = backward
  * kernel variant; value 0 = auto, 1/2 = alternative register tilings, 99 = literal (reference-order) path.
  * key 2 = sub-items one forward warp walks per RoI (0 = auto); key 4 = volume size in KB from which

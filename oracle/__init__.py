@@ -351,6 +351,72 @@ def apply_nms(full_filename_to_id, json_results, nms_thresh=0.1, score_thresh=0)
     return out
 
 
+def bbox_overlaps3d(b1, b2):
+    """bbox_overlaps, 6-column non-aligned branch (mmdet/core/bbox/geometry.py:49-60): fp32, one rounding per
+    elementwise op like torch's separate kernels.  b1 [m,>=6], b2 [n,>=6] -> [m,n]."""
+    b1, b2 = _f32(b1), _f32(b2)
+    one = np.float32(1)
+    xa = np.maximum(b1[:, None, 0], b2[None, :, 0])
+    ya = np.maximum(b1[:, None, 1], b2[None, :, 1])
+    xb = np.minimum(b1[:, None, 2], b2[None, :, 2])
+    yb = np.minimum(b1[:, None, 3], b2[None, :, 3])
+    za = np.maximum(b1[:, None, 4], b2[None, :, 4])
+    zb = np.minimum(b1[:, None, 5], b2[None, :, 5])
+    zero = np.float32(0)
+    inter = np.maximum(xb - xa + one, zero) * np.maximum(yb - ya + one, zero) * np.maximum(zb - za + one, zero)
+    a1 = (b1[:, 2] - b1[:, 0] + one) * (b1[:, 3] - b1[:, 1] + one) * (b1[:, 5] - b1[:, 4] + one)
+    a2 = (b2[:, 2] - b2[:, 0] + one) * (b2[:, 3] - b2[:, 1] + one) * (b2[:, 5] - b2[:, 4] + one)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (inter / (a1[:, None] + a2[None, :] - inter)).astype(np.float32)
+
+
+def assign_max_iou(bboxes, gt_bboxes, gt_labels=None, pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.0,
+                   gt_max_assign_all=True):
+    """MaxIoUAssigner.assign + assign_wrt_overlaps (mmdet/core/bbox/assigners/max_iou_assigner.py:100,128-171)
+    without the ignore branch.  Ties of max(dim) go to the lowest index (parity unpinned by the reference).
+    Returns (assigned_gt_inds int64 [n], max_overlaps fp32 [n], labels int64 [n] or None)."""
+    ov = bbox_overlaps3d(_f32(gt_bboxes)[:, :6], _f32(bboxes)[:, :6])  # [k, n]
+    k, n = ov.shape
+    assigned = np.full(n, -1, dtype=np.int64)
+    max_ov, argmax_ov = ov.max(axis=0), ov.argmax(axis=0)
+    gt_max, gt_argmax = ov.max(axis=1), ov.argmax(axis=1)
+    if isinstance(neg_iou_thr, float):
+        assigned[(max_ov >= 0) & (max_ov < np.float32(neg_iou_thr))] = 0
+    elif isinstance(neg_iou_thr, tuple):
+        assigned[(max_ov >= np.float32(neg_iou_thr[0])) & (max_ov < np.float32(neg_iou_thr[1]))] = 0
+    pos = max_ov >= np.float32(pos_iou_thr)
+    assigned[pos] = argmax_ov[pos] + 1
+    for i in range(k):
+        if gt_max[i] >= np.float32(min_pos_iou):
+            if gt_max_assign_all:
+                assigned[ov[i, :] == gt_max[i]] = i + 1
+            else:
+                assigned[gt_argmax[i]] = i + 1
+    labels = None
+    if gt_labels is not None:
+        gl = np.asarray(gt_labels, dtype=np.int64)
+        labels = np.zeros(n, dtype=np.int64)
+        p = assigned > 0
+        labels[p] = gl[assigned[p] - 1]
+    return assigned, max_ov.astype(np.float32), labels
+
+
+def bbox2delta3d(proposals, gt, means=(0, 0, 0, 0, 0, 0), stds=(1, 1, 1, 1, 1, 1)):
+    """bbox2delta3d (mmdet/core/bbox/transforms.py:33-63), fp32 numpy: (dx, dy, dw, dh, dz, dd)."""
+    p, g = _f32(proposals), _f32(gt)
+    half, one = np.float32(0.5), np.float32(1)
+    cols = []
+    enc = {}
+    for name, lo, hi in (("x", 0, 2), ("y", 1, 3), ("z", 4, 5)):
+        pc, ps = (p[:, lo] + p[:, hi]) * half, p[:, hi] - p[:, lo] + one
+        gc, gs = (g[:, lo] + g[:, hi]) * half, g[:, hi] - g[:, lo] + one
+        with np.errstate(invalid="ignore", divide="ignore"):
+            enc[name] = ((gc - pc) / ps, np.log(gs / ps))
+    cols = [enc["x"][0], enc["y"][0], enc["x"][1], enc["y"][1], enc["z"][0], enc["z"][1]]
+    d = np.stack(cols, axis=-1).astype(np.float32)
+    return ((d - _f32(np.asarray(means))[None]) / _f32(np.asarray(stds))[None]).astype(np.float32)
+
+
 def nms_cpu_2d(dets, thr):
     """nms_cpu_kernel (mmdet/ops/nms/src/nms_cpu.cpp:5-59): 2-D NMS over columns 0-3 ranked by column 4,
     suppressing ovr >= thr -- what the reference's CPU wrapper runs even on 7-column input."""

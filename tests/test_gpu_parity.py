@@ -645,3 +645,97 @@ def test_apply_nms_matches_reference_restatement(oracle, dev):
     assert [r['tag'] for r in got] == [r['tag'] for r in want] and len(got) > 0
     keep = oracle.nms_3d_python(np.array([r['original_bbox'] for r in results[:50]]), 0.1)
     assert [r['tag'] for r in one] == [results[i]['tag'] for i in keep]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dense 3D IoU, MaxIoU assigner, bbox2delta3d
+# ---------------------------------------------------------------------------------------------------------------
+def _assign_case(n, k, seed, dup=True):
+    rng = np.random.default_rng(seed)
+    gt = synth.c1_boxes(max(k, 8), seed=seed)[:k, :6].copy()
+    boxes = synth.c1_boxes(n, seed=seed + 1)[:, :7].copy()
+    # make a good share of the boxes overlap some gt, some of them exactly
+    take = rng.integers(0, k, n // 3)
+    boxes[: n // 3, :6] = gt[take] + rng.integers(-4, 5, (n // 3, 6)).astype(np.float32)
+    if dup:
+        boxes[5, :6] = gt[0]
+        boxes[6, :6] = gt[0]          # two boxes tie for gt 0's maximum
+        if k > 2:
+            gt[2] = gt[1]             # two gts tie for the same boxes' argmax
+    return boxes, gt
+
+
+@pytest.mark.gpu
+def test_bbox_overlaps3d_matches_oracle_and_torch(oracle, dev):
+    from roi3d_b200.core.bbox import bbox_overlaps
+    boxes, gt = _assign_case(1500, 37, 3)
+    want = oracle.bbox_overlaps3d(gt, boxes[:, :6])
+    g, b = torch.from_numpy(gt).to(dev), torch.from_numpy(boxes).to(dev)
+    got = bbox_overlaps(g, b)          # boxes carry a 7th (score) column: stride 7
+    assert got.shape == (37, 1500)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # the reference's expression evaluated by today's torch CUDA elementwise kernels
+    b1, b2 = g, b[:, :6]
+    xa, ya = torch.max(b1[:, None, 0], b2[:, 0]), torch.max(b1[:, None, 1], b2[:, 1])
+    xb, yb = torch.min(b1[:, None, 2], b2[:, 2]), torch.min(b1[:, None, 3], b2[:, 3])
+    za, zb = torch.max(b1[:, None, 4], b2[:, 4]), torch.min(b1[:, None, 5], b2[:, 5])
+    inter = (xb - xa + 1).clamp(min=0) * (yb - ya + 1).clamp(min=0) * (zb - za + 1).clamp(min=0)
+    a1 = (b1[:, 2] - b1[:, 0] + 1) * (b1[:, 3] - b1[:, 1] + 1) * (b1[:, 5] - b1[:, 4] + 1)
+    a2 = (b2[:, 2] - b2[:, 0] + 1) * (b2[:, 3] - b2[:, 1] + 1) * (b2[:, 5] - b2[:, 4] + 1)
+    assert torch.equal(got, inter / (a1[:, None] + a2 - inter))
+    assert bbox_overlaps(g[:0], b).shape == (0, 1500)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [
+    dict(pos_iou_thr=0.7, neg_iou_thr=0.3, min_pos_iou=0.3, gt_max_assign_all=True),     # rpn assigner of the config
+    dict(pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.5, gt_max_assign_all=True),     # rcnn assigner
+    dict(pos_iou_thr=0.6, neg_iou_thr=(0.1, 0.4), min_pos_iou=0.2, gt_max_assign_all=False),
+])
+@pytest.mark.parametrize("shape", [(3000, 12), (257, 1), (70000, 700)])
+def test_max_iou_assigner_matches_oracle(oracle, dev, cfg, shape):
+    from roi3d_b200.core.bbox import MaxIoUAssigner
+    n, k = shape
+    boxes, gt = _assign_case(n, k, 11 + k)
+    labels = (np.arange(k) % 3 + 1).astype(np.int64)
+    want_a, want_mo, want_l = oracle.assign_max_iou(boxes, gt, labels, **cfg)
+    res = MaxIoUAssigner(**cfg).assign(torch.from_numpy(boxes).to(dev), torch.from_numpy(gt).to(dev),
+                                       gt_labels=torch.from_numpy(labels).to(dev))
+    assert res.num_gts == k and res.gt_inds.dtype == torch.int64 and res.labels.dtype == torch.int64
+    assert np.array_equal(res.max_overlaps.cpu().numpy(), want_mo)
+    assert np.array_equal(res.gt_inds.cpu().numpy(), want_a)
+    assert np.array_equal(res.labels.cpu().numpy(), want_l)
+    assert (want_a > 0).sum() > 0 and (want_a == 0).sum() > 0
+    res2 = MaxIoUAssigner(**cfg).assign(torch.from_numpy(boxes).to(dev), [torch.from_numpy(gt).to(dev)])
+    assert res2.labels is None and torch.equal(res2.gt_inds, res.gt_inds)
+
+
+@pytest.mark.gpu
+def test_max_iou_assigner_errors_like_reference(dev):
+    from roi3d_b200.core.bbox import MaxIoUAssigner
+    a = MaxIoUAssigner(0.5, 0.5)
+    with pytest.raises(ValueError):
+        a.assign(torch.zeros(0, 6, device=dev), torch.zeros(2, 6, device=dev))
+    with pytest.raises(ValueError):
+        a.assign(torch.zeros(4, 6, device=dev), torch.zeros(0, 6, device=dev))
+    with pytest.raises(NotImplementedError):
+        a.assign(torch.zeros(4, 6), torch.zeros(1, 6))
+
+
+@pytest.mark.gpu
+def test_bbox2delta3d_matches_oracle(oracle, dev):
+    from roi3d_b200.core.bbox import bbox2delta3d, delta2bbox3D
+    rng = np.random.default_rng(0)
+    lo, sz = rng.uniform(0, 400, (4000, 3)).astype(np.float32), rng.uniform(4, 60, (4000, 3)).astype(np.float32)
+    p = np.stack([lo[:, 0], lo[:, 1], lo[:, 0] + sz[:, 0], lo[:, 1] + sz[:, 1], lo[:, 2], lo[:, 2] + sz[:, 2]], 1)
+    g = p + rng.uniform(-1.5, 1.5, p.shape).astype(np.float32)
+    means, stds = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0), (0.1, 0.1, 0.2, 0.2, 0.1, 0.2)
+    want = oracle.bbox2delta3d(p, g, means, stds)
+    got = bbox2delta3d(torch.from_numpy(p).to(dev), torch.from_numpy(g).to(dev), means, stds)
+    gn = got.cpu().numpy()
+    # dx, dy, dz are pure IEEE arithmetic: exact; dw, dh, dd go through logf (device libm vs numpy's)
+    assert np.array_equal(gn[:, [0, 1, 4]], want[:, [0, 1, 4]])
+    assert np.isfinite(want).all()
+    assert np.allclose(gn[:, [2, 3, 5]], want[:, [2, 3, 5]], rtol=1e-5, atol=1e-6)  # tolerance: 1e-5 relative
+    back = delta2bbox3D(torch.from_numpy(p).to(dev), got, means, stds)
+    assert (back - torch.from_numpy(g).to(dev)).abs().max() < 1e-2

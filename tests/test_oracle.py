@@ -193,3 +193,47 @@ def test_apply_nms_restatement_groups_by_volume_and_keeps_score_order(oracle):
     assert [r["tag"] for r in out] == ["a-high", "b-high"]
     out = oracle.apply_nms({"b": 2, "a": 1}, res, 1.0, 0.0)  # iou <= 1 keeps everything: pure ordering
     assert [r["tag"] for r in out] == ["b-high", "b-low", "a-high", "a-overlap", "a-far-weak"]
+
+
+def test_bbox_overlaps3d_known_answers_of_the_reference(oracle):
+    """bbox_overlaps_test, mmdet/core/bbox/geometry.py:81-102: the reference's own known answers (rounded to 4 dp)
+    and the 2 x 3 shape case."""
+    cases = [([39, 63, 203, 112, 4, 5], [54, 66, 198, 114, 4, 5], 0.798),
+             ([49, 75, 203, 125, 4, 5], [42, 78, 186, 126, 4, 5], 0.7899),
+             ([31, 69, 201, 125, 4, 5], [18, 63, 235, 135, 4, 5], 0.6125),
+             ([2, 3, 4, 6, 3, 4], [2, 3, 4, 6, 3, 4], 1.0)]
+    for a, b, want in cases:
+        v = oracle.bbox_overlaps3d(np.array([a], np.float32), np.array([b], np.float32))
+        assert v.shape == (1, 1) and round(float(v[0, 0]), 4) == want
+    r = oracle.bbox_overlaps3d(np.array([[2, 3, 4, 6, 3, 4], [39, 63, 203, 112, 4, 5]], np.float32),
+                               np.array([[2, 3, 4, 6, 3, 4], [54, 66, 198, 114, 4, 5], [49, 75, 203, 125, 4, 5]],
+                                        np.float32))
+    assert r.shape == (2, 3) and int(r[0, 0]) == 1
+
+
+def test_assign_max_iou_rules_in_order(oracle):
+    """max_iou_assigner.py:128-171: -1 default, negatives, positives, then every gt claims its best boxes (later gts
+    override earlier ones), labels follow."""
+    gt = np.array([[0, 0, 9, 9, 0, 9], [0, 0, 9, 9, 0, 9], [50, 50, 59, 59, 20, 29]], np.float32)  # gt 0 == gt 1
+    boxes = np.array([[0, 0, 9, 9, 0, 9],          # IoU 1 with gts 0 and 1: argmax -> gt 0, rule 4 -> gt 1 (later wins)
+                      [2, 0, 11, 9, 0, 9],         # 0.667 with gts 0/1: between neg 0.3 and pos 0.7 -> stays -1
+                      [200, 200, 209, 209, 40, 49],  # no overlap -> negative
+                      [54, 50, 63, 59, 20, 29],    # 0.43 with gt 2 only, but it is gt 2's best box -> positive via rule 4
+                      [8, 0, 17, 9, 0, 9]], np.float32)  # 0.11 -> negative
+    a, mo, lab = oracle.assign_max_iou(boxes, gt, [5, 6, 7], 0.7, 0.3, 0.3, True)
+    assert a.tolist() == [2, -1, 0, 3, 0] and lab.tolist() == [6, 0, 0, 7, 0]
+    assert mo[0] == 1.0 and mo[2] == 0.0
+    a2, _, _ = oracle.assign_max_iou(boxes, gt, None, 0.7, (0.05, 0.3), 0.5, False)  # tuple band; min_pos_iou blocks gt 2
+    assert a2.tolist() == [2, -1, -1, -1, 0]
+
+
+def test_bbox2delta3d_inverts_delta2bbox3d(oracle):
+    rng = np.random.default_rng(0)
+    lo = rng.uniform(0, 100, (50, 3)).astype(np.float32)
+    sz = rng.uniform(4, 60, (50, 3)).astype(np.float32)
+    p = np.stack([lo[:, 0], lo[:, 1], lo[:, 0] + sz[:, 0], lo[:, 1] + sz[:, 1], lo[:, 2], lo[:, 2] + sz[:, 2]], 1)
+    g = p + rng.uniform(-3, 3, p.shape).astype(np.float32)
+    means, stds = (0.0,) * 6, (0.1, 0.1, 0.2, 0.2, 0.1, 0.2)
+    d = oracle.bbox2delta3d(p, g, means, stds)
+    back = oracle.delta2bbox3d(p, d, means, stds, None)
+    assert np.abs(back - g).max() < 1e-3
