@@ -231,6 +231,51 @@ __global__ void __launch_bounds__(256) bbox2delta3d_kernel(const float *__restri
   for (int q = 0; q < 6; ++q) out[(long long)i * 6 + q] = __fdiv_rn(__fsub_rn(d[q], means.v[q]), stds.v[q]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Anchors of one level in closed form + valid / inside flags.  Flat index = ((y*W + x)*D + z)*A + a
+// (np.meshgrid(x, y, z) 'xy' order, anchor_generator_3d.py:59-70); anchor = base[a] + (x*s, y*s, x*s, y*s, z*sd, z*sd).
+// flag = cell inside the valid extent (valid_flags, :73-92) AND, if allowed_border >= 0, the anchor inside the image
+// grown by the border (anchor_inside_flags, anchor_target.py:203-217).
+// ------------------------------------------------------------------------------------------------
+struct AnchorParams {
+  int A, D, H, W;
+  float stride, dstride;
+  float base[16][6];
+  int valid_d, valid_h, valid_w;
+  float img_h, img_w, img_d, border;
+  int use_border;
+  float *anchors;
+  unsigned char *flags;
+};
+
+__global__ void __launch_bounds__(256) grid_anchors_kernel(const AnchorParams p) {
+  const long long total = (long long)p.A * p.D * p.H * p.W;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  long long t = i;
+  const int a = (int)(t % p.A);
+  t /= p.A;
+  const int z = (int)(t % p.D);
+  t /= p.D;
+  const int x = (int)(t % p.W);
+  const int y = (int)(t / p.W);
+  const float sx = (float)x * p.stride, sy = (float)y * p.stride, sz = (float)z * p.dstride;
+  float v[6];
+  v[0] = __fadd_rn(p.base[a][0], sx), v[1] = __fadd_rn(p.base[a][1], sy), v[2] = __fadd_rn(p.base[a][2], sx);
+  v[3] = __fadd_rn(p.base[a][3], sy), v[4] = __fadd_rn(p.base[a][4], sz), v[5] = __fadd_rn(p.base[a][5], sz);
+  if (p.anchors != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) p.anchors[i * 6 + q] = v[q];
+  }
+  if (p.flags != nullptr) {
+    bool f = x < p.valid_w && y < p.valid_h && z < p.valid_d;
+    if (p.use_border)
+      f = f && v[0] >= -p.border && v[1] >= -p.border && v[4] >= -p.border && v[2] < p.img_w + p.border &&
+          v[3] < p.img_h + p.border && v[5] < p.img_d + p.border;
+    p.flags[i] = f ? 1 : 0;
+  }
+}
+
 }  // namespace roi3d
 
 using namespace roi3d;
@@ -291,6 +336,27 @@ int roi3d_assign_max_iou(const float *bboxes_dev, int n, int stride, const float
     assign_labels_kernel<<<blocks, 256, 0, st>>>(assigned_gt_inds_dev, n, gt_labels_dev, assigned_labels_dev);
     ROI3D_LAUNCH_CHECK();
   }
+  return ROI3D_OK;
+}
+
+int roi3d_grid_anchors(int A, int D, int H, int W, float stride, float depth_stride, const float *base_anchors_host,
+                       int valid_d, int valid_h, int valid_w, float img_h, float img_w, float img_d, int allowed_border,
+                       float *anchors_dev, uint8_t *flags_dev, void *stream) {
+  ROI3D_CHECK_ARG(A >= 1 && A <= 16, "A=%d out of [1,16]", A);
+  ROI3D_CHECK_ARG(D > 0 && H > 0 && W > 0 && base_anchors_host, "bad arguments");
+  const long long total = (long long)A * D * H * W;
+  ROI3D_CHECK_ARG(ceil_div_ll(total, 256) < 2147483647LL, "too many anchors");
+  if (anchors_dev == nullptr && flags_dev == nullptr) return ROI3D_OK;
+  AnchorParams p;
+  p.A = A, p.D = D, p.H = H, p.W = W, p.stride = stride, p.dstride = depth_stride;
+  for (int a = 0; a < A; ++a)
+    for (int j = 0; j < 6; ++j) p.base[a][j] = base_anchors_host[a * 6 + j];
+  p.valid_d = valid_d, p.valid_h = valid_h, p.valid_w = valid_w;
+  p.img_h = img_h, p.img_w = img_w, p.img_d = img_d;
+  p.use_border = allowed_border >= 0, p.border = (float)allowed_border;
+  p.anchors = anchors_dev, p.flags = flags_dev;
+  grid_anchors_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
 }
 

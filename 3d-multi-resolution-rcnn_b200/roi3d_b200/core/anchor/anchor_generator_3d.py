@@ -2,11 +2,15 @@
 
 Base anchors are the same closed form (rounded corner offsets around the cell centre).  grid_anchors keeps the
 reference's enumeration order -- np.meshgrid(x, y, z) 'xy' indexing flattened, i.e. flat index
-((y*W + x)*D + z)*A + a -- but builds the grid on the device from aranges instead of numpy + a 31 MB H2D copy
-per call (anchor_head_3d.py:248-252).  The fused proposal path never materialises the grid at all: the decode
+((y*W + x)*D + z)*A + a -- but writes the grid on the device with one kernel (`roi3d_grid_anchors`, which can also emit
+the valid / inside flags of the training path) instead of numpy + a 31 MB H2D copy per call
+(anchor_head_3d.py:248-252).  The fused proposal path never materialises the grid at all: the decode
 kernel recomputes the anchor of each selected index (csrc/proposal.cu).
 """
 import torch
+
+from ... import _lib
+from ..._util import stream_ptr
 
 
 class AnchorGenerator3D(object):
@@ -42,13 +46,43 @@ class AnchorGenerator3D(object):
         corners = [cx - half[0], cy - half[1], cx + half[0], cy + half[1], cz - half[2], cz + half[2]]
         return torch.stack(corners, dim=-1).round()
 
+    def _launch(self, featmap_size, stride, depth_stride, device, valid_size, img_shape, allowed_border, want_anchors,
+                want_flags):
+        feat_z, feat_h, feat_w = (int(v) for v in featmap_size)
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise NotImplementedError("AnchorGenerator3D builds anchors on the GPU: the B200 path has no CPU "
+                                      "implementation")
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        A = self.num_base_anchors
+        n = feat_z * feat_h * feat_w * A
+        base = self.base_anchors.to(dtype=torch.float32, device='cpu').contiguous()
+        anchors = torch.empty((n, 6), dtype=torch.float32, device=device) if want_anchors else None
+        flags = torch.empty((n,), dtype=torch.uint8, device=device) if want_flags else None
+        vd, vh, vw = (int(v) for v in valid_size) if valid_size is not None else (feat_z, feat_h, feat_w)
+        assert vh <= feat_h and vw <= feat_w and vd <= feat_z
+        ih, iw, idp = (float(img_shape[0]), float(img_shape[1]), float(img_shape[3])) if img_shape is not None \
+            else (0.0, 0.0, 0.0)
+        if n:
+            with torch.cuda.device(device):
+                _lib.check(_lib.lib.roi3d_grid_anchors(
+                    A, feat_z, feat_h, feat_w, float(stride), float(depth_stride), base.data_ptr(), vd, vh, vw, ih, iw,
+                    idp, int(allowed_border), None if anchors is None else anchors.data_ptr(),
+                    None if flags is None else flags.data_ptr(), stream_ptr()))
+        return anchors, flags
+
     def grid_anchors(self, featmap_size, stride=16, depth_stride=2, device='cuda'):
-        """All anchors of one level, [D*H*W*A, 6], in the reference's order (y, x, z, a)."""
-        base = self.base_anchors.to(device)
-        feat_z, feat_h, feat_w = featmap_size
-        sx = torch.arange(0, feat_w, device=device, dtype=torch.float32) * stride
-        sy = torch.arange(0, feat_h, device=device, dtype=torch.float32) * stride
-        sz = torch.arange(0, feat_z, device=device, dtype=torch.float32) * depth_stride
-        yy, xx, zz = torch.meshgrid(sy, sx, sz, indexing='ij')
-        shifts = torch.stack([xx, yy, xx, yy, zz, zz], dim=-1).reshape(-1, 6)
-        return (base[None, :, :] + shifts[:, None, :]).view(-1, 6)
+        """All anchors of one level, [D*H*W*A, 6], in the reference's order (y, x, z, a); one kernel, no numpy grid,
+        no H2D copy (reference: anchor_generator_3d.py:56-71)."""
+        return self._launch(featmap_size, stride, depth_stride, device, None, None, -1, True, False)[0]
+
+    def valid_flags(self, featmap_size, valid_size, device='cuda'):
+        """uint8 [D*H*W*A]: 1 where the cell lies inside the valid (unpadded) extent (reference: :73-92)."""
+        return self._launch(featmap_size, 1, 1, device, valid_size, None, -1, False, True)[1]
+
+    def grid_anchors_and_inside_flags(self, featmap_size, stride, depth_stride, valid_size, img_shape, allowed_border=0,
+                                      device='cuda'):
+        """Anchors plus `anchor_inside_flags(anchors, valid_flags, img_shape, allowed_border)`
+        (mmdet/core/anchor/anchor_target.py:203-217) in the same launch.  img_shape = (H, W, 3, D)."""
+        return self._launch(featmap_size, stride, depth_stride, device, valid_size, img_shape, allowed_border, True, True)

@@ -172,6 +172,15 @@ int roi3d_nms3d_host(const float *dets_host, int n, float iou_thr, int64_t *keep
  * roi3d_bbox2delta3d: bbox2delta3d, mmdet/core/bbox/transforms.py:33-63; deltas [n, 6] = (dx, dy, dw, dh, dz, dd);
  *   means6 / stds6 are HOST pointers to six floats (NULL = 0 / 1).
  * ---------------------------------------------------------------------------------------------- */
+/* Anchors of one level in closed form and / or their inside flags, one launch.
+ * Replaces: AnchorGenerator3D.grid_anchors + valid_flags, mmdet/core/anchor/anchor_generator_3d.py:56-92 (numpy
+ *   meshgrid + H2D per call) and anchor_inside_flags, mmdet/core/anchor/anchor_target.py:203-217.
+ * anchors_dev [A*D*H*W, 6] fp32 and flags_dev [A*D*H*W] uint8 (either may be NULL); flat index
+ * ((y*W + x)*D + z)*A + a; flag = x < valid_w && y < valid_h && z < valid_d, and if allowed_border >= 0 also
+ * x1,y1,z1 >= -border, x2 < img_w + border, y2 < img_h + border, z2 < img_d + border.  base_anchors_host: [A,6]. */
+int roi3d_grid_anchors(int A, int D, int H, int W, float stride, float depth_stride, const float *base_anchors_host,
+                       int valid_d, int valid_h, int valid_w, float img_h, float img_w, float img_d, int allowed_border,
+                       float *anchors_dev, uint8_t *flags_dev, void *stream);
 int roi3d_bbox_overlaps3d(const float *boxes1_dev, int m, int stride1, const float *boxes2_dev, int n, int stride2,
                           float *iou_dev, void *stream);
 size_t roi3d_assign_workspace_bytes(int n, int k);

@@ -417,6 +417,28 @@ def bbox2delta3d(proposals, gt, means=(0, 0, 0, 0, 0, 0), stds=(1, 1, 1, 1, 1, 1
     return ((d - _f32(np.asarray(means))[None]) / _f32(np.asarray(stds))[None]).astype(np.float32)
 
 
+def valid_flags(featmap_size, valid_size, num_base_anchors):
+    """AnchorGenerator3D.valid_flags (mmdet/core/anchor/anchor_generator_3d.py:73-92): np.meshgrid(x, y, z) order."""
+    fz, fh, fw = featmap_size
+    vd, vh, vw = valid_size
+    vx, vy, vz = np.zeros(fw, np.uint8), np.zeros(fh, np.uint8), np.zeros(fz, np.uint8)
+    vx[:vw], vy[:vh], vz[:vd] = 1, 1, 1
+    xx, yy, zz = np.meshgrid(vx, vy, vz)
+    v = xx.flatten() & yy.flatten() & zz.flatten()
+    return np.repeat(v, num_base_anchors)
+
+
+def anchor_inside_flags(flat_anchors, valid, img_shape, allowed_border=0):
+    """anchor_inside_flags, 6-column branch (mmdet/core/anchor/anchor_target.py:203-217); img_shape = (H, W, 3, D)."""
+    a = _f32(flat_anchors)
+    if allowed_border < 0:
+        return valid
+    h, w, d = img_shape[0], img_shape[1], img_shape[3]
+    ins = (a[:, 0] >= -allowed_border) & (a[:, 1] >= -allowed_border) & (a[:, 4] >= -allowed_border) & \
+        (a[:, 2] < w + allowed_border) & (a[:, 3] < h + allowed_border) & (a[:, 5] < d + allowed_border)
+    return valid & ins.astype(valid.dtype)
+
+
 def nms_cpu_2d(dets, thr):
     """nms_cpu_kernel (mmdet/ops/nms/src/nms_cpu.cpp:5-59): 2-D NMS over columns 0-3 ranked by column 4,
     suppressing ovr >= thr -- what the reference's CPU wrapper runs even on 7-column input."""

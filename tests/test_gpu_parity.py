@@ -739,3 +739,34 @@ def test_bbox2delta3d_matches_oracle(oracle, dev):
     assert np.allclose(gn[:, [2, 3, 5]], want[:, [2, 3, 5]], rtol=1e-5, atol=1e-6)  # tolerance: 1e-5 relative
     back = delta2bbox3D(torch.from_numpy(p).to(dev), got, means, stds)
     assert (back - torch.from_numpy(g).to(dev)).abs().max() < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# anchors in closed form + valid / inside flags on the device
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    # (featmap D,H,W), stride, depth stride, scales, depth scales, ratios, valid (d,h,w), img_shape (H,W,3,D), border
+    ((5, 8, 6), 8, 4, [2], [2], [1.0], (5, 7, 6), (56, 48, 3, 20), 0),
+    ((7, 9, 11), 4, 2, [2, 4], [2, 3], [0.5, 1.0, 2.0], (6, 9, 10), (36, 42, 3, 13), 3),
+    ((3, 4, 5), 16, 8, [8], [2], [1.0], (3, 4, 5), (64, 80, 3, 24), -1),
+])
+def test_grid_anchors_and_inside_flags_match_oracle(oracle, dev, case):
+    from roi3d_b200 import AnchorGenerator3D
+    from roi3d_b200.core.anchor import anchor_inside_flags
+    fm, st, sd, scales, dscales, ratios, valid, img_shape, border = case
+    gen = AnchorGenerator3D(st, scales, dscales, ratios, sd)
+    base = oracle.gen_base_anchors(st, scales, dscales, ratios, sd)
+    assert np.array_equal(gen.base_anchors.numpy(), base)
+    want_a = oracle.grid_anchors(base, fm, st, sd)
+    want_v = oracle.valid_flags(fm, valid, base.shape[0])
+    want_f = oracle.anchor_inside_flags(want_a, want_v, img_shape, border)
+    got_a = gen.grid_anchors(fm, st, sd, device=dev)
+    assert np.array_equal(got_a.cpu().numpy(), want_a)
+    got_v = gen.valid_flags(fm, valid, device=dev)
+    assert got_v.dtype == torch.uint8 and np.array_equal(got_v.cpu().numpy(), want_v)
+    a2, f2 = gen.grid_anchors_and_inside_flags(fm, st, sd, valid, img_shape, border, device=dev)
+    assert torch.equal(a2, got_a) and np.array_equal(f2.cpu().numpy(), want_f)
+    assert torch.equal(anchor_inside_flags(got_a, got_v, img_shape, border), f2)
+    if border >= 0:
+        assert 0 < int(f2.sum()) < f2.numel()
