@@ -203,11 +203,16 @@ __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const float 
 }
 
 // rank-by-counting sort of the (unique) candidate keys, descending.  grid (ceil(k/256), nseg).
+// by_index (a segment no longer than k, when the caller asks for it): the whole segment is selected and is returned
+// in ascending logical index instead -- the reference only sorts a level that has more than nms_pre anchors
+// (rpn_head_3d.py:96,108-112).  The low key word is ~index, so "descending low word" is ascending index.
 __global__ void __launch_bounds__(256) topk_sort_kernel(const unsigned long long *__restrict__ cand,
-                                                        const SegState *__restrict__ state, int k,
-                                                        int64_t *__restrict__ out_idx, float *__restrict__ out_val) {
+                                                        const SegState *__restrict__ state, const SegTable tab,
+                                                        int small_by_index, int k, int64_t *__restrict__ out_idx,
+                                                        float *__restrict__ out_val) {
   const int seg = blockIdx.y;
   const int n = state[seg].k_take;
+  const bool by_index = small_by_index && tab.s[seg].len <= (unsigned)k;
   if ((int)(blockIdx.x * 256) >= n) return;
   const unsigned long long *c = cand + (long long)seg * k;
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(256) topk_sort_kernel(const unsigned long long
     const int lim = min(256, n - j0);
     if (i < n) {
 #pragma unroll 8
-      for (int t = 0; t < lim; ++t) rank += keys[t] > ki;
+      for (int t = 0; t < lim; ++t) rank += by_index ? ((unsigned)keys[t] > (unsigned)ki) : (keys[t] > ki);
     }
   }
   if (i < n) {
@@ -387,6 +392,66 @@ __global__ void __launch_bounds__(256) decode_proposals_batched_kernel(const Dec
   o[6] = b.scores ? b.scores[(long long)s * b.k + i] : 0.0f;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tail of RPNHead3D.get_bboxes_single for every (image, level) segment at once (rpn_head_3d.py:135-148):
+// proposals[:nms_post] of each level in NMS return order, concatenated per image in level order; scores of the
+// unused tail are -inf so that the following top-k(max_num) ignores them.
+// grid (ceil(P/256), B*L).  keep_sel[s] picks, per segment, the score-ordered or the index-ordered keep list.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rpn_collect_kernel(const float *__restrict__ dets, int k,
+                                                          const int64_t *__restrict__ keep_by_score,
+                                                          const int64_t *__restrict__ keep_by_index,
+                                                          const int32_t *__restrict__ num_keep,
+                                                          const unsigned char *__restrict__ use_index_order, int L, int P,
+                                                          float *__restrict__ cat_props, float *__restrict__ cat_scores,
+                                                          int32_t *__restrict__ n_valid) {
+  const int seg = blockIdx.y, b = seg / L, l = seg - b * L;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  int before = 0, total = 0, mine = 0;
+  for (int q = 0; q < L; ++q) {
+    const int c = min(max(num_keep[b * L + q], 0), P);
+    if (q < l) before += c;
+    if (q == l) mine = c;
+    total += c;
+  }
+  if (l == 0 && i == 0) n_valid[b] = total;
+  if (i >= P) return;
+  const long long row0 = (long long)b * L * P;
+  if (i < mine) {
+    const int64_t *keep = (use_index_order != nullptr && use_index_order[seg]) ? keep_by_index : keep_by_score;
+    long long r = keep[(long long)seg * k + i];
+    r = r < 0 ? 0 : (r >= k ? k - 1 : r);
+    const float *src = dets + ((long long)seg * k + r) * 7;
+    float *dst = cat_props + (row0 + before + i) * 7;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) dst[q] = src[q];
+    cat_scores[row0 + before + i] = src[6];
+  } else {
+    // this segment's unused slots fill the image's tail: total + (slack of earlier levels) + own slack position
+    const int slack_before = l * P - before;
+    const long long pos = row0 + total + slack_before + (i - mine);
+    cat_scores[pos] = -INFINITY;
+  }
+}
+
+// out[b][j] = rows[b][idx[b][j]] (7 floats); idx < 0 -> zeros.  grid (ceil(n/256), B)
+__global__ void __launch_bounds__(256) gather_rows7_kernel(const float *__restrict__ rows, int rows_per_seg,
+                                                           const int64_t *__restrict__ idx, int n,
+                                                           float *__restrict__ out) {
+  const int b = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  const long long r = idx[(long long)b * n + j];
+  float *dst = out + ((long long)b * n + j) * 7;
+  if (r < 0 || r >= rows_per_seg) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) dst[q] = 0.0f;
+    return;
+  }
+  const float *src = rows + ((long long)b * rows_per_seg + r) * 7;
+#pragma unroll
+  for (int q = 0; q < 7; ++q) dst[q] = src[q];
+}
+
 }  // namespace roi3d
 
 using namespace roi3d;
@@ -405,6 +470,14 @@ size_t roi3d_topk_workspace_bytes(int nseg, int k) {
 int roi3d_topk_segmented(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
                          const int32_t *seg_adhw, int nseg, int k, int apply_sigmoid, int64_t *out_idx_dev,
                          float *out_val_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
+  return roi3d_topk_segmented_ex(scores_dev, seg_off, seg_len, seg_adhw, nseg, k, apply_sigmoid, 0, out_idx_dev,
+                                 out_val_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int roi3d_topk_segmented_ex(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
+                            const int32_t *seg_adhw, int nseg, int k, int apply_sigmoid, int small_segments_in_index_order,
+                            int64_t *out_idx_dev, float *out_val_dev, void *workspace_dev, size_t workspace_bytes,
+                            void *stream) {
   ROI3D_CHECK_ARG(nseg >= 0 && k >= 0, "bad sizes");
   if (nseg == 0 || k == 0) return ROI3D_OK;
   ROI3D_CHECK_ARG(scores_dev && seg_off && seg_len && out_idx_dev && out_val_dev && workspace_dev, "NULL pointer");
@@ -458,7 +531,8 @@ int roi3d_topk_segmented(const float *scores_dev, const int64_t *seg_off, const 
     else
       topk_collect_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand);
     ROI3D_LAUNCH_CHECK();
-    topk_sort_kernel<<<dim3(ceil_div(k, 256), ns), 256, 0, st>>>(cand, state, k, out_idx_dev + (size_t)s0 * k,
+    topk_sort_kernel<<<dim3(ceil_div(k, 256), ns), 256, 0, st>>>(cand, state, tab, small_segments_in_index_order, k,
+                                                                out_idx_dev + (size_t)s0 * k,
                                                                 out_val_dev + (size_t)s0 * k);
     ROI3D_LAUNCH_CHECK();
   }
@@ -534,6 +608,35 @@ int roi3d_decode_proposals_batched(const float *const *bbox_pred_dev_ptrs, const
     decode_proposals_batched_kernel<<<dim3(ceil_div(k, 256), ns), 256, 0, st>>>(b);
     ROI3D_LAUNCH_CHECK();
   }
+  return ROI3D_OK;
+}
+
+int roi3d_rpn_collect(const float *dets_dev, int num_images, int num_levels, int k, const int64_t *keep_by_score_dev,
+                      const int64_t *keep_by_index_dev, const int32_t *num_keep_dev,
+                      const uint8_t *use_index_order_dev, int nms_post, float *cat_props_dev, float *cat_scores_dev,
+                      int32_t *n_valid_dev, void *stream) {
+  ROI3D_CHECK_ARG(num_images >= 0 && num_levels >= 1 && k >= 1 && nms_post >= 1, "bad sizes");
+  if (num_images == 0) return ROI3D_OK;
+  ROI3D_CHECK_ARG(dets_dev && keep_by_score_dev && num_keep_dev && cat_props_dev && cat_scores_dev && n_valid_dev,
+                  "NULL pointer");
+  ROI3D_CHECK_ARG(use_index_order_dev == nullptr || keep_by_index_dev != nullptr, "keep_by_index is NULL");
+  ROI3D_CHECK_ARG((long long)num_images * num_levels <= 65535, "too many segments");
+  const int P = nms_post < k ? nms_post : k;
+  rpn_collect_kernel<<<dim3(ceil_div(P, 256), num_images * num_levels), 256, 0, (cudaStream_t)stream>>>(
+      dets_dev, k, keep_by_score_dev, keep_by_index_dev, num_keep_dev, use_index_order_dev, num_levels, P, cat_props_dev,
+      cat_scores_dev, n_valid_dev);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+int roi3d_gather_rows7(const float *rows_dev, int nseg, int rows_per_seg, const int64_t *idx_dev, int n, float *out_dev,
+                       void *stream) {
+  ROI3D_CHECK_ARG(nseg >= 0 && rows_per_seg >= 0 && n >= 0 && nseg <= 65535, "bad sizes");
+  if (nseg == 0 || n == 0) return ROI3D_OK;
+  ROI3D_CHECK_ARG(rows_dev && idx_dev && out_dev, "NULL pointer");
+  gather_rows7_kernel<<<dim3(ceil_div(n, 256), nseg), 256, 0, (cudaStream_t)stream>>>(rows_dev, rows_per_seg, idx_dev, n,
+                                                                                      out_dev);
+  ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
 }
 

@@ -34,12 +34,14 @@ def _cfg_get(cfg, key, default=None):
     return getattr(cfg, key, default)
 
 
-def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False):
+def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False, small_in_index_order=False):
     """Segmented top-k over a list of CUDA fp32 tensors (one segment each).
 
     permute_adhw=True: each tensor is an [A, D, H, W] score map and indices refer to
     permute(2,3,1,0).reshape(-1) positions (rpn_head_3d.py:87-89).  Returns (idx [nseg,k] int64, val [nseg,k]);
     rows past a segment's length hold -1 / 0.  Descending, ties -> lower index.  No host sync.
+    small_in_index_order=True: a segment with no more than k elements comes back whole, in ascending index order
+    (the reference does not sort a level that has at most nms_pre anchors, rpn_head_3d.py:96,108-112).
     """
     nseg = len(scores_list)
     dev = scores_list[0].device
@@ -60,9 +62,9 @@ def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False):
     nbytes = _lib.lib.roi3d_topk_workspace_bytes(nseg, k)
     _buf, ws = scratch(dev, nbytes, "topk")
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib.roi3d_topk_segmented(base, off.ctypes.data, ln.ctypes.data, adhw_p, nseg, int(k),
-                                                 int(bool(apply_sigmoid)), idx.data_ptr(), val.data_ptr(), ws,
-                                                 nbytes, stream_ptr()))
+        _lib.check(_lib.lib.roi3d_topk_segmented_ex(base, off.ctypes.data, ln.ctypes.data, adhw_p, nseg, int(k),
+                                                    int(bool(apply_sigmoid)), int(bool(small_in_index_order)),
+                                                    idx.data_ptr(), val.data_ptr(), ws, nbytes, stream_ptr()))
     del segs, adhw
     return idx, val
 
@@ -150,18 +152,12 @@ class RPNProposal3D(object):
                 seg_meta.append((b, l))
         k = nms_pre if nms_pre > 0 else max(s.numel() for s in segs)
         k = min(k, max(s.numel() for s in segs))
-        idx, val = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True)
         # The reference only sorts a level when it has MORE than nms_pre anchors (rpn_head_3d.py:96,108-112);
         # a smaller level reaches NMS in anchor order, and `proposals[:nms_post]` then truncates in that order
-        # (nms returns ascending input indices, nms_kernel.cu:253-256).  Reproduce that: put such segments back
-        # in ascending anchor order and truncate them by original index instead of by score.
+        # (nms returns ascending input indices, nms_kernel.cu:253-256).  The top-k returns such segments whole in
+        # ascending anchor order, and step 4 truncates them by original index instead of by score.
+        idx, val = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True, small_in_index_order=nms_pre > 0)
         unsorted = [not (nms_pre > 0 and s.numel() > nms_pre) for s in segs]
-        for sid, flag in enumerate(unsorted):
-            if flag:
-                n = segs[sid].numel()
-                o = torch.argsort(idx[sid, :n])
-                idx[sid, :n] = idx[sid, :n][o]
-                val[sid, :n] = val[sid, :n][o]
 
         # 2. decode the selected anchors of every segment in ONE launch (anchors recomputed in closed form)
         dets = torch.empty((B * L, k, 7), dtype=torch.float32, device=dev)
@@ -190,25 +186,25 @@ class RPNProposal3D(object):
 
         # 3. one batched NMS; kept rows in descending-score order
         keep_i, keep_s, num_keep = nms3d_batched(dets, seg_counts, nms_thr, want_score_order=True)
-        if any(unsorted):
-            keep_s = torch.where(torch.tensor(unsorted, device=dev)[:, None], keep_i, keep_s)
 
-        # 4. proposals[:nms_post] per segment (rpn_head_3d.py:135), then per image cat + topk(max_num) (:139-148)
+        # 4. proposals[:nms_post] per segment (rpn_head_3d.py:135), per image cat in level order, topk(max_num)
+        #    (:139-148): one collect kernel, one segmented top-k, one row gather
         P = min(nms_post, k)
-        take = keep_s[:, :P].clamp_(min=0, max=k - 1)
-        valid = torch.arange(P, device=dev)[None, :] < num_keep[:, None].clamp(max=P)
-        props = torch.gather(dets, 1, take[:, :, None].expand(-1, -1, 7))          # [B*L, P, 7]
-        cat_scores = torch.where(valid, props[:, :, 6], props.new_full((), float('-inf')))
-        props = props.view(B, L * P, 7)
-        cat_scores = cat_scores.view(B, L * P)
-        n_valid = valid.view(B, L * P).sum(dim=1)
-        # compact valid rows to the front of each image (stable) so indices match the reference's cat order
-        order = torch.sort((~valid.view(B, L * P)).to(torch.uint8), dim=1, stable=True)[1]
-        props = torch.gather(props, 1, order[:, :, None].expand(-1, -1, 7))
-        cat_scores = torch.gather(cat_scores, 1, order)
+        cat_props = torch.empty((B, L * P, 7), dtype=torch.float32, device=dev)
+        cat_scores = torch.empty((B, L * P), dtype=torch.float32, device=dev)
+        n_valid = torch.empty((B,), dtype=torch.int32, device=dev)
+        use_idx = torch.tensor(unsorted, dtype=torch.uint8, device=dev) if any(unsorted) else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.roi3d_rpn_collect(
+                dets.data_ptr(), B, L, k, keep_s.data_ptr(), keep_i.data_ptr(), num_keep.data_ptr(),
+                None if use_idx is None else use_idx.data_ptr(), nms_post, cat_props.data_ptr(), cat_scores.data_ptr(),
+                n_valid.data_ptr(), stream_ptr()))
         kk = min(max_num, L * P)
         fidx, _ = topk_segmented([cat_scores[b] for b in range(B)], kk, apply_sigmoid=False)
-        final = torch.gather(props, 1, fidx.clamp(min=0)[:, :, None].expand(-1, -1, 7))  # [B, kk, 7]
+        final = torch.empty((B, kk, 7), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.roi3d_gather_rows7(cat_props.data_ptr(), B, L * P, fidx.data_ptr(), kk, final.data_ptr(),
+                                                   stream_ptr()))
         n_out = n_valid.clamp(max=kk).tolist()  # the single host read of the whole path
         result = [final[b, :n_out[b]] for b in range(B)]
         if return_anchors:

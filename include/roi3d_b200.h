@@ -223,6 +223,26 @@ size_t roi3d_topk_workspace_bytes(int nseg, int k);
 int roi3d_topk_segmented(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
                          const int32_t *seg_adhw, int nseg, int k, int apply_sigmoid, int64_t *out_idx_dev,
                          float *out_val_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+/* Same, with the reference's "sort a level only if it has more than nms_pre anchors" rule
+ * (rpn_head_3d.py:96,108-112): with small_segments_in_index_order != 0 a segment no longer than k is returned in
+ * ascending logical index (all of it), not in score order. */
+int roi3d_topk_segmented_ex(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
+                            const int32_t *seg_adhw, int nseg, int k, int apply_sigmoid,
+                            int small_segments_in_index_order, int64_t *out_idx_dev, float *out_val_dev,
+                            void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Tail of RPNHead3D.get_bboxes_single for all (image, level) segments (rpn_head_3d.py:135-148): the first
+ * min(num_keep, nms_post) kept rows of every level, in NMS return order, concatenated per image in level order.
+ * dets_dev [B*L, k, 7]; keep lists [B*L, k] from roi3d_nms3d_batched; use_index_order_dev (optional uint8 [B*L]):
+ * 1 = take keep_by_index for that segment (levels that were not score-sorted).  Outputs: cat_props_dev
+ * [B, L*P, 7], cat_scores_dev [B, L*P] (-inf past the valid rows), n_valid_dev int32 [B]; P = min(nms_post, k). */
+int roi3d_rpn_collect(const float *dets_dev, int num_images, int num_levels, int k, const int64_t *keep_by_score_dev,
+                      const int64_t *keep_by_index_dev, const int32_t *num_keep_dev,
+                      const uint8_t *use_index_order_dev, int nms_post, float *cat_props_dev, float *cat_scores_dev,
+                      int32_t *n_valid_dev, void *stream);
+/* out[s][j] = rows[s][idx[s][j]] for 7-float rows (idx < 0 -> zeros): the final `proposals[topk_inds]`, :147-148. */
+int roi3d_gather_rows7(const float *rows_dev, int nseg, int rows_per_seg, const int64_t *idx_dev, int n,
+                       float *out_dev, void *stream);
 
 /* Anchor base + decode of selected anchors for one level, fused:
  *   anchors as AnchorGenerator3D.grid_anchors would generate them
