@@ -152,12 +152,17 @@ class RPNProposal3D(object):
                 seg_meta.append((b, l))
         k = nms_pre if nms_pre > 0 else max(s.numel() for s in segs)
         k = min(k, max(s.numel() for s in segs))
+        # Small descriptor tensors go up FIRST: a pageable host-to-device copy is stream-ordered and blocks the host,
+        # so issued later it would wait for every kernel already queued and serialise the CPU with the GPU.
+        counts = [min(k, s.numel()) for s in segs]
+        unsorted = [not (nms_pre > 0 and s.numel() > nms_pre) for s in segs]
+        seg_counts = torch.tensor(counts, dtype=torch.int32, device=dev)
+        use_idx = torch.tensor(unsorted, dtype=torch.uint8, device=dev) if any(unsorted) else None
         # The reference only sorts a level when it has MORE than nms_pre anchors (rpn_head_3d.py:96,108-112);
         # a smaller level reaches NMS in anchor order, and `proposals[:nms_post]` then truncates in that order
         # (nms returns ascending input indices, nms_kernel.cu:253-256).  The top-k returns such segments whole in
         # ascending anchor order, and step 4 truncates them by original index instead of by score.
         idx, val = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True, small_in_index_order=nms_pre > 0)
-        unsorted = [not (nms_pre > 0 and s.numel() > nms_pre) for s in segs]
 
         # 2. decode the selected anchors of every segment in ONE launch (anchors recomputed in closed form)
         dets = torch.empty((B * L, k, 7), dtype=torch.float32, device=dev)
@@ -181,8 +186,6 @@ class RPNProposal3D(object):
                 ptrs, adhw.ctypes.data, lvl.ctypes.data, img.ctypes.data, B * L, L, A, base.ctypes.data,
                 strides.ctypes.data, dstrides.ctypes.data, idx.data_ptr(), val.data_ptr(), k, means.ctypes.data,
                 stds.ctypes.data, dets.data_ptr(), stream_ptr()))
-        counts = [min(k, s.numel()) for s in segs]
-        seg_counts = torch.tensor(counts, dtype=torch.int32, device=dev)
 
         # 3. one batched NMS; kept rows in descending-score order
         keep_i, keep_s, num_keep = nms3d_batched(dets, seg_counts, nms_thr, want_score_order=True)
@@ -193,7 +196,6 @@ class RPNProposal3D(object):
         cat_props = torch.empty((B, L * P, 7), dtype=torch.float32, device=dev)
         cat_scores = torch.empty((B, L * P), dtype=torch.float32, device=dev)
         n_valid = torch.empty((B,), dtype=torch.int32, device=dev)
-        use_idx = torch.tensor(unsorted, dtype=torch.uint8, device=dev) if any(unsorted) else None
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.roi3d_rpn_collect(
                 dets.data_ptr(), B, L, k, keep_s.data_ptr(), keep_i.data_ptr(), num_keep.data_ptr(),

@@ -315,10 +315,39 @@ def test_topk_segmented_exact(oracle, dev):
         assert (idx[s, m:] == -1).all()
 
 
+def test_topk_small_segments(oracle, dev):
+    """Short segments only (the final topk(max_num) of the proposal path is such a call): ties, k > n, -inf padding
+    and the 'small segments stay in index order' rule."""
+    from roi3d_b200.models.anchor_heads import topk_segmented
+    rng = np.random.default_rng(44)
+    segs = [rng.standard_normal(n).astype(np.float32) for n in (1, 5, 300, 5000, 8192)]
+    segs.append(np.round(rng.standard_normal(6000) * 4).astype(np.float32) / 4)     # heavy ties
+    segs.append(np.full(3000, 0.25, np.float32))                                     # all equal
+    segs.append(np.where(rng.random(4000) < 0.5, -np.inf, rng.standard_normal(4000)).astype(np.float32))  # -inf padding
+    for k in (2000, 1, 8192):
+        idx, val = topk_segmented([torch.from_numpy(s).to(dev) for s in segs], k)
+        idx, val = idx.cpu().numpy(), val.cpu().numpy()
+        for s, seg in enumerate(segs):
+            want = oracle.topk(seg, k)
+            m = len(want)
+            assert np.array_equal(idx[s, :m], want)
+            assert np.array_equal(val[s, :m], seg[want])
+            assert (idx[s, m:] == -1).all() and (val[s, m:] == 0).all()
+    k = 2000
+    idx, val = topk_segmented([torch.from_numpy(s).to(dev) for s in segs], k, small_in_index_order=True)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    for s, seg in enumerate(segs):
+        if len(seg) <= k:
+            assert np.array_equal(idx[s, :len(seg)], np.arange(len(seg))) and np.array_equal(val[s, :len(seg)], seg)
+        else:
+            assert np.array_equal(idx[s], oracle.topk(seg, k))
+
+
 def test_topk_permuted_sigmoid(oracle, dev):
     from roi3d_b200.models.anchor_heads import topk_segmented
     rng = np.random.default_rng(41)
-    maps = [2 * rng.standard_normal(s).astype(np.float32) for s in ((1, 8, 16, 16), (3, 4, 6, 5), (1, 2, 3, 3))]
+    maps = [2 * rng.standard_normal(s).astype(np.float32)
+            for s in ((1, 8, 16, 16), (3, 4, 6, 5), (1, 2, 3, 3), (2, 12, 24, 20))]
     maps[1] = np.round(maps[1])   # ties: the tie rule must use LOGICAL (permuted) indices
     k = 200
     idx, val = topk_segmented([torch.from_numpy(m).to(dev) for m in maps], k, apply_sigmoid=True,
@@ -330,6 +359,9 @@ def test_topk_permuted_sigmoid(oracle, dev):
         n = len(want)
         assert np.array_equal(idx[s, :n].cpu().numpy(), want)
         assert np.array_equal(val[s, :n].cpu().numpy(), flat[want])
+    idx2, val2 = topk_segmented([torch.from_numpy(m).to(dev) for m in maps[:3]], k, apply_sigmoid=True,
+                                permute_adhw=True)                           # same segments in a smaller batch
+    assert torch.equal(idx2, idx[:3]) and torch.equal(val2, val[:3])
 
 
 def test_decode_matches_oracle(oracle, dev):
