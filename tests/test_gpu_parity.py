@@ -104,6 +104,8 @@ CASES = [
     ((1, 6, 10, 16, 16), 7, 7, 0.25, 0.5, 0, 10),       # adaptive sampling, odd channel count
     ((1, 16, 6, 12, 12), 5, 4, 0.25, 0.5, 2, 8),        # generic output size
     ((1, 8, 20, 60, 60), 7, 7, 1.0, 1.0, 2, 6),         # footprint larger than the tables -> literal path
+    ((1, 160, 8, 18, 18), 7, 7, 0.25, 0.5, 2, 14),      # three channel chunks (last one half full): warps of a CTA
+    ((1, 160, 6, 12, 12), 14, 14, 0.25, 0.5, 2, 9),     # ... span RoI sub-items with different chunks and pd
 ]
 
 
@@ -160,7 +162,7 @@ def test_roi_align_empty_rois(dev):
     assert out.shape == (0, 32, 3, 7, 7)
 
 
-@pytest.mark.parametrize("case", CASES[:6])
+@pytest.mark.parametrize("case", CASES[:6] + CASES[7:])
 @pytest.mark.parametrize("layout", ["channels_last", "contiguous"])
 def test_roi_align_backward(oracle, dev, case, layout):
     from roi3d_b200.ops import RoIAlign3D
