@@ -804,3 +804,26 @@ def test_grid_anchors_and_inside_flags_match_oracle(oracle, dev, case):
     assert torch.equal(anchor_inside_flags(got_a, got_v, img_shape, border), f2)
     if border >= 0:
         assert 0 < int(f2.sum()) < f2.numel()
+
+
+@pytest.mark.gpu
+def test_roi_align_forward_slab_variant(oracle, dev):
+    """Tuning variant 80 (specialised-warp slab kernel, 7-wide outputs): same tolerance against the oracle as the
+    default kernel, for 7x7x7 and 7x7x3 outputs, several channel chunks, adversarial and wide RoIs."""
+    import roi3d_b200
+    from roi3d_b200.ops import RoIAlign3D
+    shape = (2, 160, 10, 24, 40)
+    f = _feats(shape, 33)
+    rois = np.concatenate([synth.c2_rois(40, seed=6, img=(160, 96, 20), batch=2),
+                           synth.adversarial_rois(shape[2:], 0.25, 0.5, batch=2),
+                           np.array([[1, 2, 3, 150, 90, 1, 12]], np.float32)], 0)
+    ft = cl(torch.from_numpy(f).to(dev))
+    rt = torch.from_numpy(rois).to(dev)
+    roi3d_b200._lib.set_tuning(0, 80)
+    try:
+        for pdp in (7, 3):
+            want = oracle.roi_align3d_forward(f, rois, 7, pdp, 0.25, 0.5, 2)
+            out = RoIAlign3D(7, pdp, 0.25, 0.5, 2)(ft, rt)
+            assert rel_err(out.cpu().numpy(), want) <= FWD_TOL
+    finally:
+        roi3d_b200._lib.set_tuning(0, 0)
