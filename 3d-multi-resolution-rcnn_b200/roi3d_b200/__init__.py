@@ -10,6 +10,7 @@ Module paths mirror the reference's (`mmdet.X` -> `roi3d_b200.X`):
     roi3d_b200.core.bbox                 delta2bbox3D, bbox2roi3D                       (core/bbox/transforms.py)
     roi3d_b200.core.post_processing      multiclass_nms_3d                              (core/post_processing/bbox_nms.py)
     roi3d_b200.core.evaluation           apply_nms, nms_3d_python                       (core/evaluation/coco_utils.py)
+    roi3d_b200.models.mask_heads         get_seg_masks (mask paste)                     (models/mask_heads/fcn_mask_head_3d.py)
     roi3d_b200.parallel                  shard_indices, gather_detections               (replaces eval_hooks.py:134-149)
 
 Everything computes in hand-written CUDA (libroi3d_b200.so, C ABI in include/roi3d_b200.h).  Importing this

@@ -578,6 +578,26 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ref_out = torch_way()
     ex["n2_assign_torch_formulation_us"] = med_us(torch_way, iters=3, warm=1, do_flush=False)
     ex["n2_assign_identical_to_torch_formulation"] = bool(torch.equal(ref_out, res.gt_inds))
+    # N4: mask paste of 100 detections (14x14x10 mask logits -> box-sized binary masks), host lists out
+    from roi3d_b200.models.mask_heads import paste_masks_compact
+    rng4 = np.random.default_rng(4)
+    n4 = 100
+    lg4 = torch.from_numpy((3 * rng4.standard_normal((n4, 2, 10, 14, 14))).astype(np.float32)).to(dev)
+    lo4 = np.stack([rng4.uniform(0, 400, n4), rng4.uniform(0, 400, n4), rng4.uniform(0, 120, n4)], 1)
+    sz4 = np.stack([rng4.integers(4, 64, n4), rng4.integers(4, 64, n4), rng4.integers(2, 24, n4)], 1)
+    det4 = np.stack([lo4[:, 0], lo4[:, 1], lo4[:, 0] + sz4[:, 0], lo4[:, 1] + sz4[:, 1], lo4[:, 2], lo4[:, 2] + sz4[:, 2],
+                     rng4.random(n4)], 1).astype(np.float32)
+    det4_t, lab4_t = torch.from_numpy(det4).to(dev), torch.zeros(n4, dtype=torch.long, device=dev)
+    paste_masks_compact(lg4, det4_t, lab4_t, 0.5)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        _b4, m4, _l4 = paste_masks_compact(lg4, det4_t, lab4_t, 0.5)
+    ex["n4_mask_paste_100det_us"] = (time.perf_counter() - t0) / 5 * 1e6
+    t0 = time.perf_counter()
+    _bo, mo4, _lo = oracle.get_seg_masks_compact(lg4.cpu().numpy(), det4, np.zeros(n4, np.int64), 0.5)
+    ex["n4_mask_paste_scipy_restatement_us"] = (time.perf_counter() - t0) * 1e6
+    ex["n4_mask_voxels_differing"] = int(sum(int((a != b).sum()) for a, b in zip(m4, mo4)))
     pos_idx = torch.nonzero(res.gt_inds > 0).squeeze(1)
     if pos_idx.numel():
         pa, pg = anchors[pos_idx].contiguous(), gts[res.gt_inds[pos_idx] - 1].contiguous()

@@ -192,6 +192,18 @@ int roi3d_assign_max_iou(const float *bboxes_dev, int n, int stride, const float
 int roi3d_bbox2delta3d(const float *proposals_dev, int stride_p, const float *gt_dev, int stride_g, int n,
                        const float *means6, const float *stds6, float *deltas_dev, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Mask paste: per detection sigmoid -> resize to the box -> threshold.
+ * Replaces: FCNMaskHead3D.get_seg_masks, mmdet/models/mask_heads/fcn_mask_head_3d.py:144-187 (host numpy +
+ *   skimage.transform.resize per detection).  mask_logits_dev [n, Dm, Hm, Wm] fp32 (the class channel already
+ *   selected); boxes_dev int32 [n, 6] = (x1, y1, x2, y2, z1, z2) after the reference's `(bbox / scale).astype(int32)`;
+ *   detection i's binary mask of max(z2-z1+1,1) x max(y2-y1+1,1) x max(x2-x1+1,1) voxels (z, y, x order) is written
+ *   at out_dev + offsets_dev[i].  The resize restates scikit-image 0.18.0 `resize` (n-D branch: gaussian
+ *   anti-aliasing + order-1 map_coordinates, mode reflect) in float64 like scipy.
+ * ---------------------------------------------------------------------------------------------- */
+int roi3d_mask_paste(const float *mask_logits_dev, int n, int Dm, int Hm, int Wm, const int32_t *boxes_dev,
+                     const int64_t *offsets_dev, float thr, uint8_t *out_dev, void *stream);
+
 /* Experiment knob (not part of the reference surface): key 0 = forward kernel variant, 1 = backward
  * kernel variant; value 0 = auto, 1/2 = alternative register tilings, 99 = literal (reference-order) path.
  * key 2 = sub-items one forward warp walks per RoI (0 = auto); key 4 = volume size in KB from which

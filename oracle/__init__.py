@@ -439,6 +439,43 @@ def anchor_inside_flags(flat_anchors, valid, img_shape, allowed_border=0):
     return valid & ins.astype(valid.dtype)
 
 
+def resize_nd(image, output_shape):
+    """skimage.transform.resize(image, output_shape) for a float n-D image with the defaults the reference uses
+    (mmdet/models/mask_heads/fcn_mask_head_3d.py:181): scikit-image==0.18.0 (requirements.txt:24), n-dimensional
+    branch of skimage/transform/_warps.py -- anti_aliasing on, sigma = max(0, (factors - 1) / 2), gaussian_filter
+    and order-1 map_coordinates with ndimage mode 'mirror' (skimage mode 'reflect'), clip to the input range.
+    The two primitives are scipy.ndimage's (scipy==1.5.4 pinned by the reference, requirements.txt:25; this image
+    has a newer scipy whose order-1 / mirror behaviour is the same).  skimage itself is not installed: parity
+    unpinned by the reference."""
+    import scipy.ndimage as ndi
+    image = np.asarray(image, dtype=np.float32)
+    factors = np.divide(np.asarray(image.shape, dtype=np.float64), np.asarray(output_shape, dtype=np.float64))
+    sigma = np.maximum(0, (factors - 1) / 2)
+    img = ndi.gaussian_filter(image, sigma, cval=0, mode='mirror')
+    coords = [factors[i] * (np.arange(d) + 0.5) - 0.5 for i, d in enumerate(output_shape)]
+    cmap = np.array(np.meshgrid(*coords, sparse=False, indexing='ij'))
+    out = ndi.map_coordinates(img, cmap, order=1, mode='mirror', cval=0)
+    return np.clip(out, img.min(), img.max())
+
+
+def get_seg_masks_compact(mask_logits, det_bboxes, det_labels, mask_thr_binary, scale_factor=1.0, class_agnostic=False):
+    """The per-detection part of FCNMaskHead3D.get_seg_masks (fcn_mask_head_3d.py:144-185): returns (int boxes,
+    list of uint8 (d, h, w) masks, 1-based labels).  mask_logits [n, classes, Dm, Hm, Wm]; sigmoid = oracle.sigmoid."""
+    probs = sigmoid(np.asarray(mask_logits, dtype=np.float32))
+    bboxes = np.asarray(det_bboxes, dtype=np.float32)[:, :6]
+    labels = np.asarray(det_labels) + 1
+    boxes, masks = [], []
+    for i in range(bboxes.shape[0]):
+        bbox = (bboxes[i, :] / scale_factor).astype(np.int32)
+        w = max(bbox[2] - bbox[0] + 1, 1)
+        h = max(bbox[3] - bbox[1] + 1, 1)
+        d = max(bbox[5] - bbox[4] + 1, 1)
+        m = probs[i, 0 if class_agnostic else labels[i]]
+        masks.append((resize_nd(m, (d, h, w)) > mask_thr_binary).astype(np.uint8))
+        boxes.append(bbox)
+    return np.asarray(boxes, dtype=np.int32).reshape(-1, 6), masks, labels
+
+
 def nms_cpu_2d(dets, thr):
     """nms_cpu_kernel (mmdet/ops/nms/src/nms_cpu.cpp:5-59): 2-D NMS over columns 0-3 ranked by column 4,
     suppressing ovr >= thr -- what the reference's CPU wrapper runs even on 7-column input."""

@@ -827,3 +827,41 @@ def test_roi_align_forward_slab_variant(oracle, dev):
             assert rel_err(out.cpu().numpy(), want) <= FWD_TOL
     finally:
         roi3d_b200._lib.set_tuning(0, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mask paste (sigmoid -> skimage-style resize to the box -> threshold) on the device
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_mask_paste_matches_resize_restatement(oracle, dev):
+    from roi3d_b200.models.mask_heads import get_seg_masks, paste_masks_compact
+    rng = np.random.default_rng(70)
+    n, ncls = 24, 3
+    logits = (3 * rng.standard_normal((n, ncls, 10, 14, 14))).astype(np.float32)
+    # smooth blobs make realistic masks; raw noise keeps many values near the threshold (harder test)
+    lo = np.stack([rng.uniform(0, 200, n), rng.uniform(0, 200, n), rng.uniform(0, 60, n)], 1)
+    sz = np.stack([rng.choice([1, 2, 3, 7, 14, 15, 33, 80], n), rng.choice([1, 3, 9, 14, 27, 50], n),
+                   rng.choice([1, 2, 5, 10, 11, 24], n)], 1)
+    det = np.stack([lo[:, 0], lo[:, 1], lo[:, 0] + sz[:, 0] - 0.3, lo[:, 1] + sz[:, 1] - 0.6, lo[:, 2],
+                    lo[:, 2] + sz[:, 2] - 0.5, rng.random(n)], 1).astype(np.float32)
+    labels = rng.integers(0, ncls - 1, n)
+    want_b, want_m, want_l = oracle.get_seg_masks_compact(logits, det, labels, 0.5)
+    got_b, got_m, got_l = paste_masks_compact(torch.from_numpy(logits).to(dev), torch.from_numpy(det).to(dev),
+                                              torch.from_numpy(labels).to(dev), 0.5)
+    assert np.array_equal(got_b, want_b) and np.array_equal(got_l, want_l)
+    total = diff = 0
+    for g, w in zip(got_m, want_m):
+        assert g.shape == w.shape and g.dtype == np.uint8
+        total += g.size
+        diff += int((g != w).sum())
+    # float64 arithmetic in scipy's order; a voxel can only differ when its value is within an ulp of the threshold
+    assert diff <= max(1, total // 100000), "%d of %d mask voxels differ" % (diff, total)
+    segs = get_seg_masks(torch.from_numpy(logits).to(dev), torch.from_numpy(det).to(dev),
+                         torch.from_numpy(labels).to(dev), dict(mask_thr_binary=0.5), (320, 320, 120), 1.0, True, ncls)
+    assert len(segs) == ncls - 1 and sum(len(s) for s in segs) == n
+    i0 = int(np.nonzero(labels == 0)[0][0])
+    vol = segs[0][0]
+    b = want_b[i0]
+    assert vol.shape == (120, 320, 320) and vol.sum() == got_m[i0].sum()
+    assert np.array_equal(vol[b[4]:b[4] + got_m[i0].shape[0], b[1]:b[1] + got_m[i0].shape[1],
+                              b[0]:b[0] + got_m[i0].shape[2]], got_m[i0])
