@@ -32,9 +32,9 @@ def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True):
     dev = dets.device
     keep = torch.empty((nseg, n_max), dtype=torch.int64, device=dev)
     keep_s = torch.empty((nseg, n_max), dtype=torch.int64, device=dev) if want_score_order else None
-    num = torch.zeros((nseg,), dtype=torch.int32, device=dev)
     if nseg == 0 or n_max == 0:
-        return keep, keep_s, num
+        return keep, keep_s, torch.zeros((nseg,), dtype=torch.int32, device=dev)
+    num = torch.empty((nseg,), dtype=torch.int32, device=dev)  # written for every segment by the sweep kernel
     if seg_counts is not None:
         assert seg_counts.dtype == torch.int32 and seg_counts.is_cuda and seg_counts.numel() == nseg
         seg_counts = seg_counts.contiguous()
