@@ -161,6 +161,46 @@ __global__ void __launch_bounds__(256) nms3d_mask_kernel(const SortedBox *__rest
   mask[((long long)seg * n_max + row) * cbm + cblk] = t;
 }
 
+// Same bit matrix with four times the parallelism, for few / small segments (n = 2000 alone fills only an eighth
+// of the GPU with the kernel above): one CTA per 64 x 64 tile, thread = (row, quarter of the tile's columns), the
+// four 16-bit partial words of a row are merged through shared memory.  grid (cb, cb, nseg).
+template <bool F64>
+__global__ void __launch_bounds__(256) nms3d_mask_q_kernel(const SortedBox *__restrict__ sorted,
+                                                           const int32_t *seg_counts, int n_max, float thr, double thr64,
+                                                           unsigned long long *__restrict__ mask) {
+  const int seg = blockIdx.z;
+  const int n = seg_counts ? min(max(seg_counts[seg], 0), n_max) : n_max;
+  const int cb = (n + 63) >> 6, cbm = (n_max + 63) >> 6;
+  const int rb = blockIdx.y, cblk = blockIdx.x;
+  if (rb >= cb || cblk >= cb || cblk < rb) return;
+  const SortedBox *sb = sorted + (long long)seg * n_max;
+  __shared__ SortedBox cols[64];
+  __shared__ unsigned part[4][64];
+  const int rl = threadIdx.x & 63, q = threadIdx.x >> 6;
+  if (threadIdx.x < 64) {
+    const int j = cblk * 64 + threadIdx.x;
+    if (j < n) cols[threadIdx.x] = sb[j];
+  }
+  __syncthreads();
+  const int row = rb * 64 + rl;
+  unsigned t = 0;
+  if (row < n) {
+    const SortedBox a = sb[row];
+    const float Sa = __fmul_rn(a.sxy, a.sz);
+    const int csize = min(64, n - cblk * 64);
+    const int j0 = max(q * 16, (cblk == rb) ? rl + 1 : 0), j1 = min(q * 16 + 16, csize);
+    for (int j = j0; j < j1; ++j)
+      if (F64 ? iou3d_f64_suppresses(a, cols[j], thr64) : iou3d_gt(a, Sa, cols[j], thr)) t |= 1u << (j - q * 16);
+  }
+  part[q][rl] = t;
+  __syncthreads();
+  if (q == 0 && row < n) {
+    const unsigned long long w = (unsigned long long)part[0][rl] | ((unsigned long long)part[1][rl] << 16) |
+                                 ((unsigned long long)part[2][rl] << 32) | ((unsigned long long)part[3][rl] << 48);
+    mask[((long long)seg * n_max + row) * cbm + cblk] = w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 3. greedy sweep + compaction.  One CTA (256 threads) per segment.
 // ------------------------------------------------------------------------------------------------
@@ -427,6 +467,8 @@ static NmsWorkspace carve(void *base, int nseg, int n_max) {
   return w;
 }
 
+int g_nms_mask_variant = 0;  // roi3d_set_tuning key 6: 1 = always the 4-tiles-per-CTA mask kernel
+
 }  // namespace roi3d
 
 using namespace roi3d;
@@ -462,7 +504,16 @@ static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, in
   nms3d_rank_kernel<<<dim3(ceil_div(n_max, 32), nseg), 256, 0, st>>>(dets_dev, seg_counts_dev, n_max, w.sorted,
                                                                       w.order);
   ROI3D_LAUNCH_CHECK();
-  if (f64)
+  // tiles of the upper triangle: with few of them, one tile per CTA (4x the threads) fills the GPU better
+  const long long tiles = (long long)nseg * cbm * (cbm + 1) / 2;
+  if (tiles <= 4096 && g_nms_mask_variant != 1) {
+    if (f64)
+      nms3d_mask_q_kernel<true><<<dim3(cbm, cbm, nseg), 256, 0, st>>>(w.sorted, seg_counts_dev, n_max, iou_thr, iou_thr64,
+                                                                      w.mask);
+    else
+      nms3d_mask_q_kernel<false><<<dim3(cbm, cbm, nseg), 256, 0, st>>>(w.sorted, seg_counts_dev, n_max, iou_thr, iou_thr64,
+                                                                       w.mask);
+  } else if (f64)
     nms3d_mask_kernel<true><<<dim3(ceil_div(cbm, 4), cbm, nseg), 256, 0, st>>>(w.sorted, seg_counts_dev, n_max, iou_thr,
                                                                                iou_thr64, w.mask);
   else

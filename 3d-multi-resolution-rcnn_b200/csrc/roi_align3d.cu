@@ -2334,6 +2334,7 @@ static int transpose_launch(const float *src, float *dst, int B, int rows, int c
 static int g_fwd_variant = 0;  // 0 = auto; see roi3d_set_tuning
 static int g_fwd_items_per_warp = 0;  // 0 = auto
 extern int g_host_pipeline_kb;        // host_api.cu
+extern int g_nms_mask_variant;        // nms3d.cu
 static int g_bwd_variant = 0;
 
 template <int PW, int ROWS, int CV, int NXU>
@@ -2692,6 +2693,7 @@ int roi3d_set_tuning(int key, int value) {
   else if (key == 1) g_bwd_variant = value;
   else if (key == 2) g_fwd_items_per_warp = value;
   else if (key == 4) g_host_pipeline_kb = value;
+  else if (key == 6) g_nms_mask_variant = value;
   else return ROI3D_EINVAL;
   return ROI3D_OK;
 }
