@@ -38,7 +38,11 @@ __device__ __forceinline__ float iou3d_torch(const GtBox &a, const float *b, flo
   const float h = fmaxf(__fadd_rn(__fsub_rn(fminf(a.y2, b[3]), fmaxf(a.y1, b[1])), 1.0f), 0.0f);
   const float d = fmaxf(__fadd_rn(__fsub_rn(fminf(a.z2, b[5]), fmaxf(a.z1, b[4])), 1.0f), 0.0f);
   const float inter = __fmul_rn(__fmul_rn(w, h), d);
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, area_b), inter));
+  const float uni = __fsub_rn(__fadd_rn(a.area, area_b), inter);
+  // disjoint boxes (the vast majority of pairs): 0 / uni is +0 for any positive union -- skip the IEEE division;
+  // degenerate unions (<= 0, NaN) still go through it so that -0 / NaN come out as torch computes them
+  if (inter == 0.0f && uni > 0.0f) return 0.0f;
+  return __fdiv_rn(inter, uni);
 }
 
 // order-preserving unsigned key of a float for atomicMax, and its inverse.  Degenerate boxes (x2 < x1 - 1) have
@@ -172,9 +176,13 @@ __global__ void __launch_bounds__(256) assign_pass2_kernel(const float *__restri
     for (int i = threadIdx.x; i < tk; i += 256) sgmax[i] = iou_from_key(gt_max_key[t0 + i]);
     __syncthreads();
     if (!live) continue;
+    const float my_max = max_overlaps[j];
     for (int i = 0; i < tk; ++i) {
       const float gm = sgmax[i];
       if (!(gm >= min_pos_iou)) continue;
+      // this box's IoU with gt i cannot exceed its own row maximum: nothing to recompute when that is below gm
+      // (a NaN row maximum compares false and falls through to the exact test)
+      if (my_max < gm) continue;
       if (iou3d_torch(sg[i], c, area) == gm) {
         if (assign_all) a = t0 + i + 1;
         else atomicMin(gt_argmax + t0 + i, j);
