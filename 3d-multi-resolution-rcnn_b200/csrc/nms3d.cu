@@ -47,6 +47,8 @@ __device__ __forceinline__ bool iou3d_gt(const SortedBox &a, float Sa, const Sor
   const float d = fmaxf(__fadd_rn(__fsub_rn(back, front), 1.0f), 0.0f);
   const float inter = __fmul_rn(__fmul_rn(w, h), d);
   const float uni = __fsub_rn(__fmaf_rn(b.sxy, b.sz, Sa), inter);
+  // disjoint boxes (most pairs): 0 / positive union = +0, no need for the IEEE division
+  if (inter == 0.0f && uni > 0.0f) return 0.0f > thr;
   return __fdiv_rn(inter, uni) > thr;
 }
 
@@ -68,7 +70,9 @@ __device__ __forceinline__ bool iou3d_f64_suppresses(const SortedBox &a, const S
   const double h = fmax(0.0, __dadd_rn(__dsub_rn(fmin(ay2, by2), fmax(ay1, by1)), 1.0));
   const double d = fmax(0.0, __dadd_rn(__dsub_rn(fmin(az2, bz2), fmax(az1, bz1)), 1.0));
   const double inter = __dmul_rn(__dmul_rn(w, h), d);
-  const double iou = __ddiv_rn(inter, __dsub_rn(__dadd_rn(va, vb), inter));
+  const double uni = __dsub_rn(__dadd_rn(va, vb), inter);
+  if (inter == 0.0 && uni > 0.0) return nan_in || !(0.0 <= thr);  // disjoint: iou is +0, skip the division
+  const double iou = __ddiv_rn(inter, uni);
   return nan_in || !(iou <= thr);
 }
 
