@@ -116,6 +116,7 @@ class RPNProposal3D(object):
             for b, d in zip(self.anchor_base_sizes, self.anchor_base_depths)
         ]
         self.num_anchors = len(anchor_ratios) * len(anchor_scales)
+        self._desc_cache = {}  # (segment lengths, flags, device) -> device descriptor tensors of get_bboxes
 
     def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg, rescale=False, img_meta_2=None, img_meta_3=None,
                    return_anchors=False):
@@ -156,8 +157,15 @@ class RPNProposal3D(object):
         # so issued later it would wait for every kernel already queued and serialise the CPU with the GPU.
         counts = [min(k, s.numel()) for s in segs]
         unsorted = [not (nms_pre > 0 and s.numel() > nms_pre) for s in segs]
-        seg_counts = torch.tensor(counts, dtype=torch.int32, device=dev)
-        use_idx = torch.tensor(unsorted, dtype=torch.uint8, device=dev) if any(unsorted) else None
+        ckey = (tuple(counts), tuple(unsorted), dev)
+        cached = self._desc_cache.get(ckey)
+        if cached is None:  # they depend on the level shapes and the config only: uploaded once per shape signature
+            cached = (torch.tensor(counts, dtype=torch.int32, device=dev),
+                      torch.tensor(unsorted, dtype=torch.uint8, device=dev) if any(unsorted) else None)
+            if len(self._desc_cache) > 16:
+                self._desc_cache.clear()
+            self._desc_cache[ckey] = cached
+        seg_counts, use_idx = cached
         # The reference only sorts a level when it has MORE than nms_pre anchors (rpn_head_3d.py:96,108-112);
         # a smaller level reaches NMS in anchor order, and `proposals[:nms_post]` then truncates in that order
         # (nms returns ascending input indices, nms_kernel.cu:253-256).  The top-k returns such segments whole in
