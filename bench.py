@@ -491,6 +491,18 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ex["c4_volumes_per_sec"] = Bv / dt
     ex["c4_anchors_scored_per_sec"] = Bv * sum(int(np.prod(d)) for d in dims4) / dt
     ex["c4_proposals_out"] = [int(p.shape[0]) for p in props]
+    head.cuda_graph = True   # same call with the launches captured once and replayed (stable activation buffers)
+    for _ in range(2):
+        head.get_bboxes(cls, reg, metas, cfg)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        props_g = head.get_bboxes(cls, reg, metas, cfg)
+    torch.cuda.synchronize()
+    ex["c4_proposal_path_8vol_cuda_graph_us"] = (time.perf_counter() - t0) / 5 * 1e6
+    ex["c4_cuda_graph_identical"] = bool(all(torch.equal(a, b) for a, b in zip(props, props_g)))
+    head.cuda_graph = False
+    del props_g
     del cls, reg, props
     torch.cuda.empty_cache()
     # C5: RoI stage of configs/3d-multi-resolution-rcnn.py (proposals -> bbox extractor 7x7x3 -> FC head -> decode ->

@@ -865,3 +865,30 @@ def test_mask_paste_matches_resize_restatement(oracle, dev):
     assert vol.shape == (120, 320, 320) and vol.sum() == got_m[i0].sum()
     assert np.array_equal(vol[b[4]:b[4] + got_m[i0].shape[0], b[1]:b[1] + got_m[i0].shape[1],
                               b[0]:b[0] + got_m[i0].shape[2]], got_m[i0])
+
+
+@pytest.mark.gpu
+def test_rpn_get_bboxes_cuda_graph_replay(dev):
+    """cuda_graph=True: the captured path returns the eager path's proposals, also after the input buffers have been
+    refilled in place (same addresses, new values) and for a second set of buffers."""
+    from roi3d_b200 import RPNProposal3D
+    dims = [(8, 16, 16), (4, 8, 8), (2, 4, 4)]
+    head = RPNProposal3D(anchor_scales=[2], anchor_depth_scales=[2], anchor_ratios=[1.0], anchor_strides=[4, 8, 16],
+                         anchor_strides_depth=[2, 4, 8])
+    cfg = dict(nms_pre=300, nms_post=100, max_num=150, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
+    metas = [dict(img_shape=(64, 64, 3, 16), scale_factor=1.0)] * 2
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    cls = [2 * torch.randn((2, 1) + d, device=dev, generator=g) for d in dims]
+    reg = [0.1 * torch.randn((2, 6) + d, device=dev, generator=g) for d in dims]
+    for rnd in range(3):
+        head.cuda_graph = False
+        want = head.get_bboxes(cls, reg, metas, cfg)
+        head.cuda_graph = True
+        got = head.get_bboxes(cls, reg, metas, cfg)
+        assert len(got) == len(want) == 2
+        for a, b in zip(got, want):
+            assert torch.equal(a, b) and a.shape[0] > 0
+        for t in cls + reg:   # new values at the same addresses: the replay must see them
+            t.copy_(torch.randn(t.shape, device=dev, generator=g) * (2 if t.shape[1] == 1 else 0.1))
+    assert len(head._graphs) == 1

@@ -29,6 +29,18 @@ for _ in range(10):
     out = head.get_bboxes(cls, reg, metas, cfg)
 torch.cuda.synchronize()
 print("wall per call us", (time.perf_counter() - t0) / 10 * 1e6, "props", [int(o.shape[0]) for o in out][:3])
+head.cuda_graph = True
+for _ in range(3):
+    head.get_bboxes(cls, reg, metas, cfg)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(10):
+    out = head.get_bboxes(cls, reg, metas, cfg)
+torch.cuda.synchronize()
+print("wall per call us (CUDA graph replay)", (time.perf_counter() - t0) / 10 * 1e6)
+head.cuda_graph = False
+if len(sys.argv) > 2:
+    sys.exit(0)
 from torch.profiler import profile, ProfilerActivity  # noqa: E402
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
