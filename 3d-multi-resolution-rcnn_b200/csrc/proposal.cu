@@ -40,7 +40,7 @@ struct SegState {           // device, per segment
   int k_rem;                // how many keys still to take inside the current prefix
   int k_take;               // min(k, len)
   int cand_count;
-  int pad;
+  int bnd_count;            // keys inside the boundary bin after the second digit pass (topk_split_kernel)
 };
 
 __device__ __forceinline__ unsigned okey(float s) {
@@ -75,15 +75,21 @@ __device__ __forceinline__ void pass_geometry(int pass, int &shift, int &bits) {
   shift = sh[pass], bits = bw[pass];
 }
 
+constexpr int kBndCap = 4096;  // boundary keys kept per segment after two digit passes; more (mass ties) -> full passes
+
+// bnd != nullptr (passes 2..5): if the segment's boundary bin fitted kBndCap keys, the pass runs over those keys only
+// instead of re-reading and re-scoring the whole segment.
 template <bool SIGMOID>
 __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__restrict__ scores, const SegTable tab,
                                                                  const SegState *__restrict__ state, int pass,
-                                                                 unsigned *__restrict__ hist /*[nseg][kBins]*/) {
+                                                                 unsigned *__restrict__ hist /*[nseg][kBins]*/,
+                                                                 const unsigned long long *__restrict__ bnd) {
   const int seg = blockIdx.y;
   const SegDesc d = tab.s[seg];
-  const long long base = (long long)blockIdx.x * kItemsPerCta;
-  if (base >= (long long)d.len) return;
   const SegState st = state[seg];
+  const bool use_b = bnd != nullptr && st.bnd_count <= kBndCap;
+  const long long len = use_b ? (long long)st.bnd_count : (long long)d.len;
+  if ((long long)blockIdx.x * kItemsPerCta >= len) return;
   if (st.k_take <= 0) return;
   __shared__ unsigned h[kBins];
   for (int i = threadIdx.x; i < kBins; i += kTopkThreads) h[i] = 0;
@@ -94,20 +100,30 @@ __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__
   const bool low_word = pass >= 3;
   const unsigned pre_hi = (unsigned)(st.prefix >> 32);
   const float *src = scores + d.off;
+  const unsigned long long *bsrc = bnd + (long long)seg * kBndCap;
+  // grid-stride over the segment: the boundary passes are launched with a few CTAs per segment (the usual case
+  // needs one); a segment that overflowed the boundary buffer is then walked by those few CTAs
+  for (long long base = (long long)blockIdx.x * kItemsPerCta; base < len; base += (long long)gridDim.x * kItemsPerCta)
 #pragma unroll 4
   for (int it = 0; it < kItemsPerThread; ++it) {
     const long long m = base + (long long)it * kTopkThreads + threadIdx.x;
-    if (m < (long long)d.len) {
-      float v = __ldg(src + m);
-      if (SIGMOID) v = sigmoid_ref(v);
-      const unsigned kh = okey(v);
+    if (m < len) {
+      unsigned kh, kl_b = 0;
+      if (use_b) {
+        const unsigned long long key = bsrc[m];
+        kh = (unsigned)(key >> 32), kl_b = (unsigned)key;
+      } else {
+        float v = __ldg(src + m);
+        if (SIGMOID) v = sigmoid_ref(v);
+        kh = okey(v);
+      }
       if (!low_word) {
         // participates iff the already-decided high digits match
         const int decided = 32 - (shift - 32) - bits;  // number of decided bits of the score word
         const bool match = decided == 0 || (kh >> (32 - decided)) == (pre_hi >> (32 - decided));
         if (match) atomicAdd(&h[(kh >> (shift - 32)) & dmask], 1u);
       } else if (kh == pre_hi) {
-        const unsigned kl = ~logical_index(d, (unsigned)m);
+        const unsigned kl = use_b ? kl_b : ~logical_index(d, (unsigned)m);
         const unsigned pre_lo = (unsigned)st.prefix;
         const int decided = 32 - shift - bits;
         const bool match = decided == 0 || (kl >> (32 - decided)) == (pre_lo >> (32 - decided));
@@ -175,14 +191,58 @@ __global__ void __launch_bounds__(256) topk_scan_kernel(unsigned *__restrict__ h
 template <bool SIGMOID>
 __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const float *__restrict__ scores,
                                                                     const SegTable tab, SegState *__restrict__ state,
-                                                                    int k, unsigned long long *__restrict__ cand) {
+                                                                    int k, unsigned long long *__restrict__ cand,
+                                                                    const unsigned long long *__restrict__ bnd) {
+  const int seg = blockIdx.y;
+  const SegDesc d = tab.s[seg];
+  const long long base = (long long)blockIdx.x * kItemsPerCta;
+  const SegState st = state[seg];
+  const bool use_b = bnd != nullptr && st.bnd_count <= kBndCap;  // keys above the boundary bin are in cand already
+  const long long len = use_b ? (long long)st.bnd_count : (long long)d.len;
+  if (base >= len) return;
+  if (st.k_take <= 0) return;
+  const unsigned thr_hi = (unsigned)(st.prefix >> 32);
+  const float *src = scores + d.off;
+  const unsigned long long *bsrc = bnd + (long long)seg * kBndCap;
+  for (long long base2 = base; base2 < len; base2 += (long long)gridDim.x * kItemsPerCta)
+#pragma unroll 4
+  for (int it = 0; it < kItemsPerThread; ++it) {
+    const long long m = base2 + (long long)it * kTopkThreads + threadIdx.x;
+    if (m < len) {
+      unsigned long long key;
+      if (use_b) {
+        key = bsrc[m];
+      } else {
+        float v = __ldg(src + m);
+        if (SIGMOID) v = sigmoid_ref(v);
+        const unsigned kh = okey(v);
+        if (kh < thr_hi) continue;
+        key = ((unsigned long long)kh << 32) | (unsigned)~logical_index(d, (unsigned)m);
+      }
+      if (key >= st.prefix) {
+        const int pos = atomicAdd(&state[seg].cand_count, 1);
+        if (pos < k) cand[(long long)seg * k + pos] = key;
+      }
+    }
+  }
+}
+
+// After the first two digit passes (22 bits of the score word decided): one pass over the whole segment that
+// (a) appends every key ABOVE the boundary bin to the result candidates -- they are certainly selected -- and
+// (b) copies the keys INSIDE the boundary bin to a small buffer, on which the remaining four digit passes and the
+// final collect run.  Five of the seven full passes over the scores disappear.
+template <bool SIGMOID>
+__global__ void __launch_bounds__(kTopkThreads) topk_split_kernel(const float *__restrict__ scores, const SegTable tab,
+                                                                  SegState *__restrict__ state, int k,
+                                                                  unsigned long long *__restrict__ cand,
+                                                                  unsigned long long *__restrict__ bnd) {
   const int seg = blockIdx.y;
   const SegDesc d = tab.s[seg];
   const long long base = (long long)blockIdx.x * kItemsPerCta;
   if (base >= (long long)d.len) return;
   const SegState st = state[seg];
   if (st.k_take <= 0) return;
-  const unsigned thr_hi = (unsigned)(st.prefix >> 32);
+  const unsigned p22 = (unsigned)(st.prefix >> 42);  // the 22 decided bits
   const float *src = scores + d.off;
 #pragma unroll 4
   for (int it = 0; it < kItemsPerThread; ++it) {
@@ -191,15 +251,25 @@ __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const float 
       float v = __ldg(src + m);
       if (SIGMOID) v = sigmoid_ref(v);
       const unsigned kh = okey(v);
-      if (kh >= thr_hi) {
+      const unsigned h22 = kh >> 10;
+      if (h22 >= p22) {
         const unsigned long long key = ((unsigned long long)kh << 32) | (unsigned)~logical_index(d, (unsigned)m);
-        if (key >= st.prefix) {
+        if (h22 > p22) {
           const int pos = atomicAdd(&state[seg].cand_count, 1);
           if (pos < k) cand[(long long)seg * k + pos] = key;
+        } else {
+          const int pos = atomicAdd(&state[seg].bnd_count, 1);
+          if (pos < kBndCap) bnd[(long long)seg * kBndCap + pos] = key;
         }
       }
     }
   }
+}
+
+// Boundary bin larger than the buffer (mass ties): forget the split, the full-data passes and collect take over.
+__global__ void topk_after_split_kernel(SegState *state, int nseg) {
+  const int s = threadIdx.x;
+  if (s < nseg && state[s].bnd_count > kBndCap) state[s].cand_count = 0;
 }
 
 // rank-by-counting sort of the (unique) candidate keys, descending.  grid (ceil(k/256), nseg).
@@ -235,6 +305,46 @@ __global__ void __launch_bounds__(256) topk_sort_kernel(const unsigned long long
   }
 }
 
+// Same ordering by a bitonic sort in shared memory, one CTA per segment, for k <= kBitonicMax (rank-by-counting is
+// O(k^2): 4 M key compares per segment at k = 2000).  Unused slots hold key 0, which sorts last in either order.
+constexpr int kBitonicMax = 4096;
+__global__ void __launch_bounds__(1024) topk_bitonic_kernel(const unsigned long long *__restrict__ cand,
+                                                            const SegState *__restrict__ state, const SegTable tab,
+                                                            int small_by_index, int k, int npow2,
+                                                            int64_t *__restrict__ out_idx, float *__restrict__ out_val) {
+  extern __shared__ __align__(16) unsigned long long sk[];
+  const int seg = blockIdx.x, tid = threadIdx.x;
+  const int n = state[seg].k_take;
+  if (n <= 0) return;
+  const bool by_index = small_by_index && tab.s[seg].len <= (unsigned)k;
+  const unsigned long long *c = cand + (long long)seg * k;
+  // sort key: the 64-bit key itself (descending), or only its low word = ~index (descending = ascending index)
+  for (int i = tid; i < npow2; i += 1024) {
+    unsigned long long v = i < n ? c[i] : 0ULL;
+    if (by_index && i < n) v = ((unsigned long long)(unsigned)v << 32) | (v >> 32);  // swap words: index word leads
+    sk[i] = v;
+  }
+  __syncthreads();
+  for (int size = 2; size <= npow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (npow2 >> 1); t += 1024) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;  // descending blocks first -> whole array descending at the end
+        const unsigned long long a = sk[lo], b = sk[hi];
+        if (desc ? (a < b) : (a > b)) sk[lo] = b, sk[hi] = a;
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += 1024) {
+    unsigned long long v = sk[i];
+    if (by_index) v = ((unsigned long long)(unsigned)v << 32) | (v >> 32);
+    out_idx[(long long)seg * k + i] = (int64_t)(unsigned)~(unsigned)v;
+    out_val[(long long)seg * k + i] = okey_inv((unsigned)(v >> 32));
+  }
+}
+
 __global__ void topk_init_kernel(SegState *state, const SegTable tab, int nseg, int k) {
   const int s = threadIdx.x;
   if (s >= nseg) return;
@@ -243,7 +353,7 @@ __global__ void topk_init_kernel(SegState *state, const SegTable tab, int nseg, 
   st.k_take = (int)min((unsigned)k, tab.s[s].len);
   st.k_rem = st.k_take;
   st.cand_count = 0;
-  st.pad = 0;
+  st.bnd_count = 0;
   state[s] = st;
 }
 
@@ -464,7 +574,8 @@ static const size_t kHistBytes = (size_t)kMaxSeg * kBins * sizeof(unsigned);  //
 size_t roi3d_topk_workspace_bytes(int nseg, int k) {
   if (nseg <= 0 || k <= 0) return 256;
   const size_t ns = (size_t)(nseg < kMaxSeg ? nseg : kMaxSeg);
-  return kStateBytes + kHistBytes + ns * (size_t)k * sizeof(unsigned long long);
+  return kStateBytes + kHistBytes + ns * (size_t)k * sizeof(unsigned long long) +
+         ns * (size_t)kBndCap * sizeof(unsigned long long);
 }
 
 int roi3d_topk_segmented(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
@@ -512,28 +623,49 @@ int roi3d_topk_segmented_ex(const float *scores_dev, const int64_t *seg_off, con
     SegState *state = reinterpret_cast<SegState *>(b);
     unsigned *hist = reinterpret_cast<unsigned *>(b + kStateBytes);
     unsigned long long *cand = reinterpret_cast<unsigned long long *>(b + kStateBytes + kHistBytes);
+    unsigned long long *bnd = cand + (size_t)(nseg < kMaxSeg ? nseg : kMaxSeg) * k;
     topk_init_kernel<<<1, kMaxSeg, 0, st>>>(state, tab, ns, k);
     ROI3D_LAUNCH_CHECK();
     if (maxlen == 0) continue;
     ROI3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)ns * kBins * sizeof(unsigned), st));
     const dim3 grid((unsigned)ceil_div_ll(maxlen, kItemsPerCta), ns);
+    const dim3 grid2((unsigned)(grid.x < 8 ? grid.x : 8), ns);  // boundary passes: see topk_hist_kernel
     for (int pass = 0; pass < 6; ++pass) {
+      const unsigned long long *b2 = pass >= 2 ? bnd : nullptr;
+      const dim3 g = pass >= 2 ? grid2 : grid;
       if (apply_sigmoid)
-        topk_hist_kernel<true><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist);
+        topk_hist_kernel<true><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2);
       else
-        topk_hist_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist);
+        topk_hist_kernel<false><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2);
       ROI3D_LAUNCH_CHECK();
       topk_scan_kernel<<<ns, 256, 0, st>>>(hist, state, pass);
       ROI3D_LAUNCH_CHECK();
+      if (pass == 1) {  // 22 bits decided: split off the certain keys and the boundary bin
+        if (apply_sigmoid)
+          topk_split_kernel<true><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd);
+        else
+          topk_split_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd);
+        ROI3D_LAUNCH_CHECK();
+        topk_after_split_kernel<<<1, kMaxSeg, 0, st>>>(state, ns);
+        ROI3D_LAUNCH_CHECK();
+      }
     }
     if (apply_sigmoid)
-      topk_collect_kernel<true><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand);
+      topk_collect_kernel<true><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd);
     else
-      topk_collect_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand);
+      topk_collect_kernel<false><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd);
     ROI3D_LAUNCH_CHECK();
-    topk_sort_kernel<<<dim3(ceil_div(k, 256), ns), 256, 0, st>>>(cand, state, tab, small_segments_in_index_order, k,
-                                                                out_idx_dev + (size_t)s0 * k,
-                                                                out_val_dev + (size_t)s0 * k);
+    if (k <= kBitonicMax) {
+      int npow2 = 2;
+      while (npow2 < k) npow2 <<= 1;
+      topk_bitonic_kernel<<<ns, 1024, (size_t)npow2 * sizeof(unsigned long long), st>>>(
+          cand, state, tab, small_segments_in_index_order, k, npow2, out_idx_dev + (size_t)s0 * k,
+          out_val_dev + (size_t)s0 * k);
+    } else {
+      topk_sort_kernel<<<dim3(ceil_div(k, 256), ns), 256, 0, st>>>(cand, state, tab, small_segments_in_index_order, k,
+                                                                  out_idx_dev + (size_t)s0 * k,
+                                                                  out_val_dev + (size_t)s0 * k);
+    }
     ROI3D_LAUNCH_CHECK();
   }
   return ROI3D_OK;

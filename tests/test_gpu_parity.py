@@ -345,6 +345,24 @@ def test_topk_small_segments(oracle, dev):
             assert np.array_equal(idx[s], oracle.topk(seg, k))
 
 
+def test_topk_mass_ties_overflow_the_boundary_buffer(oracle, dev):
+    """More equal scores than the 4096-key boundary buffer holds: the full-data passes take over; order stays
+    'descending score, ties to the lower index'."""
+    from roi3d_b200.models.anchor_heads import topk_segmented
+    rng = np.random.default_rng(45)
+    segs = [np.full(100000, 0.5, np.float32),
+            rng.choice(np.array([0.25, 0.5, 0.75], np.float32), 200000),
+            rng.standard_normal(50000).astype(np.float32)]
+    maps = [np.full((1, 10, 40, 50), 1.5, np.float32)]               # permuted + sigmoid, all equal
+    for k in (2000, 7):
+        idx, val = topk_segmented([torch.from_numpy(s).to(dev) for s in segs], k)
+        for s, seg in enumerate(segs):
+            want = oracle.topk(seg, k)
+            assert np.array_equal(idx[s].cpu().numpy(), want) and np.array_equal(val[s].cpu().numpy(), seg[want])
+        idx, val = topk_segmented([torch.from_numpy(m).to(dev) for m in maps], k, apply_sigmoid=True, permute_adhw=True)
+        assert np.array_equal(idx[0].cpu().numpy(), np.arange(k))      # ties: lowest LOGICAL index first
+
+
 def test_topk_permuted_sigmoid(oracle, dev):
     from roi3d_b200.models.anchor_heads import topk_segmented
     rng = np.random.default_rng(41)

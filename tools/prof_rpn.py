@@ -24,11 +24,14 @@ metas = [dict(img_shape=(512, 512, 3, 160), scale_factor=1.0)] * Bv
 for _ in range(3):
     head.get_bboxes(cls, reg, metas, cfg)
 torch.cuda.synchronize()
-t0 = time.perf_counter()
-for _ in range(10):
-    out = head.get_bboxes(cls, reg, metas, cfg)
-torch.cuda.synchronize()
-print("wall per call us", (time.perf_counter() - t0) / 10 * 1e6, "props", [int(o.shape[0]) for o in out][:3])
+for rep in range(3):
+    ts = []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        out = head.get_bboxes(cls, reg, metas, cfg)
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e6)
+    print("wall per call us", sum(ts) / len(ts), "median", sorted(ts)[5], "max", max(ts), "props", [int(o.shape[0]) for o in out][:3])
 head.cuda_graph = True
 for _ in range(3):
     head.get_bboxes(cls, reg, metas, cfg)
