@@ -81,11 +81,14 @@ __device__ __forceinline__ bool iou3d_f64_suppresses(const SortedBox &a, const S
 //    (each warp scans one slice with warp-uniform loads; partial ranks are summed through smem).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nms3d_rank_kernel(const float *__restrict__ dets, const int32_t *seg_counts,
-                                                         int n_max, SortedBox *__restrict__ sorted,
-                                                         int32_t *__restrict__ order) {
+                                                         const unsigned char *__restrict__ presorted, int n_max,
+                                                         SortedBox *__restrict__ sorted, int32_t *__restrict__ order) {
   const int seg = blockIdx.y;
   const int n = seg_counts ? min(max(seg_counts[seg], 0), n_max) : n_max;
   if ((int)(blockIdx.x * 32) >= n) return;
+  // the caller vouches that this segment's rows already are in (score descending, index ascending) order -- e.g.
+  // rows straight out of the segmented top-k: rank = row, only the sorted records are built
+  const bool identity = presorted != nullptr && presorted[seg] != 0;
   const float *d = dets + (long long)seg * n_max * 7;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) nms3d_rank_kernel(const float *__restrict
   constexpr int kTile = 2048;
   __shared__ unsigned keys[kTile];
   int rank = 0;
-  for (int t0 = 0; t0 < n; t0 += kTile) {
+  for (int t0 = 0; t0 < (identity ? 0 : n); t0 += kTile) {
     const int tn = min(kTile, n - t0);
     __syncthreads();
 #pragma unroll
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(256) nms3d_rank_kernel(const float *__restrict
     rank = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) rank += part[q][lane];
+    if (identity) rank = i;
     const float *b = d + (long long)i * 7;
     SortedBox sb;
     sb.x1 = b[0], sb.y1 = b[1], sb.x2 = b[2], sb.y2 = b[3], sb.z1 = b[4], sb.z2 = b[5];
@@ -484,7 +488,8 @@ size_t roi3d_nms3d_workspace_bytes(int nseg, int n_max) {
   return carve(nullptr, nseg, n_max).bytes;
 }
 
-static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, float iou_thr,
+static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, const uint8_t *presorted_dev, int nseg,
+                        int n_max, float iou_thr,
                         double iou_thr64, bool f64, int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev,
                         void *workspace_dev, size_t workspace_bytes, void *stream) {
   ROI3D_CHECK_ARG(nseg >= 0 && n_max >= 0, "bad sizes nseg=%d n_max=%d", nseg, n_max);
@@ -505,8 +510,8 @@ static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, in
     return ROI3D_ENOMEM;
   }
   const int cbm = (n_max + 63) / 64;
-  nms3d_rank_kernel<<<dim3(ceil_div(n_max, 32), nseg), 256, 0, st>>>(dets_dev, seg_counts_dev, n_max, w.sorted,
-                                                                      w.order);
+  nms3d_rank_kernel<<<dim3(ceil_div(n_max, 32), nseg), 256, 0, st>>>(dets_dev, seg_counts_dev, presorted_dev, n_max,
+                                                                      w.sorted, w.order);
   ROI3D_LAUNCH_CHECK();
   // tiles of the upper triangle: with few of them, one tile per CTA (4x the threads) fills the GPU better
   const long long tiles = (long long)nseg * cbm * (cbm + 1) / 2;
@@ -537,14 +542,21 @@ static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, in
 int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, float iou_thr,
                         int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev, void *workspace_dev,
                         size_t workspace_bytes, void *stream) {
-  return nms3d_launch(dets_dev, seg_counts_dev, nseg, n_max, iou_thr, 0.0, false, keep_dev, keep_by_score_dev,
+  return nms3d_launch(dets_dev, seg_counts_dev, nullptr, nseg, n_max, iou_thr, 0.0, false, keep_dev, keep_by_score_dev,
                       num_keep_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int roi3d_nms3d_batched_presorted(const float *dets_dev, const int32_t *seg_counts_dev, const uint8_t *presorted_dev,
+                                  int nseg, int n_max, float iou_thr, int64_t *keep_dev, int64_t *keep_by_score_dev,
+                                  int32_t *num_keep_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
+  return nms3d_launch(dets_dev, seg_counts_dev, presorted_dev, nseg, n_max, iou_thr, 0.0, false, keep_dev,
+                      keep_by_score_dev, num_keep_dev, workspace_dev, workspace_bytes, stream);
 }
 
 int roi3d_nms3d_eval_batched(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, double iou_thr,
                              int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev, void *workspace_dev,
                              size_t workspace_bytes, void *stream) {
-  return nms3d_launch(dets_dev, seg_counts_dev, nseg, n_max, 0.0f, iou_thr, true, keep_dev, keep_by_score_dev,
+  return nms3d_launch(dets_dev, seg_counts_dev, nullptr, nseg, n_max, 0.0f, iou_thr, true, keep_dev, keep_by_score_dev,
                       num_keep_dev, workspace_dev, workspace_bytes, stream);
 }
 

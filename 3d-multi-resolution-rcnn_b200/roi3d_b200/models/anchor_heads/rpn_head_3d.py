@@ -198,11 +198,12 @@ class RPNProposal3D(object):
         cached = self._desc_cache.get(ckey)
         if cached is None:  # they depend on the level shapes and the config only: uploaded once per shape signature
             cached = (torch.tensor(counts, dtype=torch.int32, device=dev),
-                      torch.tensor(unsorted, dtype=torch.uint8, device=dev) if any(unsorted) else None)
+                      torch.tensor(unsorted, dtype=torch.uint8, device=dev) if any(unsorted) else None,
+                      torch.tensor([not u for u in unsorted], dtype=torch.uint8, device=dev))
             if len(self._desc_cache) > 16:
                 self._desc_cache.clear()
             self._desc_cache[ckey] = cached
-        seg_counts, use_idx = cached
+        seg_counts, use_idx, presorted = cached  # top-k'd levels reach the NMS already in score order
         # The reference only sorts a level when it has MORE than nms_pre anchors (rpn_head_3d.py:96,108-112);
         # a smaller level reaches NMS in anchor order, and `proposals[:nms_post]` then truncates in that order
         # (nms returns ascending input indices, nms_kernel.cu:253-256).  The top-k returns such segments whole in
@@ -233,7 +234,7 @@ class RPNProposal3D(object):
                 stds.ctypes.data, dets.data_ptr(), stream_ptr()))
 
         # 3. one batched NMS; kept rows in descending-score order
-        keep_i, keep_s, num_keep = nms3d_batched(dets, seg_counts, nms_thr, want_score_order=True)
+        keep_i, keep_s, num_keep = nms3d_batched(dets, seg_counts, nms_thr, want_score_order=True, presorted=presorted)
 
         # 4. proposals[:nms_post] per segment (rpn_head_3d.py:135), per image cat in level order, topk(max_num)
         #    (:139-148): one collect kernel, one segmented top-k, one row gather

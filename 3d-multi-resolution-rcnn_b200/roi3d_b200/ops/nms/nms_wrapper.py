@@ -21,9 +21,11 @@ from ... import _lib
 from ..._util import check_cuda_f32, scratch, stream_ptr
 
 
-def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True):
+def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=None):
     """Batched device NMS.  dets [nseg, n_max, 7] fp32 CUDA; seg_counts int32 [nseg] CUDA or None.
 
+    presorted: optional uint8 [nseg] CUDA tensor, 1 where the segment's rows already are in descending-score order
+    (ties by ascending row), e.g. rows straight out of the segmented top-k: the ranking pass is skipped for them.
     Returns (keep [nseg, n_max] int64, keep_by_score or None, num_keep [nseg] int32); nothing syncs.
     """
     check_cuda_f32(dets, "dets", ndim=3, last=7)
@@ -41,8 +43,9 @@ def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True):
     nbytes = _lib.lib.roi3d_nms3d_workspace_bytes(nseg, n_max)
     _buf, ws = scratch(dev, nbytes, "nms")
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib.roi3d_nms3d_batched(
-            dets.data_ptr(), None if seg_counts is None else seg_counts.data_ptr(), nseg, n_max, float(iou_thr),
+        _lib.check(_lib.lib.roi3d_nms3d_batched_presorted(
+            dets.data_ptr(), None if seg_counts is None else seg_counts.data_ptr(),
+            None if presorted is None else presorted.data_ptr(), nseg, n_max, float(iou_thr),
             keep.data_ptr(), None if keep_s is None else keep_s.data_ptr(), num.data_ptr(), ws, nbytes,
             stream_ptr()))
     return keep, keep_s, num

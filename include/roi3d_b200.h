@@ -143,6 +143,13 @@ int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, in
                         float iou_thr, int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev,
                         void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Same as roi3d_nms3d_batched; presorted_dev (optional uint8 [nseg]) marks segments whose rows the caller already
+ * holds in (score descending, equal scores by ascending row) order -- rows straight out of roi3d_topk_segmented --
+ * so the ranking pass is skipped for them.  A segment marked presorted that is not gives undefined keep lists. */
+int roi3d_nms3d_batched_presorted(const float *dets_dev, const int32_t *seg_counts_dev, const uint8_t *presorted_dev,
+                                  int nseg, int n_max, float iou_thr, int64_t *keep_dev, int64_t *keep_by_score_dev,
+                                  int32_t *num_keep_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* Evaluation-time flavour of the same NMS.
  * Replaces: nms_3d_python, mmdet/core/evaluation/coco_utils.py:245-282 (numpy float64, per volume, called from
  *   apply_nms :306-332 with thr 0.1): IoU evaluated in float64 in numpy's operation order on the fp32 boxes,

@@ -910,3 +910,23 @@ def test_rpn_get_bboxes_cuda_graph_replay(dev):
         for t in cls + reg:   # new values at the same addresses: the replay must see them
             t.copy_(torch.randn(t.shape, device=dev, generator=g) * (2 if t.shape[1] == 1 else 0.1))
     assert len(head._graphs) == 1
+
+
+@pytest.mark.gpu
+def test_nms_presorted_segments_skip_the_ranking(oracle, dev):
+    """Segments flagged presorted (rows already in descending-score order, ties by row) give the same keep lists as the
+    ranked path; unflagged segments in the same call are still ranked."""
+    from roi3d_b200.ops import nms3d_batched
+    a = synth.c1_boxes(1500, seed=3)
+    a = a[np.argsort(-a[:, 6], kind="stable")]
+    a[100:140, 6] = a[100, 6]                       # a run of equal scores: order by row
+    b = synth.c1_boxes(1500, seed=4)                # not sorted
+    dets = torch.from_numpy(np.stack([a, b])).to(dev)
+    flags = torch.tensor([1, 0], dtype=torch.uint8, device=dev)
+    k0, s0, n0 = nms3d_batched(dets, None, 0.5)
+    k1, s1, n1 = nms3d_batched(dets, None, 0.5, presorted=flags)
+    assert torch.equal(n0, n1)
+    for seg in range(2):
+        m = int(n0[seg])
+        assert torch.equal(k0[seg, :m], k1[seg, :m]) and torch.equal(s0[seg, :m], s1[seg, :m])
+    assert np.array_equal(k1[0, :int(n1[0])].cpu().numpy(), oracle.nms3d(a, 0.5))
