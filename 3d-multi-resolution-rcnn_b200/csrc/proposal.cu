@@ -75,6 +75,53 @@ __device__ __forceinline__ void pass_geometry(int pass, int &shift, int &bits) {
   shift = sh[pass], bits = bw[pass];
 }
 
+// Pick the digit where the descending cumulative count crosses k_rem (256 threads; run by the LAST CTA of a
+// segment's histogram pass, see topk_hist_kernel).
+__device__ __forceinline__ void scan_segment(unsigned *__restrict__ hist, SegState *__restrict__ state, int seg, int pass) {
+  SegState st = state[seg];
+  unsigned *g = hist + (long long)seg * kBins;
+  __shared__ unsigned part[256];
+  __shared__ int s_digit, s_krem;
+  // thread t owns bins [8t, 8t+8) ; descending order means high bins first
+  unsigned loc[8], sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    loc[i] = __ldcg(g + threadIdx.x * 8 + i);  // written by other CTAs' atomics: read through L2
+    sum += loc[i];
+    g[threadIdx.x * 8 + i] = 0;  // leave the histogram clean for the next pass
+  }
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  // suffix sum over threads above me (256 entries; simple serial-in-smem log scan)
+  for (int o = 1; o < 256; o <<= 1) {
+    unsigned v = (threadIdx.x + o < 256) ? part[threadIdx.x + o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const unsigned above = part[threadIdx.x] - sum;  // keys in bins strictly above my 8 bins
+  const unsigned k = (unsigned)st.k_rem;
+  if (above < k && above + sum >= k) {
+    unsigned cum = above;
+    for (int i = 7; i >= 0; --i) {
+      if (cum + loc[i] >= k) {
+        s_digit = threadIdx.x * 8 + i;
+        s_krem = (int)(k - cum);
+        break;
+      }
+      cum += loc[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int shift, bits;
+    pass_geometry(pass, shift, bits);
+    st.prefix |= (unsigned long long)(unsigned)s_digit << shift;
+    st.k_rem = s_krem;
+    state[seg] = st;
+  }
+}
+
 constexpr int kBndCap = 4096;  // boundary keys kept per segment after two digit passes; more (mass ties) -> full passes
 
 // bnd != nullptr (passes 2..5): if the segment's boundary bin fitted kBndCap keys, the pass runs over those keys only
@@ -83,7 +130,8 @@ template <bool SIGMOID>
 __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__restrict__ scores, const SegTable tab,
                                                                  const SegState *__restrict__ state, int pass,
                                                                  unsigned *__restrict__ hist /*[nseg][kBins]*/,
-                                                                 const unsigned long long *__restrict__ bnd) {
+                                                                 const unsigned long long *__restrict__ bnd,
+                                                                 int *__restrict__ tickets) {
   const int seg = blockIdx.y;
   const SegDesc d = tab.s[seg];
   const SegState st = state[seg];
@@ -137,54 +185,20 @@ __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__
     const unsigned c = h[i];
     if (c) atomicAdd(&g[i], c);
   }
-}
-
-// One CTA per segment: pick the digit where the descending cumulative count crosses k_rem.
-__global__ void __launch_bounds__(256) topk_scan_kernel(unsigned *__restrict__ hist, SegState *__restrict__ state,
-                                                        int pass) {
-  const int seg = blockIdx.x;
-  SegState st = state[seg];
-  if (st.k_take <= 0) return;
-  unsigned *g = hist + (long long)seg * kBins;
-  __shared__ unsigned part[256];
-  __shared__ int s_digit, s_krem;
-  // thread t owns bins [8t, 8t+8) ; descending order means high bins first
-  unsigned loc[8], sum = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    loc[i] = g[threadIdx.x * 8 + i];
-    sum += loc[i];
-    g[threadIdx.x * 8 + i] = 0;  // leave the histogram clean for the next pass
-  }
-  part[threadIdx.x] = sum;
+  // the last CTA of this segment to get here scans the finished histogram (no separate scan launch)
+  __threadfence();
   __syncthreads();
-  // suffix sum over threads above me (256 entries; simple serial-in-smem log scan)
-  for (int o = 1; o < 256; o <<= 1) {
-    unsigned v = (threadIdx.x + o < 256) ? part[threadIdx.x + o] : 0u;
-    __syncthreads();
-    part[threadIdx.x] += v;
-    __syncthreads();
-  }
-  const unsigned above = part[threadIdx.x] - sum;  // keys in bins strictly above my 8 bins
-  const unsigned k = (unsigned)st.k_rem;
-  if (above < k && above + sum >= k) {
-    unsigned cum = above;
-    for (int i = 7; i >= 0; --i) {
-      if (cum + loc[i] >= k) {
-        s_digit = threadIdx.x * 8 + i;
-        s_krem = (int)(k - cum);
-        break;
-      }
-      cum += loc[i];
-    }
-  }
-  __syncthreads();
+  __shared__ int s_last;
   if (threadIdx.x == 0) {
-    int shift, bits;
-    pass_geometry(pass, shift, bits);
-    st.prefix |= (unsigned long long)(unsigned)s_digit << shift;
-    st.k_rem = s_krem;
-    state[seg] = st;
+    const long long want = (len + kItemsPerCta - 1) / kItemsPerCta;
+    const int nct = (int)(want < (long long)gridDim.x ? want : (long long)gridDim.x);
+    s_last = atomicAdd(&tickets[seg], 1) == nct - 1;
+    if (s_last) tickets[seg] = 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    scan_segment(hist, const_cast<SegState *>(state), seg, pass);
   }
 }
 
@@ -345,9 +359,10 @@ __global__ void __launch_bounds__(1024) topk_bitonic_kernel(const unsigned long 
   }
 }
 
-__global__ void topk_init_kernel(SegState *state, const SegTable tab, int nseg, int k) {
+__global__ void topk_init_kernel(SegState *state, int *tickets, const SegTable tab, int nseg, int k) {
   const int s = threadIdx.x;
   if (s >= nseg) return;
+  tickets[s] = 0;
   SegState st;
   st.prefix = 0ULL;
   st.k_take = (int)min((unsigned)k, tab.s[s].len);
@@ -618,13 +633,14 @@ int roi3d_topk_segmented_ex(const float *scores_dev, const int64_t *seg_off, con
       }
       if (seg_len[s0 + s] > maxlen) maxlen = seg_len[s0 + s];
     }
-    static_assert(sizeof(SegState) * kMaxSeg <= 2048, "state block");
+    static_assert(sizeof(SegState) * kMaxSeg + sizeof(int) * kMaxSeg <= 2048, "state block");
     char *b = static_cast<char *>(workspace_dev);
     SegState *state = reinterpret_cast<SegState *>(b);
     unsigned *hist = reinterpret_cast<unsigned *>(b + kStateBytes);
     unsigned long long *cand = reinterpret_cast<unsigned long long *>(b + kStateBytes + kHistBytes);
     unsigned long long *bnd = cand + (size_t)(nseg < kMaxSeg ? nseg : kMaxSeg) * k;
-    topk_init_kernel<<<1, kMaxSeg, 0, st>>>(state, tab, ns, k);
+    int *tickets = reinterpret_cast<int *>(b + sizeof(SegState) * kMaxSeg);  // inside the 2 KB state block
+    topk_init_kernel<<<1, kMaxSeg, 0, st>>>(state, tickets, tab, ns, k);
     ROI3D_LAUNCH_CHECK();
     if (maxlen == 0) continue;
     ROI3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)ns * kBins * sizeof(unsigned), st));
@@ -634,11 +650,9 @@ int roi3d_topk_segmented_ex(const float *scores_dev, const int64_t *seg_off, con
       const unsigned long long *b2 = pass >= 2 ? bnd : nullptr;
       const dim3 g = pass >= 2 ? grid2 : grid;
       if (apply_sigmoid)
-        topk_hist_kernel<true><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2);
+        topk_hist_kernel<true><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets);
       else
-        topk_hist_kernel<false><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2);
-      ROI3D_LAUNCH_CHECK();
-      topk_scan_kernel<<<ns, 256, 0, st>>>(hist, state, pass);
+        topk_hist_kernel<false><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets);
       ROI3D_LAUNCH_CHECK();
       if (pass == 1) {  // 22 bits decided: split off the certain keys and the boundary bin
         if (apply_sigmoid)
