@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
   const int cb = (n + 63) >> 6, cbm = (n_max + 63) >> 6;
   const unsigned long long *m = mask + (long long)seg * n_max * cbm;
   const int32_t *ord = order + (long long)seg * n_max;
-  unsigned char *fl = flags + (long long)seg * n_max;
   int64_t *kp = keep + (long long)seg * n_max;
   int64_t *kps = keep_by_score ? keep_by_score + (long long)seg * n_max : nullptr;
   const int tid = threadIdx.x;
@@ -445,7 +444,7 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
     }
   }
   if (tid == 0) num_keep[seg] = total;
-  (void)fl;
+  (void)flags;  // per-box flag workspace of an earlier sweep design; kept in the workspace layout
 }
 
 struct NmsWorkspace {
