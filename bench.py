@@ -440,6 +440,25 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     us = med_us(lambda: nms3d_batched(d40, None, 0.7), iters=10, do_flush=False)
     ex["c1_nms2000_x40_batched_us"] = us
     ex["c1_nms2000_x40_boxes_per_sec"] = 40 * 2000 / (us * 1e-6)
+    # C1 as BASELINE.json states it: numpy boxes through the nms wrapper (host buffers: upload, kernels, read-back),
+    # beside the reference's CPU paths restated in the oracle: its only CPU 3D-IoU NMS (numpy nms_3d_python) and
+    # what its wrapper really runs on CPU input, the 2-D nms_cpu on columns 0-4
+    import oracle  # CPU baseline legs only
+    from roi3d_b200.ops import nms as nms_wrapper
+    dn = synth.c1_boxes(2000, seed=0)
+    nms_wrapper(dn, 0.7, device_id=dev.index or 0)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        _, keep_h = nms_wrapper(dn, 0.7, device_id=dev.index or 0)
+    ex["c1_nms2000_numpy_in_wrapper_us"] = (time.perf_counter() - t0) / 20 * 1e6
+    t0 = time.perf_counter()
+    keep_np = oracle.nms_3d_python(dn, 0.7)
+    ex["c1_nms2000_cpu_numpy_3d_us"] = (time.perf_counter() - t0) * 1e6
+    t0 = time.perf_counter()
+    oracle.nms_cpu_2d(dn, 0.7)
+    ex["c1_nms2000_cpu_reference_wrapper_2d_semantics_us"] = (time.perf_counter() - t0) * 1e6
+    ex["c1_kept"] = int(len(keep_h))
+    ex["c1_kept_matches_cpu_3d_set"] = bool(np.array_equal(np.sort(keep_np), np.sort(np.asarray(keep_h))))
     del d40
     # C3: mask branch, 14^3, 4 levels with level mapping, 2 volumes x 512 RoIs, fwd + bwd
     dims = [(40, 128, 128), (20, 64, 64), (10, 32, 32), (5, 16, 16)]
