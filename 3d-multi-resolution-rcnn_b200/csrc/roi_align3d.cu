@@ -30,96 +30,10 @@
 
 #include "common.cuh"
 
+#include "roi_align3d_shared.cuh"
+
 namespace roi3d {
 
-struct LevelDev {
-  const float *feats;
-  float *grad;
-  int D, H, W;
-  float scale, scale_d;
-};
-
-struct RoiParams {
-  LevelDev lv[ROI3D_MAX_LEVELS];
-  int num_levels;
-  float inv_finest;
-  int B, C;
-  const float *rois;
-  int K;
-  int PD, PH, PW;
-  int sample_num;
-  float *out;             // forward
-  const float *grad_out;  // backward
-  int64_t *lvls_out;
-  const int *out_rows;    // forward: output row of RoI k (nullptr = k)
-  int nchunk, nphg;
-  long long total_items;
-  int items_per_roi, ctas_per_roi;  // ring2 kernels: CTA -> (RoI, group of kWarps * items_per_warp sub-items)
-  int items_per_warp;
-  int bug_compat;
-};
-
-constexpr int kWarps = 4;
-constexpr int RXMAX = 40, RYMAX = 40, RZMAX = 32;
-constexpr unsigned FULL = 0xffffffffu;
-
-template <int CV>
-__device__ __forceinline__ void ldv(const float *p, float (&v)[CV]) {
-  if constexpr (CV == 4) {
-    float4 t = __ldg(reinterpret_cast<const float4 *>(p));
-    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-  } else if constexpr (CV == 2) {
-    float2 t = __ldg(reinterpret_cast<const float2 *>(p));
-    v[0] = t.x, v[1] = t.y;
-  } else {
-    v[0] = __ldg(p);
-  }
-}
-
-template <int CV>
-__device__ __forceinline__ void redv(float *p, const float (&v)[CV]) {
-  if constexpr (CV == 4) {
-    atomicAdd(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
-  } else if constexpr (CV == 2) {
-    atomicAdd(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
-  } else {
-    atomicAdd(p, v[0]);
-  }
-}
-
-// Per-warp decode of one work item + RoI geometry.
-struct Item {
-  int k, krow, chunk, pd, ph0, rows, lvl, b;
-  bool ok;
-  Axis axw, axh, axd;
-  LevelDev L;
-};
-
-__device__ __forceinline__ Item decode_item(const RoiParams &p, long long item64, int ROWS) {
-  Item it;
-  unsigned item = (unsigned)item64;  // launchers guarantee total_items < 2^31: 32-bit div/mod only
-  const unsigned phg = item % (unsigned)p.nphg;
-  item /= (unsigned)p.nphg;
-  it.pd = (int)(item % (unsigned)p.PD);
-  item /= (unsigned)p.PD;
-  it.chunk = (int)(item % (unsigned)p.nchunk);
-  it.k = (int)(item / (unsigned)p.nchunk);
-  it.krow = p.out_rows != nullptr ? __ldg(p.out_rows + it.k) : it.k;
-  it.ph0 = (int)phg * ROWS;
-  it.rows = min(ROWS, p.PH - it.ph0);
-  const float *roi = p.rois + (long long)it.k * 7;
-  float r[7];
-#pragma unroll
-  for (int i = 0; i < 7; ++i) r[i] = __ldg(roi + i);
-  it.lvl = p.num_levels > 1 ? roi_level(r, p.num_levels, p.inv_finest) : 0;
-  it.L = p.lv[it.lvl];
-  it.b = (int)r[0];
-  it.ok = it.b >= 0 && it.b < p.B;
-  it.axw = axis_setup(r[1], r[3], it.L.scale, p.PW, p.sample_num);
-  it.axh = axis_setup(r[2], r[4], it.L.scale, p.PH, p.sample_num);
-  it.axd = axis_setup(r[5], r[6], it.L.scale_d, p.PD, p.sample_num);
-  return it;
-}
 
 // Per-warp weight tables in shared memory.
 //   Dx[(x - xmin) * PWP + pw], Dy[(y - ymin) * 8 + r], Dz[z - zmin]; xlo/xhi[pw] relative to xmin.
@@ -198,109 +112,6 @@ __device__ __forceinline__ void build_tables(Tables<PW> &T, const Item &it, int 
   __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------------
-// Generic (literal) evaluation of one output bin for CV channels per lane: the reference's sample
-// loops and its exact corner-weight / FFMA-chain arithmetic (roi_align_kernel.cu:134-146 + SASS).
-// ---------------------------------------------------------------------------------------------
-template <int CV>
-__device__ __forceinline__ void literal_bin_fwd(const Item &it, const float *fb, int C, int pd, int ph, int pw,
-                                                float (&out)[CV]) {
-  const int D = it.L.D, H = it.L.H, W = it.L.W;
-  float acc[CV];
-#pragma unroll
-  for (int c = 0; c < CV; ++c) acc[c] = 0.0f;
-  for (int iz = 0; iz < it.axd.S; ++iz) {
-    Tap tz = axis_tap(axis_coord(it.axd, pd, iz), D);
-    for (int iy = 0; iy < it.axh.S; ++iy) {
-      Tap ty = axis_tap(axis_coord(it.axh, ph, iy), H);
-      for (int ix = 0; ix < it.axw.S; ++ix) {
-        Tap tx = axis_tap(axis_coord(it.axw, pw, ix), W);
-        if (!(tz.valid && ty.valid && tx.valid)) continue;  // contributes 0, still counted
-        const float hxhy = __fmul_rn(tx.h, ty.h), lxhy = __fmul_rn(tx.l, ty.h);
-        const float hxly = __fmul_rn(tx.h, ty.l), lxly = __fmul_rn(tx.l, ty.l);
-        const float w1 = __fmul_rn(hxhy, tz.h), w2 = __fmul_rn(lxhy, tz.h), w3 = __fmul_rn(hxly, tz.h),
-                    w4 = __fmul_rn(lxly, tz.h), w5 = __fmul_rn(hxhy, tz.l), w6 = __fmul_rn(lxhy, tz.l),
-                    w7 = __fmul_rn(hxly, tz.l), w8 = __fmul_rn(lxly, tz.l);
-        const long long zl = (long long)tz.low * H, zh = (long long)tz.high * H;
-        float f1[CV], f2[CV], f3[CV], f4[CV], f5[CV], f6[CV], f7[CV], f8[CV];
-        ldv<CV>(fb + ((zl + ty.low) * W + tx.low) * C, f1);
-        ldv<CV>(fb + ((zl + ty.low) * W + tx.high) * C, f2);
-        ldv<CV>(fb + ((zl + ty.high) * W + tx.low) * C, f3);
-        ldv<CV>(fb + ((zl + ty.high) * W + tx.high) * C, f4);
-        ldv<CV>(fb + ((zh + ty.low) * W + tx.low) * C, f5);
-        ldv<CV>(fb + ((zh + ty.low) * W + tx.high) * C, f6);
-        ldv<CV>(fb + ((zh + ty.high) * W + tx.low) * C, f7);
-        ldv<CV>(fb + ((zh + ty.high) * W + tx.high) * C, f8);
-#pragma unroll
-        for (int c = 0; c < CV; ++c) {
-          float t = __fmul_rn(w2, f2[c]);
-          t = __fmaf_rn(w1, f1[c], t);
-          t = __fmaf_rn(w3, f3[c], t);
-          t = __fmaf_rn(w4, f4[c], t);
-          t = __fmaf_rn(w5, f5[c], t);
-          t = __fmaf_rn(w6, f6[c], t);
-          t = __fmaf_rn(w7, f7[c], t);
-          t = __fmaf_rn(w8, f8[c], t);
-          acc[c] = __fadd_rn(acc[c], t);
-        }
-      }
-    }
-  }
-  const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
-#pragma unroll
-  for (int c = 0; c < CV; ++c) out[c] = __fdiv_rn(acc[c], count);
-}
-
-template <int CV>
-__device__ __forceinline__ void literal_bin_bwd(const Item &it, float *gb, int C, int pd, int ph, int pw,
-                                                const float (&top)[CV]) {
-  const int D = it.L.D, H = it.L.H, W = it.L.W;
-  const float count = (float)(it.axd.S * it.axh.S * it.axw.S);
-  for (int iz = 0; iz < it.axd.S; ++iz) {
-    Tap tz = axis_tap(axis_coord(it.axd, pd, iz), D);
-    for (int iy = 0; iy < it.axh.S; ++iy) {
-      Tap ty = axis_tap(axis_coord(it.axh, ph, iy), H);
-      for (int ix = 0; ix < it.axw.S; ++ix) {
-        Tap tx = axis_tap(axis_coord(it.axw, pw, ix), W);
-        if (!(tz.valid && ty.valid && tx.valid)) continue;
-        const float hxhy = __fmul_rn(tx.h, ty.h), lxhy = __fmul_rn(tx.l, ty.h);
-        const float hxly = __fmul_rn(tx.h, ty.l), lxly = __fmul_rn(tx.l, ty.l);
-        const float w[8] = {__fmul_rn(hxhy, tz.h), __fmul_rn(lxhy, tz.h), __fmul_rn(hxly, tz.h),
-                            __fmul_rn(lxly, tz.h), __fmul_rn(hxhy, tz.l), __fmul_rn(lxhy, tz.l),
-                            __fmul_rn(hxly, tz.l), __fmul_rn(lxly, tz.l)};
-        const long long zl = (long long)tz.low * H, zh = (long long)tz.high * H;
-        const long long off[8] = {((zl + ty.low) * W + tx.low) * C,  ((zl + ty.low) * W + tx.high) * C,
-                                  ((zl + ty.high) * W + tx.low) * C, ((zl + ty.high) * W + tx.high) * C,
-                                  ((zh + ty.low) * W + tx.low) * C,  ((zh + ty.low) * W + tx.high) * C,
-                                  ((zh + ty.high) * W + tx.low) * C, ((zh + ty.high) * W + tx.high) * C};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float g[CV];
-#pragma unroll
-          for (int c = 0; c < CV; ++c) g[c] = __fdiv_rn(__fmul_rn(top[c], w[q]), count);
-          redv<CV>(gb + off[q], g);
-        }
-      }
-    }
-  }
-}
-
-// Literal evaluation of a warp's whole (pd, ph-group) tile, kept out of line so that its register
-// footprint does not inflate the fast kernels that only call it for oversized footprints.
-template <int CV>
-__device__ __noinline__ void literal_tile_fwd(const Item &it, const float *fb, int C, int PD, int PH, int PW,
-                                              int c_base, bool active, float *out) {
-  for (int r = 0; r < it.rows; ++r)
-    for (int pw = 0; pw < PW; ++pw) {
-      float v[CV];
-      literal_bin_fwd<CV>(it, fb, C, it.pd, it.ph0 + r, pw, v);
-      if (active) {
-#pragma unroll
-        for (int c = 0; c < CV; ++c)
-          out[((((long long)it.krow * C + c_base + c) * PD + it.pd) * PH + it.ph0 + r) * PW + pw] = v[c];
-      }
-    }
-}
 
 // Epilogue shared by the forward kernels: acc / count -> padded smem tile [bin][33] (lane = channel, no bank
 // conflicts) -> global [channel][bin] in contiguous runs.  The flattened (channel, bin) walk advances by
@@ -1165,436 +976,6 @@ __global__ void __launch_bounds__(kWarps * 32, MINB)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward "slab" kernel: the CTA is the unit for (RoI, 64-channel chunk) and its warps are specialised.
-//   * NW row workers stream the rows (z slice by z slice, every y row of the RoI footprint) ONCE: copy
-//     global -> per-worker cp.async ring, contract along x into PW partial sums and store them to a shared
-//     T1[slice buffer][y][pw][channel] tile.  In the per-warp kernels above every row is copied and contracted by
-//     each of the ~3 pd-warps whose bins contain z.
-//   * one owner warp per output row ph keeps acc[pd][pw] in registers: for every finished slice it folds the ~3
-//     y rows that carry weight for its ph, then adds the result into the ~2-3 pd bins the slice feeds.
-//   * hand-off by named barriers (bar.sync / bar.arrive): FULL[b] workers -> owners, EMPTY[b] owners -> workers,
-//     two T1 buffers.
-//   * epilogue: owners stage their bins into a [channel][bin] tile, then all warps stream the chunk's
-//     64 x (PD*PH*PW) outputs with fully contiguous 1372-byte runs per channel.
-// Summation order differs from the ring kernels (y before z), results agree to a few ulp (tolerance 1e-5).
-// Status (round 1): parity-green, 273 us on C2 against 212 us for the ring2 default -- kept as tuning variant 80.
-// One CTA of 12 warps per SM leaves the prologue and the epilogue exposed (97 us of the 273 with the slices
-// skipped) and the per-slice hand-off keeps the issue rate at 33 %; see DESIGN.md section 6 for the next steps.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// cp.async.wait_group takes an immediate: dispatch on the (warp-uniform) number of groups allowed to stay pending
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-  switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    case 4: cp_async_wait<4>(); break;
-    case 5: cp_async_wait<5>(); break;
-    default: cp_async_wait<6>(); break;
-  }
-}
-
-template <int PW, int NW, int RCAP, int RXR, int RYR>
-struct SlabLayout {
-  static constexpr int CV = 2, VOX = 64, NOWN = 7, PDM = 7;
-  static constexpr int RING = RCAP;                          // floats per worker; stages are sized to the RoI's RX
-  static_assert(RCAP >= 2 * (RXR + 2) * VOX, "at least two stages for the widest row");
-  static constexpr int T1ROW = PW * VOX;                     // floats per T1 row
-  static constexpr int T1BUF = RYR * T1ROW;
-  static constexpr int SSTR = PDM * NOWN * PW + 2;           // staging stride per channel (343 + 2, odd)
-  static constexpr int STAGE = VOX * SSTR;
-  static constexpr int TAB = RXMAX * Tables<PW>::PWP + RYMAX * 16 + 40 * 16 + 32 + 64 + 16;  // tables, xlo/xhi, lists, box
-  static constexpr int TABP = (TAB + 31) / 32 * 32;
-  static constexpr int DATA = NW * RING + 2 * T1BUF;
-  static_assert(DATA >= STAGE, "the output staging tile aliases the rings and the T1 buffers");
-  static constexpr size_t BYTES = (size_t)(TABP + DATA) * sizeof(float);
-  static constexpr int THREADS = (NW + NOWN) * 32;
-};
-
-template <int PW, int NW, int RCAP, int RXR, int RYR>
-__global__ void __launch_bounds__((NW + 7) * 32, 1) roi_align3d_fwd_slab_kernel(const RoiParams p) {
-  using LY = SlabLayout<PW, NW, RCAP, RXR, RYR>;
-  using TB = Tables<PW>;
-  constexpr int PWP = TB::PWP, VOX = LY::VOX, CV = 2, NXU = 3, PP = 16, PDM = LY::PDM;
-  constexpr int T1ROW = LY::T1ROW, SSTR = LY::SSTR;
-  constexpr int LPV = VOX / 4, VPI = 32 / LPV;
-  extern __shared__ __align__(128) float smem_slab[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  float *SDx = smem_slab;
-  float *SDy = SDx + RXMAX * PWP;
-  float *SDz = SDy + RYMAX * PP;
-  int *Sxlo = reinterpret_cast<int *>(SDz + RZMAX2 * PP);
-  int *Sxhi = Sxlo + 16;
-  unsigned char *Sylist = reinterpret_cast<unsigned char *>(Sxhi + 16);  // 40 bytes
-  unsigned char *Szlist = Sylist + 40;                                   // 40 bytes
-  int *Sbox = reinterpret_cast<int *>(Sylist + 80 + 48);                  // xmin..zmax, ny, nz
-  float *rings = smem_slab + LY::TABP;
-  float *T1 = rings + NW * LY::RING;
-  float *stage = rings;
-
-  const int k = blockIdx.x / p.nchunk;
-  const int chunk = blockIdx.x - k * p.nchunk;
-  Item it;
-  {
-    it.k = k;
-    it.krow = p.out_rows != nullptr ? __ldg(p.out_rows + k) : k;
-    it.pd = 0, it.chunk = chunk, it.ph0 = 0, it.rows = p.PH;
-    float r[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
-    it.lvl = p.num_levels > 1 ? roi_level(r, p.num_levels, p.inv_finest) : 0;
-    it.L = p.lv[it.lvl];
-    it.b = (int)r[0];
-    it.ok = it.b >= 0 && it.b < p.B;
-    it.axw = axis_setup(r[1], r[3], it.L.scale, p.PW, p.sample_num);
-    it.axh = axis_setup(r[2], r[4], it.L.scale, p.PH, p.sample_num);
-    it.axd = axis_setup(r[5], r[6], it.L.scale_d, p.PD, p.sample_num);
-  }
-  const int C = p.C;
-  if (p.lvls_out != nullptr && chunk == 0 && tid == 0) p.lvls_out[k] = it.lvl;
-
-  // ---- CTA-shared tables, as in roi_align3d_fwd_ring2_kernel ----
-  const int role = (warp == 0 && lane < PW) ? 0 : (warp == 1 && lane < p.PH) ? 1 : (warp == 2 && lane < p.PD) ? 2 : -1;
-  const Axis ax = role == 1 ? it.axh : role == 2 ? it.axd : it.axw;
-  const int asize = role == 1 ? it.L.H : role == 2 ? it.L.D : it.L.W;
-  int lo = INT_MAX, hi = -1;
-  if (role >= 0 && it.ok) {
-    for (int i = 0; i < ax.S; ++i) {
-      Tap t = axis_tap(axis_coord(ax, lane, i), asize);
-      if (t.valid) lo = min(lo, t.low), hi = max(hi, t.high);
-    }
-  }
-  if (warp < 3) {
-    const int mn = __reduce_min_sync(FULL, role >= 0 ? lo : INT_MAX);
-    const int mx = __reduce_max_sync(FULL, role >= 0 ? hi : -1);
-    if (lane == 0) Sbox[warp * 2] = mn, Sbox[warp * 2 + 1] = mx;
-  }
-  __syncthreads();
-  const int xmin = Sbox[0], xmax = Sbox[1], ymin = Sbox[2], ymax = Sbox[3], zmin = Sbox[4], zmax = Sbox[5];
-  const bool empty = !it.ok || xmax < xmin || ymax < ymin || zmax < zmin;
-  const bool fits = empty || ((xmax - xmin < RXMAX) && (ymax - ymin < RYMAX) && (zmax - zmin < RZMAX2));
-  const int RX = xmax - xmin + 1, RY = ymax - ymin + 1, RZ = zmax - zmin + 1;
-  if (!empty && fits) {
-    for (int i = tid; i < RX * PWP; i += LY::THREADS) SDx[i] = 0.0f;
-    for (int i = tid; i < RY * PP; i += LY::THREADS) SDy[i] = 0.0f;
-    for (int i = tid; i < RZ * PP; i += LY::THREADS) SDz[i] = 0.0f;
-  }
-  __syncthreads();
-  if (!empty && fits && role >= 0) {
-    float *tab = role == 0 ? SDx : role == 1 ? SDy : SDz;
-    const int stride = role == 0 ? PWP : PP;
-    const int mn = role == 0 ? xmin : role == 1 ? ymin : zmin;
-    for (int i = 0; i < ax.S; ++i) {
-      Tap t = axis_tap(axis_coord(ax, lane, i), asize);
-      if (t.valid) {
-        tab[(t.low - mn) * stride + lane] += t.h;
-        tab[(t.high - mn) * stride + lane] += t.l;
-      }
-    }
-    if (role == 0) {
-      Sxlo[lane] = hi >= lo ? lo - xmin : 0;
-      Sxhi[lane] = hi >= lo ? hi - xmin : -1;
-    }
-  }
-  __syncthreads();
-  // compact lists of the y rows / z slices that carry any weight (warp 3), shared by workers and owners
-  if (warp == 3) {
-    int ny = 0, nz = 0;
-    if (!empty && fits) {
-      for (int y0 = 0; y0 < RY; y0 += 32) {
-        const int yy = y0 + lane;
-        bool a = false;
-        if (yy < RY)
-          for (int r = 0; r < p.PH; ++r) a |= SDy[yy * PP + r] != 0.0f;
-        const unsigned bal = __ballot_sync(FULL, a);
-        if (a) Sylist[ny + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)yy;
-        ny += __popc(bal);
-      }
-      for (int z0 = 0; z0 < RZ; z0 += 32) {
-        const int zz = z0 + lane;
-        bool a = false;
-        if (zz < RZ)
-          for (int r = 0; r < p.PD; ++r) a |= SDz[zz * PP + r] != 0.0f;
-        const unsigned bal = __ballot_sync(FULL, a);
-        if (a) Szlist[nz + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)zz;
-        nz += __popc(bal);
-      }
-    }
-    if (lane == 0) Sbox[6] = ny, Sbox[7] = nz;
-  }
-  __syncthreads();
-  const int ny = Sbox[6], nz = Sbox[7];
-  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
-  const float *fb_roi = it.L.feats + (long long)(it.ok ? it.b : 0) * vox * C;
-  const int nown = p.PH;                                  // owner warps NW .. NW + PH - 1
-  const int nbar = (NW + nown) * 32;
-  const long long bins = (long long)p.PD * p.PH * PW;
-
-  if (!empty && (!fits || RX > RXR || ny > RYR)) {
-    // footprint larger than the tables / ring / T1 tile: literal evaluation, one (pd) tile per warp (rare path)
-    int c_base = (chunk * 32 + lane) * CV;
-    const bool active = c_base < C;
-    if (!active) c_base = 0;
-    for (int pd = warp; pd < p.PD; pd += NW + LY::NOWN) {
-      it.pd = pd;
-      literal_tile_fwd<CV>(it, fb_roi + c_base, C, p.PD, p.PH, PW, c_base, active, p.out);
-    }
-    return;
-  }
-  if (warp >= NW + nown) return;  // owner warps beyond PH: nothing to do, not part of any barrier below
-
-  if (warp < NW) {
-    // =========================== row worker ===========================
-    float *ring = rings + warp * LY::RING;
-    bool long_bins = false;
-    int soff[PW];
-    float tw[PW][NXU];
-#pragma unroll
-    for (int pw = 0; pw < PW; ++pw) {
-      const int l0 = empty ? 0 : Sxlo[pw];
-      const int n = empty ? 0 : Sxhi[pw] - l0 + 1;
-      long_bins |= n > NXU;
-      soff[pw] = l0 * VOX + lane * CV;
-#pragma unroll
-      for (int j = 0; j < NXU; ++j) tw[pw][j] = j < n ? SDx[(l0 + j) * PWP + pw] : 0.0f;
-    }
-    // ring stages are sized to this RoI's rows (RX real voxels + 2 zero pads): narrow RoIs get a deeper pipeline
-    const int STRIDE = (empty ? 3 : RX + 2) * VOX;
-    const int NS = min(8, LY::RING / STRIDE);
-    if (!empty) {
-      for (int sidx = 0; sidx < NS; ++sidx) {
-        float *padp = ring + sidx * STRIDE + RX * VOX;
-        for (int i = lane; i < 2 * VOX; i += 32) padp[i] = 0.0f;
-      }
-    }
-    __syncwarp();
-    const int cv_v = lane / LPV, cv_p = lane % LPV;
-    const int ch_piece = chunk * VOX + cv_p * 4;
-    const bool piece_ok = ch_piece + 4 <= C;
-    const long long row_elems = (long long)it.L.W * C;
-    const long long slice_elems = (long long)it.L.H * row_elems;
-    const float *src0 = fb_roi + ((long long)zmin * it.L.H + ymin) * row_elems + (long long)xmin * C + ch_piece +
-                        (long long)cv_v * C;
-    float *dst0 = ring + cv_p * 4 + cv_v * VOX;
-    const int nrows = ny * nz;                       // rows of the whole RoI, slice-major
-    // my rows: q = warp, warp + NW, ...
-    int pq = warp, pstage = 0;                       // producer cursor (row index) and its (slice, y) decomposition
-    int pzi = 0, pyi = warp;
-    while (ny > 0 && pyi >= ny) pyi -= ny, ++pzi;
-    auto issue = [&]() {
-      const float *src = src0 + (long long)Szlist[pzi] * slice_elems + (long long)Sylist[pyi] * row_elems;
-      float *dst = dst0 + pstage * STRIDE;
-      if (piece_ok) {
-#pragma unroll 2
-        for (int v = cv_v; v < RX; v += VPI) {
-          cp_async16(dst, src);
-          dst += VPI * VOX, src += (long long)VPI * C;
-        }
-      }
-      cp_async_commit();
-      pq += NW, pyi += NW;
-      while (pyi >= ny) pyi -= ny, ++pzi;
-      if (++pstage == NS) pstage = 0;
-    };
-    for (int r = 0; r < NS - 1; ++r) {
-      if (pq < nrows) issue();
-      else cp_async_commit();
-    }
-    int cq = warp, cstage = 0;                       // consumer cursor
-    for (int s = 0; s < nz; ++s) {
-      if (s >= 2) named_bar_sync(3 + (s & 1), nbar);  // EMPTY[s & 1]: the owners are done with this T1 buffer
-      float *t1buf = T1 + (s & 1) * LY::T1BUF;
-      const int qend = (s + 1) * ny;
-      // two of my rows of this slice at a time when possible: two independent instruction streams per warp hide
-      // the shared-memory and FMA latencies that a single row stream exposes (the workers are few)
-      while (cq < qend) {
-        const bool two = NS >= 3 && !long_bins && cq + NW < qend;
-        cp_async_wait_dyn(two ? NS - 3 : NS - 2);
-        __syncwarp();
-        const int yi = cq - s * ny;
-        const float *row = ring + cstage * STRIDE;
-        if (++cstage == NS) cstage = 0;
-        float *trow = t1buf + yi * T1ROW + lane * CV;
-        if (two) {
-          const float *rowb = ring + cstage * STRIDE;
-          if (++cstage == NS) cstage = 0;
-          float2 tza[PW], tzb[PW];
-#pragma unroll
-          for (int pw = 0; pw < PW; ++pw) {
-            const float *qa = row + soff[pw], *qb = rowb + soff[pw];
-            float2 za, zb;
-#pragma unroll
-            for (int j = 0; j < NXU; ++j) {
-              const float2 ta = *reinterpret_cast<const float2 *>(qa + j * VOX);
-              const float2 tb = *reinterpret_cast<const float2 *>(qb + j * VOX);
-              const float2 w2 = make_float2(tw[pw][j], tw[pw][j]);
-              za = j == 0 ? __fmul2_rn(w2, ta) : __ffma2_rn(w2, ta, za);
-              zb = j == 0 ? __fmul2_rn(w2, tb) : __ffma2_rn(w2, tb, zb);
-            }
-            tza[pw] = za, tzb[pw] = zb;
-          }
-          float *trowb = trow + NW * T1ROW;  // my next row of the slice is NW list positions further
-#pragma unroll
-          for (int pw = 0; pw < PW; ++pw) {
-            *reinterpret_cast<float2 *>(trow + pw * VOX) = tza[pw];
-            *reinterpret_cast<float2 *>(trowb + pw * VOX) = tzb[pw];
-          }
-          __syncwarp();
-#pragma unroll
-          for (int r2 = 0; r2 < 2; ++r2) {
-            if (pq < nrows) issue();
-            else cp_async_commit();
-          }
-          cq += 2 * NW;
-          continue;
-        }
-        float2 tz[PW];
-#pragma unroll
-        for (int pw = 0; pw < PW; ++pw) {
-          const float *q = row + soff[pw];
-          float2 z2;
-#pragma unroll
-          for (int j = 0; j < NXU; ++j) {
-            const float2 t = *reinterpret_cast<const float2 *>(q + j * VOX);
-            const float2 w2 = make_float2(tw[pw][j], tw[pw][j]);
-            z2 = j == 0 ? __fmul2_rn(w2, t) : __ffma2_rn(w2, t, z2);
-          }
-          tz[pw] = z2;
-        }
-        if (long_bins) {
-#pragma unroll
-          for (int pw = 0; pw < PW; ++pw) {
-            const int l0 = Sxlo[pw];
-            const int n = Sxhi[pw] - l0 + 1;
-            const float *q = row + soff[pw];
-            const float *wq = SDx + l0 * PWP + pw;
-#pragma unroll 1
-            for (int j = NXU; j < n; ++j) {
-              const float w = wq[j * PWP];
-              tz[pw].x = fmaf(w, q[j * VOX], tz[pw].x);
-              tz[pw].y = fmaf(w, q[j * VOX + 1], tz[pw].y);
-            }
-          }
-        }
-#pragma unroll
-        for (int pw = 0; pw < PW; ++pw) *reinterpret_cast<float2 *>(trow + pw * VOX) = tz[pw];
-        __syncwarp();
-        if (pq < nrows) issue();
-        else cp_async_commit();
-        cq += NW;
-      }
-      // (no membar: it would wait for this warp's in-flight cp.async prefetches, i.e. a DRAM round trip per slice;
-      //  the barrier itself orders the shared-memory stores above against the owners' loads)
-      named_bar_arrive(1 + (s & 1), nbar);            // FULL[s & 1]
-    }
-    cp_async_wait<0>();
-  } else {
-    // =========================== ph owner ===========================
-    const int ph = warp - NW;
-    float2 acc[PDM][PW];
-#pragma unroll
-    for (int a = 0; a < PDM; ++a)
-#pragma unroll
-      for (int w = 0; w < PW; ++w) acc[a][w] = make_float2(0.0f, 0.0f);
-    // the y rows that carry weight for this ph: the first four in registers (bins rarely span more), in list order
-    constexpr int KY = 4;
-    int yoffs[KY], ycnt = 0, yrest = ny;              // yrest: list position where the register taps end
-    float ywts[KY];
-#pragma unroll
-    for (int e = 0; e < KY; ++e) yoffs[e] = 0, ywts[e] = 0.0f;
-    for (int yi = 0; yi < ny; ++yi) {
-      const float wy = SDy[Sylist[yi] * PP + ph];
-      if (wy != 0.0f) {
-        if (ycnt == KY) {
-          yrest = yi;
-          break;
-        }
-#pragma unroll
-        for (int e = 0; e < KY; ++e)
-          if (e == ycnt) yoffs[e] = yi * T1ROW, ywts[e] = wy;
-        ++ycnt;
-      }
-    }
-    for (int s = 0; s < nz; ++s) {
-      named_bar_sync(1 + (s & 1), nbar);              // FULL[s & 1]
-      const float *t1buf = T1 + (s & 1) * LY::T1BUF + lane * CV;
-      float2 t2[PW];
-#pragma unroll
-      for (int w = 0; w < PW; ++w) t2[w] = make_float2(0.0f, 0.0f);
-#pragma unroll
-      for (int e = 0; e < KY; ++e) {
-        if (e < ycnt) {
-          const float2 w2 = make_float2(ywts[e], ywts[e]);
-#pragma unroll
-          for (int w = 0; w < PW; ++w)
-            t2[w] = __ffma2_rn(w2, *reinterpret_cast<const float2 *>(t1buf + yoffs[e] + w * VOX), t2[w]);
-        }
-      }
-      for (int yi = yrest; yi < ny; ++yi) {           // rare: more than KY rows with weight
-        const float wy = SDy[Sylist[yi] * PP + ph];
-        if (wy != 0.0f) {
-          const float2 w2 = make_float2(wy, wy);
-#pragma unroll
-          for (int w = 0; w < PW; ++w)
-            t2[w] = __ffma2_rn(w2, *reinterpret_cast<const float2 *>(t1buf + yi * T1ROW + w * VOX), t2[w]);
-        }
-      }
-      if (s + 2 < nz) {
-        named_bar_arrive(3 + (s & 1), nbar);          // EMPTY[s & 1]: the tile has been read
-      }
-      const int zz = Szlist[s];
-#pragma unroll
-      for (int a = 0; a < PDM; ++a) {
-        const float wz = a < p.PD ? SDz[zz * PP + a] : 0.0f;
-        if (wz != 0.0f) {
-          const float2 w2 = make_float2(wz, wz);
-#pragma unroll
-          for (int w = 0; w < PW; ++w) acc[a][w] = __ffma2_rn(w2, t2[w], acc[a][w]);
-        }
-      }
-    }
-    // owners only: everybody has finished reading T1 (the staging tile may reach into it)
-    named_bar_sync(6, nown * 32);
-    const float inv = __frcp_rn((float)(it.axd.S * it.axh.S * it.axw.S));
-    float *st0 = stage + (lane * CV) * SSTR;
-#pragma unroll
-    for (int a = 0; a < PDM; ++a) {
-      if (a < p.PD) {
-#pragma unroll
-        for (int w = 0; w < PW; ++w) {
-          const int bin = (a * p.PH + ph) * PW + w;
-          st0[bin] = acc[a][w].x * inv;
-          st0[SSTR + bin] = acc[a][w].y * inv;
-        }
-      }
-    }
-  }
-  // ---- all workers and owners: stream the chunk out, one channel (bins contiguous floats) at a time ----
-  named_bar_sync(5, nbar);
-  const int nwarps = NW + nown;
-  for (int cl = warp; cl < VOX; cl += nwarps) {
-    const int c = chunk * VOX + cl;
-    if (c >= C) break;
-    float *dst = p.out + ((long long)it.krow * C + c) * bins;
-    const float *src = stage + cl * SSTR;
-    constexpr int NIT = (LY::PDM * LY::NOWN * PW + 31) / 32;  // 11 for 7x7x7
-    float v[NIT];
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) v[i] = lane + 32 * i < (int)bins ? src[lane + 32 * i] : 0.0f;
-#pragma unroll
-    for (int i = 0; i < NIT; ++i)
-      if (lane + 32 * i < (int)bins) __stcs(dst + lane + 32 * i, v[i]);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Backward, channels-last, separable (transposed contraction).  Same work split as the forward.
 // One vector red per (row voxel, lane) instead of 64 scalar atomics per output element.
 // ---------------------------------------------------------------------------------------------
@@ -2447,19 +1828,6 @@ static int launch_fwd_ring2(RoiParams &p, cudaStream_t st) {
   return ROI3D_OK;
 }
 
-template <int PW, int NW, int RCAP, int RXR, int RYR>
-static int launch_fwd_slab(RoiParams &p, cudaStream_t st) {
-  using LY = SlabLayout<PW, NW, RCAP, RXR, RYR>;
-  p.nchunk = ceil_div(p.C, 64);
-  const long long blocks = (long long)p.K * p.nchunk;
-  ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
-  auto kern = roi_align3d_fwd_slab_kernel<PW, NW, RCAP, RXR, RYR>;
-  ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::BYTES));
-  kern<<<(unsigned)blocks, LY::THREADS, LY::BYTES, st>>>(p);
-  ROI3D_LAUNCH_CHECK();
-  return ROI3D_OK;
-}
-
 template <int PW, int ROWS, int CV, int RXR, bool F2 = false>
 static int launch_bwd(RoiParams &p, cudaStream_t st) {
   using TB = Tables<PW>;
@@ -2528,6 +1896,8 @@ static int pick_cv(const RoiParams &p, bool bwd) {
   return cv;
 }
 
+// Forward kernel selection.  g_fwd_variant (roi3d_set_tuning key 0): 0 = auto, 1 = one channel per lane (the
+// fallback for C % 2 != 0), 50 = the per-warp ring kernel even where the streamed kernel applies (A/B), 99 = literal.
 static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
   if (p.K == 0) return ROI3D_OK;
   const int cvmax = pick_cv(p, false);
@@ -2536,79 +1906,30 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
     if (cvmax >= 2) return launch_generic<2>(p, true, st);
     return launch_generic<1>(p, true, st);
   }
+  if (v == 0 && fwd_stream_ok(p)) return launch_fwd_stream(p, st);  // persistent TMA-fed kernel (roi_align3d_stream.cu)
   bool ring_ok = p.C % 4 == 0;
   for (int l = 0; l < p.num_levels; ++l) ring_ok = ring_ok && aligned(p.lv[l].feats, 16);
   if (p.PW == 7) {
-    if (ring_ok && cvmax >= 2) {
-      if (p.PH <= 16 && p.PD <= 16) {
-        if (v == 0 || v == 50) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, 0, true>(p, st);  // default
-        if (v == 22) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2>(p, st);  // scalar-FMA twin of the default
-        if (v >= 80 && v <= 81 && p.PH <= 7 && p.PD <= 7) {  // specialised-warp slab kernel (experimental)
-          if (v == 80) return launch_fwd_slab<7, 5, 6400, 18, 20>(p, st);
-          if (v == 81) return launch_fwd_slab<7, 4, 8000, 18, 20>(p, st);
-        }
-        if (v == 56) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, 0, true, true, 2>(p, st);  // walks 2 sub-items per warp
-        if (v >= 70 && v <= 72 && tma_ok(p, 64)) {
-          if (v == 70) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, 2, true>(p, st);
-          if (v == 71) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, 2, true>(p, st);
-        }
-        if (v == 20) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2>(p, st);
-        if (v == 51) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, 0, true>(p, st);
-        if (v == 52) return launch_fwd_ring2<7, 7, 2, 3, 6, 18, 2, 0, true>(p, st);
-        if (v == 40) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, 1>(p, st);
-        if (v == 41) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 2, 1>(p, st);
-        if (v == 42) return launch_fwd_ring2<7, 7, 2, 3, 6, 18, 2, 1>(p, st);
-        if (v == 21) return launch_fwd_ring2<7, 7, 2, 3, 3, 18, 3>(p, st);
-        if (v == 23) return launch_fwd_ring2<7, 7, 2, 3, 4, 18, 0>(p, st);
-      }
-      if (v == 0 || v == 30) return launch_fwd_ring<7, 7, 2, 3, 4, 18, 2>(p, st);  // per-warp tables (PH or PD > 16)
-      if (v == 13) return launch_fwd_ring<7, 7, 2, 3, 3, 18>(p, st);
-      if (v == 5) return launch_fwd_ring<7, 7, 2, 3, 4, 18>(p, st);
-      if (v == 6) return launch_fwd_ring<7, 7, 1, 3, 4, 20>(p, st);
-      if (v == 7) return launch_fwd_ring<7, 4, 2, 3, 3, 18>(p, st);
-      if (v == 8) return launch_fwd_ring<7, 7, 2, 3, 2, 18, 4>(p, st);
-      if (v == 11) return launch_fwd_ring<7, 7, 2, 3, 3, 18, 3>(p, st);
-      if (v == 12) return launch_fwd_ring<7, 7, 2, 3, 4, 18, 2>(p, st);
-      if (v == 9) return launch_fwd_ring<7, 7, 2, 3, 2, 18, 3>(p, st);
-      if (v == 10) return launch_fwd_ring<7, 4, 2, 3, 2, 18, 4>(p, st);
+    if (ring_ok && cvmax >= 2 && v != 1) {
+      if (p.PH <= 16 && p.PD <= 16) return launch_fwd_ring2<7, 7, 2, 3, 5, 18, 2, 0, true>(p, st);
+      return launch_fwd_ring<7, 7, 2, 3, 4, 18, 2>(p, st);  // per-warp tables (PH or PD > 16)
     }
     if (v == 1 || cvmax == 1) return launch_fwd<7, 7, 1, 3>(p, st);
-    if (v == 2 && cvmax >= 4) return launch_fwd<7, 4, 4, 3>(p, st);
     return launch_fwd<7, 7, 2, 3>(p, st);
   }
   if (p.PW == 14) {
-    if (ring_ok && cvmax >= 2) {
-      if (p.PH <= 16 && p.PD <= 16) {
-        if (v == 0 || v == 56) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0, 0, true, true, 7>(p, st);  // default
-        if (v == 50) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0, 0, true>(p, st);  // one sub-item per warp
-        if (v == 20) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0>(p, st);  // scalar-FMA twin of the default
-        if (v >= 70 && v <= 72 && tma_ok(p, 64)) {
-          if (v == 70) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0, 2, true>(p, st);
-          if (v == 71) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 0, 2, true>(p, st);
-          if (v == 72) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2, 2, true>(p, st);
-        }
-        if (v == 40) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 0, 1>(p, st);
-        if (v == 51) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2, 0, true>(p, st);
-        if (v == 52) return launch_fwd_ring2<14, 7, 2, 3, 3, 18, 0, 0, true>(p, st);
-        if (v == 21) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 3>(p, st);
-        if (v == 22) return launch_fwd_ring2<14, 4, 2, 3, 4, 18, 2>(p, st);
-        if (v == 23) return launch_fwd_ring2<14, 7, 1, 3, 4, 20, 0>(p, st);
-      }
-      if (v == 0 || v == 30) return launch_fwd_ring<14, 4, 2, 3, 3, 18>(p, st);  // per-warp tables (PH or PD > 16)
-      if (v == 12) return launch_fwd_ring<14, 4, 2, 3, 4, 18, 2>(p, st);
-      if (v == 11) return launch_fwd_ring<14, 4, 2, 3, 3, 18, 3>(p, st);
-      if (v == 5) return launch_fwd_ring<14, 4, 2, 3, 4, 18>(p, st);
-      if (v == 6) return launch_fwd_ring<14, 7, 1, 3, 4, 20>(p, st);
-      if (v == 7) return launch_fwd_ring<14, 2, 2, 3, 3, 18>(p, st);
+    if (ring_ok && cvmax >= 2 && v != 1) {
+      if (p.PH <= 16 && p.PD <= 16) return launch_fwd_ring2<14, 4, 2, 3, 3, 18, 0, 0, true, true, 7>(p, st);
+      return launch_fwd_ring<14, 4, 2, 3, 3, 18>(p, st);  // per-warp tables (PH or PD > 16)
     }
     if (v == 1 || cvmax == 1) return launch_fwd<14, 7, 1, 3>(p, st);
-    if (v == 2 && cvmax >= 4) return launch_fwd<14, 2, 4, 3>(p, st);
     return launch_fwd<14, 4, 2, 3>(p, st);
   }
   if (cvmax >= 2) return launch_generic<2>(p, true, st);
   return launch_generic<1>(p, true, st);
 }
 
+// Backward kernel selection.  g_bwd_variant (key 1): 0 = auto, 1 = one channel per lane, 3 = per-warp tables, 99 = literal.
 static int dispatch_bwd(RoiParams &p, cudaStream_t st) {
   if (p.K == 0) return ROI3D_OK;
   const int cvmax = pick_cv(p, true);
@@ -2619,34 +1940,12 @@ static int dispatch_bwd(RoiParams &p, cudaStream_t st) {
   }
   if (p.PW == 7) {
     if (v == 1 || cvmax == 1) return launch_bwd<7, 7, 1, 40>(p, st);
-    if (v == 2 && cvmax >= 4) return launch_bwd<7, 4, 4, 16>(p, st);
-    if (p.PH <= 16 && p.PD <= 16 && cvmax >= 2) {
-      if (v == 0 || v == 61) return launch_bwd2<7, 7, 2, true>(p, st);  // default
-      if (v == 60) return launch_bwd2<7, 7, 2, false>(p, st);
-      if (v == 64) return launch_bwd2<7, 4, 2, true>(p, st);
-      if (p.PH <= 8 && p.PD <= 8) {
-        if (v == 62) return launch_bwd2<7, 7, 2, false, 4, 8>(p, st);
-        if (v == 63) return launch_bwd2<7, 7, 2, true, 4, 8>(p, st);
-        if (v == 65) return launch_bwd2<7, 4, 2, true, 4, 8>(p, st);
-        if (v == 66) return launch_bwd2<7, 4, 2, true, 5, 8>(p, st);
-      }
-    }
-    if (v == 50) return launch_bwd<7, 7, 2, 26, true>(p, st);
+    if (v == 0 && p.PH <= 16 && p.PD <= 16 && cvmax >= 2) return launch_bwd2<7, 7, 2, true>(p, st);
     return launch_bwd<7, 7, 2, 26>(p, st);  // per-warp tables (v == 3, or PH / PD > 16)
   }
   if (p.PW == 14) {
     if (v == 1 || cvmax == 1) return launch_bwd<14, 7, 1, 40>(p, st);
-    if (v == 2 && cvmax >= 4) return launch_bwd<14, 2, 4, 16>(p, st);
-    if (p.PH <= 16 && p.PD <= 16 && cvmax >= 2) {
-      if (v == 0 || v == 65) return launch_bwd2<14, 2, 2, true, 4>(p, st);  // default: 2 ph rows per warp, 16 warps / SM
-      if (v == 61) return launch_bwd2<14, 4, 2, true>(p, st);
-      if (v == 60) return launch_bwd2<14, 4, 2, false>(p, st);
-      if (v == 62) return launch_bwd2<14, 4, 2, false, 3>(p, st);
-      if (v == 63) return launch_bwd2<14, 4, 2, true, 3>(p, st);
-      if (v == 64) return launch_bwd2<14, 2, 2, true>(p, st);
-      if (v == 66) return launch_bwd2<14, 2, 2, true, 5>(p, st);
-    }
-    if (v == 50) return launch_bwd<14, 4, 2, 30, true>(p, st);
+    if (v == 0 && p.PH <= 16 && p.PD <= 16 && cvmax >= 2) return launch_bwd2<14, 2, 2, true, 4>(p, st);  // 2 ph rows per warp
     return launch_bwd<14, 4, 2, 30>(p, st);  // per-warp tables (v == 3, or PH / PD > 16)
   }
   if (cvmax >= 2) return launch_generic<2>(p, false, st);

@@ -1,0 +1,701 @@
+// RoIAlign3D forward, "streamed" kernel for B200 (sm_100a): persistent CTAs, TMA-fed, warp-specialised.
+//
+// Replaces (reference, /root/reference):
+//   ROIAlignForward3D / bilinear_interpolate_3d   mmdet/ops/roi_align/src/roi_align_kernel.cu:214-291, :64-149
+//   SingleRoIExtractor.forward / map_roi_levels    mmdet/models/roi_extractors/single_level.py:58-104
+//
+// Same separable formulation as roi_align3d.cu (per-axis tap tables built with the compiled reference's rounding
+// sequence, common.cuh), different machine mapping:
+//
+//   * A small plan kernel reduces every RoI once to a 1.2 KB record (FPN level, footprint box, the <= 4 contiguous
+//     taps of each x / y / z bin, TMA tiling) and ranks the RoIs by footprint (largest first) so that the dynamic
+//     schedule of the main kernel ends on its cheapest items.
+//   * The main kernel runs ONE persistent 16-warp CTA per SM.  A work item is (RoI, 64-channel chunk), items are taken
+//     from an atomic counter, chunk-major so that the RoIs of one channel chunk (a quarter of the level: L2-sized) run
+//     together.  Warp 14 is the producer: it streams the item's footprint -- (z, y) rows of RXB voxels x 64 channels
+//     -- into a four-slot shared-memory ring with cp.async.bulk.tensor (TMA, 5-D maps over the channels-last level
+//     [B][D][H][W][C], box = 64 channels x RXB voxels x {1,2,4,8} rows), one mbarrier per slot counting bytes; the
+//     item's plan record rides on the first tile's barrier as a plain bulk copy.
+//   * Warps 0..13 are bin owners: warp (ph, half) holds acc[pd][pw] for its output row ph and its 4 (or 3) pw bins of
+//     all PD slices in registers, lanes = channel pairs (packed FFMA2 arithmetic).  For every feature row of a tile
+//     that carries weight for ph it contracts the row along x (taps at warp-uniform offsets: LDS.64 + FFMA2), folds
+//     it into the slice partial with the y weight, and at the end of a z slice folds the partial into the pd bins
+//     that slice feeds.  Every row is read from HBM/L2 exactly once per item; owners never wait for each other.
+//   * At the end of an item the owners scale by 1 / count and write their bins into a shared-memory image of the
+//     item's [64 channels][PD*49] output block, which is contiguous in the [K, C, PD, PH, PW] output; warp 15 writes
+//     it back with ONE bulk store (cp.async.bulk.global.shared::cta) while the owners already work on the next item.
+//
+// RoIs whose bins need more than four contiguous taps, or whose footprint is wider than the tiles, are flagged by the
+// plan kernel and evaluated literally (reference sample loops, bit-exact) by the same owner warps.
+#include <cuda.h>
+
+#include <mutex>
+#include <vector>
+
+#include "roi_align3d_shared.cuh"
+
+namespace roi3d {
+
+namespace {
+
+constexpr int ST_NSLOT = 4;            // ring slots (tiles in flight + the one being reduced)
+constexpr int ST_SLOT_BYTES = 30720;   // bytes per ring slot
+constexpr int ST_OWNERS = 14;          // 7 output rows x 2 halves of the 7 pw bins
+constexpr int ST_WARPS = 16;           // owners + producer + storer
+constexpr int ST_RMAX = 20;            // widest footprint box in x and y (voxels)
+constexpr int ST_RZMAX = 24;           // deepest footprint box
+constexpr int ST_CH = 64;              // channels per item
+constexpr int ST_XCLS = 10;            // box widths 2, 4, ..., 20 voxels
+constexpr int ST_YCLS = 4;             // box heights 1, 2, 4, 8 rows
+constexpr int ST_MAX_LEVELS = 4;
+constexpr int ST_SORT_MAX = 8192;      // RoIs ranked by footprint up to this K (identity order above)
+
+constexpr int PLAN_EMPTY = 1;          // output is 0 * (1 / count)
+constexpr int PLAN_SLOW = 2;           // literal evaluation
+constexpr int PLAN_X3 = 4;             // every x bin fits three taps
+
+constexpr int TILE_FIRST = 1, TILE_LAST = 2, TILE_DONE = 4;
+
+// One per RoI, written by roi_align3d_plan_kernel, copied to shared memory with the first tile of each item.
+struct alignas(16) StreamPlan {
+  int k, krow, lvl, b;
+  int flags, x0, y0, z0;
+  int RX, RY, RZ, RXB;
+  int rows_per_tile, ntiles, nrows, xcls;
+  float inv_count;
+  int pad[3];
+  int xoff[8];             // first tap of bin pw, voxels from x0 (clamped so that all NT taps stay inside the box)
+  float xw[8][4];
+  int ylo[8];              // first row (from y0) with weight for bin ph, and how many
+  int yn[8];
+  float yw[8][4];
+  float zwd[ST_RZMAX][8];  // dense: weight of slice z (from z0) in bin pd
+};
+static_assert(sizeof(StreamPlan) % 16 == 0, "bulk copies move multiples of 16 bytes");
+constexpr int PLAN_BYTES = (int)sizeof(StreamPlan);
+
+struct TileDesc {
+  int plan, nrows, z, y;      // plan slot; rows in this tile; slice / row (from the box origin) of its first row
+  int flags, rowfloats, chunk, pad;
+};
+
+struct StreamArgs {
+  RoiParams p;
+  const StreamPlan *plans;
+  const int *order;   // rank -> RoI
+  int *counter;
+  const CUtensorMap *maps[ST_MAX_LEVELS];  // [xcls][ycls] per level, device memory
+  int total_items;
+  int pdhw;           // PD * 49
+};
+
+// shared-memory carve-up (bytes from the 1024-aligned base)
+constexpr int SM_RING = 0;
+constexpr int SM_STAGE = SM_RING + ST_NSLOT * ST_SLOT_BYTES;
+constexpr int SM_STAGE_BYTES = ST_CH * 7 * 49 * 4;
+constexpr int SM_PLAN = SM_STAGE + SM_STAGE_BYTES;
+constexpr int SM_TDESC = SM_PLAN + ST_NSLOT * PLAN_BYTES;
+constexpr int SM_SDESC = SM_TDESC + ST_NSLOT * (int)sizeof(TileDesc);
+constexpr int SM_BAR = SM_SDESC + 2 * 16;
+constexpr int SM_TOTAL = SM_BAR + (2 * ST_NSLOT + 2) * 8;
+constexpr int SM_LAUNCH = (SM_TOTAL + 127) / 128 * 128;
+static_assert(SM_STAGE % 128 == 0 && SM_PLAN % 16 == 0 && SM_BAR % 8 == 0, "alignment");
+static_assert(SM_LAUNCH <= 232448, "shared memory budget of one CTA per SM");
+
+// ---- PTX helpers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned s_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void st_mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_mbar_arrive(unsigned mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar) : "memory");
+}
+// Bounded: a protocol error traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void st_mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned ok = 0;
+#pragma unroll 1
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void st_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_tma_5d(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4,
+                                          unsigned mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], "
+      "[%7];\n" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ void st_bulk_s2g(void *dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void add_tap(float (&w)[4], int i, float v) {
+  if (i == 0) w[0] += v;
+  else if (i == 1) w[1] += v;
+  else if (i == 2) w[2] += v;
+  else w[3] += v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Plan kernel: one warp per RoI.  Lanes 0..7 -> x bins, 8..15 -> y bins, 16..23 -> z bins.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p, StreamPlan *plans, int *order, int *counter,
+                                                               int sort) {
+  extern __shared__ float cost_s[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
+
+  // ---- footprint cost of every RoI (each CTA computes all of them: K is small), then the rank of this CTA's RoIs
+  if (sort) {
+    for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
+      float r[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
+      const int lvl = p.num_levels > 1 ? roi_level(r, p.num_levels, p.inv_finest) : 0;
+      const float s = p.lv[lvl].scale, sd = p.lv[lvl].scale_d;
+      const float wx = fminf(fmaxf((r[3] - r[1] + 1.0f) * s, 0.0f), 64.0f) + 2.0f;
+      const float wy = fminf(fmaxf((r[4] - r[2] + 1.0f) * s, 0.0f), 64.0f) + 2.0f;
+      const float wz = fminf(fmaxf((r[6] - r[5] + 1.0f) * sd, 0.0f), 64.0f) + 2.0f;
+      cost_s[k] = wx * wy * wz;
+    }
+    __syncthreads();
+  }
+  const int k = blockIdx.x * 8 + warp;
+  if (k >= p.K) return;
+  if (sort) {
+    const float mine = cost_s[k];
+    int rank = 0;
+    for (int j = lane; j < p.K; j += 32) {
+      const float c = cost_s[j];
+      rank += (c > mine) || (c == mine && j < k);
+    }
+    rank = __reduce_add_sync(FULL, rank);
+    if (lane == 0) order[rank] = k;
+  } else if (lane == 0) {
+    order[k] = k;
+  }
+
+  // ---- the plan
+  float r[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
+  const int lvl = p.num_levels > 1 ? roi_level(r, p.num_levels, p.inv_finest) : 0;
+  const LevelDev L = p.lv[lvl];
+  const int b = (int)r[0];
+  const bool ok = b >= 0 && b < p.B;
+  if (p.lvls_out != nullptr && lane == 0) p.lvls_out[k] = lvl;
+  const Axis axw = axis_setup(r[1], r[3], L.scale, p.PW, p.sample_num);
+  const Axis axh = axis_setup(r[2], r[4], L.scale, p.PH, p.sample_num);
+  const Axis axd = axis_setup(r[5], r[6], L.scale_d, p.PD, p.sample_num);
+
+  const int role = lane >> 3, bin = lane & 7;
+  const int P = role == 0 ? p.PW : role == 1 ? p.PH : role == 2 ? p.PD : 0;
+  const Axis ax = role == 1 ? axh : role == 2 ? axd : axw;
+  const int asize = role == 1 ? L.H : role == 2 ? L.D : L.W;
+  const bool active = bin < P;
+  int lo = INT_MAX, hi = -1;
+  if (active) {
+    for (int i = 0; i < ax.S; ++i) {
+      const Tap t = axis_tap(axis_coord(ax, bin, i), asize);
+      if (t.valid) lo = min(lo, t.low), hi = max(hi, t.high);
+    }
+  }
+  const int n = hi >= lo ? hi - lo + 1 : 0;
+  bool slow = n > 4;
+  float w[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (active && n > 0 && !slow) {
+    for (int i = 0; i < ax.S; ++i) {
+      const Tap t = axis_tap(axis_coord(ax, bin, i), asize);
+      if (t.valid) {
+        add_tap(w, t.low - lo, t.h);
+        add_tap(w, t.high - lo, t.l);
+      }
+    }
+  }
+  const int x0 = __reduce_min_sync(FULL, role == 0 && n > 0 ? lo : INT_MAX);
+  const int x1 = __reduce_max_sync(FULL, role == 0 && n > 0 ? hi : -1);
+  const int y0 = __reduce_min_sync(FULL, role == 1 && n > 0 ? lo : INT_MAX);
+  const int y1 = __reduce_max_sync(FULL, role == 1 && n > 0 ? hi : -1);
+  const int z0 = __reduce_min_sync(FULL, role == 2 && n > 0 ? lo : INT_MAX);
+  const int z1 = __reduce_max_sync(FULL, role == 2 && n > 0 ? hi : -1);
+  const bool empty = !ok || x1 < x0 || y1 < y0 || z1 < z0;
+  const int RX = empty ? 0 : x1 - x0 + 1, RY = empty ? 0 : y1 - y0 + 1, RZ = empty ? 0 : z1 - z0 + 1;
+  slow = __any_sync(FULL, slow) || RX > ST_RMAX || RY > ST_RMAX || RZ > ST_RZMAX;
+  if (empty) slow = false;
+  const bool x3 = !__any_sync(FULL, role == 0 && n > 3);
+  const int NT = x3 ? 3 : 4;
+  const int RXB = max(4, (RX + 1) & ~1);  // box width: even, at least the NT taps of one bin
+  const int rows_per_tile = ST_SLOT_BYTES / (RXB * ST_CH * 4);
+  const bool stream = !empty && !slow;
+  const int nrows = stream ? RY * RZ : 0;
+  const int ntiles = stream ? (nrows + rows_per_tile - 1) / rows_per_tile : 1;
+
+  StreamPlan *pl = plans + k;
+  if (lane == 0) {
+    pl->k = k;
+    pl->krow = p.out_rows != nullptr ? __ldg(p.out_rows + k) : k;
+    pl->lvl = lvl;
+    pl->b = ok ? b : 0;
+    pl->flags = (empty ? PLAN_EMPTY : 0) | (slow ? PLAN_SLOW : 0) | (x3 ? PLAN_X3 : 0);
+    pl->x0 = empty ? 0 : x0, pl->y0 = empty ? 0 : y0, pl->z0 = empty ? 0 : z0;
+    pl->RX = RX, pl->RY = RY, pl->RZ = RZ, pl->RXB = RXB;
+    pl->rows_per_tile = rows_per_tile, pl->ntiles = ntiles, pl->nrows = nrows, pl->xcls = RXB / 2 - 1;
+    // The reference divides by the sample count (roi_align_kernel.cu:288); 1/count is exact for the power-of-two
+    // counts of fixed sample_num and within one ulp otherwise; count == 0 gives inf -> 0 * inf = NaN like its 0/0.
+    pl->inv_count = __frcp_rn((float)(axd.S * axh.S * axw.S));
+    pl->pad[0] = pl->pad[1] = pl->pad[2] = 0;
+  }
+  if (role == 0) {
+    // shift the taps right so that tap NT-1 still lies inside the RXB-wide box (the shifted-in weights are 0)
+    int off = (n > 0 && stream) ? lo - x0 : 0;
+    const int sh = max(0, off + NT - RXB);
+    off -= sh;
+    float ws[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (n > 0 && stream) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (t + sh < 4) add_tap(ws, t + sh, w[t]);
+    }
+    pl->xoff[bin] = off;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) pl->xw[bin][t] = ws[t];
+  } else if (role == 1) {
+    pl->ylo[bin] = (n > 0 && stream) ? lo - y0 : 0;
+    pl->yn[bin] = (n > 0 && stream) ? n : 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) pl->yw[bin][t] = (n > 0 && stream) ? w[t] : 0.0f;
+  } else if (role == 2) {
+    const int zl = (n > 0 && stream) ? lo - z0 : 0;
+    for (int z = 0; z < ST_RZMAX; ++z) {
+      const int t = z - zl;
+      float v = 0.0f;
+      if (n > 0 && stream && t >= 0 && t < n) v = t == 0 ? w[0] : t == 1 ? w[1] : t == 2 ? w[2] : w[3];
+      pl->zwd[z][bin] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Owner: literal evaluation of this owner's bins of a RoI the tap tables cannot express (rare).
+// ---------------------------------------------------------------------------------------------------------------
+template <int NB>
+__device__ __noinline__ void owner_literal(const RoiParams &p, int k, int lvl, int chunk, int ph, int pw0, int lane,
+                                           float *staging, int pdhw) {
+  Item it;
+  it.k = k, it.krow = k, it.chunk = chunk, it.pd = 0, it.ph0 = ph, it.rows = 1, it.lvl = lvl;
+  float r[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
+  it.L = p.lv[lvl];
+  it.b = (int)r[0];
+  it.ok = true;
+  it.axw = axis_setup(r[1], r[3], it.L.scale, p.PW, p.sample_num);
+  it.axh = axis_setup(r[2], r[4], it.L.scale, p.PH, p.sample_num);
+  it.axd = axis_setup(r[5], r[6], it.L.scale_d, p.PD, p.sample_num);
+  const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+  const float *fb = it.L.feats + (long long)it.b * vox * p.C + chunk * ST_CH + lane * 2;
+  for (int pd = 0; pd < p.PD; ++pd)
+    for (int j = 0; j < NB; ++j) {
+      float v[2];
+      literal_bin_fwd<2>(it, fb, p.C, pd, ph, pw0 + j, v);
+      const int idx = pd * 49 + ph * 7 + pw0 + j;
+      staging[(2 * lane) * pdhw + idx] = v[0];
+      staging[(2 * lane + 1) * pdhw + idx] = v[1];
+    }
+}
+
+// x-contraction of one feature row for this owner's NB bins + fold into the slice partial with the y weight
+template <int NT, int NB>
+__device__ __forceinline__ void row_visit(const float *rowp, const int (&xo)[NB], const float (&xw)[NB][4], float wy,
+                                          float2 (&t2)[NB]) {
+  const float2 wy2 = make_float2(wy, wy);
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const float *q = rowp + xo[j];
+    const float2 v0 = *reinterpret_cast<const float2 *>(q);
+    const float2 v1 = *reinterpret_cast<const float2 *>(q + ST_CH);
+    const float2 v2 = *reinterpret_cast<const float2 *>(q + 2 * ST_CH);
+    float2 x = __fmul2_rn(make_float2(xw[j][0], xw[j][0]), v0);
+    x = __ffma2_rn(make_float2(xw[j][1], xw[j][1]), v1, x);
+    x = __ffma2_rn(make_float2(xw[j][2], xw[j][2]), v2, x);
+    if constexpr (NT == 4) {
+      const float2 v3 = *reinterpret_cast<const float2 *>(q + 3 * ST_CH);
+      x = __ffma2_rn(make_float2(xw[j][3], xw[j][3]), v3, x);
+    }
+    t2[j] = __ffma2_rn(wy2, x, t2[j]);
+  }
+}
+
+// All rows of one tile that carry weight for this owner; z fold at the end of every slice the tile completes.
+template <int NT, int NB>
+__device__ __forceinline__ void owner_tile(const TileDesc &d, const StreamPlan *P, const float *tile, int ph, int RY,
+                                           int ylo, int yhi1, const int (&xo)[NB], const float (&xw)[NB][4],
+                                           float2 (&t2)[NB], float2 (&acc)[7][NB]) {
+  int y = d.y, z = d.z, left = d.nrows;
+  const float *rowp = tile;
+  const float *ywp = &P->yw[ph][0];
+  while (left > 0) {
+    const int seg = min(left, RY - y);
+    const int ya = max(y, ylo), yb = min(y + seg, yhi1);
+    for (int yy = ya; yy < yb; ++yy) row_visit<NT, NB>(rowp + (yy - y) * d.rowfloats, xo, xw, ywp[yy - ylo], t2);
+    rowp += seg * d.rowfloats;
+    y += seg, left -= seg;
+    if (y == RY) {
+      const float4 wa = *reinterpret_cast<const float4 *>(&P->zwd[z][0]);
+      const float4 wb = *reinterpret_cast<const float4 *>(&P->zwd[z][4]);
+      const float wz[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+#pragma unroll
+      for (int pd = 0; pd < 7; ++pd) {
+        if (wz[pd] != 0.0f) {
+          const float2 w2 = make_float2(wz[pd], wz[pd]);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) acc[pd][j] = __ffma2_rn(w2, t2[j], acc[pd][j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) t2[j] = make_float2(0.0f, 0.0f);
+      y = 0, ++z;
+    }
+  }
+}
+
+template <int NB>
+__device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *smem, int ph, int pw0, int warp, int lane) {
+  const unsigned bar0 = s_u32(smem + SM_BAR);
+  const unsigned sfull = bar0 + 2 * ST_NSLOT * 8, sfree = sfull + 8;
+  float *staging = reinterpret_cast<float *>(smem + SM_STAGE);
+  const TileDesc *tdesc = reinterpret_cast<const TileDesc *>(smem + SM_TDESC);
+  const int pdhw = a.pdhw;
+  unsigned tile_seq = 0, item_seq = 0;
+  for (;;) {  // items
+    unsigned slot = tile_seq & (ST_NSLOT - 1);
+    st_mbar_wait(bar0 + slot * 8, (tile_seq / ST_NSLOT) & 1);
+    TileDesc d = tdesc[slot];
+    if (d.flags & TILE_DONE) break;
+    const StreamPlan *P = reinterpret_cast<const StreamPlan *>(smem + SM_PLAN + d.plan * PLAN_BYTES);
+    const int pflags = P->flags;
+    if (!(pflags & PLAN_SLOW)) {
+      // ---- streamed item: acc lives in registers from the first tile to the epilogue
+      float2 acc[7][NB], t2[NB];
+      int xo[NB];
+      float xw[NB][4];
+#pragma unroll
+      for (int pd = 0; pd < 7; ++pd)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[pd][j] = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        t2[j] = make_float2(0.0f, 0.0f);
+        xo[j] = P->xoff[pw0 + j] * ST_CH;
+        const float4 w4 = *reinterpret_cast<const float4 *>(&P->xw[pw0 + j][0]);
+        xw[j][0] = w4.x, xw[j][1] = w4.y, xw[j][2] = w4.z, xw[j][3] = w4.w;
+      }
+      const int RY = P->RY, ylo = P->ylo[ph], yhi1 = ylo + P->yn[ph];
+      for (;;) {  // tiles of the item
+        if (d.nrows > 0) {
+          const float *tile = reinterpret_cast<const float *>(smem + SM_RING + slot * ST_SLOT_BYTES) + lane * 2;
+          if (pflags & PLAN_X3)
+            owner_tile<3, NB>(d, P, tile, ph, RY, ylo, yhi1, xo, xw, t2, acc);
+          else
+            owner_tile<4, NB>(d, P, tile, ph, RY, ylo, yhi1, xo, xw, t2, acc);
+        }
+        ++tile_seq;
+        if (d.flags & TILE_LAST) break;
+        __syncwarp();
+        if (lane == 0) st_mbar_arrive(bar0 + (ST_NSLOT + slot) * 8);  // slot free
+        slot = tile_seq & (ST_NSLOT - 1);
+        st_mbar_wait(bar0 + slot * 8, (tile_seq / ST_NSLOT) & 1);
+        d = tdesc[slot];
+      }
+      // the staging image is free once the storer has read out the previous item
+      st_mbar_wait(sfree, (item_seq & 1) ^ 1);
+      const float inv = P->inv_count;
+      const float2 inv2 = make_float2(inv, inv);
+      float *s0 = staging + (2 * lane) * pdhw + ph * 7 + pw0;
+#pragma unroll
+      for (int pd = 0; pd < 7; ++pd) {
+        if (pd * 49 < pdhw) {
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const float2 v = __fmul2_rn(acc[pd][j], inv2);
+            s0[pd * 49 + j] = v.x;
+            s0[pdhw + pd * 49 + j] = v.y;
+          }
+        }
+      }
+    } else {
+      // ---- literal item (one descriptor-only tile)
+      ++tile_seq;
+      st_mbar_wait(sfree, (item_seq & 1) ^ 1);
+      owner_literal<NB>(a.p, P->k, P->lvl, d.chunk, ph, pw0, lane, staging, pdhw);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the bulk store
+    if (warp == 0 && lane == 0) {
+      int *sd = reinterpret_cast<int *>(smem + SM_SDESC + (item_seq & 1) * 16);
+      sd[0] = P->krow, sd[1] = d.chunk, sd[2] = 0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      st_mbar_arrive(bar0 + (ST_NSLOT + slot) * 8);  // the item's last slot and its plan record are free
+      st_mbar_arrive(sfull);
+    }
+    ++item_seq;
+  }
+  // no more items: tell the storer.  Like an item's arrivals these wait for the previous hand-back of the staging
+  // image, otherwise an owner that runs ahead would arrive twice in the phase of the item the others still write.
+  st_mbar_wait(sfree, (item_seq & 1) ^ 1);
+  if (lane == 0) {
+    if (warp == 0) reinterpret_cast<int *>(smem + SM_SDESC + (item_seq & 1) * 16)[2] = 1;
+    st_mbar_arrive(sfull);
+  }
+}
+
+__global__ void __launch_bounds__(ST_WARPS * 32, 1) roi_align3d_fwd_stream_kernel(const __grid_constant__ StreamArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];  // no static shared memory: the window starts at offset 0
+  if ((s_u32(smem) & 127u) != 0) __trap();                  // TMA destinations need 128-byte alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned bar0 = s_u32(smem + SM_BAR);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST_NSLOT; ++s) {
+      st_mbar_init(bar0 + s * 8, 1);                      // full: the producer's arrive + the tile's bytes
+      st_mbar_init(bar0 + (ST_NSLOT + s) * 8, ST_OWNERS);  // empty: one arrive per owner warp
+    }
+    st_mbar_init(bar0 + 2 * ST_NSLOT * 8, ST_OWNERS);      // staging full
+    st_mbar_init(bar0 + 2 * ST_NSLOT * 8 + 8, 1);          // staging free
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp < ST_OWNERS) {
+    if (warp < 7) owner_loop<4>(a, smem, warp, 0, warp, lane);
+    else owner_loop<3>(a, smem, warp - 7, 4, warp, lane);
+    return;
+  }
+
+  if (warp == ST_OWNERS) {
+    // ---- producer: one lane walks the items, issues the plan copy and the TMA tiles
+    if (lane != 0) return;
+    TileDesc *tdesc = reinterpret_cast<TileDesc *>(smem + SM_TDESC);
+    const int K = a.p.K;
+    unsigned tile_seq = 0, item_seq = 0;
+    for (;;) {
+      const int idx = atomicAdd(a.counter, 1);
+      if (idx >= a.total_items) break;
+      const int chunk = idx / K;
+      const int k = __ldg(a.order + (idx - chunk * K));
+      const StreamPlan *pg = a.plans + k;
+      const int4 h0 = __ldg(reinterpret_cast<const int4 *>(pg));      // k, krow, lvl, b
+      const int4 h1 = __ldg(reinterpret_cast<const int4 *>(pg) + 1);  // flags, x0, y0, z0
+      const int4 h2 = __ldg(reinterpret_cast<const int4 *>(pg) + 2);  // RX, RY, RZ, RXB
+      const int4 h3 = __ldg(reinterpret_cast<const int4 *>(pg) + 3);  // rows_per_tile, ntiles, nrows, xcls
+      const int lvl = h0.z, b = h0.w, x0 = h1.y, y0 = h1.z, z0 = h1.w;
+      const int RY = h2.y, RXB = h2.w, rpt = h3.x, ntiles = h3.y, nrows = h3.z, xcls = h3.w;
+      const int rowbytes = RXB * ST_CH * 4;
+      const CUtensorMap *maps = a.maps[lvl] + xcls * ST_YCLS;
+      const unsigned pslot = item_seq & (ST_NSLOT - 1);
+      int r = 0, y = 0, z = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const unsigned slot = tile_seq & (ST_NSLOT - 1);
+        st_mbar_wait(bar0 + (ST_NSLOT + slot) * 8, ((tile_seq / ST_NSLOT) & 1) ^ 1);
+        const int tr = min(rpt, nrows - r);
+        TileDesc d;
+        d.plan = (int)pslot, d.nrows = tr, d.z = z, d.y = y;
+        d.flags = (t == 0 ? TILE_FIRST : 0) | (t == ntiles - 1 ? TILE_LAST : 0);
+        d.rowfloats = RXB * ST_CH, d.chunk = chunk, d.pad = 0;
+        tdesc[slot] = d;
+        const unsigned full = bar0 + slot * 8;
+        st_mbar_expect_tx(full, (unsigned)(tr * rowbytes + (t == 0 ? PLAN_BYTES : 0)));
+        if (t == 0) st_bulk_g2s(s_u32(smem + SM_PLAN + pslot * PLAN_BYTES), pg, PLAN_BYTES, full);
+        unsigned dst = s_u32(smem + SM_RING + slot * ST_SLOT_BYTES);
+        int left = tr;
+        while (left > 0) {
+          int seg = min(left, RY - y);
+          left -= seg, r += seg;
+          int yy = y;
+          y += seg;
+          while (seg > 0) {
+            const int yc = seg >= 8 ? 3 : seg >= 4 ? 2 : seg >= 2 ? 1 : 0;
+            const int nr = 1 << yc;
+            st_tma_5d(dst, maps + yc, chunk * ST_CH, x0, y0 + yy, z0 + z, b, full);
+            dst += nr * rowbytes, yy += nr, seg -= nr;
+          }
+          if (y == RY) y = 0, ++z;
+        }
+        ++tile_seq;
+      }
+      ++item_seq;
+    }
+    // sentinel tile
+    const unsigned slot = tile_seq & (ST_NSLOT - 1);
+    st_mbar_wait(bar0 + (ST_NSLOT + slot) * 8, ((tile_seq / ST_NSLOT) & 1) ^ 1);
+    TileDesc d;
+    d.plan = 0, d.nrows = 0, d.z = 0, d.y = 0, d.flags = TILE_DONE, d.rowfloats = 0, d.chunk = 0, d.pad = 0;
+    tdesc[slot] = d;
+    st_mbar_arrive(bar0 + slot * 8);
+    return;
+  }
+
+  // ---- storer: one bulk store per item, the staging image is handed back as soon as it has been read
+  if (lane != 0) return;
+  const unsigned sfull = bar0 + 2 * ST_NSLOT * 8, sfree = sfull + 8;
+  const unsigned stage_s = s_u32(smem + SM_STAGE);
+  const unsigned bytes = (unsigned)(ST_CH * a.pdhw * 4);
+  for (unsigned n = 0;; ++n) {
+    st_mbar_wait(sfull, n & 1);
+    const int *sd = reinterpret_cast<const int *>(smem + SM_SDESC + (n & 1) * 16);
+    if (sd[2]) break;
+    float *dst = a.p.out + ((long long)sd[0] * a.p.C + (long long)sd[1] * ST_CH) * a.pdhw;
+    st_bulk_s2g(dst, stage_s, bytes);
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    st_mbar_arrive(sfree);
+  }
+  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+}
+
+// ---- host: tensor maps -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// Device-resident map tables, one per (device, level pointer, shape): a detector hands the same FPN buffers to the
+// extractor call after call, so the 40 descriptors of a level are encoded and uploaded once.  Entries are immutable;
+// the oldest is dropped with cudaFree (which waits for the device) when the cache is full.
+struct MapEntry {
+  int dev;
+  const void *ptr;
+  int B, C, D, H, W;
+  CUtensorMap *maps_dev;
+};
+std::mutex g_map_mutex;
+std::vector<MapEntry> g_map_cache;
+constexpr size_t MAP_CACHE_MAX = 64;
+
+int level_maps(const LevelDev &L, int B, int C, const CUtensorMap **out) {
+  int dev = 0;
+  ROI3D_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  for (size_t i = 0; i < g_map_cache.size(); ++i) {
+    const MapEntry &e = g_map_cache[i];
+    if (e.dev == dev && e.ptr == L.feats && e.B == B && e.C == C && e.D == L.D && e.H == L.H && e.W == L.W) {
+      *out = e.maps_dev;
+      return ROI3D_OK;
+    }
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ROI3D_ECUDA;
+  }
+  CUtensorMap host[ST_XCLS * ST_YCLS];
+  const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)L.D, (cuuint64_t)B};
+  const cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)L.W * C * 4, (cuuint64_t)L.H * L.W * C * 4,
+                                 (cuuint64_t)L.D * L.H * L.W * C * 4};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int xc = 0; xc < ST_XCLS; ++xc)
+    for (int yc = 0; yc < ST_YCLS; ++yc) {
+      const cuuint32_t box[5] = {(cuuint32_t)ST_CH, (cuuint32_t)(2 * (xc + 1)), (cuuint32_t)(1 << yc), 1, 1};
+      const CUresult r = enc(&host[xc * ST_YCLS + yc], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(L.feats),
+                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d) for a %dx%dx%dx%dx%d level", (int)r, B, C, L.D, L.H, L.W);
+        return ROI3D_ECUDA;
+      }
+    }
+  if (g_map_cache.size() >= MAP_CACHE_MAX) {
+    cudaFree(g_map_cache.front().maps_dev);
+    g_map_cache.erase(g_map_cache.begin());
+  }
+  MapEntry e;
+  e.dev = dev, e.ptr = L.feats, e.B = B, e.C = C, e.D = L.D, e.H = L.H, e.W = L.W, e.maps_dev = nullptr;
+  ROI3D_CUDA(cudaMalloc(&e.maps_dev, sizeof(host)));
+  ROI3D_CUDA(cudaMemcpy(e.maps_dev, host, sizeof(host), cudaMemcpyHostToDevice));
+  g_map_cache.push_back(e);
+  *out = e.maps_dev;
+  return ROI3D_OK;
+}
+
+}  // namespace
+
+bool fwd_stream_ok(const RoiParams &p) {
+  if (p.PW != 7 || p.PH != 7 || p.PD < 1 || p.PD > 7) return false;
+  if (p.C % ST_CH != 0 || p.num_levels > ST_MAX_LEVELS) return false;
+  if (p.out_rows != nullptr) return false;  // row-mapped output may be mapped host memory: kept on the ring kernel
+  if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return false;
+  if ((long long)p.K * (p.C / ST_CH) >= 2147483647LL) return false;
+  for (int l = 0; l < p.num_levels; ++l) {
+    if ((reinterpret_cast<uintptr_t>(p.lv[l].feats) & 15) != 0) return false;
+    if ((long long)p.lv[l].D * p.lv[l].H * p.lv[l].W * p.C * 4 >= (1LL << 40)) return false;  // TMA stride field
+  }
+  return true;
+}
+
+int launch_fwd_stream(RoiParams &p, cudaStream_t st) {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    ROI3D_CUDA(cudaGetDevice(&dev));
+    ROI3D_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  StreamArgs a;
+  a.p = p;
+  for (int l = 0; l < ST_MAX_LEVELS; ++l) a.maps[l] = nullptr;
+  for (int l = 0; l < p.num_levels; ++l) {
+    const int rc = level_maps(p.lv[l], p.B, p.C, &a.maps[l]);
+    if (rc) return rc;
+  }
+  // plans + order + counter from the stream-ordered pool: no host sync, re-entrant across streams
+  const size_t plan_bytes = (size_t)p.K * sizeof(StreamPlan);
+  const size_t ws_bytes = plan_bytes + ((size_t)p.K + 4) * sizeof(int);
+  unsigned char *ws = nullptr;
+  ROI3D_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), ws_bytes, st));
+  StreamPlan *plans = reinterpret_cast<StreamPlan *>(ws);
+  int *order = reinterpret_cast<int *>(ws + plan_bytes);
+  int *counter = order + p.K;
+  const int sort = p.K <= ST_SORT_MAX ? 1 : 0;
+  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(p, plans, order, counter, sort);
+  ROI3D_LAUNCH_CHECK();
+  a.plans = plans, a.order = order, a.counter = counter;
+  a.total_items = p.K * (p.C / ST_CH);
+  a.pdhw = p.PD * 49;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SM_LAUNCH));
+    attr_set = true;
+  }
+  const int grid = a.total_items < sm_count ? a.total_items : sm_count;
+  roi_align3d_fwd_stream_kernel<<<grid, ST_WARPS * 32, SM_LAUNCH, st>>>(a);
+  ROI3D_LAUNCH_CHECK();
+  ROI3D_CUDA(cudaFreeAsync(ws, st));
+  return ROI3D_OK;
+}
+
+}  // namespace roi3d

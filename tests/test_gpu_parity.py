@@ -824,27 +824,69 @@ def test_grid_anchors_and_inside_flags_match_oracle(oracle, dev, case):
         assert 0 < int(f2.sum()) < f2.numel()
 
 
+STREAM_CASES = [
+    # (B, C, D, H, W), out_size_depth, scale, scale_d, sample_num, n_rois, roi image size (W, H, D)
+    ((2, 128, 10, 24, 40), 7, 0.25, 0.5, 2, 120, (160, 96, 20)),    # two chunks, more items than SMs
+    ((1, 64, 12, 40, 40), 3, 0.25, 0.5, 2, 60, (160, 160, 24)),     # real-config bbox shape 7x7x3
+    ((1, 64, 24, 96, 96), 7, 0.25, 0.5, 2, 40, (384, 384, 48)),     # c2-sized RoIs: multi-tile items, x boxes up to 20
+    ((1, 64, 10, 20, 20), 7, 0.25, 0.5, 0, 30, (80, 80, 20)),       # adaptive sampling (S = ceil(bin))
+    ((2, 64, 6, 12, 12), 7, 0.125, 0.25, 3, 30, (96, 96, 24)),      # three samples per bin, coarse level
+    ((1, 192, 9, 14, 15), 1, 0.25, 0.5, 1, 20, (60, 56, 18)),       # one output slice, one sample per bin
+]
+
+
 @pytest.mark.gpu
-def test_roi_align_forward_slab_variant(oracle, dev):
-    """Tuning variant 80 (specialised-warp slab kernel, 7-wide outputs): same tolerance against the oracle as the
-    default kernel, for 7x7x7 and 7x7x3 outputs, several channel chunks, adversarial and wide RoIs."""
+@pytest.mark.parametrize("case", STREAM_CASES)
+def test_roi_align_forward_streamed_kernel(oracle, dev, case):
+    """The persistent TMA-fed kernel (7x7xPD outputs, C % 64 == 0, channels-last): oracle tolerance, and the per-warp
+    ring kernel (tuning variant 50) on the same inputs beside it."""
     import roi3d_b200
     from roi3d_b200.ops import RoIAlign3D
-    shape = (2, 160, 10, 24, 40)
+    shape, pdp, sc, scd, sn, k, img = case
+    B, C, D, H, W = shape
     f = _feats(shape, 33)
-    rois = np.concatenate([synth.c2_rois(40, seed=6, img=(160, 96, 20), batch=2),
-                           synth.adversarial_rois(shape[2:], 0.25, 0.5, batch=2),
-                           np.array([[1, 2, 3, 150, 90, 1, 12]], np.float32)], 0)
+    rois = np.concatenate([synth.c2_rois(k, seed=6, img=img, batch=B),
+                           synth.adversarial_rois(shape[2:], sc, scd, batch=B),
+                           np.array([[B - 1, 2, 3, img[0] - 4, img[1] - 6, 1, img[2] - 3]], np.float32)], 0)
+    if sn == 0:
+        ok = (rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2]) & (rois[:, 6] >= rois[:, 5])
+        rois = rois[ok]
     ft = cl(torch.from_numpy(f).to(dev))
     rt = torch.from_numpy(rois).to(dev)
-    roi3d_b200._lib.set_tuning(0, 80)
+    want = oracle.roi_align3d_forward(f, rois, 7, pdp, sc, scd, sn)
+    layer = RoIAlign3D(7, pdp, sc, scd, sn)
+    out = layer(ft, rt)
+    assert rel_err(out.cpu().numpy(), want) <= FWD_TOL
+    roi3d_b200._lib.set_tuning(0, 50)
     try:
-        for pdp in (7, 3):
-            want = oracle.roi_align3d_forward(f, rois, 7, pdp, 0.25, 0.5, 2)
-            out = RoIAlign3D(7, pdp, 0.25, 0.5, 2)(ft, rt)
-            assert rel_err(out.cpu().numpy(), want) <= FWD_TOL
+        ring = layer(ft, rt)
     finally:
         roi3d_b200._lib.set_tuning(0, 0)
+    assert rel_err(out.cpu().numpy(), ring.cpu().numpy()) <= FWD_TOL
+    # a second call on the same buffers (cached tensor maps, recycled workspace) gives the same bits
+    assert torch.equal(layer(ft, rt), out)
+
+
+@pytest.mark.gpu
+def test_roi_align_streamed_kernel_two_streams(oracle, dev):
+    """Two streams run the streamed kernel concurrently on different inputs: per-call workspaces, no shared scratch."""
+    from roi3d_b200.ops import RoIAlign3D
+    layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
+    fs = [_feats((1, 64, 10, 32, 32), 40 + i) for i in range(2)]
+    rs = [synth.c2_rois(150, seed=50 + i, img=(128, 128, 20)) for i in range(2)]
+    want = [oracle.roi_align3d_forward(f, r, 7, 7, 0.25, 0.5, 2) for f, r in zip(fs, rs)]
+    fts = [cl(torch.from_numpy(f).to(dev)) for f in fs]
+    rts = [torch.from_numpy(r).to(dev) for r in rs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    outs = [None, None]
+    for _ in range(3):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                outs[i] = layer(fts[i], rts[i])
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert rel_err(outs[i].cpu().numpy(), want[i]) <= FWD_TOL
 
 
 # ---------------------------------------------------------------------------------------------------------------
