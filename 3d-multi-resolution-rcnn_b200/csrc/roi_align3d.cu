@@ -1715,6 +1715,7 @@ static int transpose_launch(const float *src, float *dst, int B, int rows, int c
 static int g_fwd_variant = 0;  // 0 = auto; see roi3d_set_tuning
 static int g_fwd_items_per_warp = 0;  // 0 = auto
 extern int g_host_pipeline_kb;        // host_api.cu
+extern int g_fwd_stream_cfg, g_fwd_stream_debug;  // roi_align3d_stream.cu  // roi_align3d_stream.cu
 extern int g_nms_mask_variant;        // nms3d.cu
 static int g_bwd_variant = 0;
 
@@ -1757,53 +1758,6 @@ static int launch_fwd_ring(RoiParams &p, cudaStream_t st) {
   return ROI3D_OK;
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void *ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(ptr);
-  }();
-  return fn;
-}
-
-// Fills one descriptor per level: tensor [B*D*H*W voxels][C channels] fp32, box = box_vox voxels x box_ch channels.
-static int build_tmaps(const RoiParams &p, int box_vox, int box_ch, TmapSet &tm) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc) {
-    set_error("cuTensorMapEncodeTiled is not available from this driver");
-    return ROI3D_ECUDA;
-  }
-  for (int l = 0; l < p.num_levels; ++l) {
-    const cuuint64_t dims[2] = {(cuuint64_t)p.C, (cuuint64_t)p.B * p.lv[l].D * p.lv[l].H * p.lv[l].W};
-    const cuuint64_t strides[1] = {(cuuint64_t)p.C * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)box_ch, (cuuint32_t)box_vox};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&tm.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p.lv[l].feats), dims, strides,
-                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
-      return ROI3D_ECUDA;
-    }
-  }
-  return ROI3D_OK;
-}
-
-// TMA mode needs whole 32*CV-channel chunks, 16-byte aligned levels (checked by the caller) and int voxel indices.
-static bool tma_ok(const RoiParams &p, int vox_chunk) {
-  if (p.C % vox_chunk != 0) return false;
-  for (int l = 0; l < p.num_levels; ++l)
-    if ((long long)p.B * p.lv[l].D * p.lv[l].H * p.lv[l].W >= 2147483647LL - 64) return false;
-  return true;
-}
-
 template <int PW, int ROWS, int CV, int NXU, int NS, int RXR, int MINB = 0, int BULK = 0, bool F2 = false, bool MULTI = false, int ITEMS = 1>
 static int launch_fwd_ring2(RoiParams &p, cudaStream_t st) {
   using LY = Ring2Layout<PW, ROWS, CV, NS, RXR, BULK>;
@@ -1816,11 +1770,8 @@ static int launch_fwd_ring2(RoiParams &p, cudaStream_t st) {
   p.total_items = (long long)p.K * p.items_per_roi;
   const long long blocks = (long long)p.K * p.ctas_per_roi;
   ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
-  static TmapSet tm;  // only the TMA instantiations read it
-  if constexpr (BULK == 2) {
-    const int rc = build_tmaps(p, RXR, 32 * CV, tm);
-    if (rc) return rc;
-  }
+  static_assert(BULK == 0, "the bulk-copy / TMA row rings were measured slower and are not instantiated");
+  static TmapSet tm;  // kernel argument of the (uninstantiated) TMA row ring
   auto kern = roi_align3d_fwd_ring2_kernel<PW, ROWS, CV, NXU, NS, RXR, MINB, BULK, F2, MULTI>;
   ROI3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, kWarps * 32, smem, st>>>(p, tm);
@@ -1993,6 +1944,8 @@ int roi3d_set_tuning(int key, int value) {
   else if (key == 2) g_fwd_items_per_warp = value;
   else if (key == 4) g_host_pipeline_kb = value;
   else if (key == 6) g_nms_mask_variant = value;
+  else if (key == 7) g_fwd_stream_cfg = value;
+  else if (key == 9) g_fwd_stream_debug = value;
   else return ROI3D_EINVAL;
   return ROI3D_OK;
 }

@@ -38,8 +38,6 @@ namespace roi3d {
 
 namespace {
 
-constexpr int ST_NSLOT = 4;            // ring slots (tiles in flight + the one being reduced)
-constexpr int ST_SLOT_BYTES = 30720;   // bytes per ring slot
 constexpr int ST_OWNERS = 14;          // 7 output rows x 2 halves of the 7 pw bins
 constexpr int ST_WARPS = 16;           // owners + producer + storer
 constexpr int ST_RMAX = 20;            // widest footprint box in x and y (voxels)
@@ -49,6 +47,7 @@ constexpr int ST_XCLS = 10;            // box widths 2, 4, ..., 20 voxels
 constexpr int ST_YCLS = 4;             // box heights 1, 2, 4, 8 rows
 constexpr int ST_MAX_LEVELS = 4;
 constexpr int ST_SORT_MAX = 8192;      // RoIs ranked by footprint up to this K (identity order above)
+constexpr int ST_MAX_TILE_ROWS = 32;   // one producer lane per tile row
 
 constexpr int PLAN_EMPTY = 1;          // output is 0 * (1 / count)
 constexpr int PLAN_SLOW = 2;           // literal evaluation
@@ -56,14 +55,15 @@ constexpr int PLAN_X3 = 4;             // every x bin fits three taps
 
 constexpr int TILE_FIRST = 1, TILE_LAST = 2, TILE_DONE = 4;
 
-// One per RoI, written by roi_align3d_plan_kernel, copied to shared memory with the first tile of each item.
+// One per RoI, written by roi_align3d_plan_kernel in schedule order (largest footprint first), copied to shared
+// memory with the first tile of each item.  The first 16 words are the header the producer reads.
 struct alignas(16) StreamPlan {
   int k, krow, lvl, b;
   int flags, x0, y0, z0;
   int RX, RY, RZ, RXB;
   int rows_per_tile, ntiles, nrows, xcls;
   float inv_count;
-  int pad[3];
+  int spt, tps, pad;       // spt = ceil(2^16 / RY): (row * spt) >> 16 == row / RY for the rows of a tile
   int xoff[8];             // first tap of bin pw, voxels from x0 (clamped so that all NT taps stay inside the box)
   float xw[8][4];
   int ylo[8];              // first row (from y0) with weight for bin ph, and how many
@@ -81,26 +81,30 @@ struct TileDesc {
 
 struct StreamArgs {
   RoiParams p;
-  const StreamPlan *plans;
-  const int *order;   // rank -> RoI
+  const StreamPlan *plans;  // schedule order
   int *counter;
   const CUtensorMap *maps[ST_MAX_LEVELS];  // [xcls][ycls] per level, device memory
   int total_items;
   int pdhw;           // PD * 49
+  int debug;          // developer experiments: bit 0 = owners skip the arithmetic, bit 1 = no output store
 };
 
-// shared-memory carve-up (bytes from the 1024-aligned base)
-constexpr int SM_RING = 0;
-constexpr int SM_STAGE = SM_RING + ST_NSLOT * ST_SLOT_BYTES;
-constexpr int SM_STAGE_BYTES = ST_CH * 7 * 49 * 4;
-constexpr int SM_PLAN = SM_STAGE + SM_STAGE_BYTES;
-constexpr int SM_TDESC = SM_PLAN + ST_NSLOT * PLAN_BYTES;
-constexpr int SM_SDESC = SM_TDESC + ST_NSLOT * (int)sizeof(TileDesc);
-constexpr int SM_BAR = SM_SDESC + 2 * 16;
-constexpr int SM_TOTAL = SM_BAR + (2 * ST_NSLOT + 2) * 8;
-constexpr int SM_LAUNCH = (SM_TOTAL + 127) / 128 * 128;
-static_assert(SM_STAGE % 128 == 0 && SM_PLAN % 16 == 0 && SM_BAR % 8 == 0, "alignment");
-static_assert(SM_LAUNCH <= 232448, "shared memory budget of one CTA per SM");
+// shared-memory carve-up (bytes from the base) for a ring of NS slots of SLOT bytes
+template <int NS, int SLOT>
+struct Lay {
+  static_assert(NS >= 2 && SLOT % 128 == 0, "ring geometry");
+  static constexpr int RING = 0;
+  static constexpr int STAGE = RING + NS * SLOT;
+  static constexpr int STAGE_BYTES = ST_CH * 7 * 49 * 4;
+  static constexpr int PLAN = STAGE + STAGE_BYTES;
+  static constexpr int TDESC = PLAN + NS * PLAN_BYTES;
+  static constexpr int SDESC = TDESC + NS * (int)sizeof(TileDesc);
+  static constexpr int BAR = SDESC + 2 * 16;   // full[NS], empty[NS], staging full, staging free
+  static constexpr int TOTAL = BAR + (2 * NS + 2) * 8;
+  static constexpr int LAUNCH = (TOTAL + 127) / 128 * 128;
+  static_assert(STAGE % 128 == 0 && PLAN % 16 == 0 && BAR % 8 == 0, "alignment");
+  static_assert(LAUNCH <= 232448, "shared memory budget of one CTA per SM");
+};
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned s_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -154,8 +158,8 @@ __device__ __forceinline__ void add_tap(float (&w)[4], int i, float v) {
 // ---------------------------------------------------------------------------------------------------------------
 // Plan kernel: one warp per RoI.  Lanes 0..7 -> x bins, 8..15 -> y bins, 16..23 -> z bins.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p, StreamPlan *plans, int *order, int *counter,
-                                                               int sort) {
+__global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p, StreamPlan *plans, int *counter, int sort,
+                                                               int slot_bytes) {
   extern __shared__ float cost_s[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
@@ -177,17 +181,15 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
   }
   const int k = blockIdx.x * 8 + warp;
   if (k >= p.K) return;
+  int rank = k;
   if (sort) {
     const float mine = cost_s[k];
-    int rank = 0;
+    rank = 0;
     for (int j = lane; j < p.K; j += 32) {
       const float c = cost_s[j];
       rank += (c > mine) || (c == mine && j < k);
     }
     rank = __reduce_add_sync(FULL, rank);
-    if (lane == 0) order[rank] = k;
-  } else if (lane == 0) {
-    order[k] = k;
   }
 
   // ---- the plan
@@ -240,12 +242,14 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
   const bool x3 = !__any_sync(FULL, role == 0 && n > 3);
   const int NT = x3 ? 3 : 4;
   const int RXB = max(4, (RX + 1) & ~1);  // box width: even, at least the NT taps of one bin
-  const int rows_per_tile = ST_SLOT_BYTES / (RXB * ST_CH * 4);
+  // Tiling: consecutive (z, y) rows of the footprint, as many as fit a ring slot (one producer lane per row).
+  const int rows_per_tile = min(ST_MAX_TILE_ROWS, slot_bytes / (RXB * ST_CH * 4));
   const bool stream = !empty && !slow;
   const int nrows = stream ? RY * RZ : 0;
   const int ntiles = stream ? (nrows + rows_per_tile - 1) / rows_per_tile : 1;
+  const int spt = stream ? (65536 + RY - 1) / RY : 0, tps = 0;  // spt: 2^16 / RY rounded up (row -> slice without a division)
 
-  StreamPlan *pl = plans + k;
+  StreamPlan *pl = plans + rank;
   if (lane == 0) {
     pl->k = k;
     pl->krow = p.out_rows != nullptr ? __ldg(p.out_rows + k) : k;
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
     // The reference divides by the sample count (roi_align_kernel.cu:288); 1/count is exact for the power-of-two
     // counts of fixed sample_num and within one ulp otherwise; count == 0 gives inf -> 0 * inf = NaN like its 0/0.
     pl->inv_count = __frcp_rn((float)(axd.S * axh.S * axw.S));
-    pl->pad[0] = pl->pad[1] = pl->pad[2] = 0;
+    pl->spt = spt, pl->tps = tps, pl->pad = 0;
   }
   if (role == 0) {
     // shift the taps right so that tap NT-1 still lies inside the RXB-wide box (the shifted-in weights are 0)
@@ -342,18 +346,19 @@ __device__ __forceinline__ void row_visit(const float *rowp, const int (&xo)[NB]
 }
 
 // All rows of one tile that carry weight for this owner; z fold at the end of every slice the tile completes.
+// The tile holds rows [y, y + nrows) of the footprint's (slice, row) sequence starting in slice z.
 template <int NT, int NB>
-__device__ __forceinline__ void owner_tile(const TileDesc &d, const StreamPlan *P, const float *tile, int ph, int RY,
-                                           int ylo, int yhi1, const int (&xo)[NB], const float (&xw)[NB][4],
+__device__ __forceinline__ void owner_tile(int nrows, int z, int y, int rowfloats, const StreamPlan *P, const float *tile,
+                                           int ph, int RY, int ylo, int yhi1, const int (&xo)[NB], const float (&xw)[NB][4],
                                            float2 (&t2)[NB], float2 (&acc)[7][NB]) {
-  int y = d.y, z = d.z, left = d.nrows;
+  int left = nrows;
   const float *rowp = tile;
   const float *ywp = &P->yw[ph][0];
   while (left > 0) {
     const int seg = min(left, RY - y);
     const int ya = max(y, ylo), yb = min(y + seg, yhi1);
-    for (int yy = ya; yy < yb; ++yy) row_visit<NT, NB>(rowp + (yy - y) * d.rowfloats, xo, xw, ywp[yy - ylo], t2);
-    rowp += seg * d.rowfloats;
+    for (int yy = ya; yy < yb; ++yy) row_visit<NT, NB>(rowp + (yy - y) * rowfloats, xo, xw, ywp[yy - ylo], t2);
+    rowp += seg * rowfloats;
     y += seg, left -= seg;
     if (y == RY) {
       const float4 wa = *reinterpret_cast<const float4 *>(&P->zwd[z][0]);
@@ -374,20 +379,25 @@ __device__ __forceinline__ void owner_tile(const TileDesc &d, const StreamPlan *
   }
 }
 
-template <int NB>
+// Owner warp.  The first tile of an item carries the plan record (or the end-of-work mark); every tile has a descriptor
+// (rows, first slice / row) written by the producer before it arms the slot's barrier.
+// (Tried and dropped: letting an owner skip the wait for tiles that hold none of its rows -- slower, and a parity
+// wait can alias once a warp is more than one use of a slot ahead.)
+template <int NB, int NS, int SLOT>
 __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *smem, int ph, int pw0, int warp, int lane) {
-  const unsigned bar0 = s_u32(smem + SM_BAR);
-  const unsigned sfull = bar0 + 2 * ST_NSLOT * 8, sfree = sfull + 8;
-  float *staging = reinterpret_cast<float *>(smem + SM_STAGE);
-  const TileDesc *tdesc = reinterpret_cast<const TileDesc *>(smem + SM_TDESC);
+  using L = Lay<NS, SLOT>;
+  const unsigned bar0 = s_u32(smem + L::BAR);
+  const unsigned sfull = bar0 + 2 * NS * 8, sfree = sfull + 8;
+  float *staging = reinterpret_cast<float *>(smem + L::STAGE);
+  const TileDesc *tdesc = reinterpret_cast<const TileDesc *>(smem + L::TDESC);
   const int pdhw = a.pdhw;
   unsigned tile_seq = 0, item_seq = 0;
   for (;;) {  // items
-    unsigned slot = tile_seq & (ST_NSLOT - 1);
-    st_mbar_wait(bar0 + slot * 8, (tile_seq / ST_NSLOT) & 1);
-    TileDesc d = tdesc[slot];
+    unsigned slot = tile_seq % NS;
+    st_mbar_wait(bar0 + slot * 8, (tile_seq / NS) & 1);
+    const TileDesc d = tdesc[slot];
     if (d.flags & TILE_DONE) break;
-    const StreamPlan *P = reinterpret_cast<const StreamPlan *>(smem + SM_PLAN + d.plan * PLAN_BYTES);
+    const StreamPlan *P = reinterpret_cast<const StreamPlan *>(smem + L::PLAN + d.plan * PLAN_BYTES);
     const int pflags = P->flags;
     if (!(pflags & PLAN_SLOW)) {
       // ---- streamed item: acc lives in registers from the first tile to the epilogue
@@ -406,21 +416,22 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
         xw[j][0] = w4.x, xw[j][1] = w4.y, xw[j][2] = w4.z, xw[j][3] = w4.w;
       }
       const int RY = P->RY, ylo = P->ylo[ph], yhi1 = ylo + P->yn[ph];
+      TileDesc dt = d;
       for (;;) {  // tiles of the item
-        if (d.nrows > 0) {
-          const float *tile = reinterpret_cast<const float *>(smem + SM_RING + slot * ST_SLOT_BYTES) + lane * 2;
+        if (dt.nrows > 0 && !(a.debug & 1)) {
+          const float *tile = reinterpret_cast<const float *>(smem + L::RING + slot * SLOT) + lane * 2;
           if (pflags & PLAN_X3)
-            owner_tile<3, NB>(d, P, tile, ph, RY, ylo, yhi1, xo, xw, t2, acc);
+            owner_tile<3, NB>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph, RY, ylo, yhi1, xo, xw, t2, acc);
           else
-            owner_tile<4, NB>(d, P, tile, ph, RY, ylo, yhi1, xo, xw, t2, acc);
+            owner_tile<4, NB>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph, RY, ylo, yhi1, xo, xw, t2, acc);
         }
         ++tile_seq;
-        if (d.flags & TILE_LAST) break;
+        if (dt.flags & TILE_LAST) break;
         __syncwarp();
-        if (lane == 0) st_mbar_arrive(bar0 + (ST_NSLOT + slot) * 8);  // slot free
-        slot = tile_seq & (ST_NSLOT - 1);
-        st_mbar_wait(bar0 + slot * 8, (tile_seq / ST_NSLOT) & 1);
-        d = tdesc[slot];
+        if (lane == 0) st_mbar_arrive(bar0 + (NS + slot) * 8);  // slot free
+        slot = tile_seq % NS;
+        st_mbar_wait(bar0 + slot * 8, (tile_seq / NS) & 1);     // the next tile's bytes have landed
+        dt = tdesc[slot];
       }
       // the staging image is free once the storer has read out the previous item
       st_mbar_wait(sfree, (item_seq & 1) ^ 1);
@@ -446,12 +457,12 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the bulk store
     if (warp == 0 && lane == 0) {
-      int *sd = reinterpret_cast<int *>(smem + SM_SDESC + (item_seq & 1) * 16);
+      int *sd = reinterpret_cast<int *>(smem + L::SDESC + (item_seq & 1) * 16);
       sd[0] = P->krow, sd[1] = d.chunk, sd[2] = 0;
     }
     __syncwarp();
     if (lane == 0) {
-      st_mbar_arrive(bar0 + (ST_NSLOT + slot) * 8);  // the item's last slot and its plan record are free
+      st_mbar_arrive(bar0 + (NS + slot) * 8);  // the item's last slot and its plan record are free
       st_mbar_arrive(sfull);
     }
     ++item_seq;
@@ -460,107 +471,149 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
   // image, otherwise an owner that runs ahead would arrive twice in the phase of the item the others still write.
   st_mbar_wait(sfree, (item_seq & 1) ^ 1);
   if (lane == 0) {
-    if (warp == 0) reinterpret_cast<int *>(smem + SM_SDESC + (item_seq & 1) * 16)[2] = 1;
+    if (warp == 0) reinterpret_cast<int *>(smem + L::SDESC + (item_seq & 1) * 16)[2] = 1;
     st_mbar_arrive(sfull);
   }
 }
 
+// Producer warp.  Lane l < 22 keeps word l of an item's header (the first 20 plan words, the chunk, the schedule slot)
+// for the current item and the next one; the atomic ticket of item i+3 and the header load of item i+2 are in flight
+// while the tiles of item i are issued.  A tile's rows are spread over the lanes: lane l looks at row l (slice and row
+// from a multiply by the plan's 2^16 / RY instead of a division), the lanes that start a {8,4,2,1}-row box issue its
+// TMA copy.
+template <int NS, int SLOT>
+__device__ __forceinline__ void producer_loop(const StreamArgs &a, unsigned char *smem, int lane) {
+  using L = Lay<NS, SLOT>;
+  const unsigned bar0 = s_u32(smem + L::BAR);
+  TileDesc *tdesc = reinterpret_cast<TileDesc *>(smem + L::TDESC);
+  const int K = a.p.K, total = a.total_items;
+  auto ticket = [&]() -> int { return lane == 0 ? atomicAdd(a.counter, 1) : 0; };
+  auto header = [&](int idx) -> int {
+    if (idx >= total) return 0;
+    const int chunk = idx / K, r = idx - chunk * K;
+    if (lane < 20) return __ldg(reinterpret_cast<const int *>(a.plans + r) + lane);
+    return lane == 20 ? chunk : r;
+  };
+  int idx_cur = __shfl_sync(FULL, ticket(), 0);
+  int h_cur = header(idx_cur);
+  int idx_n1 = __shfl_sync(FULL, ticket(), 0);
+  int h_n1 = header(idx_n1);
+  int t_n2 = ticket();
+  unsigned tile_seq = 0, item_seq = 0;
+  while (idx_cur < total) {
+    const int idx_n2 = __shfl_sync(FULL, t_n2, 0);
+    t_n2 = ticket();                   // item i+3
+    const int h_n2 = header(idx_n2);   // item i+2, consumed in the next trip
+    const int lvl = __shfl_sync(FULL, h_cur, 2), b = __shfl_sync(FULL, h_cur, 3);
+    const int x0 = __shfl_sync(FULL, h_cur, 5), y0 = __shfl_sync(FULL, h_cur, 6), z0 = __shfl_sync(FULL, h_cur, 7);
+    const int RY = __shfl_sync(FULL, h_cur, 9), RZ = __shfl_sync(FULL, h_cur, 10), RXB = __shfl_sync(FULL, h_cur, 11);
+    const int rpt = __shfl_sync(FULL, h_cur, 12), ntiles = __shfl_sync(FULL, h_cur, 13);
+    const int xcls = __shfl_sync(FULL, h_cur, 15), spt = __shfl_sync(FULL, h_cur, 17), tps = __shfl_sync(FULL, h_cur, 18);
+    const int chunk = __shfl_sync(FULL, h_cur, 20), r_sched = __shfl_sync(FULL, h_cur, 21);
+    const int rowbytes = RXB * ST_CH * 4;
+    const CUtensorMap *maps = a.maps[lvl] + xcls * ST_YCLS;
+    const unsigned pslot = item_seq % NS;
+    const int nrows = __shfl_sync(FULL, h_cur, 14), magic = spt;
+    const int c0 = chunk * ST_CH;
+    (void)tps, (void)RZ;
+    int r = 0, ys = 0, zs = 0;  // first row of the next tile: index, and (row, slice) from the box origin
+    for (int t = 0; t < ntiles; ++t) {
+      const unsigned slot = tile_seq % NS;
+      st_mbar_wait(bar0 + (NS + slot) * 8, ((tile_seq / NS) & 1) ^ 1);
+      const unsigned full = bar0 + slot * 8;
+      const int tr = min(rpt, nrows - r);
+      if (lane == 0) {
+        TileDesc d;
+        d.plan = (int)pslot, d.nrows = tr, d.z = zs, d.y = ys;
+        d.flags = (t == 0 ? TILE_FIRST : 0) | (t == ntiles - 1 ? TILE_LAST : 0);
+        d.rowfloats = RXB * ST_CH, d.chunk = chunk, d.pad = 0;
+        tdesc[slot] = d;
+        st_mbar_expect_tx(full, (unsigned)(tr * rowbytes + (t == 0 ? PLAN_BYTES : 0)));
+        if (t == 0) st_bulk_g2s(s_u32(smem + L::PLAN + pslot * PLAN_BYTES), a.plans + r_sched, PLAN_BYTES, full);
+      }
+      __syncwarp();
+      // row `lane` of the tile: slice dz (from zs) and row y; the slice's run of rows inside this tile is [seg0, seg1);
+      // the lanes at the start of a box of its {8,...,8,4,2,1}-row cover issue the copy
+      const int pos = ys + lane;
+      const int dz = (pos * magic) >> 16;
+      const int y = pos - dz * RY;
+      const int seg0 = dz == 0 ? ys : 0;
+      const int seg1 = min(RY, ys + tr - dz * RY);
+      const int n = seg1 - seg0, p = y - seg0;
+      const int n8 = n & ~7, rem = n - n8;
+      int yc = -1;
+      if (p < n8) {
+        if ((p & 7) == 0) yc = 3;
+      } else {
+        const int q = p - n8;
+        if (q == 0 && (rem & 4)) yc = 2;
+        else if (q == (rem & 4) && (rem & 2)) yc = 1;
+        else if (q == (rem & 6) && (rem & 1)) yc = 0;
+      }
+      if (lane < tr && yc >= 0)
+        st_tma_5d(s_u32(smem + L::RING + slot * SLOT) + lane * rowbytes, maps + yc, c0, x0, y0 + y, z0 + zs + dz, b, full);
+      r += tr;
+      {
+        const int pe = ys + tr;
+        const int de = (pe * magic) >> 16;
+        zs += de, ys = pe - de * RY;
+      }
+      ++tile_seq;
+    }
+    ++item_seq;
+    idx_cur = idx_n1, h_cur = h_n1;
+    idx_n1 = idx_n2, h_n1 = h_n2;
+  }
+  // sentinel tile
+  const unsigned slot = tile_seq % NS;
+  st_mbar_wait(bar0 + (NS + slot) * 8, ((tile_seq / NS) & 1) ^ 1);
+  if (lane == 0) {
+    TileDesc d;
+    d.plan = 0, d.nrows = 0, d.z = 0, d.y = 0, d.flags = TILE_DONE, d.rowfloats = 0, d.chunk = 0, d.pad = 0;
+    tdesc[slot] = d;
+    st_mbar_arrive(bar0 + slot * 8);
+  }
+}
+
+template <int NS, int SLOT>
 __global__ void __launch_bounds__(ST_WARPS * 32, 1) roi_align3d_fwd_stream_kernel(const __grid_constant__ StreamArgs a) {
+  using L = Lay<NS, SLOT>;
   extern __shared__ __align__(1024) unsigned char smem[];  // no static shared memory: the window starts at offset 0
   if ((s_u32(smem) & 127u) != 0) __trap();                  // TMA destinations need 128-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned bar0 = s_u32(smem + SM_BAR);
+  const unsigned bar0 = s_u32(smem + L::BAR);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < ST_NSLOT; ++s) {
-      st_mbar_init(bar0 + s * 8, 1);                      // full: the producer's arrive + the tile's bytes
-      st_mbar_init(bar0 + (ST_NSLOT + s) * 8, ST_OWNERS);  // empty: one arrive per owner warp
+    for (int s = 0; s < NS; ++s) {
+      st_mbar_init(bar0 + s * 8, 1);                 // full: the producer's arrive + the tile's bytes
+      st_mbar_init(bar0 + (NS + s) * 8, ST_OWNERS);   // empty: one arrive per owner warp
     }
-    st_mbar_init(bar0 + 2 * ST_NSLOT * 8, ST_OWNERS);      // staging full
-    st_mbar_init(bar0 + 2 * ST_NSLOT * 8 + 8, 1);          // staging free
+    st_mbar_init(bar0 + 2 * NS * 8, ST_OWNERS);       // staging full
+    st_mbar_init(bar0 + 2 * NS * 8 + 8, 1);           // staging free
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
   if (warp < ST_OWNERS) {
-    if (warp < 7) owner_loop<4>(a, smem, warp, 0, warp, lane);
-    else owner_loop<3>(a, smem, warp - 7, 4, warp, lane);
+    if (warp < 7) owner_loop<4, NS, SLOT>(a, smem, warp, 0, warp, lane);
+    else owner_loop<3, NS, SLOT>(a, smem, warp - 7, 4, warp, lane);
     return;
   }
-
   if (warp == ST_OWNERS) {
-    // ---- producer: one lane walks the items, issues the plan copy and the TMA tiles
-    if (lane != 0) return;
-    TileDesc *tdesc = reinterpret_cast<TileDesc *>(smem + SM_TDESC);
-    const int K = a.p.K;
-    unsigned tile_seq = 0, item_seq = 0;
-    for (;;) {
-      const int idx = atomicAdd(a.counter, 1);
-      if (idx >= a.total_items) break;
-      const int chunk = idx / K;
-      const int k = __ldg(a.order + (idx - chunk * K));
-      const StreamPlan *pg = a.plans + k;
-      const int4 h0 = __ldg(reinterpret_cast<const int4 *>(pg));      // k, krow, lvl, b
-      const int4 h1 = __ldg(reinterpret_cast<const int4 *>(pg) + 1);  // flags, x0, y0, z0
-      const int4 h2 = __ldg(reinterpret_cast<const int4 *>(pg) + 2);  // RX, RY, RZ, RXB
-      const int4 h3 = __ldg(reinterpret_cast<const int4 *>(pg) + 3);  // rows_per_tile, ntiles, nrows, xcls
-      const int lvl = h0.z, b = h0.w, x0 = h1.y, y0 = h1.z, z0 = h1.w;
-      const int RY = h2.y, RXB = h2.w, rpt = h3.x, ntiles = h3.y, nrows = h3.z, xcls = h3.w;
-      const int rowbytes = RXB * ST_CH * 4;
-      const CUtensorMap *maps = a.maps[lvl] + xcls * ST_YCLS;
-      const unsigned pslot = item_seq & (ST_NSLOT - 1);
-      int r = 0, y = 0, z = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        const unsigned slot = tile_seq & (ST_NSLOT - 1);
-        st_mbar_wait(bar0 + (ST_NSLOT + slot) * 8, ((tile_seq / ST_NSLOT) & 1) ^ 1);
-        const int tr = min(rpt, nrows - r);
-        TileDesc d;
-        d.plan = (int)pslot, d.nrows = tr, d.z = z, d.y = y;
-        d.flags = (t == 0 ? TILE_FIRST : 0) | (t == ntiles - 1 ? TILE_LAST : 0);
-        d.rowfloats = RXB * ST_CH, d.chunk = chunk, d.pad = 0;
-        tdesc[slot] = d;
-        const unsigned full = bar0 + slot * 8;
-        st_mbar_expect_tx(full, (unsigned)(tr * rowbytes + (t == 0 ? PLAN_BYTES : 0)));
-        if (t == 0) st_bulk_g2s(s_u32(smem + SM_PLAN + pslot * PLAN_BYTES), pg, PLAN_BYTES, full);
-        unsigned dst = s_u32(smem + SM_RING + slot * ST_SLOT_BYTES);
-        int left = tr;
-        while (left > 0) {
-          int seg = min(left, RY - y);
-          left -= seg, r += seg;
-          int yy = y;
-          y += seg;
-          while (seg > 0) {
-            const int yc = seg >= 8 ? 3 : seg >= 4 ? 2 : seg >= 2 ? 1 : 0;
-            const int nr = 1 << yc;
-            st_tma_5d(dst, maps + yc, chunk * ST_CH, x0, y0 + yy, z0 + z, b, full);
-            dst += nr * rowbytes, yy += nr, seg -= nr;
-          }
-          if (y == RY) y = 0, ++z;
-        }
-        ++tile_seq;
-      }
-      ++item_seq;
-    }
-    // sentinel tile
-    const unsigned slot = tile_seq & (ST_NSLOT - 1);
-    st_mbar_wait(bar0 + (ST_NSLOT + slot) * 8, ((tile_seq / ST_NSLOT) & 1) ^ 1);
-    TileDesc d;
-    d.plan = 0, d.nrows = 0, d.z = 0, d.y = 0, d.flags = TILE_DONE, d.rowfloats = 0, d.chunk = 0, d.pad = 0;
-    tdesc[slot] = d;
-    st_mbar_arrive(bar0 + slot * 8);
+    producer_loop<NS, SLOT>(a, smem, lane);
     return;
   }
 
   // ---- storer: one bulk store per item, the staging image is handed back as soon as it has been read
   if (lane != 0) return;
-  const unsigned sfull = bar0 + 2 * ST_NSLOT * 8, sfree = sfull + 8;
-  const unsigned stage_s = s_u32(smem + SM_STAGE);
+  const unsigned sfull = bar0 + 2 * NS * 8, sfree = sfull + 8;
+  const unsigned stage_s = s_u32(smem + L::STAGE);
   const unsigned bytes = (unsigned)(ST_CH * a.pdhw * 4);
   for (unsigned n = 0;; ++n) {
     st_mbar_wait(sfull, n & 1);
-    const int *sd = reinterpret_cast<const int *>(smem + SM_SDESC + (n & 1) * 16);
+    const int *sd = reinterpret_cast<const int *>(smem + L::SDESC + (n & 1) * 16);
     if (sd[2]) break;
     float *dst = a.p.out + ((long long)sd[0] * a.p.C + (long long)sd[1] * ST_CH) * a.pdhw;
-    st_bulk_s2g(dst, stage_s, bytes);
+    if (!(a.debug & 2)) st_bulk_s2g(dst, stage_s, bytes);
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
     st_mbar_arrive(sfree);
@@ -647,15 +700,83 @@ int level_maps(const LevelDev &L, int B, int C, const CUtensorMap **out) {
 bool fwd_stream_ok(const RoiParams &p) {
   if (p.PW != 7 || p.PH != 7 || p.PD < 1 || p.PD > 7) return false;
   if (p.C % ST_CH != 0 || p.num_levels > ST_MAX_LEVELS) return false;
-  if (p.out_rows != nullptr) return false;  // row-mapped output may be mapped host memory: kept on the ring kernel
   if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return false;
   if ((long long)p.K * (p.C / ST_CH) >= 2147483647LL) return false;
   for (int l = 0; l < p.num_levels; ++l) {
     if ((reinterpret_cast<uintptr_t>(p.lv[l].feats) & 15) != 0) return false;
     if ((long long)p.lv[l].D * p.lv[l].H * p.lv[l].W * p.C * 4 >= (1LL << 40)) return false;  // TMA stride field
   }
+  if (p.out_rows != nullptr) {
+    // a row-mapped output may be mapped host memory (roi3d_roi_align3d_forward_host): bulk stores stay on device memory
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p.out) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+      cudaGetLastError();
+      return false;
+    }
+  }
   return true;
 }
+
+namespace {
+
+// Plans and the work counter come from a private stream-ordered pool: no host sync, re-entrant across streams, and
+// (release threshold = max) the pages stay with the pool between calls instead of going back to the driver at every
+// synchronisation as the default pool would do.
+int stream_pool(cudaMemPool_t *out) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  ROI3D_CUDA(cudaGetDevice(&dev));
+  ROI3D_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (pools[dev] == nullptr) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    ROI3D_CUDA(cudaMemPoolCreate(&pool, &props));
+    unsigned long long keep = ~0ULL;
+    ROI3D_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    pools[dev] = pool;
+  }
+  *out = pools[dev];
+  return ROI3D_OK;
+}
+
+template <int NS, int SLOT>
+int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count) {
+  using L = Lay<NS, SLOT>;
+  cudaMemPool_t pool;
+  int rc = stream_pool(&pool);
+  if (rc) return rc;
+  const size_t plan_bytes = (size_t)p.K * sizeof(StreamPlan);
+  unsigned char *ws = nullptr;
+  ROI3D_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), plan_bytes + 16, pool, st));
+  StreamPlan *plans = reinterpret_cast<StreamPlan *>(ws);
+  int *counter = reinterpret_cast<int *>(ws + plan_bytes);
+  const int sort = (p.K <= ST_SORT_MAX && !(a.debug & 4)) ? 1 : 0;
+  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(p, plans, counter, sort, SLOT);
+  ROI3D_LAUNCH_CHECK();
+  a.plans = plans, a.counter = counter;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_stream_kernel<NS, SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::LAUNCH));
+    attr_set = true;
+  }
+  const int grid = a.total_items < sm_count ? a.total_items : sm_count;
+  roi_align3d_fwd_stream_kernel<NS, SLOT><<<grid, ST_WARPS * 32, L::LAUNCH, st>>>(a);
+  ROI3D_LAUNCH_CHECK();
+  ROI3D_CUDA(cudaFreeAsync(ws, st));
+  return ROI3D_OK;
+}
+
+}  // namespace
+
+int g_fwd_stream_cfg = 0;       // roi3d_set_tuning key 7: ring geometry of the streamed kernel (0 = default)
+int g_fwd_stream_debug = 0;     // key 9: developer experiments (bit 0: owners skip the arithmetic, bit 1: no output store)
 
 int launch_fwd_stream(RoiParams &p, cudaStream_t st) {
   static int sm_count = 0;
@@ -671,31 +792,16 @@ int launch_fwd_stream(RoiParams &p, cudaStream_t st) {
     const int rc = level_maps(p.lv[l], p.B, p.C, &a.maps[l]);
     if (rc) return rc;
   }
-  // plans + order + counter from the stream-ordered pool: no host sync, re-entrant across streams
-  const size_t plan_bytes = (size_t)p.K * sizeof(StreamPlan);
-  const size_t ws_bytes = plan_bytes + ((size_t)p.K + 4) * sizeof(int);
-  unsigned char *ws = nullptr;
-  ROI3D_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), ws_bytes, st));
-  StreamPlan *plans = reinterpret_cast<StreamPlan *>(ws);
-  int *order = reinterpret_cast<int *>(ws + plan_bytes);
-  int *counter = order + p.K;
-  const int sort = p.K <= ST_SORT_MAX ? 1 : 0;
-  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(p, plans, order, counter, sort);
-  ROI3D_LAUNCH_CHECK();
-  a.plans = plans, a.order = order, a.counter = counter;
   a.total_items = p.K * (p.C / ST_CH);
   a.pdhw = p.PD * 49;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SM_LAUNCH));
-    attr_set = true;
+  a.debug = g_fwd_stream_debug;
+  // ring geometry (measured on C2, whole call): 3 x 42 KB 154 us, 4 x 32 KB 156 us, 4 x 30 KB 160 us, 5 x 24 KB 166 us,
+  // 4 x 20 KB 185 us, 8 x 15 KB 215 us -- per-tile hand-offs cost more than a shallower ring
+  switch (g_fwd_stream_cfg) {
+    case 1: return launch_cfg<4, 32768>(p, a, st, sm_count);
+    case 2: return launch_cfg<5, 24576>(p, a, st, sm_count);
+    default: return launch_cfg<3, 43008>(p, a, st, sm_count);
   }
-  const int grid = a.total_items < sm_count ? a.total_items : sm_count;
-  roi_align3d_fwd_stream_kernel<<<grid, ST_WARPS * 32, SM_LAUNCH, st>>>(a);
-  ROI3D_LAUNCH_CHECK();
-  ROI3D_CUDA(cudaFreeAsync(ws, st));
-  return ROI3D_OK;
 }
 
 }  // namespace roi3d

@@ -74,14 +74,35 @@ for K in (8, 64, 512):
     b = run(f, r[:K].contiguous(), variant=50)
     d = (a - b).abs().amax(dim=(1, 2, 3, 4))
     print("K=%d maxdiff=%g bad rois=%d" % (K, float(d.max()), int((d > 1e-4).sum())), flush=True)
-import time
-for v in (0, 50):
-    for _ in range(3):
-        run(f, r, variant=v)
-    t0 = time.perf_counter()
-    for _ in range(20):
-        _lib.set_tuning(0, v)
-        RoIAlign3D(7, 7, 0.25, 0.5, 2)(f, r)
+flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
     torch.cuda.synchronize()
-    print("variant %d: %.1f us/call (no L2 flush)" % (v, (time.perf_counter() - t0) / 20 * 1e6), flush=True)
+    ts = []
+    for _ in range(iters):
+        flush_buf.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
+for cfg, pf in ((0, 0), (4, 0), (6, 0), (5, 0)):
+    _lib.set_tuning(7, cfg)
+    _lib.set_tuning(8, pf)
+    a = layer(f, r)
+    print("cfg %d prefetch %d maxdiff vs ring %g" % (cfg, pf, float((a - b).abs().max())), flush=True)
+    print("stream cfg %d prefetch %d: median %.1f us min %.1f us (events, L2 flushed)" % ((cfg, pf) + timeit(lambda: layer(f, r))), flush=True)
+_lib.set_tuning(7, 0)
+_lib.set_tuning(8, 1)
+_lib.set_tuning(0, 50)
+print("ring2: median %.1f us min %.1f us" % timeit(lambda: layer(f, r)), flush=True)
 _lib.set_tuning(0, 0)
