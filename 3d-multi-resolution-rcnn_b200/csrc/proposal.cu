@@ -29,6 +29,7 @@ struct SegDesc {
   long long off;
   unsigned len;
   int A, D, H, W;  // A == 0: logical index == memory index
+  const unsigned char *mask;  // optional, indexed by LOGICAL index: 0 = the element does not take part (rpn_head_3d.py:97-106)
 };
 
 struct SegTable {
@@ -41,6 +42,7 @@ struct SegState {           // device, per segment
   int k_take;               // min(k, len)
   int cand_count;
   int bnd_count;            // keys inside the boundary bin after the second digit pass (topk_split_kernel)
+  unsigned eff_len;         // elements taking part: len, or the number of set mask bytes (known after digit pass 0)
 };
 
 __device__ __forceinline__ unsigned okey(float s) {
@@ -100,7 +102,18 @@ __device__ __forceinline__ void scan_segment(unsigned *__restrict__ hist, SegSta
     __syncthreads();
   }
   const unsigned above = part[threadIdx.x] - sum;  // keys in bins strictly above my 8 bins
+  if (pass == 0) {
+    // the first histogram counts every element that takes part: a masked segment learns its effective length here
+    const unsigned total = part[0];
+    st.eff_len = total;
+    if (total < (unsigned)st.k_take) st.k_take = (int)total, st.k_rem = (int)total;
+  }
   const unsigned k = (unsigned)st.k_rem;
+  if (k == 0) {  // nothing to select (all masked out)
+    __syncthreads();
+    if (threadIdx.x == 0) state[seg] = st;
+    return;
+  }
   if (above < k && above + sum >= k) {
     unsigned cum = above;
     for (int i = 7; i >= 0; --i) {
@@ -161,6 +174,7 @@ __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__
         const unsigned long long key = bsrc[m];
         kh = (unsigned)(key >> 32), kl_b = (unsigned)key;
       } else {
+        if (d.mask != nullptr && !__ldg(d.mask + logical_index(d, (unsigned)m))) continue;
         float v = __ldg(src + m);
         if (SIGMOID) v = sigmoid_ref(v);
         kh = okey(v);
@@ -231,7 +245,9 @@ __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const float 
         if (SIGMOID) v = sigmoid_ref(v);
         const unsigned kh = okey(v);
         if (kh < thr_hi) continue;
-        key = ((unsigned long long)kh << 32) | (unsigned)~logical_index(d, (unsigned)m);
+        const unsigned li = logical_index(d, (unsigned)m);
+        if (d.mask != nullptr && !__ldg(d.mask + li)) continue;
+        key = ((unsigned long long)kh << 32) | (unsigned)~li;
       }
       if (key >= st.prefix) {
         const int pos = atomicAdd(&state[seg].cand_count, 1);
@@ -267,7 +283,9 @@ __global__ void __launch_bounds__(kTopkThreads) topk_split_kernel(const float *_
       const unsigned kh = okey(v);
       const unsigned h22 = kh >> 10;
       if (h22 >= p22) {
-        const unsigned long long key = ((unsigned long long)kh << 32) | (unsigned)~logical_index(d, (unsigned)m);
+        const unsigned li = logical_index(d, (unsigned)m);
+        if (d.mask != nullptr && !__ldg(d.mask + li)) continue;
+        const unsigned long long key = ((unsigned long long)kh << 32) | (unsigned)~li;
         if (h22 > p22) {
           const int pos = atomicAdd(&state[seg].cand_count, 1);
           if (pos < k) cand[(long long)seg * k + pos] = key;
@@ -296,7 +314,7 @@ __global__ void __launch_bounds__(256) topk_sort_kernel(const unsigned long long
                                                         float *__restrict__ out_val) {
   const int seg = blockIdx.y;
   const int n = state[seg].k_take;
-  const bool by_index = small_by_index && tab.s[seg].len <= (unsigned)k;
+  const bool by_index = small_by_index && state[seg].eff_len <= (unsigned)k;
   if ((int)(blockIdx.x * 256) >= n) return;
   const unsigned long long *c = cand + (long long)seg * k;
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -330,7 +348,7 @@ __global__ void __launch_bounds__(1024) topk_bitonic_kernel(const unsigned long 
   const int seg = blockIdx.x, tid = threadIdx.x;
   const int n = state[seg].k_take;
   if (n <= 0) return;
-  const bool by_index = small_by_index && tab.s[seg].len <= (unsigned)k;
+  const bool by_index = small_by_index && state[seg].eff_len <= (unsigned)k;
   const unsigned long long *c = cand + (long long)seg * k;
   // sort key: the 64-bit key itself (descending), or only its low word = ~index (descending = ascending index)
   for (int i = tid; i < npow2; i += 1024) {
@@ -369,7 +387,18 @@ __global__ void topk_init_kernel(SegState *state, int *tickets, const SegTable t
   st.k_rem = st.k_take;
   st.cand_count = 0;
   st.bnd_count = 0;
+  st.eff_len = tab.s[s].len;
   state[s] = st;
+}
+
+// What the callers downstream need to know about each segment without a host read: how many rows came back and
+// whether they are in score order (1) or, for a small segment returned whole, in ascending logical index (0).
+__global__ void topk_report_kernel(const SegState *state, int nseg, int k, int small_by_index, int32_t *out_count,
+                                   unsigned char *out_sorted) {
+  const int s = threadIdx.x;
+  if (s >= nseg) return;
+  if (out_count != nullptr) out_count[s] = state[s].k_take;
+  if (out_sorted != nullptr) out_sorted[s] = !(small_by_index && state[s].eff_len <= (unsigned)k);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -583,7 +612,7 @@ using namespace roi3d;
 
 extern "C" {
 
-static const size_t kStateBytes = 2048;                                     // kMaxSeg * sizeof(SegState) rounded up
+static const size_t kStateBytes = 4096;                                     // kMaxSeg * sizeof(SegState) + tickets, rounded up
 static const size_t kHistBytes = (size_t)kMaxSeg * kBins * sizeof(unsigned);  // 512 KiB
 
 size_t roi3d_topk_workspace_bytes(int nseg, int k) {
@@ -604,6 +633,16 @@ int roi3d_topk_segmented_ex(const float *scores_dev, const int64_t *seg_off, con
                             const int32_t *seg_adhw, int nseg, int k, int apply_sigmoid, int small_segments_in_index_order,
                             int64_t *out_idx_dev, float *out_val_dev, void *workspace_dev, size_t workspace_bytes,
                             void *stream) {
+  return roi3d_topk_segmented_masked(scores_dev, seg_off, seg_len, seg_adhw, nullptr, nseg, k, apply_sigmoid,
+                                     small_segments_in_index_order, out_idx_dev, out_val_dev, nullptr, nullptr,
+                                     workspace_dev, workspace_bytes, stream);
+}
+
+int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
+                                const int32_t *seg_adhw, const uint8_t *const *seg_mask_dev_ptrs, int nseg, int k,
+                                int apply_sigmoid, int small_segments_in_index_order, int64_t *out_idx_dev,
+                                float *out_val_dev, int32_t *out_count_dev, uint8_t *out_sorted_dev, void *workspace_dev,
+                                size_t workspace_bytes, void *stream) {
   ROI3D_CHECK_ARG(nseg >= 0 && k >= 0, "bad sizes");
   if (nseg == 0 || k == 0) return ROI3D_OK;
   ROI3D_CHECK_ARG(scores_dev && seg_off && seg_len && out_idx_dev && out_val_dev && workspace_dev, "NULL pointer");
@@ -631,18 +670,27 @@ int roi3d_topk_segmented_ex(const float *scores_dev, const int64_t *seg_off, con
       } else {
         tab.s[s].A = tab.s[s].D = tab.s[s].H = tab.s[s].W = 0;
       }
+      tab.s[s].mask = seg_mask_dev_ptrs != nullptr ? seg_mask_dev_ptrs[s0 + s] : nullptr;
       if (seg_len[s0 + s] > maxlen) maxlen = seg_len[s0 + s];
     }
-    static_assert(sizeof(SegState) * kMaxSeg + sizeof(int) * kMaxSeg <= 2048, "state block");
+    static_assert(sizeof(SegState) * kMaxSeg + sizeof(int) * kMaxSeg <= 4096, "state block");
     char *b = static_cast<char *>(workspace_dev);
     SegState *state = reinterpret_cast<SegState *>(b);
     unsigned *hist = reinterpret_cast<unsigned *>(b + kStateBytes);
     unsigned long long *cand = reinterpret_cast<unsigned long long *>(b + kStateBytes + kHistBytes);
     unsigned long long *bnd = cand + (size_t)(nseg < kMaxSeg ? nseg : kMaxSeg) * k;
-    int *tickets = reinterpret_cast<int *>(b + sizeof(SegState) * kMaxSeg);  // inside the 2 KB state block
+    int *tickets = reinterpret_cast<int *>(b + sizeof(SegState) * kMaxSeg);  // inside the 4 KB state block
     topk_init_kernel<<<1, kMaxSeg, 0, st>>>(state, tickets, tab, ns, k);
     ROI3D_LAUNCH_CHECK();
-    if (maxlen == 0) continue;
+    if (maxlen == 0) {
+      if (out_count_dev != nullptr || out_sorted_dev != nullptr) {
+        topk_report_kernel<<<1, kMaxSeg, 0, st>>>(state, ns, k, small_segments_in_index_order,
+                                                  out_count_dev ? out_count_dev + s0 : nullptr,
+                                                  out_sorted_dev ? out_sorted_dev + s0 : nullptr);
+        ROI3D_LAUNCH_CHECK();
+      }
+      continue;
+    }
     ROI3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)ns * kBins * sizeof(unsigned), st));
     const dim3 grid((unsigned)ceil_div_ll(maxlen, kItemsPerCta), ns);
     const dim3 grid2((unsigned)(grid.x < 8 ? grid.x : 8), ns);  // boundary passes: see topk_hist_kernel
@@ -681,6 +729,12 @@ int roi3d_topk_segmented_ex(const float *scores_dev, const int64_t *seg_off, con
                                                                   out_val_dev + (size_t)s0 * k);
     }
     ROI3D_LAUNCH_CHECK();
+    if (out_count_dev != nullptr || out_sorted_dev != nullptr) {
+      topk_report_kernel<<<1, kMaxSeg, 0, st>>>(state, ns, k, small_segments_in_index_order,
+                                                out_count_dev ? out_count_dev + s0 : nullptr,
+                                                out_sorted_dev ? out_sorted_dev + s0 : nullptr);
+      ROI3D_LAUNCH_CHECK();
+    }
   }
   return ROI3D_OK;
 }

@@ -18,15 +18,17 @@ package fails if that library is missing: there is no CPU or PyTorch fallback.
 """
 from . import _lib  # noqa: F401  (raises ImportError when libroi3d_b200.so is absent)
 from . import ops
+from ._util import reuse_layout_conversions
 from .core.anchor import AnchorGenerator3D
 from .core.bbox import bbox2roi3D, delta2bbox3D
 from .core.post_processing import multiclass_nms_3d
 from .core.evaluation import apply_nms, nms_3d_eval_batched
 from .models.anchor_heads import RPNProposal3D
 from .models.builder import build_roi_extractor, build_rpn_proposal
+from .models.config import build_from_config, load_config
 from .models.roi_extractors import SingleRoIExtractor
 from .ops import RoIAlign3D, nms, roi_align_3d, soft_nms
 
 __all__ = ['ops', 'nms', 'soft_nms', 'RoIAlign3D', 'roi_align_3d', 'SingleRoIExtractor', 'RPNProposal3D',
            'AnchorGenerator3D', 'delta2bbox3D', 'bbox2roi3D', 'multiclass_nms_3d', 'build_roi_extractor',
-           'build_rpn_proposal', 'apply_nms', 'nms_3d_eval_batched']
+           'build_rpn_proposal', 'build_from_config', 'load_config', 'reuse_layout_conversions', 'apply_nms', 'nms_3d_eval_batched']

@@ -1,8 +1,4 @@
 """Small torch-side helpers shared by the host mirror: stream handle, layout handling, scratch buffers."""
-import collections
-import os
-import weakref
-
 import torch
 
 from . import _lib
@@ -22,17 +18,39 @@ def is_channels_last_3d(x):
     return x.dim() == 5 and x.is_contiguous(memory_format=torch.channels_last_3d)
 
 
-# --- NCDHW -> channels-last conversion cache ----------------------------------------------------
-# The reference API takes NCDHW-contiguous feature maps (roi_align_cuda.cpp:35-39); the kernels read
-# channels-last.  A detector calls the extractor several times per step on the SAME FPN outputs
-# (bbox, refinement and mask extractors: two_stage_3d_2scales.py:234-237,290-291,305-306), so the
-# converted copy is cached per source tensor (identity + version counter), bounded LRU.
-_CACHE_SIZE = int(os.environ.get("ROI3D_LAYOUT_CACHE", "8"))
-_cache = collections.OrderedDict()
+# --- NCDHW -> channels-last conversion -----------------------------------------------------------
+# The reference API takes NCDHW-contiguous feature maps (roi_align_cuda.cpp:35-39); the streamed / ring kernels read
+# channels-last.  A detector calls the extractor several times per step on the SAME FPN outputs (bbox, refinement and
+# mask extractors: two_stage_3d_2scales.py:234-237,290-291,305-306), so a converted copy can be reused -- but only
+# when the caller says the buffer has not been rewritten: a tensor's `_version` does not see writes through
+# `data_ptr` (a backbone replayed as a CUDA graph, a custom kernel), so reuse is OPT-IN and scoped:
+#
+#     with roi3d_b200.reuse_layout_conversions():      # e.g. around the RoI stage of one forward pass
+#         bbox_feats = bbox_extractor(feats, rois)
+#         mask_feats = mask_extractor(feats, mask_rois)
+#
+# Outside such a scope every call converts afresh (the conversion runs at HBM speed: 242 us for the 671 MB C2 level).
+# Inside, entries are keyed by (data_ptr, shape, stride, stream) and dropped when the scope ends, so nothing outlives
+# the pass or pins memory, and a copy made on one stream is never handed to another.
+_scopes = []
+
+
+class reuse_layout_conversions(object):
+    """Context manager: NCDHW feature maps converted inside the scope are converted once (see above).  The caller
+    promises not to rewrite those feature maps while the scope is open."""
+
+    def __enter__(self):
+        _scopes.append({})
+        return self
+
+    def __exit__(self, *exc):
+        _scopes.pop().clear()
+        return False
 
 
 def clear_layout_cache():
-    _cache.clear()
+    for sc in _scopes:
+        sc.clear()
 
 
 def to_channels_last_3d(x):
@@ -41,22 +59,19 @@ def to_channels_last_3d(x):
         return x, False
     if not x.is_contiguous():
         x = x.contiguous()
-    key = (x.data_ptr(), tuple(x.shape), x.device.index)
-    hit = _cache.get(key)
-    if hit is not None:
-        src_ref, version, conv = hit
-        if src_ref() is x and version == x._version:
-            _cache.move_to_end(key)
-            return conv, True
-        del _cache[key]
+    cache = _scopes[-1] if _scopes else None
+    key = None
+    if cache is not None:
+        key = (x.data_ptr(), tuple(x.shape), x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+        hit = cache.get(key)
+        if hit is not None:
+            return hit[1], True
     B, C, D, H, W = x.shape
     conv = torch.empty_like(x, memory_format=torch.channels_last_3d)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib.roi3d_ncdhw_to_ndhwc(x.data_ptr(), conv.data_ptr(), B, C, D, H, W, stream_ptr()))
-    if _CACHE_SIZE > 0:
-        _cache[key] = (weakref.ref(x), x._version, conv)
-        while len(_cache) > _CACHE_SIZE:
-            _cache.popitem(last=False)
+    if cache is not None:
+        cache[key] = (x, conv)  # holding x keeps its address from being reused inside the scope
     return conv, True
 
 
@@ -69,18 +84,14 @@ def channels_last_to_contiguous(g):
     return out
 
 
-# --- grow-only per-device byte scratch (NMS / top-k workspaces) ---------------------------------
-_scratch = {}
-
-
-def scratch(device, nbytes, tag="ws"):
-    key = (device.index, tag)
-    buf = _scratch.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
-        _scratch[key] = buf
-    off = (-buf.data_ptr()) % 256
-    return buf, buf.data_ptr() + off
+# --- kernel workspaces ----------------------------------------------------------------------------
+def workspace(device, nbytes):
+    """A fresh 256-byte aligned byte buffer for ONE call (NMS / top-k / assigner workspaces).  torch's caching
+    allocator makes this cheap, orders reuse by stream, and -- under CUDA-graph capture -- serves it from the graph's
+    own pool, so two streams never share a workspace and a replayed graph never writes into memory that was handed
+    to someone else.  Returns (tensor to keep alive until the call is enqueued, aligned address)."""
+    buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+    return buf, buf.data_ptr() + ((-buf.data_ptr()) % 256)
 
 
 def check_cuda_f32(t, name, ndim=None, last=None):

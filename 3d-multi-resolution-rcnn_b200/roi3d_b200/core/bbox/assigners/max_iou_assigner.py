@@ -7,7 +7,7 @@ the [gts x boxes] IoU matrix, its two reductions and the Python loop over the gt
 import torch
 
 from .... import _lib
-from ...._util import check_cuda_f32, scratch, stream_ptr
+from ...._util import check_cuda_f32, stream_ptr, workspace
 from .assign_result import AssignResult
 
 
@@ -37,6 +37,8 @@ class MaxIoUAssigner(object):
         check_cuda_f32(gt_bboxes, "gt_bboxes", ndim=2)
         if bboxes.shape[1] < 6 or gt_bboxes.shape[1] < 6:
             raise NotImplementedError("MaxIoUAssigner: only 3D boxes (>= 6 columns) are supported")
+        if gt_bboxes.shape[1] != 6:  # the kernel reads gt rows at a stride of 6 floats (geometry.py:49 takes 6 columns)
+            gt_bboxes = gt_bboxes[:, :6]
         if isinstance(self.neg_iou_thr, tuple):
             assert len(self.neg_iou_thr) == 2
             neg_lo, neg_hi = float(self.neg_iou_thr[0]), float(self.neg_iou_thr[1])
@@ -55,7 +57,7 @@ class MaxIoUAssigner(object):
             labels = torch.empty((n,), dtype=torch.long, device=dev)
             lab_ptr, gl_ptr = labels.data_ptr(), gl.data_ptr()
         nbytes = _lib.lib.roi3d_assign_workspace_bytes(n, k)
-        _buf, ws = scratch(dev, nbytes, "assign")
+        _buf, ws = workspace(dev, nbytes)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.roi3d_assign_max_iou(
                 b.data_ptr(), n, b.shape[1], g.data_ptr(), k, gl_ptr, float(self.pos_iou_thr), neg_lo, neg_hi,

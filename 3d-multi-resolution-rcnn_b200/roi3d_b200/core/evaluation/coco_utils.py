@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ..._util import scratch, stream_ptr
+from ..._util import stream_ptr, workspace
 
 
 def nms_3d_eval_batched(boxes_per_volume, iou_thr, device=None):
@@ -35,7 +35,7 @@ def nms_3d_eval_batched(boxes_per_volume, iou_thr, device=None):
     keep_s = torch.empty((nseg, n_max), dtype=torch.int64, device=dev)
     num = torch.zeros((nseg,), dtype=torch.int32, device=dev)
     nbytes = _lib.lib.roi3d_nms3d_workspace_bytes(nseg, n_max)
-    _buf, ws = scratch(dev, nbytes, "nms")
+    _buf, ws = workspace(dev, nbytes)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib.roi3d_nms3d_eval_batched(
             dets.data_ptr(), seg.data_ptr(), nseg, n_max, float(iou_thr), keep.data_ptr(), keep_s.data_ptr(),

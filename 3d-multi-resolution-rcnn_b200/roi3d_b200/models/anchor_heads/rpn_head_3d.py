@@ -13,9 +13,11 @@ levels together: one segmented radix-select top-k (sigmoid fused, logical permut
 anchor+decode kernel per level, one batched NMS over every (image, level) segment, a handful of torch index ops,
 one segmented top-k for the final cut, and a single host read of the result lengths at the end.
 
-Not reproduced: the `pos_indices` inside-flag filter (rpn_head_3d.py:97-106), which only triggers when a cached
-training-loss mask has exactly the same length as the level's scores, and the `min_bbox_size > 0` branch, which
-stops in a debugger in the reference (:125-132); `min_bbox_size > 0` raises here.
+The head's cached inside-flag masks `pos_indices` / `pos_indices_test` (anchor_head_3d.py:212,239-243) are honoured
+the way rpn_head_3d.py:97-106 applies them: on a level with more than nms_pre anchors, when the mask has the level's
+shape, only the masked-in anchors take part in the top-k (the mask goes into the segmented top-k; nothing is
+compacted).  Not reproduced: the `min_bbox_size > 0` branch, which stops in a debugger in the reference (:125-132)
+and raises here.
 """
 import ctypes
 
@@ -23,7 +25,7 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ..._util import check_cuda_f32, scratch, stream_ptr
+from ..._util import check_cuda_f32, stream_ptr, workspace
 from ...core.anchor import AnchorGenerator3D
 from ...ops.nms.nms_wrapper import nms3d_batched
 
@@ -34,7 +36,8 @@ def _cfg_get(cfg, key, default=None):
     return getattr(cfg, key, default)
 
 
-def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False, small_in_index_order=False):
+def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False, small_in_index_order=False, masks=None,
+                   report=False):
     """Segmented top-k over a list of CUDA fp32 tensors (one segment each).
 
     permute_adhw=True: each tensor is an [A, D, H, W] score map and indices refer to
@@ -42,6 +45,11 @@ def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False, smal
     rows past a segment's length hold -1 / 0.  Descending, ties -> lower index.  No host sync.
     small_in_index_order=True: a segment with no more than k elements comes back whole, in ascending index order
     (the reference does not sort a level that has at most nms_pre anchors, rpn_head_3d.py:96,108-112).
+    masks: optional list (one entry per segment, None = no mask) of uint8 / bool CUDA tensors indexed like the returned
+    indices; only elements whose mask byte is non-zero take part (`scores[pos_indices]`, rpn_head_3d.py:97-106), and
+    "no more than k elements" then refers to the masked-in count.
+    report=True additionally returns (count int32 [nseg], sorted uint8 [nseg]): rows returned per segment and whether
+    they are in score order (1) or in ascending index order (0) -- device tensors, no host read.
     """
     nseg = len(scores_list)
     dev = scores_list[0].device
@@ -60,12 +68,32 @@ def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False, smal
     idx = torch.empty((nseg, k), dtype=torch.int64, device=dev)
     val = torch.empty((nseg, k), dtype=torch.float32, device=dev)
     nbytes = _lib.lib.roi3d_topk_workspace_bytes(nseg, k)
-    _buf, ws = scratch(dev, nbytes, "topk")
+    _buf, ws = workspace(dev, nbytes)
+    mask_p, keep = None, []
+    if masks is not None and any(m is not None for m in masks):
+        ptrs = []
+        for m, sc in zip(masks, segs):
+            if m is None:
+                ptrs.append(None)
+                continue
+            if m.dtype == torch.bool:
+                m = m.view(torch.uint8)
+            if m.dtype != torch.uint8 or not m.is_cuda or m.numel() != sc.numel():
+                raise ValueError("a top-k mask must be a uint8 / bool CUDA tensor with one entry per score")
+            m = m.contiguous()
+            keep.append(m)
+            ptrs.append(m.data_ptr())
+        mask_p = (ctypes.c_void_p * nseg)(*ptrs)
+    cnt = torch.empty((nseg,), dtype=torch.int32, device=dev) if report else None
+    srt = torch.empty((nseg,), dtype=torch.uint8, device=dev) if report else None
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib.roi3d_topk_segmented_ex(base, off.ctypes.data, ln.ctypes.data, adhw_p, nseg, int(k),
-                                                    int(bool(apply_sigmoid)), int(bool(small_in_index_order)),
-                                                    idx.data_ptr(), val.data_ptr(), ws, nbytes, stream_ptr()))
-    del segs, adhw
+        _lib.check(_lib.lib.roi3d_topk_segmented_masked(
+            base, off.ctypes.data, ln.ctypes.data, adhw_p, mask_p, nseg, int(k), int(bool(apply_sigmoid)),
+            int(bool(small_in_index_order)), idx.data_ptr(), val.data_ptr(), None if cnt is None else cnt.data_ptr(),
+            None if srt is None else srt.data_ptr(), ws, nbytes, stream_ptr()))
+    del segs, adhw, keep, _buf
+    if report:
+        return idx, val, cnt, srt
     return idx, val
 
 
@@ -116,13 +144,24 @@ class RPNProposal3D(object):
             for b, d in zip(self.anchor_base_sizes, self.anchor_base_depths)
         ]
         self.num_anchors = len(anchor_ratios) * len(anchor_scales)
+        # the reference head's cached inside-flag masks (anchor_head_3d.py:67-68): per-level uint8 / bool CUDA tensors,
+        # set by the training loss pass (:212) or by get_bboxes for different_img_size test configs (:239-243)
+        self.pos_indices = None
+        self.pos_indices_test = None
         self._desc_cache = {}  # (segment lengths, flags, device) -> device descriptor tensors of get_bboxes
         self.cuda_graph = False  # capture + replay the path per (input buffers, shapes, config); see get_bboxes
         self._graphs = {}
 
-    def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg, rescale=False, img_meta_2=None, img_meta_3=None,
-                   return_anchors=False):
-        """Same arguments and return value as AnchorHead3D.get_bboxes (see `_enqueue`).  With `self.cuda_graph = True`
+    def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg, rescale=False, img_meta_2=None, img_meta_3=None):
+        """AnchorHead3D.get_bboxes (anchor_head_3d.py:232-268): same arguments, and the reference's return value
+        `(result_list, anchors_list)` -- every 3D caller unpacks it (`proposal_list, _ = ...`).  anchors_list holds
+        None per image: the reference only uses it for debug drawing (:270-547) and the anchors are never
+        materialised here."""
+        result = self.get_proposals(cls_scores, bbox_preds, img_metas, cfg, rescale, img_meta_2, img_meta_3)
+        return result, [None] * len(result)
+
+    def get_proposals(self, cls_scores, bbox_preds, img_metas, cfg, rescale=False, img_meta_2=None, img_meta_3=None):
+        """The proposal list alone (first element of get_bboxes' return value).  With `self.cuda_graph = True`
         the ~45 launches of the path are captured once per (input buffers, shapes, config) into a CUDA graph and
         replayed: the path is launch-bound (0.6 ms of GPU time behind ~1 ms of host-side launching for 8 volumes),
         and inference loops hand the same activation buffers to every call."""
@@ -134,7 +173,8 @@ class RPNProposal3D(object):
             final, n_valid, kk = self._enqueue(cls_scores, bbox_preds, img_metas, cfg)
             clone = False
         else:
-            key = (tuple(t.data_ptr() for t in list(cls_scores) + list(bbox_preds)),
+            masks_now = [m for lst in (self.pos_indices, self.pos_indices_test) if lst is not None for m in lst]
+            key = (tuple(t.data_ptr() for t in list(cls_scores) + list(bbox_preds) + masks_now),
                    tuple(tuple(t.shape) for t in list(cls_scores) + list(bbox_preds)),
                    tuple(tuple(m['img_shape']) for m in img_metas),
                    tuple(_cfg_get(cfg, n) for n in ('nms_pre', 'nms_post', 'max_num', 'nms_thr')))
@@ -147,16 +187,14 @@ class RPNProposal3D(object):
                     outs = self._enqueue(cls_scores, bbox_preds, img_metas, cfg)
                 if len(self._graphs) >= 4:
                     self._graphs.clear()
-                # the inputs are kept alive with the graph: their addresses are baked into it
+                # the inputs are kept alive with the graph: their addresses are baked into it (the workspaces of the
+                # captured calls are per-call torch allocations, so they live in the graph's own memory pool)
                 entry = self._graphs[key] = (graph, outs, list(cls_scores) + list(bbox_preds))
             entry[0].replay()
             final, n_valid, kk = entry[1]
             clone = True  # the graph's output buffer is overwritten by the next replay
         n_out = n_valid.clamp(max=kk).tolist()  # the single host read of the whole path
-        result = [final[b, :n_out[b]].clone() if clone else final[b, :n_out[b]] for b in range(len(n_out))]
-        if return_anchors:
-            return result, [None] * len(result)
-        return result
+        return [final[b, :n_out[b]].clone() if clone else final[b, :n_out[b]] for b in range(len(n_out))]
 
     def _enqueue(self, cls_scores, bbox_preds, img_metas, cfg):
         """cls_scores[l]: [B, A, D, H, W]; bbox_preds[l]: [B, 6A, D, H, W]; img_metas[b]['img_shape'] = (H, W, 3, D).
@@ -174,8 +212,7 @@ class RPNProposal3D(object):
         nms_thr = float(_cfg_get(cfg, 'nms_thr'))
         if _cfg_get(cfg, 'min_bbox_size', 0) > 0:
             raise NotImplementedError("min_bbox_size > 0 is broken in the reference (rpn_head_3d.py:125-132)")
-        if _cfg_get(cfg, 'nms_across_levels', False):
-            raise NotImplementedError("nms_across_levels=True is not used by the 3D config")
+        across = bool(_cfg_get(cfg, 'nms_across_levels', False))
         L, B = len(cls_scores), len(img_metas)
         dev = cls_scores[0].device
         A = self.num_anchors
@@ -194,6 +231,16 @@ class RPNProposal3D(object):
         # so issued later it would wait for every kernel already queued and serialise the CPU with the GPU.
         counts = [min(k, s.numel()) for s in segs]
         unsorted = [not (nms_pre > 0 and s.numel() > nms_pre) for s in segs]
+        # cached inside-flag masks: only on levels that are top-k'd, only when the shape matches (rpn_head_3d.py:96-106)
+        masks = [None] * len(segs)
+        for j, ((_b, l), s) in enumerate(zip(seg_meta, segs)):
+            if unsorted[j]:
+                continue
+            for lst in (self.pos_indices, self.pos_indices_test):
+                if lst is not None and tuple(lst[l].shape) == (s.numel(),):
+                    masks[j] = lst[l]
+                    break
+        masked = any(m is not None for m in masks)
         ckey = (tuple(counts), tuple(unsorted), dev)
         cached = self._desc_cache.get(ckey)
         if cached is None:  # they depend on the level shapes and the config only: uploaded once per shape signature
@@ -208,7 +255,13 @@ class RPNProposal3D(object):
         # a smaller level reaches NMS in anchor order, and `proposals[:nms_post]` then truncates in that order
         # (nms returns ascending input indices, nms_kernel.cu:253-256).  The top-k returns such segments whole in
         # ascending anchor order, and step 4 truncates them by original index instead of by score.
-        idx, val = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True, small_in_index_order=nms_pre > 0)
+        # (nms_pre <= 0: no level is sorted, every level comes back whole in anchor order)
+        if masked:  # the masked-in count decides, on the device, how many rows a level returns and whether it was sorted
+            idx, val, seg_counts, presorted = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True,
+                                                             small_in_index_order=True, masks=masks, report=True)
+            use_idx = 1 - presorted
+        else:
+            idx, val = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True, small_in_index_order=True)
 
         # 2. decode the selected anchors of every segment in ONE launch (anchors recomputed in closed form)
         dets = torch.empty((B * L, k, 7), dtype=torch.float32, device=dev)
@@ -248,7 +301,14 @@ class RPNProposal3D(object):
                 None if use_idx is None else use_idx.data_ptr(), nms_post, cat_props.data_ptr(), cat_scores.data_ptr(),
                 n_valid.data_ptr(), stream_ptr()))
         kk = min(max_num, L * P)
-        fidx, _ = topk_segmented([cat_scores[b] for b in range(B)], kk, apply_sigmoid=False)
+        if across:
+            # rpn_head_3d.py:140-142: NMS over the concatenated levels, then the first max_num rows in the order nms
+            # returns them (ascending position in the concatenation)
+            fidx, _ks, nk = nms3d_batched(cat_props, n_valid, nms_thr)
+            fidx = fidx[:, :kk].contiguous()
+            n_valid = nk
+        else:
+            fidx, _ = topk_segmented([cat_scores[b] for b in range(B)], kk, apply_sigmoid=False)
         final = torch.empty((B, kk, 7), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.roi3d_gather_rows7(cat_props.data_ptr(), B, L * P, fidx.data_ptr(), kk, final.data_ptr(),
@@ -257,6 +317,6 @@ class RPNProposal3D(object):
 
     def get_bboxes_single(self, cls_scores, bbox_preds, img_shape, cfg):
         """One image: cls_scores[l] [A, D, H, W], bbox_preds[l] [6A, D, H, W] (rpn_head_3d.py:72-79)."""
-        out = self.get_bboxes([c[None] for c in cls_scores], [r[None] for r in bbox_preds],
-                              [dict(img_shape=img_shape, scale_factor=1.0)], cfg)
+        out = self.get_proposals([c[None] for c in cls_scores], [r[None] for r in bbox_preds],
+                                 [dict(img_shape=img_shape, scale_factor=1.0)], cfg)
         return out[0]

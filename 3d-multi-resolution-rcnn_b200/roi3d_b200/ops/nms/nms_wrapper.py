@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ..._util import check_cuda_f32, scratch, stream_ptr
+from ..._util import check_cuda_f32, stream_ptr, workspace
 
 
 def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=None):
@@ -41,7 +41,7 @@ def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=No
         assert seg_counts.dtype == torch.int32 and seg_counts.is_cuda and seg_counts.numel() == nseg
         seg_counts = seg_counts.contiguous()
     nbytes = _lib.lib.roi3d_nms3d_workspace_bytes(nseg, n_max)
-    _buf, ws = scratch(dev, nbytes, "nms")
+    _buf, ws = workspace(dev, nbytes)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib.roi3d_nms3d_batched_presorted(
             dets.data_ptr(), None if seg_counts is None else seg_counts.data_ptr(),

@@ -502,11 +502,11 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
                          anchor_strides=[4, 8, 16, 32, 64], anchor_strides_depth=[2, 4, 8, 16, 32])
     cfg = dict(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
     metas = [dict(img_shape=(512, 512, 3, 160), scale_factor=1.0)] * Bv
-    props = head.get_bboxes(cls, reg, metas, cfg)
+    props = head.get_proposals(cls, reg, metas, cfg)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(5):
-        head.get_bboxes(cls, reg, metas, cfg)
+        head.get_proposals(cls, reg, metas, cfg)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 5
     ex["c4_proposal_path_8vol_us"] = dt * 1e6
@@ -515,11 +515,11 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ex["c4_proposals_out"] = [int(p.shape[0]) for p in props]
     head.cuda_graph = True   # same call with the launches captured once and replayed (stable activation buffers)
     for _ in range(2):
-        head.get_bboxes(cls, reg, metas, cfg)
+        head.get_proposals(cls, reg, metas, cfg)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(5):
-        props_g = head.get_bboxes(cls, reg, metas, cfg)
+        props_g = head.get_proposals(cls, reg, metas, cfg)
     torch.cuda.synchronize()
     ex["c4_proposal_path_8vol_cuda_graph_us"] = (time.perf_counter() - t0) / 5 * 1e6
     ex["c4_cuda_graph_identical"] = bool(all(torch.equal(a, b) for a, b in zip(props, props_g)))
@@ -543,7 +543,7 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ex["c5_detections"] = int(out5[0][0].shape[0])
 
     def hot_only():
-        props5 = stage.rpn.get_bboxes(cls5, reg5, metas5, roi_stage.TEST_CFG_RPN)
+        props5 = stage.rpn.get_proposals(cls5, reg5, metas5, roi_stage.TEST_CFG_RPN)
         rois5 = roi3d_b200.bbox2roi3D(props5)
         stage.bbox_ex(feats5[:4], rois5)
         stage.mask_ex(feats5[:4], rois5[:100].contiguous())

@@ -211,10 +211,13 @@ int roi3d_bbox2delta3d(const float *proposals_dev, int stride_p, const float *gt
 int roi3d_mask_paste(const float *mask_logits_dev, int n, int Dm, int Hm, int Wm, const int32_t *boxes_dev,
                      const int64_t *offsets_dev, float thr, uint8_t *out_dev, void *stream);
 
-/* Experiment knob (not part of the reference surface): key 0 = forward kernel variant, 1 = backward
- * kernel variant; value 0 = auto, 1/2 = alternative register tilings, 99 = literal (reference-order) path.
- * key 2 = sub-items one forward warp walks per RoI (0 = auto); key 4 = volume size in KB from which
- * roi3d_roi_align3d_forward_host pipelines its copies (0 = auto, 32 MB; -1 = never). */
+/* Experiment knob (not part of the reference surface): key 0 = forward kernel variant (0 = auto, 1 = one channel per
+ * lane, 50 = per-warp ring kernel where the streamed kernel would apply, 99 = literal reference-order path); key 1 =
+ * backward kernel variant (0 = auto, 1, 3 = per-warp tables, 99 = literal); key 2 = sub-items one ring-kernel warp
+ * walks per RoI (0 = auto); key 4 = volume size in KB from which roi3d_roi_align3d_forward_host pipelines its copies
+ * (0 = auto, 32 MB; -1 = never); key 6 = NMS mask kernel variant; key 7 = ring geometry of the streamed forward kernel
+ * (0 = 3 x 42 KB, 1 = 4 x 32 KB, 2 = 5 x 24 KB); key 9 = streamed kernel experiments (bit 0: no arithmetic, bit 1: no
+ * output store, bit 2: no largest-first order). */
 int roi3d_set_tuning(int key, int value);
 
 /* Host-buffer form of RoIAlign3D forward (H2D feats+rois, kernel, D2H out): the e2e path bench.py times. */
@@ -249,6 +252,20 @@ int roi3d_topk_segmented_ex(const float *scores_dev, const int64_t *seg_off, con
                             const int32_t *seg_adhw, int nseg, int k, int apply_sigmoid,
                             int small_segments_in_index_order, int64_t *out_idx_dev, float *out_val_dev,
                             void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Same, with the head's cached inside-flag masks (RPNHead3D.pos_indices / pos_indices_test, set at
+ * mmdet/models/anchor_heads/anchor_head_3d.py:212,239-243 and applied as `scores = scores[pos_indices]` before the
+ * top-k, rpn_head_3d.py:97-106): seg_mask_dev_ptrs is a HOST array [nseg] of DEVICE pointers (NULL entry, or a NULL
+ * array, = no mask) to uint8 masks indexed by the segment's LOGICAL index; only elements with a non-zero mask byte take
+ * part, and a segment's length for the k / small-segment rules is its masked-in count.  Returned indices are logical
+ * positions in the unmasked segment (what the decode step needs), in the order `scores[pos_indices].topk(k)` yields.
+ * out_count_dev (optional int32 [nseg]): rows returned per segment; out_sorted_dev (optional uint8 [nseg]): 1 = rows in
+ * score order, 0 = small segment returned in ascending index order.  Both are written on the device (no host read). */
+int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
+                                const int32_t *seg_adhw, const uint8_t *const *seg_mask_dev_ptrs, int nseg, int k,
+                                int apply_sigmoid, int small_segments_in_index_order, int64_t *out_idx_dev,
+                                float *out_val_dev, int32_t *out_count_dev, uint8_t *out_sorted_dev, void *workspace_dev,
+                                size_t workspace_bytes, void *stream);
 
 /* Tail of RPNHead3D.get_bboxes_single for all (image, level) segments (rpn_head_3d.py:135-148): the first
  * min(num_keep, nms_post) kept rows of every level, in NMS return order, concatenated per image in level order.

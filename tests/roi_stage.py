@@ -3,24 +3,24 @@ FPN pyramids with random-init heads.  The hot path (proposals, RoI extractors, N
 (FC / conv3d, out of scope: cuBLAS / cuDNN) are plain torch layers with the reference's shapes
 (SharedFCBBoxHead3D: convfc_bbox_head_3d.py:130-166; FCNMaskHead3D: fcn_mask_head_3d.py:89-97).
 
-The config dicts below are the reference's own values (configs/3d-multi-resolution-rcnn.py:16-27,38-45,66-73,
-132-143), copied as data so the harness also checks that they construct the drop-in modules unchanged."""
+The config dicts come from tests/golden/reference_config_hot_path.json, which tests/golden/make_config_golden.py
+extracts from the reference's own configs/3d-multi-resolution-rcnn.py (:16-27, :38-45, :66-73, :132-143) with
+roi3d_b200.models.config.load_config; tests/test_config.py re-executes the real file (where /root/reference exists)
+and checks the fixture against it, so the harness builds the drop-in modules from the reference's unchanged values."""
+import json
+import os
+
 import torch
 import torch.nn as nn
 
-RPN_HEAD = dict(type='RPNHead3D', in_channels=64, feat_channels=64, anchor_scales=[2], anchor_depth_scales=[2],
-                anchor_ratios=[1.0], anchor_strides=[4, 8, 16, 32, 64], anchor_strides_depth=[2, 4, 8, 16, 32],
-                target_means=[.0, .0, .0, .0, .0, .0], target_stds=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0],
-                use_sigmoid_cls=True)
-BBOX_ROI_EXTRACTOR = dict(type='SingleRoIExtractor',
-                          roi_layer=dict(type='RoIAlign3D', out_size=7, out_size_depth=3, sample_num=2),
-                          out_channels=64, featmap_strides=[4, 8, 16, 32], featmap_strides_depth=[2, 4, 8, 16])
-MASK_ROI_EXTRACTOR = dict(type='SingleRoIExtractor',
-                          roi_layer=dict(type='RoIAlign3D', out_size=14, out_size_depth=10, sample_num=2),
-                          out_channels=64, featmap_strides=[4, 8, 16, 32], featmap_strides_depth=[2, 4, 8, 16])
-TEST_CFG_RPN = dict(nms_across_levels=False, nms_pre=2000, nms_post=2000, max_num=2000, nms_thr=0.7, min_bbox_size=0)
-TEST_CFG_RCNN = dict(score_thr=0.2, nms=dict(type='nms', iou_thr=0.5), max_per_img=2000, mask_thr_binary=0.25)
-BBOX_TARGET_STDS = [0.1, 0.1, 0.2, 0.2, 0.1, 0.1]
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_config_hot_path.json")) as _f:
+    REF_CFG = json.load(_f)
+RPN_HEAD = REF_CFG['rpn_head']
+BBOX_ROI_EXTRACTOR = REF_CFG['bbox_roi_extractor']
+MASK_ROI_EXTRACTOR = REF_CFG['mask_roi_extractor']
+TEST_CFG_RPN = REF_CFG['test_cfg']['rpn']
+TEST_CFG_RCNN = REF_CFG['test_cfg']['rcnn']
+BBOX_TARGET_STDS = REF_CFG['bbox_head_target_stds']
 
 
 class RoIStage(nn.Module):
@@ -44,7 +44,7 @@ class RoIStage(nn.Module):
     def forward(self, feats, cls_scores, bbox_preds, img_metas):
         """feats: 4+ FPN levels [B,C,D,H,W]; returns per-image (det_bboxes [k,7], det_labels, mask logits)."""
         import roi3d_b200
-        proposals = self.rpn.get_bboxes(cls_scores, bbox_preds, img_metas, TEST_CFG_RPN)
+        proposals = self.rpn.get_proposals(cls_scores, bbox_preds, img_metas, TEST_CFG_RPN)
         rois = roi3d_b200.bbox2roi3D(proposals)
         x = self.bbox_ex(feats[:4], rois)
         h = self.fc(x.flatten(1))

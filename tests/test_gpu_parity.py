@@ -433,9 +433,9 @@ def test_rpn_get_bboxes_matches_oracle(oracle, dev):
     head = RPNProposal3D(anchor_scales=[2], anchor_depth_scales=[2], anchor_ratios=[1.0], anchor_strides=strides,
                          anchor_strides_depth=dstrides)
     metas = [dict(img_shape=(64, 64, 3, 16), scale_factor=1.0)] * B
-    got = head.get_bboxes([torch.from_numpy(c).to(dev) for c in cls], [torch.from_numpy(r).to(dev) for r in reg],
-                          metas, cfg)
-    assert len(got) == B
+    got, anchors_list = head.get_bboxes([torch.from_numpy(c).to(dev) for c in cls],
+                                        [torch.from_numpy(r).to(dev) for r in reg], metas, cfg)
+    assert len(got) == B and len(anchors_list) == B   # the reference's (result_list, anchors_list) pair
     for b in range(B):
         anchors = [oracle.grid_anchors(oracle.gen_base_anchors(s, [2], [2], [1.0], ds), d, s, ds)
                    for d, s, ds in zip(dims, strides, dstrides)]
@@ -444,6 +444,97 @@ def test_rpn_get_bboxes_matches_oracle(oracle, dev):
         g = got[b].cpu().numpy()
         assert g.shape == want.shape
         assert np.abs(g - want).max() <= 1e-3
+
+
+@pytest.mark.parametrize("which", ["pos_indices", "pos_indices_test", "shape_mismatch", "few_left"])
+def test_rpn_get_bboxes_pos_indices_filter(oracle, dev, which):
+    """The head's cached inside-flag masks (anchor_head_3d.py:212,239-243) as rpn_head_3d.py:97-106 applies them: only
+    on levels with more than nms_pre anchors, only when the mask has the scores' shape; a level left with no more than
+    nms_pre anchors after masking is not sorted."""
+    from roi3d_b200 import RPNProposal3D
+    dims = [(8, 16, 16), (4, 8, 8), (2, 4, 4)]
+    strides, dstrides = [4, 8, 16], [2, 4, 8]
+    cls, reg = _rpn_inputs(1, dims, 51)
+    nms_pre = 300
+    cfg = dict(nms_pre=nms_pre, nms_post=100, max_num=150, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
+    head = RPNProposal3D(anchor_scales=[2], anchor_depth_scales=[2], anchor_ratios=[1.0], anchor_strides=strides,
+                         anchor_strides_depth=dstrides)
+    rng = np.random.default_rng(52)
+    keep_frac = 0.1 if which == "few_left" else 0.6     # few_left: level 0 keeps ~200 < nms_pre of its 2048 anchors
+    masks = [(rng.random(int(np.prod(d))) < keep_frac).astype(np.uint8) for d in dims]
+    if which == "shape_mismatch":
+        masks = [m[None].repeat(2, 0) for m in masks]    # [imgs, n] as images_to_levels leaves it for 2 images: ignored
+    kw = {"pos_indices_test" if which == "pos_indices_test" else "pos_indices": masks}
+    setattr(head, "pos_indices_test" if which == "pos_indices_test" else "pos_indices",
+            [torch.from_numpy(m).to(dev) for m in masks])
+    metas = [dict(img_shape=(64, 64, 3, 16), scale_factor=1.0)]
+    got, _ = head.get_bboxes([torch.from_numpy(c).to(dev) for c in cls], [torch.from_numpy(r).to(dev) for r in reg],
+                             metas, cfg)
+    anchors = [oracle.grid_anchors(oracle.gen_base_anchors(s, [2], [2], [1.0], ds), d, s, ds)
+               for d, s, ds in zip(dims, strides, dstrides)]
+    want = oracle.get_bboxes_single([c[0] for c in cls], [r[0] for r in reg], anchors, (64, 64, 3, 16),
+                                    nms_pre, 100, 150, 0.7, **kw)
+    plain = oracle.get_bboxes_single([c[0] for c in cls], [r[0] for r in reg], anchors, (64, 64, 3, 16),
+                                     nms_pre, 100, 150, 0.7)
+    g = got[0].cpu().numpy()
+    assert g.shape == want.shape and np.abs(g - want).max() <= 1e-3
+    if which == "shape_mismatch":
+        assert np.array_equal(want, plain)
+    else:
+        assert want.shape != plain.shape or not np.array_equal(want, plain)   # the mask really changed the proposals
+
+
+@pytest.mark.parametrize("cfg_kw", [dict(nms_across_levels=True), dict(nms_pre=0, nms_post=60, max_num=90)])
+def test_rpn_get_bboxes_across_levels_and_unsorted(oracle, dev, cfg_kw):
+    """nms_across_levels=True (rpn_head_3d.py:140-142) and nms_pre <= 0 (no level is sorted: NMS sees anchor order and
+    `proposals[:nms_post]` cuts in that order)."""
+    from roi3d_b200 import RPNProposal3D
+    B = 2
+    dims = [(6, 12, 12), (3, 6, 6)]
+    strides, dstrides = [4, 8], [2, 4]
+    cls, reg = _rpn_inputs(B, dims, 53)
+    cfg = dict(nms_pre=200, nms_post=100, max_num=120, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
+    cfg.update(cfg_kw)
+    head = RPNProposal3D(anchor_scales=[2], anchor_depth_scales=[2], anchor_ratios=[1.0], anchor_strides=strides,
+                         anchor_strides_depth=dstrides)
+    metas = [dict(img_shape=(48, 48, 3, 12), scale_factor=1.0)] * B
+    got = head.get_proposals([torch.from_numpy(c).to(dev) for c in cls], [torch.from_numpy(r).to(dev) for r in reg],
+                             metas, cfg)
+    for b in range(B):
+        anchors = [oracle.grid_anchors(oracle.gen_base_anchors(s, [2], [2], [1.0], ds), d, s, ds)
+                   for d, s, ds in zip(dims, strides, dstrides)]
+        want = oracle.get_bboxes_single([c[b] for c in cls], [r[b] for r in reg], anchors, (48, 48, 3, 12),
+                                        cfg['nms_pre'], cfg['nms_post'], cfg['max_num'], 0.7,
+                                        nms_across_levels=cfg['nms_across_levels'])
+        g = got[b].cpu().numpy()
+        assert g.shape == want.shape
+        assert np.abs(g - want).max() <= 1e-3
+
+
+def test_layout_conversion_reuse_is_scoped_and_sees_rewrites(oracle, dev):
+    """NCDHW inputs are converted on every call unless the caller opens a reuse scope; a buffer rewritten through its
+    address (what a CUDA-graph replay does: `_version` does not change) is therefore never served stale."""
+    import roi3d_b200
+    from roi3d_b200.ops import RoIAlign3D
+    layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
+    f = torch.from_numpy(_feats((1, 64, 8, 16, 16), 60)).to(dev)
+    rois = torch.from_numpy(synth.c2_rois(12, seed=61, img=(64, 64, 16))).to(dev)
+    a = layer(f, rois)
+    v0 = f._version
+    raw = torch.from_numpy(_feats((1, 64, 8, 16, 16), 62)).to(dev)
+    # rewrite the same storage without touching the version counter (a kernel writing through data_ptr)
+    torch.cuda.current_stream().synchronize()
+    f.data.copy_(raw)
+    assert f._version == v0
+    b = layer(f, rois)
+    assert rel_err(b.cpu().numpy(), oracle.roi_align3d_forward(raw.cpu().numpy(), rois.cpu().numpy(), 7, 7, 0.25, 0.5, 2)) <= FWD_TOL
+    assert not torch.equal(a, b)
+    with roi3d_b200.reuse_layout_conversions():
+        c1 = layer(f, rois)
+        c2 = layer(f, rois)          # second call reuses the converted copy
+        assert torch.equal(c1, c2) and torch.equal(c1, b)
+        assert len(roi3d_b200._util._scopes[-1]) == 1
+    assert not roi3d_b200._util._scopes
 
 
 def test_multiclass_nms_matches_oracle(oracle, dev):
@@ -496,7 +587,7 @@ def test_reference_config_roi_stage(oracle, dev):
     assert det.shape[0] > 0, "random heads should leave some detections above score_thr=0.2"
     assert masks.shape[1:] == (2, 20, 28, 28)          # deconv doubles 10x14x14 (mask_size 28 / depth 20, config :121-122)
     # the extractor inside the stage vs the oracle, on the stage's own proposals
-    props = stage.rpn.get_bboxes(cls, reg, metas, roi_stage.TEST_CFG_RPN)
+    props = stage.rpn.get_proposals(cls, reg, metas, roi_stage.TEST_CFG_RPN)
     rois = roi3d_b200.bbox2roi3D(props)[:64].contiguous()
     got = stage.bbox_ex(feats[:4], rois).cpu().numpy()
     rn = rois.cpu().numpy()
@@ -540,6 +631,97 @@ def test_c2_full_size_properties(oracle, dev):
     lhs = float((out.detach().double() * gout.double()).sum())
     rhs = float((x.double() * xg.grad.double()).sum())
     assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_c3_full_size_parity(oracle, dev):
+    """BASELINE C3 at full size: mask branch 14x14x14 over 4 FPN levels (2 x 256 ch x {40x128x128 ... 5x16x16}), level
+    mapping, 2 x 512 RoIs, forward AND backward.  The whole 2.9 GB output is produced on the device; the oracle checks
+    three channels of every RoI (forward) and the three matching channel planes of every level's gradient (backward,
+    with the other channels' grad_out zeroed), plus the level indices and a partition-of-unity pass."""
+    from roi3d_b200 import SingleRoIExtractor
+    B, C = 2, 256
+    dims = [(40, 128, 128), (20, 64, 64), (10, 32, 32), (5, 16, 16)]
+    strides, dstrides = [4, 8, 16, 32], [2, 4, 8, 16]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)
+    pyr = [cl(torch.randn((B, C) + d, device=dev, generator=gen)).requires_grad_(True) for d in dims]
+    rois_np = synth.c3_rois(512, vols=B, seed=4)
+    rois = torch.from_numpy(rois_np).to(dev)
+    ex = SingleRoIExtractor(dict(type='RoIAlign3D', out_size=14, out_size_depth=14, sample_num=2), C, strides, dstrides)
+    lv = oracle.map_roi_levels(rois_np, 4)
+    assert np.array_equal(ex.map_roi_levels(rois, 4).cpu().numpy(), lv)
+    assert all((lv == l).sum() > 30 for l in range(4)), np.bincount(lv, minlength=4)   # all four levels populated
+    out = ex(pyr, rois)
+    assert out.shape == (1024, C, 14, 14, 14)
+    ch = [0, 131, 255]
+    got = out[:, ch].detach().cpu().numpy()
+    want = np.zeros_like(got)
+    for l in range(4):
+        sel = lv == l
+        f3 = pyr[l].detach()[:, ch].contiguous().cpu().numpy()
+        want[sel] = oracle.roi_align3d_forward(f3, rois_np[sel], 14, 14, 1 / strides[l], 1 / dstrides[l], 2)
+    assert rel_err(got, want) <= FWD_TOL
+    # backward: gradient only through the three checked channels
+    g3 = torch.randn((1024, 3, 14, 14, 14), device=dev, generator=gen)
+    gout = torch.zeros_like(out)
+    gout[:, ch] = g3
+    out.backward(gout)
+    del out, gout
+    g3n = g3.cpu().numpy()
+    for l in range(4):
+        sel = lv == l
+        wg = oracle.roi_align3d_backward(g3n[sel], rois_np[sel], (B, 3) + dims[l], 1 / strides[l], 1 / dstrides[l], 2)
+        gl = pyr[l].grad
+        assert rel_err(gl[:, ch].cpu().numpy(), wg) <= BWD_TOL
+        others = [c for c in (1, 100, 254)]
+        assert float(gl[:, others].abs().max()) == 0.0    # channels without grad_out receive nothing
+    # weights of every bin sum to one wherever all samples fall inside the map
+    ones = [cl(torch.full((B, 64) + d, 2.5, device=dev)) for d in dims]
+    ex64 = SingleRoIExtractor(dict(type='RoIAlign3D', out_size=14, out_size_depth=14, sample_num=2), 64, strides, dstrides)
+    assert float((ex64(ones, rois) - 2.5).abs().max()) <= 1e-5
+
+
+def test_c4_full_size_parity(oracle, dev):
+    """BASELINE C4 at full size: 8 volumes of 512x512x160, 5 levels (1 310 720 ... 320 anchors, A = 1), nms_pre 2000,
+    NMS 0.7, nms_post 1000, max_num 1000.  Per level the selected index sets and their order are exact against the
+    oracle's stable top-k of torch-formula sigmoid scores; the final proposals match oracle.get_bboxes_single."""
+    from roi3d_b200 import RPNProposal3D
+    from roi3d_b200.models.anchor_heads import topk_segmented
+    Bv = 8
+    dims = [(80, 128, 128), (40, 64, 64), (20, 32, 32), (10, 16, 16), (5, 8, 8)]
+    strides, dstrides = [4, 8, 16, 32, 64], [2, 4, 8, 16, 32]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(6)
+    cls = [2 * torch.randn((Bv, 1) + d, device=dev, generator=gen) for d in dims]
+    reg = [0.1 * torch.randn((Bv, 6) + d, device=dev, generator=gen) for d in dims]
+    head = RPNProposal3D(anchor_scales=[2], anchor_depth_scales=[2], anchor_ratios=[1.0], anchor_strides=strides,
+                         anchor_strides_depth=dstrides)
+    cfg = dict(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
+    metas = [dict(img_shape=(512, 512, 3, 160), scale_factor=1.0)] * Bv
+    props = head.get_proposals(cls, reg, metas, cfg)
+    # (1) per-level top-k: index sets and order, all 8 volumes of the three levels that are top-k'd
+    segs = [cls[l][b] for b in range(Bv) for l in range(3)]
+    idx, val = topk_segmented(segs, 2000, apply_sigmoid=True, permute_adhw=True, small_in_index_order=True)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    j = 0
+    for b in range(Bv):
+        for l in range(3):
+            sc = cls[l][b].permute(2, 3, 1, 0).reshape(-1).sigmoid().cpu().numpy()   # rpn_head_3d.py:87-90, on CUDA
+            want = oracle.topk(sc, 2000)
+            assert np.array_equal(idx[j], want), (b, l)
+            assert np.array_equal(val[j], sc[want])
+            j += 1
+    # (2) final proposals of every volume
+    anchors = [oracle.grid_anchors(oracle.gen_base_anchors(s, [2], [2], [1.0], ds), d, s, ds)
+               for d, s, ds in zip(dims, strides, dstrides)]
+    for b in range(Bv):
+        want = oracle.get_bboxes_single([c[b].cpu().numpy() for c in cls], [r[b].cpu().numpy() for r in reg], anchors,
+                                        (512, 512, 3, 160), 2000, 1000, 1000, 0.7)
+        g = props[b].cpu().numpy()
+        assert g.shape == want.shape, (b, g.shape, want.shape)
+        assert np.abs(g - want).max() <= 1e-3
+        assert np.abs(g[:, 6] - want[:, 6]).max() <= 2e-7   # scores: the same selection in the same order (host expf
+                                                             # and device expf may differ in the last bit)
 
 
 def test_c1_full_size_properties(oracle, dev):
@@ -943,9 +1125,9 @@ def test_rpn_get_bboxes_cuda_graph_replay(dev):
     reg = [0.1 * torch.randn((2, 6) + d, device=dev, generator=g) for d in dims]
     for rnd in range(3):
         head.cuda_graph = False
-        want = head.get_bboxes(cls, reg, metas, cfg)
+        want = head.get_proposals(cls, reg, metas, cfg)
         head.cuda_graph = True
-        got = head.get_bboxes(cls, reg, metas, cfg)
+        got = head.get_proposals(cls, reg, metas, cfg)
         assert len(got) == len(want) == 2
         for a, b in zip(got, want):
             assert torch.equal(a, b) and a.shape[0] > 0

@@ -35,7 +35,7 @@ for l in range(3):
     print("  nms kept", m, len(keep_o), np.array_equal(ks[0, :m].cpu().numpy(), so))
 cfg = dict(nms_pre=300, nms_post=100, max_num=150, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
 metas = [dict(img_shape=(64, 64, 3, 16), scale_factor=1.0)] * B
-got = head.get_bboxes([torch.from_numpy(c).to(dev) for c in cls], [torch.from_numpy(r).to(dev) for r in reg], metas, cfg)
+got = head.get_proposals([torch.from_numpy(c).to(dev) for c in cls], [torch.from_numpy(r).to(dev) for r in reg], metas, cfg)
 anchors = [oracle.grid_anchors(oracle.gen_base_anchors(s, [2], [2], [1.0], ds), d, s, ds) for d, s, ds in zip(dims, strides, dstrides)]
 want = oracle.get_bboxes_single([c[b] for c in cls], [r[b] for r in reg], anchors, (64, 64, 3, 16), 300, 100, 150, 0.7)
 g = got[b].cpu().numpy()

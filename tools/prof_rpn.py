@@ -22,23 +22,23 @@ head = RPNProposal3D(anchor_scales=[2], anchor_depth_scales=[2], anchor_ratios=[
 cfg = dict(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
 metas = [dict(img_shape=(512, 512, 3, 160), scale_factor=1.0)] * Bv
 for _ in range(3):
-    head.get_bboxes(cls, reg, metas, cfg)
+    head.get_proposals(cls, reg, metas, cfg)
 torch.cuda.synchronize()
 for rep in range(3):
     ts = []
     for _ in range(10):
         t0 = time.perf_counter()
-        out = head.get_bboxes(cls, reg, metas, cfg)
+        out = head.get_proposals(cls, reg, metas, cfg)
         torch.cuda.synchronize()
         ts.append((time.perf_counter() - t0) * 1e6)
     print("wall per call us", sum(ts) / len(ts), "median", sorted(ts)[5], "max", max(ts), "props", [int(o.shape[0]) for o in out][:3])
 head.cuda_graph = True
 for _ in range(3):
-    head.get_bboxes(cls, reg, metas, cfg)
+    head.get_proposals(cls, reg, metas, cfg)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 for _ in range(10):
-    out = head.get_bboxes(cls, reg, metas, cfg)
+    out = head.get_proposals(cls, reg, metas, cfg)
 torch.cuda.synchronize()
 print("wall per call us (CUDA graph replay)", (time.perf_counter() - t0) / 10 * 1e6)
 head.cuda_graph = False
@@ -47,6 +47,6 @@ if len(sys.argv) > 2:
 from torch.profiler import profile, ProfilerActivity  # noqa: E402
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
-        head.get_bboxes(cls, reg, metas, cfg)
+        head.get_proposals(cls, reg, metas, cfg)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))

@@ -165,11 +165,11 @@ if "c4" in which:
                          anchor_strides=[4, 8, 16, 32, 64], anchor_strides_depth=[2, 4, 8, 16, 32])
     cfg = dict(nms_pre=2000, nms_post=1000, max_num=1000, nms_thr=0.7, min_bbox_size=0, nms_across_levels=False)
     metas = [dict(img_shape=(512, 512, 3, 160), scale_factor=1.0)] * B
-    out = head.get_bboxes(cls, reg, metas, cfg)
+    out = head.get_proposals(cls, reg, metas, cfg)
     res["c4_num_proposals"] = [int(o.shape[0]) for o in out]
     t0 = time.perf_counter(); torch.cuda.synchronize()
     for _ in range(5):
-        head.get_bboxes(cls, reg, metas, cfg)
+        head.get_proposals(cls, reg, metas, cfg)
     torch.cuda.synchronize()
     res["c4_get_bboxes_8vol_wall_us"] = (time.perf_counter() - t0) / 5 * 1e6
     segs = [cls[l][b] for b in range(B) for l in range(5)]
