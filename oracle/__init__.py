@@ -259,30 +259,35 @@ def grid_anchors(base_anchors, featmap_size, stride, depth_stride):
 
 def get_bboxes_single(cls_scores, bbox_preds, mlvl_anchors, img_shape, nms_pre, nms_post, max_num, nms_thr,
                       target_means=(0, 0, 0, 0, 0, 0), target_stds=(1, 1, 1, 1, 1, 1),
-                      nms_across_levels=False, contract=True, pos_indices=None, pos_indices_test=None):
+                      nms_across_levels=False, contract=True, pos_indices=None, pos_indices_test=None, scores=None):
     """RPNHead3D.get_bboxes_single (mmdet/models/anchor_heads/rpn_head_3d.py:72-149), sigmoid scores,
     min_bbox_size == 0.  cls_scores[l]: [A, D, H, W]; bbox_preds[l]: [6A, D, H, W].  pos_indices / pos_indices_test:
     the head's cached per-level inside-flag masks (anchor_head_3d.py:212,239-243); a mask is applied only to a level
-    with more than nms_pre anchors and only when its shape equals the scores' shape (:97-106)."""
+    with more than nms_pre anchors and only when its shape equals the scores' shape (:97-106).
+    scores: optional per-level flat sigmoid scores to use instead of the host's 1/(1+expf(-x)) -- e.g. torch's CUDA
+    sigmoid of the same logits, whose last bit can differ from glibc's expf and would otherwise reorder near-ties."""
     mlvl = []
     for lvl, (cls, reg, anchors) in enumerate(zip(cls_scores, bbox_preds, mlvl_anchors)):
         cls, reg = _f32(cls), _f32(reg)
-        scores = sigmoid(np.transpose(cls, (2, 3, 1, 0)).reshape(-1))
+        if scores is None:
+            sc = sigmoid(np.transpose(cls, (2, 3, 1, 0)).reshape(-1))
+        else:
+            sc = _f32(scores[lvl]).reshape(-1)
         reg = np.transpose(reg, (2, 3, 1, 0)).reshape(-1, 6)
         anchors = _f32(anchors)
-        if nms_pre > 0 and scores.shape[0] > nms_pre:
+        if nms_pre > 0 and sc.shape[0] > nms_pre:
             sel = None
-            if pos_indices is not None and np.asarray(pos_indices[lvl]).shape == scores.shape:
+            if pos_indices is not None and np.asarray(pos_indices[lvl]).shape == sc.shape:
                 sel = np.asarray(pos_indices[lvl]).astype(bool)
-            elif pos_indices_test is not None and np.asarray(pos_indices_test[lvl]).shape == scores.shape:
+            elif pos_indices_test is not None and np.asarray(pos_indices_test[lvl]).shape == sc.shape:
                 sel = np.asarray(pos_indices_test[lvl]).astype(bool)
             if sel is not None:
-                scores, reg, anchors = scores[sel], reg[sel], anchors[sel]
-        if nms_pre > 0 and scores.shape[0] > nms_pre:
-            idx = topk(scores, nms_pre)
-            reg, anchors, scores = reg[idx], anchors[idx], scores[idx]
+                sc, reg, anchors = sc[sel], reg[sel], anchors[sel]
+        if nms_pre > 0 and sc.shape[0] > nms_pre:
+            idx = topk(sc, nms_pre)
+            reg, anchors, sc = reg[idx], anchors[idx], sc[idx]
         props = delta2bbox3d(anchors, reg, target_means, target_stds, img_shape)
-        props = np.concatenate([props, scores[:, None]], axis=1)
+        props = np.concatenate([props, sc[:, None]], axis=1)
         props, _ = nms_wrapper_3d(props, nms_thr, contract)
         mlvl.append(props[:nms_post])
     props = np.concatenate(mlvl, axis=0) if mlvl else np.zeros((0, 7), np.float32)

@@ -715,13 +715,15 @@ def test_c4_full_size_parity(oracle, dev):
     anchors = [oracle.grid_anchors(oracle.gen_base_anchors(s, [2], [2], [1.0], ds), d, s, ds)
                for d, s, ds in zip(dims, strides, dstrides)]
     for b in range(Bv):
+        # scores from the reference's own expression on CUDA (rpn_head_3d.py:87-90): glibc's expf can differ from the
+        # device's in the last bit, which would reorder near-ties of the final top-k
+        sc = [c[b].permute(2, 3, 1, 0).reshape(-1).sigmoid().cpu().numpy() for c in cls]
         want = oracle.get_bboxes_single([c[b].cpu().numpy() for c in cls], [r[b].cpu().numpy() for r in reg], anchors,
-                                        (512, 512, 3, 160), 2000, 1000, 1000, 0.7)
+                                        (512, 512, 3, 160), 2000, 1000, 1000, 0.7, scores=sc)
         g = props[b].cpu().numpy()
         assert g.shape == want.shape, (b, g.shape, want.shape)
-        assert np.abs(g - want).max() <= 1e-3
-        assert np.abs(g[:, 6] - want[:, 6]).max() <= 2e-7   # scores: the same selection in the same order (host expf
-                                                             # and device expf may differ in the last bit)
+        assert np.array_equal(g[:, 6], want[:, 6])     # scores exact: the same selection in the same order
+        assert np.abs(g[:, :6] - want[:, :6]).max() <= 1e-3
 
 
 def test_c1_full_size_properties(oracle, dev):
