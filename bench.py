@@ -8,11 +8,15 @@ Metric (BASELINE.json): RoIs/s of 3D RoIAlign forward on workload C2 = BASELINE.
 One "step" = one RoIAlign3D forward over one batch of 512 RoIs.  Every rank runs the same per-GPU workload on its own
 volume (weak scaling, no data-path collective: volumes are independent); `value` = N * 512 * K / max-over-ranks
 device time.  One JSON line is printed by rank 0 with, besides the contract keys:
-  roofline      dominant kernel (roi_align3d_fwd_ring2_kernel): algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  roofline      dominant kernel (roi_align3d_fwd_stream_kernel; its 7 us plan kernel is inside the timed step too):
+                algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json, for channels-last AND for NCDHW input
   cpu_baseline  the oracle (CPU restatement of the reference; the reference has no CPU RoIAlign) on a bounded sample
   e2e           the same metric through the C-ABI host-buffer entry (pinned host NCDHW features -> H2D -> layout
                 conversion -> kernel -> D2H of the pooled features), i.e. what a caller holding host tensors pays
   extra         secondary rows: NCDHW-input path, RoIAlign backward, C3 (mask branch fwd+bwd, 4 levels), C1 3D NMS
+  ranks         (N > 1) per-rank median step time: every rank runs the SAME RoIs and features (same seeds), so the
+                spread is the machine's, not the draw's; after the timed region the ranks also run C4 -> C5 sharded one
+                volume per rank and all-gather the detections over NCCL (the path's only collective)
 `--impl reference` times the reference's own algorithm on the host cores (oracle port, all threads) on the same workload.
 """
 import argparse
@@ -37,6 +41,12 @@ UNIT = "RoIs/s"
 C2 = dict(B=1, C=256, D=40, H=128, W=128, K=512, P=7, PD=7, scale=0.25, scale_d=0.5, sample_num=2)
 WORKLOAD = ("C2: RoIAlign3D fwd, FPN P2 level 256ch x 40x128x128 fp32 (671 MB, > L2 so no flush needed), 512 RoIs, "
             "7x7x7 bins, sample_num 2; features resident in HBM in torch.channels_last_3d memory format")
+
+
+CONFIG = {"workload": WORKLOAD, "l2": "inputs (671 MB features + 180 MB output) exceed the 126 MB L2",
+          "per_gpu": "each rank runs C2 on its own copy of the same volume and RoIs; no collective on the data path",
+          "e2e_layout": "host features NCDHW-contiguous (reference layout); conversion to channels-last "
+                        "runs on the device inside the timed call"}
 
 
 def parse_args():
@@ -152,10 +162,10 @@ class ClockSampler(object):
 def c2_inputs(torch, dev, rank):
     import synth
     g = torch.Generator(device=dev)
-    g.manual_seed(1 + rank)
+    g.manual_seed(1)   # the same volume and RoIs on every rank: the scaling curve measures the machine, not the draw
     feats = torch.randn((C2["B"], C2["C"], C2["D"], C2["H"], C2["W"]), device=dev, generator=g)
     feats_cl = feats.contiguous(memory_format=torch.channels_last_3d)
-    rois_np = synth.c2_rois(C2["K"], seed=2 + rank)
+    rois_np = synth.c2_rois(C2["K"], seed=2)
     return feats, feats_cl, rois_np
 
 
@@ -206,7 +216,11 @@ def run_reference(args):
     oracle.roi_align3d_forward(feats, rois[:8], C2["P"], C2["PD"], C2["scale"], C2["scale_d"], C2["sample_num"])
     t8 = max(time.perf_counter() - t0, 1e-4)
     n = int(min(C2["K"], max(8, 8 * round(1.0 / t8))))
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    # --steps / --warmup are honoured as given; the per-step sample (n RoIs, ~1 s of CPU work) keeps the run bounded
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    budget_steps = max(1, int(150.0 / max(t8 * n / 8.0, 1e-3)))   # never more than ~150 s of CPU work in total
+    if steps + warmup > budget_steps:
+        n = int(max(8, n * budget_steps // (steps + warmup)))
     for _ in range(warmup):
         oracle.roi_align3d_forward(feats, rois[:n], C2["P"], C2["PD"], C2["scale"], C2["scale_d"], C2["sample_num"])
     t0 = time.perf_counter()
@@ -219,7 +233,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm: host cores only, no GPU work"},
+        "config": dict(CONFIG, note="CPU arm: host cores only, no GPU work; each step is a bounded sample of the workload"),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -273,9 +287,15 @@ def main():
         launches[0] += 1
 
     total_ms, per = time_steps(torch, step, steps, warmup, dist)
-    gpu_launches = steps  # one roi_align3d_fwd_ring2_kernel launch per step inside the timed region
+    gpu_launches = 2 * steps  # per step: roi_align3d_plan_kernel (7 us) + roi_align3d_fwd_stream_kernel
     value = world * C2["K"] * steps / (total_ms * 1e-3)
-    kernel_ms = float(np.median(per))  # one launch per step: the per-step event time is the kernel's duration
+    kernel_ms = float(np.median(per))  # per-step event time = plan kernel + streamed kernel (+ the launch gap)
+    rank_us = None
+    if dist is not None:  # per-rank medians: same inputs everywhere, so the spread is contention / clocks
+        t = torch.tensor([kernel_ms * 1e3], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_us = [float(x.item()) for x in allt]
 
     # ---- e2e: host buffers through the C-ABI host entry ---------------------------------------------------
     e2e_steps = max(1, min(steps, 10))
@@ -309,6 +329,11 @@ def main():
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
+    # ---- N > 1: BASELINE configs 4-5 sharded one volume per rank + the path's only collective --------------------
+    multi = None
+    if dist is not None:
+        multi = sharded_stage_and_gather(torch, dist, dev, rank, world)
+
     # ---- secondary rows -------------------------------------------------------------------------------------
     extra = {}
     if not args.no_extra and rank == 0:
@@ -330,34 +355,83 @@ def main():
         alg_bytes = out_bytes + U * C2["C"] * 4 + C2["K"] * 28
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "r01_end_c2_fwd_ncu_summary.json")
+        prof = os.path.join(ROOT, "profiles", "r02_c2_fwd_stream_ncu_summary.json")
         if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_ring2_kernel<7,7,2,3,5,18,2,0,1,0>", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_stream_kernel<3,43008> (+ roi_align3d_plan_kernel in the same step)",
+                    "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes": alg_bytes, "unique_voxels": U, "kernel_us": kernel_ms * 1e3,
-                    "output_only_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9}
+                    "output_only_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9,
+                    "layout": "channels-last (NDHWC) features resident in HBM"}
+        if extra.get("c2_fwd_ncdhw_input_us"):
+            # the reference's own layout: the NCDHW -> NDHWC conversion (1.34 GB of traffic) runs inside the call
+            us = extra["c2_fwd_ncdhw_input_us"]
+            roofline["ncdhw_input"] = {"kernel_us": us, "achieved": alg_bytes / (us * 1e-6) / 1e9,
+                                       "frac": alg_bytes / (us * 1e-6) / 1e9 / peak,
+                                       "note": "same algorithmic bytes; the layout conversion is extra traffic, not credited"}
         cpu = cpu_baseline() if world == 1 else None  # reported on rank 0 at N=1 only
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "inputs (671 MB features + 180 MB output) exceed the 126 MB L2",
-                       "per_gpu": "each rank runs C2 on its own volume; no collective on the data path",
-                       "e2e_layout": "host features NCDHW-contiguous (reference layout); conversion to channels-last "
-                                     "runs on the device inside the timed call"},
+            "config": CONFIG,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "identical_to_device_resident_call": e2e_same},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
         }
+        if rank_us is not None:
+            line["ranks"] = {"step_us_per_rank": rank_us, "min": min(rank_us), "median": float(np.median(rank_us)),
+                             "max": max(rank_us)}
+        if multi is not None:
+            line["multi_gpu"] = multi
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sharded_stage_and_gather(torch, dist, dev, rank, world):
+    """BASELINE configs[3] / [4] as they are stated ("8 volumes sharded over 8 B200"): every rank runs the RoI stage of
+    configs/3d-multi-resolution-rcnn.py (proposal path C4 -> extractors -> heads -> multiclass NMS, C5 harness) on its
+    OWN 512x512x160 volume, then the per-volume detections are all-gathered over NCCL (roi3d_b200.parallel.
+    gather_detections, replacing eval_hooks.py:134-149).  Device-timed per rank, max over ranks reported; rank 0 checks
+    that it received every volume and that its own volume came back bit-identical."""
+    import roi_stage
+    from roi3d_b200.parallel import gather_detections
+    stage = roi_stage.RoIStage(max_masks=50).to(dev)
+    feats5, cls5, reg5, metas5 = roi_stage.synthetic_inputs(1, device=dev, seed=7 + rank)
+    out5 = stage(feats5, cls5, reg5, metas5)          # warm-up (allocations, tensor maps, cuDNN plans)
+    gather_detections([out5[0][0]], [out5[0][1]], [rank])
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    out5 = stage(feats5, cls5, reg5, metas5)
+    e1.record()
+    allv = gather_detections([out5[0][0]], [out5[0][1]], [rank])
+    e2.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e3, e1.elapsed_time(e2) * 1e3], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = sorted(allv.keys()) == list(range(world)) and torch.equal(allv[rank][0].to(dev), out5[0][0]) and \
+        torch.equal(allv[rank][1].to(dev), out5[0][1])
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res = {"workload": "C4 -> C5: RoI stage of the reference config, one 512x512x160 volume per rank, then the "
+                       "detections all-gathered (NCCL)",
+           "volumes": world, "roi_stage_us_max_over_ranks": float(t[0].item()),
+           "gather_detections_us_max_over_ranks": float(t[1].item()),
+           "volumes_per_sec": world / (float(t[0].item() + t[1].item()) * 1e-6),
+           "detections_per_volume": [int(allv[v][0].shape[0]) for v in sorted(allv.keys())],
+           "gather_reassembled_on_every_rank": bool(flag.item())}
+    del stage, feats5, cls5, reg5, out5
+    torch.cuda.empty_cache()
+    return res
 
 
 def cpu_baseline():
@@ -411,11 +485,7 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
 
     ex = {}
     # C2 with the reference's NCDHW-contiguous input: includes the on-device layout conversion (cache disabled)
-    saved = roi3d_b200._util._CACHE_SIZE
-    roi3d_b200._util._CACHE_SIZE = 0
-    roi3d_b200._util.clear_layout_cache()
-    us = med_us(lambda: layer(feats, rois), iters=5)
-    roi3d_b200._util._CACHE_SIZE = saved
+    us = med_us(lambda: layer(feats, rois), iters=5)   # no reuse scope open: converted on every call
     ex["c2_fwd_ncdhw_input_us"] = us
     ex["c2_fwd_ncdhw_input_rois_per_sec"] = C2["K"] / (us * 1e-6)
     # C2 backward (grad of the pooled features w.r.t. the level), zero-fill of the 671 MB gradient included
@@ -460,6 +530,37 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     t0 = time.perf_counter()
     oracle.nms_cpu_2d(dn, 0.7)
     ex["c1_nms2000_cpu_reference_wrapper_2d_semantics_us"] = (time.perf_counter() - t0) * 1e6
+    # the reference's own natives built by oracle/build_ref.sh (oracle/_ref), timed beside: nms_cpu.cpp (the CPU path its
+    # wrapper takes for numpy input: 2-D NMS on columns 0-4) and the CUDA kernels it ships (BASELINE.md 3:
+    # "the kernel to beat"; nms_3d includes its blocking D2H + host sweep)
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import ref_nms_cpu
+        dt_ = torch.from_numpy(dn)
+        ref_nms_cpu.nms(dt_, 0.7)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ref_nms_cpu.nms(dt_, 0.7)
+        ex["c1_nms2000_ref_nms_cpu_cpp_us"] = (time.perf_counter() - t0) / 20 * 1e6
+    except Exception as e:
+        ex["ref_nms_cpu_error"] = repr(e)
+    try:
+        import ref_nms_cuda
+        import ref_roi_align_cuda
+        ex["ref_gpu_nms2000_us"] = med_us(lambda: ref_nms_cuda.nms_3d(dets, 0.7), iters=20, do_flush=False)
+        ref_out = torch.zeros((C2["K"], C2["C"], C2["PD"], C2["P"], C2["P"]), device=dev)
+        ex["ref_gpu_c2_fwd_us"] = med_us(lambda: ref_roi_align_cuda.forward3d(
+            feats, rois, C2["PD"], C2["P"], C2["P"], C2["scale"], C2["scale_d"], C2["sample_num"], ref_out), iters=5)
+        ex["ref_gpu_c2_fwd_max_abs_diff_vs_ours"] = float((layer(feats_cl, rois) - ref_out).abs().max())
+        gref = torch.randn_like(ref_out)
+        ref_gin = torch.zeros_like(feats)
+        ex["ref_gpu_c2_bwd_us_no_zero_fill"] = med_us(lambda: ref_roi_align_cuda.backward3d(
+            gref, rois, C2["PD"], C2["P"], C2["P"], C2["scale"], C2["scale_d"], C2["sample_num"], ref_gin), iters=3, warm=1)
+        del ref_out, gref, ref_gin
+    except Exception as e:
+        ex["ref_gpu_error"] = repr(e)
     ex["c1_kept"] = int(len(keep_h))
     ex["c1_kept_matches_cpu_3d_set"] = bool(np.array_equal(np.sort(keep_np), np.sort(np.asarray(keep_h))))
     del d40
