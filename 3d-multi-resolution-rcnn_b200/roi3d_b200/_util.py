@@ -1,7 +1,30 @@
 """Small torch-side helpers shared by the host mirror: stream handle, layout handling, scratch buffers."""
+import os
+
 import torch
 
 from . import _lib
+
+
+# --- NVTX ranges (the reference has no tracing; the build adds named ranges around the hot-path calls)
+NVTX = os.environ.get("ROI3D_NVTX", "0") not in ("", "0")
+
+
+class nvtx_range(object):
+    """`with nvtx_range("roi3d.nms"):` -- a named range in Nsight timelines when ROI3D_NVTX=1, free otherwise."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def stream_ptr():

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ..._util import check_cuda_f32, stream_ptr, workspace
+from ..._util import check_cuda_f32, nvtx_range, stream_ptr, workspace
 from ...core.anchor import AnchorGenerator3D
 from ...ops.nms.nms_wrapper import nms3d_batched
 
@@ -170,7 +170,8 @@ class RPNProposal3D(object):
         if img_meta_3 is not None:
             img_metas = img_meta_3
         if not self.cuda_graph:
-            final, n_valid, kk = self._enqueue(cls_scores, bbox_preds, img_metas, cfg)
+            with nvtx_range("roi3d.rpn.get_bboxes"):
+                final, n_valid, kk = self._enqueue(cls_scores, bbox_preds, img_metas, cfg)
             clone = False
         else:
             masks_now = [m for lst in (self.pos_indices, self.pos_indices_test) if lst is not None for m in lst]

@@ -17,7 +17,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from ... import _lib, ops
-from ..._util import (channels_last_to_contiguous, check_cuda_f32, is_channels_last_3d, stream_ptr,
+from ..._util import (channels_last_to_contiguous, check_cuda_f32, is_channels_last_3d, nvtx_range, stream_ptr,
                       to_channels_last_3d)
 from ...ops.roi_align.functions.roi_align_3d import _BUG_COMPAT, _out_dims
 
@@ -55,7 +55,7 @@ class _MultiLevelRoIAlign3D(Function):
         ctx.save_for_backward(rois)
         if K > 0:
             arr = _level_array(feats_cl, scales, scales_d)
-            with torch.cuda.device(rois.device):
+            with torch.cuda.device(rois.device), nvtx_range("roi3d.extract.forward"):
                 _lib.check(_lib.lib.roi3d_extract_forward(arr, len(feats), B, C, rois.data_ptr(), K, out_d, out_h,
                                                           out_w, int(sample_num), float(finest_scale),
                                                           out.data_ptr(), None, stream_ptr()))

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ..._util import check_cuda_f32, stream_ptr, workspace
+from ..._util import check_cuda_f32, nvtx_range, stream_ptr, workspace
 
 
 def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=None):
@@ -42,7 +42,7 @@ def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=No
         seg_counts = seg_counts.contiguous()
     nbytes = _lib.lib.roi3d_nms3d_workspace_bytes(nseg, n_max)
     _buf, ws = workspace(dev, nbytes)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), nvtx_range("roi3d.nms3d_batched"):
         _lib.check(_lib.lib.roi3d_nms3d_batched_presorted(
             dets.data_ptr(), None if seg_counts is None else seg_counts.data_ptr(),
             None if presorted is None else presorted.data_ptr(), nseg, n_max, float(iou_thr),

@@ -8,7 +8,7 @@ import torch
 from torch.autograd import Function
 
 from .... import _lib
-from ...._util import (channels_last_to_contiguous, check_cuda_f32, is_channels_last_3d, stream_ptr,
+from ...._util import (channels_last_to_contiguous, check_cuda_f32, is_channels_last_3d, nvtx_range, stream_ptr,
                       to_channels_last_3d)
 
 
@@ -44,7 +44,7 @@ class RoIAlignFunction3D(Function):
         K = rois.size(0)
         output = features.new_empty((K, C, out_d, out_h, out_w))
         if K > 0:
-            with torch.cuda.device(features.device):
+            with torch.cuda.device(features.device), nvtx_range("roi3d.roi_align3d.forward"):
                 _lib.check(_lib.lib.roi3d_roi_align3d_forward(
                     feats_cl.data_ptr(), _lib.NDHWC, B, C, D, H, W, rois.data_ptr(), K, out_d, out_h, out_w,
                     ctx.spatial_scale, ctx.spatial_scale_depth, ctx.sample_num, output.data_ptr(), stream_ptr()))
@@ -61,7 +61,7 @@ class RoIAlignFunction3D(Function):
             K, _, out_d, out_h, out_w = grad_output.shape
             grad_cl = torch.empty((B, C, D, H, W), dtype=grad_output.dtype, device=grad_output.device,
                                   memory_format=torch.channels_last_3d)
-            with torch.cuda.device(grad_output.device):
+            with torch.cuda.device(grad_output.device), nvtx_range("roi3d.roi_align3d.backward"):
                 _lib.check(_lib.lib.roi3d_roi_align3d_backward(
                     grad_output.data_ptr(), rois.data_ptr(), K, out_d, out_h, out_w, ctx.spatial_scale,
                     ctx.spatial_scale_depth, ctx.sample_num, grad_cl.data_ptr(), _lib.NDHWC, B, C, D, H, W,

@@ -211,6 +211,20 @@ int roi3d_bbox2delta3d(const float *proposals_dev, int stride_p, const float *gt
 int roi3d_mask_paste(const float *mask_logits_dev, int n, int Dm, int Hm, int Wm, const int32_t *boxes_dev,
                      const int64_t *offsets_dev, float thr, uint8_t *out_dev, void *stream);
 
+/* Mask targets (training half).
+ * Replaces: mask_target_single, mmdet/core/mask/mask_target.py:17-50 (per positive proposal on the host: crop of the
+ *   assigned ground-truth mask to the proposal's int32 box, `255 * skimage.transform.resize(crop, (Md, Mh, Mw))`,
+ *   `.astype(uint8)`, non-zero -> 1).  gt_masks_dev uint8 [G, D, H, W]; boxes_host int32 [n, 6] = (x1,y1,x2,y2,z1,z2)
+ *   after the reference's `.astype(np.int32)`; gt_inds_host int64 [n]; out_dev fp32 [n, Md, Mh, Mw] of 0 / 1.
+ *   The crop is clipped to the volume like a numpy slice; an empty crop gives an all-zero target (the reference's
+ *   resize raises on it).  The resize restates scikit-image 0.18.0 `resize` on a uint8 input (img_as_float, gaussian
+ *   anti-aliasing, order-1 map_coordinates, mode reflect, clip) in float64.
+ *   crop_dhw_host for the workspace query: int32 [n, 3] = clipped (d, h, w) of every crop. */
+size_t roi3d_mask_target_workspace_bytes(const int32_t *crop_dhw_host, int n);
+int roi3d_mask_target(const uint8_t *gt_masks_dev, int G, int D, int H, int W, const int32_t *boxes_host,
+                      const int64_t *gt_inds_host, int n, int Md, int Mh, int Mw, float *out_dev, void *workspace_dev,
+                      size_t workspace_bytes, void *stream);
+
 /* Experiment knob (not part of the reference surface): key 0 = forward kernel variant (0 = auto, 1 = one channel per
  * lane, 50 = per-warp ring kernel where the streamed kernel would apply, 99 = literal reference-order path); key 1 =
  * backward kernel variant (0 = auto, 1, 3 = per-warp tables, 99 = literal); key 2 = sub-items one ring-kernel warp

@@ -491,6 +491,54 @@ def get_seg_masks_compact(mask_logits, det_bboxes, det_labels, mask_thr_binary, 
     return np.asarray(boxes, dtype=np.int32).reshape(-1, 6), masks, labels
 
 
+def resize_nd_f64(image, output_shape):
+    """skimage.transform.resize on a uint8 image as mask_target_single uses it (mmdet/core/mask/mask_target.py:42):
+    img_as_float maps uint8 v to float64 v * (1 / 255); the rest is resize_nd in float64."""
+    import scipy.ndimage as ndi
+    image = np.multiply(np.asarray(image, dtype=np.uint8), 1.0 / 255, dtype=np.float64)
+    factors = np.divide(np.asarray(image.shape, dtype=np.float64), np.asarray(output_shape, dtype=np.float64))
+    sigma = np.maximum(0, (factors - 1) / 2)
+    img = ndi.gaussian_filter(image, sigma, cval=0, mode='mirror')
+    coords = [factors[i] * (np.arange(d) + 0.5) - 0.5 for i, d in enumerate(output_shape)]
+    cmap = np.array(np.meshgrid(*coords, sparse=False, indexing='ij'))
+    out = ndi.map_coordinates(img, cmap, order=1, mode='mirror', cval=0)
+    return np.clip(out, img.min(), img.max())
+
+
+def mask_target_single(pos_proposals, pos_assigned_gt_inds, gt_masks, mask_size, mask_size_depth):
+    """mask_target_single (mmdet/core/mask/mask_target.py:17-50), 3D branch; gt_masks uint8 [G, D, H, W]."""
+    props = np.asarray(pos_proposals, dtype=np.float32)
+    out = []
+    for i in range(props.shape[0]):
+        x1, y1, x2, y2, z1, z2 = props[i].astype(np.int32)
+        w, h, d = max(x2 - x1 + 1, 1), max(y2 - y1 + 1, 1), max(z2 - z1 + 1, 1)
+        crop = np.asarray(gt_masks[int(pos_assigned_gt_inds[i])])[z1:z1 + d, y1:y1 + h, x1:x1 + w]
+        t = 255 * resize_nd_f64(crop, (mask_size_depth, mask_size, mask_size))
+        t = t.astype(np.uint8)
+        t[t > 0] = 1
+        out.append(t)
+    if not out:
+        return np.zeros((0, mask_size, mask_size), np.float32)
+    return np.stack(out).astype(np.float32)
+
+
+def random_sample(gt_inds, num, pos_fraction, neg_pos_ub=-1):
+    """RandomSampler.sample's index selection (mmdet/core/bbox/samplers/base_sampler.py:73-101 with
+    random_sampler.py:19-58) on a numpy gt_inds vector (after add_gt_); consumes np.random like the reference."""
+    gt_inds = np.asarray(gt_inds)
+
+    def pick(cands, n):
+        if len(cands) <= n:
+            return cands
+        return cands[np.random.randint(low=0, high=len(cands), size=n)]
+    pos = np.unique(pick(np.nonzero(gt_inds > 0)[0], int(num * pos_fraction)))
+    n_neg = num - len(pos)
+    if neg_pos_ub >= 0:
+        n_neg = min(n_neg, int(neg_pos_ub * max(1, len(pos))))
+    neg = np.unique(pick(np.nonzero(gt_inds == 0)[0], n_neg))
+    return pos, neg
+
+
 def nms_cpu_2d(dets, thr):
     """nms_cpu_kernel (mmdet/ops/nms/src/nms_cpu.cpp:5-59): 2-D NMS over columns 0-3 ranked by column 4,
     suppressing ovr >= thr -- what the reference's CPU wrapper runs even on 7-column input."""

@@ -1156,3 +1156,72 @@ def test_nms_presorted_segments_skip_the_ranking(oracle, dev):
         m = int(n0[seg])
         assert torch.equal(k0[seg, :m], k1[seg, :m]) and torch.equal(s0[seg, :m], s1[seg, :m])
     assert np.array_equal(k1[0, :int(n1[0])].cpu().numpy(), oracle.nms3d(a, 0.5))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY 8f N2 / N4 (training halves): RandomSampler and mask targets
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [dict(num=512, pos_fraction=0.25, neg_pos_ub=-1, add_gt_as_proposals=True),
+                                 dict(num=64, pos_fraction=0.5, neg_pos_ub=3, add_gt_as_proposals=False)])
+def test_random_sampler_matches_reference_restatement(oracle, dev, cfg):
+    """Same seed -> the same boxes as base_sampler.py:31-103 / random_sampler.py:19-58 restated in numpy."""
+    from roi3d_b200.core.bbox import MaxIoUAssigner, RandomSampler
+    props, gts = _assign_case(3000, 9, 77)
+    labels = np.arange(1, 10, dtype=np.int64)
+    pt, gt_t, lt = torch.from_numpy(props).to(dev), torch.from_numpy(gts).to(dev), torch.from_numpy(labels).to(dev)
+    res = MaxIoUAssigner(0.5, 0.5, 0.5, True).assign(pt, gt_t, None, lt)
+    gi = res.gt_inds.cpu().numpy()
+    if cfg["add_gt_as_proposals"]:
+        gi = np.concatenate([np.arange(1, 10), gi])
+    np.random.seed(123)
+    want_pos, want_neg = oracle.random_sample(gi, cfg["num"], cfg["pos_fraction"], cfg["neg_pos_ub"])
+    np.random.seed(123)
+    sr = RandomSampler(**cfg).sample(res, pt, gt_t, lt)
+    assert np.array_equal(sr.pos_inds.cpu().numpy(), want_pos) and np.array_equal(sr.neg_inds.cpu().numpy(), want_neg)
+    allb = np.concatenate([gts, props[:, :6]]) if cfg["add_gt_as_proposals"] else props[:, :6]
+    assert np.array_equal(sr.pos_bboxes.cpu().numpy(), allb[want_pos])
+    assert np.array_equal(sr.bboxes.cpu().numpy(), np.concatenate([allb[want_pos], allb[want_neg]]))
+    assert np.array_equal(sr.pos_assigned_gt_inds.cpu().numpy(), gi[want_pos] - 1)
+    assert np.array_equal(sr.pos_gt_bboxes.cpu().numpy(), gts[gi[want_pos] - 1])
+    if cfg["add_gt_as_proposals"]:
+        assert sr.pos_is_gt[:9].cpu().numpy().sum() >= 1 and sr.num_gts == 9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("values", ["0/255", "0/1"])
+def test_mask_target_matches_resize_restatement(oracle, dev, values):
+    """mask_target_single on the device vs the restated host algorithm (uint8 crop -> img_as_float -> float64 resize
+    -> *255 -> uint8 -> nonzero): crops that are enlarged, shrunk (anti-aliasing), clipped by the volume border and a
+    one-voxel box.  Parity unpinned by the reference (skimage is not installed; same restatement over scipy)."""
+    from roi3d_b200.core.mask import mask_target, mask_target_single
+    rng = np.random.default_rng(5)
+    G, D, H, W = 3, 40, 96, 96
+    gt = np.zeros((G, D, H, W), np.uint8)
+    zz, yy, xx = np.mgrid[:D, :H, :W]
+    for g in range(G):   # blobs
+        c = rng.uniform([8, 20, 20], [32, 76, 76])
+        r = rng.uniform([4, 8, 8], [12, 30, 30])
+        gt[g] = (((zz - c[0]) / r[0]) ** 2 + ((yy - c[1]) / r[1]) ** 2 + ((xx - c[2]) / r[2]) ** 2 <= 1)
+    if values == "0/255":
+        gt *= 255
+    n = 24
+    lo = np.stack([rng.uniform(0, 80, n), rng.uniform(0, 80, n), rng.uniform(0, 30, n)], 1)
+    sz = np.stack([rng.uniform(1, 70, n), rng.uniform(1, 70, n), rng.uniform(1, 30, n)], 1)
+    props = np.stack([lo[:, 0], lo[:, 1], lo[:, 0] + sz[:, 0], lo[:, 1] + sz[:, 1], lo[:, 2], lo[:, 2] + sz[:, 2]], 1)
+    props[0] = [10, 12, 10, 12, 5, 5]                 # one voxel
+    props[1] = [60, 60, 140, 150, 30, 60]             # clipped by the volume
+    props = props.astype(np.float32)
+    inds = rng.integers(0, G, n)
+    cfg = dict(mask_size=28, mask_size_depth=20)
+    got = mask_target_single(torch.from_numpy(props).to(dev), torch.from_numpy(inds).to(dev), torch.from_numpy(gt), cfg)
+    want = oracle.mask_target_single(props, inds, gt, 28, 20)
+    assert got.shape == (n, 20, 28, 28) and got.dtype == torch.float32
+    diff = int((got.cpu().numpy() != want).sum())
+    assert diff == 0, "%d of %d target voxels differ" % (diff, want.size)
+    assert 0 < want.mean() < 1
+    both = mask_target([torch.from_numpy(props[:5]).to(dev), torch.from_numpy(props[5:9]).to(dev)],
+                       [torch.from_numpy(inds[:5]).to(dev), torch.from_numpy(inds[5:9]).to(dev)],
+                       [torch.from_numpy(gt).to(dev), torch.from_numpy(gt).to(dev)], cfg)
+    assert torch.equal(both, got[:9])
+    assert mask_target_single(torch.zeros((0, 6), device=dev), torch.zeros(0, dtype=torch.long, device=dev), gt, cfg).shape == (0, 28, 28)
