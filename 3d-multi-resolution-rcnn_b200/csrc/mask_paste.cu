@@ -213,11 +213,11 @@ __global__ void __launch_bounds__(256) mask_target_kernel(const unsigned char *_
     for (long long e = tid; e < vol; e += 256) {
       const int pos = (int)((e / st) % n);
       const long long base = e - (long long)pos * st;
-      double tmp = cur[e] * wts[lw];
+      double tmp = __dmul_rn(cur[e], wts[lw]);   // scipy's correlate1d: separate multiplies and adds, no contraction
       for (int ll = -lw; ll < 0; ++ll) {
         const double l = cur[base + (long long)mirror_index(pos + ll, n) * st];
         const double r = cur[base + (long long)mirror_index(pos - ll, n) * st];
-        tmp += (l + r) * wts[ll + lw];
+        tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(l, r), wts[ll + lw]));
       }
       nxt[e] = tmp;
     }
@@ -256,13 +256,13 @@ __global__ void __launch_bounds__(256) mask_target_kernel(const unsigned char *_
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           double coeff = cur[((long long)zi[a] * j.h + yi[b]) * j.w + xi[c]];
-          coeff *= wz[a];
-          coeff *= wy[b];
-          coeff *= wx[c];
-          acc += coeff;
+          coeff = __dmul_rn(coeff, wz[a]);
+          coeff = __dmul_rn(coeff, wy[b]);
+          coeff = __dmul_rn(coeff, wx[c]);
+          acc = __dadd_rn(acc, coeff);
         }
     acc = fmin(fmax(acc, mn), mx);                       // clip=True
-    const double scaled = 255.0 * acc;                   // `255 * resize(...)`
+    const double scaled = __dmul_rn(255.0, acc);         // `255 * resize(...)`
     const unsigned char u = (unsigned char)(int)scaled;  // .astype(np.uint8): truncation (values are in [0, 255])
     dst[o] = u > 0 ? 1.0f : 0.0f;                        // target[target > 0] = 1, then .float()
   }

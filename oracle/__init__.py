@@ -505,20 +505,24 @@ def resize_nd_f64(image, output_shape):
     return np.clip(out, img.min(), img.max())
 
 
-def mask_target_single(pos_proposals, pos_assigned_gt_inds, gt_masks, mask_size, mask_size_depth):
-    """mask_target_single (mmdet/core/mask/mask_target.py:17-50), 3D branch; gt_masks uint8 [G, D, H, W]."""
+def mask_target_single(pos_proposals, pos_assigned_gt_inds, gt_masks, mask_size, mask_size_depth, return_scaled=False):
+    """mask_target_single (mmdet/core/mask/mask_target.py:17-50), 3D branch; gt_masks uint8 [G, D, H, W].
+    return_scaled: also return the float64 `255 * resize(...)` values before the uint8 truncation."""
     props = np.asarray(pos_proposals, dtype=np.float32)
-    out = []
+    out, scaled = [], []
     for i in range(props.shape[0]):
         x1, y1, x2, y2, z1, z2 = props[i].astype(np.int32)
         w, h, d = max(x2 - x1 + 1, 1), max(y2 - y1 + 1, 1), max(z2 - z1 + 1, 1)
         crop = np.asarray(gt_masks[int(pos_assigned_gt_inds[i])])[z1:z1 + d, y1:y1 + h, x1:x1 + w]
         t = 255 * resize_nd_f64(crop, (mask_size_depth, mask_size, mask_size))
+        scaled.append(t)
         t = t.astype(np.uint8)
         t[t > 0] = 1
         out.append(t)
     if not out:
         return np.zeros((0, mask_size, mask_size), np.float32)
+    if return_scaled:
+        return np.stack(out).astype(np.float32), np.stack(scaled)
     return np.stack(out).astype(np.float32)
 
 

@@ -1215,10 +1215,17 @@ def test_mask_target_matches_resize_restatement(oracle, dev, values):
     inds = rng.integers(0, G, n)
     cfg = dict(mask_size=28, mask_size_depth=20)
     got = mask_target_single(torch.from_numpy(props).to(dev), torch.from_numpy(inds).to(dev), torch.from_numpy(gt), cfg)
-    want = oracle.mask_target_single(props, inds, gt, 28, 20)
+    want, scaled = oracle.mask_target_single(props, inds, gt, 28, 20, return_scaled=True)
     assert got.shape == (n, 20, 28, 28) and got.dtype == torch.float32
-    diff = int((got.cpu().numpy() != want).sum())
-    assert diff == 0, "%d of %d target voxels differ" % (diff, want.size)
+    differ = got.cpu().numpy() != want
+    if values == "0/255":
+        assert int(differ.sum()) == 0, "%d of %d target voxels differ" % (int(differ.sum()), want.size)
+    else:
+        # {0,1} masks: the reference computes 255 * (sum_i w_i * (1/255)) and truncates to uint8, so a voxel inside the
+        # mask is 1 or 0 depending on the LAST BIT of that sum (numpy's exp and pairwise sums vs the device's).  The
+        # two restatements may only disagree exactly on that knife edge.
+        assert float(differ.mean()) < 5e-3
+        assert np.all(np.abs(scaled[differ] - 1.0) < 1e-9)
     assert 0 < want.mean() < 1
     both = mask_target([torch.from_numpy(props[:5]).to(dev), torch.from_numpy(props[5:9]).to(dev)],
                        [torch.from_numpy(inds[:5]).to(dev), torch.from_numpy(inds[5:9]).to(dev)],
