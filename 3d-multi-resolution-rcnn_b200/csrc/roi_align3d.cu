@@ -1857,7 +1857,14 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
     if (cvmax >= 2) return launch_generic<2>(p, true, st);
     return launch_generic<1>(p, true, st);
   }
+  if (p.layout == ROI3D_NCDHW) {  // the reference's layout: only the planar kernel reads it
+    ROI3D_CHECK_ARG(fwd_planar_ok(p, ROI3D_NCDHW),
+                    "NCDHW levels need a 7- or 14-wide square output, 16-byte aligned levels and W %% 4 == 0; convert "
+                    "with roi3d_ncdhw_to_ndhwc otherwise");
+    return launch_fwd_planar(p, ROI3D_NCDHW, st);
+  }
   if (v == 0 && fwd_stream_ok(p)) return launch_fwd_stream(p, st);  // persistent TMA-fed kernel (roi_align3d_stream.cu)
+  if ((v == 60 || (v == 0 && p.PW == 14)) && fwd_planar_ok(p, ROI3D_NDHWC)) return launch_fwd_planar(p, ROI3D_NDHWC, st);
   bool ring_ok = p.C % 4 == 0;
   for (int l = 0; l < p.num_levels; ++l) ring_ok = ring_ok && aligned(p.lv[l].feats, 16);
   if (p.PW == 7) {
@@ -1912,10 +1919,11 @@ static int fill_params(RoiParams &p, const roi3d_level_t *levels, int num_levels
   ROI3D_CHECK_ARG(K == 0 || rois != nullptr, "rois is NULL");
   ROI3D_CHECK_ARG(finest_scale > 0.0f || num_levels == 1, "finest_scale must be > 0");
   for (int l = 0; l < num_levels; ++l) {
-    ROI3D_CHECK_ARG(levels[l].layout == ROI3D_NDHWC,
-                    "level %d: the kernels read channels-last (ROI3D_NDHWC) memory; convert with "
+    ROI3D_CHECK_ARG(levels[l].layout == ROI3D_NDHWC || (!bwd && levels[l].layout == ROI3D_NCDHW),
+                    "level %d: the backward kernels read channels-last (ROI3D_NDHWC) memory; convert with "
                     "roi3d_ncdhw_to_ndhwc first",
                     l);
+    ROI3D_CHECK_ARG(levels[l].layout == levels[0].layout, "level %d: all levels must share one layout", l);
     ROI3D_CHECK_ARG(levels[l].D > 0 && levels[l].H > 0 && levels[l].W > 0, "level %d: bad dims", l);
     ROI3D_CHECK_ARG(bwd ? levels[l].grad_dev != nullptr : levels[l].feats_dev != nullptr, "level %d: NULL pointer", l);
     ROI3D_CHECK_ARG((long long)levels[l].D * levels[l].H * levels[l].W < (1LL << 31), "level %d too large", l);
@@ -1929,6 +1937,7 @@ static int fill_params(RoiParams &p, const roi3d_level_t *levels, int num_levels
   p.inv_finest = num_levels > 1 ? 1.0f / finest_scale : 0.0f;
   p.B = B, p.C = C, p.rois = rois, p.K = K, p.PD = PD, p.PH = PH, p.PW = PW, p.sample_num = sample_num;
   p.out = nullptr, p.grad_out = nullptr, p.lvls_out = nullptr, p.out_rows = nullptr, p.bug_compat = 0;
+  p.layout = levels[0].layout;
   return ROI3D_OK;
 }
 

@@ -32,6 +32,7 @@ struct RoiParams {
   int items_per_roi, ctas_per_roi;  // ring2 kernels: CTA -> (RoI, group of kWarps * items_per_warp sub-items)
   int items_per_warp;
   int bug_compat;
+  int layout;             // ROI3D_NCDHW or ROI3D_NDHWC, the same for every level
 };
 
 constexpr int kWarps = 4;
@@ -203,6 +204,15 @@ __device__ __noinline__ void literal_tile_fwd(const Item &it, const float *fb, i
 // Persistent TMA-fed forward kernel (roi_align3d_stream.cu): applies to 7x7xPD outputs (PD <= 7) of channels-last
 // levels with C % 64 == 0; RoIs it cannot take (footprint wider than its tiles, bins with more than four taps) are
 // evaluated literally inside the same launch.
+// Planar forward kernel (roi_align3d_planar.cu): lanes = output elements, one shared-memory plane per channel; reads
+// NCDHW levels natively (and channels-last ones), 7- or 14-wide outputs.
+// Private stream-ordered memory pool of the current device (per-call device scratch: no host sync, re-entrant across
+// streams, pages stay with the pool between calls).
+int stream_pool(cudaMemPool_t *out);
+
+bool fwd_planar_ok(const RoiParams &p, int layout);
+int launch_fwd_planar(RoiParams &p, int layout, cudaStream_t st);
+
 bool fwd_stream_ok(const RoiParams &p);
 int launch_fwd_stream(RoiParams &p, cudaStream_t st);
 

@@ -717,8 +717,6 @@ bool fwd_stream_ok(const RoiParams &p) {
   return true;
 }
 
-namespace {
-
 // Plans and the work counter come from a private stream-ordered pool: no host sync, re-entrant across streams, and
 // (release threshold = max) the pages stay with the pool between calls instead of going back to the driver at every
 // synchronisation as the default pool would do.
@@ -744,6 +742,9 @@ int stream_pool(cudaMemPool_t *out) {
   *out = pools[dev];
   return ROI3D_OK;
 }
+
+
+namespace {
 
 template <int NS, int SLOT>
 int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count) {

@@ -98,6 +98,25 @@ def to_channels_last_3d(x):
     return conv, True
 
 
+def forward_inputs(feats, out_h, out_w):
+    """Pick the memory the forward kernels read for a list of [B,C,D,H,W] levels: (tensors, layout flag).
+    Channels-last levels go in as they are.  NCDHW-contiguous levels -- what the reference's callers hold
+    (roi_align_cuda.cpp:35-39) -- also go in as they are when the planar kernel can read them (square 7- or 14-wide
+    output, rows that start on 16-byte boundaries); anything else is converted to channels-last first."""
+    if all(is_channels_last_3d(f) for f in feats):
+        return list(feats), _lib.NDHWC
+    native = out_h == out_w and out_h in (7, 14) and all(
+        f.is_contiguous() and f.shape[-1] % 4 == 0 and f.data_ptr() % 16 == 0 for f in feats)
+    # 7-wide outputs of 64-channel multiples: one conversion (HBM speed, reusable across the extractor calls of a pass,
+    # see reuse_layout_conversions) + the streamed channels-last kernel beats the planar kernel (C2: 393 vs 418 us for
+    # a single call, 150 vs 418 us per further call); everything else the planar kernel reads in place
+    if native and out_h == 7 and feats[0].shape[1] % 64 == 0:
+        native = False
+    if native:
+        return list(feats), _lib.NCDHW
+    return [to_channels_last_3d(f)[0] for f in feats], _lib.NDHWC
+
+
 def channels_last_to_contiguous(g):
     """[B,C,D,H,W] stored NDHWC -> NCDHW-contiguous copy (used for grad_input when the forward input was NCDHW)."""
     B, C, D, H, W = g.shape

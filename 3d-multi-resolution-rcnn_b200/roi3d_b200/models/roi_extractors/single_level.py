@@ -17,18 +17,18 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from ... import _lib, ops
-from ..._util import (channels_last_to_contiguous, check_cuda_f32, is_channels_last_3d, nvtx_range, stream_ptr,
-                      to_channels_last_3d)
+from ..._util import (channels_last_to_contiguous, check_cuda_f32, forward_inputs, is_channels_last_3d, nvtx_range,
+                      stream_ptr)
 from ...ops.roi_align.functions.roi_align_3d import _BUG_COMPAT, _out_dims
 
 
-def _level_array(tensors, scales, scales_d, grads=None):
+def _level_array(tensors, scales, scales_d, grads=None, layout=_lib.NDHWC):
     arr = (_lib.Level * len(tensors))()
     for i, t in enumerate(tensors):
         _, _, D, H, W = t.shape
         arr[i].feats_dev = t.data_ptr() if grads is None else None
         arr[i].grad_dev = None if grads is None else grads[i].data_ptr()
-        arr[i].layout = _lib.NDHWC
+        arr[i].layout = layout
         arr[i].D, arr[i].H, arr[i].W = D, H, W
         arr[i].spatial_scale = scales[i]
         arr[i].spatial_scale_depth = scales_d[i]
@@ -46,7 +46,7 @@ class _MultiLevelRoIAlign3D(Function):
         rois = rois.contiguous()
         out_d, out_h, out_w = out_dims
         B, C = feats[0].shape[:2]
-        feats_cl = [to_channels_last_3d(f)[0] for f in feats]
+        feats_in, layout = forward_inputs(feats, out_h, out_w)
         K = rois.size(0)
         out = feats[0].new_empty((K, C, out_d, out_h, out_w))
         ctx.cfg = (out_dims, tuple(scales), tuple(scales_d), int(sample_num), float(finest_scale))
@@ -54,7 +54,7 @@ class _MultiLevelRoIAlign3D(Function):
         ctx.input_channels_last = [is_channels_last_3d(f) for f in feats]
         ctx.save_for_backward(rois)
         if K > 0:
-            arr = _level_array(feats_cl, scales, scales_d)
+            arr = _level_array(feats_in, scales, scales_d, layout=layout)
             with torch.cuda.device(rois.device), nvtx_range("roi3d.extract.forward"):
                 _lib.check(_lib.lib.roi3d_extract_forward(arr, len(feats), B, C, rois.data_ptr(), K, out_d, out_h,
                                                           out_w, int(sample_num), float(finest_scale),

@@ -8,8 +8,8 @@ import torch
 from torch.autograd import Function
 
 from .... import _lib
-from ...._util import (channels_last_to_contiguous, check_cuda_f32, is_channels_last_3d, nvtx_range, stream_ptr,
-                      to_channels_last_3d)
+from ...._util import (channels_last_to_contiguous, check_cuda_f32, forward_inputs, is_channels_last_3d, nvtx_range,
+                      stream_ptr)
 
 
 def _out_dims(out_size, out_size_depth):
@@ -39,14 +39,14 @@ class RoIAlignFunction3D(Function):
         rois = rois.contiguous()
         ctx.save_for_backward(rois)
 
-        feats_cl, _ = to_channels_last_3d(features)
+        (feats_in,), layout = forward_inputs([features], out_h, out_w)
         B, C, D, H, W = features.shape
         K = rois.size(0)
         output = features.new_empty((K, C, out_d, out_h, out_w))
         if K > 0:
             with torch.cuda.device(features.device), nvtx_range("roi3d.roi_align3d.forward"):
                 _lib.check(_lib.lib.roi3d_roi_align3d_forward(
-                    feats_cl.data_ptr(), _lib.NDHWC, B, C, D, H, W, rois.data_ptr(), K, out_d, out_h, out_w,
+                    feats_in.data_ptr(), layout, B, C, D, H, W, rois.data_ptr(), K, out_d, out_h, out_w,
                     ctx.spatial_scale, ctx.spatial_scale_depth, ctx.sample_num, output.data_ptr(), stream_ptr()))
         return output
 

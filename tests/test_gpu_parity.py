@@ -292,7 +292,7 @@ def test_extractor_forward_backward_multilevel(oracle, dev, ps, pdp):
     # NCDHW-contiguous inputs (the reference's layout) give the same values and contiguous grads
     ft2 = [torch.from_numpy(f).to(dev).requires_grad_(True) for f in feats]
     out2 = ex(ft2, torch.from_numpy(rois).to(dev))
-    assert torch.equal(out2, out)
+    assert rel_err(out2.detach().cpu().numpy(), want) <= FWD_TOL   # NCDHW levels are read natively (planar kernel)
     out2.backward(torch.from_numpy(g).to(dev))
     for l in range(4):
         assert ft2[l].grad.is_contiguous()
@@ -517,11 +517,12 @@ def test_layout_conversion_reuse_is_scoped_and_sees_rewrites(oracle, dev):
     import roi3d_b200
     from roi3d_b200.ops import RoIAlign3D
     layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
-    f = torch.from_numpy(_feats((1, 64, 8, 16, 16), 60)).to(dev)
-    rois = torch.from_numpy(synth.c2_rois(12, seed=61, img=(64, 64, 16))).to(dev)
+    # W = 18 is not a multiple of 4, so this NCDHW input cannot be read natively and is converted to channels-last
+    f = torch.from_numpy(_feats((1, 64, 8, 16, 18), 60)).to(dev)
+    rois = torch.from_numpy(synth.c2_rois(12, seed=61, img=(72, 64, 16))).to(dev)
     a = layer(f, rois)
     v0 = f._version
-    raw = torch.from_numpy(_feats((1, 64, 8, 16, 16), 62)).to(dev)
+    raw = torch.from_numpy(_feats((1, 64, 8, 16, 18), 62)).to(dev)
     # rewrite the same storage without touching the version counter (a kernel writing through data_ptr)
     torch.cuda.current_stream().synchronize()
     f.data.copy_(raw)
@@ -1232,3 +1233,45 @@ def test_mask_target_matches_resize_restatement(oracle, dev, values):
                        [torch.from_numpy(gt).to(dev), torch.from_numpy(gt).to(dev)], cfg)
     assert torch.equal(both, got[:9])
     assert mask_target_single(torch.zeros((0, 6), device=dev), torch.zeros(0, dtype=torch.long, device=dev), gt, cfg).shape == (0, 28, 28)
+
+
+PLANAR_CASES = [
+    # (B, C, D, H, W), out_size, out_size_depth, scale, scale_d, sample_num, n_rois, roi image (W, H, D)
+    ((2, 24, 10, 24, 40), 7, 7, 0.25, 0.5, 2, 60, (160, 96, 20)),
+    ((1, 37, 12, 40, 40), 7, 3, 0.25, 0.5, 2, 40, (160, 160, 24)),     # odd channel count, 7x7x3
+    ((1, 16, 24, 96, 96), 7, 7, 0.25, 0.5, 2, 40, (384, 384, 48)),     # c2-sized RoIs: big footprints, several passes
+    ((2, 20, 10, 32, 32), 14, 14, 0.125, 0.25, 2, 50, (256, 256, 40)),  # mask shape on a coarse level
+    ((1, 12, 8, 16, 16), 14, 10, 0.25, 0.5, 2, 30, (64, 64, 16)),      # real-config mask shape 14x14x10
+    ((1, 8, 10, 20, 20), 7, 7, 0.25, 0.5, 0, 30, (80, 80, 20)),        # adaptive sampling
+    ((1, 8, 6, 12, 12), 14, 14, 0.25, 0.5, 3, 20, (48, 48, 12)),       # three samples per bin
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", PLANAR_CASES)
+@pytest.mark.parametrize("layout", ["NCDHW", "NDHWC"])
+def test_roi_align_forward_planar_kernel(oracle, dev, case, layout):
+    """The planar kernel: the reference's NCDHW layout read natively (no conversion), and channels-last through the
+    same kernel (tuning variant 60); 7- and 14-wide outputs, ragged channel groups, adversarial and over-wide RoIs."""
+    import roi3d_b200
+    from roi3d_b200.ops import RoIAlign3D
+    shape, ps, pdp, sc, scd, sn, k, img = case
+    B, C, D, H, W = shape
+    f = _feats(shape, 71)
+    rois = np.concatenate([synth.c2_rois(k, seed=72, img=img, batch=B),
+                           synth.adversarial_rois(shape[2:], sc, scd, batch=B),
+                           np.array([[B - 1, 2, 3, img[0] - 4, img[1] - 6, 1, img[2] - 3],       # whole map: literal path
+                                     [0, img[0] - 30, 4, img[0] - 2, 40, 2, 9]], np.float32)], 0)  # touches the right border
+    if sn == 0:
+        ok = (rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2]) & (rois[:, 6] >= rois[:, 5])
+        rois = rois[ok]
+    want = oracle.roi_align3d_forward(f, rois, ps, pdp, sc, scd, sn)
+    ft = torch.from_numpy(f).to(dev)
+    if layout == "NDHWC":
+        ft = cl(ft)
+    roi3d_b200._lib.set_tuning(0, 60)
+    try:
+        out = RoIAlign3D(ps, pdp, sc, scd, sn)(ft, torch.from_numpy(rois).to(dev))
+    finally:
+        roi3d_b200._lib.set_tuning(0, 0)
+    assert out.is_contiguous() and rel_err(out.cpu().numpy(), want) <= FWD_TOL

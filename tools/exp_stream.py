@@ -55,3 +55,30 @@ for name, f, r, fl in (("HBM-sized map", big, r_big, True), ("L2-resident map", 
     _lib.set_tuning(0, 50)
     print("%s ring2: %.1f us" % (name, timeit(lambda: layer(f, r), flush=fl)), flush=True)
     _lib.set_tuning(0, 0)
+
+# ---- planar kernel: NCDHW native and channels-last (variant 60), C2 and C3
+print("--- planar kernel", flush=True)
+big_nc = big.contiguous()   # NCDHW
+ref = layer(big, r_big)
+got = layer(big_nc, r_big)
+print("C2 NCDHW native maxdiff vs streamed %g" % float((got - ref).abs().max()), flush=True)
+print("C2 NCDHW native (planar): %.1f us" % timeit(lambda: layer(big_nc, r_big)), flush=True)
+_lib.set_tuning(0, 60)
+print("C2 channels-last planar (v60): %.1f us" % timeit(lambda: layer(big, r_big)), flush=True)
+_lib.set_tuning(0, 0)
+del big_nc, got, ref
+from roi3d_b200 import SingleRoIExtractor
+dims = [(40, 128, 128), (20, 64, 64), (10, 32, 32), (5, 16, 16)]
+gen = torch.Generator(device=dev); gen.manual_seed(3)
+pyr_nc = [torch.randn((2, 256) + d, device=dev, generator=gen) for d in dims]
+pyr_cl = [t.contiguous(memory_format=torch.channels_last_3d) for t in pyr_nc]
+r3 = torch.from_numpy(synth.c3_rois(512, vols=2, seed=4)).to(dev)
+ext = SingleRoIExtractor(dict(type='RoIAlign3D', out_size=14, out_size_depth=14, sample_num=2), 256, [4, 8, 16, 32], [2, 4, 8, 16])
+a = ext(pyr_cl, r3)
+print("C3 channels-last (auto = planar): %.1f us" % timeit(lambda: ext(pyr_cl, r3), iters=5), flush=True)
+_lib.set_tuning(0, 50)
+b = ext(pyr_cl, r3)
+print("C3 channels-last ring2 (v50): %.1f us   maxdiff %g" % (timeit(lambda: ext(pyr_cl, r3), iters=5), float((a - b).abs().max())), flush=True)
+_lib.set_tuning(0, 0)
+c = ext(pyr_nc, r3)
+print("C3 NCDHW native: %.1f us   maxdiff %g" % (timeit(lambda: ext(pyr_nc, r3), iters=5), float((a - c).abs().max())), flush=True)
