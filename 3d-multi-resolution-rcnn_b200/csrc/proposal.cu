@@ -30,6 +30,7 @@ struct SegDesc {
   unsigned len;
   int A, D, H, W;  // A == 0: logical index == memory index
   const unsigned char *mask;  // optional, indexed by LOGICAL index: 0 = the element does not take part (rpn_head_3d.py:97-106)
+  long long koff;             // this segment's first entry in the key buffer (see topk_hist_kernel)
 };
 
 struct SegTable {
@@ -48,7 +49,8 @@ struct SegState {           // device, per segment
 __device__ __forceinline__ unsigned okey(float s) {
   s = s + 0.0f;
   unsigned u = __float_as_uint(s);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  const unsigned k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return k != 0u ? k : 1u;  // 0 is reserved for "masked out" in the key buffer (only -NaN with a full payload maps there)
 }
 
 __device__ __forceinline__ float okey_inv(unsigned k) {
@@ -139,12 +141,17 @@ constexpr int kBndCap = 4096;  // boundary keys kept per segment after two digit
 
 // bnd != nullptr (passes 2..5): if the segment's boundary bin fitted kBndCap keys, the pass runs over those keys only
 // instead of re-reading and re-scoring the whole segment.
+// keys (optional u32 buffer, one entry per score): digit pass 0 stores every element's order-preserving key there (0 =
+// the element does not take part: masked out), so that the sigmoid, the mask lookup and the HBM read happen ONCE; the
+// later full passes (digit pass 1, the split, and the rare overflow passes) read the keys back from L2.
+// Bin counts are aggregated per warp (__match_any_sync) before they touch shared memory: sigmoid scores crowd into a
+// handful of exponent bins, which would serialise the shared-memory atomics 32-fold.
 template <bool SIGMOID>
 __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__restrict__ scores, const SegTable tab,
                                                                  const SegState *__restrict__ state, int pass,
                                                                  unsigned *__restrict__ hist /*[nseg][kBins]*/,
                                                                  const unsigned long long *__restrict__ bnd,
-                                                                 int *__restrict__ tickets) {
+                                                                 int *__restrict__ tickets, unsigned *__restrict__ keys) {
   const int seg = blockIdx.y;
   const SegDesc d = tab.s[seg];
   const SegState st = state[seg];
@@ -162,36 +169,49 @@ __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__
   const unsigned pre_hi = (unsigned)(st.prefix >> 32);
   const float *src = scores + d.off;
   const unsigned long long *bsrc = bnd + (long long)seg * kBndCap;
+  unsigned *kbuf = keys != nullptr ? keys + d.koff : nullptr;
+  const unsigned lane = threadIdx.x & 31u;
   // grid-stride over the segment: the boundary passes are launched with a few CTAs per segment (the usual case
   // needs one); a segment that overflowed the boundary buffer is then walked by those few CTAs
   for (long long base = (long long)blockIdx.x * kItemsPerCta; base < len; base += (long long)gridDim.x * kItemsPerCta)
 #pragma unroll 4
   for (int it = 0; it < kItemsPerThread; ++it) {
     const long long m = base + (long long)it * kTopkThreads + threadIdx.x;
+    unsigned bin = 0xFFFFFFFFu;  // no contribution
     if (m < len) {
       unsigned kh, kl_b = 0;
+      bool take = true;
       if (use_b) {
         const unsigned long long key = bsrc[m];
         kh = (unsigned)(key >> 32), kl_b = (unsigned)key;
+      } else if (kbuf != nullptr && pass > 0) {
+        kh = __ldg(kbuf + m);
+        take = kh != 0u;
       } else {
-        if (d.mask != nullptr && !__ldg(d.mask + logical_index(d, (unsigned)m))) continue;
+        take = d.mask == nullptr || __ldg(d.mask + logical_index(d, (unsigned)m)) != 0;
         float v = __ldg(src + m);
         if (SIGMOID) v = sigmoid_ref(v);
-        kh = okey(v);
+        kh = take ? okey(v) : 0u;
+        if (kbuf != nullptr) kbuf[m] = kh;
       }
-      if (!low_word) {
-        // participates iff the already-decided high digits match
-        const int decided = 32 - (shift - 32) - bits;  // number of decided bits of the score word
-        const bool match = decided == 0 || (kh >> (32 - decided)) == (pre_hi >> (32 - decided));
-        if (match) atomicAdd(&h[(kh >> (shift - 32)) & dmask], 1u);
-      } else if (kh == pre_hi) {
-        const unsigned kl = use_b ? kl_b : ~logical_index(d, (unsigned)m);
-        const unsigned pre_lo = (unsigned)st.prefix;
-        const int decided = 32 - shift - bits;
-        const bool match = decided == 0 || (kl >> (32 - decided)) == (pre_lo >> (32 - decided));
-        if (match) atomicAdd(&h[(kl >> shift) & dmask], 1u);
+      if (take) {
+        if (!low_word) {
+          // participates iff the already-decided high digits match
+          const int decided = 32 - (shift - 32) - bits;  // number of decided bits of the score word
+          const bool match = decided == 0 || (kh >> (32 - decided)) == (pre_hi >> (32 - decided));
+          if (match) bin = (kh >> (shift - 32)) & dmask;
+        } else if (kh == pre_hi) {
+          const unsigned kl = use_b ? kl_b : ~logical_index(d, (unsigned)m);
+          const unsigned pre_lo = (unsigned)st.prefix;
+          const int decided = 32 - shift - bits;
+          const bool match = decided == 0 || (kl >> (32 - decided)) == (pre_lo >> (32 - decided));
+          if (match) bin = (kl >> shift) & dmask;
+        }
       }
     }
+    // one shared-memory atomic per distinct bin of the warp
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin != 0xFFFFFFFFu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
   }
   __syncthreads();
   unsigned *g = hist + (long long)seg * kBins;
@@ -220,7 +240,8 @@ template <bool SIGMOID>
 __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const float *__restrict__ scores,
                                                                     const SegTable tab, SegState *__restrict__ state,
                                                                     int k, unsigned long long *__restrict__ cand,
-                                                                    const unsigned long long *__restrict__ bnd) {
+                                                                    const unsigned long long *__restrict__ bnd,
+                                                                    const unsigned *__restrict__ keys) {
   const int seg = blockIdx.y;
   const SegDesc d = tab.s[seg];
   const long long base = (long long)blockIdx.x * kItemsPerCta;
@@ -240,6 +261,10 @@ __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const float 
       unsigned long long key;
       if (use_b) {
         key = bsrc[m];
+      } else if (keys != nullptr) {
+        const unsigned kh = __ldg(keys + d.koff + m);   // 0 (masked out) is below every threshold that selects anything
+        if (kh == 0u || kh < thr_hi) continue;
+        key = ((unsigned long long)kh << 32) | (unsigned)~logical_index(d, (unsigned)m);
       } else {
         float v = __ldg(src + m);
         if (SIGMOID) v = sigmoid_ref(v);
@@ -265,7 +290,8 @@ template <bool SIGMOID>
 __global__ void __launch_bounds__(kTopkThreads) topk_split_kernel(const float *__restrict__ scores, const SegTable tab,
                                                                   SegState *__restrict__ state, int k,
                                                                   unsigned long long *__restrict__ cand,
-                                                                  unsigned long long *__restrict__ bnd) {
+                                                                  unsigned long long *__restrict__ bnd,
+                                                                  const unsigned *__restrict__ keys) {
   const int seg = blockIdx.y;
   const SegDesc d = tab.s[seg];
   const long long base = (long long)blockIdx.x * kItemsPerCta;
@@ -278,13 +304,19 @@ __global__ void __launch_bounds__(kTopkThreads) topk_split_kernel(const float *_
   for (int it = 0; it < kItemsPerThread; ++it) {
     const long long m = base + (long long)it * kTopkThreads + threadIdx.x;
     if (m < (long long)d.len) {
-      float v = __ldg(src + m);
-      if (SIGMOID) v = sigmoid_ref(v);
-      const unsigned kh = okey(v);
+      unsigned kh;
+      if (keys != nullptr) {
+        kh = __ldg(keys + d.koff + m);
+        if (kh == 0u) continue;
+      } else {
+        float v = __ldg(src + m);
+        if (SIGMOID) v = sigmoid_ref(v);
+        kh = okey(v);
+      }
       const unsigned h22 = kh >> 10;
       if (h22 >= p22) {
         const unsigned li = logical_index(d, (unsigned)m);
-        if (d.mask != nullptr && !__ldg(d.mask + li)) continue;
+        if (keys == nullptr && d.mask != nullptr && !__ldg(d.mask + li)) continue;
         const unsigned long long key = ((unsigned long long)kh << 32) | (unsigned)~li;
         if (h22 > p22) {
           const int pos = atomicAdd(&state[seg].cand_count, 1);
@@ -618,8 +650,15 @@ static const size_t kHistBytes = (size_t)kMaxSeg * kBins * sizeof(unsigned);  //
 size_t roi3d_topk_workspace_bytes(int nseg, int k) {
   if (nseg <= 0 || k <= 0) return 256;
   const size_t ns = (size_t)(nseg < kMaxSeg ? nseg : kMaxSeg);
-  return kStateBytes + kHistBytes + ns * (size_t)k * sizeof(unsigned long long) +
-         ns * (size_t)kBndCap * sizeof(unsigned long long);
+  const size_t b = kStateBytes + kHistBytes + ns * (size_t)k * sizeof(unsigned long long) +
+                   ns * (size_t)kBndCap * sizeof(unsigned long long);
+  return (b + 255) / 256 * 256;
+}
+
+size_t roi3d_topk_workspace_bytes_keys(int nseg, int k, int64_t total_len) {
+  const size_t base = roi3d_topk_workspace_bytes(nseg, k);
+  if (nseg <= 0 || k <= 0 || total_len <= 0) return base;
+  return base + ((size_t)total_len * sizeof(unsigned) + 255) / 256 * 256;
 }
 
 int roi3d_topk_segmented(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
@@ -654,10 +693,18 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
   cudaStream_t st = (cudaStream_t)stream;
   ROI3D_CUDA(cudaMemsetAsync(out_idx_dev, 0xFF, sizeof(int64_t) * (size_t)nseg * k, st));
   ROI3D_CUDA(cudaMemsetAsync(out_val_dev, 0, sizeof(float) * (size_t)nseg * k, st));
+  // optional key buffer behind the base workspace (roi3d_topk_workspace_bytes_keys): one u32 per score of a batch of
+  // kMaxSeg segments, written by the first digit pass and read back (from L2) by the later full passes
+  long long total_len = 0;
+  for (int s = 0; s < nseg; ++s) total_len += seg_len[s] > 0 ? seg_len[s] : 0;
+  const size_t base_bytes = roi3d_topk_workspace_bytes(nseg, k);
+  unsigned *keys = workspace_bytes >= roi3d_topk_workspace_bytes_keys(nseg, k, total_len) && total_len > 0
+                       ? reinterpret_cast<unsigned *>(static_cast<char *>(workspace_dev) + base_bytes)
+                       : nullptr;
   for (int s0 = 0; s0 < nseg; s0 += kMaxSeg) {
     const int ns = nseg - s0 < kMaxSeg ? nseg - s0 : kMaxSeg;
     SegTable tab;
-    long long maxlen = 0;
+    long long maxlen = 0, koff = 0;
     for (int s = 0; s < ns; ++s) {
       ROI3D_CHECK_ARG(seg_len[s0 + s] >= 0 && seg_len[s0 + s] < 4294967295LL, "segment %d too long", s0 + s);
       tab.s[s].off = seg_off[s0 + s];
@@ -671,6 +718,8 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
         tab.s[s].A = tab.s[s].D = tab.s[s].H = tab.s[s].W = 0;
       }
       tab.s[s].mask = seg_mask_dev_ptrs != nullptr ? seg_mask_dev_ptrs[s0 + s] : nullptr;
+      tab.s[s].koff = koff;
+      koff += seg_len[s0 + s];
       if (seg_len[s0 + s] > maxlen) maxlen = seg_len[s0 + s];
     }
     static_assert(sizeof(SegState) * kMaxSeg + sizeof(int) * kMaxSeg <= 4096, "state block");
@@ -698,24 +747,24 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
       const unsigned long long *b2 = pass >= 2 ? bnd : nullptr;
       const dim3 g = pass >= 2 ? grid2 : grid;
       if (apply_sigmoid)
-        topk_hist_kernel<true><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets);
+        topk_hist_kernel<true><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets, keys);
       else
-        topk_hist_kernel<false><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets);
+        topk_hist_kernel<false><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets, keys);
       ROI3D_LAUNCH_CHECK();
       if (pass == 1) {  // 22 bits decided: split off the certain keys and the boundary bin
         if (apply_sigmoid)
-          topk_split_kernel<true><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd);
+          topk_split_kernel<true><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
         else
-          topk_split_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd);
+          topk_split_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
         ROI3D_LAUNCH_CHECK();
         topk_after_split_kernel<<<1, kMaxSeg, 0, st>>>(state, ns);
         ROI3D_LAUNCH_CHECK();
       }
     }
     if (apply_sigmoid)
-      topk_collect_kernel<true><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd);
+      topk_collect_kernel<true><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
     else
-      topk_collect_kernel<false><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd);
+      topk_collect_kernel<false><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
     ROI3D_LAUNCH_CHECK();
     if (k <= kBitonicMax) {
       int npow2 = 2;

@@ -1717,6 +1717,7 @@ static int g_fwd_items_per_warp = 0;  // 0 = auto
 extern int g_host_pipeline_kb;        // host_api.cu
 extern int g_fwd_stream_cfg, g_fwd_stream_debug;  // roi_align3d_stream.cu  // roi_align3d_stream.cu
 extern int g_nms_mask_variant;        // nms3d.cu
+extern int g_planar_smem_floats;      // roi_align3d_planar.cu
 static int g_bwd_variant = 0;
 
 template <int PW, int ROWS, int CV, int NXU>
@@ -1920,9 +1921,9 @@ static int fill_params(RoiParams &p, const roi3d_level_t *levels, int num_levels
   ROI3D_CHECK_ARG(finest_scale > 0.0f || num_levels == 1, "finest_scale must be > 0");
   for (int l = 0; l < num_levels; ++l) {
     ROI3D_CHECK_ARG(levels[l].layout == ROI3D_NDHWC || (!bwd && levels[l].layout == ROI3D_NCDHW),
-                    "level %d: the backward kernels read channels-last (ROI3D_NDHWC) memory; convert with "
-                    "roi3d_ncdhw_to_ndhwc first",
-                    l);
+                    "level %d: bad layout %d (forward: ROI3D_NCDHW or ROI3D_NDHWC; the backward kernels read "
+                    "channels-last ROI3D_NDHWC memory, convert with roi3d_ncdhw_to_ndhwc first)",
+                    l, levels[l].layout);
     ROI3D_CHECK_ARG(levels[l].layout == levels[0].layout, "level %d: all levels must share one layout", l);
     ROI3D_CHECK_ARG(levels[l].D > 0 && levels[l].H > 0 && levels[l].W > 0, "level %d: bad dims", l);
     ROI3D_CHECK_ARG(bwd ? levels[l].grad_dev != nullptr : levels[l].feats_dev != nullptr, "level %d: NULL pointer", l);
@@ -1955,6 +1956,7 @@ int roi3d_set_tuning(int key, int value) {
   else if (key == 6) g_nms_mask_variant = value;
   else if (key == 7) g_fwd_stream_cfg = value;
   else if (key == 9) g_fwd_stream_debug = value;
+  else if (key == 10) g_planar_smem_floats = value;
   else return ROI3D_EINVAL;
   return ROI3D_OK;
 }

@@ -36,9 +36,12 @@ constexpr int PL_SMEM_FLOATS = 27648;  // plane storage per CTA (108 KB): two CT
 
 struct PlanarTables {
   int xo[PL_MAXP], yo[PL_MAXP], zo[PL_MAXP];       // first tap of a bin, from the box origin (x: from the aligned origin)
-  float xw[PL_MAXP][4], yw[PL_MAXP][4], zw[PL_MAXP][4];
+  int nz[PL_MAXP];                                 // slices of z bin pd
+  alignas(16) float xw[PL_MAXP][4];
+  alignas(16) float yw[PL_MAXP][4];
+  alignas(16) float zw[PL_MAXP][4];                // pre-multiplied by 1 / count
   int lo[48], hi[48];                              // per (axis, bin): tap range in level coordinates
-  int box[20];                                     // xa, RXB, y0, RY, z0, RZ, flags(1 = empty, 2 = slow), NTX; per-axis min / max / widest bin
+  int box[20];                                     // xa, RXB, y0, RY, z0, RZ, flags(1 = empty, 2 = slow), NTX; per-axis min / max / widest bin; CGs, ZC, NTY
 };
 
 __device__ __forceinline__ void cp_async16_pl(void *dst, const void *src) {
@@ -88,44 +91,84 @@ __device__ float literal_bin_strided(const Axis &axw, const Axis &axh, const Axi
   return __fdiv_rn(acc, (float)(axd.S * axh.S * axw.S));
 }
 
-// One contraction stage for one output element over the channels of a pass: NT taps at s[t * TS] (TS compile-time),
-// source planes src_plane floats apart, results handed to `put(c, v)`.  Four channels per trip keep twelve to sixteen
-// independent shared-memory loads in flight per thread.
-template <int NT, int TS, typename Put>
-__device__ __forceinline__ void planar_taps(const float *s, int src_plane, int nch, const float (&w)[4], Put put) {
-  int c = 0;
-  for (; c + 4 <= nch; c += 4) {
-    float v[4];
+// acc += w * v for the four channels of a packed entry: two packed-fp32 FFMA2, each half rounded like fmaf
+__device__ __forceinline__ void fma4(float4 &a, float w, const float4 v) {
+  const float2 w2 = make_float2(w, w);
+  const float2 lo = __ffma2_rn(w2, make_float2(v.x, v.y), make_float2(a.x, a.y));
+  const float2 hi = __ffma2_rn(w2, make_float2(v.z, v.w), make_float2(a.z, a.w));
+  a = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 mul4(float w, const float4 v) {
+  const float2 w2 = make_float2(w, w);
+  const float2 lo = __fmul2_rn(w2, make_float2(v.x, v.y)), hi = __fmul2_rn(w2, make_float2(v.z, v.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// NT taps, STRIDE floats apart, of packed (four-channel) entries: one LDS.128 + two FFMA2 per tap
+template <int NT, int STRIDE>
+__device__ __forceinline__ float4 taps4(const float *s, const float4 w) {
+  float4 a = mul4(w.x, *reinterpret_cast<const float4 *>(s));
+  if (NT > 1) fma4(a, w.y, *reinterpret_cast<const float4 *>(s + STRIDE));
+  if (NT > 2) fma4(a, w.z, *reinterpret_cast<const float4 *>(s + 2 * STRIDE));
+  if (NT > 3) fma4(a, w.w, *reinterpret_cast<const float4 *>(s + 3 * STRIDE));
+  return a;
+}
+// same with a per-thread tap count (the z stage: bins of one RoI differ in how many slices they touch)
+template <int STRIDE>
+__device__ __forceinline__ float4 taps4_n(int n, const float *s, const float4 w) {
+  float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (n > 0) a = mul4(w.x, *reinterpret_cast<const float4 *>(s));
+  if (n > 1) fma4(a, w.y, *reinterpret_cast<const float4 *>(s + STRIDE));
+  if (n > 2) fma4(a, w.z, *reinterpret_cast<const float4 *>(s + 2 * STRIDE));
+  if (n > 3) fma4(a, w.w, *reinterpret_cast<const float4 *>(s + 3 * STRIDE));
+  return a;
+}
+
+// ---- x stage: footprint rows -> T1[group][row][pw][4 channels].  NCDHW: the footprint lies in one plane per channel
+//      (rows of RXB floats), four scalar taps rows; channels-last: packed entries, one LDS.128 per tap.
+template <int P, bool CL, int NT>
+__device__ __forceinline__ void planar_x_stage(const PlanarTables &T, const float *raw, float *T1, int rowsC, int rowsMax,
+                                               int RXB, int szR, int NG, int tid) {
+  const unsigned ntask = (unsigned)(rowsC * P), total = ntask * (unsigned)NG, m_nt = fast_magic(ntask);
+  for (unsigned e = tid; e < total; e += PL_THREADS) {
+    const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
+    const unsigned row = t / P, pw = t - row * P;
+    const float4 w = *reinterpret_cast<const float4 *>(&T.xw[pw][0]);
+    const int xo = T.xo[pw];
+    float4 a;
+    if constexpr (CL) {
+      a = taps4<NT, 4>(raw + ((cg * rowsMax + row) * RXB + xo) * 4, w);
+    } else {
+      const float *s = raw + (4 * cg) * szR + row * RXB + xo;
+      float v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float *q = s + u * src_plane;
-      float a = w[0] * q[0];
-      if (NT > 1) a = fmaf(w[1], q[TS], a);
-      if (NT > 2) a = fmaf(w[2], q[2 * TS], a);
-      if (NT > 3) a = fmaf(w[3], q[3 * TS], a);
-      v[u] = a;
+      for (int u = 0; u < 4; ++u) {
+        const float *q = s + u * szR;
+        float x = __fmul_rn(w.x, q[0]);
+        if (NT > 1) x = __fmaf_rn(w.y, q[1], x);
+        if (NT > 2) x = __fmaf_rn(w.z, q[2], x);
+        if (NT > 3) x = __fmaf_rn(w.w, q[3], x);
+        v[u] = x;
+      }
+      a = make_float4(v[0], v[1], v[2], v[3]);
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) put(c + u, v[u]);
-    s += 4 * src_plane;
-  }
-  for (; c < nch; ++c) {
-    float a = w[0] * s[0];
-    if (NT > 1) a = fmaf(w[1], s[TS], a);
-    if (NT > 2) a = fmaf(w[2], s[2 * TS], a);
-    if (NT > 3) a = fmaf(w[3], s[3 * TS], a);
-    put(c, a);
-    s += src_plane;
+    *reinterpret_cast<float4 *>(T1 + ((cg * rowsMax + row) * P + pw) * 4) = a;
   }
 }
 
-// Tap count as a template argument from a runtime value in 1..4.
-template <int TS, typename Put>
-__device__ __forceinline__ void planar_taps_n(int nt, const float *s, int src_plane, int nch, const float (&w)[4], Put put) {
-  if (nt >= 4) planar_taps<4, TS>(s, src_plane, nch, w, put);
-  else if (nt == 3) planar_taps<3, TS>(s, src_plane, nch, w, put);
-  else if (nt == 2) planar_taps<2, TS>(s, src_plane, nch, w, put);
-  else planar_taps<1, TS>(s, src_plane, nch, w, put);
+// ---- y stage: T1[group][zr * RY + y][pw][4] -> T2[group][z][ph * P + pw][4]
+template <int P, int NT>
+__device__ __forceinline__ void planar_y_stage(const PlanarTables &T, const float *T1, float *T2, int zb, int zc, int rowsMax,
+                                               int RY, int RZ, int NG, int tid) {
+  constexpr int PP = P * P;
+  const unsigned ntask = (unsigned)(zc * PP), total = ntask * (unsigned)NG, m_nt = fast_magic(ntask);
+  for (unsigned e = tid; e < total; e += PL_THREADS) {
+    const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
+    const unsigned zr = t / PP, q = t - zr * PP;
+    const unsigned ph = q / P, pw = q - ph * P;
+    const float4 w = *reinterpret_cast<const float4 *>(&T.yw[ph][0]);
+    const float4 a = taps4<NT, P * 4>(T1 + ((cg * rowsMax + zr * RY + T.yo[ph]) * P + pw) * 4, w);
+    *reinterpret_cast<float4 *>(T2 + ((cg * RZ + zb + zr) * PP + q) * 4) = a;
+  }
 }
 
 // Visit order of the RoIs: by (level, volume, z, y, x) of their first corner.  In NCDHW a RoI uses 40 to 70 bytes of
@@ -155,11 +198,12 @@ __global__ void __launch_bounds__(256) roi_align3d_order_kernel(const RoiParams 
   order[rank] = k;
 }
 
-template <int P>  // PW == PH == P
-__global__ void __launch_bounds__(PL_THREADS) roi_align3d_fwd_planar_kernel(const RoiParams p, int CG, int ngroups, int ndhwc,
-                                                                            const int *__restrict__ order) {
+template <int P, bool CL>  // PW == PH == P; CL: channels-last levels
+__global__ void __launch_bounds__(PL_THREADS, 2)
+    roi_align3d_fwd_planar_kernel(const RoiParams p, int CG, int ngroups, int smem_floats, const int *__restrict__ order) {
   extern __shared__ __align__(16) float planes[];
   __shared__ PlanarTables T;
+  constexpr int PP = P * P;
   const int tid = threadIdx.x;
   const int kslot = blockIdx.x / ngroups, g = blockIdx.x - kslot * ngroups;
   const int k = order != nullptr ? __ldg(order + kslot) : kslot;
@@ -167,7 +211,7 @@ __global__ void __launch_bounds__(PL_THREADS) roi_align3d_fwd_planar_kernel(cons
   const int nch_all = min(CG, p.C - c_first);
   const int PD = p.PD;
 
-  // ---- RoI geometry (every thread), tap tables (threads 0..47: axis = tid / 16, bin = tid % 16)
+  // ---- RoI geometry (every thread), tap ranges (threads 0..47: axis = tid / 16, bin = tid % 16)
   float r[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
@@ -180,7 +224,7 @@ __global__ void __launch_bounds__(PL_THREADS) roi_align3d_fwd_planar_kernel(cons
   const Axis axw = axis_setup(r[1], r[3], L.scale, P, p.sample_num);
   const Axis axh = axis_setup(r[2], r[4], L.scale, P, p.sample_num);
   const Axis axd = axis_setup(r[5], r[6], L.scale_d, PD, p.sample_num);
-  const long long out_elems = (long long)PD * P * P;
+  const long long out_elems = (long long)PD * PP;
   float *out_roi = p.out + (krow * p.C + c_first) * out_elems;
   {
     const int axis = tid >> 4, bin = tid & 15;
@@ -218,26 +262,38 @@ __global__ void __launch_bounds__(PL_THREADS) roi_align3d_fwd_planar_kernel(cons
     const int *q = T.box + 8;
     const bool empty = !ok || q[1] < q[0] || q[4] < q[3] || q[7] < q[6];
     const bool slow = q[2] > 4 || q[5] > 4 || q[8] > 4;
-    const int xa = empty ? 0 : (q[0] & ~3);                          // 16-byte aligned row start
-    const int RXB = empty ? 4 : max(4, ((q[1] - xa + 1) + 3) & ~3);  // floats per plane row (whole 16-byte pieces)
+    // NCDHW rows are copied in whole 16-byte pieces from a 16-byte aligned start; channels-last rows voxel by voxel
+    const int xa = empty ? 0 : (CL ? q[0] : (q[0] & ~3));
+    const int RXB = empty ? 4 : (CL ? q[1] - q[0] + 1 : max(4, ((q[1] - xa + 1) + 3) & ~3));
+    const int RY = empty ? 0 : q[4] - q[3] + 1, RZ = empty ? 0 : q[7] - q[6] + 1;
+    // Shared-memory plan: CGs channels per pass (whole groups of four) and ZC slices per step.  T2 holds every slice of
+    // the pass; the footprint (two buffers: the next step is copied while this one is reduced) and T1 hold one step.
+    // Fewest steps wins, ties go to more channels per pass.
+    int bestCG = 0, bestZC = 0, bestSteps = INT_MAX;
+    if (!empty && !slow) {
+      const int ncap = min((nch_all + 3) & ~3, PL_MAXCG);
+      for (int cg = ncap; cg >= 4; cg -= 4) {
+        const int rem = smem_floats - cg * RZ * PP;
+        const int per = cg * (2 * RY * RXB + RY * P);
+        const int zmax = rem > 0 ? min(RZ, rem / per) : 0;
+        if (zmax < 1) continue;
+        const int nchunk = (RZ + zmax - 1) / zmax;
+        const int steps = ((nch_all + cg - 1) / cg) * nchunk;
+        if (steps < bestSteps) bestSteps = steps, bestCG = cg, bestZC = (RZ + nchunk - 1) / nchunk;
+      }
+    }
     T.box[0] = xa, T.box[1] = RXB;
-    T.box[2] = empty ? 0 : q[3], T.box[3] = empty ? 0 : q[4] - q[3] + 1;
-    T.box[4] = empty ? 0 : q[6], T.box[5] = empty ? 0 : q[7] - q[6] + 1;
+    T.box[2] = empty ? 0 : q[3], T.box[3] = RY;
+    T.box[4] = empty ? 0 : q[6], T.box[5] = RZ;
     T.box[6] = (empty ? 1 : 0) | (slow && !empty ? 2 : 0);
-    T.box[7] = q[2] <= 3 ? 3 : 4;   // taps per x bin the x stage reads (RXB >= 4 holds either)
+    T.box[7] = max(1, q[2]);    // taps per x bin (widest bin)
+    T.box[17] = bestCG, T.box[18] = bestZC;
+    T.box[19] = max(1, q[5]);   // taps per y bin
   }
   __syncthreads();
   const int xa = T.box[0], RXB = T.box[1], y0 = T.box[2], RY = T.box[3], z0 = T.box[4], RZ = T.box[5];
-  const int flags = T.box[6], NTX = T.box[7];
-  // planes: A holds the footprint, then (after the x stage) T2; B holds T1.  +1 float per plane against bank conflicts
-  const int rows = RZ * RY;
-  const int szA = ((max(rows * RXB, RZ * P * P) + 3) & ~3) + 4, szB = ((rows * P + 3) & ~3) + 4;  // 16-byte aligned planes
-  // two input buffers (the next pass is copied while this one is reduced) + one T1 buffer
-  int CGs = (flags == 0) ? min(min(nch_all, PL_MAXCG), PL_SMEM_FLOATS / (2 * szA + szB)) : 0;
-  if (CGs > 4) CGs &= ~3;  // whole groups of four channels (the stage loops walk four at a time)
+  const int flags = T.box[6], NTX = T.box[7], CGs = T.box[17], ZC = T.box[18], NTY = T.box[19];
   const long long vox = (long long)L.D * L.H * L.W;
-  // element strides of the level: NCDHW (sc = vox, sx = 1) or channels-last (sc = 1, sx = C)
-  const long long sc = ndhwc ? 1 : vox, sx = ndhwc ? p.C : 1, sy = sx * L.W, sz = sy * L.H;
   const float *fb = L.feats + (long long)(ok ? b : 0) * vox * p.C;
 
   if (flags & 1) {  // no sample inside the level (or batch index out of range): 0 / count, NaN for count == 0
@@ -246,20 +302,21 @@ __global__ void __launch_bounds__(PL_THREADS) roi_align3d_fwd_planar_kernel(cons
     return;
   }
   if (CGs == 0) {  // literal path: lanes over output elements, one channel at a time (rare)
+    const long long sc = CL ? 1 : vox, sx = CL ? p.C : 1, sy = sx * L.W, sz = sy * L.H;
     for (int c = 0; c < nch_all; ++c) {
       const float *fc = fb + (long long)(c_first + c) * sc;
       for (int e = tid; e < (int)out_elems; e += PL_THREADS) {
-        const int pw = e % P, ph = (e / P) % P, pd = e / (P * P);
+        const int pw = e % P, ph = (e / P) % P, pd = e / PP;
         __stcs(out_roi + c * out_elems + e, literal_bin_strided(axw, axh, axd, L.D, L.H, L.W, fc, sz, sy, sx, pd, ph, pw));
       }
     }
     return;
   }
 
-  // ---- tap tables: the taps of a bin are NT consecutive voxels of its axis (NT = 4, or the axis extent if smaller; 3
-  //      along x when no bin needs more), weights summed per voxel, first tap relative to the box origin (x: to the
-  //      aligned row start) and shifted left where the NT taps would leave the box (the shifted-in weights are 0), so
-  //      that every tap reads copied data
+  // ---- tap tables.  x / y: every bin reads NTX / NTY consecutive voxels (the widest bin of the axis), first tap
+  //      relative to the box origin and shifted left where the taps would leave the box (the shifted-in weights are 0),
+  //      so that every tap reads copied data.  z: exactly the slices of the bin, weights pre-multiplied by 1 / count
+  //      (exact for the power-of-two counts of fixed sample_num).
   if (tid < 48) {
     const int axis = tid >> 4, bin = tid & 15;
     const int nb = axis == 2 ? PD : P;
@@ -268,13 +325,16 @@ __global__ void __launch_bounds__(PL_THREADS) roi_align3d_fwd_planar_kernel(cons
       const int asize = axis == 0 ? L.W : axis == 1 ? L.H : L.D;
       const int lo = T.lo[tid], hi = T.hi[tid];
       float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
-      int off = 0;
+      int off = 0, n = 0;
       if (hi >= lo) {
+        n = hi - lo + 1;
         off = lo - (axis == 0 ? xa : axis == 1 ? y0 : z0);
-        const int extent = axis == 0 ? RXB : axis == 1 ? RY : RZ;
-        const int nt = axis == 0 ? NTX : min(4, extent);
-        const int sh = max(0, off + nt - extent);
-        off -= sh;
+        int sh = 0;
+        if (axis < 2) {
+          const int extent = axis == 0 ? RXB : RY, nt = axis == 0 ? NTX : NTY;
+          sh = max(0, off + nt - extent);
+          off -= sh;
+        }
         for (int i = 0; i < ax.S; ++i) {
           const Tap t = axis_tap(axis_coord(ax, bin, i), asize);
           if (t.valid) {
@@ -284,107 +344,129 @@ __global__ void __launch_bounds__(PL_THREADS) roi_align3d_fwd_planar_kernel(cons
           }
         }
       }
+      if (axis == 2) {
+        const float inv = __frcp_rn((float)(axd.S * axh.S * axw.S));
+        w0 *= inv, w1 *= inv, w2 *= inv, w3 *= inv;
+        T.nz[bin] = n;
+      }
       int *po = axis == 0 ? T.xo : axis == 1 ? T.yo : T.zo;
       float(*pwt)[4] = axis == 0 ? T.xw : axis == 1 ? T.yw : T.zw;
       po[bin] = off;
       pwt[bin][0] = w0, pwt[bin][1] = w1, pwt[bin][2] = w2, pwt[bin][3] = w3;
     }
   }
-  __syncthreads();
-  const float inv = __frcp_rn((float)(axd.S * axh.S * axw.S));  // exact for the power-of-two counts of fixed sample_num
-  float *A0 = planes, *A1 = planes + (size_t)CGs * szA, *B = planes + (size_t)2 * CGs * szA;
+  // (visible to all threads after the first barrier of the step loop)
+
+  const int rowsMax = ZC * RY;             // rows of a step's footprint / T1 planes
+  const int szR = rowsMax * RXB;           // NCDHW: floats per channel plane of a step
+  const int rawsz = CGs * szR;             // one footprint buffer (either layout)
+  float *raw0 = planes, *raw1 = planes + rawsz, *T1 = planes + 2 * rawsz, *T2 = T1 + CGs * rowsMax * P;
   const int npass = (nch_all + CGs - 1) / CGs;
-  auto issue_copy = [&](int c0, float *Ad) {
-    const int nch = min(CGs, nch_all - c0);
-    // ---- copy the footprint planes (32-bit element offsets from the volume's first element: checked by the launcher)
-    if (!ndhwc) {
-      const unsigned npc = (unsigned)RXB >> 2;       // 16-byte pieces per row
-      const unsigned per_ch = (unsigned)rows * npc;
-      const unsigned m_npc = fast_magic(npc), m_ry = fast_magic((unsigned)RY);
+  const int nchunk = (RZ + ZC - 1) / ZC;
+  const int nsteps = npass * nchunk;
+
+  auto issue_copy = [&](int s, float *dstbuf) {
+    const int pass = s / nchunk, chunk = s - pass * nchunk;
+    const int c0 = pass * CGs, nch = min(CGs, nch_all - c0);
+    const int zb = chunk * ZC, zc = min(ZC, RZ - zb);
+    const unsigned rows = (unsigned)(zc * RY);
+    const unsigned m_ry = fast_magic((unsigned)RY);
+    // 32-bit element offsets from the volume's first element: checked by the launcher
+    if constexpr (!CL) {
+      const unsigned npc = (unsigned)RXB >> 2;       // 16-byte pieces per row; every piece lies inside the row (W % 4 == 0)
+      const unsigned per_ch = rows * npc;
+      const unsigned m_npc = fast_magic(npc);
       const unsigned W_ = (unsigned)L.W, HW = (unsigned)(L.H * L.W);
-      const unsigned base0 = (unsigned)((z0 * L.H + y0) * L.W + xa);
+      const unsigned base0 = (unsigned)(((z0 + zb) * L.H + y0) * L.W + xa);
+      const float *src0 = fb + (size_t)(c_first + c0) * (size_t)vox;
       // a thread's (row, piece) walk is the same for every channel: decode once per row-piece, loop channels inside
       for (unsigned rr = tid; rr < per_ch; rr += PL_THREADS) {
         const unsigned row = fast_div(rr, npc, m_npc), pc = rr - row * npc;
         const unsigned z = fast_div(row, (unsigned)RY, m_ry), y = row - z * (unsigned)RY;
-        const int x = xa + (int)pc * 4;
-        const unsigned goff = base0 + z * HW + y * W_ + pc * 4;
-        float *dst = Ad + row * RXB + pc * 4;
-        const float *src = fb + (size_t)(c_first + c0) * (size_t)vox + goff;
-        if (x + 4 <= L.W) {
-          for (int c = 0; c < nch; ++c) cp_async16_pl(dst + c * szA, src + (size_t)c * (size_t)vox);
-        } else {
-          for (int c = 0; c < nch; ++c)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[c * szA + j] = (x + j < L.W) ? __ldg(src + (size_t)c * (size_t)vox + j) : 0.0f;
-        }
+        float *dst = dstbuf + row * RXB + pc * 4;
+        const float *src = src0 + (base0 + z * HW + y * W_ + pc * 4);
+        for (int c = 0; c < nch; ++c) cp_async16_pl(dst + c * szR, src + (size_t)c * (size_t)vox);
       }
     } else {
-      // channels-last: the nch channels of a voxel are contiguous; thread -> (voxel, channel), channels fastest
-      const unsigned per_vox = (unsigned)(rows * RXB);
-      const unsigned m_nch = fast_magic((unsigned)nch), m_rxb = fast_magic((unsigned)RXB), m_ry = fast_magic((unsigned)RY);
+      // channels-last: four channels of a voxel per 16-byte copy, straight into the packed layout [group][row][x][4]
+      const unsigned NG = (unsigned)(nch >> 2);
+      const unsigned total = rows * (unsigned)RXB * NG;
+      const unsigned m_ng = fast_magic(NG), m_rxb = fast_magic((unsigned)RXB);
       const unsigned C_ = (unsigned)p.C, WC = (unsigned)L.W * C_, HWC = (unsigned)L.H * WC;
-      const float *src0 = fb + (size_t)((z0 * L.H + y0) * L.W + xa) * C_ + (c_first + c0);
-      for (unsigned q = tid; q < (unsigned)nch * per_vox; q += PL_THREADS) {
-        const unsigned v = fast_div(q, (unsigned)nch, m_nch), c = q - v * (unsigned)nch;
+      const float *src0 = fb + (size_t)(((z0 + zb) * L.H + y0) * L.W + xa) * C_ + (c_first + c0);
+      for (unsigned q = tid; q < total; q += PL_THREADS) {
+        const unsigned v = fast_div(q, NG, m_ng), cg = q - v * NG;
         const unsigned row = fast_div(v, (unsigned)RXB, m_rxb), xx = v - row * (unsigned)RXB;
         const unsigned z = fast_div(row, (unsigned)RY, m_ry), y = row - z * (unsigned)RY;
-        float *dst = Ad + c * szA + v;
-        if (xa + (int)xx < L.W)
-          cp_async4_pl(dst, src0 + (z * HWC + y * WC + xx * C_ + c));
-        else
-          *dst = 0.0f;
+        cp_async16_pl(dstbuf + ((cg * rowsMax + row) * RXB + xx) * 4, src0 + (z * HWC + y * WC + xx * C_ + cg * 4));
       }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
-  issue_copy(0, A0);
-  for (int ip = 0; ip < npass; ++ip) {
-    const int c0 = ip * CGs;
-    const int nch = min(CGs, nch_all - c0);
-    float *A = (ip & 1) ? A1 : A0;
-    if (ip + 1 < npass) {
-      issue_copy(c0 + CGs, (ip & 1) ? A0 : A1);
+
+  issue_copy(0, raw0);
+  for (int s = 0; s < nsteps; ++s) {
+    const int pass = s / nchunk, chunk = s - pass * nchunk;
+    const int c0 = pass * CGs, nch = min(CGs, nch_all - c0), NG = (nch + 3) >> 2;
+    const int zb = chunk * ZC, zc = min(ZC, RZ - zb);
+    const float *raw = (s & 1) ? raw1 : raw0;
+    if (s + 1 < nsteps) {
+      issue_copy(s + 1, (s & 1) ? raw0 : raw1);
       asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
     __syncthreads();
-    // ---- x stage: A[c][row][RXB] -> B[c][row][P]
-    for (int e = tid; e < rows * P; e += PL_THREADS) {
-      const int row = e / P, pw = e - row * P;
-      const float4 w4 = *reinterpret_cast<const float4 *>(&T.xw[pw][0]);
-      const float w[4] = {w4.x, w4.y, w4.z, w4.w};
-      float *d = B + e;
-      auto put = [&](int c, float v) { d[c * szB] = v; };
-      planar_taps_n<1>(NTX, A + row * RXB + T.xo[pw], szA, nch, w, put);
-    }
+    const int rowsC = zc * RY;
+    if (NTX >= 4) planar_x_stage<P, CL, 4>(T, raw, T1, rowsC, rowsMax, RXB, szR, NG, tid);
+    else if (NTX == 3) planar_x_stage<P, CL, 3>(T, raw, T1, rowsC, rowsMax, RXB, szR, NG, tid);
+    else if (NTX == 2) planar_x_stage<P, CL, 2>(T, raw, T1, rowsC, rowsMax, RXB, szR, NG, tid);
+    else planar_x_stage<P, CL, 1>(T, raw, T1, rowsC, rowsMax, RXB, szR, NG, tid);
     __syncthreads();
-    // ---- y stage: B[c][z][y][P] -> A[c][z][ph][P]
-    for (int e = tid; e < RZ * P * P; e += PL_THREADS) {
-      const int pw = e % P, t1 = e / P;
-      const int ph = t1 % P, z = t1 / P;
-      const float4 w4 = *reinterpret_cast<const float4 *>(&T.yw[ph][0]);
-      const float w[4] = {w4.x, w4.y, w4.z, w4.w};
-      float *d = A + e;
-      auto put = [&](int c, float v) { d[c * szA] = v; };
-      planar_taps_n<P>(min(RY, 4), B + (z * RY + T.yo[ph]) * P + pw, szB, nch, w, put);
-    }
+    if (NTY >= 4) planar_y_stage<P, 4>(T, T1, T2, zb, zc, rowsMax, RY, RZ, NG, tid);
+    else if (NTY == 3) planar_y_stage<P, 3>(T, T1, T2, zb, zc, rowsMax, RY, RZ, NG, tid);
+    else if (NTY == 2) planar_y_stage<P, 2>(T, T1, T2, zb, zc, rowsMax, RY, RZ, NG, tid);
+    else planar_y_stage<P, 1>(T, T1, T2, zb, zc, rowsMax, RY, RZ, NG, tid);
+    if (chunk + 1 < nchunk) continue;
     __syncthreads();
-    // ---- z stage: A[c][z][P*P] -> out[c][pd][P*P], scaled by 1 / count, streamed to global
+    // ---- z stage: T2[group][z][q][4] -> out[c][pd][q], streamed to global: consecutive lanes = consecutive floats
     {
-      constexpr int PP = P * P;
       float *oc = out_roi + (long long)c0 * out_elems;
-      for (int e = tid; e < PD * PP; e += PL_THREADS) {
-        const int pd = e / PP, q = e - pd * PP;
-        const float4 w4 = *reinterpret_cast<const float4 *>(&T.zw[pd][0]);
-        const float w[4] = {w4.x * inv, w4.y * inv, w4.z * inv, w4.w * inv};
-        float *d = oc + e;
-        auto put = [&](int c, float v) { __stcs(d + c * out_elems, v); };
-        planar_taps_n<PP>(min(RZ, 4), A + T.zo[pd] * PP + q, szA, nch, w, put);
+      const int gT2 = RZ * PP * 4;
+      if constexpr (PP >= PL_THREADS / 2) {
+        // wide outputs: a thread keeps its element and walks the channel groups (offsets / weights looked up once)
+        for (int e = tid; e < PD * PP; e += PL_THREADS) {
+          const int pd = e / PP, q = e - pd * PP;
+          const int n = T.nz[pd];
+          const float4 w = *reinterpret_cast<const float4 *>(&T.zw[pd][0]);
+          const float *sp = T2 + (T.zo[pd] * PP + q) * 4;
+          float *d = oc + e;
+          for (int cg = 0; cg < NG; ++cg) {
+            const float4 a = taps4_n<PP * 4>(n, sp, w);
+            const int left = nch - cg * 4;
+            __stcs(d, a.x);
+            if (left > 1) __stcs(d + out_elems, a.y);
+            if (left > 2) __stcs(d + 2 * out_elems, a.z);
+            if (left > 3) __stcs(d + 3 * out_elems, a.w);
+            sp += gT2, d += 4 * out_elems;
+          }
+        }
+      } else {
+        const unsigned ntask = (unsigned)(PD * PP), total = ntask * (unsigned)NG, m_nt = fast_magic(ntask);
+        for (unsigned e = tid; e < total; e += PL_THREADS) {
+          const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
+          const unsigned pd = t / PP, q = t - pd * PP;
+          const float4 w = *reinterpret_cast<const float4 *>(&T.zw[pd][0]);
+          const float4 a = taps4_n<PP * 4>(T.nz[pd], T2 + ((cg * RZ + T.zo[pd]) * PP + q) * 4, w);
+          float *d = oc + (long long)(cg * 4) * out_elems + t;
+          const int left = nch - (int)cg * 4;
+          __stcs(d, a.x);
+          if (left > 1) __stcs(d + out_elems, a.y);
+          if (left > 2) __stcs(d + 2 * out_elems, a.z);
+          if (left > 3) __stcs(d + 3 * out_elems, a.w);
+        }
       }
     }
-    __syncthreads();
   }
 }
 
@@ -396,13 +478,33 @@ bool fwd_planar_ok(const RoiParams &p, int layout) {
   for (int l = 0; l < p.num_levels; ++l)
     if ((long long)p.lv[l].D * p.lv[l].H * p.lv[l].W * p.C >= 2147483647LL) return false;  // 32-bit offsets inside a volume
   for (int l = 0; l < p.num_levels; ++l) {
+    if ((reinterpret_cast<uintptr_t>(p.lv[l].feats) & 15) != 0) return false;
     if (layout == ROI3D_NCDHW) {
-      // 16-byte row pieces: rows must start on 16-byte boundaries
-      if ((reinterpret_cast<uintptr_t>(p.lv[l].feats) & 15) != 0 || p.lv[l].W % 4 != 0) return false;
+      if (p.lv[l].W % 4 != 0) return false;   // 16-byte row pieces: rows must start on 16-byte boundaries
+    } else {
+      if (p.C % 4 != 0) return false;         // 16-byte copies of four channels of a voxel
     }
   }
   return true;
 }
+
+int g_planar_smem_floats = 0;  // roi3d_set_tuning key 10: plane storage per CTA in floats (0 = default, two CTAs per SM)
+
+namespace {
+template <int P, bool CL>
+int launch_planar_cfg(const RoiParams &p, int CG, int ngroups, long long blocks, const int *order, cudaStream_t st) {
+  const int smem_floats = g_planar_smem_floats > 0 ? g_planar_smem_floats : PL_SMEM_FLOATS;
+  const size_t smem = (size_t)smem_floats * sizeof(float);
+  static size_t attr_set = 0;
+  if (attr_set < smem) {
+    ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_planar_kernel<P, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
+  roi_align3d_fwd_planar_kernel<P, CL><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, ngroups, smem_floats, order);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+}  // namespace
 
 int launch_fwd_planar(RoiParams &p, int layout, cudaStream_t st) {
   // a CTA takes 64 channels of a RoI (its prologue -- RoI geometry, tap tables -- is paid once for them) and walks them
@@ -410,10 +512,9 @@ int launch_fwd_planar(RoiParams &p, int layout, cudaStream_t st) {
   int CG = 64;
   if (p.C < CG) CG = p.C;
   const int ngroups = ceil_div(p.C, CG);
-  const size_t smem = (size_t)PL_SMEM_FLOATS * sizeof(float);
   const long long blocks = (long long)p.K * ngroups;
   ROI3D_CHECK_ARG(blocks < 2147483647LL, "roi_align3d forward: too many work items");
-  const int ndhwc = layout == ROI3D_NDHWC ? 1 : 0;
+  const bool cl = layout == ROI3D_NDHWC;
   int *order = nullptr;
   if (p.K > 1 && p.K <= 8192) {
     cudaMemPool_t pool;
@@ -423,24 +524,11 @@ int launch_fwd_planar(RoiParams &p, int layout, cudaStream_t st) {
     roi_align3d_order_kernel<<<ceil_div(p.K, 256), 256, (size_t)p.K * sizeof(unsigned long long), st>>>(p, order);
     ROI3D_LAUNCH_CHECK();
   }
-  if (p.PW == 7) {
-    static bool set7 = false;
-    if (!set7) {
-      ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_planar_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      set7 = true;
-    }
-    roi_align3d_fwd_planar_kernel<7><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, ngroups, ndhwc, order);
-  } else {
-    static bool set14 = false;
-    if (!set14) {
-      ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_planar_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      set14 = true;
-    }
-    roi_align3d_fwd_planar_kernel<14><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, ngroups, ndhwc, order);
-  }
-  ROI3D_LAUNCH_CHECK();
+  int rc;
+  if (p.PW == 7) rc = cl ? launch_planar_cfg<7, true>(p, CG, ngroups, blocks, order, st) : launch_planar_cfg<7, false>(p, CG, ngroups, blocks, order, st);
+  else rc = cl ? launch_planar_cfg<14, true>(p, CG, ngroups, blocks, order, st) : launch_planar_cfg<14, false>(p, CG, ngroups, blocks, order, st);
   if (order != nullptr) ROI3D_CUDA(cudaFreeAsync(order, st));
-  return ROI3D_OK;
+  return rc;
 }
 
 }  // namespace roi3d

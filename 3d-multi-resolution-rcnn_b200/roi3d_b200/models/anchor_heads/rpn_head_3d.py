@@ -67,7 +67,8 @@ def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False, smal
         adhw, adhw_p = None, None
     idx = torch.empty((nseg, k), dtype=torch.int64, device=dev)
     val = torch.empty((nseg, k), dtype=torch.float32, device=dev)
-    nbytes = _lib.lib.roi3d_topk_workspace_bytes(nseg, k)
+    # base workspace + one u32 key per score (the first digit pass stores the keys, later passes re-read them from L2)
+    nbytes = _lib.lib.roi3d_topk_workspace_bytes_keys(nseg, k, int(ln.sum()))
     _buf, ws = workspace(dev, nbytes)
     mask_p, keep = None, []
     if masks is not None and any(m is not None for m in masks):

@@ -256,6 +256,10 @@ int roi3d_roi_align3d_forward_host(const float *feats_host, int layout, int B, i
  * out_idx_dev: int64 [nseg, k] (index within the segment); out_val_dev: fp32 [nseg, k];
  * rows beyond k_s are filled with -1 / 0. */
 size_t roi3d_topk_workspace_bytes(int nseg, int k);
+/* Workspace that additionally holds one u32 key per score (total_len = sum of seg_len): when the workspace passed to
+ * the top-k entries is at least this large, the first digit pass stores every element's order-preserving key
+ * (sigmoid, mask lookup and the HBM read happen once) and the later full passes read the keys back from L2. */
+size_t roi3d_topk_workspace_bytes_keys(int nseg, int k, int64_t total_len);
 int roi3d_topk_segmented(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
                          const int32_t *seg_adhw, int nseg, int k, int apply_sigmoid, int64_t *out_idx_dev,
                          float *out_val_dev, void *workspace_dev, size_t workspace_bytes, void *stream);

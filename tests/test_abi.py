@@ -82,11 +82,11 @@ def test_argument_errors_are_codes_with_messages_not_prints_or_exits():
     from roi3d_b200 import _lib
     lib = _lib.lib
     lv = (_lib.Level * 1)()
-    lv[0].layout = _lib.NCDHW          # the kernels need channels-last: must be refused, not mis-read
+    lv[0].layout = 7                   # neither NCDHW nor NDHWC: must be refused, not mis-read
     lv[0].D, lv[0].H, lv[0].W = 4, 4, 4
     lv[0].feats_dev = 1 << 20
     rc = lib.roi3d_extract_forward(lv, 1, 1, 32, 1 << 20, 5, 7, 7, 7, 2, 56.0, 1 << 20, None, None)
-    assert rc == -1 and b"channels-last" in lib.roi3d_last_error()
+    assert rc == -1 and b"layout" in lib.roi3d_last_error()
     rc = lib.roi3d_extract_forward(lv, 0, 1, 32, None, 0, 7, 7, 7, 2, 56.0, None, None, None)
     assert rc == -1 and b"num_levels" in lib.roi3d_last_error()
     rc = lib.roi3d_nms3d_batched(None, None, -1, 10, 0.5, None, None, None, None, 0, None)

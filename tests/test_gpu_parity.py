@@ -1250,9 +1250,12 @@ PLANAR_CASES = [
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", PLANAR_CASES)
 @pytest.mark.parametrize("layout", ["NCDHW", "NDHWC"])
-def test_roi_align_forward_planar_kernel(oracle, dev, case, layout):
+@pytest.mark.parametrize("smem_floats", [0, 5000])
+def test_roi_align_forward_planar_kernel(oracle, dev, case, layout, smem_floats):
     """The planar kernel: the reference's NCDHW layout read natively (no conversion), and channels-last through the
-    same kernel (tuning variant 60); 7- and 14-wide outputs, ragged channel groups, adversarial and over-wide RoIs."""
+    same kernel (tuning variant 60); 7- and 14-wide outputs, ragged channel groups, adversarial and over-wide RoIs.
+    smem_floats = 5000 shrinks the plane storage (tuning key 10) so that footprints are walked in several z chunks with
+    four channels per pass, and the largest ones fall back to the literal path."""
     import roi3d_b200
     from roi3d_b200.ops import RoIAlign3D
     shape, ps, pdp, sc, scd, sn, k, img = case
@@ -1270,8 +1273,10 @@ def test_roi_align_forward_planar_kernel(oracle, dev, case, layout):
     if layout == "NDHWC":
         ft = cl(ft)
     roi3d_b200._lib.set_tuning(0, 60)
+    roi3d_b200._lib.set_tuning(10, smem_floats)
     try:
         out = RoIAlign3D(ps, pdp, sc, scd, sn)(ft, torch.from_numpy(rois).to(dev))
     finally:
         roi3d_b200._lib.set_tuning(0, 0)
+        roi3d_b200._lib.set_tuning(10, 0)
     assert out.is_contiguous() and rel_err(out.cpu().numpy(), want) <= FWD_TOL
