@@ -112,46 +112,76 @@ __device__ __forceinline__ float4 taps4(const float *s, const float4 w) {
   if (NT > 3) fma4(a, w.w, *reinterpret_cast<const float4 *>(s + 3 * STRIDE));
   return a;
 }
-// same with a per-thread tap count (the z stage: bins of one RoI differ in how many slices they touch)
+// the z stage: bins of one RoI differ in how many slices they touch.  The tables widen every bin to two slices where
+// the footprint has two (TWO, uniform over the CTA), so the common case runs without a branch; a third / fourth tap is rare
 template <int STRIDE>
-__device__ __forceinline__ float4 taps4_n(int n, const float *s, const float4 w) {
-  float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  if (n > 0) a = mul4(w.x, *reinterpret_cast<const float4 *>(s));
-  if (n > 1) fma4(a, w.y, *reinterpret_cast<const float4 *>(s + STRIDE));
-  if (n > 2) fma4(a, w.z, *reinterpret_cast<const float4 *>(s + 2 * STRIDE));
-  if (n > 3) fma4(a, w.w, *reinterpret_cast<const float4 *>(s + 3 * STRIDE));
+__device__ __forceinline__ float4 taps4_n(int n, bool two, const float *s, const float4 w) {
+  float4 a = mul4(w.x, *reinterpret_cast<const float4 *>(s));
+  if (two) fma4(a, w.y, *reinterpret_cast<const float4 *>(s + STRIDE));
+  if (n > 2) {
+    fma4(a, w.z, *reinterpret_cast<const float4 *>(s + 2 * STRIDE));
+    if (n > 3) fma4(a, w.w, *reinterpret_cast<const float4 *>(s + 3 * STRIDE));
+  }
   return a;
+}
+// four channel planes of one output element, OE floats apart (compile-time when the output depth is)
+template <bool FULL4>
+__device__ __forceinline__ void store4(float *d, long long oe, const float4 a, int left) {
+  __stcs(d, a.x);
+  if (FULL4 || left > 1) __stcs(d + oe, a.y);
+  if (FULL4 || left > 2) __stcs(d + 2 * oe, a.z);
+  if (FULL4 || left > 3) __stcs(d + 3 * oe, a.w);
 }
 
 // ---- x stage: footprint rows -> T1[group][row][pw][4 channels].  NCDHW: the footprint lies in one plane per channel
-//      (rows of RXB floats), four scalar taps rows; channels-last: packed entries, one LDS.128 per tap.
+//      (rows of RXB floats), four scalar tap rows per group; channels-last: packed entries, one LDS.128 per tap.
+// Wide outputs (P = 14) have enough (row, pw) tasks per step to fill the CTA: a thread decodes its task once and walks
+// the channel groups; narrow ones spread (group, row, pw) over the threads.
+template <int P, bool CL, int NT>
+__device__ __forceinline__ float4 planar_x_one(const float *raw, const float4 w, int cg, int row, int xo, int rowsMax, int RXB,
+                                               int szR) {
+  if constexpr (CL) {
+    return taps4<NT, 4>(raw + ((cg * rowsMax + row) * RXB + xo) * 4, w);
+  } else {
+    const float *s = raw + (4 * cg) * szR + row * RXB + xo;
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float *q = s + u * szR;
+      float x = __fmul_rn(w.x, q[0]);
+      if (NT > 1) x = __fmaf_rn(w.y, q[1], x);
+      if (NT > 2) x = __fmaf_rn(w.z, q[2], x);
+      if (NT > 3) x = __fmaf_rn(w.w, q[3], x);
+      v[u] = x;
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 template <int P, bool CL, int NT>
 __device__ __forceinline__ void planar_x_stage(const PlanarTables &T, const float *raw, float *T1, int rowsC, int rowsMax,
                                                int RXB, int szR, int NG, int tid) {
-  const unsigned ntask = (unsigned)(rowsC * P), total = ntask * (unsigned)NG, m_nt = fast_magic(ntask);
-  for (unsigned e = tid; e < total; e += PL_THREADS) {
-    const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
-    const unsigned row = t / P, pw = t - row * P;
-    const float4 w = *reinterpret_cast<const float4 *>(&T.xw[pw][0]);
-    const int xo = T.xo[pw];
-    float4 a;
-    if constexpr (CL) {
-      a = taps4<NT, 4>(raw + ((cg * rowsMax + row) * RXB + xo) * 4, w);
-    } else {
-      const float *s = raw + (4 * cg) * szR + row * RXB + xo;
-      float v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float *q = s + u * szR;
-        float x = __fmul_rn(w.x, q[0]);
-        if (NT > 1) x = __fmaf_rn(w.y, q[1], x);
-        if (NT > 2) x = __fmaf_rn(w.z, q[2], x);
-        if (NT > 3) x = __fmaf_rn(w.w, q[3], x);
-        v[u] = x;
+  const unsigned ntask = (unsigned)(rowsC * P);
+  if constexpr (P >= 14) {
+    for (unsigned t = tid; t < ntask; t += PL_THREADS) {
+      const unsigned row = t / P, pw = t - row * P;
+      const float4 w = *reinterpret_cast<const float4 *>(&T.xw[pw][0]);
+      const int xo = T.xo[pw];
+      float *d = T1 + (row * P + pw) * 4;
+      for (int cg = 0; cg < NG; ++cg) {
+        *reinterpret_cast<float4 *>(d) = planar_x_one<P, CL, NT>(raw, w, cg, row, xo, rowsMax, RXB, szR);
+        d += rowsMax * P * 4;
       }
-      a = make_float4(v[0], v[1], v[2], v[3]);
     }
-    *reinterpret_cast<float4 *>(T1 + ((cg * rowsMax + row) * P + pw) * 4) = a;
+  } else {
+    const unsigned total = ntask * (unsigned)NG, m_nt = fast_magic(ntask);
+    for (unsigned e = tid; e < total; e += PL_THREADS) {
+      const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
+      const unsigned row = t / P, pw = t - row * P;
+      const float4 w = *reinterpret_cast<const float4 *>(&T.xw[pw][0]);
+      *reinterpret_cast<float4 *>(T1 + ((cg * rowsMax + row) * P + pw) * 4) =
+          planar_x_one<P, CL, NT>(raw, w, cg, row, T.xo[pw], rowsMax, RXB, szR);
+    }
   }
 }
 
@@ -160,14 +190,29 @@ template <int P, int NT>
 __device__ __forceinline__ void planar_y_stage(const PlanarTables &T, const float *T1, float *T2, int zb, int zc, int rowsMax,
                                                int RY, int RZ, int NG, int tid) {
   constexpr int PP = P * P;
-  const unsigned ntask = (unsigned)(zc * PP), total = ntask * (unsigned)NG, m_nt = fast_magic(ntask);
-  for (unsigned e = tid; e < total; e += PL_THREADS) {
-    const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
-    const unsigned zr = t / PP, q = t - zr * PP;
-    const unsigned ph = q / P, pw = q - ph * P;
-    const float4 w = *reinterpret_cast<const float4 *>(&T.yw[ph][0]);
-    const float4 a = taps4<NT, P * 4>(T1 + ((cg * rowsMax + zr * RY + T.yo[ph]) * P + pw) * 4, w);
-    *reinterpret_cast<float4 *>(T2 + ((cg * RZ + zb + zr) * PP + q) * 4) = a;
+  const unsigned ntask = (unsigned)(zc * PP);
+  if constexpr (P >= 14) {
+    for (unsigned t = tid; t < ntask; t += PL_THREADS) {
+      const unsigned zr = t / PP, q = t - zr * PP;
+      const unsigned ph = q / P, pw = q - ph * P;
+      const float4 w = *reinterpret_cast<const float4 *>(&T.yw[ph][0]);
+      const float *sp = T1 + ((zr * RY + T.yo[ph]) * P + pw) * 4;
+      float *d = T2 + ((zb + zr) * PP + q) * 4;
+      for (int cg = 0; cg < NG; ++cg) {
+        *reinterpret_cast<float4 *>(d) = taps4<NT, P * 4>(sp, w);
+        sp += rowsMax * P * 4, d += RZ * PP * 4;
+      }
+    }
+  } else {
+    const unsigned total = ntask * (unsigned)NG, m_nt = fast_magic(ntask);
+    for (unsigned e = tid; e < total; e += PL_THREADS) {
+      const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
+      const unsigned zr = t / PP, q = t - zr * PP;
+      const unsigned ph = q / P, pw = q - ph * P;
+      const float4 w = *reinterpret_cast<const float4 *>(&T.yw[ph][0]);
+      const float4 a = taps4<NT, P * 4>(T1 + ((cg * rowsMax + zr * RY + T.yo[ph]) * P + pw) * 4, w);
+      *reinterpret_cast<float4 *>(T2 + ((cg * RZ + zb + zr) * PP + q) * 4) = a;
+    }
   }
 }
 
@@ -198,18 +243,20 @@ __global__ void __launch_bounds__(256) roi_align3d_order_kernel(const RoiParams 
   order[rank] = k;
 }
 
-template <int P, bool CL>  // PW == PH == P; CL: channels-last levels
+template <int P, bool CL, int PDT>  // PW == PH == P; CL: channels-last levels; PDT: output depth (0 = p.PD at run time)
 __global__ void __launch_bounds__(PL_THREADS, 2)
     roi_align3d_fwd_planar_kernel(const RoiParams p, int CG, int ngroups, int smem_floats, const int *__restrict__ order) {
   extern __shared__ __align__(16) float planes[];
   __shared__ PlanarTables T;
   constexpr int PP = P * P;
   const int tid = threadIdx.x;
-  const int kslot = blockIdx.x / ngroups, g = blockIdx.x - kslot * ngroups;
+  // channel-group-major: the RoIs of one 64-channel group run together, so the part of the level they share (a quarter
+  // of a 256-channel level: L2-sized) is fetched from HBM once
+  const int g = blockIdx.x / p.K, kslot = blockIdx.x - g * p.K;
   const int k = order != nullptr ? __ldg(order + kslot) : kslot;
   const int c_first = g * CG;
   const int nch_all = min(CG, p.C - c_first);
-  const int PD = p.PD;
+  const int PD = PDT > 0 ? PDT : p.PD;
 
   // ---- RoI geometry (every thread), tap ranges (threads 0..47: axis = tid / 16, bin = tid % 16)
   float r[7];
@@ -224,7 +271,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2)
   const Axis axw = axis_setup(r[1], r[3], L.scale, P, p.sample_num);
   const Axis axh = axis_setup(r[2], r[4], L.scale, P, p.sample_num);
   const Axis axd = axis_setup(r[5], r[6], L.scale_d, PD, p.sample_num);
-  const long long out_elems = (long long)PD * PP;
+  const long long out_elems = PDT > 0 ? (long long)PDT * PP : (long long)PD * PP;   // a constant for PDT > 0: immediates
   float *out_roi = p.out + (krow * p.C + c_first) * out_elems;
   {
     const int axis = tid >> 4, bin = tid & 15;
@@ -347,7 +394,11 @@ __global__ void __launch_bounds__(PL_THREADS, 2)
       if (axis == 2) {
         const float inv = __frcp_rn((float)(axd.S * axh.S * axw.S));
         w0 *= inv, w1 *= inv, w2 *= inv, w3 *= inv;
-        T.nz[bin] = n;
+        if (n < 2 && RZ >= 2) {  // at least two slices per bin (weight 0 on the added one): see taps4_n
+          if (off + 1 >= RZ) off -= 1, w1 = w0, w0 = 0.0f;
+          n = 2;
+        }
+        T.nz[bin] = max(n, 1);   // a bin without a valid sample reads slice 0 with weight 0
       }
       int *po = axis == 0 ? T.xo : axis == 1 ? T.yo : T.zo;
       float(*pwt)[4] = axis == 0 ? T.xw : axis == 1 ? T.yw : T.zw;
@@ -383,9 +434,12 @@ __global__ void __launch_bounds__(PL_THREADS, 2)
       for (unsigned rr = tid; rr < per_ch; rr += PL_THREADS) {
         const unsigned row = fast_div(rr, npc, m_npc), pc = rr - row * npc;
         const unsigned z = fast_div(row, (unsigned)RY, m_ry), y = row - z * (unsigned)RY;
-        float *dst = dstbuf + row * RXB + pc * 4;
+        unsigned dst = (unsigned)__cvta_generic_to_shared(dstbuf + row * RXB + pc * 4);
         const float *src = src0 + (base0 + z * HW + y * W_ + pc * 4);
-        for (int c = 0; c < nch; ++c) cp_async16_pl(dst + c * szR, src + (size_t)c * (size_t)vox);
+        for (int c = 0; c < nch; ++c) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+          dst += (unsigned)szR * 4u, src += vox;
+        }
       }
     } else {
       // channels-last: four channels of a voxel per 16-byte copy, straight into the packed layout [group][row][x][4]
@@ -433,6 +487,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2)
     {
       float *oc = out_roi + (long long)c0 * out_elems;
       const int gT2 = RZ * PP * 4;
+      const bool full4 = (nch & 3) == 0, two = RZ >= 2;
       if constexpr (PP >= PL_THREADS / 2) {
         // wide outputs: a thread keeps its element and walks the channel groups (offsets / weights looked up once)
         for (int e = tid; e < PD * PP; e += PL_THREADS) {
@@ -441,14 +496,16 @@ __global__ void __launch_bounds__(PL_THREADS, 2)
           const float4 w = *reinterpret_cast<const float4 *>(&T.zw[pd][0]);
           const float *sp = T2 + (T.zo[pd] * PP + q) * 4;
           float *d = oc + e;
-          for (int cg = 0; cg < NG; ++cg) {
-            const float4 a = taps4_n<PP * 4>(n, sp, w);
-            const int left = nch - cg * 4;
-            __stcs(d, a.x);
-            if (left > 1) __stcs(d + out_elems, a.y);
-            if (left > 2) __stcs(d + 2 * out_elems, a.z);
-            if (left > 3) __stcs(d + 3 * out_elems, a.w);
-            sp += gT2, d += 4 * out_elems;
+          if (full4) {
+            for (int cg = 0; cg < NG; ++cg) {
+              store4<true>(d, out_elems, taps4_n<PP * 4>(n, two, sp, w), 4);
+              sp += gT2, d += 4 * out_elems;
+            }
+          } else {
+            for (int cg = 0; cg < NG; ++cg) {
+              store4<false>(d, out_elems, taps4_n<PP * 4>(n, two, sp, w), nch - cg * 4);
+              sp += gT2, d += 4 * out_elems;
+            }
           }
         }
       } else {
@@ -457,13 +514,10 @@ __global__ void __launch_bounds__(PL_THREADS, 2)
           const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
           const unsigned pd = t / PP, q = t - pd * PP;
           const float4 w = *reinterpret_cast<const float4 *>(&T.zw[pd][0]);
-          const float4 a = taps4_n<PP * 4>(T.nz[pd], T2 + ((cg * RZ + T.zo[pd]) * PP + q) * 4, w);
+          const float4 a = taps4_n<PP * 4>(T.nz[pd], two, T2 + ((cg * RZ + T.zo[pd]) * PP + q) * 4, w);
           float *d = oc + (long long)(cg * 4) * out_elems + t;
-          const int left = nch - (int)cg * 4;
-          __stcs(d, a.x);
-          if (left > 1) __stcs(d + out_elems, a.y);
-          if (left > 2) __stcs(d + 2 * out_elems, a.z);
-          if (left > 3) __stcs(d + 3 * out_elems, a.w);
+          if (full4) store4<true>(d, out_elems, a, 4);
+          else store4<false>(d, out_elems, a, nch - (int)cg * 4);
         }
       }
     }
@@ -491,16 +545,16 @@ bool fwd_planar_ok(const RoiParams &p, int layout) {
 int g_planar_smem_floats = 0;  // roi3d_set_tuning key 10: plane storage per CTA in floats (0 = default, two CTAs per SM)
 
 namespace {
-template <int P, bool CL>
+template <int P, bool CL, int PDT>
 int launch_planar_cfg(const RoiParams &p, int CG, int ngroups, long long blocks, const int *order, cudaStream_t st) {
   const int smem_floats = g_planar_smem_floats > 0 ? g_planar_smem_floats : PL_SMEM_FLOATS;
   const size_t smem = (size_t)smem_floats * sizeof(float);
   static size_t attr_set = 0;
   if (attr_set < smem) {
-    ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_planar_kernel<P, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_planar_kernel<P, CL, PDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = smem;
   }
-  roi_align3d_fwd_planar_kernel<P, CL><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, ngroups, smem_floats, order);
+  roi_align3d_fwd_planar_kernel<P, CL, PDT><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, ngroups, smem_floats, order);
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
 }
@@ -524,9 +578,14 @@ int launch_fwd_planar(RoiParams &p, int layout, cudaStream_t st) {
     roi_align3d_order_kernel<<<ceil_div(p.K, 256), 256, (size_t)p.K * sizeof(unsigned long long), st>>>(p, order);
     ROI3D_LAUNCH_CHECK();
   }
+  // output depths with their own instantiation (compile-time plane strides): the cubic shapes and the real config's
+  // 7 x 7 x 3 / 14 x 14 x 10 (configs/3d-multi-resolution-rcnn.py); any other depth runs with PD as a run-time value
   int rc;
-  if (p.PW == 7) rc = cl ? launch_planar_cfg<7, true>(p, CG, ngroups, blocks, order, st) : launch_planar_cfg<7, false>(p, CG, ngroups, blocks, order, st);
-  else rc = cl ? launch_planar_cfg<14, true>(p, CG, ngroups, blocks, order, st) : launch_planar_cfg<14, false>(p, CG, ngroups, blocks, order, st);
+#define ROI3D_PLANAR_GO(P_, PDT_) \
+  (cl ? launch_planar_cfg<P_, true, PDT_>(p, CG, ngroups, blocks, order, st) : launch_planar_cfg<P_, false, PDT_>(p, CG, ngroups, blocks, order, st))
+  if (p.PW == 7) rc = p.PD == 7 ? ROI3D_PLANAR_GO(7, 7) : p.PD == 3 ? ROI3D_PLANAR_GO(7, 3) : ROI3D_PLANAR_GO(7, 0);
+  else rc = p.PD == 14 ? ROI3D_PLANAR_GO(14, 14) : p.PD == 10 ? ROI3D_PLANAR_GO(14, 10) : ROI3D_PLANAR_GO(14, 0);
+#undef ROI3D_PLANAR_GO
   if (order != nullptr) ROI3D_CUDA(cudaFreeAsync(order, st));
   return rc;
 }

@@ -98,6 +98,9 @@ def to_channels_last_3d(x):
     return conv, True
 
 
+FORCE_NATIVE_NCDHW = [False]   # developer switch: always hand NCDHW levels to the planar kernel when it can read them
+
+
 def forward_inputs(feats, out_h, out_w):
     """Pick the memory the forward kernels read for a list of [B,C,D,H,W] levels: (tensors, layout flag).
     Channels-last levels go in as they are.  NCDHW-contiguous levels -- what the reference's callers hold
@@ -110,7 +113,7 @@ def forward_inputs(feats, out_h, out_w):
     # 7-wide outputs of 64-channel multiples: one conversion (HBM speed, reusable across the extractor calls of a pass,
     # see reuse_layout_conversions) + the streamed channels-last kernel beats the planar kernel (C2: 393 vs 418 us for
     # a single call, 150 vs 418 us per further call); everything else the planar kernel reads in place
-    if native and out_h == 7 and feats[0].shape[1] % 64 == 0:
+    if native and out_h == 7 and feats[0].shape[1] % 64 == 0 and not FORCE_NATIVE_NCDHW[0]:
         native = False
     if native:
         return list(feats), _lib.NCDHW

@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "3d-multi-resolution-rcnn_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import synth  # noqa: E402
-from roi3d_b200 import SingleRoIExtractor, _lib  # noqa: E402
+from roi3d_b200 import SingleRoIExtractor, _lib, _util  # noqa: E402
 from roi3d_b200.ops import RoIAlign3D  # noqa: E402
 
 dev = torch.device("cuda:0")
@@ -40,6 +40,8 @@ r_big = torch.from_numpy(synth.c2_rois(512, seed=2)).to(dev)
 big_nc = big.contiguous()
 ref = layer(big, r_big)
 print("C2 channels-last streamed: %.1f us" % timeit(lambda: layer(big, r_big)), flush=True)
+print("C2 NCDHW convert + streamed: %.1f us" % timeit(lambda: layer(big_nc, r_big)), flush=True)
+_util.FORCE_NATIVE_NCDHW[0] = True
 for sm in smem_opts:
     _lib.set_tuning(10, sm)
     got = layer(big_nc, r_big)

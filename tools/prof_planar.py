@@ -9,7 +9,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "3d-multi-resolution-rcnn_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import synth  # noqa: E402
-from roi3d_b200 import SingleRoIExtractor  # noqa: E402
+from roi3d_b200 import SingleRoIExtractor, _util  # noqa: E402
+_util.FORCE_NATIVE_NCDHW[0] = True
 from roi3d_b200.ops import RoIAlign3D  # noqa: E402
 
 dev = torch.device("cuda:0")
