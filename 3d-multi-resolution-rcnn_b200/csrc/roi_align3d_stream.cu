@@ -16,11 +16,14 @@
 //     -- into a four-slot shared-memory ring with cp.async.bulk.tensor (TMA, 5-D maps over the channels-last level
 //     [B][D][H][W][C], box = 64 channels x RXB voxels x {1,2,4,8} rows), one mbarrier per slot counting bytes; the
 //     item's plan record rides on the first tile's barrier as a plain bulk copy.
-//   * Warps 0..13 are bin owners: warp (ph, half) holds acc[pd][pw] for its output row ph and its 4 (or 3) pw bins of
-//     all PD slices in registers, lanes = channel pairs (packed FFMA2 arithmetic).  For every feature row of a tile
-//     that carries weight for ph it contracts the row along x (taps at warp-uniform offsets: LDS.64 + FFMA2), folds
-//     it into the slice partial with the y weight, and at the end of a z slice folds the partial into the pd bins
-//     that slice feeds.  Every row is read from HBM/L2 exactly once per item; owners never wait for each other.
+//   * Warps 0..13 are bin owners: warp (pw, half) holds acc[pd][ph] for its output column pw and 4 (or 3) output rows
+//     ph of all PD slices in registers, lanes = channel pairs (packed FFMA2 arithmetic).  For every feature row of a
+//     tile inside the y support of its output rows it contracts the row along x ONCE for its pw bin (taps at a
+//     warp-uniform offset: LDS.64 + FFMA2), folds the value into the slice partials of its output rows with the row's
+//     dense y weights (one broadcast LDS.128), and at the end of a z slice folds the partials into the pd bins that
+//     slice feeds.  (Owners used to be (ph, half of the pw bins): every row was then contracted by the ~2 output rows
+//     whose support holds it -- 1.75x the shared-memory reads and x-stage arithmetic.)  Every row is read from HBM/L2
+//     exactly once per item; owners never wait for each other.
 //   * At the end of an item the owners scale by 1 / count and write their bins into a shared-memory image of the
 //     item's [64 channels][PD*49] output block, which is contiguous in the [K, C, PD, PH, PW] output; warp 15 writes
 //     it back with ONE bulk store (cp.async.bulk.global.shared::cta) while the owners already work on the next item.
@@ -43,7 +46,7 @@ constexpr int ST_WARPS = 16;           // owners + producer + storer
 constexpr int ST_RMAX = 20;            // widest footprint box in x and y (voxels)
 constexpr int ST_RZMAX = 24;           // deepest footprint box
 constexpr int ST_CH = 64;              // channels per item
-constexpr int ST_XCLS = 10;            // box widths 2, 4, ..., 20 voxels
+constexpr int ST_XCLS = 20;            // box widths 1, 2, ..., 20 voxels
 constexpr int ST_YCLS = 4;             // box heights 1, 2, 4, 8 rows
 constexpr int ST_MAX_LEVELS = 4;
 constexpr int ST_SORT_MAX = 8192;      // RoIs ranked by footprint up to this K (identity order above)
@@ -70,6 +73,7 @@ struct alignas(16) StreamPlan {
   int yn[8];
   float yw[8][4];
   float zwd[ST_RZMAX][8];  // dense: weight of slice z (from z0) in bin pd
+  float ywd[ST_RMAX][8];   // dense: weight of row y (from y0) in bin ph
 };
 static_assert(sizeof(StreamPlan) % 16 == 0, "bulk copies move multiples of 16 bytes");
 constexpr int PLAN_BYTES = (int)sizeof(StreamPlan);
@@ -162,6 +166,9 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
                                                                int slot_bytes) {
   extern __shared__ float cost_s[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // programmatic dependent launch: the streamed kernel may be scheduled now; it waits (griddepcontrol.wait) for this
+  // grid to finish before it touches the plans or the counter
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
 
   // ---- footprint cost of every RoI (each CTA computes all of them: K is small), then the rank of this CTA's RoIs
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
   if (empty) slow = false;
   const bool x3 = !__any_sync(FULL, role == 0 && n > 3);
   const int NT = x3 ? 3 : 4;
-  const int RXB = max(4, (RX + 1) & ~1);  // box width: even, at least the NT taps of one bin
+  const int RXB = max(4, RX);  // box width: at least the NT taps of one bin
   // Tiling: consecutive (z, y) rows of the footprint, as many as fit a ring slot (one producer lane per row).
   const int rows_per_tile = min(ST_MAX_TILE_ROWS, slot_bytes / (RXB * ST_CH * 4));
   const bool stream = !empty && !slow;
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
     pl->flags = (empty ? PLAN_EMPTY : 0) | (slow ? PLAN_SLOW : 0) | (x3 ? PLAN_X3 : 0);
     pl->x0 = empty ? 0 : x0, pl->y0 = empty ? 0 : y0, pl->z0 = empty ? 0 : z0;
     pl->RX = RX, pl->RY = RY, pl->RZ = RZ, pl->RXB = RXB;
-    pl->rows_per_tile = rows_per_tile, pl->ntiles = ntiles, pl->nrows = nrows, pl->xcls = RXB / 2 - 1;
+    pl->rows_per_tile = rows_per_tile, pl->ntiles = ntiles, pl->nrows = nrows, pl->xcls = RXB - 1;
     // The reference divides by the sample count (roi_align_kernel.cu:288); 1/count is exact for the power-of-two
     // counts of fixed sample_num and within one ulp otherwise; count == 0 gives inf -> 0 * inf = NaN like its 0/0.
     pl->inv_count = __frcp_rn((float)(axd.S * axh.S * axw.S));
@@ -283,6 +290,13 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
     pl->yn[bin] = (n > 0 && stream) ? n : 0;
 #pragma unroll
     for (int t = 0; t < 4; ++t) pl->yw[bin][t] = (n > 0 && stream) ? w[t] : 0.0f;
+    const int yl = (n > 0 && stream) ? lo - y0 : 0;
+    for (int y = 0; y < ST_RMAX; ++y) {
+      const int t = y - yl;
+      float v = 0.0f;
+      if (n > 0 && stream && t >= 0 && t < n) v = t == 0 ? w[0] : t == 1 ? w[1] : t == 2 ? w[2] : w[3];
+      pl->ywd[y][bin] = v;
+    }
   } else if (role == 2) {
     const int zl = (n > 0 && stream) ? lo - z0 : 0;
     for (int z = 0; z < ST_RZMAX; ++z) {
@@ -297,11 +311,11 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
 // ---------------------------------------------------------------------------------------------------------------
 // Owner: literal evaluation of this owner's bins of a RoI the tap tables cannot express (rare).
 // ---------------------------------------------------------------------------------------------------------------
-template <int NB>
-__device__ __noinline__ void owner_literal(const RoiParams &p, int k, int lvl, int chunk, int ph, int pw0, int lane,
+template <int NPH>
+__device__ __noinline__ void owner_literal(const RoiParams &p, int k, int lvl, int chunk, int ph0, int pw, int lane,
                                            float *staging, int pdhw) {
   Item it;
-  it.k = k, it.krow = k, it.chunk = chunk, it.pd = 0, it.ph0 = ph, it.rows = 1, it.lvl = lvl;
+  it.k = k, it.krow = k, it.chunk = chunk, it.pd = 0, it.ph0 = ph0, it.rows = 1, it.lvl = lvl;
   float r[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
@@ -314,50 +328,54 @@ __device__ __noinline__ void owner_literal(const RoiParams &p, int k, int lvl, i
   const long long vox = (long long)it.L.D * it.L.H * it.L.W;
   const float *fb = it.L.feats + (long long)it.b * vox * p.C + chunk * ST_CH + lane * 2;
   for (int pd = 0; pd < p.PD; ++pd)
-    for (int j = 0; j < NB; ++j) {
+    for (int j = 0; j < NPH; ++j) {
       float v[2];
-      literal_bin_fwd<2>(it, fb, p.C, pd, ph, pw0 + j, v);
-      const int idx = pd * 49 + ph * 7 + pw0 + j;
+      literal_bin_fwd<2>(it, fb, p.C, pd, ph0 + j, pw, v);
+      const int idx = pd * 49 + (ph0 + j) * 7 + pw;
       staging[(2 * lane) * pdhw + idx] = v[0];
       staging[(2 * lane + 1) * pdhw + idx] = v[1];
     }
 }
 
-// x-contraction of one feature row for this owner's NB bins + fold into the slice partial with the y weight
-template <int NT, int NB>
-__device__ __forceinline__ void row_visit(const float *rowp, const int (&xo)[NB], const float (&xw)[NB][4], float wy,
-                                          float2 (&t2)[NB]) {
-  const float2 wy2 = make_float2(wy, wy);
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    const float *q = rowp + xo[j];
-    const float2 v0 = *reinterpret_cast<const float2 *>(q);
-    const float2 v1 = *reinterpret_cast<const float2 *>(q + ST_CH);
-    const float2 v2 = *reinterpret_cast<const float2 *>(q + 2 * ST_CH);
-    float2 x = __fmul2_rn(make_float2(xw[j][0], xw[j][0]), v0);
-    x = __ffma2_rn(make_float2(xw[j][1], xw[j][1]), v1, x);
-    x = __ffma2_rn(make_float2(xw[j][2], xw[j][2]), v2, x);
-    if constexpr (NT == 4) {
-      const float2 v3 = *reinterpret_cast<const float2 *>(q + 3 * ST_CH);
-      x = __ffma2_rn(make_float2(xw[j][3], xw[j][3]), v3, x);
-    }
-    t2[j] = __ffma2_rn(wy2, x, t2[j]);
+// x-contraction of one feature row for this owner's pw bin, then the fold into the slice partials of its NPH output rows
+// with the row's (dense) y weights: a row outside a bin's support has weight 0
+template <int NT, int NPH>
+__device__ __forceinline__ void row_visit(const float *q, const float (&xw)[4], const float *ywrow, float2 (&t2)[NPH]) {
+  const float2 v0 = *reinterpret_cast<const float2 *>(q);
+  const float2 v1 = *reinterpret_cast<const float2 *>(q + ST_CH);
+  const float2 v2 = *reinterpret_cast<const float2 *>(q + 2 * ST_CH);
+  const float4 wy = *reinterpret_cast<const float4 *>(ywrow);
+  float2 x = __fmul2_rn(make_float2(xw[0], xw[0]), v0);
+  x = __ffma2_rn(make_float2(xw[1], xw[1]), v1, x);
+  x = __ffma2_rn(make_float2(xw[2], xw[2]), v2, x);
+  if constexpr (NT == 4) {
+    const float2 v3 = *reinterpret_cast<const float2 *>(q + 3 * ST_CH);
+    x = __ffma2_rn(make_float2(xw[3], xw[3]), v3, x);
   }
+  t2[0] = __ffma2_rn(make_float2(wy.x, wy.x), x, t2[0]);
+  t2[1] = __ffma2_rn(make_float2(wy.y, wy.y), x, t2[1]);
+  t2[2] = __ffma2_rn(make_float2(wy.z, wy.z), x, t2[2]);
+  if constexpr (NPH == 4) t2[3] = __ffma2_rn(make_float2(wy.w, wy.w), x, t2[3]);
 }
 
 // All rows of one tile that carry weight for this owner; z fold at the end of every slice the tile completes.
 // The tile holds rows [y, y + nrows) of the footprint's (slice, row) sequence starting in slice z.
-template <int NT, int NB>
+template <int NT, int NPH>
 __device__ __forceinline__ void owner_tile(int nrows, int z, int y, int rowfloats, const StreamPlan *P, const float *tile,
-                                           int ph, int RY, int ylo, int yhi1, const int (&xo)[NB], const float (&xw)[NB][4],
-                                           float2 (&t2)[NB], float2 (&acc)[7][NB]) {
+                                           int ph0, int RY, int ylo, int yhi1, const float (&xw)[4], float2 (&t2)[NPH],
+                                           float2 (&acc)[7][NPH]) {
   int left = nrows;
   const float *rowp = tile;
-  const float *ywp = &P->yw[ph][0];
   while (left > 0) {
     const int seg = min(left, RY - y);
     const int ya = max(y, ylo), yb = min(y + seg, yhi1);
-    for (int yy = ya; yy < yb; ++yy) row_visit<NT, NB>(rowp + (yy - y) * rowfloats, xo, xw, ywp[yy - ylo], t2);
+    const float *q = rowp + (ya - y) * rowfloats;
+    const float *yw = &P->ywd[ya][ph0];
+#pragma unroll 2
+    for (int yy = ya; yy < yb; ++yy) {
+      row_visit<NT, NPH>(q, xw, yw, t2);
+      q += rowfloats, yw += 8;
+    }
     rowp += seg * rowfloats;
     y += seg, left -= seg;
     if (y == RY) {
@@ -369,22 +387,23 @@ __device__ __forceinline__ void owner_tile(int nrows, int z, int y, int rowfloat
         if (wz[pd] != 0.0f) {
           const float2 w2 = make_float2(wz[pd], wz[pd]);
 #pragma unroll
-          for (int j = 0; j < NB; ++j) acc[pd][j] = __ffma2_rn(w2, t2[j], acc[pd][j]);
+          for (int j = 0; j < NPH; ++j) acc[pd][j] = __ffma2_rn(w2, t2[j], acc[pd][j]);
         }
       }
 #pragma unroll
-      for (int j = 0; j < NB; ++j) t2[j] = make_float2(0.0f, 0.0f);
+      for (int j = 0; j < NPH; ++j) t2[j] = make_float2(0.0f, 0.0f);
       y = 0, ++z;
     }
   }
 }
 
-// Owner warp.  The first tile of an item carries the plan record (or the end-of-work mark); every tile has a descriptor
-// (rows, first slice / row) written by the producer before it arms the slot's barrier.
+// Owner warp (pw, half of the output rows): ph0 = 0 with NPH = 4 rows, or ph0 = 4 with NPH = 3.  The first tile of an
+// item carries the plan record (or the end-of-work mark); every tile has a descriptor (rows, first slice / row) written by
+// the producer before it arms the slot's barrier.
 // (Tried and dropped: letting an owner skip the wait for tiles that hold none of its rows -- slower, and a parity
 // wait can alias once a warp is more than one use of a slot ahead.)
-template <int NB, int NS, int SLOT>
-__device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *smem, int ph, int pw0, int warp, int lane) {
+template <int NPH, int NS, int SLOT>
+__device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *smem, int ph0, int pw, int warp, int lane) {
   using L = Lay<NS, SLOT>;
   const unsigned bar0 = s_u32(smem + L::BAR);
   const unsigned sfull = bar0 + 2 * NS * 8, sfree = sfull + 8;
@@ -401,29 +420,35 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
     const int pflags = P->flags;
     if (!(pflags & PLAN_SLOW)) {
       // ---- streamed item: acc lives in registers from the first tile to the epilogue
-      float2 acc[7][NB], t2[NB];
-      int xo[NB];
-      float xw[NB][4];
+      float2 acc[7][NPH], t2[NPH];
+      float xw[4];
 #pragma unroll
       for (int pd = 0; pd < 7; ++pd)
 #pragma unroll
-        for (int j = 0; j < NB; ++j) acc[pd][j] = make_float2(0.0f, 0.0f);
+        for (int j = 0; j < NPH; ++j) acc[pd][j] = make_float2(0.0f, 0.0f);
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        t2[j] = make_float2(0.0f, 0.0f);
-        xo[j] = P->xoff[pw0 + j] * ST_CH;
-        const float4 w4 = *reinterpret_cast<const float4 *>(&P->xw[pw0 + j][0]);
-        xw[j][0] = w4.x, xw[j][1] = w4.y, xw[j][2] = w4.z, xw[j][3] = w4.w;
+      for (int j = 0; j < NPH; ++j) t2[j] = make_float2(0.0f, 0.0f);
+      const int xo = P->xoff[pw] * ST_CH;
+      {
+        const float4 w4 = *reinterpret_cast<const float4 *>(&P->xw[pw][0]);
+        xw[0] = w4.x, xw[1] = w4.y, xw[2] = w4.z, xw[3] = w4.w;
       }
-      const int RY = P->RY, ylo = P->ylo[ph], yhi1 = ylo + P->yn[ph];
+      // rows with weight for any of this owner's output rows
+      const int RY = P->RY;
+      int ylo = RY, yhi1 = 0;
+#pragma unroll
+      for (int j = 0; j < NPH; ++j) {
+        const int n = P->yn[ph0 + j], lo = P->ylo[ph0 + j];
+        if (n > 0) ylo = min(ylo, lo), yhi1 = max(yhi1, lo + n);
+      }
       TileDesc dt = d;
       for (;;) {  // tiles of the item
         if (dt.nrows > 0 && !(a.debug & 1)) {
-          const float *tile = reinterpret_cast<const float *>(smem + L::RING + slot * SLOT) + lane * 2;
+          const float *tile = reinterpret_cast<const float *>(smem + L::RING + slot * SLOT) + lane * 2 + xo;
           if (pflags & PLAN_X3)
-            owner_tile<3, NB>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph, RY, ylo, yhi1, xo, xw, t2, acc);
+            owner_tile<3, NPH>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph0, RY, ylo, yhi1, xw, t2, acc);
           else
-            owner_tile<4, NB>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph, RY, ylo, yhi1, xo, xw, t2, acc);
+            owner_tile<4, NPH>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph0, RY, ylo, yhi1, xw, t2, acc);
         }
         ++tile_seq;
         if (dt.flags & TILE_LAST) break;
@@ -437,15 +462,15 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
       st_mbar_wait(sfree, (item_seq & 1) ^ 1);
       const float inv = P->inv_count;
       const float2 inv2 = make_float2(inv, inv);
-      float *s0 = staging + (2 * lane) * pdhw + ph * 7 + pw0;
+      float *s0 = staging + (2 * lane) * pdhw + ph0 * 7 + pw;
 #pragma unroll
       for (int pd = 0; pd < 7; ++pd) {
         if (pd * 49 < pdhw) {
 #pragma unroll
-          for (int j = 0; j < NB; ++j) {
+          for (int j = 0; j < NPH; ++j) {
             const float2 v = __fmul2_rn(acc[pd][j], inv2);
-            s0[pd * 49 + j] = v.x;
-            s0[pdhw + pd * 49 + j] = v.y;
+            s0[pd * 49 + j * 7] = v.x;
+            s0[pdhw + pd * 49 + j * 7] = v.y;
           }
         }
       }
@@ -453,7 +478,7 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
       // ---- literal item (one descriptor-only tile)
       ++tile_seq;
       st_mbar_wait(sfree, (item_seq & 1) ^ 1);
-      owner_literal<NB>(a.p, P->k, P->lvl, d.chunk, ph, pw0, lane, staging, pdhw);
+      owner_literal<NPH>(a.p, P->k, P->lvl, d.chunk, ph0, pw, lane, staging, pdhw);
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the bulk store
     if (warp == 0 && lane == 0) {
@@ -592,10 +617,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) roi_align3d_fwd_stream_kerne
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
+  // launched as a programmatic dependent of the plan kernel: everything above overlapped with it
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
   if (warp < ST_OWNERS) {
-    if (warp < 7) owner_loop<4, NS, SLOT>(a, smem, warp, 0, warp, lane);
-    else owner_loop<3, NS, SLOT>(a, smem, warp - 7, 4, warp, lane);
+    if (warp < 7) owner_loop<4, NS, SLOT>(a, smem, 0, warp, warp, lane);
+    else owner_loop<3, NS, SLOT>(a, smem, 4, warp - 7, warp, lane);
     return;
   }
   if (warp == ST_OWNERS) {
@@ -673,7 +700,7 @@ int level_maps(const LevelDev &L, int B, int C, const CUtensorMap **out) {
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   for (int xc = 0; xc < ST_XCLS; ++xc)
     for (int yc = 0; yc < ST_YCLS; ++yc) {
-      const cuuint32_t box[5] = {(cuuint32_t)ST_CH, (cuuint32_t)(2 * (xc + 1)), (cuuint32_t)(1 << yc), 1, 1};
+      const cuuint32_t box[5] = {(cuuint32_t)ST_CH, (cuuint32_t)(xc + 1), (cuuint32_t)(1 << yc), 1, 1};
       const CUresult r = enc(&host[xc * ST_YCLS + yc], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(L.feats),
                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -768,7 +795,15 @@ int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count)
     attr_set = true;
   }
   const int grid = a.total_items < sm_count ? a.total_items : sm_count;
-  roi_align3d_fwd_stream_kernel<NS, SLOT><<<grid, ST_WARPS * 32, L::LAUNCH, st>>>(a);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(ST_WARPS * 32), cfg.dynamicSmemBytes = L::LAUNCH, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    ROI3D_CUDA(cudaLaunchKernelEx(&cfg, roi_align3d_fwd_stream_kernel<NS, SLOT>, a));
+  }
   ROI3D_LAUNCH_CHECK();
   ROI3D_CUDA(cudaFreeAsync(ws, st));
   return ROI3D_OK;

@@ -47,7 +47,7 @@ rs[:, 2] = rs[:, 2] % (256 - 66); rs[:, 4] = rs[:, 2] + h
 rs[:, 5] = rs[:, 5] % 4; rs[:, 6] = rs[:, 5] + d
 r_small = torch.from_numpy(rs).to(dev)
 for name, f, r, fl in (("HBM-sized map", big, r_big, True), ("L2-resident map", small, r_small, False)):
-    for dbg in (0, 4, 3, 7):
+    for dbg in (0, 1, 2, 3):
         _lib.set_tuning(9, dbg)
         t = timeit(lambda: layer(f, r), flush=fl)
         print("%s debug=%d (1: no arithmetic, 2: no store, 4: roi-major item order): %.1f us" % (name, dbg, t), flush=True)
