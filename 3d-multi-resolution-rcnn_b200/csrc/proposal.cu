@@ -35,7 +35,20 @@ struct SegDesc {
 
 struct SegTable {
   SegDesc s[kMaxSeg];
+  // flat grids of the full passes over long segments: segment i owns CTAs [cta0[i], cta0[i + 1]) of kFirstItemsPerCta
+  // elements each (none for a segment that the tail kernel finishes alone)
+  unsigned cta0[kMaxSeg + 1];
 };
+
+// CTA index of a flat grid -> its segment (binary search over the <= 64 prefix sums in the kernel parameters)
+__device__ __forceinline__ int flat_segment(const SegTable &tab, unsigned cta) {
+  int lo = 0, hi = kMaxSeg;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tab.cta0[mid] <= cta) lo = mid; else hi = mid;
+  }
+  return lo;
+}
 
 struct SegState {           // device, per segment
   unsigned long long prefix;  // key bits decided so far (left-aligned value of the decided digits)
@@ -86,24 +99,27 @@ __device__ __forceinline__ void scan_segment(unsigned *__restrict__ hist, SegSta
   unsigned *g = hist + (long long)seg * kBins;
   __shared__ unsigned part[256];
   __shared__ int s_digit, s_krem;
+  const bool act = threadIdx.x < 256;   // CTAs larger than 256 threads: the rest only keep the barriers company
   // thread t owns bins [8t, 8t+8) ; descending order means high bins first
   unsigned loc[8], sum = 0;
+  if (act) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    loc[i] = __ldcg(g + threadIdx.x * 8 + i);  // written by other CTAs' atomics: read through L2
-    sum += loc[i];
-    g[threadIdx.x * 8 + i] = 0;  // leave the histogram clean for the next pass
+    for (int i = 0; i < 8; ++i) {
+      loc[i] = __ldcg(g + threadIdx.x * 8 + i);  // written by other CTAs' atomics: read through L2
+      sum += loc[i];
+      g[threadIdx.x * 8 + i] = 0;  // leave the histogram clean for the next pass
+    }
+    part[threadIdx.x] = sum;
   }
-  part[threadIdx.x] = sum;
   __syncthreads();
   // suffix sum over threads above me (256 entries; simple serial-in-smem log scan)
   for (int o = 1; o < 256; o <<= 1) {
-    unsigned v = (threadIdx.x + o < 256) ? part[threadIdx.x + o] : 0u;
+    unsigned v = (act && threadIdx.x + o < 256) ? part[threadIdx.x + o] : 0u;
     __syncthreads();
-    part[threadIdx.x] += v;
+    if (act) part[threadIdx.x] += v;
     __syncthreads();
   }
-  const unsigned above = part[threadIdx.x] - sum;  // keys in bins strictly above my 8 bins
+  const unsigned above = act ? part[threadIdx.x] - sum : 0u;  // keys in bins strictly above my 8 bins
   if (pass == 0) {
     // the first histogram counts every element that takes part: a masked segment learns its effective length here
     const unsigned total = part[0];
@@ -116,7 +132,7 @@ __device__ __forceinline__ void scan_segment(unsigned *__restrict__ hist, SegSta
     if (threadIdx.x == 0) state[seg] = st;
     return;
   }
-  if (above < k && above + sum >= k) {
+  if (act && above < k && above + sum >= k) {
     unsigned cum = above;
     for (int i = 7; i >= 0; --i) {
       if (cum + loc[i] >= k) {
@@ -144,16 +160,17 @@ constexpr int kBndCap = 4096;  // boundary keys kept per segment after two digit
 // keys (optional u32 buffer, one entry per score): digit pass 0 stores every element's order-preserving key there (0 =
 // the element does not take part: masked out), so that the sigmoid, the mask lookup and the HBM read happen ONCE; the
 // later full passes (digit pass 1, the split, and the rare overflow passes) read the keys back from L2.
-// Bin counts are aggregated per warp (__match_any_sync) before they touch shared memory: sigmoid scores crowd into a
-// handful of exponent bins, which would serialise the shared-memory atomics 32-fold.
+// Digit pass 0 of a full segment runs in topk_first_kernel (lane-private counters); this kernel takes the later passes.
 template <bool SIGMOID>
 __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__restrict__ scores, const SegTable tab,
                                                                  const SegState *__restrict__ state, int pass,
                                                                  unsigned *__restrict__ hist /*[nseg][kBins]*/,
                                                                  const unsigned long long *__restrict__ bnd,
-                                                                 int *__restrict__ tickets, unsigned *__restrict__ keys) {
+                                                                 int *__restrict__ tickets, unsigned *__restrict__ keys,
+                                                                 unsigned small_max) {
   const int seg = blockIdx.y;
   const SegDesc d = tab.s[seg];
+  if (d.len <= small_max) return;   // (0 when the tail kernel is not in use: k > kBitonicMax)
   const SegState st = state[seg];
   const bool use_b = bnd != nullptr && st.bnd_count <= kBndCap;
   const long long len = use_b ? (long long)st.bnd_count : (long long)d.len;
@@ -170,11 +187,19 @@ __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__
   const float *src = scores + d.off;
   const unsigned long long *bsrc = bnd + (long long)seg * kBndCap;
   unsigned *kbuf = keys != nullptr ? keys + d.koff : nullptr;
-  const unsigned lane = threadIdx.x & 31u;
   // grid-stride over the segment: the boundary passes are launched with a few CTAs per segment (the usual case
   // needs one); a segment that overflowed the boundary buffer is then walked by those few CTAs
-  for (long long base = (long long)blockIdx.x * kItemsPerCta; base < len; base += (long long)gridDim.x * kItemsPerCta)
-#pragma unroll 4
+  const bool from_keys = !use_b && kbuf != nullptr && pass > 0;
+  for (long long base = (long long)blockIdx.x * kItemsPerCta; base < len; base += (long long)gridDim.x * kItemsPerCta) {
+  unsigned kpre[kItemsPerThread];   // key-buffer passes: all of a thread's loads are issued before the first atomic
+  if (from_keys) {
+#pragma unroll
+    for (int it = 0; it < kItemsPerThread; ++it) {
+      const long long m = base + (long long)it * kTopkThreads + threadIdx.x;
+      kpre[it] = m < len ? __ldg(kbuf + m) : 0u;
+    }
+  }
+#pragma unroll
   for (int it = 0; it < kItemsPerThread; ++it) {
     const long long m = base + (long long)it * kTopkThreads + threadIdx.x;
     unsigned bin = 0xFFFFFFFFu;  // no contribution
@@ -184,8 +209,8 @@ __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__
       if (use_b) {
         const unsigned long long key = bsrc[m];
         kh = (unsigned)(key >> 32), kl_b = (unsigned)key;
-      } else if (kbuf != nullptr && pass > 0) {
-        kh = __ldg(kbuf + m);
+      } else if (from_keys) {
+        kh = kpre[it];
         take = kh != 0u;
       } else {
         take = d.mask == nullptr || __ldg(d.mask + logical_index(d, (unsigned)m)) != 0;
@@ -209,9 +234,8 @@ __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__
         }
       }
     }
-    // one shared-memory atomic per distinct bin of the warp
-    const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    if (bin != 0xFFFFFFFFu && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+    if (bin != 0xFFFFFFFFu) atomicAdd(&h[bin], 1u);
+  }
   }
   __syncthreads();
   unsigned *g = hist + (long long)seg * kBins;
@@ -233,6 +257,219 @@ __global__ void __launch_bounds__(kTopkThreads) topk_hist_kernel(const float *__
   if (s_last) {
     __threadfence();
     scan_segment(hist, const_cast<SegState *>(state), seg, pass);
+  }
+}
+
+// Digit pass 0 over whole segments.  Sigmoid scores crowd into a handful of exponent bins (half of them share ONE
+// 11-bit prefix), which serialises shared-memory atomics on a common histogram up to 32-fold.  Here every lane counts
+// in its own 16-bit counter: table [bin][16 words], lanes 2j / 2j+1 share word j (low / high half), so an atomic
+// instruction never meets more than a two-way conflict, whatever the distribution.  A (bin, lane) counter sees at
+// most kFirstItemsPerThread * 16 warps = 1024 increments.  The pass also stores every element's order-preserving key
+// (0 = masked out) when a key buffer is given, 16 bytes per thread and load.
+constexpr int kFirstThreads = 1024;
+constexpr int kFirstItemsPerThread = 32;
+constexpr int kFirstItemsPerCta = kFirstThreads * kFirstItemsPerThread;
+constexpr int kFirstSmemBytes = kBins * 16 * 4;
+
+template <bool SIGMOID>
+__device__ __forceinline__ unsigned first_key(const SegDesc &d, unsigned m, float v) {
+  const bool take = d.mask == nullptr || __ldg(d.mask + logical_index(d, m)) != 0;
+  if (SIGMOID) v = sigmoid_ref(v);
+  return take ? okey(v) : 0u;
+}
+
+// last CTA of a segment's flat range runs the scan (no separate launch)
+__device__ __forceinline__ void flat_finish(const SegTable &tab, int seg, unsigned *hist, SegState *state, int *tickets, int pass,
+                                            int ctas_per_chunk = 1) {
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const int nct = (int)(tab.cta0[seg + 1] - tab.cta0[seg]) * ctas_per_chunk;
+    s_last = atomicAdd(&tickets[seg], 1) == nct - 1;
+    if (s_last) tickets[seg] = 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    scan_segment(hist, state, seg, pass);
+  }
+}
+
+template <bool SIGMOID>
+__global__ void __launch_bounds__(kFirstThreads, 1) topk_first_kernel(const float *__restrict__ scores, const SegTable tab,
+                                                                      SegState *__restrict__ state, unsigned *__restrict__ hist,
+                                                                      int *__restrict__ tickets, unsigned *__restrict__ keys) {
+  extern __shared__ __align__(16) unsigned ftab[];   // [kBins][16]
+  const int seg = flat_segment(tab, blockIdx.x);
+  const SegDesc d = tab.s[seg];
+  const unsigned len = d.len;
+  const unsigned base = (blockIdx.x - tab.cta0[seg]) * (unsigned)kFirstItemsPerCta;
+  for (int i = threadIdx.x; i < kBins * 4; i += kFirstThreads) reinterpret_cast<uint4 *>(ftab)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  const float *src = scores + d.off;
+  unsigned *kbuf = keys != nullptr ? keys + d.koff : nullptr;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned inc = (lane & 1u) ? 0x10000u : 1u;
+  unsigned *col = ftab + (lane >> 1);
+  const bool vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0;   // (the key buffer's segments are 16-byte aligned)
+  if (vec) {
+    constexpr int NB = 4;   // 16-byte loads in flight per thread: issued together, then scored
+#pragma unroll 1
+    for (int it0 = 0; it0 < kFirstItemsPerThread / 4; it0 += NB) {
+      float4 v[NB];
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const unsigned m = base + ((unsigned)(it0 + u) * kFirstThreads + threadIdx.x) * 4u;
+        v[u] = m + 4u <= len ? __ldcs(reinterpret_cast<const float4 *>(src + m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const unsigned m = base + ((unsigned)(it0 + u) * kFirstThreads + threadIdx.x) * 4u;
+        if (m + 4u <= len) {
+          uint4 kk;
+          kk.x = first_key<SIGMOID>(d, m, v[u].x), kk.y = first_key<SIGMOID>(d, m + 1, v[u].y);
+          kk.z = first_key<SIGMOID>(d, m + 2, v[u].z), kk.w = first_key<SIGMOID>(d, m + 3, v[u].w);
+          if (kbuf != nullptr) *reinterpret_cast<uint4 *>(kbuf + m) = kk;
+          if (kk.x) atomicAdd(col + (kk.x >> 21) * 16, inc);
+          if (kk.y) atomicAdd(col + (kk.y >> 21) * 16, inc);
+          if (kk.z) atomicAdd(col + (kk.z >> 21) * 16, inc);
+          if (kk.w) atomicAdd(col + (kk.w >> 21) * 16, inc);
+        } else {
+          for (unsigned mm = m; mm < len; ++mm) {
+            const unsigned kh = first_key<SIGMOID>(d, mm, __ldg(src + mm));
+            if (kbuf != nullptr) kbuf[mm] = kh;
+            if (kh) atomicAdd(col + (kh >> 21) * 16, inc);
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int it = 0; it < kFirstItemsPerThread; ++it) {
+      const unsigned m = base + (unsigned)it * kFirstThreads + threadIdx.x;
+      if (m < len) {
+        const unsigned kh = first_key<SIGMOID>(d, m, __ldg(src + m));
+        if (kbuf != nullptr) kbuf[m] = kh;
+        if (kh) atomicAdd(col + (kh >> 21) * 16, inc);
+      }
+    }
+  }
+  __syncthreads();
+  unsigned *g = hist + (long long)seg * kBins;
+  for (int b = threadIdx.x; b < kBins; b += kFirstThreads) {
+    const uint4 *row = reinterpret_cast<const uint4 *>(ftab + b * 16);
+    unsigned c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 w = row[q];
+      c += (w.x & 0xFFFFu) + (w.x >> 16) + (w.y & 0xFFFFu) + (w.y >> 16) + (w.z & 0xFFFFu) + (w.z >> 16) + (w.w & 0xFFFFu) +
+           (w.w >> 16);
+    }
+    if (c) atomicAdd(&g[b], c);
+  }
+  flat_finish(tab, seg, hist, state, tickets, 0);
+}
+
+// Digit pass 1 and the split pass in their key-buffer form: one u32 load per element, flat grid, every load of a batch
+// issued before the first atomic.  (The generic kernels above remain for callers without a key buffer and k > kBitonicMax.)
+constexpr int kKeyThreads = 256;
+constexpr int kKeyBatch = 16;
+constexpr int kKeySub = 4;   // CTAs per chunk of kFirstItemsPerCta keys: short CTAs, ten per SM, hide the load latency
+constexpr int kKeyItemsPerCta = kFirstItemsPerCta / kKeySub;
+
+__global__ void __launch_bounds__(kKeyThreads) topk_second_kernel(const SegTable tab, SegState *__restrict__ state,
+                                                                  unsigned *__restrict__ hist, int *__restrict__ tickets,
+                                                                  const unsigned *__restrict__ keys) {
+  __shared__ unsigned h[kBins];
+  const unsigned chunk = blockIdx.x / kKeySub, sub = blockIdx.x - chunk * kKeySub;
+  const int seg = flat_segment(tab, chunk);
+  const SegDesc d = tab.s[seg];
+  const unsigned top11 = (unsigned)(state[seg].prefix >> 53);
+  const bool live = state[seg].k_take > 0;
+  for (int i = threadIdx.x; i < kBins; i += kKeyThreads) h[i] = 0;
+  __syncthreads();
+  const unsigned *kb = keys + d.koff;
+  const unsigned base = (chunk - tab.cta0[seg]) * (unsigned)kFirstItemsPerCta + sub * (unsigned)kKeyItemsPerCta;
+  const unsigned end = min(d.len, base + (unsigned)kKeyItemsPerCta);
+  if (live) {
+    for (unsigned m0 = base + threadIdx.x; m0 < end; m0 += kKeyThreads * kKeyBatch) {
+      unsigned kk[kKeyBatch];
+#pragma unroll
+      for (int u = 0; u < kKeyBatch; ++u) {
+        const unsigned m = m0 + u * kKeyThreads;
+        kk[u] = m < end ? __ldg(kb + m) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < kKeyBatch; ++u)
+        if (kk[u] != 0u && (kk[u] >> 21) == top11) atomicAdd(&h[(kk[u] >> 10) & 0x7FFu], 1u);
+    }
+  }
+  __syncthreads();
+  unsigned *g = hist + (long long)seg * kBins;
+  for (int i = threadIdx.x; i < kBins; i += kKeyThreads) {
+    const unsigned c = h[i];
+    if (c) atomicAdd(&g[i], c);
+  }
+  flat_finish(tab, seg, hist, state, tickets, 1, kKeySub);
+}
+
+constexpr int kSplitStage = 1024;   // selected keys a CTA stages before it reserves their slots with one atomic per list
+__global__ void __launch_bounds__(kKeyThreads) topk_split_keys_kernel(const SegTable tab, SegState *__restrict__ state, int k,
+                                                                      unsigned long long *__restrict__ cand,
+                                                                      unsigned long long *__restrict__ bnd,
+                                                                      const unsigned *__restrict__ keys) {
+  __shared__ unsigned long long stage[2][kSplitStage];   // [0]: above the boundary bin, [1]: inside it
+  __shared__ int s_n[2], s_base[2];
+  const unsigned chunk = blockIdx.x / kKeySub, sub = blockIdx.x - chunk * kKeySub;
+  const int seg = flat_segment(tab, chunk);
+  const SegDesc d = tab.s[seg];
+  if (state[seg].k_take <= 0) return;
+  const unsigned p22 = (unsigned)(state[seg].prefix >> 42);  // the 22 decided bits
+  const unsigned *kb = keys + d.koff;
+  const unsigned base = (chunk - tab.cta0[seg]) * (unsigned)kFirstItemsPerCta + sub * (unsigned)kKeyItemsPerCta;
+  const unsigned end = min(d.len, base + (unsigned)kKeyItemsPerCta);
+  if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
+  __syncthreads();
+  for (unsigned m0 = base + threadIdx.x; m0 < end; m0 += kKeyThreads * kKeyBatch) {
+    unsigned kk[kKeyBatch];
+#pragma unroll
+    for (int u = 0; u < kKeyBatch; ++u) {
+      const unsigned m = m0 + u * kKeyThreads;
+      kk[u] = m < end ? __ldg(kb + m) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kKeyBatch; ++u) {
+      const unsigned h22 = kk[u] >> 10;
+      if (kk[u] != 0u && h22 >= p22) {
+        const unsigned li = logical_index(d, m0 + u * kKeyThreads);
+        const unsigned long long key = ((unsigned long long)kk[u] << 32) | (unsigned)~li;
+        const int which = h22 > p22 ? 0 : 1;
+        const int pos = atomicAdd(&s_n[which], 1);
+        if (pos < kSplitStage) {
+          stage[which][pos] = key;
+        } else if (which == 0) {   // staging full (a CTA rarely holds this many): straight to the lists
+          const int gp = atomicAdd(&state[seg].cand_count, 1);
+          if (gp < k) cand[(long long)seg * k + gp] = key;
+        } else {
+          const int gp = atomicAdd(&state[seg].bnd_count, 1);
+          if (gp < kBndCap) bnd[(long long)seg * kBndCap + gp] = key;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int n = min(s_n[threadIdx.x], kSplitStage);
+    s_base[threadIdx.x] = n > 0 ? atomicAdd(threadIdx.x == 0 ? &state[seg].cand_count : &state[seg].bnd_count, n) : 0;
+  }
+  __syncthreads();
+  for (int which = 0; which < 2; ++which) {
+    const int n = min(s_n[which], kSplitStage), gb = s_base[which];
+    const int cap = which == 0 ? k : kBndCap;
+    unsigned long long *dst = which == 0 ? cand + (long long)seg * k : bnd + (long long)seg * kBndCap;
+    for (int i = threadIdx.x; i < n; i += kKeyThreads)
+      if (gb + i < cap) dst[gb + i] = stage[which][i];
   }
 }
 
@@ -291,22 +528,30 @@ __global__ void __launch_bounds__(kTopkThreads) topk_split_kernel(const float *_
                                                                   SegState *__restrict__ state, int k,
                                                                   unsigned long long *__restrict__ cand,
                                                                   unsigned long long *__restrict__ bnd,
-                                                                  const unsigned *__restrict__ keys) {
+                                                                  const unsigned *__restrict__ keys, unsigned small_max) {
   const int seg = blockIdx.y;
   const SegDesc d = tab.s[seg];
   const long long base = (long long)blockIdx.x * kItemsPerCta;
-  if (base >= (long long)d.len) return;
+  if (base >= (long long)d.len || d.len <= small_max) return;
   const SegState st = state[seg];
   if (st.k_take <= 0) return;
   const unsigned p22 = (unsigned)(st.prefix >> 42);  // the 22 decided bits
   const float *src = scores + d.off;
-#pragma unroll 4
+  unsigned kpre[kItemsPerThread];   // key-buffer form: all loads first
+  if (keys != nullptr) {
+#pragma unroll
+    for (int it = 0; it < kItemsPerThread; ++it) {
+      const long long m = base + (long long)it * kTopkThreads + threadIdx.x;
+      kpre[it] = m < (long long)d.len ? __ldg(keys + d.koff + m) : 0u;
+    }
+  }
+#pragma unroll
   for (int it = 0; it < kItemsPerThread; ++it) {
     const long long m = base + (long long)it * kTopkThreads + threadIdx.x;
     if (m < (long long)d.len) {
       unsigned kh;
       if (keys != nullptr) {
-        kh = __ldg(keys + d.koff + m);
+        kh = kpre[it];
         if (kh == 0u) continue;
       } else {
         float v = __ldg(src + m);
@@ -406,6 +651,268 @@ __global__ void __launch_bounds__(1024) topk_bitonic_kernel(const unsigned long 
     if (by_index) v = ((unsigned long long)(unsigned)v << 32) | (v >> 32);
     out_idx[(long long)seg * k + i] = (int64_t)(unsigned)~(unsigned)v;
     out_val[(long long)seg * k + i] = okey_inv((unsigned)(v >> 32));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tail of the selection, ONE launch, one CTA per segment (k <= kBitonicMax): what used to be four digit passes over
+// the boundary buffer, the collect pass, the final sort and the report -- seven launches of ~10 us each, all of it
+// latency (a few global round trips per launch), for a few dozen boundary keys.
+//   * a segment of at most kSmallMax elements never enters the digit passes: the CTA scores it, sorts it in shared
+//     memory and writes the result (the final `topk(max_num)` over 5 x 1000 rows per image is this case);
+//   * otherwise the boundary keys the split pass put aside are sorted and the k_rem largest join the certain keys;
+//   * a boundary bin that overflowed its buffer (mass ties) is resolved by this CTA alone with the remaining digit
+//     passes over the whole segment -- slow, and only for degenerate inputs.
+// Rows past a segment's count are filled with -1 / 0 here (no separate fills of the outputs).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallMax = 8192;
+constexpr int kTailThreads = 1024;
+constexpr int kTailSmemBytes = kSmallMax * 8 + 4096 * 8 + kBins * 4;   // keys, selected keys (k <= kBitonicMax), histogram
+
+template <bool SIGMOID>
+__device__ __forceinline__ unsigned long long tail_key64(const SegDesc &d, const float *src, const unsigned *kbuf, unsigned m) {
+  const unsigned li = logical_index(d, m);
+  unsigned kh;
+  if (kbuf != nullptr) {
+    kh = __ldg(kbuf + m);
+  } else {
+    const bool take = d.mask == nullptr || __ldg(d.mask + li) != 0;
+    float v = __ldg(src + m);
+    if (SIGMOID) v = sigmoid_ref(v);
+    kh = take ? okey(v) : 0u;
+  }
+  return kh != 0u ? (((unsigned long long)kh << 32) | (unsigned)~li) : 0ULL;
+}
+
+__device__ __forceinline__ int pow2_at_least(int n) {
+  int p = 2;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// descending bitonic sort of sk[0, npow2) by the whole CTA; ends with a barrier.  A thread's (up to four) compare-
+// exchanges of a stage are independent: all loads are issued before the first store (the stage is latency-bound)
+__device__ __forceinline__ void tail_bitonic(unsigned long long *sk, int npow2, int tid) {
+  const int half = npow2 >> 1;
+  for (int size = 2; size <= npow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t0 = tid; t0 < half; t0 += 4 * kTailThreads) {
+        unsigned long long a[4], b[4];
+        int lo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + u * kTailThreads;
+          lo[u] = 2 * t - (t & (stride - 1));
+          if (t < half) a[u] = sk[lo[u]], b[u] = sk[lo[u] + stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + u * kTailThreads;
+          if (t < half) {
+            const bool desc = (lo[u] & size) == 0;
+            if (desc ? (a[u] < b[u]) : (a[u] > b[u])) sk[lo[u]] = b[u], sk[lo[u] + stride] = a[u];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long swap_words(unsigned long long v) {
+  return ((unsigned long long)(unsigned)v << 32) | (v >> 32);
+}
+
+// The need-th largest of the non-zero keys sk[0, n) (need <= their count): MSB-first 11/11/10-bit digits like the global
+// passes, histogram and scan in shared memory.  Stops as soon as a digit's bin holds exactly what is still needed (the
+// returned threshold then has its undecided bits clear): every key >= the result is selected, and there are `need` of them.
+__device__ __forceinline__ unsigned long long tail_select(const unsigned long long *sk, int n, int need, unsigned *h, int tid) {
+  __shared__ unsigned part[256];
+  __shared__ int s_digit, s_need, s_done;
+  unsigned long long prefix = 0ULL;
+  for (int pass = 0; pass < 6; ++pass) {
+    int shift, bits;
+    pass_geometry(pass, shift, bits);
+    const int decided = 64 - shift - bits;
+    for (int i = tid; i < kBins; i += kTailThreads) h[i] = 0u;
+    __syncthreads();
+    for (int i = tid; i < n; i += kTailThreads) {
+      const unsigned long long key = sk[i];
+      if (key != 0ULL && (decided == 0 || (key >> (64 - decided)) == (prefix >> (64 - decided))))
+        atomicAdd(&h[(unsigned)(key >> shift) & ((1u << bits) - 1u)], 1u);
+    }
+    __syncthreads();
+    const bool act = tid < 256;   // thread t owns bins [8t, 8t + 8); descending order: high bins first
+    unsigned loc[8], sum = 0;
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) loc[i] = h[tid * 8 + i], sum += loc[i];
+      part[tid] = sum;
+    }
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+      const unsigned v = (act && tid + o < 256) ? part[tid + o] : 0u;
+      __syncthreads();
+      if (act) part[tid] += v;
+      __syncthreads();
+    }
+    const unsigned above = act ? part[tid] - sum : 0u;
+    if (act && above < (unsigned)need && above + sum >= (unsigned)need) {
+      unsigned cum = above;
+      for (int i = 7; i >= 0; --i) {
+        if (cum + loc[i] >= (unsigned)need) {
+          s_digit = tid * 8 + i;
+          s_need = need - (int)cum;
+          s_done = loc[i] == (unsigned)need - cum;
+          break;
+        }
+        cum += loc[i];
+      }
+    }
+    __syncthreads();
+    prefix |= (unsigned long long)(unsigned)s_digit << shift;
+    need = s_need;
+    const int done = s_done;
+    __syncthreads();
+    if (done) break;
+  }
+  return prefix;
+}
+
+template <bool SIGMOID>
+__global__ void __launch_bounds__(kTailThreads) topk_tail_kernel(const float *__restrict__ scores, const SegTable tab,
+                                                                 SegState *__restrict__ state, unsigned *__restrict__ hist,
+                                                                 int k, const unsigned long long *__restrict__ cand,
+                                                                 const unsigned long long *__restrict__ bnd,
+                                                                 const unsigned *__restrict__ keys, unsigned small_max,
+                                                                 int small_by_index, int64_t *__restrict__ out_idx,
+                                                                 float *__restrict__ out_val, int32_t *__restrict__ out_count,
+                                                                 unsigned char *__restrict__ out_sorted) {
+  extern __shared__ __align__(16) unsigned long long sk[];   // kSmallMax keys | kBitonicMax selected keys | kBins counters
+  __shared__ int s_cnt;
+  const int seg = blockIdx.x, tid = threadIdx.x;
+  const SegDesc d = tab.s[seg];
+  const float *src = scores + d.off;
+  int n_out = 0;
+  bool by_index = false;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  unsigned long long *res = sk;   // where the sorted result ends up
+  if (d.len <= small_max) {
+    // ---- small segment: score; select the k largest if there are more (radix select in shared memory); sort
+    const int len = (int)d.len;
+    int mine = 0;
+    for (int i = tid; i < len; i += kTailThreads) {
+      const unsigned long long key = tail_key64<SIGMOID>(d, src, nullptr, (unsigned)i);
+      sk[i] = key;
+      mine += key != 0ULL;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((tid & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+    __syncthreads();
+    const int eff = s_cnt;
+    n_out = min(k, eff);
+    by_index = small_by_index && eff <= k;
+    int nsort = len;
+    if (eff > k) {
+      unsigned long long *sk2 = sk + kSmallMax;
+      unsigned *h = reinterpret_cast<unsigned *>(sk2 + kBitonicMax);
+      const unsigned long long thr = tail_select(sk, len, k, h, tid);
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int i = tid; i < len; i += kTailThreads) {
+        const unsigned long long key = sk[i];
+        if (key != 0ULL && key >= thr) {
+          const int pos = atomicAdd(&s_cnt, 1);
+          if (pos < kBitonicMax) sk2[pos] = key;
+        }
+      }
+      res = sk2, nsort = n_out;
+    }
+    const int np2 = pow2_at_least(nsort);
+    __syncthreads();
+    for (int i = nsort + tid; i < np2; i += kTailThreads) res[i] = 0ULL;
+    if (by_index)
+      for (int i = tid; i < nsort; i += kTailThreads) res[i] = swap_words(res[i]);   // index word leads (0 stays 0)
+    __syncthreads();
+    tail_bitonic(res, np2, tid);
+  } else {
+    SegState st = state[seg];
+    n_out = st.k_take;
+    by_index = small_by_index && st.eff_len <= (unsigned)k;
+    if (n_out > 0) {
+      if (st.bnd_count <= kBndCap) {
+        // ---- the k_rem largest keys of the boundary bin join the cand_count certain ones
+        const int nb = st.bnd_count, need = st.k_rem, c = n_out - need;
+        const int np2 = pow2_at_least(nb);
+        for (int i = tid; i < np2; i += kTailThreads) sk[i] = i < nb ? bnd[(long long)seg * kBndCap + i] : 0ULL;
+        __syncthreads();
+        tail_bitonic(sk, np2, tid);
+        unsigned long long pick[kBndCap / kTailThreads];
+#pragma unroll
+        for (int j = 0; j < kBndCap / kTailThreads; ++j) {
+          const int i = tid + j * kTailThreads;
+          pick[j] = i < need ? sk[i] : 0ULL;
+        }
+        __syncthreads();
+        for (int i = tid; i < c; i += kTailThreads) sk[i] = cand[(long long)seg * k + i];
+#pragma unroll
+        for (int j = 0; j < kBndCap / kTailThreads; ++j) {
+          const int i = tid + j * kTailThreads;
+          if (i < need) sk[c + i] = pick[j];
+        }
+      } else {
+        // ---- mass ties: the remaining digit passes over the whole segment, by this CTA alone
+        const unsigned *kbuf = keys != nullptr ? keys + d.koff : nullptr;
+        unsigned *g = hist + (long long)seg * kBins;   // all zero: every scan leaves it clean
+        for (int pass = 2; pass < 6; ++pass) {
+          int shift, bits;
+          pass_geometry(pass, shift, bits);
+          const int decided = 64 - shift - bits;
+          for (unsigned m = tid; m < d.len; m += kTailThreads) {
+            const unsigned long long key = tail_key64<SIGMOID>(d, src, kbuf, m);
+            if (key != 0ULL && (key >> (64 - decided)) == (st.prefix >> (64 - decided)))
+              atomicAdd(&g[(unsigned)(key >> shift) & ((1u << bits) - 1u)], 1u);
+          }
+          __threadfence();
+          __syncthreads();
+          scan_segment(hist, state, seg, pass);
+          __threadfence();
+          __syncthreads();
+          st.prefix = __ldcg(&state[seg].prefix), st.k_rem = __ldcg(&state[seg].k_rem);
+        }
+        for (unsigned m = tid; m < d.len; m += kTailThreads) {
+          const unsigned long long key = tail_key64<SIGMOID>(d, src, kbuf, m);
+          if (key != 0ULL && key >= st.prefix) {
+            const int pos = atomicAdd(&s_cnt, 1);
+            if (pos < kSmallMax) sk[pos] = key;
+          }
+        }
+      }
+      __syncthreads();
+      const int np2 = pow2_at_least(n_out);
+      for (int i = n_out + tid; i < np2; i += kTailThreads) sk[i] = 0ULL;
+      if (by_index)
+        for (int i = tid; i < n_out; i += kTailThreads) sk[i] = swap_words(sk[i]);
+      __syncthreads();
+      tail_bitonic(sk, np2, tid);
+    }
+  }
+  for (int i = tid; i < k; i += kTailThreads) {
+    long long oi = -1;
+    float ov = 0.0f;
+    if (i < n_out) {
+      unsigned long long v = res[i];
+      if (by_index) v = swap_words(v);
+      oi = (long long)(unsigned)~(unsigned)v;
+      ov = okey_inv((unsigned)(v >> 32));
+    }
+    out_idx[(long long)seg * k + i] = oi;
+    out_val[(long long)seg * k + i] = ov;
+  }
+  if (tid == 0) {
+    if (out_count != nullptr) out_count[seg] = n_out;
+    if (out_sorted != nullptr) out_sorted[seg] = !by_index;
   }
 }
 
@@ -658,7 +1165,7 @@ size_t roi3d_topk_workspace_bytes(int nseg, int k) {
 size_t roi3d_topk_workspace_bytes_keys(int nseg, int k, int64_t total_len) {
   const size_t base = roi3d_topk_workspace_bytes(nseg, k);
   if (nseg <= 0 || k <= 0 || total_len <= 0) return base;
-  return base + ((size_t)total_len * sizeof(unsigned) + 255) / 256 * 256;
+  return base + (((size_t)total_len + 4 * (size_t)nseg) * sizeof(unsigned) + 255) / 256 * 256;
 }
 
 int roi3d_topk_segmented(const float *scores_dev, const int64_t *seg_off, const int64_t *seg_len,
@@ -691,8 +1198,13 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
     return ROI3D_ENOMEM;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  ROI3D_CUDA(cudaMemsetAsync(out_idx_dev, 0xFF, sizeof(int64_t) * (size_t)nseg * k, st));
-  ROI3D_CUDA(cudaMemsetAsync(out_val_dev, 0, sizeof(float) * (size_t)nseg * k, st));
+  // k <= kBitonicMax: the tail kernel finishes every segment in one launch (and fills the unused rows itself)
+  const bool tail = k <= kBitonicMax;
+  const unsigned small_max = tail ? (unsigned)kSmallMax : 0u;
+  if (!tail) {
+    ROI3D_CUDA(cudaMemsetAsync(out_idx_dev, 0xFF, sizeof(int64_t) * (size_t)nseg * k, st));
+    ROI3D_CUDA(cudaMemsetAsync(out_val_dev, 0, sizeof(float) * (size_t)nseg * k, st));
+  }
   // optional key buffer behind the base workspace (roi3d_topk_workspace_bytes_keys): one u32 per score of a batch of
   // kMaxSeg segments, written by the first digit pass and read back (from L2) by the later full passes
   long long total_len = 0;
@@ -704,7 +1216,7 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
   for (int s0 = 0; s0 < nseg; s0 += kMaxSeg) {
     const int ns = nseg - s0 < kMaxSeg ? nseg - s0 : kMaxSeg;
     SegTable tab;
-    long long maxlen = 0, koff = 0;
+    long long maxlen = 0, koff = 0;   // maxlen: over the segments that go through the digit passes
     for (int s = 0; s < ns; ++s) {
       ROI3D_CHECK_ARG(seg_len[s0 + s] >= 0 && seg_len[s0 + s] < 4294967295LL, "segment %d too long", s0 + s);
       tab.s[s].off = seg_off[s0 + s];
@@ -719,9 +1231,17 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
       }
       tab.s[s].mask = seg_mask_dev_ptrs != nullptr ? seg_mask_dev_ptrs[s0 + s] : nullptr;
       tab.s[s].koff = koff;
-      koff += seg_len[s0 + s];
-      if (seg_len[s0 + s] > maxlen) maxlen = seg_len[s0 + s];
+      koff += (seg_len[s0 + s] + 3) / 4 * 4;   // every segment's keys start on a 16-byte boundary
+      if (seg_len[s0 + s] > (long long)small_max && seg_len[s0 + s] > maxlen) maxlen = seg_len[s0 + s];
     }
+    {
+      unsigned c = 0;
+      for (int s = 0; s <= kMaxSeg; ++s) {
+        tab.cta0[s] = c;
+        if (s < ns && seg_len[s0 + s] > (long long)small_max) c += (unsigned)ceil_div_ll(seg_len[s0 + s], kFirstItemsPerCta);
+      }
+    }
+    const unsigned flat_ctas = tab.cta0[kMaxSeg];
     static_assert(sizeof(SegState) * kMaxSeg + sizeof(int) * kMaxSeg <= 4096, "state block");
     char *b = static_cast<char *>(workspace_dev);
     SegState *state = reinterpret_cast<SegState *>(b);
@@ -729,59 +1249,90 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
     unsigned long long *cand = reinterpret_cast<unsigned long long *>(b + kStateBytes + kHistBytes);
     unsigned long long *bnd = cand + (size_t)(nseg < kMaxSeg ? nseg : kMaxSeg) * k;
     int *tickets = reinterpret_cast<int *>(b + sizeof(SegState) * kMaxSeg);  // inside the 4 KB state block
-    topk_init_kernel<<<1, kMaxSeg, 0, st>>>(state, tickets, tab, ns, k);
-    ROI3D_LAUNCH_CHECK();
-    if (maxlen == 0) {
-      if (out_count_dev != nullptr || out_sorted_dev != nullptr) {
-        topk_report_kernel<<<1, kMaxSeg, 0, st>>>(state, ns, k, small_segments_in_index_order,
-                                                  out_count_dev ? out_count_dev + s0 : nullptr,
-                                                  out_sorted_dev ? out_sorted_dev + s0 : nullptr);
+    int32_t *cnt_out = out_count_dev ? out_count_dev + s0 : nullptr;
+    uint8_t *srt_out = out_sorted_dev ? out_sorted_dev + s0 : nullptr;
+    if (maxlen > 0 || !tail) {
+      topk_init_kernel<<<1, kMaxSeg, 0, st>>>(state, tickets, tab, ns, k);
+      ROI3D_LAUNCH_CHECK();
+    }
+    if (maxlen > 0) {
+      ROI3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)ns * kBins * sizeof(unsigned), st));
+      const dim3 grid((unsigned)ceil_div_ll(maxlen, kItemsPerCta), ns);
+      const dim3 grid2((unsigned)(grid.x < 8 ? grid.x : 8), ns);  // boundary passes: see topk_hist_kernel
+      {
+        static bool attr_set = false;
+        if (!attr_set) {
+          ROI3D_CUDA(cudaFuncSetAttribute(topk_first_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstSmemBytes));
+          ROI3D_CUDA(cudaFuncSetAttribute(topk_first_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstSmemBytes));
+          attr_set = true;
+        }
+        if (apply_sigmoid)
+          topk_first_kernel<true><<<flat_ctas, kFirstThreads, kFirstSmemBytes, st>>>(scores_dev, tab, state, hist, tickets, keys);
+        else
+          topk_first_kernel<false><<<flat_ctas, kFirstThreads, kFirstSmemBytes, st>>>(scores_dev, tab, state, hist, tickets, keys);
         ROI3D_LAUNCH_CHECK();
       }
+      if (keys != nullptr) {  // digit pass 1 and the split over the stored keys
+        topk_second_kernel<<<flat_ctas * kKeySub, kKeyThreads, 0, st>>>(tab, state, hist, tickets, keys);
+        ROI3D_LAUNCH_CHECK();
+        topk_split_keys_kernel<<<flat_ctas * kKeySub, kKeyThreads, 0, st>>>(tab, state, k, cand, bnd, keys);
+        ROI3D_LAUNCH_CHECK();
+        if (!tail) {
+          topk_after_split_kernel<<<1, kMaxSeg, 0, st>>>(state, ns);
+          ROI3D_LAUNCH_CHECK();
+        }
+      }
+      for (int pass = keys != nullptr ? 2 : 1; pass < (tail ? 2 : 6); ++pass) {
+        const unsigned long long *b2 = pass >= 2 ? bnd : nullptr;
+        const dim3 g = pass >= 2 ? grid2 : grid;
+        if (apply_sigmoid)
+          topk_hist_kernel<true><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets, keys, small_max);
+        else
+          topk_hist_kernel<false><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets, keys, small_max);
+        ROI3D_LAUNCH_CHECK();
+        if (pass == 1) {  // 22 bits decided: split off the certain keys and the boundary bin
+          if (apply_sigmoid)
+            topk_split_kernel<true><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys, small_max);
+          else
+            topk_split_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys, small_max);
+          ROI3D_LAUNCH_CHECK();
+          if (!tail) {
+            topk_after_split_kernel<<<1, kMaxSeg, 0, st>>>(state, ns);
+            ROI3D_LAUNCH_CHECK();
+          }
+        }
+      }
+      if (!tail) {
+        if (apply_sigmoid)
+          topk_collect_kernel<true><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
+        else
+          topk_collect_kernel<false><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
+        ROI3D_LAUNCH_CHECK();
+      }
+    }
+    if (tail) {
+      static bool tail_attr = false;
+      if (!tail_attr) {
+        ROI3D_CUDA(cudaFuncSetAttribute(topk_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
+        ROI3D_CUDA(cudaFuncSetAttribute(topk_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
+        tail_attr = true;
+      }
+      if (apply_sigmoid)
+        topk_tail_kernel<true><<<ns, kTailThreads, kTailSmemBytes, st>>>(
+            scores_dev, tab, state, hist, k, cand, bnd, keys, small_max, small_segments_in_index_order,
+            out_idx_dev + (size_t)s0 * k, out_val_dev + (size_t)s0 * k, cnt_out, srt_out);
+      else
+        topk_tail_kernel<false><<<ns, kTailThreads, kTailSmemBytes, st>>>(
+            scores_dev, tab, state, hist, k, cand, bnd, keys, small_max, small_segments_in_index_order,
+            out_idx_dev + (size_t)s0 * k, out_val_dev + (size_t)s0 * k, cnt_out, srt_out);
+      ROI3D_LAUNCH_CHECK();
       continue;
     }
-    ROI3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)ns * kBins * sizeof(unsigned), st));
-    const dim3 grid((unsigned)ceil_div_ll(maxlen, kItemsPerCta), ns);
-    const dim3 grid2((unsigned)(grid.x < 8 ? grid.x : 8), ns);  // boundary passes: see topk_hist_kernel
-    for (int pass = 0; pass < 6; ++pass) {
-      const unsigned long long *b2 = pass >= 2 ? bnd : nullptr;
-      const dim3 g = pass >= 2 ? grid2 : grid;
-      if (apply_sigmoid)
-        topk_hist_kernel<true><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets, keys);
-      else
-        topk_hist_kernel<false><<<g, kTopkThreads, 0, st>>>(scores_dev, tab, state, pass, hist, b2, tickets, keys);
-      ROI3D_LAUNCH_CHECK();
-      if (pass == 1) {  // 22 bits decided: split off the certain keys and the boundary bin
-        if (apply_sigmoid)
-          topk_split_kernel<true><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
-        else
-          topk_split_kernel<false><<<grid, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
-        ROI3D_LAUNCH_CHECK();
-        topk_after_split_kernel<<<1, kMaxSeg, 0, st>>>(state, ns);
-        ROI3D_LAUNCH_CHECK();
-      }
-    }
-    if (apply_sigmoid)
-      topk_collect_kernel<true><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
-    else
-      topk_collect_kernel<false><<<grid2, kTopkThreads, 0, st>>>(scores_dev, tab, state, k, cand, bnd, keys);
+    topk_sort_kernel<<<dim3(ceil_div(k, 256), ns), 256, 0, st>>>(cand, state, tab, small_segments_in_index_order, k,
+                                                                out_idx_dev + (size_t)s0 * k, out_val_dev + (size_t)s0 * k);
     ROI3D_LAUNCH_CHECK();
-    if (k <= kBitonicMax) {
-      int npow2 = 2;
-      while (npow2 < k) npow2 <<= 1;
-      topk_bitonic_kernel<<<ns, 1024, (size_t)npow2 * sizeof(unsigned long long), st>>>(
-          cand, state, tab, small_segments_in_index_order, k, npow2, out_idx_dev + (size_t)s0 * k,
-          out_val_dev + (size_t)s0 * k);
-    } else {
-      topk_sort_kernel<<<dim3(ceil_div(k, 256), ns), 256, 0, st>>>(cand, state, tab, small_segments_in_index_order, k,
-                                                                  out_idx_dev + (size_t)s0 * k,
-                                                                  out_val_dev + (size_t)s0 * k);
-    }
-    ROI3D_LAUNCH_CHECK();
-    if (out_count_dev != nullptr || out_sorted_dev != nullptr) {
-      topk_report_kernel<<<1, kMaxSeg, 0, st>>>(state, ns, k, small_segments_in_index_order,
-                                                out_count_dev ? out_count_dev + s0 : nullptr,
-                                                out_sorted_dev ? out_sorted_dev + s0 : nullptr);
+    if (cnt_out != nullptr || srt_out != nullptr) {
+      topk_report_kernel<<<1, kMaxSeg, 0, st>>>(state, ns, k, small_segments_in_index_order, cnt_out, srt_out);
       ROI3D_LAUNCH_CHECK();
     }
   }
