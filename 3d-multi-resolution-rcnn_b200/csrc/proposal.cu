@@ -378,6 +378,17 @@ constexpr int kKeyBatch = 16;
 constexpr int kKeySub = 4;   // CTAs per chunk of kFirstItemsPerCta keys: short CTAs, ten per SM, hide the load latency
 constexpr int kKeyItemsPerCta = kFirstItemsPerCta / kKeySub;
 
+// a thread's batch of kKeyBatch keys, kKeyThreads apart: whole batches are loaded from one pointer with immediate offsets
+__device__ __forceinline__ void load_key_batch(const unsigned *__restrict__ p, unsigned m0, unsigned end, unsigned (&kk)[kKeyBatch]) {
+  if (m0 + (kKeyBatch - 1) * kKeyThreads < end) {
+#pragma unroll
+    for (int u = 0; u < kKeyBatch; ++u) kk[u] = __ldg(p + u * kKeyThreads);
+  } else {
+#pragma unroll
+    for (int u = 0; u < kKeyBatch; ++u) kk[u] = m0 + u * kKeyThreads < end ? __ldg(p + u * kKeyThreads) : 0u;
+  }
+}
+
 __global__ void __launch_bounds__(kKeyThreads) topk_second_kernel(const SegTable tab, SegState *__restrict__ state,
                                                                   unsigned *__restrict__ hist, int *__restrict__ tickets,
                                                                   const unsigned *__restrict__ keys) {
@@ -395,11 +406,7 @@ __global__ void __launch_bounds__(kKeyThreads) topk_second_kernel(const SegTable
   if (live) {
     for (unsigned m0 = base + threadIdx.x; m0 < end; m0 += kKeyThreads * kKeyBatch) {
       unsigned kk[kKeyBatch];
-#pragma unroll
-      for (int u = 0; u < kKeyBatch; ++u) {
-        const unsigned m = m0 + u * kKeyThreads;
-        kk[u] = m < end ? __ldg(kb + m) : 0u;
-      }
+      load_key_batch(kb + m0, m0, end, kk);
 #pragma unroll
       for (int u = 0; u < kKeyBatch; ++u)
         if (kk[u] != 0u && (kk[u] >> 21) == top11) atomicAdd(&h[(kk[u] >> 10) & 0x7FFu], 1u);
@@ -433,11 +440,7 @@ __global__ void __launch_bounds__(kKeyThreads) topk_split_keys_kernel(const SegT
   __syncthreads();
   for (unsigned m0 = base + threadIdx.x; m0 < end; m0 += kKeyThreads * kKeyBatch) {
     unsigned kk[kKeyBatch];
-#pragma unroll
-    for (int u = 0; u < kKeyBatch; ++u) {
-      const unsigned m = m0 + u * kKeyThreads;
-      kk[u] = m < end ? __ldg(kb + m) : 0u;
-    }
+    load_key_batch(kb + m0, m0, end, kk);
 #pragma unroll
     for (int u = 0; u < kKeyBatch; ++u) {
       const unsigned h22 = kk[u] >> 10;
@@ -614,45 +617,8 @@ __global__ void __launch_bounds__(256) topk_sort_kernel(const unsigned long long
   }
 }
 
-// Same ordering by a bitonic sort in shared memory, one CTA per segment, for k <= kBitonicMax (rank-by-counting is
-// O(k^2): 4 M key compares per segment at k = 2000).  Unused slots hold key 0, which sorts last in either order.
+// k up to kBitonicMax: the tail kernel (below) finishes every segment in one launch; above it the rank-by-counting sort.
 constexpr int kBitonicMax = 4096;
-__global__ void __launch_bounds__(1024) topk_bitonic_kernel(const unsigned long long *__restrict__ cand,
-                                                            const SegState *__restrict__ state, const SegTable tab,
-                                                            int small_by_index, int k, int npow2,
-                                                            int64_t *__restrict__ out_idx, float *__restrict__ out_val) {
-  extern __shared__ __align__(16) unsigned long long sk[];
-  const int seg = blockIdx.x, tid = threadIdx.x;
-  const int n = state[seg].k_take;
-  if (n <= 0) return;
-  const bool by_index = small_by_index && state[seg].eff_len <= (unsigned)k;
-  const unsigned long long *c = cand + (long long)seg * k;
-  // sort key: the 64-bit key itself (descending), or only its low word = ~index (descending = ascending index)
-  for (int i = tid; i < npow2; i += 1024) {
-    unsigned long long v = i < n ? c[i] : 0ULL;
-    if (by_index && i < n) v = ((unsigned long long)(unsigned)v << 32) | (v >> 32);  // swap words: index word leads
-    sk[i] = v;
-  }
-  __syncthreads();
-  for (int size = 2; size <= npow2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (npow2 >> 1); t += 1024) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = (lo & size) == 0;  // descending blocks first -> whole array descending at the end
-        const unsigned long long a = sk[lo], b = sk[hi];
-        if (desc ? (a < b) : (a > b)) sk[lo] = b, sk[hi] = a;
-      }
-      __syncthreads();
-    }
-  }
-  for (int i = tid; i < n; i += 1024) {
-    unsigned long long v = sk[i];
-    if (by_index) v = ((unsigned long long)(unsigned)v << 32) | (v >> 32);
-    out_idx[(long long)seg * k + i] = (int64_t)(unsigned)~(unsigned)v;
-    out_val[(long long)seg * k + i] = okey_inv((unsigned)(v >> 32));
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Tail of the selection, ONE launch, one CTA per segment (k <= kBitonicMax): what used to be four digit passes over
@@ -690,33 +656,37 @@ __device__ __forceinline__ int pow2_at_least(int n) {
   return p;
 }
 
-// descending bitonic sort of sk[0, npow2) by the whole CTA; ends with a barrier.  A thread's (up to four) compare-
-// exchanges of a stage are independent: all loads are issued before the first store (the stage is latency-bound)
-__device__ __forceinline__ void tail_bitonic(unsigned long long *sk, int npow2, int tid) {
+// descending bitonic sort of sk[0, npow2) by the whole CTA; ends with a barrier.  A thread's PAIRS compare-exchanges of
+// a stage are independent: all loads are issued before the first store (the stage is latency-bound)
+template <int PAIRS>
+__device__ __forceinline__ void tail_bitonic_p(unsigned long long *sk, int npow2, int tid) {
   const int half = npow2 >> 1;
   for (int size = 2; size <= npow2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t0 = tid; t0 < half; t0 += 4 * kTailThreads) {
-        unsigned long long a[4], b[4];
-        int lo[4];
+      unsigned long long a[PAIRS], b[PAIRS];
+      int lo[PAIRS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + u * kTailThreads;
-          lo[u] = 2 * t - (t & (stride - 1));
-          if (t < half) a[u] = sk[lo[u]], b[u] = sk[lo[u] + stride];
-        }
+      for (int u = 0; u < PAIRS; ++u) {
+        const int t = tid + u * kTailThreads;
+        lo[u] = 2 * t - (t & (stride - 1));
+        if (PAIRS > 1 || t < half) a[u] = sk[lo[u]], b[u] = sk[lo[u] + stride];
+      }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + u * kTailThreads;
-          if (t < half) {
-            const bool desc = (lo[u] & size) == 0;
-            if (desc ? (a[u] < b[u]) : (a[u] > b[u])) sk[lo[u]] = b[u], sk[lo[u] + stride] = a[u];
-          }
+      for (int u = 0; u < PAIRS; ++u) {
+        const int t = tid + u * kTailThreads;
+        if (PAIRS > 1 || t < half) {
+          const bool desc = (lo[u] & size) == 0;
+          if (desc ? (a[u] < b[u]) : (a[u] > b[u])) sk[lo[u]] = b[u], sk[lo[u] + stride] = a[u];
         }
       }
       __syncthreads();
     }
   }
+}
+__device__ __forceinline__ void tail_bitonic(unsigned long long *sk, int npow2, int tid) {
+  if (npow2 <= 2 * kTailThreads) tail_bitonic_p<1>(sk, npow2, tid);        // at most one pair per thread
+  else if (npow2 == 4 * kTailThreads) tail_bitonic_p<2>(sk, npow2, tid);
+  else tail_bitonic_p<4>(sk, npow2, tid);                                  // 8 * kTailThreads = kSmallMax
 }
 
 __device__ __forceinline__ unsigned long long swap_words(unsigned long long v) {
