@@ -19,6 +19,8 @@
 // Ties (parity unpinned by the reference: torch 1.0.1's max(dim) index on ties): the LOWEST index wins.
 #include <float.h>
 
+#include <cmath>
+
 #include "common.cuh"
 
 namespace roi3d {
@@ -239,6 +241,37 @@ __global__ void __launch_bounds__(256) bbox2delta3d_kernel(const float *__restri
   for (int q = 0; q < 6; ++q) out[(long long)i * 6 + q] = __fdiv_rn(__fsub_rn(d[q], means.v[q]), stds.v[q]);
 }
 
+// Inverse of the above for the bbox head: [n, 6k] class-wise deltas applied to [n] boxes (delta2bbox3D,
+// mmdet/core/bbox/transforms.py:105-160), one thread per (box, class).  All four size / depth terms are clamped with
+// |log(wh_ratio_clip)| as the reference does (:122-128).  Same operation order as the fused proposal decode (proposal.cu).
+__global__ void __launch_bounds__(256) delta2bbox3d_kernel(const float *__restrict__ rois, int sr,
+                                                           const float *__restrict__ deltas, int n, int k, Float6 means,
+                                                           Float6 stds, float max_ratio, float img_h, float img_w,
+                                                           float img_d, float *__restrict__ out) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)n * k) return;
+  const int i = (int)(t / k), c = (int)(t - (long long)i * k);
+  float r[6], d[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    r[q] = __ldg(rois + (long long)i * sr + q);
+    d[q] = __fadd_rn(__fmul_rn(__ldg(deltas + ((long long)i * k + c) * 6 + q), stds.v[q]), means.v[q]);
+  }
+  float *o = out + ((long long)i * k + c) * 6;
+  // pairs (0,2) (1,3) (4,5); deltas (0,2) (1,3) (4,5) = (centre shift, log size ratio)
+  const int lo[3] = {0, 1, 4}, hi[3] = {2, 3, 5};
+  const float lim[3] = {img_w, img_h, img_d};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float pc = __fmul_rn(__fadd_rn(r[lo[a]], r[hi[a]]), 0.5f), ps = __fadd_rn(__fsub_rn(r[hi[a]], r[lo[a]]), 1.0f);
+    const float ds = fminf(fmaxf(d[hi[a]], -max_ratio), max_ratio);
+    const float gs = __fmul_rn(ps, expf(ds)), gc = __fadd_rn(pc, __fmul_rn(ps, d[lo[a]]));
+    float v1 = __fadd_rn(__fsub_rn(gc, __fmul_rn(gs, 0.5f)), 0.5f), v2 = __fsub_rn(__fadd_rn(gc, __fmul_rn(gs, 0.5f)), 0.5f);
+    if (img_w > 0.0f) v1 = fminf(fmaxf(v1, 0.0f), lim[a] - 1.0f), v2 = fminf(fmaxf(v2, 0.0f), lim[a] - 1.0f);
+    o[lo[a]] = v1, o[hi[a]] = v2;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Anchors of one level in closed form + valid / inside flags.  Flat index = ((y*W + x)*D + z)*A + a
 // (np.meshgrid(x, y, z) 'xy' order, anchor_generator_3d.py:59-70); anchor = base[a] + (x*s, y*s, x*s, y*s, z*sd, z*sd).
@@ -377,6 +410,24 @@ int roi3d_bbox2delta3d(const float *proposals_dev, int stride_p, const float *gt
   for (int q = 0; q < 6; ++q) m.v[q] = means6 ? means6[q] : 0.0f, s.v[q] = stds6 ? stds6[q] : 1.0f;
   bbox2delta3d_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(proposals_dev, stride_p, gt_dev, stride_g, n, m,
                                                                           s, deltas_dev);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+
+int roi3d_delta2bbox3d(const float *rois_dev, int stride_r, const float *deltas_dev, int n, int num_classes,
+                       const float *means6, const float *stds6, float wh_ratio_clip, float img_h, float img_w, float img_d,
+                       float *out_dev, void *stream) {
+  ROI3D_CHECK_ARG(n >= 0 && num_classes >= 1 && stride_r >= 6, "bad sizes");
+  ROI3D_CHECK_ARG(wh_ratio_clip > 0.0f, "wh_ratio_clip must be > 0");
+  if (n == 0) return ROI3D_OK;
+  ROI3D_CHECK_ARG(rois_dev && deltas_dev && out_dev, "NULL pointer");
+  Float6 m, s;
+  for (int q = 0; q < 6; ++q) m.v[q] = means6 ? means6[q] : 0.0f, s.v[q] = stds6 ? stds6[q] : 1.0f;
+  // max_ratio = np.abs(np.log(wh_ratio_clip)) evaluated in float64, then used as a python float by clamp
+  const float max_ratio = (float)std::fabs(std::log((double)wh_ratio_clip));
+  const long long total = (long long)n * num_classes;
+  delta2bbox3d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      rois_dev, stride_r, deltas_dev, n, num_classes, m, s, max_ratio, img_h, img_w, img_d, out_dev);
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
 }

@@ -163,13 +163,13 @@ __device__ __forceinline__ void add_tap(float (&w)[4], int i, float v) {
 // Plan kernel: one warp per RoI.  Lanes 0..7 -> x bins, 8..15 -> y bins, 16..23 -> z bins.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p, StreamPlan *plans, int *counter, int sort,
-                                                               int slot_bytes) {
+                                                               int slot_bytes, int counter_init) {
   extern __shared__ float cost_s[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // programmatic dependent launch: the streamed kernel may be scheduled now; it waits (griddepcontrol.wait) for this
   // grid to finish before it touches the plans or the counter
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = counter_init;   // the first items of every CTA are static
 
   // ---- footprint cost of every RoI (each CTA computes all of them: K is small), then the rank of this CTA's RoIs
   if (sort) {
@@ -519,11 +519,12 @@ __device__ __forceinline__ void producer_loop(const StreamArgs &a, unsigned char
     if (lane < 20) return __ldg(reinterpret_cast<const int *>(a.plans + r) + lane);
     return lane == 20 ? chunk : r;
   };
-  int idx_cur = __shfl_sync(FULL, ticket(), 0);
+  // the first three items of a CTA are static (blockIdx.x + {0, 1, 2} * grid; the counter starts behind them): no chain
+  // of dependent atomic / header round trips before the first tile is requested
+  int idx_cur = (int)blockIdx.x, idx_n1 = (int)(blockIdx.x + gridDim.x);
   int h_cur = header(idx_cur);
-  int idx_n1 = __shfl_sync(FULL, ticket(), 0);
   int h_n1 = header(idx_n1);
-  int t_n2 = ticket();
+  int t_n2 = (int)(blockIdx.x + 2 * gridDim.x);
   unsigned tile_seq = 0, item_seq = 0;
   while (idx_cur < total) {
     const int idx_n2 = __shfl_sync(FULL, t_n2, 0);
@@ -785,7 +786,8 @@ int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count)
   StreamPlan *plans = reinterpret_cast<StreamPlan *>(ws);
   int *counter = reinterpret_cast<int *>(ws + plan_bytes);
   const int sort = (p.K <= ST_SORT_MAX && !(a.debug & 4)) ? 1 : 0;
-  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(p, plans, counter, sort, SLOT);
+  const int grid = a.total_items < sm_count ? a.total_items : sm_count;
+  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(p, plans, counter, sort, SLOT, 3 * grid);
   ROI3D_LAUNCH_CHECK();
   a.plans = plans, a.counter = counter;
   static bool attr_set = false;
@@ -794,7 +796,6 @@ int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count)
                                     L::LAUNCH));
     attr_set = true;
   }
-  const int grid = a.total_items < sm_count ? a.total_items : sm_count;
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(ST_WARPS * 32), cfg.dynamicSmemBytes = L::LAUNCH, cfg.stream = st;

@@ -198,6 +198,13 @@ int roi3d_assign_max_iou(const float *bboxes_dev, int n, int stride, const float
                          size_t workspace_bytes, void *stream);
 int roi3d_bbox2delta3d(const float *proposals_dev, int stride_p, const float *gt_dev, int stride_g, int n,
                        const float *means6, const float *stds6, float *deltas_dev, void *stream);
+/* delta2bbox3D for class-wise deltas (the bbox head's decode; mmdet/core/bbox/transforms.py:105-160): deltas [n, 6k]
+ * applied to rois [n, >= 6] (row stride stride_r), out [n, 6k].  dw, dh, dz AND dd are clamped with |log(wh_ratio_clip)|
+ * as the reference does (:122-128; its d_ratio_clip argument is unused).  img_w <= 0: no clamp to the image
+ * (max_shape=None); otherwise x in [0, img_w - 1], y in [0, img_h - 1], z in [0, img_d - 1]. */
+int roi3d_delta2bbox3d(const float *rois_dev, int stride_r, const float *deltas_dev, int n, int num_classes,
+                       const float *means6, const float *stds6, float wh_ratio_clip, float img_h, float img_w, float img_d,
+                       float *out_dev, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Mask paste: per detection sigmoid -> resize to the box -> threshold.

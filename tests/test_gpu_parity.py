@@ -409,11 +409,44 @@ def test_decode_matches_oracle(oracle, dev):
     ok = idx >= 0
     assert np.abs(got[ok, :6] - want[ok]).max() <= 1e-3      # expf last-bit differences only (glibc vs CUDA)
     assert np.array_equal(got[ok, 6], sc[ok]) and np.all(got[~ok] == 0)
-    # against the torch-op form of the reference expression on the same device
+    # against today's torch CUDA ops evaluating the reference's expression (transforms.py:105-160) on the same device:
+    # every step is an fp32 elementwise kernel there, and the fused kernels keep its operation order -> bit-exact
+    tw = _torch_delta2bbox3d(torch.from_numpy(anchors[sel]).to(dev), torch.from_numpy(deltas[sel]).to(dev), means, stds,
+                             img_shape).cpu().numpy()
+    assert np.array_equal(got[ok, :6], tw[ok])
+    # the bbox head's decode entry (class-wise deltas [n, 6k]) against the same expression
     from roi3d_b200 import delta2bbox3D
-    tw = delta2bbox3D(torch.from_numpy(anchors[sel]).to(dev), torch.from_numpy(deltas[sel]).to(dev), means, stds,
-                      img_shape).cpu().numpy()
-    assert np.abs(got[ok, :6] - tw[ok]).max() <= 1e-4
+    rois_t = torch.from_numpy(anchors[sel]).to(dev)
+    d3 = torch.from_numpy(np.concatenate([deltas[sel], 0.5 * deltas[sel][::-1], 3.0 * deltas[sel]], 1).astype(np.float32)).to(dev)
+    for shape in (img_shape, None):
+        mine = delta2bbox3D(rois_t, d3, means, stds, shape)
+        ref = _torch_delta2bbox3d(rois_t, d3, means, stds, shape)
+        assert mine.shape == d3.shape and torch.equal(mine, ref)
+    assert delta2bbox3D(rois_t[:0], d3[:0], means, stds, img_shape).shape == (0, 18)
+
+
+def _torch_delta2bbox3d(rois, deltas, means, stds, max_shape, wh_ratio_clip=16 / 1000):
+    """The reference's delta2bbox3D expression (mmdet/core/bbox/transforms.py:105-160) with today's torch ops: the
+    yardstick for the fused decode kernels (the reference ran it on torch 1.0.1 CUDA kernels, not available here)."""
+    k = deltas.size(1) // 6
+    d = deltas * deltas.new_tensor(stds).repeat(1, k) + deltas.new_tensor(means).repeat(1, k)
+    mr = float(np.abs(np.log(wh_ratio_clip)))
+    ctr, size = {}, {}
+    for name, lo, hi in (("x", 0, 2), ("y", 1, 3), ("z", 4, 5)):
+        p_c = ((rois[:, lo] + rois[:, hi]) * 0.5).unsqueeze(1)
+        p_s = (rois[:, hi] - rois[:, lo] + 1.0).unsqueeze(1)
+        size[name] = p_s * d[:, hi::6].clamp(-mr, mr).exp()
+        ctr[name] = p_c + p_s * d[:, lo::6]
+    lims = None if max_shape is None else {"x": max_shape[1] - 1, "y": max_shape[0] - 1, "z": max_shape[3] - 1}
+    cols = {}
+    for name in ("x", "y", "z"):
+        v1 = ctr[name] - size[name] * 0.5 + 0.5
+        v2 = ctr[name] + size[name] * 0.5 - 0.5
+        if lims is not None:
+            v1, v2 = v1.clamp(0, lims[name]), v2.clamp(0, lims[name])
+        cols[name] = (v1, v2)
+    return torch.stack([cols["x"][0], cols["y"][0], cols["x"][1], cols["y"][1], cols["z"][0], cols["z"][1]],
+                       dim=-1).view_as(deltas)
 
 
 def _rpn_inputs(B, dims, seed):
