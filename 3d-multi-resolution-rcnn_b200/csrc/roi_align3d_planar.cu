@@ -18,8 +18,9 @@
 // writes the [K, C, PD, PH, PW] output directly: consecutive lanes = consecutive floats, 128-byte stores, no staging
 // -- which also makes this the kernel for the 14 x 14 x 14 mask branch, where the output (2.9 GB at C3) is 93 % of
 // the traffic.  Channels-last levels are accepted too (4-byte cp.async that transposes into the planes).
-// A CTA walks the 64 channels of its item in passes of up to 16 channels; the next pass's planes are copied while
-// the current pass is reduced (two input buffers), and two CTAs are resident per SM.
+// A CTA walks the 64 channels of its item in passes of up to 16 channels (packed four by four: LDS.128 + FFMA2 in the
+// y / z stages) and, where the footprint does not fit, in chunks of z slices; the next step's planes are copied while
+// the current one is reduced (two input buffers); three CTAs are resident per SM (64 registers, 72 KB).
 //
 // RoIs with a bin of more than four taps, or a footprint that does not fit the planes even one channel at a time,
 // are evaluated literally (reference sample loops, bit-exact) by the same CTA.
@@ -32,7 +33,7 @@ namespace {
 constexpr int PL_THREADS = 256;
 constexpr int PL_MAXP = 16;          // bins per axis the tables hold
 constexpr int PL_MAXCG = 16;         // channels reduced per pass
-constexpr int PL_SMEM_FLOATS = 27648;  // plane storage per CTA (108 KB): two CTAs per SM
+constexpr int PL_SMEM_FLOATS = 18432;  // plane storage per CTA (72 KB): three CTAs per SM (measured: 2 x 108 KB 782 us, 3 x 72 KB 733 us, 4 x 54 KB 731 us on C3)
 
 struct PlanarTables {
   int xo[PL_MAXP], yo[PL_MAXP], zo[PL_MAXP];       // first tap of a bin, from the box origin (x: from the aligned origin)
@@ -113,24 +114,43 @@ __device__ __forceinline__ float4 taps4(const float *s, const float4 w) {
   return a;
 }
 // the z stage: bins of one RoI differ in how many slices they touch.  The tables widen every bin to two slices where
-// the footprint has two (TWO, uniform over the CTA), so the common case runs without a branch; a third / fourth tap is rare
-template <int STRIDE>
-__device__ __forceinline__ float4 taps4_n(int n, bool two, const float *s, const float4 w) {
-  float4 a = mul4(w.x, *reinterpret_cast<const float4 *>(s));
-  if (two) fma4(a, w.y, *reinterpret_cast<const float4 *>(s + STRIDE));
+// the footprint has two (TWO: uniform over the CTA, a template argument so that the common case has no predicated
+// merges); a third / fourth tap is rare.  Accumulators are two packed pairs updated in place.
+struct Acc4 {
+  float2 lo, hi;
+};
+template <int STRIDE, bool TWO>
+__device__ __forceinline__ Acc4 taps4_n(int n, const float *s, const float4 w) {
+  Acc4 a;
+  {
+    const float4 v = *reinterpret_cast<const float4 *>(s);
+    a.lo = __fmul2_rn(make_float2(w.x, w.x), make_float2(v.x, v.y));
+    a.hi = __fmul2_rn(make_float2(w.x, w.x), make_float2(v.z, v.w));
+  }
+  if (TWO) {
+    const float4 v = *reinterpret_cast<const float4 *>(s + STRIDE);
+    a.lo = __ffma2_rn(make_float2(w.y, w.y), make_float2(v.x, v.y), a.lo);
+    a.hi = __ffma2_rn(make_float2(w.y, w.y), make_float2(v.z, v.w), a.hi);
+  }
   if (n > 2) {
-    fma4(a, w.z, *reinterpret_cast<const float4 *>(s + 2 * STRIDE));
-    if (n > 3) fma4(a, w.w, *reinterpret_cast<const float4 *>(s + 3 * STRIDE));
+    const float4 v = *reinterpret_cast<const float4 *>(s + 2 * STRIDE);
+    a.lo = __ffma2_rn(make_float2(w.z, w.z), make_float2(v.x, v.y), a.lo);
+    a.hi = __ffma2_rn(make_float2(w.z, w.z), make_float2(v.z, v.w), a.hi);
+    if (n > 3) {
+      const float4 u = *reinterpret_cast<const float4 *>(s + 3 * STRIDE);
+      a.lo = __ffma2_rn(make_float2(w.w, w.w), make_float2(u.x, u.y), a.lo);
+      a.hi = __ffma2_rn(make_float2(w.w, w.w), make_float2(u.z, u.w), a.hi);
+    }
   }
   return a;
 }
 // four channel planes of one output element, OE floats apart (compile-time when the output depth is)
 template <bool FULL4>
-__device__ __forceinline__ void store4(float *d, long long oe, const float4 a, int left) {
-  __stcs(d, a.x);
-  if (FULL4 || left > 1) __stcs(d + oe, a.y);
-  if (FULL4 || left > 2) __stcs(d + 2 * oe, a.z);
-  if (FULL4 || left > 3) __stcs(d + 3 * oe, a.w);
+__device__ __forceinline__ void store4(float *d, long long oe, const Acc4 a, int left) {
+  __stcs(d, a.lo.x);
+  if (FULL4 || left > 1) __stcs(d + oe, a.lo.y);
+  if (FULL4 || left > 2) __stcs(d + 2 * oe, a.hi.x);
+  if (FULL4 || left > 3) __stcs(d + 3 * oe, a.hi.y);
 }
 
 // ---- x stage: footprint rows -> T1[group][row][pw][4 channels].  NCDHW: the footprint lies in one plane per channel
@@ -216,6 +236,47 @@ __device__ __forceinline__ void planar_y_stage(const PlanarTables &T, const floa
   }
 }
 
+// ---- z stage: T2[group][z][q][4] -> out[c][pd][q]
+template <int P, bool TWO>
+__device__ __forceinline__ void planar_z_stage(const PlanarTables &T, const float *T2, float *oc, long long out_elems, int PD,
+                                               int RZ, int NG, int nch, int tid) {
+  constexpr int PP = P * P;
+  const int gT2 = RZ * PP * 4;
+  const bool full4 = (nch & 3) == 0;
+  if constexpr (PP >= PL_THREADS / 2) {
+    // wide outputs: a thread keeps its element and walks the channel groups (offsets / weights looked up once)
+    for (int e = tid; e < PD * PP; e += PL_THREADS) {
+      const int pd = e / PP, q = e - pd * PP;
+      const int n = T.nz[pd];
+      const float4 w = *reinterpret_cast<const float4 *>(&T.zw[pd][0]);
+      const float *sp = T2 + (T.zo[pd] * PP + q) * 4;
+      float *d = oc + e;
+      if (full4) {
+        for (int cg = 0; cg < NG; ++cg) {
+          store4<true>(d, out_elems, taps4_n<PP * 4, TWO>(n, sp, w), 4);
+          sp += gT2, d += 4 * out_elems;
+        }
+      } else {
+        for (int cg = 0; cg < NG; ++cg) {
+          store4<false>(d, out_elems, taps4_n<PP * 4, TWO>(n, sp, w), nch - cg * 4);
+          sp += gT2, d += 4 * out_elems;
+        }
+      }
+    }
+  } else {
+    const unsigned ntask = (unsigned)(PD * PP), total = ntask * (unsigned)NG, m_nt = fast_magic(ntask);
+    for (unsigned e = tid; e < total; e += PL_THREADS) {
+      const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
+      const unsigned pd = t / PP, q = t - pd * PP;
+      const float4 w = *reinterpret_cast<const float4 *>(&T.zw[pd][0]);
+      const Acc4 a = taps4_n<PP * 4, TWO>(T.nz[pd], T2 + ((cg * RZ + T.zo[pd]) * PP + q) * 4, w);
+      float *d = oc + (long long)(cg * 4) * out_elems + t;
+      if (full4) store4<true>(d, out_elems, a, 4);
+      else store4<false>(d, out_elems, a, nch - (int)cg * 4);
+    }
+  }
+}
+
 // Visit order of the RoIs: by (level, volume, z, y, x) of their first corner.  In NCDHW a RoI uses 40 to 70 bytes of
 // each 512-byte feature row it touches while DRAM is fetched in 128-byte lines; x-neighbours processed close in time
 // find the rest of the line in L2.  Rank by counting over keys staged in shared memory (K <= 8192).
@@ -244,7 +305,7 @@ __global__ void __launch_bounds__(256) roi_align3d_order_kernel(const RoiParams 
 }
 
 template <int P, bool CL, int PDT>  // PW == PH == P; CL: channels-last levels; PDT: output depth (0 = p.PD at run time)
-__global__ void __launch_bounds__(PL_THREADS, 2)
+__global__ void __launch_bounds__(PL_THREADS, 4)
     roi_align3d_fwd_planar_kernel(const RoiParams p, int CG, int ngroups, int smem_floats, const int *__restrict__ order) {
   extern __shared__ __align__(16) float planes[];
   __shared__ PlanarTables T;
@@ -484,43 +545,8 @@ __global__ void __launch_bounds__(PL_THREADS, 2)
     if (chunk + 1 < nchunk) continue;
     __syncthreads();
     // ---- z stage: T2[group][z][q][4] -> out[c][pd][q], streamed to global: consecutive lanes = consecutive floats
-    {
-      float *oc = out_roi + (long long)c0 * out_elems;
-      const int gT2 = RZ * PP * 4;
-      const bool full4 = (nch & 3) == 0, two = RZ >= 2;
-      if constexpr (PP >= PL_THREADS / 2) {
-        // wide outputs: a thread keeps its element and walks the channel groups (offsets / weights looked up once)
-        for (int e = tid; e < PD * PP; e += PL_THREADS) {
-          const int pd = e / PP, q = e - pd * PP;
-          const int n = T.nz[pd];
-          const float4 w = *reinterpret_cast<const float4 *>(&T.zw[pd][0]);
-          const float *sp = T2 + (T.zo[pd] * PP + q) * 4;
-          float *d = oc + e;
-          if (full4) {
-            for (int cg = 0; cg < NG; ++cg) {
-              store4<true>(d, out_elems, taps4_n<PP * 4>(n, two, sp, w), 4);
-              sp += gT2, d += 4 * out_elems;
-            }
-          } else {
-            for (int cg = 0; cg < NG; ++cg) {
-              store4<false>(d, out_elems, taps4_n<PP * 4>(n, two, sp, w), nch - cg * 4);
-              sp += gT2, d += 4 * out_elems;
-            }
-          }
-        }
-      } else {
-        const unsigned ntask = (unsigned)(PD * PP), total = ntask * (unsigned)NG, m_nt = fast_magic(ntask);
-        for (unsigned e = tid; e < total; e += PL_THREADS) {
-          const unsigned cg = fast_div(e, ntask, m_nt), t = e - cg * ntask;
-          const unsigned pd = t / PP, q = t - pd * PP;
-          const float4 w = *reinterpret_cast<const float4 *>(&T.zw[pd][0]);
-          const float4 a = taps4_n<PP * 4>(T.nz[pd], two, T2 + ((cg * RZ + T.zo[pd]) * PP + q) * 4, w);
-          float *d = oc + (long long)(cg * 4) * out_elems + t;
-          if (full4) store4<true>(d, out_elems, a, 4);
-          else store4<false>(d, out_elems, a, nch - (int)cg * 4);
-        }
-      }
-    }
+    if (RZ >= 2) planar_z_stage<P, true>(T, T2, out_roi + (long long)c0 * out_elems, out_elems, PD, RZ, NG, nch, tid);
+    else planar_z_stage<P, false>(T, T2, out_roi + (long long)c0 * out_elems, out_elems, PD, RZ, NG, nch, tid);
   }
 }
 
@@ -542,7 +568,7 @@ bool fwd_planar_ok(const RoiParams &p, int layout) {
   return true;
 }
 
-int g_planar_smem_floats = 0;  // roi3d_set_tuning key 10: plane storage per CTA in floats (0 = default, two CTAs per SM)
+int g_planar_smem_floats = 0;  // roi3d_set_tuning key 10: plane storage per CTA in floats (0 = default, three CTAs per SM)
 
 namespace {
 template <int P, bool CL, int PDT>

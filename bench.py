@@ -373,6 +373,13 @@ def main():
             roofline["ncdhw_input"] = {"kernel_us": us, "achieved": alg_bytes / (us * 1e-6) / 1e9,
                                        "frac": alg_bytes / (us * 1e-6) / 1e9 / peak,
                                        "note": "same algorithmic bytes; the layout conversion is extra traffic, not credited"}
+        if extra.get("c3_fwd_output_gbs"):
+            # the mask branch (C3, 14^3 bins, four levels): the 2.88 GB output is 93 % of its traffic; output bytes only
+            roofline["c3_mask_branch"] = {
+                "kernel": "roi_align3d_fwd_planar_kernel<14,*,14>", "kernel_us": extra["c3_fwd_us"],
+                "achieved_output_only": extra["c3_fwd_output_gbs"], "frac_output_only": extra["c3_fwd_output_gbs"] / peak,
+                "ncdhw": {"kernel_us": extra.get("c3_fwd_ncdhw_us"),
+                          "frac_output_only": (extra.get("c3_fwd_ncdhw_output_gbs") or 0.0) / peak}}
         cpu = cpu_baseline() if world == 1 else None  # reported on rank 0 at N=1 only
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -488,6 +495,14 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     us = med_us(lambda: layer(feats, rois), iters=5)   # no reuse scope open: converted on every call
     ex["c2_fwd_ncdhw_input_us"] = us
     ex["c2_fwd_ncdhw_input_rois_per_sec"] = C2["K"] / (us * 1e-6)
+    # the same NCDHW tensor read in place by the planar kernel (no conversion; the mirror's default for 7-wide outputs
+    # of 64-channel multiples is conversion + streamed kernel, because the converted copy is reusable within a pass)
+    from roi3d_b200 import _util
+    _util.FORCE_NATIVE_NCDHW[0] = True
+    try:
+        ex["c2_fwd_ncdhw_native_planar_us"] = med_us(lambda: layer(feats, rois), iters=5)
+    finally:
+        _util.FORCE_NATIVE_NCDHW[0] = False
     # C2 backward (grad of the pooled features w.r.t. the level), zero-fill of the 671 MB gradient included
     fcl = feats_cl.detach().requires_grad_(True)
     out = layer(fcl, rois)
@@ -576,6 +591,10 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ex["c3_level_hist"] = torch.bincount(ext.map_roi_levels(r3, 4), minlength=4).tolist()
     us_f = med_us(lambda: ext(pyr, r3), iters=5)
     ex["c3_fwd_us"] = us_f
+    pyr_nc = [t.contiguous() for t in pyr]   # the reference's NCDHW layout, read natively
+    us_nc = med_us(lambda: ext(pyr_nc, r3), iters=5)
+    ex["c3_fwd_ncdhw_us"] = us_nc
+    del pyr_nc
     for t in pyr:
         t.requires_grad_(True)
     o3 = ext(pyr, r3)
@@ -589,6 +608,7 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ex["c3_bwd_us_incl_zero_fill"] = us_b
     ex["c3_fwd_bwd_rois_per_sec"] = 1024 / ((us_f + us_b) * 1e-6)
     ex["c3_fwd_output_gbs"] = o3.numel() * 4 / (us_f * 1e-6) / 1e9
+    ex["c3_fwd_ncdhw_output_gbs"] = o3.numel() * 4 / (us_nc * 1e-6) / 1e9
     del pyr, o3, g3
     torch.cuda.empty_cache()
     # C4: RPN proposal path, 8 volumes of 512x512x160 (5 levels, A=1) on this GPU: top-k 2000 -> decode -> 3D NMS 0.7
