@@ -110,10 +110,11 @@ def forward_inputs(feats, out_h, out_w):
         return list(feats), _lib.NDHWC
     native = out_h == out_w and out_h in (7, 14) and all(
         f.is_contiguous() and f.shape[-1] % 4 == 0 and f.data_ptr() % 16 == 0 for f in feats)
-    # 7-wide outputs of 64-channel multiples: one conversion (HBM speed, reusable across the extractor calls of a pass,
-    # see reuse_layout_conversions) + the streamed channels-last kernel beats the planar kernel (C2: 393 vs 418 us for
-    # a single call, 150 vs 418 us per further call); everything else the planar kernel reads in place
-    if native and out_h == 7 and feats[0].shape[1] % 64 == 0 and not FORCE_NATIVE_NCDHW[0]:
+    # Inside a reuse_layout_conversions() scope a 7-wide extractor on 64-channel multiples converts once and runs the
+    # streamed channels-last kernel: the converted copy serves every extractor call of the pass (C2: 137 us per call
+    # after a 240 us conversion).  A lone call reads the NCDHW tensor in place with the planar kernel (357 us against
+    # 377 us for conversion + streamed kernel).
+    if native and out_h == 7 and feats[0].shape[1] % 64 == 0 and _scopes and not FORCE_NATIVE_NCDHW[0]:
         native = False
     if native:
         return list(feats), _lib.NCDHW
