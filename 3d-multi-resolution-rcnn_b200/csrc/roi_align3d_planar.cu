@@ -550,6 +550,285 @@ __global__ void __launch_bounds__(PL_THREADS, 4)
   }
 }
 
+// =================================================================================================================
+// Backward of the planar formulation (mask branch: 14-wide outputs; channels-last gradients).
+//
+// Replaces (reference): ROIAlignBackward3D / bilinear_interpolate_gradient_3d, roi_align_kernel.cu:519-636, :383-442 -- 64
+// scalar atomics per output element.  Here the three contractions run transposed, lanes over elements, four channels per
+// 16-byte entry like the forward:
+//     z^T: T2[z][ph,pw]  = sum_pd wz[pd][z] * g[pd][ph,pw]   scatter form, but a thread owns its (ph, pw, group) column for
+//                          all pd, so the slices live in a 4-deep register window (bins are monotone in z): grad_out is
+//                          read from global exactly once, coalesced, and every T2 entry is written once;
+//     y^T: T1[z,y][pw]   = sum_ph wy[ph][y] * T2[z][ph,pw]   gather over the bins whose support holds row y;
+//     x^T: d[z,y,x]      = sum_pw wx[pw][x] * T1[z,y][pw]    gather, then ONE 16-byte vector red per (voxel, 4 channels):
+//                          each voxel of the footprint receives exactly one red per RoI and channel group (the per-warp
+//                          kernels issue one per (voxel, z slice of every pd bin), ~2.6x as many).
+// =================================================================================================================
+constexpr int PLB_MAXR = 32;   // footprint rows / voxels per row the dense gather tables hold
+
+struct PlanarBwdTables {
+  int xo[PL_MAXP], yo[PL_MAXP], zo[PL_MAXP];
+  int nx[PL_MAXP], ny[PL_MAXP], nz[PL_MAXP];       // taps per bin (0: the bin has no valid sample)
+  alignas(16) float xw[PL_MAXP][4];
+  alignas(16) float yw[PL_MAXP][4];
+  alignas(16) float zw[PL_MAXP][4];                // pre-multiplied by 1 / count
+  int lo[48], hi[48];
+  int box[20];
+  int ylo[PLB_MAXR], yhi[PLB_MAXR], xlo[PLB_MAXR], xhi[PLB_MAXR];   // bins whose support holds row y / voxel x
+  alignas(16) float ywd[PLB_MAXR][PL_MAXP];        // dense: weight of row y in bin ph
+  alignas(16) float xwd[PLB_MAXR][PL_MAXP];
+  alignas(16) float zwd[PLB_MAXR][PL_MAXP];        // dense: weight of slice z in bin pd, pre-multiplied by 1 / count
+};
+
+__device__ __forceinline__ void red4(float *dst, const float4 v) { atomicAdd(reinterpret_cast<float4 *>(dst), v); }
+
+// Literal gradient of one output bin for one channel (reference sample loops, roi_align_kernel.cu:590-632)
+__device__ void literal_bin_bwd_strided(const Axis &axw, const Axis &axh, const Axis &axd, int D, int H, int W, float *gc,
+                                        long long sz, long long sy, long long sx, int pd, int ph, int pw, float top) {
+  const float count = (float)(axd.S * axh.S * axw.S);
+  for (int iz = 0; iz < axd.S; ++iz) {
+    const Tap tz = axis_tap(axis_coord(axd, pd, iz), D);
+    for (int iy = 0; iy < axh.S; ++iy) {
+      const Tap ty = axis_tap(axis_coord(axh, ph, iy), H);
+      for (int ix = 0; ix < axw.S; ++ix) {
+        const Tap tx = axis_tap(axis_coord(axw, pw, ix), W);
+        if (!(tz.valid && ty.valid && tx.valid)) continue;
+        const float hxhy = __fmul_rn(tx.h, ty.h), lxhy = __fmul_rn(tx.l, ty.h);
+        const float hxly = __fmul_rn(tx.h, ty.l), lxly = __fmul_rn(tx.l, ty.l);
+        const float w[8] = {__fmul_rn(hxhy, tz.h), __fmul_rn(lxhy, tz.h), __fmul_rn(hxly, tz.h), __fmul_rn(lxly, tz.h),
+                            __fmul_rn(hxhy, tz.l), __fmul_rn(lxhy, tz.l), __fmul_rn(hxly, tz.l), __fmul_rn(lxly, tz.l)};
+        const long long zl = tz.low * sz, zh = tz.high * sz, yl = ty.low * sy, yh = ty.high * sy;
+        const long long xl = tx.low * sx, xh = tx.high * sx;
+        const long long off[8] = {zl + yl + xl, zl + yl + xh, zl + yh + xl, zl + yh + xh,
+                                  zh + yl + xl, zh + yl + xh, zh + yh + xl, zh + yh + xh};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) atomicAdd(gc + off[q], __fdiv_rn(__fmul_rn(top, w[q]), count));
+      }
+    }
+  }
+}
+
+template <int P, int PDT>
+__global__ void __launch_bounds__(PL_THREADS, 2)
+    roi_align3d_bwd_planar_kernel(const RoiParams p, int CG, int smem_floats, const int *__restrict__ order) {
+  extern __shared__ __align__(16) float planes[];
+  __shared__ PlanarBwdTables T;
+  constexpr int PP = P * P;
+  const int tid = threadIdx.x;
+  const int g = blockIdx.x / p.K, kslot = blockIdx.x - g * p.K;
+  const int k = order != nullptr ? __ldg(order + kslot) : kslot;
+  const int c_first = g * CG;
+  const int nch_all = min(CG, p.C - c_first);
+  const int PD = PDT > 0 ? PDT : p.PD;
+
+  float r[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) r[i] = __ldg(p.rois + (long long)k * 7 + i);
+  const int lvl = p.num_levels > 1 ? roi_level(r, p.num_levels, p.inv_finest) : 0;
+  const LevelDev L = p.lv[lvl];
+  const int b = (int)r[0];
+  const bool ok = b >= 0 && b < p.B;
+  const Axis axw = axis_setup(r[1], r[3], L.scale, P, p.sample_num);
+  const Axis axh = axis_setup(r[2], r[4], L.scale, P, p.sample_num);
+  const Axis axd = axis_setup(r[5], r[6], L.scale_d, PD, p.sample_num);
+  const long long out_elems = PDT > 0 ? (long long)PDT * PP : (long long)PD * PP;
+  const float *g_roi = p.grad_out + ((long long)k * p.C + c_first) * out_elems;
+  if (!ok) return;   // the forward wrote zeros for this RoI: no gradient
+  {
+    const int axis = tid >> 4, bin = tid & 15;
+    if (tid < 48) {
+      const int nb = axis == 2 ? PD : P;
+      const Axis ax = axis == 0 ? axw : axis == 1 ? axh : axd;
+      const int asize = axis == 0 ? L.W : axis == 1 ? L.H : L.D;
+      int lo = INT_MAX, hi = -1;
+      if (bin < nb) {
+        for (int i = 0; i < ax.S; ++i) {
+          const Tap t = axis_tap(axis_coord(ax, bin, i), asize);
+          if (t.valid) lo = min(lo, t.low), hi = max(hi, t.high);
+        }
+      }
+      T.lo[tid] = lo, T.hi[tid] = hi;
+    }
+    for (int i = tid; i < PLB_MAXR * PL_MAXP; i += PL_THREADS)
+      (&T.ywd[0][0])[i] = 0.0f, (&T.xwd[0][0])[i] = 0.0f, (&T.zwd[0][0])[i] = 0.0f;
+    if (tid < PLB_MAXR) T.ylo[tid] = INT_MAX, T.yhi[tid] = -1, T.xlo[tid] = INT_MAX, T.xhi[tid] = -1;
+  }
+  if (tid < 64) {
+    const int lo = tid < 48 ? T.lo[tid] : INT_MAX, hi = tid < 48 ? T.hi[tid] : -1;
+    const bool has = hi >= lo;
+    int mn = has ? lo : INT_MAX, mx = has ? hi : -1, wide = has ? hi - lo + 1 : 0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(FULL, mn, o)), mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+      wide = max(wide, __shfl_xor_sync(FULL, wide, o));
+    }
+    if ((tid & 15) == 0 && tid < 48) {
+      const int axis = tid >> 4;
+      T.box[8 + axis * 3 + 0] = mn, T.box[8 + axis * 3 + 1] = mx, T.box[8 + axis * 3 + 2] = wide;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int *q = T.box + 8;
+    const bool empty = q[1] < q[0] || q[4] < q[3] || q[7] < q[6];
+    const int RX = empty ? 0 : q[1] - q[0] + 1, RY = empty ? 0 : q[4] - q[3] + 1, RZ = empty ? 0 : q[7] - q[6] + 1;
+    const bool slow = q[2] > 4 || q[5] > 4 || q[8] > 4 || RX > PLB_MAXR || RY > PLB_MAXR || RZ > PLB_MAXR;
+    int CGs = 0;
+    if (!empty && !slow) {
+      const int per = RZ * PP + RZ * RY * P;   // T2 + T1 floats per channel
+      for (int cg = min((nch_all + 3) & ~3, PL_MAXCG); cg >= 4; cg -= 4)
+        if (cg * per <= smem_floats) {
+          CGs = cg;
+          break;
+        }
+    }
+    T.box[0] = empty ? 0 : q[0], T.box[1] = RX;
+    T.box[2] = empty ? 0 : q[3], T.box[3] = RY;
+    T.box[4] = empty ? 0 : q[6], T.box[5] = RZ;
+    T.box[6] = empty ? 1 : 0;
+    T.box[17] = CGs;
+  }
+  __syncthreads();
+  const int x0 = T.box[0], RX = T.box[1], y0 = T.box[2], RY = T.box[3], z0 = T.box[4], RZ = T.box[5];
+  const int CGs = T.box[17];
+  if (T.box[6] & 1) return;   // no sample inside the level: no gradient
+  const long long vox = (long long)L.D * L.H * L.W;
+  float *gb = L.grad + (long long)b * vox * p.C;
+  if (CGs == 0) {  // literal path (rare): one (channel, element) per thread and trip, scalar atomics
+    const long long sx = p.C, sy = sx * L.W, sz = sy * L.H;
+    for (long long i = tid; i < (long long)nch_all * out_elems; i += PL_THREADS) {
+      const int c = (int)(i / out_elems), e = (int)(i - (long long)c * out_elems);
+      const int pw = e % P, ph = (e / P) % P, pd = e / PP;
+      literal_bin_bwd_strided(axw, axh, axd, L.D, L.H, L.W, gb + c_first + c, sz, sy, sx, pd, ph, pw, __ldg(g_roi + i));
+    }
+    return;
+  }
+
+  // ---- per-bin taps (exact ranges), then the dense gather tables of the y and x axes
+  if (tid < 48) {
+    const int axis = tid >> 4, bin = tid & 15;
+    const int nb = axis == 2 ? PD : P;
+    if (bin < nb) {
+      const Axis ax = axis == 0 ? axw : axis == 1 ? axh : axd;
+      const int asize = axis == 0 ? L.W : axis == 1 ? L.H : L.D;
+      const int lo = T.lo[tid], hi = T.hi[tid];
+      float w[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      int off = 0, n = 0;
+      if (hi >= lo) {
+        n = hi - lo + 1;
+        off = lo - (axis == 0 ? x0 : axis == 1 ? y0 : z0);
+        for (int i = 0; i < ax.S; ++i) {
+          const Tap t = axis_tap(axis_coord(ax, bin, i), asize);
+          if (t.valid) {
+            const int a0 = t.low - lo, a1 = t.high - lo;
+            if (a0 == 0) w[0] += t.h; else if (a0 == 1) w[1] += t.h; else if (a0 == 2) w[2] += t.h; else w[3] += t.h;
+            if (a1 == 0) w[0] += t.l; else if (a1 == 1) w[1] += t.l; else if (a1 == 2) w[2] += t.l; else w[3] += t.l;
+          }
+        }
+      }
+      if (axis == 2) {
+        const float inv = __frcp_rn((float)(axd.S * axh.S * axw.S));
+#pragma unroll
+        for (int t = 0; t < 4; ++t) w[t] *= inv;
+        for (int t = 0; t < n; ++t) T.zwd[off + t][bin] = t == 0 ? w[0] : t == 1 ? w[1] : t == 2 ? w[2] : w[3];
+      } else {
+        float(*dense)[PL_MAXP] = axis == 0 ? T.xwd : T.ywd;
+        int *blo = axis == 0 ? T.xlo : T.ylo, *bhi = axis == 0 ? T.xhi : T.yhi;
+        for (int t = 0; t < n; ++t) {
+          dense[off + t][bin] = t == 0 ? w[0] : t == 1 ? w[1] : t == 2 ? w[2] : w[3];
+          atomicMin(&blo[off + t], bin);
+          atomicMax(&bhi[off + t], bin);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  const int rows = RZ * RY;
+  float *T2 = planes, *T1 = planes + (size_t)CGs * RZ * PP;   // T2: [g][z][q][4] = CGs * RZ * PP floats; then T1
+  const int npass = (nch_all + CGs - 1) / CGs;
+  for (int ip = 0; ip < npass; ++ip) {
+    const int c0 = ip * CGs, nch = min(CGs, nch_all - c0), NG = (nch + 3) >> 2;
+    // ---- z^T: a thread owns (q, group): the grad_out values of all PD bins (4 channels each) are requested together --
+    //      one exposed global latency per task, read exactly once, coalesced -- and stay in registers; every slice is
+    //      then one pass over the bins with the slice's dense weights (0 outside a bin's support; warp-uniform).
+    {
+      constexpr int NPD = PDT > 0 ? PDT : PL_MAXP;
+      for (int t = tid; t < PP * NG; t += PL_THREADS) {
+        const int cg = t / PP, q = t - cg * PP;
+        const float *gp = g_roi + (long long)(c0 + cg * 4) * out_elems + q;
+        const int left = nch - cg * 4;
+        float4 gv[NPD];
+#pragma unroll
+        for (int pd = 0; pd < NPD; ++pd) {
+          gv[pd] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (PDT > 0 || pd < PD) {
+            gv[pd].x = __ldcs(gp + pd * PP);
+            if (left > 1) gv[pd].y = __ldcs(gp + out_elems + pd * PP);
+            if (left > 2) gv[pd].z = __ldcs(gp + 2 * out_elems + pd * PP);
+            if (left > 3) gv[pd].w = __ldcs(gp + 3 * out_elems + pd * PP);
+          }
+        }
+        float *dst = T2 + ((cg * RZ) * PP + q) * 4;
+        for (int z = 0; z < RZ; ++z) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float *wz = &T.zwd[z][0];
+#pragma unroll
+          for (int pd = 0; pd < NPD; ++pd) {
+            const float w = wz[pd];
+            if (w != 0.0f) fma4(a, w, gv[pd]);
+          }
+          *reinterpret_cast<float4 *>(dst + z * PP * 4) = a;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- y^T: T1[g][z * RY + y][pw] = sum over the bins ph that hold row y
+    {
+      const unsigned ntask = (unsigned)(rows * P), total = ntask * (unsigned)NG;
+      const unsigned m_nt = fast_magic(ntask), m_ry = fast_magic((unsigned)RY);
+      for (unsigned t = tid; t < total; t += PL_THREADS) {
+        const unsigned cg = fast_div(t, ntask, m_nt), u = t - cg * ntask;
+        const unsigned row = u / P, pw = u - row * P;
+        const unsigned z = fast_div(row, (unsigned)RY, m_ry), y = row - z * (unsigned)RY;
+        const int plo = T.ylo[y], phi = T.yhi[y];
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *sp = T2 + ((cg * RZ + z) * PP + pw) * 4;
+        const float *wp = &T.ywd[y][0];
+        for (int ph = plo; ph <= phi; ++ph) fma4(a, wp[ph], *reinterpret_cast<const float4 *>(sp + ph * P * 4));
+        *reinterpret_cast<float4 *>(T1 + ((cg * rows + row) * P + pw) * 4) = a;
+      }
+    }
+    __syncthreads();
+    // ---- x^T + scatter: one vector red per (voxel, four channels); groups fastest: 4 lanes = 64 contiguous bytes
+    {
+      const unsigned total = (unsigned)(rows * RX * NG);
+      const unsigned m_ng = fast_magic((unsigned)NG), m_rx = fast_magic((unsigned)RX), m_ry = fast_magic((unsigned)RY);
+      for (unsigned t = tid; t < total; t += PL_THREADS) {
+        const unsigned u = fast_div(t, (unsigned)NG, m_ng), cg = t - u * (unsigned)NG;
+        const unsigned row = fast_div(u, (unsigned)RX, m_rx), x = u - row * (unsigned)RX;
+        const unsigned z = fast_div(row, (unsigned)RY, m_ry), y = row - z * (unsigned)RY;
+        const int plo = T.xlo[x], phi = T.xhi[x];
+        if (phi < plo) continue;   // no bin samples this voxel column
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *sp = T1 + ((cg * rows + row) * P) * 4;
+        const float *wp = &T.xwd[x][0];
+        for (int pw = plo; pw <= phi; ++pw) fma4(a, wp[pw], *reinterpret_cast<const float4 *>(sp + pw * 4));
+        float *dst = gb + ((long long)((z0 + (int)z) * L.H + (y0 + (int)y)) * L.W + (x0 + (int)x)) * p.C + c_first + c0 + cg * 4;
+        const int left = nch - (int)cg * 4;
+        if (left >= 4) {
+          red4(dst, a);
+        } else {
+          atomicAdd(dst, a.x);
+          if (left > 1) atomicAdd(dst + 1, a.y);
+          if (left > 2) atomicAdd(dst + 2, a.z);
+        }
+      }
+    }
+    // (the next pass's z^T writes T2 only; its barrier separates this pass's T1 reads from the next y^T's writes)
+  }
+}
+
 }  // namespace
 
 bool fwd_planar_ok(const RoiParams &p, int layout) {
@@ -614,6 +893,50 @@ int launch_fwd_planar(RoiParams &p, int layout, cudaStream_t st) {
 #undef ROI3D_PLANAR_GO
   if (order != nullptr) ROI3D_CUDA(cudaFreeAsync(order, st));
   return rc;
+}
+
+bool bwd_planar_ok(const RoiParams &p) {
+  if (p.PW != p.PH || p.PW != 14 || p.PD < 1 || p.PD > PL_MAXP) return false;   // (7-wide: the per-warp kernel is faster)
+  if (p.bug_compat || p.C % 4 != 0) return false;
+  if ((long long)p.K * ((p.C + 63) / 64) >= 2147483647LL) return false;
+  for (int l = 0; l < p.num_levels; ++l)
+    if ((reinterpret_cast<uintptr_t>(p.lv[l].grad) & 15) != 0) return false;
+  return (reinterpret_cast<uintptr_t>(p.grad_out) & 3) == 0;
+}
+
+int launch_bwd_planar(RoiParams &p, cudaStream_t st) {
+  int CG = 64;
+  if (p.C < CG) CG = p.C;
+  const int ngroups = ceil_div(p.C, CG);
+  const long long blocks = (long long)p.K * ngroups;
+  const int smem_floats = g_planar_smem_floats > 0 ? g_planar_smem_floats : PL_SMEM_FLOATS;
+  const size_t smem = (size_t)smem_floats * sizeof(float);
+  int *order = nullptr;
+  if (p.K > 1 && p.K <= 8192) {
+    cudaMemPool_t pool;
+    const int rc = stream_pool(&pool);
+    if (rc) return rc;
+    ROI3D_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&order), (size_t)p.K * sizeof(int), pool, st));
+    roi_align3d_order_kernel<<<ceil_div(p.K, 256), 256, (size_t)p.K * sizeof(unsigned long long), st>>>(p, order);
+    ROI3D_LAUNCH_CHECK();
+  }
+  static size_t attr_set[2] = {0, 0};
+  if (p.PD == 14) {
+    if (attr_set[0] < smem) {
+      ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_bwd_planar_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[0] = smem;
+    }
+    roi_align3d_bwd_planar_kernel<14, 14><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, smem_floats, order);
+  } else {
+    if (attr_set[1] < smem) {
+      ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_bwd_planar_kernel<14, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[1] = smem;
+    }
+    roi_align3d_bwd_planar_kernel<14, 0><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, smem_floats, order);
+  }
+  ROI3D_LAUNCH_CHECK();
+  if (order != nullptr) ROI3D_CUDA(cudaFreeAsync(order, st));
+  return ROI3D_OK;
 }
 
 }  // namespace roi3d

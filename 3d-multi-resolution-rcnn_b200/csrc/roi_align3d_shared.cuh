@@ -213,6 +213,10 @@ int stream_pool(cudaMemPool_t *out);
 bool fwd_planar_ok(const RoiParams &p, int layout);
 int launch_fwd_planar(RoiParams &p, int layout, cudaStream_t st);
 
+// Planar backward (14-wide outputs, channels-last gradients): transposed stages, one vector red per (voxel, 4 channels).
+bool bwd_planar_ok(const RoiParams &p);
+int launch_bwd_planar(RoiParams &p, cudaStream_t st);
+
 bool fwd_stream_ok(const RoiParams &p);
 int launch_fwd_stream(RoiParams &p, cudaStream_t st);
 
