@@ -1898,12 +1898,14 @@ static int dispatch_bwd(RoiParams &p, cudaStream_t st) {
     return launch_generic<1>(p, false, st);
   }
   if (p.PW == 7) {
+    if (v == 60 && bwd_planar_ok(p)) return launch_bwd_planar(p, st);   // (A/B: the planar backward on 7-wide outputs)
+    if (v == 0 && bwd_stream_ok(p)) return launch_bwd_stream(p, st);    // one red per voxel (roi_align3d_stream.cu)
     if (v == 1 || cvmax == 1) return launch_bwd<7, 7, 1, 40>(p, st);
-    if (v == 0 && p.PH <= 16 && p.PD <= 16 && cvmax >= 2) return launch_bwd2<7, 7, 2, true>(p, st);
+    if ((v == 0 || v == 50) && p.PH <= 16 && p.PD <= 16 && cvmax >= 2) return launch_bwd2<7, 7, 2, true>(p, st);
     return launch_bwd<7, 7, 2, 26>(p, st);  // per-warp tables (v == 3, or PH / PD > 16)
   }
   if (p.PW == 14) {
-    if (v == 0 && bwd_planar_ok(p)) return launch_bwd_planar(p, st);   // transposed planar stages (roi_align3d_planar.cu)
+    if ((v == 0 || v == 60) && bwd_planar_ok(p)) return launch_bwd_planar(p, st);   // transposed planar stages (roi_align3d_planar.cu)
     if (v == 1 || cvmax == 1) return launch_bwd<14, 7, 1, 40>(p, st);
     if ((v == 0 || v == 50) && p.PH <= 16 && p.PD <= 16 && cvmax >= 2) return launch_bwd2<14, 2, 2, true, 4>(p, st);  // 2 ph rows per warp
     return launch_bwd<14, 4, 2, 30>(p, st);  // per-warp tables (v == 3, or PH / PD > 16)

@@ -896,13 +896,28 @@ int launch_fwd_planar(RoiParams &p, int layout, cudaStream_t st) {
 }
 
 bool bwd_planar_ok(const RoiParams &p) {
-  if (p.PW != p.PH || p.PW != 14 || p.PD < 1 || p.PD > PL_MAXP) return false;   // (7-wide: the per-warp kernel is faster)
+  if (p.PW != p.PH || (p.PW != 14 && p.PW != 7) || p.PD < 1 || p.PD > PL_MAXP) return false;
   if (p.bug_compat || p.C % 4 != 0) return false;
   if ((long long)p.K * ((p.C + 63) / 64) >= 2147483647LL) return false;
   for (int l = 0; l < p.num_levels; ++l)
     if ((reinterpret_cast<uintptr_t>(p.lv[l].grad) & 15) != 0) return false;
   return (reinterpret_cast<uintptr_t>(p.grad_out) & 3) == 0;
 }
+
+namespace {
+template <int P, int PDT>
+int launch_bwd_planar_cfg(const RoiParams &p, int CG, long long blocks, int smem_floats, const int *order, cudaStream_t st) {
+  const size_t smem = (size_t)smem_floats * sizeof(float);
+  static size_t attr_set = 0;
+  if (attr_set < smem) {
+    ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_bwd_planar_kernel<P, PDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
+  roi_align3d_bwd_planar_kernel<P, PDT><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, smem_floats, order);
+  ROI3D_LAUNCH_CHECK();
+  return ROI3D_OK;
+}
+}  // namespace
 
 int launch_bwd_planar(RoiParams &p, cudaStream_t st) {
   int CG = 64;
@@ -920,21 +935,12 @@ int launch_bwd_planar(RoiParams &p, cudaStream_t st) {
     roi_align3d_order_kernel<<<ceil_div(p.K, 256), 256, (size_t)p.K * sizeof(unsigned long long), st>>>(p, order);
     ROI3D_LAUNCH_CHECK();
   }
-  static size_t attr_set[2] = {0, 0};
-  if (p.PD == 14) {
-    if (attr_set[0] < smem) {
-      ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_bwd_planar_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set[0] = smem;
-    }
-    roi_align3d_bwd_planar_kernel<14, 14><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, smem_floats, order);
-  } else {
-    if (attr_set[1] < smem) {
-      ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_bwd_planar_kernel<14, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set[1] = smem;
-    }
-    roi_align3d_bwd_planar_kernel<14, 0><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, smem_floats, order);
-  }
-  ROI3D_LAUNCH_CHECK();
+  int rc;
+  if (p.PW == 14) rc = p.PD == 14 ? launch_bwd_planar_cfg<14, 14>(p, CG, blocks, smem_floats, order, st)
+                                  : launch_bwd_planar_cfg<14, 0>(p, CG, blocks, smem_floats, order, st);
+  else rc = p.PD == 7 ? launch_bwd_planar_cfg<7, 7>(p, CG, blocks, smem_floats, order, st)
+                      : launch_bwd_planar_cfg<7, 0>(p, CG, blocks, smem_floats, order, st);
+  if (rc) return rc;
   if (order != nullptr) ROI3D_CUDA(cudaFreeAsync(order, st));
   return ROI3D_OK;
 }

@@ -217,6 +217,10 @@ int launch_fwd_planar(RoiParams &p, int layout, cudaStream_t st);
 bool bwd_planar_ok(const RoiParams &p);
 int launch_bwd_planar(RoiParams &p, cudaStream_t st);
 
+// Streamed backward (7 x 7 x PD outputs, channels-last gradients, C % 64 == 0): one vector red per voxel, RoI and channel.
+bool bwd_stream_ok(const RoiParams &p);
+int launch_bwd_stream(RoiParams &p, cudaStream_t st);
+
 bool fwd_stream_ok(const RoiParams &p);
 int launch_fwd_stream(RoiParams &p, cudaStream_t st);
 

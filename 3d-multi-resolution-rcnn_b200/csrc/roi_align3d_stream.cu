@@ -74,6 +74,7 @@ struct alignas(16) StreamPlan {
   float yw[8][4];
   float zwd[ST_RZMAX][8];  // dense: weight of slice z (from z0) in bin pd
   float ywd[ST_RMAX][8];   // dense: weight of row y (from y0) in bin ph
+  float xwd[ST_RMAX][8];   // dense: weight of voxel x (from x0) in bin pw (the backward's x expansion)
 };
 static_assert(sizeof(StreamPlan) % 16 == 0, "bulk copies move multiples of 16 bytes");
 constexpr int PLAN_BYTES = (int)sizeof(StreamPlan);
@@ -285,6 +286,10 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
     pl->xoff[bin] = off;
 #pragma unroll
     for (int t = 0; t < 4; ++t) pl->xw[bin][t] = ws[t];
+    for (int x = 0; x < ST_RMAX; ++x) {
+      const int t = x - off;
+      pl->xwd[x][bin] = (t >= 0 && t < 4) ? (t == 0 ? ws[0] : t == 1 ? ws[1] : t == 2 ? ws[2] : ws[3]) : 0.0f;
+    }
   } else if (role == 1) {
     pl->ylo[bin] = (n > 0 && stream) ? lo - y0 : 0;
     pl->yn[bin] = (n > 0 && stream) ? n : 0;
@@ -649,6 +654,142 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) roi_align3d_fwd_stream_kerne
   asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
 }
 
+// =================================================================================================================
+// Backward of the streamed formulation (bbox branch: 7 x 7 x PD outputs, channels-last gradients, C % 64 == 0).
+//
+// Replaces (reference): ROIAlignBackward3D / bilinear_interpolate_gradient_3d, roi_align_kernel.cu:519-636, :383-442.
+// Same plans and schedule as the forward (one persistent 16-warp CTA per SM, items = (RoI, 64-channel chunk), largest
+// footprints first, round-robin over the CTAs).  The item's grad_out block [64 channels][PD * 49] is copied into shared
+// memory TRANSPOSED ([element][channel], 4-byte cp.async, the next item's block in flight while this one is reduced),
+// so that lanes = channel pairs read it with LDS.64.  The unit of work is then one (z, y) ROW of the footprint per
+// warp: V[pw] = sum over the (ph, pd) bins that hold (y, z) of wy * wz * g[pd][ph][pw]  (a handful of warp-uniform
+// non-zero weight pairs, 7 LDS.64 + FFMA2 each), then for every voxel x of the row sum_pw wx[x][pw] * V[pw] and ONE
+// 8-byte vector red per lane: every voxel of the footprint receives exactly one red per RoI and channel -- the
+// per-warp kernel (roi_align3d_bwd2_kernel) issues one per (voxel, pd bin whose support holds z), ~2.6x as many.
+// =================================================================================================================
+constexpr int SB_GSTRIDE = 66;                              // floats per element of the transposed image (2-way STS conflicts)
+constexpr int SB_GBYTES = (343 * SB_GSTRIDE * 4 + 15) / 16 * 16;
+constexpr int SB_PLAN = 2 * SB_GBYTES;
+constexpr int SB_TOTAL = SB_PLAN + 2 * PLAN_BYTES;
+static_assert(SB_TOTAL <= 232448, "shared memory budget of one CTA per SM");
+
+__global__ void __launch_bounds__(ST_WARPS * 32, 1) roi_align3d_bwd_stream_kernel(const __grid_constant__ StreamArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = a.p.K, total = a.total_items, pdhw = a.pdhw, C = a.p.C;
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");   // the plans come from the kernel launched just before
+
+  auto issue_load = [&](int idx, int buf) {
+    const int chunk = idx / K, r = idx - chunk * K;
+    const StreamPlan *gp = a.plans + r;
+    if (tid < PLAN_BYTES / 16) {
+      const unsigned dst = s_u32(smem + SB_PLAN + buf * PLAN_BYTES) + tid * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(reinterpret_cast<const char *>(gp) + tid * 16)
+                   : "memory");
+    }
+    const int k = __ldcg(&gp->k);
+    const float *src = a.p.grad_out + ((long long)k * C + (long long)chunk * ST_CH) * pdhw;
+    const unsigned g0 = s_u32(smem + buf * SB_GBYTES);
+    for (int ch = warp; ch < ST_CH; ch += ST_WARPS) {
+      const float *sp = src + (long long)ch * pdhw;
+      for (int e = lane; e < pdhw; e += 32) {
+        const unsigned dst = g0 + (unsigned)(e * SB_GSTRIDE + ch) * 4u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(sp + e) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  int idx = (int)blockIdx.x;
+  if (idx < total) issue_load(idx, 0);
+  for (int it_n = 0; idx < total; ++it_n, idx += (int)gridDim.x) {
+    const int buf = it_n & 1;
+    const int nxt = idx + (int)gridDim.x;
+    if (nxt < total) {
+      issue_load(nxt, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
+    const StreamPlan *P = reinterpret_cast<const StreamPlan *>(smem + SB_PLAN + buf * PLAN_BYTES);
+    const float *G = reinterpret_cast<const float *>(smem + buf * SB_GBYTES) + lane * 2;
+    const int chunk = idx / K;
+    const int pflags = P->flags;
+    if (!(pflags & (PLAN_EMPTY | PLAN_SLOW))) {
+      const LevelDev L = a.p.lv[P->lvl];
+      const int RY = P->RY, RX = P->RX, nrows = P->nrows, spt = P->spt;
+      const float inv = P->inv_count;
+      float *gbase = L.grad + ((((long long)P->b * L.D + P->z0) * L.H + P->y0) * L.W + P->x0) * C + chunk * ST_CH + lane * 2;
+      for (int row = warp; row < nrows; row += ST_WARPS) {
+        const int z = (row * spt) >> 16, y = row - z * RY;
+        float wy[8], wz[8];
+        {
+          const float4 ya = *reinterpret_cast<const float4 *>(&P->ywd[y][0]), yb = *reinterpret_cast<const float4 *>(&P->ywd[y][4]);
+          const float4 za = *reinterpret_cast<const float4 *>(&P->zwd[z][0]), zb = *reinterpret_cast<const float4 *>(&P->zwd[z][4]);
+          wy[0] = ya.x, wy[1] = ya.y, wy[2] = ya.z, wy[3] = ya.w, wy[4] = yb.x, wy[5] = yb.y, wy[6] = yb.z, wy[7] = yb.w;
+          wz[0] = za.x * inv, wz[1] = za.y * inv, wz[2] = za.z * inv, wz[3] = za.w * inv;
+          wz[4] = zb.x * inv, wz[5] = zb.y * inv, wz[6] = zb.z * inv, wz[7] = zb.w * inv;
+        }
+        float2 V[7];
+#pragma unroll
+        for (int pw = 0; pw < 7; ++pw) V[pw] = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int ph = 0; ph < 7; ++ph) {
+          if (wy[ph] != 0.0f) {   // warp-uniform
+#pragma unroll
+            for (int pd = 0; pd < 7; ++pd) {
+              if (wz[pd] != 0.0f) {
+                const float w = wy[ph] * wz[pd];
+                const float2 w2 = make_float2(w, w);
+                const float *gp = G + (pd * 49 + ph * 7) * SB_GSTRIDE;
+#pragma unroll
+                for (int pw = 0; pw < 7; ++pw)
+                  V[pw] = __ffma2_rn(w2, *reinterpret_cast<const float2 *>(gp + pw * SB_GSTRIDE), V[pw]);
+              }
+            }
+          }
+        }
+        float *dst = gbase + ((long long)z * L.H + y) * L.W * C;
+        for (int x = 0; x < RX; ++x) {
+          const float4 xa = *reinterpret_cast<const float4 *>(&P->xwd[x][0]), xb = *reinterpret_cast<const float4 *>(&P->xwd[x][4]);
+          float2 acc = __fmul2_rn(make_float2(xa.x, xa.x), V[0]);
+          acc = __ffma2_rn(make_float2(xa.y, xa.y), V[1], acc);
+          acc = __ffma2_rn(make_float2(xa.z, xa.z), V[2], acc);
+          acc = __ffma2_rn(make_float2(xa.w, xa.w), V[3], acc);
+          acc = __ffma2_rn(make_float2(xb.x, xb.x), V[4], acc);
+          acc = __ffma2_rn(make_float2(xb.y, xb.y), V[5], acc);
+          acc = __ffma2_rn(make_float2(xb.z, xb.z), V[6], acc);
+          atomicAdd(reinterpret_cast<float2 *>(dst + (long long)x * C), acc);
+        }
+      }
+    } else if (pflags & PLAN_SLOW) {
+      // literal gradient of the bins of a RoI the tables cannot express (rare): one bin per warp and trip
+      Item it;
+      const int k = P->k;
+      it.k = k, it.krow = k, it.chunk = chunk, it.pd = 0, it.ph0 = 0, it.rows = 1, it.lvl = P->lvl;
+      float r[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) r[i] = __ldg(a.p.rois + (long long)k * 7 + i);
+      it.L = a.p.lv[it.lvl];
+      it.b = (int)r[0];
+      it.ok = true;
+      it.axw = axis_setup(r[1], r[3], it.L.scale, a.p.PW, a.p.sample_num);
+      it.axh = axis_setup(r[2], r[4], it.L.scale, a.p.PH, a.p.sample_num);
+      it.axd = axis_setup(r[5], r[6], it.L.scale_d, a.p.PD, a.p.sample_num);
+      const long long vox = (long long)it.L.D * it.L.H * it.L.W;
+      float *gb = it.L.grad + (long long)it.b * vox * C + chunk * ST_CH + lane * 2;
+      for (int e = warp; e < pdhw; e += ST_WARPS) {
+        const int pd = e / 49, q = e - pd * 49, ph = q / 7, pw = q - ph * 7;
+        const float2 t2 = *reinterpret_cast<const float2 *>(G + e * SB_GSTRIDE);
+        const float top[2] = {t2.x, t2.y};
+        literal_bin_bwd<2>(it, gb, C, pd, ph, pw, top);
+      }
+    }
+    __syncthreads();   // everyone is done with this buffer before the next trip's loads overwrite it
+  }
+}
+
 // ---- host: tensor maps -------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -839,6 +980,62 @@ int launch_fwd_stream(RoiParams &p, cudaStream_t st) {
     case 2: return launch_cfg<5, 24576>(p, a, st, sm_count);
     default: return launch_cfg<3, 43008>(p, a, st, sm_count);
   }
+}
+
+bool bwd_stream_ok(const RoiParams &p) {
+  if (p.PW != 7 || p.PH != 7 || p.PD < 1 || p.PD > 7) return false;
+  if (p.C % ST_CH != 0 || p.num_levels > ST_MAX_LEVELS || p.bug_compat) return false;
+  if ((long long)p.K * (p.C / ST_CH) >= 2147483647LL) return false;
+  for (int l = 0; l < p.num_levels; ++l)
+    if ((reinterpret_cast<uintptr_t>(p.lv[l].grad) & 7) != 0) return false;
+  return (reinterpret_cast<uintptr_t>(p.grad_out) & 3) == 0;
+}
+
+int launch_bwd_stream(RoiParams &p, cudaStream_t st) {
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    ROI3D_CUDA(cudaGetDevice(&dev));
+    ROI3D_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  StreamArgs a;
+  a.p = p;
+  for (int l = 0; l < ST_MAX_LEVELS; ++l) a.maps[l] = nullptr;
+  a.total_items = p.K * (p.C / ST_CH);
+  a.pdhw = p.PD * 49;
+  a.debug = 0;
+  cudaMemPool_t pool;
+  int rc = stream_pool(&pool);
+  if (rc) return rc;
+  const size_t plan_bytes = (size_t)p.K * sizeof(StreamPlan);
+  unsigned char *ws = nullptr;
+  ROI3D_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), plan_bytes + 16, pool, st));
+  StreamPlan *plans = reinterpret_cast<StreamPlan *>(ws);
+  int *counter = reinterpret_cast<int *>(ws + plan_bytes);
+  const int sort = p.K <= ST_SORT_MAX ? 1 : 0;
+  const int grid = a.total_items < sm_count ? a.total_items : sm_count;
+  RoiParams pp = p;
+  pp.lvls_out = nullptr;   // (the forward reports the levels)
+  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(pp, plans, counter, sort, 43008, 0);
+  ROI3D_LAUNCH_CHECK();
+  a.plans = plans, a.counter = counter;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
+    attr_set = true;
+  }
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(ST_WARPS * 32), cfg.dynamicSmemBytes = SB_TOTAL, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    ROI3D_CUDA(cudaLaunchKernelEx(&cfg, roi_align3d_bwd_stream_kernel, a));
+  }
+  ROI3D_LAUNCH_CHECK();
+  ROI3D_CUDA(cudaFreeAsync(ws, st));
+  return ROI3D_OK;
 }
 
 }  // namespace roi3d

@@ -1268,6 +1268,77 @@ def test_mask_target_matches_resize_restatement(oracle, dev, values):
     assert mask_target_single(torch.zeros((0, 6), device=dev), torch.zeros(0, dtype=torch.long, device=dev), gt, cfg).shape == (0, 28, 28)
 
 
+PLANAR_CASES_FOR_BWD = [
+    # PLANAR_CASES rows with 14-wide outputs (+ plane storage in floats, 0 = default)
+    ((2, 20, 10, 32, 32), 14, 14, 0.125, 0.25, 2, 50, (256, 256, 40), 0),
+    ((1, 12, 8, 16, 16), 14, 10, 0.25, 0.5, 2, 30, (64, 64, 16), 0),
+    ((1, 8, 6, 12, 12), 14, 14, 0.25, 0.5, 3, 20, (48, 48, 12), 0),
+    ((2, 20, 10, 32, 32), 14, 14, 0.125, 0.25, 2, 50, (256, 256, 40), 5000),
+    ((1, 40, 12, 20, 20), 14, 14, 0.25, 0.5, 0, 12, (80, 80, 24), 0),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", STREAM_CASES)
+def test_roi_align_backward_streamed_kernel(oracle, dev, case):
+    """The streamed backward (7x7xPD outputs, C % 64 == 0, channels-last gradients; one vector red per voxel, RoI and
+    channel): oracle tolerance, with the per-warp kernel (tuning variant 50) on the same inputs beside it.  The RoI set
+    holds empty, inverted and whole-map RoIs (literal path inside the same launch)."""
+    import roi3d_b200
+    from roi3d_b200.ops import RoIAlign3D
+    shape, pdp, sc, scd, sn, k, img = case
+    B, C, D, H, W = shape
+    rois = np.concatenate([synth.c2_rois(k, seed=6, img=img, batch=B),
+                           synth.adversarial_rois(shape[2:], sc, scd, batch=B),
+                           np.array([[B - 1, 2, 3, img[0] - 4, img[1] - 6, 1, img[2] - 3]], np.float32)], 0)
+    ok = (rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2]) & (rois[:, 6] >= rois[:, 5])
+    rois = rois[ok] if sn == 0 else rois
+    g = _feats((rois.shape[0], C, pdp, 7, 7), 8)
+    want = oracle.roi_align3d_backward(g, rois, shape, sc, scd, sn)
+    grads = {}
+    for variant in (0, 50):
+        ft = cl(torch.zeros(shape, device=dev)).requires_grad_(True)
+        roi3d_b200._lib.set_tuning(1, variant)
+        try:
+            RoIAlign3D(7, pdp, sc, scd, sn)(ft, torch.from_numpy(rois).to(dev)).backward(torch.from_numpy(g).to(dev))
+        finally:
+            roi3d_b200._lib.set_tuning(1, 0)
+        grads[variant] = ft.grad.cpu().numpy()
+        assert rel_err(grads[variant], want) <= BWD_TOL
+    assert rel_err(grads[0], grads[50]) <= BWD_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in PLANAR_CASES_FOR_BWD])
+def test_roi_align_backward_planar_kernel(oracle, dev, case):
+    """The planar backward (14-wide outputs, channels-last gradients): oracle tolerance, per-warp kernel (variant 50)
+    beside it; smem_floats = 5000 forces four channels per pass and sends the largest footprints down the literal path."""
+    import roi3d_b200
+    from roi3d_b200.ops import RoIAlign3D
+    shape, ps, pdp, sc, scd, sn, k, img, smem_floats = case
+    B, C, D, H, W = shape
+    rois = np.concatenate([synth.c2_rois(k, seed=72, img=img, batch=B),
+                           synth.adversarial_rois(shape[2:], sc, scd, batch=B),
+                           np.array([[B - 1, 2, 3, img[0] - 4, img[1] - 6, 1, img[2] - 3]], np.float32)], 0)
+    ok = (rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2]) & (rois[:, 6] >= rois[:, 5])
+    rois = rois[ok] if sn == 0 else rois
+    g = _feats((rois.shape[0], C, pdp, ps, ps), 9)
+    want = oracle.roi_align3d_backward(g, rois, shape, sc, scd, sn)
+    grads = {}
+    for variant in (0, 50):
+        ft = cl(torch.zeros(shape, device=dev)).requires_grad_(True)
+        roi3d_b200._lib.set_tuning(1, variant)
+        roi3d_b200._lib.set_tuning(10, smem_floats)
+        try:
+            RoIAlign3D(ps, pdp, sc, scd, sn)(ft, torch.from_numpy(rois).to(dev)).backward(torch.from_numpy(g).to(dev))
+        finally:
+            roi3d_b200._lib.set_tuning(1, 0)
+            roi3d_b200._lib.set_tuning(10, 0)
+        grads[variant] = ft.grad.cpu().numpy()
+        assert rel_err(grads[variant], want) <= BWD_TOL
+    assert rel_err(grads[0], grads[50]) <= BWD_TOL
+
+
 PLANAR_CASES = [
     # (B, C, D, H, W), out_size, out_size_depth, scale, scale_d, sample_num, n_rois, roi image (W, H, D)
     ((2, 24, 10, 24, 40), 7, 7, 0.25, 0.5, 2, 60, (160, 96, 20)),

@@ -59,3 +59,28 @@ a, b = res["per-warp bwd2 (variant 50)"], res["planar"]
 for l in range(4):
     d = (a[l] - b[l]).abs().max().item()
     print("level %d: max |diff| %.3g  (max |grad| %.3g)" % (l, d, a[l].abs().max().item()))
+
+# ---- C2 (bbox branch, 7^3): per-warp bwd2 (default) vs the planar backward (variant 60)
+from roi3d_b200.ops import RoIAlign3D  # noqa: E402
+del pyr, o3, g3, res, a, b
+torch.cuda.empty_cache()
+f = torch.randn(1, 256, 40, 128, 128, device=dev).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+r2 = torch.from_numpy(synth.c2_rois(512, seed=2)).to(dev)
+layer = RoIAlign3D(7, 7, 0.25, 0.5, 2)
+o2 = layer(f, r2)
+g2 = torch.randn_like(o2)
+
+
+def bwd2():
+    f.grad = None
+    o2.backward(g2, retain_graph=True)
+
+
+grads = {}
+for name, v in (("per-warp bwd2", 50), ("planar (variant 60)", 60), ("streamed", 0)):
+    _lib.set_tuning(1, v)
+    bwd2()
+    grads[name] = f.grad.clone()
+    print("C2 backward incl. zero-fill, %s: %.1f us" % (name, timeit(bwd2)), flush=True)
+_lib.set_tuning(1, 0)
+print("C2 max |diff| planar %.3g streamed %.3g" % ((grads["per-warp bwd2"] - grads["planar (variant 60)"]).abs().max().item(), (grads["per-warp bwd2"] - grads["streamed"]).abs().max().item()))
