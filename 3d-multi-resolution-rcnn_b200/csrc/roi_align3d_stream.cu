@@ -751,8 +751,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) roi_align3d_bwd_stream_kerne
           }
         }
         float *dst = gbase + ((long long)z * L.H + y) * L.W * C;
+        const float4 *xw4 = reinterpret_cast<const float4 *>(&P->xwd[0][0]);
+#pragma unroll 2
         for (int x = 0; x < RX; ++x) {
-          const float4 xa = *reinterpret_cast<const float4 *>(&P->xwd[x][0]), xb = *reinterpret_cast<const float4 *>(&P->xwd[x][4]);
+          const float4 xa = xw4[0], xb = xw4[1];
           float2 acc = __fmul2_rn(make_float2(xa.x, xa.x), V[0]);
           acc = __ffma2_rn(make_float2(xa.y, xa.y), V[1], acc);
           acc = __ffma2_rn(make_float2(xa.z, xa.z), V[2], acc);
@@ -760,7 +762,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) roi_align3d_bwd_stream_kerne
           acc = __ffma2_rn(make_float2(xb.x, xb.x), V[4], acc);
           acc = __ffma2_rn(make_float2(xb.y, xb.y), V[5], acc);
           acc = __ffma2_rn(make_float2(xb.z, xb.z), V[6], acc);
-          atomicAdd(reinterpret_cast<float2 *>(dst + (long long)x * C), acc);
+          atomicAdd(reinterpret_cast<float2 *>(dst), acc);
+          dst += C, xw4 += 2;
         }
       }
     } else if (pflags & PLAN_SLOW) {
