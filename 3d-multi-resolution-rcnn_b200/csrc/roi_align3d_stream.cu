@@ -272,43 +272,44 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
     pl->inv_count = __frcp_rn((float)(axd.S * axh.S * axw.S));
     pl->spt = spt, pl->tps = tps, pl->pad = 0;
   }
+  // per-bin words; the x taps are shifted right so that tap NT-1 still lies inside the RXB-wide box (the shifted-in weights are 0)
+  int off_d = 0;                                 // first voxel of this lane's bin in its dense table (x: after the shift)
+  float wd[4] = {0.0f, 0.0f, 0.0f, 0.0f};        // and its weights
+  const bool on = n > 0 && stream;
   if (role == 0) {
-    // shift the taps right so that tap NT-1 still lies inside the RXB-wide box (the shifted-in weights are 0)
-    int off = (n > 0 && stream) ? lo - x0 : 0;
+    int off = on ? lo - x0 : 0;
     const int sh = max(0, off + NT - RXB);
     off -= sh;
-    float ws[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (n > 0 && stream) {
+    if (on) {
 #pragma unroll
       for (int t = 0; t < 4; ++t)
-        if (t + sh < 4) add_tap(ws, t + sh, w[t]);
+        if (t + sh < 4) add_tap(wd, t + sh, w[t]);
     }
+    off_d = off;
     pl->xoff[bin] = off;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) pl->xw[bin][t] = ws[t];
-    for (int x = 0; x < ST_RMAX; ++x) {
-      const int t = x - off;
-      pl->xwd[x][bin] = (t >= 0 && t < 4) ? (t == 0 ? ws[0] : t == 1 ? ws[1] : t == 2 ? ws[2] : ws[3]) : 0.0f;
+    *reinterpret_cast<float4 *>(&pl->xw[bin][0]) = make_float4(wd[0], wd[1], wd[2], wd[3]);
+  } else if (role == 1 || role == 2) {
+    off_d = on ? lo - (role == 1 ? y0 : z0) : 0;
+    if (on) wd[0] = w[0], wd[1] = w[1], wd[2] = w[2], wd[3] = w[3];
+    if (role == 1) {
+      pl->ylo[bin] = off_d;
+      pl->yn[bin] = on ? n : 0;
+      *reinterpret_cast<float4 *>(&pl->yw[bin][0]) = make_float4(wd[0], wd[1], wd[2], wd[3]);
     }
-  } else if (role == 1) {
-    pl->ylo[bin] = (n > 0 && stream) ? lo - y0 : 0;
-    pl->yn[bin] = (n > 0 && stream) ? n : 0;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) pl->yw[bin][t] = (n > 0 && stream) ? w[t] : 0.0f;
-    const int yl = (n > 0 && stream) ? lo - y0 : 0;
-    for (int y = 0; y < ST_RMAX; ++y) {
-      const int t = y - yl;
-      float v = 0.0f;
-      if (n > 0 && stream && t >= 0 && t < n) v = t == 0 ? w[0] : t == 1 ? w[1] : t == 2 ? w[2] : w[3];
-      pl->ywd[y][bin] = v;
-    }
-  } else if (role == 2) {
-    const int zl = (n > 0 && stream) ? lo - z0 : 0;
-    for (int z = 0; z < ST_RZMAX; ++z) {
-      const int t = z - zl;
-      float v = 0.0f;
-      if (n > 0 && stream && t >= 0 && t < n) v = t == 0 ? w[0] : t == 1 ? w[1] : t == 2 ? w[2] : w[3];
-      pl->zwd[z][bin] = v;
+  }
+  // dense [voxel][bin] tables (x, y, z), written by the whole warp: element e = voxel * 8 + bin takes its weight from the
+  // lane that owns the bin (role * 8 + bin), consecutive lanes = consecutive floats
+#pragma unroll 1
+  for (int tb = 0; tb < 3; ++tb) {
+    const int nvox = tb == 2 ? ST_RZMAX : ST_RMAX;
+    float *base = tb == 0 ? &pl->xwd[0][0] : tb == 1 ? &pl->ywd[0][0] : &pl->zwd[0][0];
+    for (int e0 = 0; e0 < nvox * 8; e0 += 32) {
+      const int e = e0 + lane, src = tb * 8 + (e & 7);
+      const int so = __shfl_sync(FULL, off_d, src);
+      const float s0 = __shfl_sync(FULL, wd[0], src), s1 = __shfl_sync(FULL, wd[1], src);
+      const float s2 = __shfl_sync(FULL, wd[2], src), s3 = __shfl_sync(FULL, wd[3], src);
+      const int t = (e >> 3) - so;
+      base[e] = t == 0 ? s0 : t == 1 ? s1 : t == 2 ? s2 : t == 3 ? s3 : 0.0f;
     }
   }
 }

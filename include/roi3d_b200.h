@@ -19,8 +19,11 @@
  *   - Boxes are (x1,y1,x2,y2,z1,z2) in input-image pixels with the +1 size convention
  *     (nms_kernel.cu:23-33); RoIs are (batch_idx, x1,y1,x2,y2,z1,z2) fp32 (roi_align_kernel.cu:231-238).
  *   - Feature layout: ROI3D_NCDHW is the reference's contiguous [B,C,D,H,W]; ROI3D_NDHWC is the same
- *     logical tensor stored channels-last ([B,D,H,W,C] in memory, torch.channels_last_3d), which is
- *     what the kernels read natively with channel-contiguous vector loads.
+ *     logical tensor stored channels-last ([B,D,H,W,C] in memory, torch.channels_last_3d).  The FORWARD
+ *     entries take either: channels-last levels feed the streamed / per-warp kernels, NCDHW levels are read
+ *     in place by the planar kernel (square 7- or 14-wide outputs, 16-byte aligned levels, W % 4 == 0;
+ *     other NCDHW shapes return ROI3D_EINVAL: convert with roi3d_ncdhw_to_ndhwc).  The BACKWARD entries
+ *     accumulate into channels-last (ROI3D_NDHWC) gradients only.
  */
 #ifndef ROI3D_B200_H_
 #define ROI3D_B200_H_
@@ -69,7 +72,7 @@ typedef struct roi3d_level {
  * Replaces: roi_align_cuda.forward3d -> roi_align_forward_cuda_3d -> ROIAlignForwardLaucher3D,
  *   mmdet/ops/roi_align/src/roi_align_cuda.cpp:68-94, roi_align_kernel.cu:316-337 (kernel :214-291).
  * out_dev: [K, C, PD, PH, PW] contiguous, fully overwritten (no pre-zeroing needed, unlike
- *   functions/roi_align_3d.py:32).  feats: [B,C,D,H,W] in `layout`.
+ *   functions/roi_align_3d.py:32).  feats: [B,C,D,H,W] in `layout` (ROI3D_NDHWC or ROI3D_NCDHW, see above).
  * ---------------------------------------------------------------------------------------------- */
 int roi3d_roi_align3d_forward(const float *feats_dev, int layout, int B, int C, int D, int H, int W,
                               const float *rois_dev, int K, int PD, int PH, int PW, float spatial_scale,
@@ -87,7 +90,7 @@ int roi3d_roi_align3d_forward_rows(const float *feats_dev, int layout, int B, in
  * RoIAlign3D backward.
  * Replaces: roi_align_cuda.backward3d -> ROIAlignBackwardLaucher3D,
  *   roi_align_cuda.cpp:123-150, roi_align_kernel.cu:666-692 (kernel :519-636).
- * grad_in_dev [B,C,D,H,W] in `layout` is ACCUMULATED into (caller zero-fills, as
+ * grad_in_dev [B,C,D,H,W], `layout` must be ROI3D_NDHWC, is ACCUMULATED into (caller zero-fills, as
  *   functions/roi_align_3d.py:84 does); pass zero_fill=1 to have the library clear it first.
  * bug_compat=1 reproduces the reference's top_diff index for non-cubic outputs
  *   (roi_align_kernel.cu:554-555); default 0 = the mathematically correct gradient.
@@ -233,12 +236,14 @@ int roi3d_mask_target(const uint8_t *gt_masks_dev, int G, int D, int H, int W, c
                       size_t workspace_bytes, void *stream);
 
 /* Experiment knob (not part of the reference surface): key 0 = forward kernel variant (0 = auto, 1 = one channel per
- * lane, 50 = per-warp ring kernel where the streamed kernel would apply, 99 = literal reference-order path); key 1 =
- * backward kernel variant (0 = auto, 1, 3 = per-warp tables, 99 = literal); key 2 = sub-items one ring-kernel warp
- * walks per RoI (0 = auto); key 4 = volume size in KB from which roi3d_roi_align3d_forward_host pipelines its copies
- * (0 = auto, 32 MB; -1 = never); key 6 = NMS mask kernel variant; key 7 = ring geometry of the streamed forward kernel
- * (0 = 3 x 42 KB, 1 = 4 x 32 KB, 2 = 5 x 24 KB); key 9 = streamed kernel experiments (bit 0: no arithmetic, bit 1: no
- * output store, bit 2: no largest-first order). */
+ * lane, 50 = per-warp ring kernel where the streamed kernel would apply, 60 = planar kernel on channels-last 7-wide
+ * outputs, 99 = literal reference-order path); key 1 = backward kernel variant (0 = auto: streamed / planar where they
+ * apply, 50 = per-warp kernel, 60 = planar backward on 7-wide outputs, 1, 3 = per-warp tables, 99 = literal); key 2 =
+ * sub-items one ring-kernel warp walks per RoI (0 = auto); key 4 = volume size in KB from which
+ * roi3d_roi_align3d_forward_host pipelines its copies (0 = auto, 32 MB; -1 = never); key 6 = NMS mask kernel variant;
+ * key 7 = ring geometry of the streamed forward kernel (0 = 3 x 42 KB, 1 = 4 x 32 KB, 2 = 5 x 24 KB); key 9 = streamed
+ * kernel experiments (bit 0: no arithmetic, bit 1: no output store, bit 2: no largest-first order); key 10 = plane
+ * storage of the planar kernels per CTA in floats (0 = 18432). */
 int roi3d_set_tuning(int key, int value);
 
 /* Host-buffer form of RoIAlign3D forward (H2D feats+rois, kernel, D2H out): the e2e path bench.py times. */
