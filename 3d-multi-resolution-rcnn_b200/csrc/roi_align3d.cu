@@ -1718,6 +1718,7 @@ extern int g_host_pipeline_kb;        // host_api.cu
 extern int g_fwd_stream_cfg, g_fwd_stream_debug;  // roi_align3d_stream.cu  // roi_align3d_stream.cu
 extern int g_nms_mask_variant;        // nms3d.cu
 extern int g_planar_smem_floats;      // roi_align3d_planar.cu
+extern thread_local cudaEvent_t g_timing_ev[2];  // roi_align3d_stream.cu
 static int g_bwd_variant = 0;
 
 template <int PW, int ROWS, int CV, int NXU>
@@ -1950,6 +1951,12 @@ static int fill_params(RoiParams &p, const roi3d_level_t *levels, int num_levels
 using namespace roi3d;
 
 extern "C" {
+
+int roi3d_set_kernel_timing_events(void *start_event, void *stop_event) {
+  g_timing_ev[0] = static_cast<cudaEvent_t>(start_event);
+  g_timing_ev[1] = static_cast<cudaEvent_t>(stop_event);
+  return ROI3D_OK;
+}
 
 int roi3d_set_tuning(int key, int value) {
   if (key == 0) g_fwd_variant = value;

@@ -39,6 +39,8 @@
 
 namespace roi3d {
 
+extern thread_local cudaEvent_t g_timing_ev[2];
+
 namespace {
 
 constexpr int ST_OWNERS = 14;          // 7 output rows x 2 halves of the 7 pw bins
@@ -919,15 +921,75 @@ int stream_pool(cudaMemPool_t *out) {
 
 namespace {
 
+// Plan workspace of the streamed kernels: one grow-only buffer per (device, stream).  Calls on one stream are ordered, so
+// the next call's plan kernel cannot overwrite plans the previous call's main kernel still reads; calls on different
+// streams get different buffers (re-entrant across streams).  (A stream-ordered pool allocation per call costs ~3 us of
+// stream work around each launch pair.)
+struct PlanWs {
+  int dev;
+  cudaStream_t st;
+  unsigned char *ptr;
+  size_t bytes;
+};
+std::mutex g_planws_mutex;
+std::vector<PlanWs> g_planws;
+
+int plan_workspace(size_t bytes, cudaStream_t st, unsigned char **out) {
+  int dev = 0;
+  ROI3D_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_planws_mutex);
+  for (PlanWs &e : g_planws) {
+    if (e.dev == dev && e.st == st) {
+      if (e.bytes < bytes) {
+        // the old buffer may still be read by work enqueued on this stream: release it in stream order
+        ROI3D_CUDA(cudaFreeAsync(e.ptr, st));
+        e.ptr = nullptr, e.bytes = 0;
+        ROI3D_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&e.ptr), bytes, st));
+        e.bytes = bytes;
+      }
+      *out = e.ptr;
+      return ROI3D_OK;
+    }
+  }
+  PlanWs e;
+  e.dev = dev, e.st = st, e.ptr = nullptr, e.bytes = bytes < (1u << 20) ? (1u << 20) : bytes;
+  ROI3D_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&e.ptr), e.bytes, st));
+  if (g_planws.size() >= 256) {   // streams come and go: forget the oldest entry (its buffer is released in ITS stream's order)
+    cudaFreeAsync(g_planws.front().ptr, g_planws.front().st);
+    g_planws.erase(g_planws.begin());
+  }
+  g_planws.push_back(e);
+  *out = e.ptr;
+  return ROI3D_OK;
+}
+
+// Under stream capture the workspace comes from the stream-ordered pool instead (alloc / free nodes inside the graph: a
+// replayed graph owns its plans); *pooled tells the caller to free it after the launches.
+int acquire_plan_ws(size_t bytes, cudaStream_t st, unsigned char **ws, bool *pooled) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  ROI3D_CUDA(cudaStreamIsCapturing(st, &cap));
+  cudaMemPool_t pool;
+  if (cap == cudaStreamCaptureStatusNone) {
+    const int rc0 = stream_pool(&pool);   // created here, outside any capture (pool creation is not capturable)
+    if (rc0) return rc0;
+    *pooled = false;
+    return plan_workspace(bytes, st, ws);
+  }
+  const int rc = stream_pool(&pool);
+  if (rc) return rc;
+  ROI3D_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(ws), bytes, pool, st));
+  *pooled = true;
+  return ROI3D_OK;
+}
+
 template <int NS, int SLOT>
 int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count) {
   using L = Lay<NS, SLOT>;
-  cudaMemPool_t pool;
-  int rc = stream_pool(&pool);
-  if (rc) return rc;
   const size_t plan_bytes = (size_t)p.K * sizeof(StreamPlan);
   unsigned char *ws = nullptr;
-  ROI3D_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), plan_bytes + 16, pool, st));
+  bool pooled = false;
+  int rc = acquire_plan_ws(plan_bytes + 16, st, &ws, &pooled);
+  if (rc) return rc;
   StreamPlan *plans = reinterpret_cast<StreamPlan *>(ws);
   int *counter = reinterpret_cast<int *>(ws + plan_bytes);
   const int sort = (p.K <= ST_SORT_MAX && !(a.debug & 4)) ? 1 : 0;
@@ -941,6 +1003,7 @@ int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count)
                                     L::LAUNCH));
     attr_set = true;
   }
+  if (g_timing_ev[0] != nullptr) ROI3D_CUDA(cudaEventRecord(g_timing_ev[0], st));   // (measurement hook, see roi3d_set_kernel_timing_events)
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(ST_WARPS * 32), cfg.dynamicSmemBytes = L::LAUNCH, cfg.stream = st;
@@ -951,11 +1014,16 @@ int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count)
     ROI3D_CUDA(cudaLaunchKernelEx(&cfg, roi_align3d_fwd_stream_kernel<NS, SLOT>, a));
   }
   ROI3D_LAUNCH_CHECK();
-  ROI3D_CUDA(cudaFreeAsync(ws, st));
+  if (g_timing_ev[1] != nullptr) ROI3D_CUDA(cudaEventRecord(g_timing_ev[1], st));
+  if (pooled) ROI3D_CUDA(cudaFreeAsync(ws, st));
   return ROI3D_OK;
 }
 
 }  // namespace
+
+// Measurement hook: when set, launch_fwd_stream records these events right before and right after the launch of the
+// streamed forward kernel, so that a benchmark can time the dominant kernel by itself (without the plan kernel).
+thread_local cudaEvent_t g_timing_ev[2] = {nullptr, nullptr};
 
 int g_fwd_stream_cfg = 0;       // roi3d_set_tuning key 7: ring geometry of the streamed kernel (0 = default)
 int g_fwd_stream_debug = 0;     // key 9: developer experiments (bit 0: owners skip the arithmetic, bit 1: no output store)
@@ -1008,12 +1076,11 @@ int launch_bwd_stream(RoiParams &p, cudaStream_t st) {
   a.total_items = p.K * (p.C / ST_CH);
   a.pdhw = p.PD * 49;
   a.debug = 0;
-  cudaMemPool_t pool;
-  int rc = stream_pool(&pool);
-  if (rc) return rc;
   const size_t plan_bytes = (size_t)p.K * sizeof(StreamPlan);
   unsigned char *ws = nullptr;
-  ROI3D_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), plan_bytes + 16, pool, st));
+  bool pooled = false;
+  int rc = acquire_plan_ws(plan_bytes + 16, st, &ws, &pooled);
+  if (rc) return rc;
   StreamPlan *plans = reinterpret_cast<StreamPlan *>(ws);
   int *counter = reinterpret_cast<int *>(ws + plan_bytes);
   const int sort = p.K <= ST_SORT_MAX ? 1 : 0;
@@ -1038,7 +1105,7 @@ int launch_bwd_stream(RoiParams &p, cudaStream_t st) {
     ROI3D_CUDA(cudaLaunchKernelEx(&cfg, roi_align3d_bwd_stream_kernel, a));
   }
   ROI3D_LAUNCH_CHECK();
-  ROI3D_CUDA(cudaFreeAsync(ws, st));
+  if (pooled) ROI3D_CUDA(cudaFreeAsync(ws, st));
   return ROI3D_OK;
 }
 

@@ -39,6 +39,7 @@ def _load():
         "roi3d_last_error": (ctypes.c_char_p, []),
         "roi3d_device_info": (c_int, [ctypes.POINTER(c_int)] * 3 + [ctypes.POINTER(c_size_t)]),
         "roi3d_set_tuning": (c_int, [c_int, c_int]),
+        "roi3d_set_kernel_timing_events": (c_int, [P, P]),
         "roi3d_roi_align3d_forward": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int,
                                               c_int, c_float, c_float, c_int, P, P]),
         "roi3d_roi_align3d_forward_rows": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int,

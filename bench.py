@@ -290,6 +290,20 @@ def main():
     gpu_launches = 2 * steps  # per step: roi_align3d_plan_kernel (7 us) + roi_align3d_fwd_stream_kernel
     value = world * C2["K"] * steps / (total_ms * 1e-3)
     kernel_ms = float(np.median(per))  # per-step event time = plan kernel + streamed kernel (+ the launch gap)
+    # ---- the dominant kernel by itself: a second region of the same K steps in which the library records a CUDA
+    #      event right before and right after the launch of roi_align3d_fwd_stream_kernel (roi3d_set_kernel_timing_events;
+    #      the plan kernel then no longer overlaps the main kernel's start, so these steps are not the headline's)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a_, b_ in evs:   # torch creates the cudaEvent_t at the first record
+        a_.record()
+        b_.record()
+    torch.cuda.synchronize()
+    for a_, b_ in evs:
+        _lib.check(_lib.lib.roi3d_set_kernel_timing_events(a_.cuda_event, b_.cuda_event))
+        layer(feats_cl, rois)
+    _lib.check(_lib.lib.roi3d_set_kernel_timing_events(None, None))
+    torch.cuda.synchronize()
+    main_kernel_ms = float(np.median([a_.elapsed_time(b_) for a_, b_ in evs]))
     rank_us = None
     if dist is not None:  # per-rank medians: same inputs everywhere, so the spread is contention / clocks
         t = torch.tensor([kernel_ms * 1e3], device=dev, dtype=torch.float64)
@@ -353,7 +367,8 @@ def main():
                           C2["sample_num"])
         out_bytes = C2["K"] * C2["C"] * C2["PD"] * C2["P"] * C2["P"] * 4
         alg_bytes = out_bytes + U * C2["C"] * 4 + C2["K"] * 28
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        achieved = alg_bytes / (main_kernel_ms * 1e-3) / 1e9          # the dominant kernel's own launch duration
+        achieved_step = alg_bytes / (kernel_ms * 1e-3) / 1e9            # the whole step (plan kernel + launch gap included)
         traffic = None
         prof = os.path.join(ROOT, "profiles", "r02_final_c2_fwd_stream_ncu_summary.json")
         if os.path.exists(prof):
@@ -361,11 +376,17 @@ def main():
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_stream_kernel<3,43008> (+ roi_align3d_plan_kernel in the same step)",
+        roofline = {"bound": "hbm", "kernel": "roi_align3d_fwd_stream_kernel<3,43008>",
                     "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes": alg_bytes, "unique_voxels": U, "kernel_us": kernel_ms * 1e3,
-                    "output_only_gbs": out_bytes / (kernel_ms * 1e-3) / 1e9,
+                    "algorithmic_bytes": alg_bytes, "unique_voxels": U, "kernel_us": main_kernel_ms * 1e3,
+                    "kernel_timing": "CUDA events recorded by the library right before / after the kernel's launch, "
+                                     "median over a second region of the same K steps",
+                    "whole_step": {"step_us": kernel_ms * 1e3, "achieved": achieved_step, "frac": achieved_step / peak,
+                                   "note": "one step = roi_align3d_plan_kernel + the streamed kernel (programmatic "
+                                           "dependent launch) + the launch gap to the next step; this is what "
+                                           "ms_per_step and value measure"},
+                    "output_only_gbs": out_bytes / (main_kernel_ms * 1e-3) / 1e9,
                     "layout": "channels-last (NDHWC) features resident in HBM"}
         if extra.get("c2_fwd_ncdhw_input_us"):
             # the reference's own layout, read in place by the planar kernel (rows of a RoI are 40-70 bytes of a 512-byte

@@ -246,6 +246,12 @@ int roi3d_mask_target(const uint8_t *gt_masks_dev, int G, int D, int H, int W, c
  * storage of the planar kernels per CTA in floats (0 = 18432). */
 int roi3d_set_tuning(int key, int value);
 
+/* Measurement hook (not part of the reference surface): two cudaEvent_t (as void*) that the calling thread's next
+ * roi3d_roi_align3d_forward / roi3d_extract_forward calls record right before and right after the launch of the streamed
+ * forward kernel, so that a benchmark can time the dominant kernel by itself; NULL, NULL switches it off.  With the
+ * events set the plan kernel no longer overlaps the main kernel's start (the event sits between the two launches). */
+int roi3d_set_kernel_timing_events(void *start_event, void *stop_event);
+
 /* Host-buffer form of RoIAlign3D forward (H2D feats+rois, kernel, D2H out): the e2e path bench.py times. */
 int roi3d_roi_align3d_forward_host(const float *feats_host, int layout, int B, int C, int D, int H, int W,
                                    const float *rois_host, int K, int PD, int PH, int PW, float spatial_scale,
