@@ -1859,7 +1859,8 @@ static int dispatch_fwd(RoiParams &p, cudaStream_t st) {
     if (cvmax >= 2) return launch_generic<2>(p, true, st);
     return launch_generic<1>(p, true, st);
   }
-  if (p.layout == ROI3D_NCDHW) {  // the reference's layout: only the planar kernel reads it
+  if (p.layout == ROI3D_NCDHW) {  // the reference's layout: the streamed kernel's NCDHW twin (bbox branch) or the planar kernel
+    if (v == 0 && fwd_stream_ok(p)) return launch_fwd_stream(p, st);
     ROI3D_CHECK_ARG(fwd_planar_ok(p, ROI3D_NCDHW),
                     "NCDHW levels need a 7- or 14-wide square output, 16-byte aligned levels and W %% 4 == 0; convert "
                     "with roi3d_ncdhw_to_ndhwc otherwise");

@@ -58,40 +58,6 @@ __device__ __forceinline__ void cp_async4_pl(void *dst, const void *src) {
 __device__ __forceinline__ unsigned fast_magic(unsigned d) { return d <= 1 ? 0u : 0xFFFFFFFFu / d + 1u; }
 __device__ __forceinline__ unsigned fast_div(unsigned q, unsigned d, unsigned magic) { return d <= 1 ? q : __umulhi(q, magic); }
 
-// Literal evaluation of one output bin for one channel, any layout (element strides sc / sz / sy / sx): the
-// reference's sample loops with its corner-weight / FFMA-chain arithmetic (roi_align_kernel.cu:134-146 + SASS).
-__device__ float literal_bin_strided(const Axis &axw, const Axis &axh, const Axis &axd, int D, int H, int W,
-                                     const float *fc, long long sz, long long sy, long long sx, int pd, int ph, int pw) {
-  float acc = 0.0f;
-  for (int iz = 0; iz < axd.S; ++iz) {
-    const Tap tz = axis_tap(axis_coord(axd, pd, iz), D);
-    for (int iy = 0; iy < axh.S; ++iy) {
-      const Tap ty = axis_tap(axis_coord(axh, ph, iy), H);
-      for (int ix = 0; ix < axw.S; ++ix) {
-        const Tap tx = axis_tap(axis_coord(axw, pw, ix), W);
-        if (!(tz.valid && ty.valid && tx.valid)) continue;  // contributes 0, still counted
-        const float hxhy = __fmul_rn(tx.h, ty.h), lxhy = __fmul_rn(tx.l, ty.h);
-        const float hxly = __fmul_rn(tx.h, ty.l), lxly = __fmul_rn(tx.l, ty.l);
-        const float w1 = __fmul_rn(hxhy, tz.h), w2 = __fmul_rn(lxhy, tz.h), w3 = __fmul_rn(hxly, tz.h),
-                    w4 = __fmul_rn(lxly, tz.h), w5 = __fmul_rn(hxhy, tz.l), w6 = __fmul_rn(lxhy, tz.l),
-                    w7 = __fmul_rn(hxly, tz.l), w8 = __fmul_rn(lxly, tz.l);
-        const long long zl = tz.low * sz, zh = tz.high * sz, yl = ty.low * sy, yh = ty.high * sy;
-        const long long xl = tx.low * sx, xh = tx.high * sx;
-        float t = __fmul_rn(w2, __ldg(fc + zl + yl + xh));
-        t = __fmaf_rn(w1, __ldg(fc + zl + yl + xl), t);
-        t = __fmaf_rn(w3, __ldg(fc + zl + yh + xl), t);
-        t = __fmaf_rn(w4, __ldg(fc + zl + yh + xh), t);
-        t = __fmaf_rn(w5, __ldg(fc + zh + yl + xl), t);
-        t = __fmaf_rn(w6, __ldg(fc + zh + yl + xh), t);
-        t = __fmaf_rn(w7, __ldg(fc + zh + yh + xl), t);
-        t = __fmaf_rn(w8, __ldg(fc + zh + yh + xh), t);
-        acc = __fadd_rn(acc, t);
-      }
-    }
-  }
-  return __fdiv_rn(acc, (float)(axd.S * axh.S * axw.S));
-}
-
 // acc += w * v for the four channels of a packed entry: two packed-fp32 FFMA2, each half rounded like fmaf
 __device__ __forceinline__ void fma4(float4 &a, float w, const float4 v) {
   const float2 w2 = make_float2(w, w);

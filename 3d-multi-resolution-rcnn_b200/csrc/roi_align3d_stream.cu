@@ -54,6 +54,17 @@ constexpr int ST_MAX_LEVELS = 4;
 constexpr int ST_SORT_MAX = 8192;      // RoIs ranked by footprint up to this K (identity order above)
 constexpr int ST_MAX_TILE_ROWS = 32;   // one producer lane per tile row
 
+// NCDHW twin (roi_align3d_fwd_stream_ncdhw_kernel): a ring slot is [64 channels][SN_S floats], SN_S = 4 x odd (16-byte
+// aligned channel rows; lanes = channels then fall into 8 bank groups of 4 lanes, which read their four taps in rotated
+// order: 32 different banks); the producers are SN_PROD warps issuing 16-byte cp.async (TMA delivers such 48..80-byte
+// runs at ~10 B/clk/SM: tools/probe/tma_probe_ncdhw.cu; 4-byte cp.async retires about one lane per clock)
+constexpr int SN_S = 164;                   // 4 x 41
+constexpr int SN_SLOT = ST_CH * SN_S * 4;   // 41984 bytes = 328 x 128
+constexpr int SN_PROD = 4;
+constexpr int SN_WARPS = ST_OWNERS + SN_PROD + 1;
+constexpr int SN_HALF = 32 * SN_S;          // lane l holds channels l and l + 32
+constexpr int SN_EMAX = (SN_S / 4 + 31) / 32;   // 16-byte pieces per lane and tile
+
 constexpr int PLAN_EMPTY = 1;          // output is 0 * (1 / count)
 constexpr int PLAN_SLOW = 2;           // literal evaluation
 constexpr int PLAN_X3 = 4;             // every x bin fits three taps
@@ -106,7 +117,8 @@ struct Lay {
   static constexpr int PLAN = STAGE + STAGE_BYTES;
   static constexpr int TDESC = PLAN + NS * PLAN_BYTES;
   static constexpr int SDESC = TDESC + NS * (int)sizeof(TileDesc);
-  static constexpr int BAR = SDESC + 2 * 16;   // full[NS], empty[NS], staging full, staging free
+  static constexpr int SCHED = SDESC + 2 * 16; // NCDHW twin: item index mailbox of the producer warps (two entries)
+  static constexpr int BAR = SCHED + 16;       // full[NS], empty[NS], staging full, staging free
   static constexpr int TOTAL = BAR + (2 * NS + 2) * 8;
   static constexpr int LAUNCH = (TOTAL + 127) / 128 * 128;
   static_assert(STAGE % 128 == 0 && PLAN % 16 == 0 && BAR % 8 == 0, "alignment");
@@ -166,7 +178,7 @@ __device__ __forceinline__ void add_tap(float (&w)[4], int i, float v) {
 // Plan kernel: one warp per RoI.  Lanes 0..7 -> x bins, 8..15 -> y bins, 16..23 -> z bins.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p, StreamPlan *plans, int *counter, int sort,
-                                                               int slot_bytes, int counter_init) {
+                                                               int slot_bytes, int counter_init, int ncdhw) {
   extern __shared__ float cost_s[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // programmatic dependent launch: the streamed kernel may be scheduled now; it waits (griddepcontrol.wait) for this
@@ -185,7 +197,20 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
       const float wx = fminf(fmaxf((r[3] - r[1] + 1.0f) * s, 0.0f), 64.0f) + 2.0f;
       const float wy = fminf(fmaxf((r[4] - r[2] + 1.0f) * s, 0.0f), 64.0f) + 2.0f;
       const float wz = fminf(fmaxf((r[6] - r[5] + 1.0f) * sd, 0.0f), 64.0f) + 2.0f;
-      cost_s[k] = wx * wy * wz;
+      if (sort == 2) {
+        // spatial order: Morton code of the cell (16 x 16 x 8 voxels) that holds the RoI's centre, level-major --
+        // RoIs that overlap run close together in time, so a line fetched for one is still in L2 for the next
+        const int cx = min(31, max(0, (int)((r[1] + r[3]) * 0.5f * s) >> 4));
+        const int cy = min(31, max(0, (int)((r[2] + r[4]) * 0.5f * s) >> 4));
+        const int cz = min(31, max(0, (int)((r[5] + r[6]) * 0.5f * sd) >> 3));
+        int code = 0;
+#pragma unroll
+        for (int bit = 0; bit < 5; ++bit)
+          code |= (((cx >> bit) & 1) << (3 * bit)) | (((cy >> bit) & 1) << (3 * bit + 1)) | (((cz >> bit) & 1) << (3 * bit + 2));
+        cost_s[k] = (float)((lvl << 15) | code);
+      } else {
+        cost_s[k] = -(wx * wy * wz);   // largest footprint first
+      }
     }
     __syncthreads();
   }
@@ -197,7 +222,7 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
     rank = 0;
     for (int j = lane; j < p.K; j += 32) {
       const float c = cost_s[j];
-      rank += (c > mine) || (c == mine && j < k);
+      rank += (c < mine) || (c == mine && j < k);
     }
     rank = __reduce_add_sync(FULL, rank);
   }
@@ -249,9 +274,12 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
   const int RX = empty ? 0 : x1 - x0 + 1, RY = empty ? 0 : y1 - y0 + 1, RZ = empty ? 0 : z1 - z0 + 1;
   slow = __any_sync(FULL, slow) || RX > ST_RMAX || RY > ST_RMAX || RZ > ST_RZMAX;
   if (empty) slow = false;
-  const bool x3 = !__any_sync(FULL, role == 0 && n > 3);
+  const bool x3 = !ncdhw && !__any_sync(FULL, role == 0 && n > 3);
   const int NT = x3 ? 3 : 4;
-  const int RXB = max(4, RX);  // box width: at least the NT taps of one bin
+  // box origin and width in x.  Channels-last: the footprint, at least the NT taps of one bin.  NCDHW: whole 16-byte
+  // pieces of the level's rows (W % 4 == 0), so the origin moves left to a multiple of 4 and the width is rounded up.
+  const int xa = (ncdhw && !empty) ? (x0 & ~3) : x0;
+  const int RXB = ncdhw ? (empty ? 4 : ((x0 + RX - xa + 3) & ~3)) : max(4, RX);
   // Tiling: consecutive (z, y) rows of the footprint, as many as fit a ring slot (one producer lane per row).
   const int rows_per_tile = min(ST_MAX_TILE_ROWS, slot_bytes / (RXB * ST_CH * 4));
   const bool stream = !empty && !slow;
@@ -266,7 +294,7 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
     pl->lvl = lvl;
     pl->b = ok ? b : 0;
     pl->flags = (empty ? PLAN_EMPTY : 0) | (slow ? PLAN_SLOW : 0) | (x3 ? PLAN_X3 : 0);
-    pl->x0 = empty ? 0 : x0, pl->y0 = empty ? 0 : y0, pl->z0 = empty ? 0 : z0;
+    pl->x0 = empty ? 0 : xa, pl->y0 = empty ? 0 : y0, pl->z0 = empty ? 0 : z0;
     pl->RX = RX, pl->RY = RY, pl->RZ = RZ, pl->RXB = RXB;
     pl->rows_per_tile = rows_per_tile, pl->ntiles = ntiles, pl->nrows = nrows, pl->xcls = RXB - 1;
     // The reference divides by the sample count (roi_align_kernel.cu:288); 1/count is exact for the power-of-two
@@ -279,7 +307,7 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
   float wd[4] = {0.0f, 0.0f, 0.0f, 0.0f};        // and its weights
   const bool on = n > 0 && stream;
   if (role == 0) {
-    int off = on ? lo - x0 : 0;
+    int off = on ? lo - xa : 0;
     const int sh = max(0, off + NT - RXB);
     off -= sh;
     if (on) {
@@ -319,7 +347,7 @@ __global__ void __launch_bounds__(256) roi_align3d_plan_kernel(const RoiParams p
 // ---------------------------------------------------------------------------------------------------------------
 // Owner: literal evaluation of this owner's bins of a RoI the tap tables cannot express (rare).
 // ---------------------------------------------------------------------------------------------------------------
-template <int NPH>
+template <int NPH, bool NC>
 __device__ __noinline__ void owner_literal(const RoiParams &p, int k, int lvl, int chunk, int ph0, int pw, int lane,
                                            float *staging, int pdhw) {
   Item it;
@@ -334,30 +362,56 @@ __device__ __noinline__ void owner_literal(const RoiParams &p, int k, int lvl, i
   it.axh = axis_setup(r[2], r[4], it.L.scale, p.PH, p.sample_num);
   it.axd = axis_setup(r[5], r[6], it.L.scale_d, p.PD, p.sample_num);
   const long long vox = (long long)it.L.D * it.L.H * it.L.W;
-  const float *fb = it.L.feats + (long long)it.b * vox * p.C + chunk * ST_CH + lane * 2;
-  for (int pd = 0; pd < p.PD; ++pd)
-    for (int j = 0; j < NPH; ++j) {
-      float v[2];
-      literal_bin_fwd<2>(it, fb, p.C, pd, ph0 + j, pw, v);
-      const int idx = pd * 49 + (ph0 + j) * 7 + pw;
-      staging[(2 * lane) * pdhw + idx] = v[0];
-      staging[(2 * lane + 1) * pdhw + idx] = v[1];
-    }
+  if constexpr (NC) {
+    // NCDHW level: channels lane and lane + 32 of the chunk, one plane each
+    const long long sy = it.L.W, sz = (long long)it.L.H * it.L.W;
+    const float *f0 = it.L.feats + ((long long)it.b * p.C + chunk * ST_CH + lane) * vox;
+    const float *f1 = f0 + 32 * vox;
+    for (int pd = 0; pd < p.PD; ++pd)
+      for (int j = 0; j < NPH; ++j) {
+        const int idx = pd * 49 + (ph0 + j) * 7 + pw;
+        staging[lane * pdhw + idx] = literal_bin_strided(it.axw, it.axh, it.axd, it.L.D, it.L.H, it.L.W, f0, sz, sy, 1, pd, ph0 + j, pw);
+        staging[(lane + 32) * pdhw + idx] = literal_bin_strided(it.axw, it.axh, it.axd, it.L.D, it.L.H, it.L.W, f1, sz, sy, 1, pd, ph0 + j, pw);
+      }
+  } else {
+    const float *fb = it.L.feats + (long long)it.b * vox * p.C + chunk * ST_CH + lane * 2;
+    for (int pd = 0; pd < p.PD; ++pd)
+      for (int j = 0; j < NPH; ++j) {
+        float v[2];
+        literal_bin_fwd<2>(it, fb, p.C, pd, ph0 + j, pw, v);
+        const int idx = pd * 49 + (ph0 + j) * 7 + pw;
+        staging[(2 * lane) * pdhw + idx] = v[0];
+        staging[(2 * lane + 1) * pdhw + idx] = v[1];
+      }
+  }
 }
 
 // x-contraction of one feature row for this owner's pw bin, then the fold into the slice partials of its NPH output rows
 // with the row's (dense) y weights: a row outside a bin's support has weight 0
-template <int NT, int NPH>
-__device__ __forceinline__ void row_visit(const float *q, const float (&xw)[4], const float *ywrow, float2 (&t2)[NPH]) {
-  const float2 v0 = *reinterpret_cast<const float2 *>(q);
-  const float2 v1 = *reinterpret_cast<const float2 *>(q + ST_CH);
-  const float2 v2 = *reinterpret_cast<const float2 *>(q + 2 * ST_CH);
+template <int NT, int NPH, bool NC>
+__device__ __forceinline__ void row_visit(const float *q, const float (&xw)[4], const float *ywrow, float2 (&t2)[NPH],
+                                          const int3 rot) {
+  // channels-last tile: taps ST_CH floats apart, the lane's two channels adjacent; NCDHW tile: taps adjacent, the lane's
+  // two channels SN_HALF floats apart
+  float2 v0, v1, v2;
+  if constexpr (NC) {
+    // q points at this lane's FIRST tap in its rotated order; steps 1..3 are at the lane's offsets (xw is rotated alike)
+    v0 = make_float2(q[0], q[SN_HALF]);
+    v1 = make_float2(q[rot.x], q[rot.x + SN_HALF]);
+    v2 = make_float2(q[rot.y], q[rot.y + SN_HALF]);
+  } else {
+    v0 = *reinterpret_cast<const float2 *>(q);
+    v1 = *reinterpret_cast<const float2 *>(q + ST_CH);
+    v2 = *reinterpret_cast<const float2 *>(q + 2 * ST_CH);
+  }
   const float4 wy = *reinterpret_cast<const float4 *>(ywrow);
   float2 x = __fmul2_rn(make_float2(xw[0], xw[0]), v0);
   x = __ffma2_rn(make_float2(xw[1], xw[1]), v1, x);
   x = __ffma2_rn(make_float2(xw[2], xw[2]), v2, x);
   if constexpr (NT == 4) {
-    const float2 v3 = *reinterpret_cast<const float2 *>(q + 3 * ST_CH);
+    float2 v3;
+    if constexpr (NC) v3 = make_float2(q[rot.z], q[rot.z + SN_HALF]);
+    else v3 = *reinterpret_cast<const float2 *>(q + 3 * ST_CH);
     x = __ffma2_rn(make_float2(xw[3], xw[3]), v3, x);
   }
   t2[0] = __ffma2_rn(make_float2(wy.x, wy.x), x, t2[0]);
@@ -368,10 +422,10 @@ __device__ __forceinline__ void row_visit(const float *q, const float (&xw)[4], 
 
 // All rows of one tile that carry weight for this owner; z fold at the end of every slice the tile completes.
 // The tile holds rows [y, y + nrows) of the footprint's (slice, row) sequence starting in slice z.
-template <int NT, int NPH>
+template <int NT, int NPH, bool NC>
 __device__ __forceinline__ void owner_tile(int nrows, int z, int y, int rowfloats, const StreamPlan *P, const float *tile,
                                            int ph0, int RY, int ylo, int yhi1, const float (&xw)[4], float2 (&t2)[NPH],
-                                           float2 (&acc)[7][NPH]) {
+                                           float2 (&acc)[7][NPH], const int3 rot) {
   int left = nrows;
   const float *rowp = tile;
   while (left > 0) {
@@ -381,7 +435,7 @@ __device__ __forceinline__ void owner_tile(int nrows, int z, int y, int rowfloat
     const float *yw = &P->ywd[ya][ph0];
 #pragma unroll 2
     for (int yy = ya; yy < yb; ++yy) {
-      row_visit<NT, NPH>(q, xw, yw, t2);
+      row_visit<NT, NPH, NC>(q, xw, yw, t2, rot);
       q += rowfloats, yw += 8;
     }
     rowp += seg * rowfloats;
@@ -410,7 +464,7 @@ __device__ __forceinline__ void owner_tile(int nrows, int z, int y, int rowfloat
 // the producer before it arms the slot's barrier.
 // (Tried and dropped: letting an owner skip the wait for tiles that hold none of its rows -- slower, and a parity
 // wait can alias once a warp is more than one use of a slot ahead.)
-template <int NPH, int NS, int SLOT>
+template <int NPH, int NS, int SLOT, bool NC = false>
 __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *smem, int ph0, int pw, int warp, int lane) {
   using L = Lay<NS, SLOT>;
   const unsigned bar0 = s_u32(smem + L::BAR);
@@ -436,10 +490,23 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
         for (int j = 0; j < NPH; ++j) acc[pd][j] = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int j = 0; j < NPH; ++j) t2[j] = make_float2(0.0f, 0.0f);
-      const int xo = P->xoff[pw] * ST_CH;
+      const int xo = NC ? P->xoff[pw] : P->xoff[pw] * ST_CH;
+      int3 rot = make_int3(0, 0, 0);
+      int first = 0;
       {
         const float4 w4 = *reinterpret_cast<const float4 *>(&P->xw[pw][0]);
         xw[0] = w4.x, xw[1] = w4.y, xw[2] = w4.z, xw[3] = w4.w;
+        if constexpr (NC) {
+          // step i reads tap (i + lane / 8) % 4: offsets of steps 1..3 relative to step 0, weights in step order
+          const int r0 = (lane >> 3) & 3;
+          const float t0 = xw[0], t1 = xw[1], t2w = xw[2], t3 = xw[3];
+          xw[0] = r0 == 0 ? t0 : r0 == 1 ? t1 : r0 == 2 ? t2w : t3;
+          xw[1] = r0 == 0 ? t1 : r0 == 1 ? t2w : r0 == 2 ? t3 : t0;
+          xw[2] = r0 == 0 ? t2w : r0 == 1 ? t3 : r0 == 2 ? t0 : t1;
+          xw[3] = r0 == 0 ? t3 : r0 == 1 ? t0 : r0 == 2 ? t1 : t2w;
+          first = r0;
+          rot = make_int3(((r0 + 1) & 3) - r0, ((r0 + 2) & 3) - r0, ((r0 + 3) & 3) - r0);
+        }
       }
       // rows with weight for any of this owner's output rows
       const int RY = P->RY;
@@ -452,11 +519,11 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
       TileDesc dt = d;
       for (;;) {  // tiles of the item
         if (dt.nrows > 0 && !(a.debug & 1)) {
-          const float *tile = reinterpret_cast<const float *>(smem + L::RING + slot * SLOT) + lane * 2 + xo;
-          if (pflags & PLAN_X3)
-            owner_tile<3, NPH>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph0, RY, ylo, yhi1, xw, t2, acc);
+          const float *tile = reinterpret_cast<const float *>(smem + L::RING + slot * SLOT) + (NC ? lane * SN_S + first : lane * 2) + xo;
+          if (!NC && (pflags & PLAN_X3))
+            owner_tile<3, NPH, NC>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph0, RY, ylo, yhi1, xw, t2, acc, rot);
           else
-            owner_tile<4, NPH>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph0, RY, ylo, yhi1, xw, t2, acc);
+            owner_tile<4, NPH, NC>(dt.nrows, dt.z, dt.y, dt.rowfloats, P, tile, ph0, RY, ylo, yhi1, xw, t2, acc, rot);
         }
         ++tile_seq;
         if (dt.flags & TILE_LAST) break;
@@ -470,7 +537,8 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
       st_mbar_wait(sfree, (item_seq & 1) ^ 1);
       const float inv = P->inv_count;
       const float2 inv2 = make_float2(inv, inv);
-      float *s0 = staging + (2 * lane) * pdhw + ph0 * 7 + pw;
+      float *s0 = staging + (NC ? lane : 2 * lane) * pdhw + ph0 * 7 + pw;
+      const int second = NC ? 32 * pdhw : pdhw;   // the lane's other channel
 #pragma unroll
       for (int pd = 0; pd < 7; ++pd) {
         if (pd * 49 < pdhw) {
@@ -478,7 +546,7 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
           for (int j = 0; j < NPH; ++j) {
             const float2 v = __fmul2_rn(acc[pd][j], inv2);
             s0[pd * 49 + j * 7] = v.x;
-            s0[pdhw + pd * 49 + j * 7] = v.y;
+            s0[second + pd * 49 + j * 7] = v.y;
           }
         }
       }
@@ -486,7 +554,7 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
       // ---- literal item (one descriptor-only tile)
       ++tile_seq;
       st_mbar_wait(sfree, (item_seq & 1) ^ 1);
-      owner_literal<NPH>(a.p, P->k, P->lvl, d.chunk, ph0, pw, lane, staging, pdhw);
+      owner_literal<NPH, NC>(a.p, P->k, P->lvl, d.chunk, ph0, pw, lane, staging, pdhw);
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the bulk store
     if (warp == 0 && lane == 0) {
@@ -609,6 +677,28 @@ __device__ __forceinline__ void producer_loop(const StreamArgs &a, unsigned char
   }
 }
 
+// Storer warp: one bulk store per item, the staging image is handed back as soon as it has been read.
+template <int NS, int SLOT>
+__device__ __forceinline__ void storer_loop(const StreamArgs &a, unsigned char *smem, int lane) {
+  using L = Lay<NS, SLOT>;
+  if (lane != 0) return;
+  const unsigned bar0 = s_u32(smem + L::BAR);
+  const unsigned sfull = bar0 + 2 * NS * 8, sfree = sfull + 8;
+  const unsigned stage_s = s_u32(smem + L::STAGE);
+  const unsigned bytes = (unsigned)(ST_CH * a.pdhw * 4);
+  for (unsigned n = 0;; ++n) {
+    st_mbar_wait(sfull, n & 1);
+    const int *sd = reinterpret_cast<const int *>(smem + L::SDESC + (n & 1) * 16);
+    if (sd[2]) break;
+    float *dst = a.p.out + ((long long)sd[0] * a.p.C + (long long)sd[1] * ST_CH) * a.pdhw;
+    if (!(a.debug & 2)) st_bulk_s2g(dst, stage_s, bytes);
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    st_mbar_arrive(sfree);
+  }
+  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+}
+
 template <int NS, int SLOT>
 __global__ void __launch_bounds__(ST_WARPS * 32, 1) roi_align3d_fwd_stream_kernel(const __grid_constant__ StreamArgs a) {
   using L = Lay<NS, SLOT>;
@@ -639,22 +729,161 @@ __global__ void __launch_bounds__(ST_WARPS * 32, 1) roi_align3d_fwd_stream_kerne
     return;
   }
 
-  // ---- storer: one bulk store per item, the staging image is handed back as soon as it has been read
-  if (lane != 0) return;
-  const unsigned sfull = bar0 + 2 * NS * 8, sfree = sfull + 8;
-  const unsigned stage_s = s_u32(smem + L::STAGE);
-  const unsigned bytes = (unsigned)(ST_CH * a.pdhw * 4);
-  for (unsigned n = 0;; ++n) {
-    st_mbar_wait(sfull, n & 1);
-    const int *sd = reinterpret_cast<const int *>(smem + L::SDESC + (n & 1) * 16);
-    if (sd[2]) break;
-    float *dst = a.p.out + ((long long)sd[0] * a.p.C + (long long)sd[1] * ST_CH) * a.pdhw;
-    if (!(a.debug & 2)) st_bulk_s2g(dst, stage_s, bytes);
-    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-    st_mbar_arrive(sfree);
+  storer_loop<NS, SLOT>(a, smem, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCDHW twin: the reference's layout (roi_align_cuda.cpp:35-39) read in place.
+//
+// Same plans, owners and storer; what changes is the supply.  In NCDHW the 64 channels of a voxel are D*H*W floats
+// apart and only the x-run of a footprint row (RX ~ 11 floats) is contiguous.  TMA needs 16-byte aligned box origins
+// and moves such 48..80-byte runs at ~10 B/clk/SM (tools/probe/tma_probe_ncdhw.cu); 4-byte cp.async retires about one
+// lane per clock (measured: 540 us of supply on C2).  So the producers are SN_PROD warps that issue 16-byte cp.async
+// (LDGSTS.128) over whole 16-byte pieces of the level's rows (W % 4 == 0; the plan widens the box to multiples of 4
+// voxels): a tile is a run of consecutive (z, y) rows of the footprint, stored per channel as [row][RXB] in a slot of
+// [64 channels][SN_S floats]; lane l of a producer warp owns pieces l and l + 32 of the tile (their offset inside a
+// channel's volume is computed once per tile) and walks its 64 / SN_PROD channels.  Every producer lane arrives on the
+// slot's barrier through cp.async.mbarrier.arrive.noinc (the arrival fires when the lane's copies have landed).
+// SN_S = 4 x odd: the owners' lanes = channels fall into 8 groups of 4 lanes per 4-bank group; the four lanes of a
+// group read the four taps of a row in rotated order (tap (i + lane / 8) % 4 in step i), so every LDS.32 touches 32
+// different banks.
+// Schedule order is spatial (Morton order of the RoI centres, level-major) instead of largest-first: DRAM reads on C2
+// 1.17 GB -> 0.93 GB (a line fetched for one RoI is still in L2 for its neighbours), same time; items are tickets of an
+// atomic counter.  What bounds it (measured on C2): the LSU retires about one cp.async lane per clock whatever its size
+// (16 B/clk/SM at best; 778 MB of row pieces in 210 us with the owners idle), a two-slot ring is as fast as three, and the
+// owners' LDS traffic shares that pipe (317 us with everything on; planar kernel on the same call: 392 us).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_cp_async16(unsigned dst, const float *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void st_cp_async_arrive(unsigned mbar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(mbar) : "memory");
+}
+
+template <int NS>
+__device__ __forceinline__ void producer_loop_ncdhw(const StreamArgs &a, unsigned char *smem, int pwarp, int lane) {
+  using L = Lay<NS, SN_SLOT>;
+  const unsigned bar0 = s_u32(smem + L::BAR);
+  TileDesc *tdesc = reinterpret_cast<TileDesc *>(smem + L::TDESC);
+  const int K = a.p.K, total = a.total_items, C = a.p.C;
+  const bool leader = pwarp == 0 && lane == 0;
+  constexpr int CPW = ST_CH / SN_PROD;   // channels per producer warp
+  unsigned tile_seq = 0, item_seq = 0;
+  // Items: the first two of a CTA are static (blockIdx.x, + grid), later ones are tickets of the atomic counter (it starts
+  // at 2 * grid) drawn by the leader one item ahead; the producer warps agree on an item through a two-entry mailbox and
+  // one named barrier per item.
+  volatile int *sched = reinterpret_cast<volatile int *>(smem + L::SCHED);
+  int idx_cur = (int)blockIdx.x, idx_n1 = (int)(blockIdx.x + gridDim.x);
+  int t_n2 = leader ? atomicAdd(a.counter, 1) : 0;
+  for (;; ++item_seq) {
+    if (leader) sched[item_seq & 1] = idx_cur;
+    asm volatile("bar.sync 1, %0;\n" ::"n"(SN_PROD * 32) : "memory");
+    const int idx = sched[item_seq & 1];
+    if (idx >= total) break;
+    if (leader) {
+      idx_cur = idx_n1, idx_n1 = t_n2;
+      t_n2 = atomicAdd(a.counter, 1);
+    }
+    const int chunk = idx / K, r_sched = idx - chunk * K;
+    const int h = lane < 20 ? __ldg(reinterpret_cast<const int *>(a.plans + r_sched) + lane) : 0;
+    const int lvl = __shfl_sync(FULL, h, 2), b = __shfl_sync(FULL, h, 3);
+    const int x0 = __shfl_sync(FULL, h, 5), y0 = __shfl_sync(FULL, h, 6), z0 = __shfl_sync(FULL, h, 7);
+    const int RY = __shfl_sync(FULL, h, 9), RXB = __shfl_sync(FULL, h, 11);
+    const int rpt = __shfl_sync(FULL, h, 12), ntiles = __shfl_sync(FULL, h, 13), nrows = __shfl_sync(FULL, h, 14);
+    const int magic_y = __shfl_sync(FULL, h, 17);
+    const int npr = RXB >> 2;                       // 16-byte pieces per row
+    const int magic_x = (65536 + npr - 1) / npr;
+    const LevelDev Lv = a.p.lv[lvl];
+    const int Wd = Lv.W, HW = Lv.H * Lv.W;
+    const long long vox = (long long)Lv.D * HW;
+    const float *base = Lv.feats + ((long long)b * C + chunk * ST_CH + pwarp * CPW) * vox;
+    const unsigned pslot = item_seq % NS;
+    int r = 0, ys = 0, zs = 0;   // first row of the next tile: index, and (row, slice) from the box origin
+    for (int t = 0; t < ntiles; ++t) {
+      const unsigned slot = tile_seq % NS;
+      const int tr = min(rpt, nrows - r);
+      // this lane's 16-byte pieces of the tile (piece p = row * RXB / 4 + quarter lands at float 4 p of every channel
+      // row): offset inside a channel's volume, -1 = none
+      const int np = tr * npr;
+      int off[SN_EMAX];
+#pragma unroll
+      for (int j = 0; j < SN_EMAX; ++j) {
+        const int pc = lane + 32 * j;
+        const int row = (pc * magic_x) >> 16, q = pc - row * npr;
+        const int pos = ys + row;
+        const int dz = (pos * magic_y) >> 16, y = pos - dz * RY;
+        off[j] = pc < np ? (z0 + zs + dz) * HW + (y0 + y) * Wd + x0 + 4 * q : -1;
+      }
+      st_mbar_wait(bar0 + (NS + slot) * 8, ((tile_seq / NS) & 1) ^ 1);
+      const unsigned full = bar0 + slot * 8;
+      if (leader) {
+        TileDesc d;
+        d.plan = (int)pslot, d.nrows = tr, d.z = zs, d.y = ys;
+        d.flags = (t == 0 ? TILE_FIRST : 0) | (t == ntiles - 1 ? TILE_LAST : 0);
+        d.rowfloats = RXB, d.chunk = chunk, d.pad = 0;
+        tdesc[slot] = d;
+        st_mbar_expect_tx(full, t == 0 ? (unsigned)PLAN_BYTES : 0u);
+        if (t == 0) st_bulk_g2s(s_u32(smem + L::PLAN + pslot * PLAN_BYTES), a.plans + r_sched, PLAN_BYTES, full);
+      }
+      const unsigned dst0 = s_u32(smem + L::RING + slot * SN_SLOT) + (unsigned)((pwarp * CPW * SN_S + lane * 4) * 4);
+      const float *src = base;
+#pragma unroll 4
+      for (int c = 0; c < CPW; ++c) {
+#pragma unroll
+        for (int j = 0; j < SN_EMAX; ++j)
+          if (off[j] >= 0) st_cp_async16(dst0 + (unsigned)((c * SN_S + 128 * j) * 4), src + off[j]);
+        src += vox;
+      }
+      st_cp_async_arrive(full);
+      r += tr;
+      {
+        const int pe = ys + tr;
+        const int de = (pe * magic_y) >> 16;
+        zs += de, ys = pe - de * RY;
+      }
+      ++tile_seq;
+    }
   }
-  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+  // sentinel tile
+  const unsigned slot = tile_seq % NS;
+  st_mbar_wait(bar0 + (NS + slot) * 8, ((tile_seq / NS) & 1) ^ 1);
+  if (leader) {
+    TileDesc d;
+    d.plan = 0, d.nrows = 0, d.z = 0, d.y = 0, d.flags = TILE_DONE, d.rowfloats = 0, d.chunk = 0, d.pad = 0;
+    tdesc[slot] = d;
+    st_mbar_arrive(bar0 + slot * 8);
+  }
+  st_cp_async_arrive(bar0 + slot * 8);
+}
+
+template <int NS>
+__global__ void __launch_bounds__(SN_WARPS * 32, 1) roi_align3d_fwd_stream_ncdhw_kernel(const __grid_constant__ StreamArgs a) {
+  using L = Lay<NS, SN_SLOT>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned bar0 = s_u32(smem + L::BAR);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      st_mbar_init(bar0 + s * 8, SN_PROD * 32 + 1);   // full: every producer lane's copies + the leader's arrive (+ plan bytes)
+      st_mbar_init(bar0 + (NS + s) * 8, ST_OWNERS);    // empty: one arrive per owner warp
+    }
+    st_mbar_init(bar0 + 2 * NS * 8, ST_OWNERS);        // staging full
+    st_mbar_init(bar0 + 2 * NS * 8 + 8, 1);            // staging free
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+
+  if (warp < ST_OWNERS) {
+    if (warp < 7) owner_loop<4, NS, SN_SLOT, true>(a, smem, 0, warp, warp, lane);
+    else owner_loop<3, NS, SN_SLOT, true>(a, smem, 4, warp - 7, warp, lane);
+    return;
+  }
+  if (warp < ST_OWNERS + SN_PROD) {
+    producer_loop_ncdhw<NS>(a, smem, warp - ST_OWNERS, lane);
+    return;
+  }
+  storer_loop<NS, SN_SLOT>(a, smem, lane);
 }
 
 // =================================================================================================================
@@ -874,6 +1103,9 @@ int level_maps(const LevelDev &L, int B, int C, const CUtensorMap **out) {
 
 bool fwd_stream_ok(const RoiParams &p) {
   if (p.PW != 7 || p.PH != 7 || p.PD < 1 || p.PD > 7) return false;
+  if (p.layout == ROI3D_NCDHW)   // 32-bit offsets inside one channel's volume
+    for (int l = 0; l < p.num_levels; ++l)
+      if ((long long)p.lv[l].D * p.lv[l].H * p.lv[l].W >= 2147483647LL || p.lv[l].W % 4 != 0) return false;   // 16-byte row pieces
   if (p.C % ST_CH != 0 || p.num_levels > ST_MAX_LEVELS) return false;
   if ((reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return false;
   if ((long long)p.K * (p.C / ST_CH) >= 2147483647LL) return false;
@@ -982,9 +1214,13 @@ int acquire_plan_ws(size_t bytes, cudaStream_t st, unsigned char **ws, bool *poo
   return ROI3D_OK;
 }
 
-template <int NS, int SLOT>
+template <int NS, int SLOT, bool NC = false>
 int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count) {
   using L = Lay<NS, SLOT>;
+  auto kernel = [] {
+    if constexpr (NC) return roi_align3d_fwd_stream_ncdhw_kernel<NS>;
+    else return roi_align3d_fwd_stream_kernel<NS, SLOT>;
+  }();
   const size_t plan_bytes = (size_t)p.K * sizeof(StreamPlan);
   unsigned char *ws = nullptr;
   bool pooled = false;
@@ -994,24 +1230,23 @@ int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count)
   int *counter = reinterpret_cast<int *>(ws + plan_bytes);
   const int sort = (p.K <= ST_SORT_MAX && !(a.debug & 4)) ? 1 : 0;
   const int grid = a.total_items < sm_count ? a.total_items : sm_count;
-  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(p, plans, counter, sort, SLOT, 3 * grid);
+  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(p, plans, counter, NC && sort && !(a.debug & 16) ? 2 : sort, SLOT, NC ? 2 * grid : 3 * grid, NC ? 1 : 0);
   ROI3D_LAUNCH_CHECK();
   a.plans = plans, a.counter = counter;
   static bool attr_set = false;
   if (!attr_set) {
-    ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_stream_kernel<NS, SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    L::LAUNCH));
+    ROI3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::LAUNCH));
     attr_set = true;
   }
   if (g_timing_ev[0] != nullptr) ROI3D_CUDA(cudaEventRecord(g_timing_ev[0], st));   // (measurement hook, see roi3d_set_kernel_timing_events)
   {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(ST_WARPS * 32), cfg.dynamicSmemBytes = L::LAUNCH, cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3((NC ? SN_WARPS : ST_WARPS) * 32), cfg.dynamicSmemBytes = L::LAUNCH, cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    ROI3D_CUDA(cudaLaunchKernelEx(&cfg, roi_align3d_fwd_stream_kernel<NS, SLOT>, a));
+    ROI3D_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
   }
   ROI3D_LAUNCH_CHECK();
   if (g_timing_ev[1] != nullptr) ROI3D_CUDA(cudaEventRecord(g_timing_ev[1], st));
@@ -1026,7 +1261,7 @@ int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count)
 thread_local cudaEvent_t g_timing_ev[2] = {nullptr, nullptr};
 
 int g_fwd_stream_cfg = 0;       // roi3d_set_tuning key 7: ring geometry of the streamed kernel (0 = default)
-int g_fwd_stream_debug = 0;     // key 9: developer experiments (bit 0: owners skip the arithmetic, bit 1: no output store)
+int g_fwd_stream_debug = 0;     // key 9: developer experiments (bit 0: owners skip the arithmetic, bit 1: no output store, bit 2: no sort, bit 4: NCDHW twin in largest-first order)
 
 int launch_fwd_stream(RoiParams &p, cudaStream_t st) {
   static int sm_count = 0;
@@ -1038,13 +1273,16 @@ int launch_fwd_stream(RoiParams &p, cudaStream_t st) {
   StreamArgs a;
   a.p = p;
   for (int l = 0; l < ST_MAX_LEVELS; ++l) a.maps[l] = nullptr;
+  a.total_items = p.K * (p.C / ST_CH);
+  a.pdhw = p.PD * 49;
+  a.debug = g_fwd_stream_debug;
+  if (p.layout == ROI3D_NCDHW) {   // cp.async producers, no tensor maps
+    return launch_cfg<3, SN_SLOT, true>(p, a, st, sm_count);
+  }
   for (int l = 0; l < p.num_levels; ++l) {
     const int rc = level_maps(p.lv[l], p.B, p.C, &a.maps[l]);
     if (rc) return rc;
   }
-  a.total_items = p.K * (p.C / ST_CH);
-  a.pdhw = p.PD * 49;
-  a.debug = g_fwd_stream_debug;
   // ring geometry (measured on C2, whole call): 3 x 42 KB 154 us, 4 x 32 KB 156 us, 4 x 30 KB 160 us, 5 x 24 KB 166 us,
   // 4 x 20 KB 185 us, 8 x 15 KB 215 us -- per-tile hand-offs cost more than a shallower ring
   switch (g_fwd_stream_cfg) {
@@ -1087,7 +1325,7 @@ int launch_bwd_stream(RoiParams &p, cudaStream_t st) {
   const int grid = a.total_items < sm_count ? a.total_items : sm_count;
   RoiParams pp = p;
   pp.lvls_out = nullptr;   // (the forward reports the levels)
-  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(pp, plans, counter, sort, 43008, 0);
+  roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(pp, plans, counter, sort, 43008, 0, 0);
   ROI3D_LAUNCH_CHECK();
   a.plans = plans, a.counter = counter;
   static bool attr_set = false;

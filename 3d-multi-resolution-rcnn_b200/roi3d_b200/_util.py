@@ -98,22 +98,23 @@ def to_channels_last_3d(x):
     return conv, True
 
 
-FORCE_NATIVE_NCDHW = [False]   # developer switch: always hand NCDHW levels to the planar kernel when it can read them
+FORCE_NATIVE_NCDHW = [False]   # developer switch: always hand NCDHW levels to the native kernels when they can read them
 
 
 def forward_inputs(feats, out_h, out_w):
     """Pick the memory the forward kernels read for a list of [B,C,D,H,W] levels: (tensors, layout flag).
     Channels-last levels go in as they are.  NCDHW-contiguous levels -- what the reference's callers hold
-    (roi_align_cuda.cpp:35-39) -- also go in as they are when the planar kernel can read them (square 7- or 14-wide
-    output, rows that start on 16-byte boundaries); anything else is converted to channels-last first."""
+    (roi_align_cuda.cpp:35-39) -- also go in as they are when a native kernel can read them (square 7- or 14-wide
+    output, rows that start on 16-byte boundaries: the streamed kernel's NCDHW twin for 7-wide outputs on multiples of 64
+    channels, the planar kernel otherwise); anything else is converted to channels-last first."""
     if all(is_channels_last_3d(f) for f in feats):
         return list(feats), _lib.NDHWC
     native = out_h == out_w and out_h in (7, 14) and all(
         f.is_contiguous() and f.shape[-1] % 4 == 0 and f.data_ptr() % 16 == 0 for f in feats)
     # Inside a reuse_layout_conversions() scope a 7-wide extractor on 64-channel multiples converts once and runs the
     # streamed channels-last kernel: the converted copy serves every extractor call of the pass (C2: 137 us per call
-    # after a 240 us conversion).  A lone call reads the NCDHW tensor in place with the planar kernel (357 us against
-    # 377 us for conversion + streamed kernel).
+    # after a 240 us conversion).  A lone call reads the NCDHW tensor in place with the streamed kernel's NCDHW twin
+    # (planar kernel 357 us, conversion + streamed kernel 377 us).
     if native and out_h == 7 and feats[0].shape[1] % 64 == 0 and _scopes and not FORCE_NATIVE_NCDHW[0]:
         native = False
     if native:

@@ -389,8 +389,8 @@ def main():
                     "output_only_gbs": out_bytes / (main_kernel_ms * 1e-3) / 1e9,
                     "layout": "channels-last (NDHWC) features resident in HBM"}
         if extra.get("c2_fwd_ncdhw_input_us"):
-            # the reference's own layout, read in place by the planar kernel (rows of a RoI are 40-70 bytes of a 512-byte
-            # feature row: DRAM moves about 1 GB for the same algorithmic bytes)
+            # the reference's own layout, read in place by the streamed kernel's NCDHW twin (rows of a RoI are 40-70 bytes
+            # of a 512-byte feature row: DRAM moves about 1 GB for the same algorithmic bytes)
             us = extra["c2_fwd_ncdhw_input_us"]
             roofline["ncdhw_input"] = {"kernel": extra.get("c2_fwd_ncdhw_input_kernel"), "kernel_us": us,
                                        "achieved": alg_bytes / (us * 1e-6) / 1e9,
@@ -515,11 +515,17 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
         return float(np.median(ts))
 
     ex = {}
-    # C2 with the reference's NCDHW-contiguous input, as a lone call: the planar kernel reads the tensor in place
+    # C2 with the reference's NCDHW-contiguous input, as a lone call: the NCDHW twin of the streamed kernel reads the tensor
+    # in place (16-byte cp.async producers); the planar kernel on the same call is timed beside it (tuning variant 60)
     us = med_us(lambda: layer(feats, rois), iters=5)
     ex["c2_fwd_ncdhw_input_us"] = us
     ex["c2_fwd_ncdhw_input_rois_per_sec"] = C2["K"] / (us * 1e-6)
-    ex["c2_fwd_ncdhw_input_kernel"] = "roi_align3d_fwd_planar_kernel<7,false,7> (native NCDHW, no conversion)"
+    ex["c2_fwd_ncdhw_input_kernel"] = "roi_align3d_fwd_stream_ncdhw_kernel<3> (native NCDHW, no conversion)"
+    roi3d_b200._lib.set_tuning(0, 60)
+    try:
+        ex["c2_fwd_ncdhw_input_planar_kernel_us"] = med_us(lambda: layer(feats, rois), iters=5)
+    finally:
+        roi3d_b200._lib.set_tuning(0, 0)
     # the other route: convert to channels-last once (reusable by every extractor call of a pass, see
     # roi3d_b200.reuse_layout_conversions) + the streamed kernel; a fresh scope per call = conversion paid every time
     import roi3d_b200 as _r3

@@ -1083,6 +1083,14 @@ def test_roi_align_forward_streamed_kernel(oracle, dev, case):
     assert rel_err(out.cpu().numpy(), ring.cpu().numpy()) <= FWD_TOL
     # a second call on the same buffers (cached tensor maps, recycled workspace) gives the same bits
     assert torch.equal(layer(ft, rt), out)
+    # the NCDHW twin (cp.async producers, the reference's layout read in place; W % 4 == 0, otherwise the planar kernel
+    # or the conversion path take the call): same owners with the x taps summed in a lane-rotated order
+    fn = torch.from_numpy(f).to(dev)
+    assert fn.is_contiguous()
+    nat = layer(fn, rt)
+    assert rel_err(nat.cpu().numpy(), want) <= FWD_TOL
+    assert rel_err(nat.cpu().numpy(), out.cpu().numpy()) <= FWD_TOL
+    assert torch.equal(layer(fn, rt), nat)
 
 
 @pytest.mark.gpu
