@@ -8,6 +8,7 @@ OUT=$HERE/lib
 mkdir -p "$OUT" "$HERE/build"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -DROI3D_BUILD)
 [ "${VERBOSE_PTXAS:-0}" = "1" ] && FLAGS+=(-Xptxas -v)
+[ -n "${ROI3D_EXTRA_NVCC_FLAGS:-}" ] && FLAGS+=(${ROI3D_EXTRA_NVCC_FLAGS})
 pids=()
 for f in roi_align3d roi_align3d_stream roi_align3d_planar nms3d proposal assign mask_paste host_api; do
   src=$HERE/csrc/$f.cu

@@ -235,8 +235,9 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
   __shared__ unsigned long long remv[kMaxColBlocks];
   __shared__ unsigned long long keptw[kMaxColBlocks];
   extern __shared__ __align__(16) unsigned long long panel_dyn[];  // [kPanelBufs][64][kPanelW]
+  // row stride kPanelW + 1 words: lanes = words (helpers' stores) and lanes = rows (resolver, apply) are both conflict-free
   auto panel = [&](int buf, int row, int w) -> unsigned long long & {
-    return panel_dyn[((size_t)buf * 64 + row) * kPanelW + w];
+    return panel_dyn[((size_t)buf * 64 + row) * (kPanelW + 1) + w];
   };
   __shared__ int s_warp[8];
 
@@ -244,108 +245,120 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
   for (int i = tid; i < cb; i += 256) keptw[i] = 0ULL;
 
   // Pipeline over the 64-box diagonal tiles, one __syncthreads per tile:
-  //   warp 0 (resolver)   resolves tile b from panel[b%4] (lane 0: the 64 diagonal words in registers, a
-  //                       test -> predicated-OR chain on 32-bit halves), then ORs the kept rows into word b+1
-  //                       itself, so the next tile's state is complete without waiting for anyone;
-  //   warps 1..7 (helpers) meanwhile apply tile b-1's kept rows (panel[(b-1)%4]) to the words >= b+1 and
-  //                       prefetch tile b+2's rows (words [b+2, b+2+kPanelW) of its 64 mask rows) with
-  //                       cp.async into panel[(b+2)%4] (two tiles ahead hides the L2 round trip); the mask
-  //                       rows do not depend on the sweep state.
+  //   warp 0 (resolver)   resolves tile b from panel[b%4]: lane l holds diagonal rows l and l + 32 (the bits above the
+  //                       row's own index) and the warp iterates  K <- cand & ~OR{row_j : j in K}  from K = cand (the
+  //                       boxes not yet removed) until K repeats.  Bit i of K is final after i rounds (it depends on
+  //                       the bits below it only) and a repeated K satisfies the greedy recurrence, whose solution is
+  //                       unique -- so the result is exactly the sequential sweep's, in about twice the depth of the
+  //                       longest suppression chain (a few rounds of two warp-wide ORs) instead of 64 dependent steps.
+  //                       The warp then ORs the kept rows into word b+1 itself, so the next tile's state is complete
+  //                       without waiting for anyone;
+  //   warps 1..7 (helpers) meanwhile apply tile b-1's kept rows (panel[(b-1)%4]) to the words >= b+1 and move the mask
+  //                       rows of the tiles ahead (words [t, t+kPanelW) of tile t's 64 rows; they do not depend on the
+  //                       sweep state) through registers: loaded in iteration t-6 (coalesced 8-byte loads, a row per
+  //                       warp instruction; four register sets take turns), stored to panel[t%4] in iteration t-2.  (8-byte cp.async was the helpers'
+  //                       critical path: the LSU retires about one cp.async lane per clock.)
   const int warp = tid >> 5, lane = tid & 31;
-  auto prefetch = [&](int blk) {  // helpers only: 224 threads
-    if (blk < cb) {
-      const int buf = blk % kPanelBufs;
-      const int nwp = min(kPanelW, cb - blk);
-      for (int idx = tid - 32; idx < 64 * kPanelW; idx += 224) {
-        const int row = idx / kPanelW, w = idx - row * kPanelW;
-        const int grow = blk * 64 + row;
-        unsigned long long *dst = &panel(buf, row, w);
-        if (grow < n && w < nwp) {
-          const unsigned sd = (unsigned)__cvta_generic_to_shared(dst);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sd), "l"(m + (long long)grow * cbm + blk + w)
-                       : "memory");
-        } else {
-          *dst = 0ULL;
-        }
-      }
+  // helper warp g moves rows g, g + 7, ... of a tile (lane = word of the panel: one coalesced 256-byte row per load)
+  constexpr int kHelperLoads = (64 + 6) / 7;
+  static_assert(kPanelW == 32, "helper lanes are the panel's words");
+  const int hg = warp - 1;
+  const long long tile_step = 64LL * cbm + 1;                      // words from a tile's panel origin to the next tile's
+  const unsigned long long *hbase = m + (long long)hg * cbm + lane;   // row hg of tile 0, word `lane`
+  unsigned long long stage0[kHelperLoads], stage1[kHelperLoads], stage2[kHelperLoads], stage3[kHelperLoads];   // tiles blk+2 .. blk+5 on their way to the panel
+  auto load_tile = [&](int blk, unsigned long long (&stage)[kHelperLoads]) {   // helpers only
+    const bool on = blk < cb && lane < cb - blk;
+    const unsigned long long *src = hbase + blk * tile_step;
+    const int row_lim = min(64, n - blk * 64) - hg;   // rows hg + 7 q below this exist
+#pragma unroll
+    for (int q = 0; q < kHelperLoads; ++q) {
+      stage[q] = (on && 7 * q < row_lim) ? __ldcg(src) : 0ULL;
+      src += 7 * cbm;
     }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  auto store_tile = [&](int blk, const unsigned long long (&stage)[kHelperLoads]) {
+    unsigned long long *dst = &panel(blk % kPanelBufs, hg, lane);
+#pragma unroll
+    for (int q = 0; q < kHelperLoads; ++q)
+      if (hg + 7 * q < 64) dst[q * 7 * (kPanelW + 1)] = stage[q];
   };
   if (warp > 0) {
-    prefetch(0);
-    prefetch(1);
-    asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // tile 0 landed, tile 1 may still be in flight
+    load_tile(0, stage0), load_tile(1, stage1);
+    store_tile(0, stage0), store_tile(1, stage1);
+    load_tile(2, stage0), load_tile(3, stage1), load_tile(4, stage2), load_tile(5, stage3);   // stored in iterations 0..3
   }
   __syncthreads();
 
-  for (int blk = 0; blk < cb; ++blk) {
+  unsigned long long nd0 = 0ULL, nd1 = 0ULL;
+  if (warp == 0) nd0 = panel(0, lane, 0), nd1 = panel(0, lane + 32, 0);
+  auto sweep_tile = [&](int blk, unsigned long long (&stage)[kHelperLoads]) {
     if (warp == 0) {
       const int buf = blk % kPanelBufs;
       const int bs = min(64, n - blk * 64);
-      unsigned long long kept = 0ULL;
-      if (lane == 0) {
-        unsigned dlo[32], dhi[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const unsigned long long d = panel(buf, i, 0);
-          if (i < 32) dlo[i] = (unsigned)d;
-          dhi[i] = (unsigned)(d >> 32);
+      // this tile's diagonal rows were fetched at the end of the previous iteration
+      const unsigned long long d0 = nd0 & ~((2ULL << lane) - 1ULL);                               // bits above the row's own index
+      const unsigned long long d1 = lane == 31 ? 0ULL : nd1 & ~((2ULL << (lane + 32)) - 1ULL);
+      unsigned long long r0 = remv[blk];
+      if (bs < 64) r0 |= ~0ULL << bs;  // rows past n never count as kept
+      const unsigned long long cand = ~r0;
+      unsigned long long kept = cand;
+#pragma unroll 1
+      for (int it = 0; it < 64; ++it) {
+        unsigned long long v = 0ULL;
+        if ((kept >> lane) & 1ULL) v |= d0;
+        if ((kept >> (lane + 32)) & 1ULL) v |= d1;
+        v &= cand;
+        unsigned long long next = cand;
+        if (__any_sync(0xffffffffu, v != 0ULL)) {   // (a vote is much cheaper than the two warp-wide ORs)
+          const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+          const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+          next = cand & ~(((unsigned long long)hi << 32) | lo);
         }
-        // pin all 96 words in registers before the chain starts (otherwise ptxas sinks the shared-memory
-        // loads into the chain and every step pays their latency)
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          if (i < 32) asm volatile("" : "+r"(dlo[i]));
-          asm volatile("" : "+r"(dhi[i]));
-        }
-        unsigned long long r0 = remv[blk];
-        if (bs < 64) r0 |= ~0ULL << bs;  // rows past n never count as kept
-        unsigned rlo = (unsigned)r0, rhi = (unsigned)(r0 >> 32), klo = 0u, khi = 0u;
-        asm volatile("" : "+r"(rlo), "+r"(rhi));  // ordered after the pins above: the chain starts with all words loaded
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (!(rlo & (1u << i))) {
-            klo |= 1u << i;
-            rlo |= dlo[i];
-            rhi |= dhi[i];
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (!(rhi & (1u << i))) {
-            khi |= 1u << i;
-            rhi |= dhi[32 + i];
-          }
-        }
-        kept = ((unsigned long long)khi << 32) | klo;
-        keptw[blk] = kept;
+        if (next == kept) break;
+        kept = next;
       }
-      kept = __shfl_sync(0xffffffffu, kept, 0);
+      if (lane == 0) keptw[blk] = kept;
       if (blk + 1 < cb) {
         // word blk+1: lanes take rows lane and lane+32, OR-reduce across the warp
         unsigned long long v = 0ULL;
         if ((kept >> lane) & 1ULL) v |= panel(buf, lane, 1);
         if ((kept >> (lane + 32)) & 1ULL) v |= panel(buf, lane + 32, 1);
-        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
-        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-        if (lane == 0) atomicOr(&remv[blk + 1], ((unsigned long long)hi << 32) | lo);
+        const int nbuf = (blk + 1) % kPanelBufs;   // the next tile's diagonal rows (landed an iteration ago)
+        nd0 = panel(nbuf, lane, 0), nd1 = panel(nbuf, lane + 32, 0);
+        if (__any_sync(0xffffffffu, v != 0ULL)) {
+          const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+          const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+          if (lane == 0) {
+            unsigned *dst = reinterpret_cast<unsigned *>(&remv[blk + 1]);
+            if (lo) atomicOr(dst, lo);
+            if (hi) atomicOr(dst + 1, hi);
+          }
+        }
       }
     } else {
-      // helpers: finish tile blk-1 (words >= blk+1), then fetch tile blk+1
+      // helpers: park the rows loaded last iteration, request the next tile's, then finish tile blk-1 (words >= blk+1)
+      store_tile(blk + 2, stage);
+      load_tile(blk + 6, stage);
       if (blk >= 1) {
         const int pb = blk - 1, buf = pb % kPanelBufs;
         const unsigned long long kept = keptw[pb];
         const int nw = cb - pb - 1;              // words after the diagonal of tile pb
         const int nwp = min(kPanelW - 1, nw);    // of which the panel holds nwp (w = 1..nwp)
-        // panel words w = 2..nwp  (w = 1 was applied by the resolver): thread -> (word, 8-row group)
+        // panel words w = 2..nwp (w = 1 was applied by the resolver): lane = word, helper warp g ORs the kept rows among
+        // its rows g * 10 .. g * 10 + 9 (the row test is warp-uniform) and merges with native 32-bit shared atomics
         const int ht = tid - 32;                 // 0..223
-        const int w = 2 + (ht & 31), g = ht >> 5;  // g in 0..6 -> rows are split 7 ways (10 rows each, last 4)
+        const int w = 2 + lane;
         if (w <= nwp) {
           unsigned long long v = 0ULL;
-          const int r0 = g * 10, r1 = min(64, r0 + 10);
-          for (int row = r0; row < r1; ++row)
-            if ((kept >> row) & 1ULL) v |= panel(buf, row, w);
-          if (v) atomicOr(&remv[pb + w], v);
+          const int r0 = hg * 10;
+          const unsigned rows = (unsigned)(kept >> r0) & (r0 + 10 <= 64 ? 0x3ffu : 0xfu);
+          const unsigned long long *pp = &panel(buf, r0, w);
+#pragma unroll
+          for (int r = 0; r < 10; ++r)
+            if (rows & (1u << r)) v |= pp[r * (kPanelW + 1)];
+          unsigned *dst = reinterpret_cast<unsigned *>(&remv[pb + w]);
+          if ((unsigned)v) atomicOr(dst, (unsigned)v);
+          if ((unsigned)(v >> 32)) atomicOr(dst + 1, (unsigned)(v >> 32));
         }
         // words beyond the panel (only when n > 64*kPanelW): straight from global memory
         for (int idx = ht; idx < (nw - nwp) * 64; idx += 224) {
@@ -356,10 +369,14 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
           }
         }
       }
-      prefetch(blk + 2);                                       // two tiles ahead: hides the L2 round trip
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // tile blk+1 has landed
     }
     __syncthreads();
+  };
+  for (int blk = 0; blk < cb; blk += 4) {   // four register sets take turns: a tile's rows have four iterations to arrive
+    sweep_tile(blk, stage0);                 // (two were not enough: an L2 round trip is longer than two iterations)
+    if (blk + 1 < cb) sweep_tile(blk + 1, stage1);
+    if (blk + 2 < cb) sweep_tile(blk + 2, stage2);
+    if (blk + 3 < cb) sweep_tile(blk + 3, stage3);
   }
   // the last tile's kept rows have no later words to update; nothing left to apply
 
@@ -367,6 +384,7 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
   // Everything below is position-parallel: no per-thread serial chains of dependent global loads.
   __shared__ int excl[kMaxColBlocks];           // exclusive prefix of popc(keptw)
   __shared__ unsigned bitmap[kMaxColBlocks * 2];  // kept flags by ORIGINAL index
+  __shared__ int excl_idx[kMaxColBlocks * 2];     // exclusive prefix of popc(bitmap)
   __shared__ int s_total;
   // (1) block scan of the per-word kept counts (cb <= 512: two words per thread)
   {
@@ -395,28 +413,40 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
     __syncthreads();
   }
   const int total = s_total;
-  // (2) every sorted position in parallel: rank among the kept, original index (coalesced load)
-  for (int pos = tid; pos < n; pos += 256) {
-    const unsigned long long kw = keptw[pos >> 6];
-    const int b = pos & 63;
-    if ((kw >> b) & 1ULL) {
-      const int rank = excl[pos >> 6] + __popcll(kw & ((1ULL << b) - 1ULL));
-      const int orig = ord[pos];
-      if (kps) kps[rank] = orig;
-      atomicOr(&bitmap[orig >> 5], 1u << (orig & 31));
+  // (2) every sorted position in parallel: rank among the kept, original index (coalesced loads, eight in flight per
+  //     thread: one global round trip per 2048 positions)
+  for (int pos0 = 0; pos0 < n; pos0 += 256 * 8) {
+    int orig[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int pos = pos0 + q * 256 + tid;
+      orig[q] = pos < n ? __ldg(ord + pos) : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int pos = pos0 + q * 256 + tid;
+      if (pos < n) {
+        const unsigned long long kw = keptw[pos >> 6];
+        const int b = pos & 63;
+        if ((kw >> b) & 1ULL) {
+          const int rank = excl[pos >> 6] + __popcll(kw & ((1ULL << b) - 1ULL));
+          if (kps) kps[rank] = orig[q];
+          atomicOr(&bitmap[orig[q] >> 5], 1u << (orig[q] & 31));
+        }
+      }
     }
   }
   __syncthreads();
-  // (3) ascending original index: scan the bitmap words (<= 1024: four per thread), then write out
+  // (3) ascending original index: exclusive scan of the bitmap words' counts (<= 1024 words: four per thread), then every
+  //     original index in parallel
   {
     const int nbw = (n + 31) >> 5;
-    unsigned wds[4];
-    int cnt = 0;
+    int c[4], cnt = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int w = tid * 4 + q;
-      wds[q] = w < nbw ? bitmap[w] : 0u;
-      cnt += __popc(wds[q]);
+      c[q] = w < nbw ? __popc(bitmap[w]) : 0;
+      cnt += c[q];
     }
     int incl = cnt;
 #pragma unroll
@@ -431,16 +461,18 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       if (q < warp) woff += s_warp[q];
-    int outp = woff + incl - cnt;
+    int run = woff + incl - cnt;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      unsigned bits = wds[q];
-      const int base_idx = (tid * 4 + q) * 32;
-      while (bits) {
-        const int bb = __ffs((int)bits) - 1;
-        bits &= bits - 1;
-        kp[outp++] = base_idx + bb;
-      }
+      const int w = tid * 4 + q;
+      if (w < nbw) excl_idx[w] = run;
+      run += c[q];
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+      const unsigned bits = bitmap[i >> 5];
+      const int bb = i & 31;
+      if ((bits >> bb) & 1u) kp[excl_idx[i >> 5] + __popc(bits & ((1u << bb) - 1u))] = i;
     }
   }
   if (tid == 0) num_keep[seg] = total;
@@ -529,7 +561,7 @@ static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, co
                                                                                 iou_thr64, w.mask);
   ROI3D_LAUNCH_CHECK();
   {
-    const size_t panel_bytes = (size_t)kPanelBufs * 64 * kPanelW * sizeof(unsigned long long);  // 64 KiB
+    const size_t panel_bytes = (size_t)kPanelBufs * 64 * (kPanelW + 1) * sizeof(unsigned long long);  // 66 KiB
     ROI3D_CUDA(cudaFuncSetAttribute(nms3d_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_bytes));
     nms3d_sweep_kernel<<<nseg, 256, panel_bytes, st>>>(w.mask, w.order, seg_counts_dev, n_max, w.flags, keep_dev,
                                                       keep_by_score_dev, num_keep_dev);

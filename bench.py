@@ -555,6 +555,19 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
     ex["c1_nms2000_us"] = us
     ex["c1_nms2000_boxes_per_sec"] = 2000 / (us * 1e-6)
     ex["c1_nms2000_iou_pairs_per_sec"] = 1999000 / (us * 1e-6)
+    # the same call 200 times back to back (the launch queue never runs dry: device time per NMS without the host's
+    # per-call latency), and the host's own CPU time per call (python glue + ctypes + three launches)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(200):
+        nms3d_batched(d1, None, 0.7)
+    b.record()
+    host_us = (time.perf_counter() - t0) / 200 * 1e6
+    torch.cuda.synchronize()
+    ex["c1_nms2000_back_to_back_us"] = a.elapsed_time(b) * 1e3 / 200
+    ex["c1_nms2000_host_cpu_us_per_call"] = host_us
     d40 = dets[None].repeat(40, 1, 1).contiguous()
     us = med_us(lambda: nms3d_batched(d40, None, 0.7), iters=10, do_flush=False)
     ex["c1_nms2000_x40_batched_us"] = us
