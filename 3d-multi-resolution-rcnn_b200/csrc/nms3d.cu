@@ -12,10 +12,12 @@
 //   2. mask kernel     -- upper-triangular 64x64 tiles only, column boxes staged in shared memory,
 //                         one uint64 word per (row, column-tile);
 //   3. sweep kernel    -- one CTA per segment walks the 64-box diagonal tiles as a pipeline: warp 0 resolves
-//                         tile b (one lane, the 64 diagonal words in registers) and updates the next tile's
-//                         `removed` word itself, while warps 1..7 apply tile b-1 to the later words and
-//                         prefetch the mask rows of tile b+2 with cp.async; the kept set is then compacted
-//                         position-parallel twice (descending score, and ascending original index).
+//                         tile b with a warp-parallel fixed-point iteration (lanes hold the diagonal rows; K <- cand &
+//                         ~OR{row_j : j in K} until K repeats: exactly the sequential sweep's set) and updates the
+//                         next tile's `removed` word itself, while warps 1..7 apply tile b-1 to the later words and
+//                         stage the mask rows of the tiles ahead through registers (coalesced loads, four tiles
+//                         deep); the kept set is then compacted position-parallel twice (descending score, and
+//                         ascending original index).
 // No host synchronisation, no D2H copy; many (volume, level, class) segments share the three launches.
 //
 // Bit-exactness: IoU uses explicit _rn intrinsics in exactly the operation order of the compiled

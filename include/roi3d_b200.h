@@ -21,8 +21,9 @@
  *   - Feature layout: ROI3D_NCDHW is the reference's contiguous [B,C,D,H,W]; ROI3D_NDHWC is the same
  *     logical tensor stored channels-last ([B,D,H,W,C] in memory, torch.channels_last_3d).  The FORWARD
  *     entries take either: channels-last levels feed the streamed / per-warp kernels, NCDHW levels are read
- *     in place by the planar kernel (square 7- or 14-wide outputs, 16-byte aligned levels, W % 4 == 0;
- *     other NCDHW shapes return ROI3D_EINVAL: convert with roi3d_ncdhw_to_ndhwc).  The BACKWARD entries
+ *     in place -- by the streamed kernel's NCDHW twin (7 x 7 x PD outputs, C % 64 == 0) or the planar kernel
+ *     (square 7- or 14-wide outputs); both want 16-byte aligned levels and W % 4 == 0, other NCDHW shapes
+ *     return ROI3D_EINVAL: convert with roi3d_ncdhw_to_ndhwc.  The BACKWARD entries
  *     accumulate into channels-last (ROI3D_NDHWC) gradients only.
  */
 #ifndef ROI3D_B200_H_
