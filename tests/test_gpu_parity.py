@@ -657,6 +657,13 @@ def test_c2_full_size_properties(oracle, dev):
     ch = [0, 101, 255]
     want = oracle.roi_align3d_forward(x[:, ch].cpu().numpy(), rois_np, 7, 7, 0.25, 0.5, 2)
     assert rel_err(fx[:, ch].cpu().numpy(), want) <= FWD_TOL
+    # the same call on the reference's NCDHW tensor (read in place by the streamed kernel's NCDHW twin)
+    xn = x.contiguous()
+    assert xn.is_contiguous() and not xn.is_contiguous(memory_format=torch.channels_last_3d)
+    fn = layer(xn, rois)
+    assert float((fn - fx).abs().max()) <= 1e-5
+    assert rel_err(fn[:, ch].cpu().numpy(), want) <= FWD_TOL
+    del xn, fn
     # adjointness <f(x), g> == <x, f^T(g)> in float64
     xg = x.clone().requires_grad_(True)
     out = layer(xg, rois)
