@@ -32,7 +32,7 @@ for line in sass.split("\n"):
         tot += 1
 if cur:
     rows.append((cur, cnt, tot))
-KEEP = ("roi_align3d_fwd_stream_kernel", "roi_align3d_plan_kernel", "roi_align3d_fwd_planar_kernel", "roi_align3d_bwd2_kernel",
+KEEP = ("roi_align3d_fwd_stream_kernel", "roi_align3d_fwd_stream_ncdhw_kernel", "roi_align3d_bwd_stream_kernel", "roi_align3d_bwd_planar_kernel", "roi_align3d_plan_kernel", "roi_align3d_fwd_planar_kernel", "roi_align3d_bwd2_kernel",
         "nms3d_", "topk_first_kernel", "topk_second_kernel", "topk_split_keys_kernel", "topk_tail_kernel",
         "decode_proposals_batched_kernel", "assign_pass", "mask_paste_kernel", "transpose_r32c128")
 with open(sys.argv[1], "w") as f:
