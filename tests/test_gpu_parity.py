@@ -856,6 +856,17 @@ def test_roi_align_forward_row_map(dev, out_size):
         out.data_ptr(), perm.data_ptr(), stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(out[perm.long()], plain)
+    if out_size in (7, 14):
+        # the same row map over the reference's NCDHW tensor (streamed kernel's NCDHW twin / planar kernel)
+        fn = f.contiguous()
+        plain_n = RoIAlign3D(out_size, out_size, 0.25, 0.5, 2)(fn, rois)
+        out_n = torch.full_like(plain, float("nan"))
+        _lib.check(_lib.lib.roi3d_roi_align3d_forward_rows(
+            fn.data_ptr(), _lib.NCDHW, 1, 64, 12, 40, 72, rois.data_ptr(), K, out_size, out_size, out_size, 0.25, 0.5, 2,
+            out_n.data_ptr(), perm.data_ptr(), stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(out_n[perm.long()], plain_n)
+        assert float((plain_n - plain).abs().max()) <= 1e-5
 
 
 # ---------------------------------------------------------------------------------------------------------------
