@@ -30,6 +30,10 @@
 //
 // RoIs whose bins need more than four contiguous taps, or whose footprint is wider than the tiles, are flagged by the
 // plan kernel and evaluated literally (reference sample loops, bit-exact) by the same owner warps.
+//
+// The file also holds the kernel's NCDHW twin (roi_align3d_fwd_stream_ncdhw_kernel: the reference's layout read in
+// place, same plans / owners / storer, producers = warps issuing 16-byte cp.async; see the comment above it) and the
+// streamed backward (roi_align3d_bwd_stream_kernel).
 #include <cuda.h>
 
 #include <mutex>
