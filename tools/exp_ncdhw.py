@@ -45,11 +45,3 @@ _lib.set_tuning(9, 0)
 _lib.set_tuning(0, 60)
 print("NCDHW planar: %.1f us" % timeit(lambda: layer(nat, r)), flush=True)
 _lib.set_tuning(0, 0)
-
-for cfg in (3, 0):
-    _lib.set_tuning(7, cfg)
-    for dbg in (0, 3):
-        _lib.set_tuning(9, dbg)
-        print("ring cfg %d (3 = two slots) debug=%d: %.1f us" % (cfg, dbg, timeit(lambda: layer(nat, r))), flush=True)
-_lib.set_tuning(9, 0)
-_lib.set_tuning(7, 0)
