@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/roi3d_b200.h"
 
 namespace roi3d {
@@ -102,6 +104,41 @@ __device__ __forceinline__ int roi_level(const float *roi, int num_levels, float
   if (!(t > 0.0f)) t = 0.0f;
   if (t > (float)(num_levels - 1)) t = (float)(num_levels - 1);
   return (int)t;
+}
+
+
+// cudaFuncSetAttribute (the opt-in to more than 48 KB of dynamic shared memory) is a per-DEVICE property of a kernel:
+// a process that drives several GPUs has to set it on each.  `need(bytes)` is true until `mark(bytes)` has recorded
+// at least that size for the current device (two threads racing set the attribute twice: harmless).
+struct PerDeviceSmemOptIn {
+  std::atomic<size_t> set_bytes[64] = {};
+  static int dev_index() {
+    int dev = 0;
+    return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) ? dev : -1;
+  }
+  bool need(size_t bytes) const {
+    const int d = dev_index();
+    return d < 0 || set_bytes[d].load(std::memory_order_acquire) < bytes;
+  }
+  void mark(size_t bytes) {
+    const int d = dev_index();
+    if (d >= 0) set_bytes[d].store(bytes, std::memory_order_release);
+  }
+};
+
+
+// SM count of the current device, looked up once per device.
+inline int current_sm_count(int *out) {
+  static std::atomic<int> cached[64] = {};
+  int dev = 0;
+  ROI3D_CUDA(cudaGetDevice(&dev));
+  int n = (dev >= 0 && dev < 64) ? cached[dev].load(std::memory_order_relaxed) : 0;
+  if (n == 0) {
+    ROI3D_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
+  }
+  *out = n;
+  return ROI3D_OK;
 }
 
 }  // namespace roi3d

@@ -1230,11 +1230,11 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
       const dim3 grid((unsigned)ceil_div_ll(maxlen, kItemsPerCta), ns);
       const dim3 grid2((unsigned)(grid.x < 8 ? grid.x : 8), ns);  // boundary passes: see topk_hist_kernel
       {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceSmemOptIn opt_in;
+        if (opt_in.need(kFirstSmemBytes)) {
           ROI3D_CUDA(cudaFuncSetAttribute(topk_first_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstSmemBytes));
           ROI3D_CUDA(cudaFuncSetAttribute(topk_first_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstSmemBytes));
-          attr_set = true;
+          opt_in.mark(kFirstSmemBytes);
         }
         if (apply_sigmoid)
           topk_first_kernel<true><<<flat_ctas, kFirstThreads, kFirstSmemBytes, st>>>(scores_dev, tab, state, hist, tickets, keys);
@@ -1281,11 +1281,11 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
       }
     }
     if (tail) {
-      static bool tail_attr = false;
-      if (!tail_attr) {
+      static PerDeviceSmemOptIn tail_opt_in;
+      if (tail_opt_in.need(kTailSmemBytes)) {
         ROI3D_CUDA(cudaFuncSetAttribute(topk_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
         ROI3D_CUDA(cudaFuncSetAttribute(topk_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
-        tail_attr = true;
+        tail_opt_in.mark(kTailSmemBytes);
       }
       if (apply_sigmoid)
         topk_tail_kernel<true><<<ns, kTailThreads, kTailSmemBytes, st>>>(

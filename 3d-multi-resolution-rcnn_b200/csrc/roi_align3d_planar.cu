@@ -49,10 +49,6 @@ __device__ __forceinline__ void cp_async16_pl(void *dst, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
                : "memory");
 }
-__device__ __forceinline__ void cp_async4_pl(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
-               : "memory");
-}
 
 // q / d for the small operands of the copy loops: magic = ceil(2^32 / d), exact while q * d < 2^32
 __device__ __forceinline__ unsigned fast_magic(unsigned d) { return d <= 1 ? 0u : 0xFFFFFFFFu / d + 1u; }
@@ -820,10 +816,10 @@ template <int P, bool CL, int PDT>
 int launch_planar_cfg(const RoiParams &p, int CG, int ngroups, long long blocks, const int *order, cudaStream_t st) {
   const int smem_floats = g_planar_smem_floats > 0 ? g_planar_smem_floats : PL_SMEM_FLOATS;
   const size_t smem = (size_t)smem_floats * sizeof(float);
-  static size_t attr_set = 0;
-  if (attr_set < smem) {
+  static PerDeviceSmemOptIn opt_in;
+  if (opt_in.need(smem)) {
     ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_fwd_planar_kernel<P, CL, PDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
+    opt_in.mark(smem);
   }
   roi_align3d_fwd_planar_kernel<P, CL, PDT><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, ngroups, smem_floats, order);
   ROI3D_LAUNCH_CHECK();
@@ -874,10 +870,10 @@ namespace {
 template <int P, int PDT>
 int launch_bwd_planar_cfg(const RoiParams &p, int CG, long long blocks, int smem_floats, const int *order, cudaStream_t st) {
   const size_t smem = (size_t)smem_floats * sizeof(float);
-  static size_t attr_set = 0;
-  if (attr_set < smem) {
+  static PerDeviceSmemOptIn opt_in;
+  if (opt_in.need(smem)) {
     ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_bwd_planar_kernel<P, PDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
+    opt_in.mark(smem);
   }
   roi_align3d_bwd_planar_kernel<P, PDT><<<(unsigned)blocks, PL_THREADS, smem, st>>>(p, CG, smem_floats, order);
   ROI3D_LAUNCH_CHECK();
@@ -891,7 +887,6 @@ int launch_bwd_planar(RoiParams &p, cudaStream_t st) {
   const int ngroups = ceil_div(p.C, CG);
   const long long blocks = (long long)p.K * ngroups;
   const int smem_floats = g_planar_smem_floats > 0 ? g_planar_smem_floats : PL_SMEM_FLOATS;
-  const size_t smem = (size_t)smem_floats * sizeof(float);
   int *order = nullptr;
   if (p.K > 1 && p.K <= 8192) {
     cudaMemPool_t pool;

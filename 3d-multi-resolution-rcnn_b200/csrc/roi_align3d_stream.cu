@@ -1237,10 +1237,10 @@ int launch_cfg(const RoiParams &p, StreamArgs &a, cudaStream_t st, int sm_count)
   roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(p, plans, counter, NC && sort && !(a.debug & 16) ? 2 : sort, SLOT, NC ? 2 * grid : 3 * grid, NC ? 1 : 0);
   ROI3D_LAUNCH_CHECK();
   a.plans = plans, a.counter = counter;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceSmemOptIn opt_in;   // (one per instantiation = per kernel)
+  if (opt_in.need(L::LAUNCH)) {
     ROI3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::LAUNCH));
-    attr_set = true;
+    opt_in.mark(L::LAUNCH);
   }
   if (g_timing_ev[0] != nullptr) ROI3D_CUDA(cudaEventRecord(g_timing_ev[0], st));   // (measurement hook, see roi3d_set_kernel_timing_events)
   {
@@ -1268,11 +1268,10 @@ int g_fwd_stream_cfg = 0;       // roi3d_set_tuning key 7: ring geometry of the 
 int g_fwd_stream_debug = 0;     // key 9: developer experiments (bit 0: owners skip the arithmetic, bit 1: no output store, bit 2: no sort, bit 4: NCDHW twin in largest-first order)
 
 int launch_fwd_stream(RoiParams &p, cudaStream_t st) {
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    ROI3D_CUDA(cudaGetDevice(&dev));
-    ROI3D_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  int sm_count = 0;
+  {
+    const int rc = current_sm_count(&sm_count);
+    if (rc) return rc;
   }
   StreamArgs a;
   a.p = p;
@@ -1306,11 +1305,10 @@ bool bwd_stream_ok(const RoiParams &p) {
 }
 
 int launch_bwd_stream(RoiParams &p, cudaStream_t st) {
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    ROI3D_CUDA(cudaGetDevice(&dev));
-    ROI3D_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  int sm_count = 0;
+  {
+    const int rc = current_sm_count(&sm_count);
+    if (rc) return rc;
   }
   StreamArgs a;
   a.p = p;
@@ -1332,10 +1330,10 @@ int launch_bwd_stream(RoiParams &p, cudaStream_t st) {
   roi_align3d_plan_kernel<<<ceil_div(p.K, 8), 256, sort ? p.K * sizeof(float) : 0, st>>>(pp, plans, counter, sort, 43008, 0, 0);
   ROI3D_LAUNCH_CHECK();
   a.plans = plans, a.counter = counter;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceSmemOptIn opt_in;
+  if (opt_in.need(SB_TOTAL)) {
     ROI3D_CUDA(cudaFuncSetAttribute(roi_align3d_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_TOTAL));
-    attr_set = true;
+    opt_in.mark(SB_TOTAL);
   }
   {
     cudaLaunchConfig_t cfg = {};

@@ -1410,3 +1410,31 @@ def test_roi_align_forward_planar_kernel(oracle, dev, case, layout, smem_floats)
         roi3d_b200._lib.set_tuning(0, 0)
         roi3d_b200._lib.set_tuning(10, 0)
     assert out.is_contiguous() and rel_err(out.cpu().numpy(), want) <= FWD_TOL
+
+
+@pytest.mark.gpu
+def test_second_device_in_one_process(oracle):
+    """A process that drives two GPUs: the opt-in to large dynamic shared memory is a per-device kernel attribute, so
+    every large-shared-memory kernel (streamed forward / backward, NCDHW twin, planar, NMS sweep, top-k) has to be set
+    up on each device it runs on.  Skipped on a single-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from roi3d_b200.ops import RoIAlign3D, nms
+    f = _feats((1, 64, 10, 32, 32), 5)
+    rois = synth.c2_rois(60, seed=6, img=(128, 128, 20))
+    want = oracle.roi_align3d_forward(f, rois, 7, 7, 0.25, 0.5, 2)
+    want14 = oracle.roi_align3d_forward(f, rois, 14, 14, 0.25, 0.5, 2)
+    dets = synth.c1_boxes(700, seed=3)
+    keep_want = oracle.nms3d(dets, 0.5)
+    for d in (0, 1):
+        dv = torch.device("cuda:%d" % d)
+        rt = torch.from_numpy(rois).to(dv)
+        x = cl(torch.from_numpy(f).to(dv)).requires_grad_(True)
+        out = RoIAlign3D(7, 7, 0.25, 0.5, 2)(x, rt)
+        assert rel_err(out.detach().cpu().numpy(), want) <= FWD_TOL
+        out.backward(torch.ones_like(out))
+        assert torch.isfinite(x.grad).all()
+        assert rel_err(RoIAlign3D(7, 7, 0.25, 0.5, 2)(torch.from_numpy(f).to(dv), rt).cpu().numpy(), want) <= FWD_TOL
+        assert rel_err(RoIAlign3D(14, 14, 0.25, 0.5, 2)(cl(torch.from_numpy(f).to(dv)), rt).cpu().numpy(), want14) <= FWD_TOL
+        _, inds = nms(torch.from_numpy(dets).to(dv), 0.5)
+        assert np.array_equal(inds.cpu().numpy(), keep_want)
