@@ -165,8 +165,21 @@ __global__ void __launch_bounds__(256) nms3d_mask_kernel(const SortedBox *__rest
   const int csize = min(64, n - cblk * 64);
   const int start = (cblk == rb) ? rl + 1 : 0;
   unsigned long long t = 0;
-  for (int j = start; j < csize; ++j) {
-    if (F64 ? iou3d_f64_suppresses(a, cols[cq][j], thr64) : iou3d_gt(a, Sa, cols[cq][j], thr)) t |= 1ULL << j;
+  if (start == 0 && csize == 64) {
+    // full off-diagonal tile (most of them): bits are collected eight at a time at compile-time positions -- one
+    // predicated OR per pair instead of a 64-bit variable shift, two selects and two ORs
+#pragma unroll 1
+    for (int jb = 0; jb < 64; jb += 8) {
+      unsigned byte = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (F64 ? iou3d_f64_suppresses(a, cols[cq][jb + u], thr64) : iou3d_gt(a, Sa, cols[cq][jb + u], thr)) byte |= 1u << u;
+      t |= (unsigned long long)byte << jb;
+    }
+  } else {
+    for (int j = start; j < csize; ++j) {
+      if (F64 ? iou3d_f64_suppresses(a, cols[cq][j], thr64) : iou3d_gt(a, Sa, cols[cq][j], thr)) t |= 1ULL << j;
+    }
   }
   mask[((long long)seg * n_max + row) * cbm + cblk] = t;
 }
