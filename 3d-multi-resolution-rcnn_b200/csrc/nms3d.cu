@@ -212,8 +212,15 @@ __global__ void __launch_bounds__(256) nms3d_mask_q_kernel(const SortedBox *__re
     const float Sa = __fmul_rn(a.sxy, a.sz);
     const int csize = min(64, n - cblk * 64);
     const int j0 = max(q * 16, (cblk == rb) ? rl + 1 : 0), j1 = min(q * 16 + 16, csize);
-    for (int j = j0; j < j1; ++j)
-      if (F64 ? iou3d_f64_suppresses(a, cols[j], thr64) : iou3d_gt(a, Sa, cols[j], thr)) t |= 1u << (j - q * 16);
+    if (j0 == q * 16 && j1 == q * 16 + 16) {   // a full quarter: compile-time bit positions (see nms3d_mask_kernel)
+      const SortedBox *cq16 = cols + q * 16;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (F64 ? iou3d_f64_suppresses(a, cq16[u], thr64) : iou3d_gt(a, Sa, cq16[u], thr)) t |= 1u << u;
+    } else {
+      for (int j = j0; j < j1; ++j)
+        if (F64 ? iou3d_f64_suppresses(a, cols[j], thr64) : iou3d_gt(a, Sa, cols[j], thr)) t |= 1u << (j - q * 16);
+    }
   }
   part[q][rl] = t;
   __syncthreads();

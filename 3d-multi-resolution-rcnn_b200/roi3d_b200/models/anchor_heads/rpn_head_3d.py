@@ -173,7 +173,6 @@ class RPNProposal3D(object):
         if not self.cuda_graph:
             with nvtx_range("roi3d.rpn.get_bboxes"):
                 final, n_valid, kk = self._enqueue(cls_scores, bbox_preds, img_metas, cfg)
-            clone = False
         else:
             masks_now = [m for lst in (self.pos_indices, self.pos_indices_test) if lst is not None for m in lst]
             key = (tuple(t.data_ptr() for t in list(cls_scores) + list(bbox_preds) + masks_now),
@@ -194,9 +193,11 @@ class RPNProposal3D(object):
                 entry = self._graphs[key] = (graph, outs, list(cls_scores) + list(bbox_preds))
             entry[0].replay()
             final, n_valid, kk = entry[1]
-            clone = True  # the graph's output buffer is overwritten by the next replay
-        n_out = n_valid.clamp(max=kk).tolist()  # the single host read of the whole path
-        return [final[b, :n_out[b]].clone() if clone else final[b, :n_out[b]] for b in range(len(n_out))]
+            # the graph's output buffer is overwritten by the next replay: ONE copy of the whole block, queued before
+            # the host read below (a clone per image after it costs a launch + an idle gap each)
+            final = final.clone()
+        n_out = [min(int(v), kk) for v in n_valid.tolist()]  # the single host read of the whole path
+        return [final[b, :n_out[b]] for b in range(len(n_out))]
 
     def _enqueue(self, cls_scores, bbox_preds, img_metas, cfg):
         """cls_scores[l]: [B, A, D, H, W]; bbox_preds[l]: [B, 6A, D, H, W]; img_metas[b]['img_shape'] = (H, W, 3, D).
