@@ -51,40 +51,54 @@ def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False, smal
     report=True additionally returns (count int32 [nseg], sorted uint8 [nseg]): rows returned per segment and whether
     they are in score order (1) or in ascending index order (0) -- device tensors, no host read.
     """
-    nseg = len(scores_list)
-    dev = scores_list[0].device
     segs = []
     for s in scores_list:
         check_cuda_f32(s, "scores")
         segs.append(s if s.is_contiguous() else s.contiguous())
-    base = min(s.data_ptr() for s in segs)
-    off = np.array([(s.data_ptr() - base) // 4 for s in segs], dtype=np.int64)
-    ln = np.array([s.numel() for s in segs], dtype=np.int64)
-    if permute_adhw:
-        adhw = np.array([list(s.shape[-4:]) for s in segs], dtype=np.int32)
+    ptrs = [s.data_ptr() for s in segs]
+    lens = [s.numel() for s in segs]
+    adhw = [list(s.shape[-4:]) for s in segs] if permute_adhw else None
+    mask_ptrs, keep = None, []
+    if masks is not None and any(m is not None for m in masks):
+        mask_ptrs = []
+        for m, sc in zip(masks, segs):
+            if m is None:
+                mask_ptrs.append(None)
+                continue
+            m = _check_mask(m, sc.numel())
+            keep.append(m)
+            mask_ptrs.append(m.data_ptr())
+    out = _topk_segmented_desc(segs[0].device, ptrs, lens, adhw, k, apply_sigmoid, small_in_index_order, mask_ptrs, report)
+    del segs, keep
+    return out
+
+
+def _check_mask(m, numel):
+    if m.dtype == torch.bool:
+        m = m.view(torch.uint8)
+    if m.dtype != torch.uint8 or not m.is_cuda or m.numel() != numel:
+        raise ValueError("a top-k mask must be a uint8 / bool CUDA tensor with one entry per score")
+    return m.contiguous()
+
+
+def _topk_segmented_desc(dev, ptrs, lens, adhw, k, apply_sigmoid, small_in_index_order, mask_ptrs, report):
+    """topk_segmented on raw descriptors: device addresses, lengths and (optionally) [A, D, H, W] shapes of the segments.
+    The caller keeps the tensors behind the addresses alive until the call is enqueued."""
+    nseg = len(ptrs)
+    base = min(ptrs)
+    off = np.array([(q - base) // 4 for q in ptrs], dtype=np.int64)
+    ln = np.array(lens, dtype=np.int64)
+    if adhw is not None:
+        adhw = np.array(adhw, dtype=np.int32)
         adhw_p = adhw.ctypes.data
     else:
-        adhw, adhw_p = None, None
+        adhw_p = None
     idx = torch.empty((nseg, k), dtype=torch.int64, device=dev)
     val = torch.empty((nseg, k), dtype=torch.float32, device=dev)
     # base workspace + one u32 key per score (the first digit pass stores the keys, later passes re-read them from L2)
     nbytes = _lib.lib.roi3d_topk_workspace_bytes_keys(nseg, k, int(ln.sum()))
     _buf, ws = workspace(dev, nbytes)
-    mask_p, keep = None, []
-    if masks is not None and any(m is not None for m in masks):
-        ptrs = []
-        for m, sc in zip(masks, segs):
-            if m is None:
-                ptrs.append(None)
-                continue
-            if m.dtype == torch.bool:
-                m = m.view(torch.uint8)
-            if m.dtype != torch.uint8 or not m.is_cuda or m.numel() != sc.numel():
-                raise ValueError("a top-k mask must be a uint8 / bool CUDA tensor with one entry per score")
-            m = m.contiguous()
-            keep.append(m)
-            ptrs.append(m.data_ptr())
-        mask_p = (ctypes.c_void_p * nseg)(*ptrs)
+    mask_p = (ctypes.c_void_p * nseg)(*mask_ptrs) if mask_ptrs is not None else None
     cnt = torch.empty((nseg,), dtype=torch.int32, device=dev) if report else None
     srt = torch.empty((nseg,), dtype=torch.uint8, device=dev) if report else None
     with torch.cuda.device(dev):
@@ -92,7 +106,7 @@ def topk_segmented(scores_list, k, apply_sigmoid=False, permute_adhw=False, smal
             base, off.ctypes.data, ln.ctypes.data, adhw_p, mask_p, nseg, int(k), int(bool(apply_sigmoid)),
             int(bool(small_in_index_order)), idx.data_ptr(), val.data_ptr(), None if cnt is None else cnt.data_ptr(),
             None if srt is None else srt.data_ptr(), ws, nbytes, stream_ptr()))
-    del segs, adhw, keep, _buf
+    del _buf
     if report:
         return idx, val, cnt, srt
     return idx, val
@@ -220,27 +234,38 @@ class RPNProposal3D(object):
         dev = cls_scores[0].device
         A = self.num_anchors
 
-        # 1. top-k of sigmoid(score) per (image, level) segment, all in one pass set
-        segs, seg_meta = [], []
-        for b in range(B):
-            for l in range(L):
-                s = cls_scores[l][b].detach()
-                assert s.shape[0] == A, "cls_score channels must equal num_anchors"
-                segs.append(s)
-                seg_meta.append((b, l))
-        k = nms_pre if nms_pre > 0 else max(s.numel() for s in segs)
-        k = min(k, max(s.numel() for s in segs))
+        # 1. top-k of sigmoid(score) per (image, level) segment, all in one pass set.  Segments are described by address:
+        #    image b of level l starts b * A*D*H*W floats into the level's [B, A, D, H, W] tensor (no per-segment tensor
+        #    views: 2 x B x L torch indexing calls cost more host time than the whole GPU path)
+        cls_c, reg_c = [], []
+        for l in range(L):
+            c, r = cls_scores[l].detach(), bbox_preds[l].detach()
+            check_cuda_f32(c, "cls_score", ndim=5)
+            check_cuda_f32(r, "bbox_pred", ndim=5)
+            assert c.shape[1] == A, "cls_score channels must equal num_anchors"
+            assert c.shape[0] >= B and r.shape[0] >= B and tuple(r.shape[2:]) == tuple(c.shape[2:]) and r.shape[1] == 6 * A
+            cls_c.append(c if c.is_contiguous() else c.contiguous())
+            reg_c.append(r if r.is_contiguous() else r.contiguous())
+        lvl_numel = [int(c.shape[1] * c.shape[2] * c.shape[3] * c.shape[4]) for c in cls_c]
+        lvl_adhw = [[int(c.shape[1]), int(c.shape[2]), int(c.shape[3]), int(c.shape[4])] for c in cls_c]
+        cls_ptr = [c.data_ptr() for c in cls_c]
+        reg_ptr = [r.data_ptr() for r in reg_c]
+        seg_meta = [(b, l) for b in range(B) for l in range(L)]
+        seg_numel = [lvl_numel[l] for (_b, l) in seg_meta]
+        seg_ptrs = [cls_ptr[l] + 4 * b * lvl_numel[l] for (b, l) in seg_meta]
+        k = nms_pre if nms_pre > 0 else max(seg_numel)
+        k = min(k, max(seg_numel))
         # Small descriptor tensors go up FIRST: a pageable host-to-device copy is stream-ordered and blocks the host,
         # so issued later it would wait for every kernel already queued and serialise the CPU with the GPU.
-        counts = [min(k, s.numel()) for s in segs]
-        unsorted = [not (nms_pre > 0 and s.numel() > nms_pre) for s in segs]
+        counts = [min(k, n) for n in seg_numel]
+        unsorted = [not (nms_pre > 0 and n > nms_pre) for n in seg_numel]
         # cached inside-flag masks: only on levels that are top-k'd, only when the shape matches (rpn_head_3d.py:96-106)
-        masks = [None] * len(segs)
-        for j, ((_b, l), s) in enumerate(zip(seg_meta, segs)):
+        masks = [None] * len(seg_meta)
+        for j, (_b, l) in enumerate(seg_meta):
             if unsorted[j]:
                 continue
             for lst in (self.pos_indices, self.pos_indices_test):
-                if lst is not None and tuple(lst[l].shape) == (s.numel(),):
+                if lst is not None and tuple(lst[l].shape) == (seg_numel[j],):
                     masks[j] = lst[l]
                     break
         masked = any(m is not None for m in masks)
@@ -259,30 +284,37 @@ class RPNProposal3D(object):
         # (nms returns ascending input indices, nms_kernel.cu:253-256).  The top-k returns such segments whole in
         # ascending anchor order, and step 4 truncates them by original index instead of by score.
         # (nms_pre <= 0: no level is sorted, every level comes back whole in anchor order)
+        seg_adhw = [lvl_adhw[l] for (_b, l) in seg_meta]
         if masked:  # the masked-in count decides, on the device, how many rows a level returns and whether it was sorted
-            idx, val, seg_counts, presorted = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True,
-                                                             small_in_index_order=True, masks=masks, report=True)
+            mask_keep = [None if m is None else _check_mask(m, seg_numel[j]) for j, m in enumerate(masks)]
+            idx, val, seg_counts, presorted = _topk_segmented_desc(
+                dev, seg_ptrs, seg_numel, seg_adhw, k, True, True, [None if m is None else m.data_ptr() for m in mask_keep], True)
             use_idx = 1 - presorted
+            del mask_keep
         else:
-            idx, val = topk_segmented(segs, k, apply_sigmoid=True, permute_adhw=True, small_in_index_order=True)
+            idx, val = _topk_segmented_desc(dev, seg_ptrs, seg_numel, seg_adhw, k, True, True, None, False)
 
         # 2. decode the selected anchors of every segment in ONE launch (anchors recomputed in closed form)
         dets = torch.empty((B * L, k, 7), dtype=torch.float32, device=dev)
-        preds = [bbox_preds[l][b].detach() for (b, l) in seg_meta]
-        preds = [t if t.is_contiguous() else t.contiguous() for t in preds]
-        for t in preds:
-            check_cuda_f32(t, "bbox_pred", ndim=4)
-        ptrs = (ctypes.c_void_p * len(preds))(*[t.data_ptr() for t in preds])
-        adhw = np.array([[A] + list(t.shape[1:]) for t in preds], dtype=np.int32)
-        lvl = np.array([l for (_b, l) in seg_meta], dtype=np.int32)
-        img = np.array([[img_metas[b]['img_shape'][0], img_metas[b]['img_shape'][1], img_metas[b]['img_shape'][3]]
-                        for (b, _l) in seg_meta], dtype=np.float32)
-        base = np.ascontiguousarray(np.stack([g.base_anchors.numpy() for g in self.anchor_generators[:L]]),
-                                    dtype=np.float32)
-        strides = np.asarray(self.anchor_strides[:L], dtype=np.float32)
-        dstrides = np.asarray(self.anchor_strides_depth[:L], dtype=np.float32)
-        means = np.asarray(self.target_means, dtype=np.float32)
-        stds = np.asarray(self.target_stds, dtype=np.float32)
+        ptrs = (ctypes.c_void_p * len(seg_meta))(*[reg_ptr[l] + 4 * b * 6 * lvl_numel[l] for (b, l) in seg_meta])
+        # host-side descriptors of the decode call depend on the level shapes, the image shapes and the head's constants only
+        hkey = ("decode", B, tuple(tuple(a) for a in lvl_adhw), tuple(tuple(m['img_shape']) for m in img_metas[:B]))
+        host = self._desc_cache.get(hkey)
+        if host is None:
+            host = (np.array(seg_adhw, dtype=np.int32),
+                    np.array([l for (_b, l) in seg_meta], dtype=np.int32),
+                    np.array([[img_metas[b]['img_shape'][0], img_metas[b]['img_shape'][1], img_metas[b]['img_shape'][3]]
+                              for (b, _l) in seg_meta], dtype=np.float32),
+                    np.ascontiguousarray(np.stack([g.base_anchors.numpy() for g in self.anchor_generators[:L]]),
+                                         dtype=np.float32),
+                    np.asarray(self.anchor_strides[:L], dtype=np.float32),
+                    np.asarray(self.anchor_strides_depth[:L], dtype=np.float32),
+                    np.asarray(self.target_means, dtype=np.float32),
+                    np.asarray(self.target_stds, dtype=np.float32))
+            if len(self._desc_cache) > 16:
+                self._desc_cache.clear()
+            self._desc_cache[hkey] = host
+        adhw, lvl, img, base, strides, dstrides, means, stds = host
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.roi3d_decode_proposals_batched(
                 ptrs, adhw.ctypes.data, lvl.ctypes.data, img.ctypes.data, B * L, L, A, base.ctypes.data,
