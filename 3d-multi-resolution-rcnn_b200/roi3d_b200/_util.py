@@ -10,6 +10,25 @@ from . import _lib
 NVTX = os.environ.get("ROI3D_NVTX", "0") not in ("", "0")
 
 
+class device_guard(object):
+    """`with device_guard(dev):` -- torch.cuda.device(dev), but free when `dev` already is the current device (the
+    common case: one process per GPU)."""
+
+    def __init__(self, dev):
+        idx = dev.index if isinstance(dev, torch.device) else int(dev)
+        self.ctx = None if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
+
+
 class nvtx_range(object):
     """`with nvtx_range("roi3d.nms"):` -- a named range in Nsight timelines when ROI3D_NVTX=1, free otherwise."""
 

@@ -18,7 +18,10 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ..._util import check_cuda_f32, nvtx_range, stream_ptr, workspace
+from ..._util import check_cuda_f32, device_guard, nvtx_range, stream_ptr, workspace
+
+
+_WS_BYTES = {}   # (nseg, n_max) -> workspace size (a ctypes round trip per call otherwise)
 
 
 def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=None):
@@ -40,9 +43,13 @@ def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=No
     if seg_counts is not None:
         assert seg_counts.dtype == torch.int32 and seg_counts.is_cuda and seg_counts.numel() == nseg
         seg_counts = seg_counts.contiguous()
-    nbytes = _lib.lib.roi3d_nms3d_workspace_bytes(nseg, n_max)
+    nbytes = _WS_BYTES.get((nseg, n_max))
+    if nbytes is None:
+        if len(_WS_BYTES) > 256:
+            _WS_BYTES.clear()
+        nbytes = _WS_BYTES[(nseg, n_max)] = _lib.lib.roi3d_nms3d_workspace_bytes(nseg, n_max)
     _buf, ws = workspace(dev, nbytes)
-    with torch.cuda.device(dev), nvtx_range("roi3d.nms3d_batched"):
+    with device_guard(dev), nvtx_range("roi3d.nms3d_batched"):
         _lib.check(_lib.lib.roi3d_nms3d_batched_presorted(
             dets.data_ptr(), None if seg_counts is None else seg_counts.data_ptr(),
             None if presorted is None else presorted.data_ptr(), nseg, n_max, float(iou_thr),
