@@ -102,11 +102,14 @@ __global__ void __launch_bounds__(256) bbox_overlaps3d_kernel(const float *__res
 __global__ void __launch_bounds__(256) assign_pass1_kernel(const float *__restrict__ boxes, int n, int stride,
                                                            const float *__restrict__ gt, int k,
                                                            float *__restrict__ max_overlaps, int32_t *__restrict__ argmax,
-                                                           unsigned *__restrict__ gt_max_key) {
+                                                           unsigned *__restrict__ gt_max_key,
+                                                           const uint8_t *__restrict__ ignore) {
   __shared__ GtBox sg[kGtTile];
   __shared__ unsigned smax[kGtTile];
   const int j = blockIdx.x * 256 + threadIdx.x;
   const bool live = j < n;
+  // a box inside an ignore region: its whole column of the overlap matrix reads -1 (max_iou_assigner.py:111)
+  const bool ign = ignore != nullptr && live && __ldg(ignore + j) != 0;
   float c[6] = {0, 0, 0, 0, 0, 0};
   if (live) {
 #pragma unroll
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(256) assign_pass1_kernel(const float *__restri
     for (int i = threadIdx.x; i < tk; i += 256) smax[i] = 0u;
     __syncthreads();
     for (int i = 0; i < tk; ++i) {
-      const float v = live ? iou3d_torch(sg[i], c, area) : 0.0f;
+      const float v = live ? (ign ? -1.0f : iou3d_torch(sg[i], c, area)) : 0.0f;
       // torch.max propagates NaN: the first NaN wins and stays
       if (!best_nan) {
         if (v != v) best = v, besti = t0 + i, best_nan = true;
@@ -154,11 +157,13 @@ __global__ void __launch_bounds__(256) assign_pass2_kernel(const float *__restri
                                                            const int32_t *__restrict__ argmax,
                                                            const unsigned *__restrict__ gt_max_key, float pos_thr,
                                                            float neg_lo, float neg_hi, float min_pos_iou, int assign_all,
-                                                           int64_t *__restrict__ assigned, int32_t *__restrict__ gt_argmax) {
+                                                           int64_t *__restrict__ assigned, int32_t *__restrict__ gt_argmax,
+                                                           const uint8_t *__restrict__ ignore) {
   __shared__ GtBox sg[kGtTile];
   __shared__ float sgmax[kGtTile];
   const int j = blockIdx.x * 256 + threadIdx.x;
   const bool live = j < n;
+  const bool ign = ignore != nullptr && live && __ldg(ignore + j) != 0;
   float c[6] = {0, 0, 0, 0, 0, 0};
   if (live) {
 #pragma unroll
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(256) assign_pass2_kernel(const float *__restri
       // this box's IoU with gt i cannot exceed its own row maximum: nothing to recompute when that is below gm
       // (a NaN row maximum compares false and falls through to the exact test)
       if (my_max < gm) continue;
-      if (iou3d_torch(sg[i], c, area) == gm) {
+      if ((ign ? -1.0f : iou3d_torch(sg[i], c, area)) == gm) {
         if (assign_all) a = t0 + i + 1;
         else atomicMin(gt_argmax + t0 + i, j);
       }
@@ -345,6 +350,16 @@ int roi3d_assign_max_iou(const float *bboxes_dev, int n, int stride, const float
                          float min_pos_iou, int gt_max_assign_all, int64_t *assigned_gt_inds_dev,
                          float *max_overlaps_dev, int64_t *assigned_labels_dev, void *workspace_dev,
                          size_t workspace_bytes, void *stream) {
+  return roi3d_assign_max_iou_ignore(bboxes_dev, n, stride, gt_dev, k, gt_labels_dev, nullptr, pos_iou_thr, neg_iou_lo,
+                                     neg_iou_hi, min_pos_iou, gt_max_assign_all, assigned_gt_inds_dev, max_overlaps_dev,
+                                     assigned_labels_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int roi3d_assign_max_iou_ignore(const float *bboxes_dev, int n, int stride, const float *gt_dev, int k,
+                                const int64_t *gt_labels_dev, const uint8_t *ignore_flags_dev, float pos_iou_thr,
+                                float neg_iou_lo, float neg_iou_hi, float min_pos_iou, int gt_max_assign_all,
+                                int64_t *assigned_gt_inds_dev, float *max_overlaps_dev, int64_t *assigned_labels_dev,
+                                void *workspace_dev, size_t workspace_bytes, void *stream) {
   ROI3D_CHECK_ARG(n > 0 && k > 0, "No gt or bboxes (n=%d, k=%d)", n, k);  // the reference raises ValueError
   ROI3D_CHECK_ARG(stride >= 6, "bboxes need at least 6 columns");
   ROI3D_CHECK_ARG(bboxes_dev && gt_dev && assigned_gt_inds_dev && max_overlaps_dev && workspace_dev, "NULL pointer");
@@ -362,11 +377,12 @@ int roi3d_assign_max_iou(const float *bboxes_dev, int n, int stride, const float
   ROI3D_CUDA(cudaMemsetAsync(gt_max_key, 0, sizeof(unsigned) * (size_t)k, st));
   ROI3D_CUDA(cudaMemsetAsync(gt_argmax, 0x7f, sizeof(int32_t) * (size_t)k, st));  // 0x7f7f7f7f > any index
   const int blocks = ceil_div(n, 256);
-  assign_pass1_kernel<<<blocks, 256, 0, st>>>(bboxes_dev, n, stride, gt_dev, k, max_overlaps_dev, argmax, gt_max_key);
+  assign_pass1_kernel<<<blocks, 256, 0, st>>>(bboxes_dev, n, stride, gt_dev, k, max_overlaps_dev, argmax, gt_max_key,
+                                              ignore_flags_dev);
   ROI3D_LAUNCH_CHECK();
   assign_pass2_kernel<<<blocks, 256, 0, st>>>(bboxes_dev, n, stride, gt_dev, k, max_overlaps_dev, argmax, gt_max_key,
                                               pos_iou_thr, neg_iou_lo, neg_iou_hi, min_pos_iou, gt_max_assign_all,
-                                              assigned_gt_inds_dev, gt_argmax);
+                                              assigned_gt_inds_dev, gt_argmax, ignore_flags_dev);
   ROI3D_LAUNCH_CHECK();
   if (!gt_max_assign_all) {
     assign_pass3_kernel<<<1, 32, 0, st>>>(gt_argmax, k, n, assigned_gt_inds_dev);

@@ -69,6 +69,8 @@ def _load():
         "roi3d_assign_workspace_bytes": (c_size_t, [c_int, c_int]),
         "roi3d_assign_max_iou": (c_int, [P, c_int, c_int, P, c_int, P, c_float, c_float, c_float, c_float, c_int, P, P, P,
                                          P, c_size_t, P]),
+        "roi3d_assign_max_iou_ignore": (c_int, [P, c_int, c_int, P, c_int, P, P, c_float, c_float, c_float, c_float, c_int,
+                                                P, P, P, P, c_size_t, P]),
         "roi3d_bbox2delta3d": (c_int, [P, c_int, P, c_int, c_int, P, P, P, P]),
         "roi3d_delta2bbox3d": (c_int, [P, c_int, P, c_int, c_int, P, P, c_float, c_float, c_float, c_float, P, P]),
         "roi3d_topk_workspace_bytes": (c_size_t, [c_int, c_int]),

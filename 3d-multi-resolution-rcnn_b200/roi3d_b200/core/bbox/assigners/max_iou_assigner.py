@@ -30,9 +30,7 @@ class MaxIoUAssigner(object):
             gt_labels = gt_labels[0]
         if bboxes.shape[0] == 0 or gt_bboxes.shape[0] == 0:
             raise ValueError('No gt or bboxes')
-        if (self.ignore_iof_thr > 0) and (gt_bboxes_ignore is not None) and (gt_bboxes_ignore.numel() > 0):
-            raise NotImplementedError("ignore regions (ignore_iof_thr > 0) are not on the 3D path: the config sets "
-                                      "ignore_iof_thr=-1")
+        use_ignore = (self.ignore_iof_thr > 0) and (gt_bboxes_ignore is not None) and (gt_bboxes_ignore.numel() > 0)
         check_cuda_f32(bboxes, "bboxes", ndim=2)
         check_cuda_f32(gt_bboxes, "gt_bboxes", ndim=2)
         if bboxes.shape[1] < 6 or gt_bboxes.shape[1] < 6:
@@ -56,11 +54,24 @@ class MaxIoUAssigner(object):
             gl = gt_labels.to(device=dev, dtype=torch.long).contiguous()
             labels = torch.empty((n,), dtype=torch.long, device=dev)
             lab_ptr, gl_ptr = labels.data_ptr(), gl.data_ptr()
+        ign = None
+        if use_ignore:
+            # max_iou_assigner.py:101-111.  For 6-column boxes the reference's bbox_overlaps never looks at mode='iof'
+            # (geometry.py:49-60): the "iof" against the ignore regions is the plain IoU, in either orientation.
+            from ..geometry import bbox_overlaps
+            check_cuda_f32(gt_bboxes_ignore, "gt_bboxes_ignore", ndim=2)
+            gi = gt_bboxes_ignore.detach()[:, :6].contiguous()
+            b6 = b[:, :6]
+            if self.ignore_wrt_candidates:
+                ign_max = bbox_overlaps(b6, gi, mode='iof').max(dim=1)[0]
+            else:
+                ign_max = bbox_overlaps(gi, b6, mode='iof').max(dim=0)[0]
+            ign = (ign_max > self.ignore_iof_thr).to(torch.uint8).contiguous()
         nbytes = _lib.lib.roi3d_assign_workspace_bytes(n, k)
         _buf, ws = workspace(dev, nbytes)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib.roi3d_assign_max_iou(
-                b.data_ptr(), n, b.shape[1], g.data_ptr(), k, gl_ptr, float(self.pos_iou_thr), neg_lo, neg_hi,
-                float(self.min_pos_iou), 1 if self.gt_max_assign_all else 0, gt_inds.data_ptr(),
-                max_overlaps.data_ptr(), lab_ptr, ws, nbytes, stream_ptr()))
+            _lib.check(_lib.lib.roi3d_assign_max_iou_ignore(
+                b.data_ptr(), n, b.shape[1], g.data_ptr(), k, gl_ptr, None if ign is None else ign.data_ptr(),
+                float(self.pos_iou_thr), neg_lo, neg_hi, float(self.min_pos_iou), 1 if self.gt_max_assign_all else 0,
+                gt_inds.data_ptr(), max_overlaps.data_ptr(), lab_ptr, ws, nbytes, stream_ptr()))
         return AssignResult(k, gt_inds, max_overlaps, labels=labels)

@@ -8,9 +8,12 @@ from ..._util import check_cuda_f32, stream_ptr
 
 def bbox_overlaps(bboxes1, bboxes2, mode='iou', is_aligned=False):
     """bboxes1 [m, >=6], bboxes2 [n, >=6] fp32 CUDA (x1,y1,x2,y2,z1,z2,...) -> ious [m, n]."""
-    if mode != 'iou' or is_aligned:
-        raise NotImplementedError("only mode='iou', is_aligned=False is on the 3D path (the reference's aligned branch "
-                                  "stops in a debugger, geometry.py:33)")
+    assert mode in ['iou', 'iof']
+    # mode='iof': the reference's 6-column branch never looks at `mode` (geometry.py:49-60 divide by the union whatever
+    # it says), so 'iof' returns the IoU here as it does there
+    if is_aligned:
+        raise NotImplementedError("is_aligned=True is not on the 3D path (the reference's aligned branch stops in a "
+                                  "debugger, geometry.py:33)")
     check_cuda_f32(bboxes1, "bboxes1", ndim=2)
     check_cuda_f32(bboxes2, "bboxes2", ndim=2)
     if bboxes1.shape[1] < 6 or bboxes2.shape[1] < 6:

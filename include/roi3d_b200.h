@@ -179,7 +179,12 @@ int roi3d_nms3d_host(const float *dets_host, int n, float iou_thr, int64_t *keep
  *   gt_max[i] >= min_pos_iou: i + 1 for every box whose IoU equals gt_max[i] (gt_max_assign_all) or for the
  *   lowest-index such box.  Ties of the per-box argmax go to the lowest gt index.  assigned_labels_dev (optional)
  *   = gt_labels[assigned - 1] for positives, 0 otherwise.  n == 0 or k == 0 is an error like the reference's
- *   ValueError.  The ignore-region branch (ignore_iof_thr > 0) is not implemented (unused by the config).
+ *   ValueError.
+ * roi3d_assign_max_iou_ignore: the same with the ignore-region branch (max_iou_assigner.py:101-111): boxes whose
+ *   ignore_flags_dev byte is non-zero have their whole column of the overlap matrix read -1, so they stay -1
+ *   ("ignore") unless they attain a gt's maximum of -1.  The caller derives the flags from
+ *   roi3d_bbox_overlaps3d(bboxes, gt_bboxes_ignore) > ignore_iof_thr -- for 6-column boxes the reference's
+ *   bbox_overlaps ignores mode='iof' and returns the IoU (geometry.py:49-60).  NULL flags = the plain entry.
  * roi3d_bbox2delta3d: bbox2delta3d, mmdet/core/bbox/transforms.py:33-63; deltas [n, 6] = (dx, dy, dw, dh, dz, dd);
  *   means6 / stds6 are HOST pointers to six floats (NULL = 0 / 1).
  * ---------------------------------------------------------------------------------------------- */
@@ -200,6 +205,11 @@ int roi3d_assign_max_iou(const float *bboxes_dev, int n, int stride, const float
                          float min_pos_iou, int gt_max_assign_all, int64_t *assigned_gt_inds_dev,
                          float *max_overlaps_dev, int64_t *assigned_labels_dev, void *workspace_dev,
                          size_t workspace_bytes, void *stream);
+int roi3d_assign_max_iou_ignore(const float *bboxes_dev, int n, int stride, const float *gt_dev, int k,
+                                const int64_t *gt_labels_dev, const uint8_t *ignore_flags_dev, float pos_iou_thr,
+                                float neg_iou_lo, float neg_iou_hi, float min_pos_iou, int gt_max_assign_all,
+                                int64_t *assigned_gt_inds_dev, float *max_overlaps_dev, int64_t *assigned_labels_dev,
+                                void *workspace_dev, size_t workspace_bytes, void *stream);
 int roi3d_bbox2delta3d(const float *proposals_dev, int stride_p, const float *gt_dev, int stride_g, int n,
                        const float *means6, const float *stds6, float *deltas_dev, void *stream);
 /* delta2bbox3D for class-wise deltas (the bbox head's decode; mmdet/core/bbox/transforms.py:105-160): deltas [n, 6k]

@@ -999,6 +999,36 @@ def test_max_iou_assigner_matches_oracle(oracle, dev, cfg, shape):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("wrt_candidates", [True, False])
+@pytest.mark.parametrize("assign_all", [True, False])
+def test_max_iou_assigner_ignore_regions(oracle, dev, wrt_candidates, assign_all):
+    """The ignore-region branch (max_iou_assigner.py:101-111): boxes whose overlap with an ignore box exceeds
+    ignore_iof_thr read -1 against every gt and stay "don't care" -- also when they would have been a gt's best box."""
+    from roi3d_b200.core.bbox import MaxIoUAssigner
+    n, k = 5000, 9
+    boxes, gt = _assign_case(n, k, 31)
+    labels = (np.arange(k) % 3 + 1).astype(np.int64)
+    rng = np.random.default_rng(5)
+    # ignore regions: two copies of gt boxes (so that some would-be positives are ignored) and two random boxes
+    extra = boxes[rng.choice(n, 2, replace=False), :6] + np.float32(1.0)
+    ign = np.concatenate([gt[[1, 4], :6], extra], 0).astype(np.float32)
+    cfg = dict(pos_iou_thr=0.5, neg_iou_thr=0.3, min_pos_iou=0.2, gt_max_assign_all=assign_all, ignore_iof_thr=0.4,
+               ignore_wrt_candidates=wrt_candidates)
+    want_a, want_mo, want_l = oracle.assign_max_iou(boxes, gt, labels, gt_bboxes_ignore=ign, **cfg)
+    plain_a, _, _ = oracle.assign_max_iou(boxes, gt, labels, **{**cfg, 'ignore_iof_thr': -1})
+    assert (want_a != plain_a).sum() > 0 and (want_mo == -1).sum() > 0   # the branch changes something here
+    res = MaxIoUAssigner(**cfg).assign(torch.from_numpy(boxes).to(dev), torch.from_numpy(gt).to(dev),
+                                       gt_bboxes_ignore=torch.from_numpy(ign).to(dev), gt_labels=torch.from_numpy(labels).to(dev))
+    assert np.array_equal(res.max_overlaps.cpu().numpy(), want_mo)
+    assert np.array_equal(res.gt_inds.cpu().numpy(), want_a)
+    assert np.array_equal(res.labels.cpu().numpy(), want_l)
+    # an empty ignore list, or ignore_iof_thr <= 0, is the plain assigner
+    res0 = MaxIoUAssigner(**cfg).assign(torch.from_numpy(boxes).to(dev), torch.from_numpy(gt).to(dev),
+                                        gt_bboxes_ignore=torch.zeros(0, 6, device=dev))
+    assert np.array_equal(res0.gt_inds.cpu().numpy(), plain_a)
+
+
+@pytest.mark.gpu
 def test_max_iou_assigner_errors_like_reference(dev):
     from roi3d_b200.core.bbox import MaxIoUAssigner
     a = MaxIoUAssigner(0.5, 0.5)
