@@ -515,6 +515,33 @@ def secondary_rows(torch, dev, feats, feats_cl, rois, layer, nms3d_batched, fwd_
         return float(np.median(ts))
 
     ex = {}
+    # the headline step (plan kernel + streamed kernel) captured once and replayed as a CUDA graph of 20 steps: what the
+    # step costs the GPU without the host's launch gaps (the headline itself is timed through eager calls)
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                layer(feats_cl, rois)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(20):
+                    gout = layer(feats_cl, rois)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ex["c2_fwd_step_cuda_graph_us"] = a.elapsed_time(b) * 1e3 / 100
+        ex["c2_fwd_step_cuda_graph_identical"] = bool(torch.equal(gout, layer(feats_cl, rois)))
+        del graph, gout
+    except Exception as e:  # measurement only: never fail the bench line over it
+        ex["c2_fwd_step_cuda_graph_error"] = repr(e)
     # C2 with the reference's NCDHW-contiguous input, as a lone call: the NCDHW twin of the streamed kernel reads the tensor
     # in place (16-byte cp.async producers); the planar kernel on the same call is timed beside it (tuning variant 60)
     us = med_us(lambda: layer(feats, rois), iters=5)
