@@ -389,8 +389,8 @@ def assign_max_iou(bboxes, gt_bboxes, gt_labels=None, pos_iou_thr=0.5, neg_iou_t
                    gt_max_assign_all=True, ignore_iof_thr=-1, ignore_wrt_candidates=True, gt_bboxes_ignore=None):
     """MaxIoUAssigner.assign + assign_wrt_overlaps (mmdet/core/bbox/assigners/max_iou_assigner.py:100-171), the
     ignore branch (:101-111) included: for 6-column boxes the reference's bbox_overlaps(..., mode='iof') is the IoU
-    (geometry.py:49-60 never reads `mode`).  Ties of max(dim) go to the lowest index (parity unpinned by the
-    reference).  Returns (assigned_gt_inds int64 [n], max_overlaps fp32 [n], labels int64 [n] or None)."""
+    (geometry.py:49-60 never reads `mode`).  Ties of max(dim) go to the lowest index.  Pinned: tests/golden/
+    assigner_ref.npz holds the outputs of the reference's own class on twelve seeded cases (test_golden.py).  Returns (assigned_gt_inds int64 [n], max_overlaps fp32 [n], labels int64 [n] or None)."""
     ov = bbox_overlaps3d(_f32(gt_bboxes)[:, :6], _f32(bboxes)[:, :6])  # [k, n]
     if ignore_iof_thr > 0 and gt_bboxes_ignore is not None and np.asarray(gt_bboxes_ignore).size > 0:
         gi = _f32(gt_bboxes_ignore)[:, :6]

@@ -51,3 +51,41 @@ def test_nms_keep_list_equals_reference_kernel(oracle, tag):
     z = _load("nms3d_ref.npz")
     got = oracle.nms3d(z["%s_dets" % tag], float(z["%s_thr" % tag]), contract=True)
     assert np.array_equal(got, z["%s_keep" % tag])
+
+
+def _assigner_cases():
+    path = os.path.join(HERE, "golden", "assigner_ref.npz")
+    return range(int(np.load(path)["num_cases"])) if os.path.exists(path) else []
+
+
+@pytest.mark.parametrize("i", list(_assigner_cases()))
+def test_assigner_equals_the_reference_assigner(oracle, i):
+    """tests/golden/assigner_ref.npz holds the outputs of the REFERENCE's MaxIoUAssigner (its own Python, CPU tensors;
+    tests/golden/make_assigner_golden.py), with and without ignore regions: the oracle restatement gives the same
+    gt_inds, max_overlaps and labels, bit for bit."""
+    z = _load("assigner_ref.npz")
+    pos, neg, mpi, assign_all, ign_thr, wrt = (float(v) for v in z["cfg_%d" % i])
+    a, mo, lab = oracle.assign_max_iou(z["boxes_%d" % i], z["gt_%d" % i], z["labels_%d" % i], pos_iou_thr=pos,
+                                       neg_iou_thr=neg, min_pos_iou=mpi, gt_max_assign_all=bool(assign_all),
+                                       ignore_iof_thr=ign_thr, ignore_wrt_candidates=bool(wrt),
+                                       gt_bboxes_ignore=z["ign_%d" % i])
+    assert np.array_equal(a, z["gt_inds_%d" % i])
+    assert np.array_equal(mo, z["max_overlaps_%d" % i])
+    assert np.array_equal(lab, z["assigned_labels_%d" % i])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", list(_assigner_cases()))
+def test_device_assigner_equals_the_reference_assigner(i):
+    """The same fixture against the product (roi3d_assign_max_iou_ignore through the MaxIoUAssigner mirror)."""
+    import torch
+    from roi3d_b200.core.bbox import MaxIoUAssigner
+    z = _load("assigner_ref.npz")
+    pos, neg, mpi, assign_all, ign_thr, wrt = (float(v) for v in z["cfg_%d" % i])
+    dev = torch.device("cuda:0")
+    res = MaxIoUAssigner(pos, neg, mpi, bool(assign_all), ign_thr, bool(wrt)).assign(
+        torch.from_numpy(z["boxes_%d" % i]).to(dev), torch.from_numpy(z["gt_%d" % i]).to(dev),
+        gt_bboxes_ignore=torch.from_numpy(z["ign_%d" % i]).to(dev), gt_labels=torch.from_numpy(z["labels_%d" % i]).to(dev))
+    assert np.array_equal(res.gt_inds.cpu().numpy(), z["gt_inds_%d" % i])
+    assert np.array_equal(res.max_overlaps.cpu().numpy(), z["max_overlaps_%d" % i])
+    assert np.array_equal(res.labels.cpu().numpy(), z["assigned_labels_%d" % i])
