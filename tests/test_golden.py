@@ -89,3 +89,131 @@ def test_device_assigner_equals_the_reference_assigner(i):
     assert np.array_equal(res.gt_inds.cpu().numpy(), z["gt_inds_%d" % i])
     assert np.array_equal(res.max_overlaps.cpu().numpy(), z["max_overlaps_%d" % i])
     assert np.array_equal(res.labels.cpu().numpy(), z["assigned_labels_%d" % i])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tests/golden/python_ref.npz: outputs of the reference's own pure-Python pieces (imported from /root/reference by
+# tests/golden/make_python_ref_golden.py and run on CPU tensors) -- pins the oracle restatements of the rows next to
+# the hot path to the reference itself.
+# ---------------------------------------------------------------------------------------------------------------
+ANCHOR_CASES = [
+    ((5, 8, 6), 8, 4, [2], [2], [1.0], (5, 7, 6), (56, 48, 3, 20), 0),
+    ((7, 9, 11), 4, 2, [2, 4], [2, 3], [0.5, 1.0, 2.0], (6, 9, 10), (36, 42, 3, 13), 3),
+    ((3, 4, 5), 16, 8, [8], [2], [1.0], (3, 4, 5), (64, 80, 3, 24), -1),
+]
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_anchor_generator_equals_the_reference_class(oracle, i):
+    z = _load("python_ref.npz")
+    fm, st, sd, scales, dscales, ratios, valid, img_shape, border = ANCHOR_CASES[i]
+    base = oracle.gen_base_anchors(st, scales, dscales, ratios, sd)
+    assert np.array_equal(base, z["anchor_base_%d" % i])
+    grid = oracle.grid_anchors(base, fm, st, sd)
+    assert np.array_equal(grid, z["anchor_grid_%d" % i])
+    v = oracle.valid_flags(fm, valid, base.shape[0])
+    assert np.array_equal(v, z["anchor_valid_%d" % i])
+    assert np.array_equal(oracle.anchor_inside_flags(grid, v, img_shape, border), z["anchor_inside_%d" % i])
+
+
+def test_bbox_transforms_equal_the_reference_functions(oracle):
+    z = _load("python_ref.npz")
+    means, stds = (0.0,) * 6, tuple(float(v) for v in z["t_stds"])
+    d = oracle.bbox2delta3d(z["t_props"], z["t_gt"], means, stds)
+    want = z["t_deltas"]
+    # dx, dy, dz: IEEE add / mul / div only -> exact; dw, dh, dd go through log (numpy's vs torch's CPU libm)
+    assert np.array_equal(d[:, [0, 1, 4]], want[:, [0, 1, 4]])
+    assert np.allclose(d[:, [2, 3, 5]], want[:, [2, 3, 5]], rtol=1e-6, atol=1e-6)   # tolerance: 1e-6
+    ms = tuple(int(v) for v in z["t_max_shape"])
+    back = oracle.delta2bbox3d(z["t_props"], z["t_rand_deltas"], means, stds, max_shape=ms)
+    assert np.abs(back - z["t_decoded"]).max() <= 1e-3                               # tolerance: 1e-3 px (exp)
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_eval_nms_equals_the_reference_function(oracle, i):
+    z = _load("python_ref.npz")
+    assert np.array_equal(oracle.nms_3d_python(z["e_dets_%d" % i], 0.1), z["e_keep_%d" % i])
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_random_sampler_equals_the_reference_class(oracle, i):
+    """Same numpy seed -> the same sampled indices as the reference's RandomSampler.sample (gt boxes prepended when
+    add_gt_as_proposals)."""
+    z = _load("python_ref.npz")
+    num, frac, ub, add_gt = z["s_cfg_%d" % i]
+    gi = z["s_gt_inds_%d" % i]
+    k = z["s_gt_%d" % i].shape[0]
+    if add_gt:
+        gi = np.concatenate([np.arange(1, k + 1), gi])
+    np.random.seed(int(z["s_seed_%d" % i]))
+    pos, neg = oracle.random_sample(gi, int(num), float(frac), float(ub))
+    assert np.array_equal(pos, z["s_pos_inds_%d" % i]) and np.array_equal(neg, z["s_neg_inds_%d" % i])
+    allb = np.concatenate([z["s_gt_%d" % i], z["s_boxes_%d" % i]]) if add_gt else z["s_boxes_%d" % i]
+    assert np.array_equal(allb[pos], z["s_pos_bboxes_%d" % i])
+    assert np.array_equal(gi[pos] - 1, z["s_pos_assigned_%d" % i])
+
+
+def test_map_roi_levels_equals_the_reference_method(oracle):
+    z = _load("python_ref.npz")
+    assert np.array_equal(oracle.map_roi_levels(z["m_rois"], 4), z["m_levels"])
+
+
+# ---- the same fixture against the product (device kernels through the Python mirror) ---------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_device_anchor_generator_equals_the_reference_class(i):
+    import torch
+    from roi3d_b200 import AnchorGenerator3D
+    z = _load("python_ref.npz")
+    fm, st, sd, scales, dscales, ratios, valid, img_shape, border = ANCHOR_CASES[i]
+    dev = torch.device("cuda:0")
+    gen = AnchorGenerator3D(st, scales, dscales, ratios, sd)
+    assert np.array_equal(gen.base_anchors.numpy(), z["anchor_base_%d" % i])
+    a, f = gen.grid_anchors_and_inside_flags(fm, st, sd, valid, img_shape, border, device=dev)
+    assert np.array_equal(a.cpu().numpy(), z["anchor_grid_%d" % i])
+    assert np.array_equal(f.cpu().numpy(), z["anchor_inside_%d" % i])
+    assert np.array_equal(gen.valid_flags(fm, valid, device=dev).cpu().numpy(), z["anchor_valid_%d" % i])
+
+
+@pytest.mark.gpu
+def test_device_eval_nms_map_levels_and_deltas_equal_the_reference():
+    import torch
+    import roi3d_b200
+    from roi3d_b200.core.bbox import bbox2delta3d
+    from roi3d_b200.core.evaluation import nms_3d_python
+    z = _load("python_ref.npz")
+    dev = torch.device("cuda:0")
+    for i in (0, 1):
+        dets = z["e_dets_%d" % i]
+        kept = nms_3d_python(np.arange(len(dets)), dets, 0.1)
+        assert np.array_equal(np.asarray(kept, dtype=np.int64), z["e_keep_%d" % i])
+    ex = roi3d_b200.SingleRoIExtractor(dict(type='RoIAlign3D', out_size=7, out_size_depth=7, sample_num=2), 64,
+                                       [4, 8, 16, 32], [2, 4, 8, 16])
+    lv = ex.map_roi_levels(torch.from_numpy(z["m_rois"]).to(dev), 4)
+    assert np.array_equal(lv.cpu().numpy(), z["m_levels"])
+    d = bbox2delta3d(torch.from_numpy(z["t_props"]).to(dev), torch.from_numpy(z["t_gt"]).to(dev), (0.0,) * 6,
+                     tuple(float(v) for v in z["t_stds"])).cpu().numpy()
+    assert np.array_equal(d[:, [0, 1, 4]], z["t_deltas"][:, [0, 1, 4]])
+    assert np.allclose(d[:, [2, 3, 5]], z["t_deltas"][:, [2, 3, 5]], rtol=1e-5, atol=1e-6)   # tolerance: 1e-5 (logf)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", [0, 1])
+def test_device_random_sampler_equals_the_reference_class(i):
+    import torch
+    from roi3d_b200.core.bbox import AssignResult, RandomSampler
+    z = _load("python_ref.npz")
+    dev = torch.device("cuda:0")
+    num, frac, ub, add_gt = z["s_cfg_%d" % i]
+    gi, labels = z["s_gt_inds_%d" % i], z["s_labels_%d" % i]
+    k = z["s_gt_%d" % i].shape[0]
+    lab = labels[np.maximum(gi, 1) - 1] * (gi > 0)
+    ar = AssignResult(k, torch.from_numpy(gi.copy()).to(dev), torch.zeros(len(gi), device=dev), labels=torch.from_numpy(lab).to(dev))
+    np.random.seed(int(z["s_seed_%d" % i]))
+    res = RandomSampler(int(num), float(frac), float(ub), bool(add_gt)).sample(
+        ar, torch.from_numpy(z["s_boxes_%d" % i].copy()).to(dev), torch.from_numpy(z["s_gt_%d" % i]).to(dev),
+        torch.from_numpy(labels).to(dev))
+    assert np.array_equal(res.pos_inds.cpu().numpy(), z["s_pos_inds_%d" % i])
+    assert np.array_equal(res.neg_inds.cpu().numpy(), z["s_neg_inds_%d" % i])
+    assert np.array_equal(res.pos_bboxes.cpu().numpy(), z["s_pos_bboxes_%d" % i])
+    assert np.array_equal(res.pos_assigned_gt_inds.cpu().numpy(), z["s_pos_assigned_%d" % i])
