@@ -15,9 +15,12 @@
 // (11/11/10 bits over the score word, 11/11/10 over the index word) find the k-th largest key exactly;
 // one collect pass appends the k keys >= it; a rank-by-counting pass sorts them.  Every (volume, level)
 // segment shares each launch; nothing syncs the host.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace roi3d {
+namespace cg = cooperative_groups;
 
 constexpr int kMaxSeg = 64;
 constexpr int kBins = 2048;
@@ -57,9 +60,13 @@ struct SegState {           // device, per segment
   int cand_count;
   int bnd_count;            // keys inside the boundary bin after the second digit pass (topk_split_kernel)
   unsigned eff_len;         // elements taking part: len, or the number of set mask bytes (known after digit pass 0)
+  float sieve_t;            // sieve path: raw-score threshold picked from a sample of the segment (topk_sample_kernel)
+  int sieve_count;          // sieve path: elements with a raw score >= sieve_t (may exceed the list's capacity)
+  int need_slow;            // 1: the digit passes run for this segment (sieve off, or its result could not be proven exact)
 };
 
 __device__ __forceinline__ unsigned okey(float s) {
+  if (s != s) return 0xFFFFFFFFu;   // NaN of either sign ranks above everything, as torch.topk has it
   s = s + 0.0f;
   unsigned u = __float_as_uint(s);
   const unsigned k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -90,6 +97,51 @@ __device__ __forceinline__ void pass_geometry(int pass, int &shift, int &bits) {
   const int sh[6] = {53, 42, 32, 21, 10, 0};
   const int bw[6] = {11, 11, 10, 11, 11, 10};
   shift = sh[pass], bits = bw[pass];
+}
+
+// Bin of h[0, kBins) (shared memory) where the descending cumulative count reaches `need` (1 <= need <= total): returns
+// the bin, leaves what is still needed inside it in `need`, and tells whether the bin holds exactly that many.  The
+// whole CTA calls it; warp 0 works: lanes sum 64 bins each (rotated, so that the 32 lanes read 32 banks), a shuffle scan
+// finds the lane that crosses, the same again over that lane's 64 bins.  Two barriers; h must not change before the next
+// barrier of the caller.
+__device__ __forceinline__ unsigned find_bin_desc(const unsigned *h, unsigned &need, bool &exact, int tid) {
+  __shared__ unsigned s_fb[3];
+  static_assert(kBins == 2048, "32 lanes x 64 bins");
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
+    unsigned sum = 0;
+#pragma unroll 16
+    for (int j = 0; j < 64; ++j) sum += h[lane * 64 + ((j + lane) & 63)];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += v;
+    }
+    const unsigned above = incl - sum;
+    const unsigned ball = __ballot_sync(0xffffffffu, above < need && above + sum >= need);
+    const int L = ball ? __ffs(ball) - 1 : 0;
+    const unsigned aboveL = __shfl_sync(0xffffffffu, above, L);
+    const unsigned c0 = h[L * 64 + 2 * lane], c1 = h[L * 64 + 2 * lane + 1];
+    const unsigned s2 = c0 + c1;
+    unsigned incl2 = s2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_down_sync(0xffffffffu, incl2, o);
+      if (lane + o < 32) incl2 += v;
+    }
+    const unsigned above2 = aboveL + incl2 - s2;
+    if (above2 < need && above2 + s2 >= need) {
+      const bool hi = above2 + c1 >= need;
+      const unsigned rem = hi ? need - above2 : need - above2 - c1;
+      s_fb[0] = (unsigned)(L * 64 + 2 * lane + (hi ? 1 : 0)), s_fb[1] = rem, s_fb[2] = (hi ? c1 : c0) == rem;
+    }
+  }
+  __syncthreads();
+  need = s_fb[1];
+  exact = s_fb[2] != 0u;
+  return s_fb[0];
 }
 
 // Pick the digit where the descending cumulative count crosses k_rem (256 threads; run by the LAST CTA of a
@@ -303,6 +355,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) topk_first_kernel(const floa
   extern __shared__ __align__(16) unsigned ftab[];   // [kBins][16]
   const int seg = flat_segment(tab, blockIdx.x);
   const SegDesc d = tab.s[seg];
+  if (!state[seg].need_slow) return;   // the sieve path already finished this segment
   const unsigned len = d.len;
   const unsigned base = (blockIdx.x - tab.cta0[seg]) * (unsigned)kFirstItemsPerCta;
   for (int i = threadIdx.x; i < kBins * 4; i += kFirstThreads) reinterpret_cast<uint4 *>(ftab)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -396,6 +449,7 @@ __global__ void __launch_bounds__(kKeyThreads) topk_second_kernel(const SegTable
   const unsigned chunk = blockIdx.x / kKeySub, sub = blockIdx.x - chunk * kKeySub;
   const int seg = flat_segment(tab, chunk);
   const SegDesc d = tab.s[seg];
+  if (!state[seg].need_slow) return;
   const unsigned top11 = (unsigned)(state[seg].prefix >> 53);
   const bool live = state[seg].k_take > 0;
   for (int i = threadIdx.x; i < kBins; i += kKeyThreads) h[i] = 0;
@@ -431,7 +485,7 @@ __global__ void __launch_bounds__(kKeyThreads) topk_split_keys_kernel(const SegT
   const unsigned chunk = blockIdx.x / kKeySub, sub = blockIdx.x - chunk * kKeySub;
   const int seg = flat_segment(tab, chunk);
   const SegDesc d = tab.s[seg];
-  if (state[seg].k_take <= 0) return;
+  if (state[seg].k_take <= 0 || !state[seg].need_slow) return;
   const unsigned p22 = (unsigned)(state[seg].prefix >> 42);  // the 22 decided bits
   const unsigned *kb = keys + d.koff;
   const unsigned base = (chunk - tab.cta0[seg]) * (unsigned)kFirstItemsPerCta + sub * (unsigned)kKeyItemsPerCta;
@@ -618,6 +672,172 @@ __global__ void __launch_bounds__(256) topk_sort_kernel(const unsigned long long
 }
 
 // k up to kBitonicMax: the tail kernel (below) finishes every segment in one launch; above it the rank-by-counting sort.
+// ------------------------------------------------------------------------------------------------
+// Sieve path (k <= kBitonicMax, no masks): ONE pass over the scores at memory speed instead of three digit passes.
+//   * topk_sample_kernel (one cluster of CTAs per long segment; also initialises the segment states) reads a jittered sample of at
+//     most kSieveSample RAW scores and picks the threshold T whose rank in the sample predicts k + kBndCap / 2
+//     elements >= T in the whole segment (capacity of the list: k + kBndCap, the slow path's two lists end to end);
+//   * topk_sieve_kernel streams the segment once: `x < T` drops an element without scoring it (no expf, no division
+//     for 99.7 % of the anchors); the others are scored exactly and appended as 64-bit keys;
+//   * the tail kernel sorts the list and PROVES the result: the list must hold at least k keys without overflowing, and
+//     the k-th score must exceed sigmoid(T) by more than the rounding slack of the fp32 sigmoid (every dropped element
+//     has x < T, hence a score below that bound) -- for raw scores: the k-th key >= key(T).  A segment that fails the
+//     proof (mass ties, saturated scores, an unlucky sample) goes through the digit passes, which are launched behind
+//     the tail and return at once for every segment that passed.
+// The result is the same bit for bit: same keys, same order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSieveSample = 32768;
+constexpr int kSieveCluster = 8;      // CTAs per segment in the sampling kernel
+constexpr int kSieveThreads = 512;    // 8 sample keys per thread, kept in registers
+
+__device__ __forceinline__ unsigned sieve_hash(unsigned i) {
+  i ^= i >> 16, i *= 0x7feb352du, i ^= i >> 15, i *= 0x846ca68bu, i ^= i >> 16;
+  return i;
+}
+
+__global__ void __cluster_dims__(kSieveCluster, 1, 1) __launch_bounds__(kSieveThreads)
+    topk_sample_kernel(const float *__restrict__ scores, const SegTable tab, SegState *__restrict__ state,
+                       int *__restrict__ tickets, int k, unsigned small_max) {
+  // One CLUSTER of kSieveCluster CTAs per segment: a single SM gathers scattered 32-byte sectors too slowly (a 32 K
+  // sample is 1 MB of them).  Every CTA keeps its share of the sample keys in registers; per digit the CTAs count into
+  // their own table, CTA r adds up bins [r * 256, r * 256 + 256) of all tables through distributed shared memory and
+  // writes the totals into every CTA's copy, and every CTA scans its copy -- two cluster barriers per digit.
+  __shared__ unsigned h[kBins], tot[kBins];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int seg = blockIdx.x / kSieveCluster, rank = (int)cluster.block_rank(), tid = threadIdx.x;
+  const SegDesc d = tab.s[seg];
+  const unsigned len = d.len;
+  if (tid == 0 && rank == 0) {
+    tickets[seg] = 0;
+    SegState st;
+    st.prefix = 0ULL;
+    st.k_take = (int)min((unsigned)k, len);
+    st.k_rem = st.k_take;
+    st.cand_count = 0, st.bnd_count = 0;
+    st.eff_len = len;
+    st.sieve_t = 0.0f, st.sieve_count = 0, st.need_slow = 1;
+    state[seg] = st;
+  }
+  if (len <= small_max) return;   // the whole cluster
+  const float *src = scores + d.off;
+  const unsigned S = min(len, (unsigned)kSieveSample), step = len / S;
+  unsigned need = (unsigned)(((unsigned long long)(k + kBndCap / 2) * S + len - 1) / len);   // rank of T in the sample
+  need = max(1u, min(need, S));
+  constexpr int PER = kSieveSample / kSieveCluster / kSieveThreads;
+  unsigned key[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const unsigned i = ((unsigned)u * kSieveCluster + rank) * kSieveThreads + tid;
+    key[u] = 0u;
+    if (i < S) key[u] = okey(__ldg(src + (size_t)i * step + (step > 1u ? sieve_hash(i) % step : 0u)));
+  }
+  unsigned prefix = 0u;
+  const int shifts[3] = {21, 10, 0};
+#pragma unroll
+  for (int dg = 0; dg < 3; ++dg) {
+    const int shift = shifts[dg];
+    const unsigned bins_mask = dg == 2 ? 0x3FFu : 0x7FFu;
+    for (int b = tid; b < kBins; b += kSieveThreads) h[b] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PER; ++u)
+      if (key[u] && (dg == 0 || (key[u] >> (shift + (dg == 2 ? 10 : 11))) == prefix)) atomicAdd(&h[(key[u] >> shift) & bins_mask], 1u);
+    cluster.sync();
+    if (tid < kBins / kSieveCluster) {
+      const int b = rank * (kBins / kSieveCluster) + tid;
+      unsigned c = 0;
+#pragma unroll
+      for (int r = 0; r < kSieveCluster; ++r) c += *cluster.map_shared_rank(h + b, r);
+#pragma unroll
+      for (int r = 0; r < kSieveCluster; ++r) *cluster.map_shared_rank(tot + b, r) = c;
+    }
+    cluster.sync();
+    bool exact;
+    const unsigned dgt = find_bin_desc(tot, need, exact, tid);
+    prefix = (prefix << (dg == 2 ? 10 : 11)) | dgt;
+  }
+  if (tid == 0 && rank == 0) state[seg].sieve_t = okey_inv(prefix);
+}
+
+constexpr int kSieveStage = 2048;   // keys a CTA stages before it reserves their slots in the list with ONE global atomic
+constexpr int kSieveBatch = kKeyItemsPerCta / kKeyThreads / 4;   // 16-byte loads per thread, all issued before the first compare
+static_assert(kSieveBatch * 4 <= 32, "one bit per element in a thread's batch");
+
+// ONE copy of the rare path in the kernel (inlined at each of the 32 compares the code outgrew the instruction cache:
+// 'no instruction' was the top stall): a thread only notes WHICH of its elements passed and walks that bit mask
+// afterwards, reading the score again (an L1 / L2 hit).
+template <bool SIGMOID>
+__global__ void __launch_bounds__(kKeyThreads) topk_sieve_kernel(const float *__restrict__ scores, const SegTable tab,
+                                                                 SegState *__restrict__ state, int k,
+                                                                 unsigned long long *__restrict__ lists) {
+  __shared__ unsigned long long stage[kSieveStage];
+  __shared__ int s_n, s_base;
+  const unsigned chunk = blockIdx.x / kKeySub, sub = blockIdx.x - chunk * kKeySub;
+  const int seg = flat_segment(tab, chunk);
+  const SegDesc d = tab.s[seg];
+  const int cap = k + kBndCap;
+  SegState *st = state + seg;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const float T = st->sieve_t;
+  unsigned long long *list = lists + (long long)seg * cap;
+  const float *src = scores + d.off;
+  const unsigned base = (chunk - tab.cta0[seg]) * (unsigned)kFirstItemsPerCta + sub * (unsigned)kKeyItemsPerCta;
+  const unsigned end = min(d.len, base + (unsigned)kKeyItemsPerCta);
+  const bool vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  // element j of the thread's batch: vec -> base + ((j / 4) * kKeyThreads + tid) * 4 + j % 4, else base + j * kKeyThreads + tid
+  unsigned mask = 0u;
+  if (vec) {
+    float4 v[kSieveBatch];
+#pragma unroll
+    for (int u = 0; u < kSieveBatch; ++u) {
+      const unsigned m = base + ((unsigned)u * kKeyThreads + threadIdx.x) * 4u;
+      v[u] = m + 4u <= end ? __ldcs(reinterpret_cast<const float4 *>(src + m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kSieveBatch; ++u) {
+      const unsigned m = base + ((unsigned)u * kKeyThreads + threadIdx.x) * 4u;
+      if (m + 4u <= end) {
+        mask |= (v[u].x < T ? 0u : 1u) << (4 * u) | (v[u].y < T ? 0u : 2u) << (4 * u) | (v[u].z < T ? 0u : 4u) << (4 * u) |
+                (v[u].w < T ? 0u : 8u) << (4 * u);
+      } else if (m < end) {
+        mask |= ((1u << (end - m)) - 1u) << (4 * u);   // the segment's last, partial vector: looked at one by one below
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < kSieveBatch * 4; ++j) {
+      const unsigned m = base + (unsigned)j * kKeyThreads + threadIdx.x;
+      if (m < end && !(__ldg(src + m) < T)) mask |= 1u << j;
+    }
+  }
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    const unsigned m = vec ? base + ((unsigned)(j >> 2) * kKeyThreads + threadIdx.x) * 4u + (unsigned)(j & 3)
+                           : base + (unsigned)j * kKeyThreads + threadIdx.x;
+    const float x = __ldg(src + m);
+    if (x < T) continue;   // NaN stays in
+    const unsigned kh = okey(SIGMOID ? sigmoid_ref(x) : x);
+    const unsigned long long key = ((unsigned long long)kh << 32) | (unsigned)~logical_index(d, m);
+    const int pos = atomicAdd(&s_n, 1);
+    if (pos < kSieveStage) {
+      stage[pos] = key;
+    } else {   // staging full (a segment of a few CTAs puts a large share of its elements on the list)
+      const int gp = atomicAdd(&st->sieve_count, 1);
+      if (gp < cap) list[gp] = key;
+    }
+  }
+  __syncthreads();
+  const int n = min(s_n, kSieveStage);
+  if (n == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(&st->sieve_count, n);
+  __syncthreads();
+  const int gb = s_base;
+  for (int i = threadIdx.x; i < n; i += kKeyThreads)
+    if (gb + i < cap) list[gb + i] = stage[i];
+}
+
 constexpr int kBitonicMax = 4096;
 
 // ------------------------------------------------------------------------------------------------
@@ -697,8 +917,6 @@ __device__ __forceinline__ unsigned long long swap_words(unsigned long long v) {
 // passes, histogram and scan in shared memory.  Stops as soon as a digit's bin holds exactly what is still needed (the
 // returned threshold then has its undecided bits clear): every key >= the result is selected, and there are `need` of them.
 __device__ __forceinline__ unsigned long long tail_select(const unsigned long long *sk, int n, int need, unsigned *h, int tid) {
-  __shared__ unsigned part[256];
-  __shared__ int s_digit, s_need, s_done;
   unsigned long long prefix = 0ULL;
   for (int pass = 0; pass < 6; ++pass) {
     int shift, bits;
@@ -711,39 +929,11 @@ __device__ __forceinline__ unsigned long long tail_select(const unsigned long lo
       if (key != 0ULL && (decided == 0 || (key >> (64 - decided)) == (prefix >> (64 - decided))))
         atomicAdd(&h[(unsigned)(key >> shift) & ((1u << bits) - 1u)], 1u);
     }
-    __syncthreads();
-    const bool act = tid < 256;   // thread t owns bins [8t, 8t + 8); descending order: high bins first
-    unsigned loc[8], sum = 0;
-    if (act) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) loc[i] = h[tid * 8 + i], sum += loc[i];
-      part[tid] = sum;
-    }
-    __syncthreads();
-    for (int o = 1; o < 256; o <<= 1) {
-      const unsigned v = (act && tid + o < 256) ? part[tid + o] : 0u;
-      __syncthreads();
-      if (act) part[tid] += v;
-      __syncthreads();
-    }
-    const unsigned above = act ? part[tid] - sum : 0u;
-    if (act && above < (unsigned)need && above + sum >= (unsigned)need) {
-      unsigned cum = above;
-      for (int i = 7; i >= 0; --i) {
-        if (cum + loc[i] >= (unsigned)need) {
-          s_digit = tid * 8 + i;
-          s_need = need - (int)cum;
-          s_done = loc[i] == (unsigned)need - cum;
-          break;
-        }
-        cum += loc[i];
-      }
-    }
-    __syncthreads();
-    prefix |= (unsigned long long)(unsigned)s_digit << shift;
-    need = s_need;
-    const int done = s_done;
-    __syncthreads();
+    unsigned nd = (unsigned)need;
+    bool done;
+    const unsigned digit = find_bin_desc(h, nd, done, tid);   // (its first barrier closes the counting above)
+    prefix |= (unsigned long long)digit << shift;
+    need = (int)nd;
     if (done) break;
   }
   return prefix;
@@ -757,18 +947,58 @@ __global__ void __launch_bounds__(kTailThreads) topk_tail_kernel(const float *__
                                                                  const unsigned *__restrict__ keys, unsigned small_max,
                                                                  int small_by_index, int64_t *__restrict__ out_idx,
                                                                  float *__restrict__ out_val, int32_t *__restrict__ out_count,
-                                                                 unsigned char *__restrict__ out_sorted) {
+                                                                 unsigned char *__restrict__ out_sorted, int phase) {
+  // phase 0: every segment, long ones through the digit passes' lists; phase 1: sieve path -- short segments and the
+  // sieve lists of the long ones (3: the same, but every long segment gives up -- tests); phase 2: behind the guarded
+  // digit passes -- only the segments the sieve gave up on
   extern __shared__ __align__(16) unsigned long long sk[];   // kSmallMax keys | kBitonicMax selected keys | kBins counters
   __shared__ int s_cnt;
   const int seg = blockIdx.x, tid = threadIdx.x;
   const SegDesc d = tab.s[seg];
+  if (phase == 2 && (d.len <= small_max || !state[seg].need_slow)) return;
   const float *src = scores + d.off;
   int n_out = 0;
   bool by_index = false;
   if (tid == 0) s_cnt = 0;
   __syncthreads();
   unsigned long long *res = sk;   // where the sorted result ends up
-  if (d.len <= small_max) {
+  if (d.len > small_max && (phase == 1 || phase == 3)) {
+    // ---- sieve path: select the k largest of the list, sort, prove that nothing outside the list can belong (see above)
+    const SegState st = state[seg];
+    const int cap = k + kBndCap, nc = st.sieve_count;
+    if (nc < k || nc > cap || phase == 3) return;   // need_slow stays 1
+    for (int i = tid; i < nc; i += kTailThreads) sk[i] = cand[(long long)seg * cap + i];
+    __syncthreads();
+    unsigned long long *sk2 = sk + kSmallMax;
+    unsigned *h = reinterpret_cast<unsigned *>(sk2 + kBitonicMax);
+    const unsigned long long thr = nc > k ? tail_select(sk, nc, k, h, tid) : 0ULL;
+    for (int i = tid; i < nc; i += kTailThreads) {
+      const unsigned long long key = sk[i];
+      if (key >= thr) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < kBitonicMax) sk2[pos] = key;
+      }
+    }
+    res = sk2, n_out = k;
+    const int np2 = pow2_at_least(k);
+    __syncthreads();
+    for (int i = k + tid; i < np2; i += kTailThreads) res[i] = 0ULL;
+    __syncthreads();
+    tail_bitonic(res, np2, tid);
+    const unsigned kth = (unsigned)(res[k - 1] >> 32);
+    bool proven;
+    if (SIGMOID) {
+      // fp32 sigmoid = true sigmoid within 1.5 * 2^-22 relative (expf 2 ulp, one add, one division) where the result is
+      // normal: a dropped x < T scores at most sigmoid_ref(T) * (1 + 2^-20); twice that slack and an absolute term for
+      // subnormal scores are asked for here
+      const double bound = (double)sigmoid_ref(st.sieve_t) * (1.0 + 1.9073486328125e-6) + 1e-37;
+      proven = (double)okey_inv(kth) > bound;   // false for NaN
+    } else {
+      proven = kth >= okey(st.sieve_t);
+    }
+    if (!proven) return;
+    if (tid == 0) state[seg].need_slow = 0;
+  } else if (d.len <= small_max) {
     // ---- small segment: score; select the k largest if there are more (radix select in shared memory); sort
     const int len = (int)d.len;
     int mine = 0;
@@ -897,6 +1127,7 @@ __global__ void topk_init_kernel(SegState *state, int *tickets, const SegTable t
   st.cand_count = 0;
   st.bnd_count = 0;
   st.eff_len = tab.s[s].len;
+  st.sieve_t = 0.0f, st.sieve_count = 0, st.need_slow = 1;
   state[s] = st;
 }
 
@@ -1115,6 +1346,8 @@ __global__ void __launch_bounds__(256) gather_rows7_kernel(const float *__restri
   for (int q = 0; q < 7; ++q) dst[q] = src[q];
 }
 
+int g_topk_sieve = 0;   // roi3d_set_tuning key 11: 0 = sieve path where it applies, -1 = digit passes only, 2 = sieve gives up (tests)
+
 }  // namespace roi3d
 
 using namespace roi3d;
@@ -1221,7 +1454,34 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
     int *tickets = reinterpret_cast<int *>(b + sizeof(SegState) * kMaxSeg);  // inside the 4 KB state block
     int32_t *cnt_out = out_count_dev ? out_count_dev + s0 : nullptr;
     uint8_t *srt_out = out_sorted_dev ? out_sorted_dev + s0 : nullptr;
-    if (maxlen > 0 || !tail) {
+    // sieve path (see topk_sample_kernel): one pass over the scores; needs the key buffer for its guarded fallback
+    bool sieve = tail && keys != nullptr && maxlen > 0 && g_topk_sieve >= 0;
+    for (int s = 0; s < ns && sieve; ++s) sieve = tab.s[s].mask == nullptr;
+    if (sieve) {
+      static PerDeviceSmemOptIn tail_opt_in;
+      if (tail_opt_in.need(kTailSmemBytes)) {
+        ROI3D_CUDA(cudaFuncSetAttribute(topk_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
+        ROI3D_CUDA(cudaFuncSetAttribute(topk_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
+        tail_opt_in.mark(kTailSmemBytes);
+      }
+      topk_sample_kernel<<<ns * kSieveCluster, kSieveThreads, 0, st>>>(scores_dev, tab, state, tickets, k, small_max);
+      ROI3D_LAUNCH_CHECK();
+      const int phase = g_topk_sieve == 2 ? 3 : 1;
+      if (apply_sigmoid) {
+        topk_sieve_kernel<true><<<flat_ctas * kKeySub, kKeyThreads, 0, st>>>(scores_dev, tab, state, k, cand);
+        ROI3D_LAUNCH_CHECK();
+        topk_tail_kernel<true><<<ns, kTailThreads, kTailSmemBytes, st>>>(
+            scores_dev, tab, state, hist, k, cand, bnd, keys, small_max, small_segments_in_index_order,
+            out_idx_dev + (size_t)s0 * k, out_val_dev + (size_t)s0 * k, cnt_out, srt_out, phase);
+      } else {
+        topk_sieve_kernel<false><<<flat_ctas * kKeySub, kKeyThreads, 0, st>>>(scores_dev, tab, state, k, cand);
+        ROI3D_LAUNCH_CHECK();
+        topk_tail_kernel<false><<<ns, kTailThreads, kTailSmemBytes, st>>>(
+            scores_dev, tab, state, hist, k, cand, bnd, keys, small_max, small_segments_in_index_order,
+            out_idx_dev + (size_t)s0 * k, out_val_dev + (size_t)s0 * k, cnt_out, srt_out, phase);
+      }
+      ROI3D_LAUNCH_CHECK();
+    } else if (maxlen > 0 || !tail) {
       topk_init_kernel<<<1, kMaxSeg, 0, st>>>(state, tickets, tab, ns, k);
       ROI3D_LAUNCH_CHECK();
     }
@@ -1290,11 +1550,11 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
       if (apply_sigmoid)
         topk_tail_kernel<true><<<ns, kTailThreads, kTailSmemBytes, st>>>(
             scores_dev, tab, state, hist, k, cand, bnd, keys, small_max, small_segments_in_index_order,
-            out_idx_dev + (size_t)s0 * k, out_val_dev + (size_t)s0 * k, cnt_out, srt_out);
+            out_idx_dev + (size_t)s0 * k, out_val_dev + (size_t)s0 * k, cnt_out, srt_out, sieve ? 2 : 0);
       else
         topk_tail_kernel<false><<<ns, kTailThreads, kTailSmemBytes, st>>>(
             scores_dev, tab, state, hist, k, cand, bnd, keys, small_max, small_segments_in_index_order,
-            out_idx_dev + (size_t)s0 * k, out_val_dev + (size_t)s0 * k, cnt_out, srt_out);
+            out_idx_dev + (size_t)s0 * k, out_val_dev + (size_t)s0 * k, cnt_out, srt_out, sieve ? 2 : 0);
       ROI3D_LAUNCH_CHECK();
       continue;
     }

@@ -1718,6 +1718,7 @@ extern int g_host_pipeline_kb;        // host_api.cu
 extern int g_fwd_stream_cfg, g_fwd_stream_debug;  // roi_align3d_stream.cu  // roi_align3d_stream.cu
 extern int g_nms_mask_variant;        // nms3d.cu
 extern int g_planar_smem_floats;      // roi_align3d_planar.cu
+extern int g_topk_sieve;              // proposal.cu
 extern thread_local cudaEvent_t g_timing_ev[2];  // roi_align3d_stream.cu
 static int g_bwd_variant = 0;
 
@@ -1968,6 +1969,7 @@ int roi3d_set_tuning(int key, int value) {
   else if (key == 7) g_fwd_stream_cfg = value;
   else if (key == 9) g_fwd_stream_debug = value;
   else if (key == 10) g_planar_smem_floats = value;
+  else if (key == 11) g_topk_sieve = value;
   else return ROI3D_EINVAL;
   return ROI3D_OK;
 }

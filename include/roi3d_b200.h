@@ -254,7 +254,8 @@ int roi3d_mask_target(const uint8_t *gt_masks_dev, int G, int D, int H, int W, c
  * roi3d_roi_align3d_forward_host pipelines its copies (0 = auto, 32 MB; -1 = never); key 6 = NMS mask kernel variant;
  * key 7 = ring geometry of the streamed forward kernel (0 = 3 x 42 KB, 1 = 4 x 32 KB, 2 = 5 x 24 KB); key 9 = streamed
  * kernel experiments (bit 0: no arithmetic, bit 1: no output store, bit 2: no largest-first order); key 10 = plane
- * storage of the planar kernels per CTA in floats (0 = 18432). */
+ * storage of the planar kernels per CTA in floats (0 = 18432); key 11 = top-k sieve path (0 = on where it applies,
+ * -1 = digit passes only, 2 = the sieve gives up on every segment so that its fallback runs -- tests). */
 int roi3d_set_tuning(int key, int value);
 
 /* Measurement hook (not part of the reference surface): two cudaEvent_t (as void*) that the calling thread's next

@@ -384,6 +384,53 @@ def test_topk_permuted_sigmoid(oracle, dev):
     assert torch.equal(idx2, idx[:3]) and torch.equal(val2, val[:3])
 
 
+@pytest.mark.parametrize("mode", [0, 2, -1])
+def test_topk_sieve_path_and_its_fallback(oracle, dev, mode):
+    """The sieve path of the segmented top-k (sample -> threshold -> one pass -> proof, csrc/proposal.cu) returns the
+    digit passes' result bit for bit: mode 0 = sieve where it applies, 2 = the sieve gives up on every long segment so
+    that the guarded digit passes behind it run, -1 = digit passes only.  Inputs include the cases where the proof
+    must fail on its own: saturated sigmoid scores (thousands of exact 1.0), constant segments, NaNs, a sorted ramp
+    (the k largest in one corner), lengths around the sample size and a segment that starts off a 16-byte boundary."""
+    import roi3d_b200
+    from roi3d_b200.models.anchor_heads import topk_segmented
+    rng = np.random.default_rng(77)
+    raw = [rng.standard_normal(n).astype(np.float32) for n in (8193, 32768, 32769, 150001, 1310720)]
+    raw.append(np.arange(200000, dtype=np.float32) / 7)                                   # ascending ramp
+    raw.append(np.full(60000, -3.0, np.float32))                                          # constant
+    raw.append(np.round(rng.standard_normal(90000) * 3).astype(np.float32))               # heavy ties
+    withnan = rng.standard_normal(50000).astype(np.float32)
+    withnan[::997] = np.nan
+    raw.append(withnan)
+    big = torch.from_numpy(np.concatenate([np.zeros(1, np.float32), raw[3]])).to(dev)
+    roi3d_b200._lib.set_tuning(11, mode)
+    try:
+        for k in (2000, 100, 4096):
+            segs = [torch.from_numpy(r).to(dev) for r in raw] + [big[1:]]                  # last: off a 16-byte boundary
+            idx, val = topk_segmented(segs, k)
+            for s, r in enumerate(raw + [raw[3]]):
+                if np.isnan(r).any():
+                    got = idx[s].cpu().numpy()
+                    nn = int(np.isnan(r).sum())
+                    assert np.isnan(r[got[:nn]]).all()                                     # NaNs lead, as in torch.topk
+                    rest = np.where(np.isnan(r), -np.inf, r)
+                    assert np.array_equal(got[nn:], oracle.topk(rest, k)[:k - nn])
+                    continue
+                want = oracle.topk(r, k)
+                assert np.array_equal(idx[s].cpu().numpy(), want), (mode, k, s)
+                assert np.array_equal(val[s].cpu().numpy(), r[want])
+        # sigmoid scores in the reference's anchor order; x 12 saturates thousands of scores to exactly 1.0
+        maps = [rng.standard_normal(sh).astype(np.float32) * sc
+                for sh, sc in (((3, 20, 32, 32), 2.0), ((3, 20, 32, 32), 12.0), ((1, 80, 128, 128), 2.0), ((1, 40, 64, 64), 30.0))]
+        idx, val = topk_segmented([torch.from_numpy(m).to(dev) for m in maps], 2000, apply_sigmoid=True, permute_adhw=True)
+        for s, m in enumerate(maps):
+            flat = torch.from_numpy(m).to(dev).permute(2, 3, 1, 0).reshape(-1).sigmoid().cpu().numpy()
+            want = oracle.topk(flat, 2000)
+            assert np.array_equal(idx[s].cpu().numpy(), want), (mode, s)
+            assert np.array_equal(val[s].cpu().numpy(), flat[want])
+    finally:
+        roi3d_b200._lib.set_tuning(11, 0)
+
+
 def test_decode_matches_oracle(oracle, dev):
     from roi3d_b200 import AnchorGenerator3D
     from roi3d_b200.models.anchor_heads import decode_proposals
