@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(kKeyThreads) topk_sieve_kernel(const float *__
     if (x < T) continue;   // NaN stays in
     const unsigned kh = okey(SIGMOID ? sigmoid_ref(x) : x);
     const unsigned long long key = ((unsigned long long)kh << 32) | (unsigned)~logical_index(d, m);
-    const int pos = atomicAdd(&s_n, 1);
+    const int pos = atomicAdd(&s_n, 1);   // (same-address shared-memory atomics are cheap: aggregating them per warp was slower)
     if (pos < kSieveStage) {
       stage[pos] = key;
     } else {   // staging full (a segment of a few CTAs puts a large share of its elements on the list)
@@ -903,8 +903,46 @@ __device__ __forceinline__ void tail_bitonic_p(unsigned long long *sk, int npow2
     }
   }
 }
+// npow2 <= 2 * kTailThreads: thread t keeps elements 2t and 2t + 1 in registers.  Stride 1 is a compare inside the
+// thread, strides 2..32 are warp shuffles (partner lane = lane ^ stride / 2, both elements travel), only strides >= 64
+// go through shared memory: 20 barriers for 2048 keys instead of 66.
+__device__ __forceinline__ void tail_bitonic_regs(unsigned long long *sk, int npow2, int tid) {
+  const int e0 = 2 * tid;
+  const bool mine = e0 < npow2;
+  unsigned long long x0 = mine ? sk[e0] : 0ULL, x1 = mine ? sk[e0 + 1] : 0ULL;
+  for (int size = 2; size <= npow2; size <<= 1) {
+    const bool desc = (e0 & size) == 0;
+    int j = size >> 1;
+    if (j >= 64) {
+      if (mine) sk[e0] = x0, sk[e0 + 1] = x1;
+      __syncthreads();
+      for (; j >= 64; j >>= 1) {
+        if (tid < (npow2 >> 1)) {
+          const int lo = 2 * tid - (tid & (j - 1));
+          const unsigned long long a = sk[lo], b = sk[lo + j];
+          if (((lo & size) == 0) ? (a < b) : (a > b)) sk[lo] = b, sk[lo + j] = a;
+        }
+        __syncthreads();
+      }
+      if (mine) x0 = sk[e0], x1 = sk[e0 + 1];
+    }
+    for (; j >= 2; j >>= 1) {
+      const unsigned long long y0 = __shfl_xor_sync(0xffffffffu, x0, j >> 1), y1 = __shfl_xor_sync(0xffffffffu, x1, j >> 1);
+      const bool keep_max = ((tid & (j >> 1)) == 0) == desc;
+      x0 = keep_max ? (x0 > y0 ? x0 : y0) : (x0 < y0 ? x0 : y0);
+      x1 = keep_max ? (x1 > y1 ? x1 : y1) : (x1 < y1 ? x1 : y1);
+    }
+    if (desc ? (x0 < x1) : (x0 > x1)) {
+      const unsigned long long t = x0;
+      x0 = x1, x1 = t;
+    }
+  }
+  if (mine) sk[e0] = x0, sk[e0 + 1] = x1;   // (reads of other threads' elements all lie behind a barrier already)
+  __syncthreads();
+}
+
 __device__ __forceinline__ void tail_bitonic(unsigned long long *sk, int npow2, int tid) {
-  if (npow2 <= 2 * kTailThreads) tail_bitonic_p<1>(sk, npow2, tid);        // at most one pair per thread
+  if (npow2 <= 2 * kTailThreads) tail_bitonic_regs(sk, npow2, tid);        // one pair per thread, in registers
   else if (npow2 == 4 * kTailThreads) tail_bitonic_p<2>(sk, npow2, tid);
   else tail_bitonic_p<4>(sk, npow2, tid);                                  // 8 * kTailThreads = kSmallMax
 }
