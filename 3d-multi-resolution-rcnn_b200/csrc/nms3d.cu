@@ -54,6 +54,81 @@ __device__ __forceinline__ bool iou3d_gt(const SortedBox &a, float Sa, const Sor
   return __fdiv_rn(inter, uni) > thr;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Coarse rejection for the bit-matrix kernels.  Most pairs of a proposal set are far apart, yet a lane spends ~25
+// instructions to find inter == 0.  Every CTA therefore lays a 32 x 32 x 32 grid over the bounding range of ITS row and
+// column boxes and gives each box three 32-bit masks (the cells its [lo - 1, hi + 1] interval covers per axis); a pair
+// whose masks miss each other on any axis has inter == 0 exactly as the reference computes it, and for thr >= 0 the
+// reference's answer to inter == 0 is "no" whatever the union is (0 / u is +-0 or NaN):
+//   * the cell of a coordinate is a non-decreasing function of it (float subtract / multiply by a non-negative
+//     constant / float -> int conversion, clamped), so disjoint cell ranges mean fl(a.hi + 1) < fl(b.lo - 1), hence
+//     a.hi + 1 < b.lo - 1, hence min(hi) - max(lo) < -2, hence fl(fl(min(hi) - max(lo)) + 1) <= -1: the reference's
+//     clamped extent is 0 on that axis (a box stored inverted by more than the margin gets an empty mask: it
+//     intersects nothing in the reference either);
+//   * a box with a NaN / infinite coordinate, a degenerate range, or thr < 0 (where inter == 0 can still suppress)
+//     gets all-ones masks and the pair is evaluated in full.
+// Pairs that pass are evaluated exactly as before, so the bit matrix is unchanged.
+// ------------------------------------------------------------------------------------------------
+struct CellMap {
+  float lo[3], inv[3];
+  int on;
+};
+
+__device__ __forceinline__ unsigned cell_range(float lo, float hi, float origin, float inv) {
+  const int c0 = min(max(__float2int_rd(__fmul_rn(__fsub_rn(__fsub_rn(lo, 1.0f), origin), inv)), 0), 31);
+  const int c1 = min(max(__float2int_rd(__fmul_rn(__fsub_rn(__fadd_rn(hi, 1.0f), origin), inv)), 0), 31);
+  return ((2u << c1) - 1u) & ~((1u << c0) - 1u);
+}
+
+__device__ __forceinline__ uint4 box_cells(const SortedBox &b, const CellMap &m) {
+  const float s = b.x1 + b.y1 + b.x2 + b.y2 + b.z1 + b.z2;
+  if (!m.on || !(fabsf(s) <= 3.0e38f)) return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+  return make_uint4(cell_range(b.x1, b.x2, m.lo[0], m.inv[0]), cell_range(b.y1, b.y2, m.lo[1], m.inv[1]),
+                    cell_range(b.z1, b.z2, m.lo[2], m.inv[2]), 0u);
+}
+
+__device__ __forceinline__ bool cells_meet(const uint4 &a, const uint4 &b) {
+  return ((a.x & b.x) != 0u) & ((a.y & b.y) != 0u) & ((a.z & b.z) != 0u);
+}
+
+// Bounding range of the boxes the CTA's threads hold (has_box: this thread contributes `b`), 256 threads.  Ends with
+// a barrier; the result is in shared memory.
+__device__ __forceinline__ void cta_cell_map(const SortedBox &b, bool has_box, bool enabled, CellMap *out) {
+  __shared__ float red[8][6];
+  const float inf = __int_as_float(0x7f800000);
+  float v[6] = {inf, inf, inf, -inf, -inf, -inf};
+  if (has_box) {
+    v[0] = fminf(b.x1, b.x2), v[1] = fminf(b.y1, b.y2), v[2] = fminf(b.z1, b.z2);
+    v[3] = fmaxf(b.x1, b.x2), v[4] = fmaxf(b.y1, b.y2), v[5] = fmaxf(b.z1, b.z2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[c] = fminf(v[c], __shfl_xor_sync(0xffffffffu, v[c], o));
+      v[c + 3] = fmaxf(v[c + 3], __shfl_xor_sync(0xffffffffu, v[c + 3], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) red[threadIdx.x >> 5][c] = v[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int c = threadIdx.x;
+    float lo = red[0][c], hi = red[0][c + 3];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) lo = fminf(lo, red[w][c]), hi = fmaxf(hi, red[w][c + 3]);
+    lo -= 1.0f, hi += 1.0f;   // the masks cover [lo - 1, hi + 1] of every box
+    const float range = hi - lo;
+    const bool ok = range > 0.0f && range <= 3.0e38f && fabsf(lo) <= 3.0e38f;
+    out->lo[c] = ok ? lo : 0.0f;
+    out->inv[c] = ok ? 32.0f / range : 0.0f;
+    if (c == 0) out->on = enabled ? 1 : 0;
+  }
+  __syncthreads();
+}
+
 // Evaluation-time flavour (N1): the reference's numpy nms_3d_python (mmdet/core/evaluation/coco_utils.py:245-282)
 // works in float64 on the json boxes (fp32 values widened), volume = ((x2-x1+1)*(y2-y1+1))*(z2-z1+1), iou =
 // inter / ((vol_i + vol_j) - inter), and KEEPS iou <= thr -- so a NaN iou suppresses.  Same operation order,
@@ -151,16 +226,32 @@ __global__ void __launch_bounds__(256) nms3d_mask_kernel(const SortedBox *__rest
   if (rb >= cb || c0 >= cb || c0 + 3 < rb) return;
   const SortedBox *sb = sorted + (long long)seg * n_max;
   __shared__ SortedBox cols[4][64];
+  __shared__ uint4 colm[4][64];
+  __shared__ CellMap cmap;
   const int rl = threadIdx.x & 63, cq = threadIdx.x >> 6;
-  {
-    const int j = (c0 + cq) * 64 + rl;
-    if (j < n) cols[cq][rl] = sb[j];
-  }
-  __syncthreads();
   const int cblk = c0 + cq;
   const int row = rb * 64 + rl;
+  SortedBox a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cbox = a;
+  const int jc = cblk * 64 + rl;
+  if (jc < n) cbox = sb[jc], cols[cq][rl] = cbox;
+  if (row < n) a = sb[row];
+  {
+    // bounding range over the CTA's 64 rows and up to 256 columns: a thread folds its column and (cq == 0) its row
+    SortedBox u = cbox;
+    const bool hc = jc < n, hr = cq == 0 && row < n;
+    if (hc && hr) {
+      u.x1 = fminf(fminf(cbox.x1, cbox.x2), fminf(a.x1, a.x2)), u.x2 = fmaxf(fmaxf(cbox.x1, cbox.x2), fmaxf(a.x1, a.x2));
+      u.y1 = fminf(fminf(cbox.y1, cbox.y2), fminf(a.y1, a.y2)), u.y2 = fmaxf(fmaxf(cbox.y1, cbox.y2), fmaxf(a.y1, a.y2));
+      u.z1 = fminf(fminf(cbox.z1, cbox.z2), fminf(a.z1, a.z2)), u.z2 = fmaxf(fmaxf(cbox.z1, cbox.z2), fmaxf(a.z1, a.z2));
+    } else if (hr) {
+      u = a;
+    }
+    cta_cell_map(u, hc || hr, F64 ? (0.0 <= thr64) : (thr >= 0.0f), &cmap);
+  }
+  if (jc < n) colm[cq][rl] = box_cells(cbox, cmap);
+  __syncthreads();
   if (cblk < rb || cblk >= cb || row >= n) return;
-  const SortedBox a = sb[row];
+  const uint4 am = box_cells(a, cmap);
   const float Sa = __fmul_rn(a.sxy, a.sz);
   const int csize = min(64, n - cblk * 64);
   const int start = (cblk == rb) ? rl + 1 : 0;
@@ -173,12 +264,15 @@ __global__ void __launch_bounds__(256) nms3d_mask_kernel(const SortedBox *__rest
       unsigned byte = 0;
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (F64 ? iou3d_f64_suppresses(a, cols[cq][jb + u], thr64) : iou3d_gt(a, Sa, cols[cq][jb + u], thr)) byte |= 1u << u;
+        if (cells_meet(am, colm[cq][jb + u]) &&
+            (F64 ? iou3d_f64_suppresses(a, cols[cq][jb + u], thr64) : iou3d_gt(a, Sa, cols[cq][jb + u], thr)))
+          byte |= 1u << u;
       t |= (unsigned long long)byte << jb;
     }
   } else {
     for (int j = start; j < csize; ++j) {
-      if (F64 ? iou3d_f64_suppresses(a, cols[cq][j], thr64) : iou3d_gt(a, Sa, cols[cq][j], thr)) t |= 1ULL << j;
+      if (cells_meet(am, colm[cq][j]) && (F64 ? iou3d_f64_suppresses(a, cols[cq][j], thr64) : iou3d_gt(a, Sa, cols[cq][j], thr)))
+        t |= 1ULL << j;
     }
   }
   mask[((long long)seg * n_max + row) * cbm + cblk] = t;
@@ -198,28 +292,36 @@ __global__ void __launch_bounds__(256) nms3d_mask_q_kernel(const SortedBox *__re
   if (rb >= cb || cblk >= cb || cblk < rb) return;
   const SortedBox *sb = sorted + (long long)seg * n_max;
   __shared__ SortedBox cols[64];
+  __shared__ uint4 colm[64];
+  __shared__ CellMap cmap;
   __shared__ unsigned part[4][64];
   const int rl = threadIdx.x & 63, q = threadIdx.x >> 6;
-  if (threadIdx.x < 64) {
-    const int j = cblk * 64 + threadIdx.x;
-    if (j < n) cols[threadIdx.x] = sb[j];
-  }
-  __syncthreads();
   const int row = rb * 64 + rl;
+  SortedBox a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cbox = a;
+  const int jc = cblk * 64 + rl;
+  const bool hc = q == 0 && jc < n, hr = q == 1 && row < n;   // quarter 0 folds the columns, quarter 1 the rows
+  if (q == 0 && jc < n) cbox = sb[jc], cols[rl] = cbox;
+  if (row < n) a = sb[row];
+  cta_cell_map(hc ? cbox : a, hc || hr, F64 ? (0.0 <= thr64) : (thr >= 0.0f), &cmap);
+  if (hc) colm[rl] = box_cells(cbox, cmap);
+  __syncthreads();
   unsigned t = 0;
   if (row < n) {
-    const SortedBox a = sb[row];
+    const uint4 am = box_cells(a, cmap);
     const float Sa = __fmul_rn(a.sxy, a.sz);
     const int csize = min(64, n - cblk * 64);
     const int j0 = max(q * 16, (cblk == rb) ? rl + 1 : 0), j1 = min(q * 16 + 16, csize);
     if (j0 == q * 16 && j1 == q * 16 + 16) {   // a full quarter: compile-time bit positions (see nms3d_mask_kernel)
       const SortedBox *cq16 = cols + q * 16;
+      const uint4 *mq16 = colm + q * 16;
 #pragma unroll
       for (int u = 0; u < 16; ++u)
-        if (F64 ? iou3d_f64_suppresses(a, cq16[u], thr64) : iou3d_gt(a, Sa, cq16[u], thr)) t |= 1u << u;
+        if (cells_meet(am, mq16[u]) && (F64 ? iou3d_f64_suppresses(a, cq16[u], thr64) : iou3d_gt(a, Sa, cq16[u], thr)))
+          t |= 1u << u;
     } else {
       for (int j = j0; j < j1; ++j)
-        if (F64 ? iou3d_f64_suppresses(a, cols[j], thr64) : iou3d_gt(a, Sa, cols[j], thr)) t |= 1u << (j - q * 16);
+        if (cells_meet(am, colm[j]) && (F64 ? iou3d_f64_suppresses(a, cols[j], thr64) : iou3d_gt(a, Sa, cols[j], thr)))
+          t |= 1u << (j - q * 16);
     }
   }
   part[q][rl] = t;

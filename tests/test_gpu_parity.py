@@ -60,6 +60,39 @@ def test_nms_ties_and_duplicates(oracle, dev):
     assert np.array_equal(inds.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("thr", [0.5, 0.0, -0.25])
+def test_nms_coarse_rejection_edge_cases(oracle, dev, thr):
+    """The bit-matrix kernels skip a pair whose coarse cell masks miss each other (csrc/nms3d.cu).  The kept list must
+    stay the oracle's where that shortcut could go wrong: boxes one voxel apart (the reference's +1 makes them touch),
+    boxes stored inverted, huge and non-finite coordinates, sparse sets with far outliers, and a negative threshold
+    (every pair with a finite iou suppresses, disjoint ones included)."""
+    from roi3d_b200.ops import nms
+    rng = np.random.default_rng(5)
+    n = 700
+    c = rng.uniform(0, 400, (n, 3)).astype(np.float32)
+    h = rng.uniform(0.5, 6, (n, 3)).astype(np.float32)
+    d = np.stack([c[:, 0] - h[:, 0], c[:, 1] - h[:, 1], c[:, 0] + h[:, 0], c[:, 1] + h[:, 1], c[:, 2] - h[:, 2],
+                  c[:, 2] + h[:, 2], rng.uniform(0, 1, n).astype(np.float32)], 1).astype(np.float32)
+    d[1, :6] = d[0, :6]
+    d[1, [0, 2]] += (d[0, 2] - d[0, 0]) + 1.0            # abuts box 0 along x: extent + 1 - 1 > 0 in the reference
+    d[2, :6] = d[0, :6]
+    d[2, [0, 2]] += (d[0, 2] - d[0, 0]) + 2.0            # one voxel further: extent 0
+    d[10, [0, 2]] = d[10, [2, 0]]                        # inverted box
+    d[11, [0, 2]] = d[11, [2, 0]] + np.float32([3, -3])  # inverted by more than the margin
+    d[20, :6] = [1e9, 1e9, 1e9 + 64, 1e9 + 64, 1e9, 1e9 + 64]    # far outlier stretches the CTA's grid
+    d[21, :6] = [-3e38, -3e38, 3e38, 3e38, -3e38, 3e38]            # covers everything, sums overflow
+    want = oracle.nms3d(d, thr)
+    _, inds = nms(torch.from_numpy(d).to(dev), thr)
+    assert np.array_equal(inds.cpu().numpy(), want)
+    # a large sparse set: most 64 x 64 tiles see no overlap at all
+    big = synth.c1_boxes(2000, seed=3)
+    big[:, [0, 2]] *= 7
+    big[:, [1, 3]] *= 5
+    want = oracle.nms3d(big, thr)
+    _, inds = nms(torch.from_numpy(big).to(dev), thr)
+    assert np.array_equal(inds.cpu().numpy(), want)
+
+
 def test_nms_batched_segments(oracle, dev):
     from roi3d_b200.ops import nms3d_batched
     sizes = [0, 1, 64, 130, 700, 2000]
