@@ -255,25 +255,23 @@ __global__ void __launch_bounds__(256) nms3d_mask_kernel(const SortedBox *__rest
   const float Sa = __fmul_rn(a.sxy, a.sz);
   const int csize = min(64, n - cblk * 64);
   const int start = (cblk == rb) ? rl + 1 : 0;
-  unsigned long long t = 0;
-  if (start == 0 && csize == 64) {
-    // full off-diagonal tile (most of them): bits are collected eight at a time at compile-time positions -- one
-    // predicated OR per pair instead of a 64-bit variable shift, two selects and two ORs
-#pragma unroll 1
-    for (int jb = 0; jb < 64; jb += 8) {
-      unsigned byte = 0;
+  // coarse pass over the tile's 64 columns at compile-time bit positions (a handful of logic instructions per pair),
+  // then the full test only for this lane's own survivors: a warp pays for the longest survivor list among its lanes,
+  // not for every column that ANY lane cannot rule out
+  unsigned plo = 0, phi = 0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (cells_meet(am, colm[cq][jb + u]) &&
-            (F64 ? iou3d_f64_suppresses(a, cols[cq][jb + u], thr64) : iou3d_gt(a, Sa, cols[cq][jb + u], thr)))
-          byte |= 1u << u;
-      t |= (unsigned long long)byte << jb;
-    }
-  } else {
-    for (int j = start; j < csize; ++j) {
-      if (cells_meet(am, colm[cq][j]) && (F64 ? iou3d_f64_suppresses(a, cols[cq][j], thr64) : iou3d_gt(a, Sa, cols[cq][j], thr)))
-        t |= 1ULL << j;
-    }
+  for (int u = 0; u < 32; ++u) {
+    if (cells_meet(am, colm[cq][u])) plo |= 1u << u;
+    if (cells_meet(am, colm[cq][32 + u])) phi |= 1u << u;
+  }
+  unsigned long long pm = ((unsigned long long)phi << 32) | plo;
+  if (start > 0) pm = start < 64 ? pm & ~((1ULL << start) - 1ULL) : 0ULL;
+  if (csize < 64) pm &= (1ULL << csize) - 1ULL;
+  unsigned long long t = 0;
+  while (pm) {
+    const int j = __ffsll((long long)pm) - 1;
+    pm &= pm - 1ULL;
+    if (F64 ? iou3d_f64_suppresses(a, cols[cq][j], thr64) : iou3d_gt(a, Sa, cols[cq][j], thr)) t |= 1ULL << j;
   }
   mask[((long long)seg * n_max + row) * cbm + cblk] = t;
 }
@@ -311,17 +309,17 @@ __global__ void __launch_bounds__(256) nms3d_mask_q_kernel(const SortedBox *__re
     const float Sa = __fmul_rn(a.sxy, a.sz);
     const int csize = min(64, n - cblk * 64);
     const int j0 = max(q * 16, (cblk == rb) ? rl + 1 : 0), j1 = min(q * 16 + 16, csize);
-    if (j0 == q * 16 && j1 == q * 16 + 16) {   // a full quarter: compile-time bit positions (see nms3d_mask_kernel)
-      const SortedBox *cq16 = cols + q * 16;
-      const uint4 *mq16 = colm + q * 16;
+    const uint4 *mq16 = colm + q * 16;   // coarse pass at compile-time bit positions, full test for the survivors
+    unsigned pm = 0;                     // (see nms3d_mask_kernel)
 #pragma unroll
-      for (int u = 0; u < 16; ++u)
-        if (cells_meet(am, mq16[u]) && (F64 ? iou3d_f64_suppresses(a, cq16[u], thr64) : iou3d_gt(a, Sa, cq16[u], thr)))
-          t |= 1u << u;
-    } else {
-      for (int j = j0; j < j1; ++j)
-        if (cells_meet(am, colm[j]) && (F64 ? iou3d_f64_suppresses(a, cols[j], thr64) : iou3d_gt(a, Sa, cols[j], thr)))
-          t |= 1u << (j - q * 16);
+    for (int u = 0; u < 16; ++u)
+      if (cells_meet(am, mq16[u])) pm |= 1u << u;
+    const int l0 = j0 - q * 16, l1 = j1 - q * 16;   // valid local columns [l0, l1)
+    pm = l1 > l0 ? pm & ((1u << l1) - 1u) & ~((1u << l0) - 1u) : 0u;
+    while (pm) {
+      const int u = __ffs(pm) - 1;
+      pm &= pm - 1u;
+      if (F64 ? iou3d_f64_suppresses(a, cols[q * 16 + u], thr64) : iou3d_gt(a, Sa, cols[q * 16 + u], thr)) t |= 1u << u;
     }
   }
   part[q][rl] = t;
