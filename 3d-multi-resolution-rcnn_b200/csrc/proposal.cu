@@ -102,8 +102,8 @@ __device__ __forceinline__ void pass_geometry(int pass, int &shift, int &bits) {
 // Bin of h[0, kBins) (shared memory) where the descending cumulative count reaches `need` (1 <= need <= total): returns
 // the bin, leaves what is still needed inside it in `need`, and tells whether the bin holds exactly that many.  The
 // whole CTA calls it; warp 0 works: lanes sum 64 bins each (rotated, so that the 32 lanes read 32 banks), a shuffle scan
-// finds the lane that crosses, the same again over that lane's 64 bins.  Two barriers; h must not change before the next
-// barrier of the caller.
+// finds the lane that crosses, the same again over that lane's 64 bins.  Three barriers (before, after, and after the
+// result is read).
 __device__ __forceinline__ unsigned find_bin_desc(const unsigned *h, unsigned &need, bool &exact, int tid) {
   __shared__ unsigned s_fb[3];
   static_assert(kBins == 2048, "32 lanes x 64 bins");
@@ -139,9 +139,11 @@ __device__ __forceinline__ unsigned find_bin_desc(const unsigned *h, unsigned &n
     }
   }
   __syncthreads();
+  const unsigned bin = s_fb[0];
   need = s_fb[1];
   exact = s_fb[2] != 0u;
-  return s_fb[0];
+  __syncthreads();   // nobody is still reading the result when a caller goes on to write shared memory
+  return bin;
 }
 
 // Pick the digit where the descending cumulative count crosses k_rem (256 threads; run by the LAST CTA of a
