@@ -733,17 +733,17 @@ __global__ void __cluster_dims__(kSieveCluster, 1, 1) __launch_bounds__(kSieveTh
     key[u] = 0u;
     if (i < S) key[u] = okey(__ldg(src + (size_t)i * step + (step > 1u ? sieve_hash(i) % step : 0u)));
   }
+  // two 11-bit digits: T is the lower edge of the 22-bit bin that holds the sample's need-th largest key (the last ten
+  // bits would move it by 2^-13 of its value -- any threshold is valid, the tail proves the result)
   unsigned prefix = 0u;
-  const int shifts[3] = {21, 10, 0};
 #pragma unroll
-  for (int dg = 0; dg < 3; ++dg) {
-    const int shift = shifts[dg];
-    const unsigned bins_mask = dg == 2 ? 0x3FFu : 0x7FFu;
+  for (int dg = 0; dg < 2; ++dg) {
+    const int shift = dg == 0 ? 21 : 10;
     for (int b = tid; b < kBins; b += kSieveThreads) h[b] = 0u;
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < PER; ++u)
-      if (key[u] && (dg == 0 || (key[u] >> (shift + (dg == 2 ? 10 : 11))) == prefix)) atomicAdd(&h[(key[u] >> shift) & bins_mask], 1u);
+      if (key[u] && (dg == 0 || (key[u] >> 21) == prefix)) atomicAdd(&h[(key[u] >> shift) & 0x7FFu], 1u);
     cluster.sync();
     if (tid < kBins / kSieveCluster) {
       const int b = rank * (kBins / kSieveCluster) + tid;
@@ -756,8 +756,9 @@ __global__ void __cluster_dims__(kSieveCluster, 1, 1) __launch_bounds__(kSieveTh
     cluster.sync();
     bool exact;
     const unsigned dgt = find_bin_desc(tot, need, exact, tid);
-    prefix = (prefix << (dg == 2 ? 10 : 11)) | dgt;
+    prefix = (prefix << 11) | dgt;
   }
+  prefix <<= 10;
   if (tid == 0 && rank == 0) state[seg].sieve_t = okey_inv(prefix);
 }
 
