@@ -699,7 +699,7 @@ __device__ __forceinline__ unsigned sieve_hash(unsigned i) {
 
 __global__ void __cluster_dims__(kSieveCluster, 1, 1) __launch_bounds__(kSieveThreads)
     topk_sample_kernel(const float *__restrict__ scores, const SegTable tab, SegState *__restrict__ state,
-                       int *__restrict__ tickets, int k, unsigned small_max) {
+                       int *__restrict__ tickets, unsigned *__restrict__ hist, int k, unsigned small_max) {
   // One CLUSTER of kSieveCluster CTAs per segment: a single SM gathers scattered 32-byte sectors too slowly (a 32 K
   // sample is 1 MB of them).  Every CTA keeps its share of the sample keys in registers; per digit the CTAs count into
   // their own table, CTA r adds up bins [r * 256, r * 256 + 256) of all tables through distributed shared memory and
@@ -721,6 +721,8 @@ __global__ void __cluster_dims__(kSieveCluster, 1, 1) __launch_bounds__(kSieveTh
     state[seg] = st;
   }
   if (len <= small_max) return;   // the whole cluster
+  // the digit passes' global histogram of this segment starts out clean (no memset node in front of the path)
+  if (tid < kBins / kSieveCluster) hist[(long long)seg * kBins + rank * (kBins / kSieveCluster) + tid] = 0u;
   const float *src = scores + d.off;
   const unsigned S = min(len, (unsigned)kSieveSample), step = len / S;
   unsigned need = (unsigned)(((unsigned long long)(k + kBndCap / 2) * S + len - 1) / len);   // rank of T in the sample
@@ -1505,7 +1507,7 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
         ROI3D_CUDA(cudaFuncSetAttribute(topk_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemBytes));
         tail_opt_in.mark(kTailSmemBytes);
       }
-      topk_sample_kernel<<<ns * kSieveCluster, kSieveThreads, 0, st>>>(scores_dev, tab, state, tickets, k, small_max);
+      topk_sample_kernel<<<ns * kSieveCluster, kSieveThreads, 0, st>>>(scores_dev, tab, state, tickets, hist, k, small_max);
       ROI3D_LAUNCH_CHECK();
       const int phase = g_topk_sieve == 2 ? 3 : 1;
       if (apply_sigmoid) {
@@ -1527,7 +1529,7 @@ int roi3d_topk_segmented_masked(const float *scores_dev, const int64_t *seg_off,
       ROI3D_LAUNCH_CHECK();
     }
     if (maxlen > 0) {
-      ROI3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)ns * kBins * sizeof(unsigned), st));
+      if (!sieve) ROI3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)ns * kBins * sizeof(unsigned), st));
       const dim3 grid((unsigned)ceil_div_ll(maxlen, kItemsPerCta), ns);
       const dim3 grid2((unsigned)(grid.x < 8 ? grid.x : 8), ns);  // boundary passes: see topk_hist_kernel
       {
