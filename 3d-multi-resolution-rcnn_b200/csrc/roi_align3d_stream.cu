@@ -484,6 +484,8 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
     if (d.flags & TILE_DONE) break;
     const StreamPlan *P = reinterpret_cast<const StreamPlan *>(smem + L::PLAN + d.plan * PLAN_BYTES);
     const int pflags = P->flags;
+    int krow = 0;
+    bool released = false;
     if (!(pflags & PLAN_SLOW)) {
       // ---- streamed item: acc lives in registers from the first tile to the epilogue
       float2 acc[7][NPH], t2[NPH];
@@ -537,9 +539,15 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
         st_mbar_wait(bar0 + slot * 8, (tile_seq / NS) & 1);     // the next tile's bytes have landed
         dt = tdesc[slot];
       }
+      // the item's last slot and its plan record go back to the producer BEFORE the epilogue (what the epilogue needs
+      // of the plan is in registers): the producer fills it while the owners wait for the staging image and write it
+      const float inv = P->inv_count;
+      krow = P->krow;
+      released = true;
+      __syncwarp();
+      if (lane == 0) st_mbar_arrive(bar0 + (NS + slot) * 8);
       // the staging image is free once the storer has read out the previous item
       st_mbar_wait(sfree, (item_seq & 1) ^ 1);
-      const float inv = P->inv_count;
       const float2 inv2 = make_float2(inv, inv);
       float *s0 = staging + (NC ? lane : 2 * lane) * pdhw + ph0 * 7 + pw;
       const int second = NC ? 32 * pdhw : pdhw;   // the lane's other channel
@@ -559,15 +567,16 @@ __device__ __forceinline__ void owner_loop(const StreamArgs &a, unsigned char *s
       ++tile_seq;
       st_mbar_wait(sfree, (item_seq & 1) ^ 1);
       owner_literal<NPH, NC>(a.p, P->k, P->lvl, d.chunk, ph0, pw, lane, staging, pdhw);
+      krow = P->krow;
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the bulk store
     if (warp == 0 && lane == 0) {
       int *sd = reinterpret_cast<int *>(smem + L::SDESC + (item_seq & 1) * 16);
-      sd[0] = P->krow, sd[1] = d.chunk, sd[2] = 0;
+      sd[0] = krow, sd[1] = d.chunk, sd[2] = 0;
     }
     __syncwarp();
     if (lane == 0) {
-      st_mbar_arrive(bar0 + (NS + slot) * 8);  // the item's last slot and its plan record are free
+      if (!released) st_mbar_arrive(bar0 + (NS + slot) * 8);  // (literal item) its slot and plan record are free
       st_mbar_arrive(sfull);
     }
     ++item_seq;
