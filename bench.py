@@ -370,7 +370,9 @@ def main():
         achieved = alg_bytes / (main_kernel_ms * 1e-3) / 1e9          # the dominant kernel's own launch duration
         achieved_step = alg_bytes / (kernel_ms * 1e-3) / 1e9            # the whole step (plan kernel + launch gap included)
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "r02_final_c2_fwd_stream_ncu_summary.json")
+        prof = os.path.join(ROOT, "profiles", "r02_s4_c2_fwd_stream_ncu_summary.json")   # ncu --set full of this kernel
+        if not os.path.exists(prof):
+            prof = os.path.join(ROOT, "profiles", "r02_final_c2_fwd_stream_ncu_summary.json")
         if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
