@@ -344,8 +344,14 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
                                                           unsigned char *__restrict__ flags,
                                                           int64_t *__restrict__ keep,
                                                           int64_t *__restrict__ keep_by_score,
-                                                          int32_t *__restrict__ num_keep) {
+                                                          int32_t *__restrict__ num_keep,
+                                                          const unsigned char *__restrict__ limited, int max_keep) {
   const int seg = blockIdx.x;
+  // optional early stop (the proposal path only uses the first nms_post kept boxes of a score-sorted level): once
+  // `limit` boxes are kept the remaining tiles are not swept; the lists then hold a prefix of the full result
+  const int limit = (max_keep > 0 && limited != nullptr && limited[seg] != 0) ? max_keep : 0x7fffffff;
+  __shared__ int s_kept[2];   // running kept count after tile b, in entry b & 1 (the resolver is a tile ahead of the readers)
+  int kept_total = 0;
   const int n = seg_counts ? min(max(seg_counts[seg], 0), n_max) : n_max;
   const int cb = (n + 63) >> 6, cbm = (n_max + 63) >> 6;
   const unsigned long long *m = mask + (long long)seg * n_max * cbm;
@@ -439,7 +445,8 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
         if (next == kept) break;
         kept = next;
       }
-      if (lane == 0) keptw[blk] = kept;
+      kept_total += __popcll(kept);
+      if (lane == 0) keptw[blk] = kept, s_kept[blk & 1] = kept_total;
       if (blk + 1 < cb) {
         // word blk+1: lanes take rows lane and lane+32, OR-reduce across the warp
         unsigned long long v = 0ULL;
@@ -496,9 +503,19 @@ __global__ void __launch_bounds__(256) nms3d_sweep_kernel(const unsigned long lo
   };
   for (int blk = 0; blk < cb; blk += 4) {   // four register sets take turns: a tile's rows have four iterations to arrive
     sweep_tile(blk, stage0);                 // (two were not enough: an L2 round trip is longer than two iterations)
-    if (blk + 1 < cb) sweep_tile(blk + 1, stage1);
-    if (blk + 2 < cb) sweep_tile(blk + 2, stage2);
-    if (blk + 3 < cb) sweep_tile(blk + 3, stage3);
+    if (s_kept[blk & 1] >= limit) break;     // (read behind the tile's barrier; uniform over the CTA)
+    if (blk + 1 < cb) {
+      sweep_tile(blk + 1, stage1);
+      if (s_kept[(blk + 1) & 1] >= limit) break;
+    }
+    if (blk + 2 < cb) {
+      sweep_tile(blk + 2, stage2);
+      if (s_kept[(blk + 2) & 1] >= limit) break;
+    }
+    if (blk + 3 < cb) {
+      sweep_tile(blk + 3, stage3);
+      if (s_kept[(blk + 3) & 1] >= limit) break;
+    }
   }
   // the last tile's kept rows have no later words to update; nothing left to apply
 
@@ -642,7 +659,7 @@ size_t roi3d_nms3d_workspace_bytes(int nseg, int n_max) {
 }
 
 static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, const uint8_t *presorted_dev, int nseg,
-                        int n_max, float iou_thr,
+                        int n_max, float iou_thr, int max_keep_presorted,
                         double iou_thr64, bool f64, int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev,
                         void *workspace_dev, size_t workspace_bytes, void *stream) {
   ROI3D_CHECK_ARG(nseg >= 0 && n_max >= 0, "bad sizes nseg=%d n_max=%d", nseg, n_max);
@@ -686,7 +703,7 @@ static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, co
     const size_t panel_bytes = (size_t)kPanelBufs * 64 * (kPanelW + 1) * sizeof(unsigned long long);  // 66 KiB
     ROI3D_CUDA(cudaFuncSetAttribute(nms3d_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_bytes));
     nms3d_sweep_kernel<<<nseg, 256, panel_bytes, st>>>(w.mask, w.order, seg_counts_dev, n_max, w.flags, keep_dev,
-                                                      keep_by_score_dev, num_keep_dev);
+                                                      keep_by_score_dev, num_keep_dev, presorted_dev, max_keep_presorted);
   }
   ROI3D_LAUNCH_CHECK();
   return ROI3D_OK;
@@ -695,21 +712,29 @@ static int nms3d_launch(const float *dets_dev, const int32_t *seg_counts_dev, co
 int roi3d_nms3d_batched(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, float iou_thr,
                         int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev, void *workspace_dev,
                         size_t workspace_bytes, void *stream) {
-  return nms3d_launch(dets_dev, seg_counts_dev, nullptr, nseg, n_max, iou_thr, 0.0, false, keep_dev, keep_by_score_dev,
+  return nms3d_launch(dets_dev, seg_counts_dev, nullptr, nseg, n_max, iou_thr, 0, 0.0, false, keep_dev, keep_by_score_dev,
                       num_keep_dev, workspace_dev, workspace_bytes, stream);
 }
 
 int roi3d_nms3d_batched_presorted(const float *dets_dev, const int32_t *seg_counts_dev, const uint8_t *presorted_dev,
                                   int nseg, int n_max, float iou_thr, int64_t *keep_dev, int64_t *keep_by_score_dev,
                                   int32_t *num_keep_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
-  return nms3d_launch(dets_dev, seg_counts_dev, presorted_dev, nseg, n_max, iou_thr, 0.0, false, keep_dev,
+  return nms3d_launch(dets_dev, seg_counts_dev, presorted_dev, nseg, n_max, iou_thr, 0, 0.0, false, keep_dev,
                       keep_by_score_dev, num_keep_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int roi3d_nms3d_batched_limited(const float *dets_dev, const int32_t *seg_counts_dev, const uint8_t *presorted_dev,
+                                int nseg, int n_max, float iou_thr, int max_keep_presorted, int64_t *keep_dev,
+                                int64_t *keep_by_score_dev, int32_t *num_keep_dev, void *workspace_dev,
+                                size_t workspace_bytes, void *stream) {
+  return nms3d_launch(dets_dev, seg_counts_dev, presorted_dev, nseg, n_max, iou_thr, max_keep_presorted, 0.0, false,
+                      keep_dev, keep_by_score_dev, num_keep_dev, workspace_dev, workspace_bytes, stream);
 }
 
 int roi3d_nms3d_eval_batched(const float *dets_dev, const int32_t *seg_counts_dev, int nseg, int n_max, double iou_thr,
                              int64_t *keep_dev, int64_t *keep_by_score_dev, int32_t *num_keep_dev, void *workspace_dev,
                              size_t workspace_bytes, void *stream) {
-  return nms3d_launch(dets_dev, seg_counts_dev, nullptr, nseg, n_max, 0.0f, iou_thr, true, keep_dev, keep_by_score_dev,
+  return nms3d_launch(dets_dev, seg_counts_dev, nullptr, nseg, n_max, 0.0f, 0, iou_thr, true, keep_dev, keep_by_score_dev,
                       num_keep_dev, workspace_dev, workspace_bytes, stream);
 }
 

@@ -56,6 +56,7 @@ def _load():
         "roi3d_nms3d_workspace_bytes": (c_size_t, [c_int, c_int]),
         "roi3d_nms3d_batched": (c_int, [P, P, c_int, c_int, c_float, P, P, P, P, c_size_t, P]),
         "roi3d_nms3d_batched_presorted": (c_int, [P, P, P, c_int, c_int, c_float, P, P, P, P, c_size_t, P]),
+        "roi3d_nms3d_batched_limited": (c_int, [P, P, P, c_int, c_int, c_float, c_int, P, P, P, P, c_size_t, P]),
         "roi3d_nms3d_eval_batched": (c_int, [P, P, c_int, c_int, ctypes.c_double, P, P, P, P, c_size_t, P]),
         "roi3d_nms3d_host": (c_int, [P, c_int, c_float, P, P]),
         "roi3d_roi_align3d_forward_host": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int,

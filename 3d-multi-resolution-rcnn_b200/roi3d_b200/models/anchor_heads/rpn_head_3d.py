@@ -322,7 +322,9 @@ class RPNProposal3D(object):
                 stds.ctypes.data, dets.data_ptr(), stream_ptr()))
 
         # 3. one batched NMS; kept rows in descending-score order
-        keep_i, keep_s, num_keep = nms3d_batched(dets, seg_counts, nms_thr, want_score_order=True, presorted=presorted)
+        #    (a score-sorted level only contributes proposals[:nms_post]: its sweep stops once that many are kept)
+        keep_i, keep_s, num_keep = nms3d_batched(dets, seg_counts, nms_thr, want_score_order=True, presorted=presorted,
+                                                 max_keep=nms_post)
 
         # 4. proposals[:nms_post] per segment (rpn_head_3d.py:135), per image cat in level order, topk(max_num)
         #    (:139-148): one collect kernel, one segmented top-k, one row gather

@@ -24,11 +24,14 @@ from ..._util import check_cuda_f32, device_guard, nvtx_range, stream_ptr, works
 _WS_BYTES = {}   # (nseg, n_max) -> workspace size (a ctypes round trip per call otherwise)
 
 
-def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=None):
+def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=None, max_keep=0):
     """Batched device NMS.  dets [nseg, n_max, 7] fp32 CUDA; seg_counts int32 [nseg] CUDA or None.
 
     presorted: optional uint8 [nseg] CUDA tensor, 1 where the segment's rows already are in descending-score order
     (ties by ascending row), e.g. rows straight out of the segmented top-k: the ranking pass is skipped for them.
+    max_keep > 0 (with presorted): the sweep of a presorted segment stops with the 64-box tile in which the kept count
+    reaches max_keep -- the proposal path only reads `proposals[:nms_post]` (rpn_head_3d.py:135); the lists then hold
+    that prefix of the full result (num_keep in [max_keep, max_keep + 63]).
     Returns (keep [nseg, n_max] int64, keep_by_score or None, num_keep [nseg] int32); nothing syncs.
     """
     check_cuda_f32(dets, "dets", ndim=3, last=7)
@@ -50,9 +53,9 @@ def nms3d_batched(dets, seg_counts, iou_thr, want_score_order=True, presorted=No
         nbytes = _WS_BYTES[(nseg, n_max)] = _lib.lib.roi3d_nms3d_workspace_bytes(nseg, n_max)
     _buf, ws = workspace(dev, nbytes)
     with device_guard(dev), nvtx_range("roi3d.nms3d_batched"):
-        _lib.check(_lib.lib.roi3d_nms3d_batched_presorted(
+        _lib.check(_lib.lib.roi3d_nms3d_batched_limited(
             dets.data_ptr(), None if seg_counts is None else seg_counts.data_ptr(),
-            None if presorted is None else presorted.data_ptr(), nseg, n_max, float(iou_thr),
+            None if presorted is None else presorted.data_ptr(), nseg, n_max, float(iou_thr), int(max_keep),
             keep.data_ptr(), None if keep_s is None else keep_s.data_ptr(), num.data_ptr(), ws, nbytes,
             stream_ptr()))
     return keep, keep_s, num

@@ -154,6 +154,16 @@ int roi3d_nms3d_batched_presorted(const float *dets_dev, const int32_t *seg_coun
                                   int nseg, int n_max, float iou_thr, int64_t *keep_dev, int64_t *keep_by_score_dev,
                                   int32_t *num_keep_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Same as roi3d_nms3d_batched_presorted with an early stop for the proposal path, which only uses the first nms_post
+ * kept boxes of a score-sorted level (`proposals[:nms_post]`, rpn_head_3d.py:135): for a segment flagged presorted the
+ * greedy sweep ends with the 64-box tile in which the kept count reaches max_keep_presorted.  num_keep of such a segment
+ * is then between max_keep_presorted and max_keep_presorted + 63, keep_by_score holds that prefix of the full list and
+ * keep (ascending index) the same boxes.  Segments not flagged, and max_keep_presorted <= 0, are swept in full. */
+int roi3d_nms3d_batched_limited(const float *dets_dev, const int32_t *seg_counts_dev, const uint8_t *presorted_dev,
+                                int nseg, int n_max, float iou_thr, int max_keep_presorted, int64_t *keep_dev,
+                                int64_t *keep_by_score_dev, int32_t *num_keep_dev, void *workspace_dev,
+                                size_t workspace_bytes, void *stream);
+
 /* Evaluation-time flavour of the same NMS.
  * Replaces: nms_3d_python, mmdet/core/evaluation/coco_utils.py:245-282 (numpy float64, per volume, called from
  *   apply_nms :306-332 with thr 0.1): IoU evaluated in float64 in numpy's operation order on the fp32 boxes,

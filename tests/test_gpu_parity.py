@@ -1328,6 +1328,33 @@ def test_nms_presorted_segments_skip_the_ranking(oracle, dev):
     assert np.array_equal(k1[0, :int(n1[0])].cpu().numpy(), oracle.nms3d(a, 0.5))
 
 
+@pytest.mark.parametrize("max_keep", [1, 64, 100, 1000, 5000])
+def test_nms_limited_sweep_returns_a_prefix(oracle, dev, max_keep):
+    """roi3d_nms3d_batched_limited: a presorted segment's sweep stops with the 64-box tile in which the kept count
+    reaches max_keep -- the lists are a prefix of the full result (what `proposals[:nms_post]` reads), unflagged
+    segments and segments that never reach the limit are swept in full."""
+    from roi3d_b200.ops import nms3d_batched
+    segs = []
+    for seed, n in ((3, 2000), (4, 2000), (5, 700), (6, 2000)):
+        a = synth.c1_boxes(n, seed=seed)
+        a = a[np.argsort(-a[:, 6], kind="stable")]
+        segs.append(np.concatenate([a, np.zeros((2000 - n, 7), np.float32)]))
+    segs[3] = synth.c1_boxes(2000, seed=6)              # unsorted, unflagged
+    dets = torch.from_numpy(np.stack(segs)).to(dev)
+    cnt = torch.tensor([2000, 2000, 700, 2000], dtype=torch.int32, device=dev)
+    flags = torch.tensor([1, 1, 1, 0], dtype=torch.uint8, device=dev)
+    k0, s0, n0 = nms3d_batched(dets, cnt, 0.5, presorted=flags)
+    k1, s1, n1 = nms3d_batched(dets, cnt, 0.5, presorted=flags, max_keep=max_keep)
+    for seg in range(4):
+        full, got = int(n0[seg]), int(n1[seg])
+        if seg == 3 or full <= max_keep:
+            assert got == full and torch.equal(k0[seg, :full], k1[seg, :full]) and torch.equal(s0[seg, :full], s1[seg, :full])
+            continue
+        assert max_keep <= got <= min(full, max_keep + 63)
+        assert torch.equal(s1[seg, :got], s0[seg, :got])                              # a prefix in score order
+        assert torch.equal(k1[seg, :got], torch.sort(s0[seg, :got]).values)           # the same boxes by index
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # SURVEY 8f N2 / N4 (training halves): RandomSampler and mask targets
 # ---------------------------------------------------------------------------------------------------------------
