@@ -946,7 +946,8 @@ __device__ __forceinline__ void tail_bitonic_regs(unsigned long long *sk, int np
   __syncthreads();
 }
 
-__device__ __forceinline__ void tail_bitonic(unsigned long long *sk, int npow2, int tid) {
+// (not inlined: four call sites x three variants made the tail kernel 70 KB of mostly straight-line code)
+__device__ __noinline__ void tail_bitonic(unsigned long long *sk, int npow2, int tid) {
   if (npow2 <= 2 * kTailThreads) tail_bitonic_regs(sk, npow2, tid);        // one pair per thread, in registers
   else if (npow2 == 4 * kTailThreads) tail_bitonic_p<2>(sk, npow2, tid);
   else tail_bitonic_p<4>(sk, npow2, tid);                                  // 8 * kTailThreads = kSmallMax
@@ -959,7 +960,7 @@ __device__ __forceinline__ unsigned long long swap_words(unsigned long long v) {
 // The need-th largest of the non-zero keys sk[0, n) (need <= their count): MSB-first 11/11/10-bit digits like the global
 // passes, histogram and scan in shared memory.  Stops as soon as a digit's bin holds exactly what is still needed (the
 // returned threshold then has its undecided bits clear): every key >= the result is selected, and there are `need` of them.
-__device__ __forceinline__ unsigned long long tail_select(const unsigned long long *sk, int n, int need, unsigned *h, int tid) {
+__device__ __noinline__ unsigned long long tail_select(const unsigned long long *sk, int n, int need, unsigned *h, int tid) {
   unsigned long long prefix = 0ULL;
   for (int pass = 0; pass < 6; ++pass) {
     int shift, bits;

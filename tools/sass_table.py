@@ -33,7 +33,7 @@ for line in sass.split("\n"):
 if cur:
     rows.append((cur, cnt, tot))
 KEEP = ("roi_align3d_fwd_stream_kernel", "roi_align3d_fwd_stream_ncdhw_kernel", "roi_align3d_bwd_stream_kernel", "roi_align3d_bwd_planar_kernel", "roi_align3d_plan_kernel", "roi_align3d_fwd_planar_kernel", "roi_align3d_bwd2_kernel",
-        "nms3d_", "topk_first_kernel", "topk_second_kernel", "topk_split_keys_kernel", "topk_tail_kernel",
+        "nms3d_", "topk_sample_kernel", "topk_sieve_kernel", "topk_first_kernel", "topk_second_kernel", "topk_split_keys_kernel", "topk_tail_kernel",
         "decode_proposals_batched_kernel", "assign_pass", "mask_paste_kernel", "transpose_r32c128")
 with open(sys.argv[1], "w") as f:
     f.write("# SASS opcode counts of the product kernels (static instruction counts, `cuobjdump -sass lib/libroi3d_b200.so`)\n\n")
