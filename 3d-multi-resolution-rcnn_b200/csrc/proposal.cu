@@ -725,7 +725,10 @@ __global__ void __cluster_dims__(kSieveCluster, 1, 1) __launch_bounds__(kSieveTh
   if (tid < kBins / kSieveCluster) hist[(long long)seg * kBins + rank * (kBins / kSieveCluster) + tid] = 0u;
   const float *src = scores + d.off;
   const unsigned S = min(len, (unsigned)kSieveSample), step = len / S;
-  unsigned need = (unsigned)(((unsigned long long)(k + kBndCap / 2) * S + len - 1) / len);   // rank of T in the sample
+  // rank of T in the sample: predicts k + kBndCap / 2 elements >= T in the segment; a segment that is sampled whole
+  // needs no statistical slack, only room for the proof (the k-th score must clear sigmoid(T) by the rounding margin)
+  unsigned need = S == len ? (unsigned)(k + kBndCap / 16)
+                           : (unsigned)(((unsigned long long)(k + kBndCap / 2) * S + len - 1) / len);
   need = max(1u, min(need, S));
   constexpr int PER = kSieveSample / kSieveCluster / kSieveThreads;
   unsigned key[PER];
